@@ -1,0 +1,171 @@
+/* b200_sph.h -- C-ABI of the B200-native SPH hot path (libb200sph.so).
+ *
+ * This is the drop-in boundary for the reference's USER-SPH path.  A LAMMPS
+ * `/b200` Pair/Fix/Integrate shell binds exactly these
+ * entry points; nothing but plain pointers, sizes and ints crosses it.
+ * The only implementation is the sm_100a CUDA library: there is no CPU
+ * fallback.  All `file:line` citations are relative to /root/reference/.
+ *
+ * Conventions (src/GPU prior art, gpu_extra.h:26-64):
+ *   - every call returns 0 on success, <0 on error; b200_last_error() gives text
+ *   - per-type tables are 1-based, length ntypes+1        (src/pair.h cutsq etc.)
+ *   - per-type-pair tables are row-major (ntypes+1)x(ntypes+1), 1-based
+ *   - per-atom vectors are LAMMPS' contiguous AoS blocks: x = &atom->x[0][0]
+ *     is [n][3] doubles (src/memory.h:124-137); the library never keeps host
+ *     pointers after a call returns
+ *   - all physics is fp64, indices int32
+ */
+#ifndef B200_SPH_H
+#define B200_SPH_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_sph b200_sph; /* one engine instance per MPI rank / GPU */
+
+/* ---- pair sub-styles (src/USER-SPH/pair_sph_*.h PairStyle() names) -------- */
+enum {
+  B200_PAIR_RHOSUM = 1,             /* sph/rhosum                    pair_sph_rhosum.cpp:66-204 */
+  B200_PAIR_RHOSUM_MULTIPHASE = 2,  /* sph/rhosum/multiphase         pair_sph_rhosum_multiphase.cpp:68-174 */
+  B200_PAIR_TAITWATER = 3,          /* sph/taitwater                 pair_sph_taitwater.cpp:53-200 */
+  B200_PAIR_TAITWATER_MORRIS = 4,   /* sph/taitwater/morris          pair_sph_taitwater_morris.cpp:52-200 */
+  B200_PAIR_TAITWATER_MULTIPHASE = 5,/* sph/taitwater/multiphase     pair_sph_taitwater_multiphase.cpp:55-186 */
+  B200_PAIR_COLORGRADIENT = 6,      /* sph/colorgradient             pair_sph_colorgradient.cpp:70-191 */
+  B200_PAIR_SURFACETENSION = 7,     /* sph/surfacetension            pair_sph_surfacetension.cpp:50-192 */
+  B200_PAIR_HEATCONDUCTION = 8,     /* sph/heatconduction            pair_sph_heatconduction.cpp:47-134 */
+  B200_PAIR_HEATCONDUCTION_MULTIPHASE = 9,  /* sph/heatconduction/multiphase  ..._multiphase.cpp:49-129 */
+  B200_PAIR_HEATCONDUCTION_PHASECHANGE = 10 /* sph/heatconduction/phasechange ..._phasechange.cpp:52-141 */
+};
+
+/* One sub-style of `pair_style hybrid/overlay` (or the single pair style),
+ * described by the tables the reference objects hold after Pair::init()
+ * (src/pair.cpp:174-235, src/pair_hybrid.cpp:407-543).  Unused pointers NULL.
+ *   mapped[i][j] = 1 iff this sub-style computes type pair (i,j)
+ *                  (= !ijskip of its neighbor request, pair_hybrid.cpp:452-471)
+ *   cut, cutsq   = PairSPH*::cut / Pair::cutsq of the sub-style
+ * per-type:  rho0, B, soundspeed (taitwater*), gamma, rbackground (multiphase)
+ * per-pair:  viscosity (taitwater*), alpha (colorgradient alpha / heat D),
+ *            tc + fixflag (heatconduction/phasechange :124-129)               */
+typedef struct {
+  int style;                 /* B200_PAIR_* */
+  int nstep;                 /* rhosum*, colorgradient: settings() arg; else 0 */
+  const int    *mapped;
+  const double *cut;
+  const double *cutsq;
+  const double *rho0;
+  const double *B;
+  const double *soundspeed;
+  const double *gamma;
+  const double *rbackground;
+  const double *viscosity;
+  const double *alpha;
+  const double *tc;
+  const int    *fixflag;
+} b200_pair_desc;
+
+/* fix phase_change arguments, fix_phase_change.cpp:57-79 (constructor order) */
+typedef struct {
+  int    groupbit;
+  double Tc, Tt, Hwv, dr, to_mass, cutoff;
+  int    from_type, to_type, nfreq, seed;
+  int    energy_chance_flag;     /* 1: "ENERGY rate" form                     */
+  double change_chance;          /* prob form                                 */
+  double phase_change_rate;      /* ENERGY form                               */
+  int    maxattempt;             /* "attempt N", default 10 (:364)            */
+  long long first_step;          /* next_reneighbor at creation = ntimestep+1 */
+} b200_phase_change_desc;
+
+/* per-atom field bundle, LAMMPS local order (atom->x, v, vest, ... src/atom.h:76-126).
+ * Any pointer may be NULL (field skipped).  Arrays hold n atoms.               */
+typedef struct {
+  double *x, *v, *vest, *f;        /* [n][3] */
+  double *rho, *drho, *e, *de, *cv, *rmass;
+  double *colorgradient;           /* [n][3] */
+  int    *type, *mask, *tag;
+} b200_atoms;
+
+/* ---- life cycle ---------------------------------------------------------- */
+int  b200_create(b200_sph **h, int device);
+int  b200_destroy(b200_sph *h);
+const char *b200_last_error(void);
+const char *b200_version(void);
+
+/* ---- problem definition (host state LAMMPS already parsed) ---------------- */
+/* Domain: dimension, box, periodicity  (src/domain.h boxlo/boxhi/periodicity).
+ * sublo/subhi = this rank's sub-domain (== box on one GPU), src/domain.h sublo. */
+int  b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[3],
+                 const int periodicity[3], const double sublo[3], const double subhi[3]);
+/* atom_style meso (multiphase=0, atom_vec_meso.cpp) or meso/multiphase (=1);
+ * mass = atom->mass [ntypes+1] (may be NULL for multiphase: rmass is used).    */
+int  b200_atom_style(b200_sph *h, int multiphase, int ntypes, const double *mass);
+/* neighbor <skin> bin + neigh_modify every/delay/check (neighbor.cpp:1332-1347);
+ * cutneighsq = Neighbor::cutneighsq [(ntypes+1)^2] verbatim (neighbor.cpp:259-268),
+ * cutneighmax likewise; cutghost = comm->cutghost (comm_brick.cpp:166-172).    */
+int  b200_neighbor(b200_sph *h, double skin, int every, int delay, int check,
+                   const double *cutneighsq, double cutneighmax, double cutghost);
+int  b200_timestep(b200_sph *h, double dt, double ftm2v, long long ntimestep);
+/* comm_modify vel yes: ghosts carry v (needed by fix phase_change)             */
+int  b200_comm_modify(b200_sph *h, int ghost_velocity);
+
+/* Pair sub-styles in deck order (PairHybrid::compute order, pair_hybrid.cpp:101-109). */
+int  b200_pair_clear(b200_sph *h);
+int  b200_pair_add(b200_sph *h, const b200_pair_desc *d);      /* returns slot >= 0 */
+
+/* Fixes, in deck order (Modify hook order, src/modify.cpp).                    */
+int  b200_fix_clear(b200_sph *h);
+int  b200_fix_meso(b200_sph *h, int groupbit);                  /* fix_meso.cpp:91-180 */
+int  b200_fix_meso_stationary(b200_sph *h, int groupbit);       /* fix_meso_stationary.cpp:71-112 */
+int  b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc); /* fix_gravity.cpp:244-295 */
+int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix_phase_change.cpp:167-352 */
+
+/* ---- per-atom data -------------------------------------------------------- */
+/* Upload nlocal owned atoms (LAMMPS local order).  x,v,rho,e,type,mask,tag are
+ * required; vest defaults to v, cv to 0, rmass to mass[type], cg to 0.         */
+int  b200_set_atoms(b200_sph *h, int nlocal, const b200_atoms *a);
+int  b200_get_natoms(b200_sph *h, int *nlocal, int *nghost);
+/* Download owned atoms back in LAMMPS local order (non-NULL fields only).
+ * Atoms created by fix phase_change are appended in creation order.            */
+int  b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* Verlet::setup (verlet.cpp:88-142): pbc, ghosts, neighbor build, forces.      */
+int  b200_setup(b200_sph *h);
+/* Verlet::run(n) (verlet.cpp:207-309), device resident, no host copies.        */
+int  b200_run(b200_sph *h, int nsteps);
+
+/* Stage-level entry points for Pair::compute / Fix hooks driven by LAMMPS' own
+ * Verlet loop, and for the parity tests.                                      */
+int  b200_initial_integrate(b200_sph *h);
+int  b200_final_integrate(b200_sph *h);
+int  b200_neigh_decide(b200_sph *h, int *rebuild);   /* Neighbor::decide                */
+int  b200_forward_comm(b200_sph *h);                 /* CommBrick::forward_comm :444    */
+int  b200_reneighbor(b200_sph *h);                   /* pre_exchange..neighbor->build   */
+int  b200_force_clear(b200_sph *h);                  /* Verlet::force_clear :325        */
+int  b200_pair_compute(b200_sph *h, int slot);       /* one PairSPH*::compute           */
+int  b200_pair_compute_all(b200_sph *h);             /* PairHybrid::compute (fused)     */
+int  b200_reverse_comm(b200_sph *h);                 /* CommBrick::reverse_comm :513    */
+int  b200_post_force(b200_sph *h);
+
+/* Full neighbor list of the last build (Neighbor::full_bin, neigh_full.cpp:241-340)
+ * for the bit-exact check: per owned atom (LAMMPS local order) numneigh[i], then
+ * entries as (tag of j, image code of j) with image = (px+1) + 3*(py+1) + 9*(pz+1),
+ * 13 = owned atom; rows sorted by (tag,image).  Call with jtag==NULL to get counts. */
+int  b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh,
+                            long long nentries, int *jtag, int *jimage);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* counters[0]=kernel launches, [1]=neighbor builds, [2]=steps, [3]=max neighbors,
+ * [4]=nghost, [5]=row stride, [6]=phase-change insertions, [7]=dangerous builds */
+int  b200_get_counters(b200_sph *h, long long counters[8]);
+/* Per-stage CUDA-event timing (ms) accumulated since the last reset; names via
+ * b200_timer_name(i).  Enabled with b200_set_timing(h,1) (adds event records). */
+int  b200_set_timing(b200_sph *h, int on);
+int  b200_get_timers(b200_sph *h, int n, double *ms, long long *calls);
+const char *b200_timer_name(int i);
+int  b200_sync(b200_sph *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SPH_H */

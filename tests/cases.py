@@ -1,0 +1,306 @@
+"""Parity cases: small decks that exercise every style on the hot path.
+
+Each case has
+  create : LAMMPS commands (our own text, in the reference's deck language) that
+           build the box and the atoms -- executed ONLY by the real reference when
+           the golden fixtures are generated (tests/golden/make_golden.py);
+  cmds   : the hot-path commands as tuples, applied verbatim both to the reference
+           (rendered to text by `lammps_text`) and to the host mirror `Deck`;
+  nsteps : length of the trajectory check.
+The reference-generated initial state travels in tests/golden/<name>.npz.
+"""
+import importlib
+import math
+
+pkg = importlib.import_module("lammps-sph-multiphase_b200")
+Deck = pkg.Deck
+
+
+def _f(v):
+    return repr(float(v)) if isinstance(v, float) else str(v)
+
+
+class Case:
+    def __init__(self, name, dim, boundary, box, atom_style, ntypes, create, cmds, nsteps, units="si", groups=(),
+                 tol_traj=1e-9):
+        self.name, self.dim, self.boundary, self.box = name, dim, boundary, box
+        self.atom_style, self.ntypes, self.create, self.cmds, self.nsteps = atom_style, ntypes, create, cmds, nsteps
+        self.units, self.groups, self.tol_traj = units, groups, tol_traj
+
+    @property
+    def multiphase(self):
+        return self.atom_style == "meso/multiphase"
+
+    def header_text(self):
+        (x0, y0, z0), (x1, y1, z1) = self.box
+        return "\n".join([
+            "units %s" % self.units, "dimension %d" % self.dim, "boundary %s" % self.boundary, "newton on",
+            "atom_style %s" % self.atom_style, "atom_modify map array sort 0 0",
+            "region box block %s %s %s %s %s %s units box" % tuple(_f(float(v)) for v in (x0, x1, y0, y1, z0, z1)),
+            "create_box %d box" % self.ntypes])
+
+    def lammps_text(self):
+        out = []
+        for g, t in self.groups:
+            out.append("group %s type %d" % (g, t))
+        nfix = 0
+        for c in self.cmds:
+            k, a = c[0], c[1:]
+            if k == "pair_style":
+                out.append("pair_style " + " ".join(str(v) for v in a))
+            elif k == "pair_coeff":
+                out.append("pair_coeff " + " ".join(_f(v) for v in a))
+            elif k == "mass":
+                out.append("mass %s %s" % (a[0], _f(a[1])))
+            elif k == "neighbor":
+                out.append("neighbor %s bin" % _f(a[0]))
+            elif k == "neigh_modify":
+                out.append("neigh_modify " + " ".join("%s %s" % (kk, vv) for kk, vv in a[0].items()))
+            elif k == "comm_modify":
+                out.append("comm_modify vel %s" % a[0])
+            elif k == "timestep":
+                out.append("timestep %s" % _f(a[0]))
+            elif k == "fix":
+                nfix += 1
+                out.append("fix f%d %s %s %s" % (nfix, a[0], a[1], " ".join(_f(v) for v in a[2:])))
+            else:
+                raise ValueError(k)
+        return "\n".join(out)
+
+    def deck(self):
+        d = Deck(dimension=self.dim, boundary=self.boundary, box=self.box, atom_style=self.atom_style,
+                 ntypes=self.ntypes, units=self.units)
+        for g, t in self.groups:
+            d.group(g)
+        nfix = 0
+        for c in self.cmds:
+            k, a = c[0], c[1:]
+            if k == "pair_style":
+                d.pair_style(*a)
+            elif k == "pair_coeff":
+                d.pair_coeff(*a)
+            elif k == "mass":
+                d.mass(*a)
+            elif k == "neighbor":
+                d.neighbor(a[0])
+            elif k == "neigh_modify":
+                d.neigh_modify(**a[0])
+            elif k == "comm_modify":
+                d.comm_modify(a[0])
+            elif k == "timestep":
+                d.timestep(a[0])
+            elif k == "fix":
+                nfix += 1
+                d.fix("f%d" % nfix, a[0], a[1], *a[2:])
+        return d.init()
+
+
+def _single(atoms):
+    return "\n".join("create_atoms %d single %s %s %s units box" % (t, _f(float(x)), _f(float(y)), _f(float(z)))
+                     for t, (x, y, z) in atoms)
+
+
+KATBOX = ((0, 0, -10), (10, 10, 10))
+KAT3 = [(1, (5, 5, 5)), (2, (5.5, 5, 5)), (2, (5, 5, 4.8))]
+_kat_tail = [("neighbor", 0.0), ("comm_modify", "yes"), ("timestep", 0.0), ("fix", "all", "meso")]
+
+CASES = {}
+
+
+def _add(c):
+    CASES[c.name] = c
+
+
+# ---- the six known-answer decks of examples/USER/sph/multiphase_two_atoms ----
+_add(Case("kat_rhosum_multiphase", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _single(KAT3) + "\nset type 1 mass 2\nset type 2 mass 1\nset type 1 meso_rho 1\nset type 2 meso_rho 1",
+          [("pair_style", "sph/rhosum/multiphase", 1), ("pair_coeff", "* *", 1.0)] + _kat_tail, 1))
+_add(Case("kat_taitwater_multiphase", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _single(KAT3) + "\nset type 1 mass 2\nset type 2 mass 1\nset type 1 meso_rho 1\nset type 2 meso_rho 1",
+          [("pair_style", "sph/taitwater/multiphase"), ("pair_coeff", "* *", 1.0, 1.0, 0.0, 1.0, 1.0, 0.5)] + _kat_tail, 1))
+_add(Case("kat_colorgradient", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _single(KAT3) + "\nset type 1 mass 2\nset type 2 mass 1\nset type 1 meso_rho 1\nset type 2 meso_rho 1",
+          [("pair_style", "sph/colorgradient", 1), ("pair_coeff", "1 1", 1.0, 0.0), ("pair_coeff", "2 2", 1.0, 0.0),
+           ("pair_coeff", "1 2", 1.0, 1.0)] + _kat_tail, 1))
+_add(Case("kat_surfacetension", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _single([(1, (4.6, 5.3, 5)), (2, (5.5, 5, 5.2)), (2, (5.0, 5.0, 5.0))])
+          + "\nset type 1 mass 1\nset type 2 mass 1\nset type 1 meso_rho 1\nset type 2 meso_rho 1",
+          [("pair_style", "hybrid/overlay", "sph/colorgradient 1", "sph/surfacetension"),
+           ("pair_coeff", "1 1", "sph/colorgradient", 1.0, 0.0), ("pair_coeff", "2 2", "sph/colorgradient", 1.0, 0.0),
+           ("pair_coeff", "1 2", "sph/colorgradient", 1.0, 1.0), ("pair_coeff", "1 1", "sph/surfacetension", 1.0),
+           ("pair_coeff", "2 2", "sph/surfacetension", 1.0), ("pair_coeff", "1 2", "sph/surfacetension", 1.0)] + _kat_tail, 1))
+_kat_heat_atoms = (_single([(1, (5, 5, 5)), (2, (5.6, 5, 5))]) + "\nset type 1 meso_rho 1\nset type 2 meso_rho 1\n"
+                   "set type 1 meso_cv 3.0\nset type 2 meso_cv 1.0\n")
+_add(Case("kat_heatconduction_phasechange", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _kat_heat_atoms + "set type 1 mass 1\nset type 2 mass 2\nset type 1 meso_e 1.0\nset type 2 meso_e 2.0",
+          [("pair_style", "sph/heatconduction/phasechange"), ("pair_coeff", "1 1", 1.0, 1.0), ("pair_coeff", "1 2", 1.0, 1.0),
+           ("pair_coeff", "2 2", 1.0, 1.0)] + _kat_tail, 1))
+_add(Case("kat_phase_change", 3, "p p p", KATBOX, "meso/multiphase", 2,
+          _kat_heat_atoms + "set type 1 mass 10\nset type 2 mass 2\nset type 1 meso_e 10.0\nset type 2 meso_e 2.0",
+          [("pair_style", "sph/colorgradient", 1), ("pair_coeff", "1 1", 1.0, 0.0), ("pair_coeff", "2 2", 1.0, 0.0),
+           ("pair_coeff", "1 2", 1.0, 1.0), ("neighbor", 0.0), ("comm_modify", "yes"), ("timestep", 0.0),
+           ("fix", "all", "phase_change", 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1, 2, 1, 123456, 1.0, "region", "box", "units", "box"),
+           ("fix", "all", "meso")], 1))
+
+# ---- C1: the shipped 2-D heat-conduction deck (heatconduction/sph_heat_conduction_2d.lmp) ----
+_heat2d_create = """lattice sq 0.01
+create_atoms 1 box
+region left block EDGE 0.499 EDGE EDGE EDGE EDGE units box
+region right block 0.5 EDGE EDGE EDGE EDGE EDGE units box
+set region left meso_e 1.0
+set region right meso_e 2.0
+set group all meso_rho 0.1"""
+_add(Case("heat2d", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso", 1, _heat2d_create,
+          [("mass", "1", 1.0e-5), ("pair_style", "sph/heatconduction"), ("pair_coeff", "1 1", 1.0e-4, 2.0e-2),
+           ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso/stationary")], 160))
+# C1 variant with density summation + fix meso (covers rhosum + fix meso on the C1 geometry)
+_add(Case("heat2d_rhosum", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso", 1, _heat2d_create,
+          [("mass", "1", 1.0e-5), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/heatconduction"),
+           ("pair_coeff", "1 1", "sph/rhosum", 2.0e-2), ("pair_coeff", "1 1", "sph/heatconduction", 1.0e-4, 2.0e-2),
+           ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso")], 40))
+_add(Case("heat3d", 3, "f p p", ((0, 0, 0), (0.4, 0.08, 0.08)), "meso", 1,
+          """lattice sc 0.01
+create_atoms 1 box
+region left block EDGE 0.199 EDGE EDGE EDGE EDGE units box
+region right block 0.2 EDGE EDGE EDGE EDGE EDGE units box
+set region left meso_e 1.0
+set region right meso_e 2.0
+set group all meso_rho 10.0""",
+          [("mass", "1", 1.0e-5), ("pair_style", "sph/heatconduction"), ("pair_coeff", "1 1", 1.0e-4, 2.0e-2),
+           ("timestep", 0.025), ("neighbor", 0.002), ("neigh_modify", dict(every=20, delay=0, check="no")),
+           ("fix", "all", "meso/stationary")], 30))
+
+
+# ---- C2 scaled down: dam break, sph/rhosum (1 1 only) + sph/taitwater, walls, gravity ----
+def _dam(name, dim, nsteps, morris=False):
+    dx, h, c = 0.01, 0.03, 30.0
+    if dim == 2:
+        box = ((0, 0, -0.001), (0.60, 0.44, 0.001)); lat = "sq"
+        water = "region water block 0.03 0.23 0.03 0.33 EDGE EDGE units box"
+        inner = "region inner block 0.03 0.57 0.03 EDGE EDGE EDGE units box"
+        m = 1000.0 * dx * dx; grav = ("gravity", -9.81, "vector", 0, 1, 0); bnd = "f f p"
+    else:
+        box = ((0, 0, 0), (0.22, 0.16, 0.16)); lat = "sc"
+        water = "region water block 0.03 0.10 0.03 0.10 0.03 0.10 units box"
+        inner = "region inner block 0.03 0.19 0.03 0.13 0.03 EDGE units box"
+        m = 1000.0 * dx ** 3; grav = ("gravity", -9.81, "vector", 0, 0, 1); bnd = "f f f"
+    # walls = lattice sites of the box outside the open-top inner region
+    create = """lattice %s %s origin 0.5 0.5 %s
+%s
+%s
+create_atoms 2 box
+delete_atoms region inner
+create_atoms 1 region water
+set group all meso_rho 1000.0
+set group all meso_e 0.0""" % (lat, _f(dx), "0.5" if dim == 3 else "0", water, inner)
+    tait = "sph/taitwater/morris" if morris else "sph/taitwater"
+    nu = 1.0e-3 if morris else 1.0
+    cmds = [("mass", "*", m), ("pair_style", "hybrid/overlay", "sph/rhosum 1", tait),
+            ("pair_coeff", "* *", tait, 1000.0, c, nu, h), ("pair_coeff", "1 1", "sph/rhosum", h),
+            ("fix", "water", *grav), ("fix", "water", "meso"), ("fix", "bc", "meso/stationary"),
+            ("neigh_modify", dict(every=5, delay=0, check="no")), ("neighbor", 0.3 * h), ("timestep", 0.1 * h / c)]
+    return Case(name, dim, bnd, box, "meso", 2, create, cmds, nsteps, groups=(("bc", 2), ("water", 1)))
+
+
+_add(_dam("dam2d", 2, 60))
+_add(_dam("dam3d", 3, 25))
+_add(_dam("dam2d_morris", 2, 40, morris=True))
+
+
+# ---- C3 scaled down: periodic two-phase box (square_to_sphere/droplet.lmp + cube.lmp) ----
+def _droplet(name, dim, nx, nsteps, heat=None, skin=0.0, every=1, check="yes"):
+    L = 1.0; dx = L / nx; h = 3.0 * dx; rho = 1.0; c = 10.0; eta = 5e-2; alpha = 0.2; a = 0.2
+    m = dx ** dim * rho
+    if dim == 2:
+        box = ((0, 0, -1e-3), (L, L, 1e-3)); lat = "sq"
+        rsq = "region rsq block %s %s %s %s EDGE EDGE units box" % tuple(_f(v) for v in (0.5 - a, 0.5 + a, 0.5 - a, 0.5 + a))
+    else:
+        box = ((0, 0, 0), (L, L, L)); lat = "sc"
+        rsq = "region rsq block %s %s %s %s %s %s units box" % tuple(_f(v) for v in (0.5 - a, 0.5 + a) * 3)
+    create = """lattice %s %s
+create_atoms 1 region box
+%s
+set region rsq type 2
+set group all meso_rho %s
+set group all mass %s
+set type 1 meso_e 1.0
+set type 2 meso_e 1.5
+set type 1 meso_cv 1.0
+set type 2 meso_cv 2.0
+displace_atoms all random %s %s %s 4711 units box""" % (lat, _f(dx), rsq, _f(rho), _f(m), _f(0.05 * dx), _f(0.05 * dx),
+                                                         _f(0.05 * dx) if dim == 3 else "0.0")
+    subs = ["sph/rhosum/multiphase 1", "sph/colorgradient 1", "sph/taitwater/multiphase", "sph/surfacetension"]
+    if heat:
+        subs.append(heat)
+    cmds = [("pair_style", "hybrid/overlay", *subs), ("pair_coeff", "* *", "sph/rhosum/multiphase", h),
+            ("pair_coeff", "2 2", "sph/colorgradient", h, 0.0), ("pair_coeff", "1 2", "sph/colorgradient", h, alpha),
+            ("pair_coeff", "1 1", "sph/colorgradient", h, 0.0),
+            ("pair_coeff", "1 2", "sph/taitwater/multiphase", rho, c, eta, 7.0, h, 0.0),
+            ("pair_coeff", "1 1", "sph/taitwater/multiphase", rho, c, eta, 7.0, h, 0.0),
+            ("pair_coeff", "2 2", "sph/taitwater/multiphase", rho, c, eta, 7.0, h, 0.0),
+            ("pair_coeff", "* *", "sph/surfacetension", h)]
+    if heat == "sph/heatconduction/multiphase":
+        cmds += [("pair_coeff", "* *", heat, 0.3, h)]
+    elif heat == "sph/heatconduction/phasechange":
+        cmds += [("pair_coeff", "1 1", heat, 0.2, h), ("pair_coeff", "1 2", heat, 0.3, h, "NULL", 1.2),
+                 ("pair_coeff", "2 2", heat, 0.6, h)]
+    dt = min(0.25 * dx / c, 0.125 * dx * dx / eta * rho)
+    cmds += [("neighbor", skin), ("neigh_modify", dict(delay=0, every=every, check=check)), ("comm_modify", "yes"),
+             ("timestep", dt), ("fix", "all", "meso")]
+    return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps)
+
+
+_add(_droplet("droplet2d", 2, 30, 40))
+_add(_droplet("droplet3d", 3, 12, 20))
+_add(_droplet("droplet3d_heat", 3, 12, 15, heat="sph/heatconduction/multiphase"))
+_add(_droplet("droplet2d_pcheat_skin", 2, 30, 40, heat="sph/heatconduction/phasechange", skin=0.002, every=2))
+
+
+# ---- C4 scaled down: random liquid box with a vapour seed, heat conduction + fix phase_change ----
+def _bubble(name, dim, nx, nsteps):
+    L = 1.0; dx = L / nx; h = 3.0 * dx
+    rho_l, rho_v = 1.0, 0.1
+    c_v, c_l = 200.0 / math.sqrt(rho_v), 200.0 / math.sqrt(rho_l)
+    eta_l, eta_v, alpha = 1.0, 0.69, 500.0
+    D_l, D_v, cv_l, cv_v = 0.2, 0.6, 0.04, 0.06
+    Hwv, Tc, Tinf = 8.0, 0.0, 1.0; Tt = Tc + 0.1
+    m_v, m_l = dx ** dim * rho_v, dx ** dim * rho_l
+    eta_ld = 2 * eta_l * eta_v / (eta_v + eta_l); D_ld = 2 * D_l * D_v / (D_v + D_l)
+    box = ((0, 0, 0), (L, L, L if dim == 3 else dx))
+    zc = 0.5 if dim == 3 else 0.0
+    create = """lattice %s %s origin 0.5 0.5 %s
+create_atoms 1 region box
+displace_atoms all random %s %s %s 12345 units box
+region rsq sphere 0.5 0.5 %s 0.22 units box
+set region rsq type 2
+set type 2 meso_cv %s
+set type 1 meso_cv %s
+set type 2 meso_e %s
+set type 1 meso_e %s
+set type 2 mass %s
+set type 1 mass %s
+set type 2 meso_rho %s
+set type 1 meso_rho %s""" % ("sc" if dim == 3 else "sq", _f(dx), "0.5" if dim == 3 else "0", _f(0.2 * dx), _f(0.2 * dx),
+                            _f(0.2 * dx) if dim == 3 else "0.0", _f(zc), _f(cv_v), _f(cv_l), _f(cv_v * 0.6), _f(cv_l * Tinf),
+                            _f(m_v), _f(m_l), _f(rho_v), _f(rho_l))
+    dts = [0.125 * dx * dx / eta_v * rho_v, 0.125 * dx * dx / eta_l * rho_l, 0.25 * math.sqrt(rho_v * dx ** 3 / (6.0 * alpha)),
+           0.25 * dx / c_v, 0.25 * dx / c_l, 0.1 * 1.44 * rho_l * cv_l * dx * dx / D_l, 0.1 * 1.44 * rho_v * cv_v * dx * dx / D_v]
+    hp = "sph/heatconduction/phasechange"
+    cmds = [("pair_style", "hybrid/overlay", "sph/rhosum/multiphase 1", "sph/colorgradient 1", "sph/taitwater/multiphase",
+             "sph/surfacetension", hp),
+            ("pair_coeff", "* *", "sph/rhosum/multiphase", h),
+            ("pair_coeff", "2 2", "sph/colorgradient", h, 0.0), ("pair_coeff", "1 2", "sph/colorgradient", h, alpha),
+            ("pair_coeff", "1 1", "sph/colorgradient", h, 0.0),
+            ("pair_coeff", "1 2", "sph/taitwater/multiphase", rho_l, c_l, eta_ld, 1.0, h, 0.0),
+            ("pair_coeff", "1 1", "sph/taitwater/multiphase", rho_l, c_l, eta_l, 1.0, h, 0.0),
+            ("pair_coeff", "2 2", "sph/taitwater/multiphase", rho_v, c_v, eta_v, 1.0, h, 0.0),
+            ("pair_coeff", "* *", "sph/surfacetension", h),
+            ("pair_coeff", "1 1", hp, D_l, h), ("pair_coeff", "1 2", hp, D_ld, h, "NULL", Tc), ("pair_coeff", "2 2", hp, D_v, h),
+            ("neighbor", 0.0), ("neigh_modify", dict(delay=0, every=1)), ("comm_modify", "yes"), ("timestep", min(dts)),
+            ("fix", "all", "meso"),
+            ("fix", "bubble", "phase_change", Tc, Tt, Hwv, 0.5 * dx, m_v, h, 1, 2, 1, 123456, 0.05, "region", "box", "units", "box")]
+    return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps, groups=(("bubble", 2),), tol_traj=1e-8)
+
+
+_add(_bubble("bubble2d", 2, 32, 30))
+_add(_bubble("bubble3d", 3, 12, 12))
