@@ -1,0 +1,108 @@
+// b200_fix.cuh -- per-atom stages: fix meso / meso/stationary / gravity, reverse
+// accumulation of ghost contributions, and the rebuild trigger.
+#pragma once
+#include "b200_common.cuh"
+
+struct StepArrays {
+  double4 *xt, *vr, *vm, *fd;
+  double *e, *de;
+  const int *mask;
+};
+
+// FixMeso::setup_pre_force (fix_meso.cpp:68-85): vest = v for atoms of the fix group
+__global__ void k_setup_pre_force(int nlocal, FixList fl, StepArrays a)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  int m = a.mask[i];
+  for (int k = 0; k < fl.n; k++)
+    if (fl.kind[k] == 1 && (m & fl.bit[k])) {
+      double4 v = a.vm[i], vr = a.vr[i];
+      vr.x = v.x; vr.y = v.y; vr.z = v.z;
+      a.vr[i] = vr;
+    }
+}
+
+// modify->initial_integrate: FixMeso::initial_integrate (fix_meso.cpp:91-140) and
+// FixMesoStationary::initial_integrate (fix_meso_stationary.cpp:71-92), fixes in deck order;
+// plus Neighbor::check_distance's per-atom test (neighbor.cpp:1396-1404) on the new positions.
+__global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double dtv, double dtf, int check,
+                                    const double *xhold, double triggersq, int *flag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  int m = a.mask[i];
+  double4 x = a.xt[i], vr = a.vr[i], v = a.vm[i], f = a.fd[i];
+  double e = a.e[i], de = a.de[i];
+  bool moved = false, touched = false;
+  for (int k = 0; k < fl.n; k++) {
+    if (fl.kind[k] > 2 || !(m & fl.bit[k])) continue;
+    touched = true;
+    e += dtf * de;            // half-step update of particle internal energy
+    vr.w += dtf * f.w;        // ... and density
+    if (fl.kind[k] == 1) {
+      double dtfm = dtf / v.w;
+      vr.x = v.x + 2.0 * dtfm * f.x; vr.y = v.y + 2.0 * dtfm * f.y; vr.z = v.z + 2.0 * dtfm * f.z;
+      v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
+      x.x += dtv * v.x; x.y += dtv * v.y; x.z += dtv * v.z;
+      moved = true;
+    }
+  }
+  if (touched) { a.e[i] = e; a.vr[i] = vr; }
+  if (moved) { a.vm[i] = v; a.xt[i] = x; }
+  if (check) {
+    double dx = x.x - xhold[3 * i], dy = x.y - xhold[3 * i + 1], dz = x.z - xhold[3 * i + 2];
+    if (dx * dx + dy * dy + dz * dz > triggersq) *flag = 1;
+  }
+}
+
+// comm->reverse_comm (comm_brick.cpp:513-560: f, drho, de of ghosts added to their owners), then
+// modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
+// (fix_meso.cpp:144-180, fix_meso_stationary.cpp:96-112).  The three stages can be run fused (one
+// pass over the owned atoms) or one by one for the stage-level ABI.
+__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_reverse, int do_post, int do_final,
+                             const int *goff, const int *gslot)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 f = a.fd[i];
+  double de = a.de[i];
+  bool fdirty = false;
+  if (do_reverse) {
+    for (int q = goff[i]; q < goff[i + 1]; q++) {
+      int g = gslot[q];
+      double4 fg = a.fd[g];
+      f.x += fg.x; f.y += fg.y; f.z += fg.z; f.w += fg.w;
+      de += a.de[g];
+      fdirty = true;
+    }
+    if (fdirty) a.de[i] = de;
+  }
+  int m = a.mask[i];
+  double4 v = a.vm[i];
+  if (do_post)
+    for (int k = 0; k < fl.n; k++)
+      if (fl.kind[k] == 3 && (m & fl.bit[k])) {
+        f.x += v.w * fl.acc[k][0]; f.y += v.w * fl.acc[k][1]; f.z += v.w * fl.acc[k][2];
+        fdirty = true;
+      }
+  if (fdirty) a.fd[i] = f;
+  if (do_final) {
+    double4 vr = a.vr[i];
+    double e = a.e[i];
+    bool vd = false, ed = false;
+    for (int k = 0; k < fl.n; k++) {
+      if (fl.kind[k] > 2 || !(m & fl.bit[k])) continue;
+      if (fl.kind[k] == 1) {
+        double dtfm = dtf / v.w;
+        v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
+        vd = true;
+      }
+      e += dtf * de;
+      vr.w += dtf * f.w;
+      ed = true;
+    }
+    if (vd) a.vm[i] = v;
+    if (ed) { a.e[i] = e; a.vr[i] = vr; }
+  }
+}

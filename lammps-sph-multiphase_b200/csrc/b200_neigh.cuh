@@ -1,0 +1,401 @@
+// b200_neigh.cuh -- binning, ghost (halo) construction and the neighbor build.
+//
+// Replaces Neighbor::bin_atoms / full_bin (src/neighbor.cpp:1911-1990,
+// src/neigh_full.cpp:241-340), half_from_full_newton (src/neigh_derive.cpp:83-145)
+// and CommBrick::borders / forward_comm for periodic self-images
+// (src/comm_brick.cpp:444-506,696-864).  All paths relative to /root/reference/.
+//
+// Layout: owned particles [0,nlocal) sorted by engine cell (cell edge >= cutneighmax,
+// 3x3x3 stencil), ghosts [nlocal,nall) sorted by cell as well; inside a cell the
+// order is ascending tag (ghosts: tag*32+image), so every summation order in the
+// engine is a pure function of the particle set -- no atomics decide an order.
+#pragma once
+#include "b200_common.cuh"
+
+// ---------------------------------------------------------------- helpers ---
+__device__ __forceinline__ double rsq_nofma(double dx, double dy, double dz)
+{ // delx*delx + dely*dely + delz*delz exactly as the reference's x86-64 build rounds it
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Neighbor::coord2bin, one dimension (neighbor.cpp:1961-1990)
+__device__ __forceinline__ int refbin1(double x, double lo, double hi, double inv, int nbin)
+{
+  if (x >= hi) return __double2int_rz(__dmul_rn(__dsub_rn(x, hi), inv)) + nbin;
+  if (x >= lo) return imin(__double2int_rz(__dmul_rn(__dsub_rn(x, lo), inv)), nbin - 1);
+  return __double2int_rz(__dmul_rn(__dsub_rn(x, lo), inv)) - 1;
+}
+__device__ __forceinline__ unsigned long long make_tw(const Geom &g, int type, double x, double y, double z)
+{
+  return pack_tw(type, refbin1(x, g.boxlo[0], g.boxhi[0], g.bininv[0], g.nbin[0]),
+                 refbin1(y, g.boxlo[1], g.boxhi[1], g.bininv[1], g.nbin[1]),
+                 refbin1(z, g.boxlo[2], g.boxhi[2], g.bininv[2], g.nbin[2]));
+}
+__device__ __forceinline__ int cell1(double x, double lo, double inv, int n)
+{
+  int c = __double2int_rd((x - lo) * inv);
+  return imin(imax(c, 0), n - 1);
+}
+__device__ __forceinline__ int cell_of(const Geom &g, double x, double y, double z)
+{
+  int cx = cell1(x, g.clo[0], g.cinv[0], g.nc[0]), cy = cell1(y, g.clo[1], g.cinv[1], g.nc[1]),
+      cz = cell1(z, g.clo[2], g.cinv[2], g.nc[2]);
+  return (cz * g.nc[1] + cy) * g.nc[0] + cx;
+}
+
+// ------------------------------------------------------------------ scan ----
+// exclusive scan of int arrays (counts -> offsets); data[n] receives the total.
+#define SCAN_T 256
+#define SCAN_E 4
+__global__ void k_scan_block(int *data, int n, int *sums)
+{
+  __shared__ int sh[SCAN_T];
+  int base = blockIdx.x * SCAN_T * SCAN_E + threadIdx.x * SCAN_E;
+  int v[SCAN_E], t = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) { v[k] = (base + k < n) ? data[base + k] : 0; t += v[k]; }
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 1; o < SCAN_T; o <<= 1) {
+    int a = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += a;
+    __syncthreads();
+  }
+  int excl = sh[threadIdx.x] - t;
+  if (threadIdx.x == SCAN_T - 1) sums[blockIdx.x] = sh[threadIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) { if (base + k < n) data[base + k] = excl; excl += v[k]; }
+}
+__global__ void k_scan_add(int *data, int n, const int *sums)
+{
+  int i = blockIdx.x * SCAN_T * SCAN_E + threadIdx.x;
+  int add = sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++, i += SCAN_T) if (i < n) data[i] += add;
+}
+
+// ------------------------------------------------------- owned: pbc + cells --
+// Domain::pbc (src/domain.cpp:476-560) then engine-cell id + histogram
+__global__ void k_owned_cells(Geom g, int nlocal, double4 *xt, int *cellid, int *cellcnt, int do_pbc)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  if (do_pbc) {
+    double c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      if (g.periodic[d]) {
+        if (c[d] < g.boxlo[d]) c[d] = __dadd_rn(c[d], g.prd[d]);
+        if (c[d] >= g.boxhi[d]) { c[d] = __dsub_rn(c[d], g.prd[d]); c[d] = fmax(c[d], g.boxlo[d]); }
+      }
+    p.x = c[0]; p.y = c[1]; p.z = c[2];
+    xt[i] = p;
+  }
+  int c = cell_of(g, p.x, p.y, p.z);
+  cellid[i] = c;
+  atomicAdd(&cellcnt[c], 1);
+}
+
+// scatter element ids into their cell segment (arbitrary order inside a segment; fixed by k_sort_segments)
+__global__ void k_scatter(int n, const int *cellid, const int *cellstart, int *cellfill, int *perm)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cellid[i];
+  perm[cellstart[c] + atomicAdd(&cellfill[c], 1)] = i;
+}
+
+// rank-sort every cell segment by key (unique keys) -> deterministic in-cell order; one warp per cell
+__global__ void k_sort_segments(int ncells, const int *cellstart, const int *perm_in, int *perm_out,
+                                const unsigned long long *key)
+{
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= ncells) return;
+  int s = cellstart[w], n = cellstart[w + 1] - s;
+  for (int a = lane; a < n; a += 32) {
+    int ea = perm_in[s + a];
+    unsigned long long ka = key[ea];
+    int rank = 0;
+    for (int b = 0; b < n; b++) rank += key[perm_in[s + b]] < ka;
+    perm_out[s + rank] = ea;
+  }
+}
+
+// gather the owned particles into cell order; xt.w gets type + reference bin of the (wrapped) position
+struct OwnedArrays {
+  double4 *xt, *vr, *vm, *fd, *cgm;
+  double *e, *de, *cv;
+  int *tag, *mask, *orig;
+};
+__global__ void k_permute_owned(Geom g, int nlocal, const int *perm, OwnedArrays a, OwnedArrays b, int multiphase,
+                                unsigned long long *key)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nlocal) return;
+  int i = perm[s];
+  double4 p = a.xt[i];
+  int type = tw_type(__double_as_longlong(p.w));
+  p.w = __longlong_as_double((long long)make_tw(g, type, p.x, p.y, p.z));
+  b.xt[s] = p; b.vr[s] = a.vr[i]; b.vm[s] = a.vm[i]; b.fd[s] = a.fd[i];
+  if (multiphase) b.cgm[s] = a.cgm[i];
+  b.e[s] = a.e[i]; b.de[s] = a.de[i]; b.cv[s] = a.cv[i];
+  b.tag[s] = a.tag[i]; b.mask[s] = a.mask[i]; b.orig[s] = a.orig[i];
+}
+__global__ void k_owned_keys(int nlocal, const int *tag, unsigned long long *key)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nlocal) key[i] = (unsigned long long)(unsigned)tag[i];
+}
+// remember positions of the build for Neighbor::check_distance (neighbor.cpp:1428-1441)
+__global__ void k_store_xhold(int nlocal, const double4 *xt, double *xhold)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  xhold[3 * i] = p.x; xhold[3 * i + 1] = p.y; xhold[3 * i + 2] = p.z;
+}
+
+// ---------------------------------------------------------------- ghosts ----
+// Image set of an owned atom on a 1x1x1 processor grid = what CommBrick::borders
+// creates through its x, y, z swap chain (comm_brick.cpp:713-851): per periodic
+// dimension +prd if x <= sublo+cutghost (sent "left"), -prd if x >= subhi-cutghost.
+__device__ __forceinline__ void image_flags(const Geom &g, double x, double y, double z, int lo[3], int hi[3])
+{
+  double c[3] = {x, y, z};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    bool on = g.periodic[d] && !(g.dim == 2 && d == 2);
+    lo[d] = on && c[d] <= g.slab_lo_hi[d];
+    hi[d] = on && c[d] >= g.slab_hi_lo[d];
+  }
+}
+__global__ void k_ghost_count(Geom g, int nlocal, const double4 *xt, int *gcount)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  int lo[3], hi[3];
+  image_flags(g, p.x, p.y, p.z, lo, hi);
+  gcount[i] = (1 + lo[0] + hi[0]) * (1 + lo[1] + hi[1]) * (1 + lo[2] + hi[2]) - 1;
+}
+// descriptors (owner, image code) + ghost cell histogram
+__global__ void k_ghost_desc(Geom g, int nlocal, const double4 *xt, const int *tag, const int *goff, int *gown, int *gimg,
+                             int *gcell, int *gcellcnt, unsigned long long *gkey)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  int lo[3], hi[3];
+  image_flags(g, p.x, p.y, p.z, lo, hi);
+  int q = goff[i];
+  for (int pz = -1; pz <= 1; pz++) {
+    if ((pz == 1 && !lo[2]) || (pz == -1 && !hi[2])) continue;
+    for (int py = -1; py <= 1; py++) {
+      if ((py == 1 && !lo[1]) || (py == -1 && !hi[1])) continue;
+      for (int px = -1; px <= 1; px++) {
+        if ((px == 1 && !lo[0]) || (px == -1 && !hi[0])) continue;
+        if (!px && !py && !pz) continue;
+        double x = px ? __dadd_rn(p.x, px * g.prd[0]) : p.x;   // x[j][0] + pbc*xprd (pack_border)
+        double y = py ? __dadd_rn(p.y, py * g.prd[1]) : p.y;
+        double z = pz ? __dadd_rn(p.z, pz * g.prd[2]) : p.z;
+        int code = (px + 1) + 3 * (py + 1) + 9 * (pz + 1);
+        int c = cell_of(g, x, y, z);
+        gown[q] = i; gimg[q] = code; gcell[q] = c;
+        gkey[q] = ((unsigned long long)(unsigned)tag[i] << 5) | (unsigned)code;
+        atomicAdd(&gcellcnt[c], 1);
+        q++;
+      }
+    }
+  }
+}
+// materialise ghosts in cell order from their owners (pack_border[_vel] / unpack_border fields:
+// x+shift, tag, type, mask, rho, cg, rmass, e, cv, vest (+v); atom_vec_meso_multiphase.cpp:555-721)
+struct GhostArrays {
+  double4 *xt, *vr, *vm, *cgm;
+  double *e, *cv;
+  int *tag, *mask, *gowner, *gimage;
+};
+__global__ void k_ghost_fill(Geom g, int nlocal, int nghost, const int *gperm, const int *gown, const int *gimg,
+                             GhostArrays a, int multiphase, int *gslot)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nghost) return;
+  int q = gperm[s], i = gown[q], code = gimg[q], gi = nlocal + s;
+  int px = code % 3 - 1, py = (code / 3) % 3 - 1, pz = code / 9 - 1;
+  double4 p = a.xt[i];
+  if (px) p.x = __dadd_rn(p.x, px * g.prd[0]);
+  if (py) p.y = __dadd_rn(p.y, py * g.prd[1]);
+  if (pz) p.z = __dadd_rn(p.z, pz * g.prd[2]);
+  int type = tw_type(__double_as_longlong(p.w));
+  p.w = __longlong_as_double((long long)make_tw(g, type, p.x, p.y, p.z));
+  a.xt[gi] = p; a.vr[gi] = a.vr[i]; a.vm[gi] = a.vm[i];
+  if (multiphase) a.cgm[gi] = a.cgm[i];
+  a.e[gi] = a.e[i]; a.cv[gi] = a.cv[i];
+  a.tag[gi] = a.tag[i]; a.mask[gi] = a.mask[i]; a.gowner[gi] = i; a.gimage[gi] = code;
+  gslot[q] = gi;
+}
+// CommBrick::forward_comm with pack_comm[_vel] (atom_vec_meso_multiphase.cpp:319-465, atom_vec_meso.cpp:246-330):
+// x+shift, rho, [cg, rmass], e, vest (+v).  cv, type, tag, mask are NOT refreshed.
+__global__ void k_forward_comm(Geom g, int nlocal, int nghost, GhostArrays a, int multiphase, int ghost_velocity)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nghost) return;
+  int gi = nlocal + s, i = a.gowner[gi], code = a.gimage[gi];
+  int px = code % 3 - 1, py = (code / 3) % 3 - 1, pz = code / 9 - 1;
+  double4 p = a.xt[i], old = a.xt[gi];
+  if (px) p.x = __dadd_rn(p.x, px * g.prd[0]);
+  if (py) p.y = __dadd_rn(p.y, py * g.prd[1]);
+  if (pz) p.z = __dadd_rn(p.z, pz * g.prd[2]);
+  p.w = old.w;
+  a.xt[gi] = p; a.vr[gi] = a.vr[i];
+  double4 vo = a.vm[i], vg = a.vm[gi];
+  if (ghost_velocity) { vg.x = vo.x; vg.y = vo.y; vg.z = vo.z; }
+  if (multiphase) { vg.w = vo.w; a.cgm[gi] = a.cgm[i]; }
+  a.vm[gi] = vg;
+  a.e[gi] = a.e[i];
+}
+// CommBrick::forward_comm_pair for sph/rhosum (pair_sph_rhosum.cpp:203,290-313): ghost rho <- owner rho
+__global__ void k_ghost_rho(int nlocal, int nghost, const int *gowner, double4 *vr)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nghost) return;
+  int gi = nlocal + s;
+  vr[gi].w = vr[gowner[gi]].w;
+}
+
+// ------------------------------------------------------------ the build -----
+#define BUILD_WARPS 4
+#define BUILD_CH 128
+struct BuildSmem {
+  double x[BUILD_CH], y[BUILD_CH], z[BUILD_CH];
+  unsigned long long w[BUILD_CH];
+  int j[BUILD_CH], o[BUILD_CH];
+};
+struct BuildArgs {
+  Geom g;
+  int nlocal, nghost, stride, ntypes1;
+  const double4 *xt;
+  const int *orig;
+  const int *cso, *csg;          // cell starts: owned / ghost (ghost offsets relative to nlocal)
+  const double *cutneighsq;      // [MAXTT]
+  unsigned *nbr;
+  int *numneigh;
+  int *maxcount;
+};
+
+// half_from_full_newton's rule for an (owned i, ghost j) pair (neigh_derive.cpp:121-134): keep iff j is "above/right" of i
+__device__ __forceinline__ bool ghost_above(double xi, double yi, double zi, double xj, double yj, double zj)
+{
+  if (zj < zi) return false;
+  if (zj == zi) {
+    if (yj < yi) return false;
+    if (yj == yi && xj < xi) return false;
+  }
+  return true;
+}
+
+// One warp per engine cell.  Each lane owns one row particle; the candidates of the
+// 3x3x3 stencil are staged through shared memory in chunks and read back as
+// broadcasts (one wavefront per 32 pair tests); hits are collected as 32-bit masks.
+// Rows [0,nlocal): Neighbor::full_bin's list of the owned atom (rsq <= cutneighsq, and
+// j inside the reference's own bin stencil), each entry tagged with the half-list
+// ownership bit frozen at build time.  Rows [nlocal,nall): for a ghost g, the owned
+// atoms i whose half list holds (i,g) -- used to accumulate what the reference adds
+// to ghost atoms and reverse-communicates.
+__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
+{
+  __shared__ BuildSmem sm_all[BUILD_WARPS];
+  __shared__ double s_cut[MAXTT];
+  for (int k = threadIdx.x; k < MAXTT; k += blockDim.x) s_cut[k] = A.cutneighsq[k];
+  __syncthreads();
+  const Geom &g = A.g;
+  int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int c = blockIdx.x * BUILD_WARPS + wib;
+  if (c >= g.ncells) return;
+  BuildSmem &sm = sm_all[wib];
+  int o0 = A.cso[c], nO = A.cso[c + 1] - o0, g0 = A.csg[c], nG = A.csg[c + 1] - g0;
+  if (nO + nG == 0) return;
+  int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
+  const double cutmaxsq = g.cutneighmaxsq;
+
+  for (int pass = 0; pass < 2; pass++) {          // 0: owned rows, 1: ghost rows
+    int nrow = pass ? nG : nO, r0 = pass ? A.nlocal + g0 : o0;
+    for (int rb = 0; rb < nrow; rb += 32) {
+      bool valid = rb + lane < nrow;
+      int i = r0 + rb + lane;
+      double xi = 1e300, yi = 1e300, zi = 1e300;
+      unsigned long long wi = 0; int oi = 0;
+      if (valid) { double4 p = A.xt[i]; xi = p.x; yi = p.y; zi = p.z; wi = (unsigned long long)__double_as_longlong(p.w); if (!pass) oi = A.orig[i]; }
+      int ti = tw_type(wi), bxi = tw_bx(wi), byi = tw_by(wi), bzi = tw_bz(wi);
+      int cnt = 0;
+      unsigned *row = A.nbr + (size_t)i * A.stride;
+      int fill = 0;
+
+      auto process = [&](int n) {
+        for (int base = 0; base < n; base += 32) {
+          unsigned mask = 0;
+          int m = imin(32, n - base);
+          for (int b = 0; b < m; b++) {
+            double dx = xi - sm.x[base + b], dy = yi - sm.y[base + b], dz = zi - sm.z[base + b];
+            double rsq = rsq_nofma(dx, dy, dz);
+            mask |= (unsigned)(rsq <= cutmaxsq) << b;
+          }
+          while (mask) {
+            int b = __ffs(mask) - 1; mask &= mask - 1;
+            int idx = base + b, j = sm.j[idx];
+            if (j == i) continue;
+            unsigned long long wj = sm.w[idx];
+            double xj = sm.x[idx], yj = sm.y[idx], zj = sm.z[idx];
+            double rsq = rsq_nofma(xi - xj, yi - yj, zi - zj);
+            if (!(rsq <= s_cut[ti * MAXT1 + tw_type(wj)])) continue;
+            // j must sit in a bin of the reference's stencil around i's bin (neigh_stencil.cpp:434-448)
+            int dbx = abs(tw_bx(wj) - bxi), dby = abs(tw_by(wj) - byi), dbz = abs(tw_bz(wj) - bzi);
+            if (dbx > g.sx || dby > g.sy || dbz > g.sz) continue;
+            double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0,
+                   ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
+            if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) continue;
+            unsigned ent;
+            if (!pass) {
+              bool own = (j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj);
+              ent = (unsigned)j | (own ? NBR_OWNER_BIT : 0u);
+            } else {
+              if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
+              ent = (unsigned)j | NBR_OWNER_BIT;
+            }
+            if (cnt < A.stride) row[cnt] = ent;
+            cnt++;
+          }
+        }
+      };
+
+      for (int dz = -1; dz <= 1; dz++) {
+        int nz = cz + dz; if (nz < 0 || nz >= g.nc[2]) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+          int ny = cy + dy; if (ny < 0 || ny >= g.nc[1]) continue;
+          for (int dx = -1; dx <= 1; dx++) {
+            int nx = cx + dx; if (nx < 0 || nx >= g.nc[0]) continue;
+            int n = (nz * g.nc[1] + ny) * g.nc[0] + nx;
+            for (int rng = 0; rng < (pass ? 1 : 2); rng++) {
+              int s = rng ? A.nlocal + A.csg[n] : A.cso[n], e = rng ? A.nlocal + A.csg[n + 1] : A.cso[n + 1];
+              while (s < e) {
+                int take = imin(BUILD_CH - fill, e - s);
+                for (int k = lane; k < take; k += 32) {
+                  double4 p = A.xt[s + k];
+                  sm.x[fill + k] = p.x; sm.y[fill + k] = p.y; sm.z[fill + k] = p.z;
+                  sm.w[fill + k] = (unsigned long long)__double_as_longlong(p.w);
+                  sm.j[fill + k] = s + k; sm.o[fill + k] = (s + k < A.nlocal) ? A.orig[s + k] : 0;
+                }
+                fill += take; s += take;
+                if (fill == BUILD_CH) { __syncwarp(); process(fill); __syncwarp(); fill = 0; }
+              }
+            }
+          }
+        }
+      }
+      if (fill) { __syncwarp(); process(fill); __syncwarp(); }
+      if (valid) { A.numneigh[i] = cnt; if (cnt > A.stride) atomicMax(A.maxcount, cnt); else atomicMax(A.maxcount + 1, cnt); }
+    }
+  }
+}

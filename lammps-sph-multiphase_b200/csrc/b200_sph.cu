@@ -1,0 +1,786 @@
+// b200_sph.cu -- host side of libb200sph.so: device state, the Verlet loop and the C-ABI
+// of include/b200_sph.h.  sm_100a only; there is no CPU path in this library.
+#include "b200_common.cuh"
+#include "b200_neigh.cuh"
+#include "b200_pair.cuh"
+#include "b200_fix.cuh"
+#include <algorithm>
+#include <cmath>
+
+static inline double ll_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline long long double_as_ll(double d) { long long v; memcpy(&v, &d, 8); return v; }
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::string(#call) + ": " + cudaGetErrorString(e_); } while (0)
+#define API_BEGIN try {
+#define API_END } catch (const std::string &m) { return fail(m); } catch (const std::exception &e) { return fail(e.what()); } return 0;
+
+enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_NTIMERS };
+static const char *timer_names[T_NTIMERS] = {"initial_integrate", "forward_comm", "neigh_bin_sort_ghost", "neigh_build", "density",
+                                             "colorgradient", "derive", "force", "reverse_post_final", "phase_change"};
+
+template <class T> struct DevBuf {
+  T *p = nullptr; size_t cap = 0;
+  void ensure(size_t n, bool keep = false, cudaStream_t st = 0)
+  {
+    if (n <= cap) return;
+    size_t nc = n + n / 8 + 64;
+    T *q; CK(cudaMalloc(&q, nc * sizeof(T)));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(p)); }
+    p = q; cap = nc;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct OwnedSet {
+  DevBuf<double4> xt, vr, vm, fd, cgm;
+  DevBuf<double> e, de, cv;
+  DevBuf<int> tag, mask, orig;
+  void ensure(size_t n, bool keep, cudaStream_t st)
+  {
+    xt.ensure(n, keep, st); vr.ensure(n, keep, st); vm.ensure(n, keep, st); fd.ensure(n, keep, st); cgm.ensure(n, keep, st);
+    e.ensure(n, keep, st); de.ensure(n, keep, st); cv.ensure(n, keep, st);
+    tag.ensure(n, keep, st); mask.ensure(n, keep, st); orig.ensure(n, keep, st);
+  }
+  void release() { xt.release(); vr.release(); vm.release(); fd.release(); cgm.release(); e.release(); de.release(); cv.release(); tag.release(); mask.release(); orig.release(); }
+  OwnedArrays view() { return OwnedArrays{xt.p, vr.p, vm.p, fd.p, cgm.p, e.p, de.p, cv.p, tag.p, mask.p, orig.p}; }
+};
+
+struct Pass { int type; int kinds; int nslots; int slots[4]; };   // type: 0 rhosum 1 rhosum/mp 2 colorgradient 3 force
+
+struct b200_sph {
+  int device = 0;
+  cudaStream_t st = 0;
+  // problem
+  Geom g{};
+  bool have_domain = false, have_neigh = false;
+  int multiphase = 0, ntypes = 0, ghost_velocity = 0;
+  double mass[MAXT1] = {0};
+  double skin = 0.3, cutneighmax = 0, triggersq = 0;
+  int every = 1, delay = 10, check = 1, ago = 0;
+  double h_cutneighsq[MAXTT] = {0};
+  DevBuf<double> d_cutneighsq;
+  double dt = 0, ftm2v = 1; long long ntimestep = 0;
+  int npair = 0; PairTab h_tab[MAXPAIR]; PairTab *d_tab[MAXPAIR] = {nullptr};
+  std::vector<Pass> plan;
+  FixList fl{};
+  // particles
+  int nlocal = 0, nghost = 0;
+  OwnedSet S[2]; int cur = 0;
+  DevBuf<double4> dq;
+  DevBuf<int> gowner, gimage;
+  DevBuf<int> cellid, perm, perm2, gcount, gown, gimg, gcell, gperm, gperm2, gslot;
+  DevBuf<unsigned long long> key, gkey;
+  DevBuf<int> cso, csg, cellfill, scan_tmp;
+  DevBuf<double> xhold;
+  DevBuf<unsigned> nbr; DevBuf<int> numneigh; int stride = 32;
+  int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
+  bool setup_done = false, geom_ready = false;
+  // instrumentation
+  long long launches = 0, nbuilds = 0, nsteps = 0, maxneigh = 0, ndanger = 0, ninserted = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool; std::vector<int> ev_timer; size_t ev_used = 0;
+  double t_ms[T_NTIMERS] = {0}; long long t_calls[T_NTIMERS] = {0};
+
+  OwnedSet &C() { return S[cur]; }
+  int nall() const { return nlocal + nghost; }
+  void ensure_cap(size_t n, bool keep)
+  {
+    S[0].ensure(n, keep && cur == 0, st); S[1].ensure(n, keep && cur == 1, st);
+    dq.ensure(n, false, st); gowner.ensure(n, false, st); gimage.ensure(n, false, st);
+    numneigh.ensure(n, false, st);
+  }
+  StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p}; }
+  GhostArrays ghost_arrays() { OwnedSet &c = C(); return GhostArrays{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.tag.p, c.mask.p, gowner.p, gimage.p}; }
+
+  // ---- timing helpers ----
+  void tbegin(int which)
+  {
+    if (!timing) return;
+    if (ev_used == ev_pool.size()) { cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); ev_pool.push_back({a, b}); ev_timer.push_back(0); }
+    ev_timer[ev_used] = which;
+    CK(cudaEventRecord(ev_pool[ev_used].first, st));
+  }
+  void tend()
+  {
+    if (!timing) return;
+    CK(cudaEventRecord(ev_pool[ev_used].second, st));
+    ev_used++;
+    if (ev_used >= 4096) tflush();
+  }
+  void tflush()
+  {
+    if (!ev_used) return;
+    CK(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < ev_used; k++) {
+      float ms = 0; CK(cudaEventElapsedTime(&ms, ev_pool[k].first, ev_pool[k].second));
+      t_ms[ev_timer[k]] += ms; t_calls[ev_timer[k]]++;
+    }
+    ev_used = 0;
+  }
+};
+
+#define LAUNCH(h, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (h)->st>>>(__VA_ARGS__); (h)->launches++; } while (0)
+static inline int nblk(long long n, int b) { return (int)std::max<long long>(1, (n + b - 1) / b); }
+
+// ------------------------------------------------------------------ scan ----
+static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch)
+{
+  // data[0..n) counts -> exclusive offsets, data[n] = total; recursive on the per-block totals
+  int per = SCAN_T * SCAN_E, nb = (n + per - 1) / per;
+  LAUNCH(h, k_scan_block, nb, SCAN_T, data, n, scratch);
+  if (nb == 1) {
+    CK(cudaMemcpyAsync(data + n, scratch, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+  } else {
+    scan_exclusive(h, scratch, nb, scratch + nb + 2);
+    LAUNCH(h, k_scan_add, nb, SCAN_T, data, n, scratch);
+    CK(cudaMemcpyAsync(data + n, scratch + nb, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+  }
+}
+
+// -------------------------------------------------------------- geometry ----
+static void setup_geometry(b200_sph *h)
+{
+  Geom &g = h->g;
+  if (!h->have_domain || !h->have_neigh) throw std::string("b200_domain / b200_neighbor must be called before setup");
+  double cut = h->cutneighmax;
+  for (int d = 0; d < 3; d++) {
+    g.prd[d] = g.boxhi[d] - g.boxlo[d];
+    g.slab_lo_hi[d] = g.sublo[d] + g.cutghost;
+    g.slab_hi_lo[d] = g.subhi[d] - g.cutghost;
+    bool swaps = g.periodic[d] && !(g.dim == 2 && d == 2);
+    if (swaps) {
+      int maxneed = (int)(g.cutghost * 1 / g.prd[d]) + 1;   // comm_brick.cpp:228-230 on a 1x1x1 grid
+      if (maxneed > 1) throw std::string("b200: ghost cutoff >= box length in a periodic dimension is not supported");
+    }
+    double lo = swaps ? g.sublo[d] - g.cutghost : g.sublo[d];
+    double hi = swaps ? g.subhi[d] + g.cutghost : g.subhi[d];
+    double len = hi - lo;
+    int nc = (cut > 0.0) ? (int)(len / cut) : 1;
+    if (nc < 1) nc = 1;
+    if (g.dim == 2 && d == 2) nc = 1;
+    if (nc > 4000) nc = 4000;
+    g.clo[d] = lo; g.nc[d] = nc; g.cinv[d] = nc / len;
+  }
+  g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
+  // the reference's bins: Neighbor::setup_bins, neighbor.cpp:1618-1735
+  double binsize_optimal = 0.5 * cut;
+  if (binsize_optimal == 0.0) binsize_optimal = g.prd[0];
+  double binsizeinv = 1.0 / binsize_optimal;
+  for (int d = 0; d < 3; d++) {
+    int nb = (int)(g.prd[d] * binsizeinv);
+    if (g.dim == 2 && d == 2) nb = 1;
+    if (nb == 0) nb = 1;
+    g.nbin[d] = nb; g.binsize[d] = g.prd[d] / nb; g.bininv[d] = 1.0 / g.binsize[d];
+    if (nb + 64 > RB_BIAS * 32) throw std::string("b200: too many reference bins per dimension");
+  }
+  int s[3];
+  for (int d = 0; d < 3; d++) { s[d] = (int)(cut * g.bininv[d]); if (s[d] * g.binsize[d] < cut) s[d]++; }
+  if (g.dim == 2) s[2] = 0;
+  g.sx = s[0]; g.sy = s[1]; g.sz = s[2];
+  g.cutneighmaxsq = cut * cut;
+  h->cso.ensure(g.ncells + 2); h->csg.ensure(g.ncells + 2); h->cellfill.ensure(g.ncells + 2);
+  CK(cudaMemsetAsync(h->csg.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+  h->geom_ready = true;
+}
+
+// ------------------------------------------------------------- reneighbor ---
+static void ensure_scan_tmp(b200_sph *h, size_t n) { h->scan_tmp.ensure(n / (SCAN_T * SCAN_E) * 2 + 4096); }
+
+static void neighbor_build(b200_sph *h, bool do_pbc)
+{
+  Geom &g = h->g;
+  const int B = 256;
+  int nl = h->nlocal;
+  h->tbegin(T_NEIGH_BIN);
+  h->ensure_cap(nl + h->nghost, true);
+  h->cellid.ensure(nl); h->perm.ensure(nl); h->perm2.ensure(nl); h->key.ensure(nl); h->gcount.ensure(nl + 2);
+  ensure_scan_tmp(h, std::max<size_t>(nl + 2, g.ncells + 2));
+  // 1. owned atoms -> cell order
+  CK(cudaMemsetAsync(h->cso.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->cellfill.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+  if (nl) {
+    LAUNCH(h, k_owned_cells, nblk(nl, B), B, g, nl, h->C().xt.p, h->cellid.p, h->cso.p, do_pbc ? 1 : 0);
+    scan_exclusive(h, h->cso.p, g.ncells, h->scan_tmp.p);
+    LAUNCH(h, k_scatter, nblk(nl, B), B, nl, h->cellid.p, h->cso.p, h->cellfill.p, h->perm.p);
+    LAUNCH(h, k_owned_keys, nblk(nl, B), B, nl, h->C().tag.p, h->key.p);
+    LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->cso.p, h->perm.p, h->perm2.p, h->key.p);
+    OwnedSet &a = h->S[h->cur], &b = h->S[h->cur ^ 1];
+    LAUNCH(h, k_permute_owned, nblk(nl, B), B, g, nl, h->perm2.p, a.view(), b.view(), h->multiphase, h->key.p);
+    h->cur ^= 1;
+  }
+  // 2. ghosts (periodic self-images)
+  bool any_swap = false;
+  for (int d = 0; d < 3; d++) any_swap |= g.periodic[d] && !(g.dim == 2 && d == 2);
+  h->nghost = 0;
+  CK(cudaMemsetAsync(h->csg.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+  if (any_swap && nl) {
+    LAUNCH(h, k_ghost_count, nblk(nl, B), B, g, nl, h->C().xt.p, h->gcount.p);
+    scan_exclusive(h, h->gcount.p, nl, h->scan_tmp.p);
+    CK(cudaMemcpyAsync(h->h_flags + 4, h->gcount.p + nl, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int ng = h->h_flags[4];
+    h->nghost = ng;
+    if (ng) {
+      h->ensure_cap(nl + ng, true);
+      h->gown.ensure(ng); h->gimg.ensure(ng); h->gcell.ensure(ng); h->gperm.ensure(ng); h->gperm2.ensure(ng); h->gslot.ensure(ng); h->gkey.ensure(ng);
+      CK(cudaMemsetAsync(h->cellfill.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+      LAUNCH(h, k_ghost_desc, nblk(nl, B), B, g, nl, h->C().xt.p, h->C().tag.p, h->gcount.p, h->gown.p, h->gimg.p, h->gcell.p, h->csg.p, h->gkey.p);
+      scan_exclusive(h, h->csg.p, g.ncells, h->scan_tmp.p);
+      LAUNCH(h, k_scatter, nblk(ng, B), B, ng, h->gcell.p, h->csg.p, h->cellfill.p, h->gperm.p);
+      LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->csg.p, h->gperm.p, h->gperm2.p, h->gkey.p);
+      LAUNCH(h, k_ghost_fill, nblk(ng, B), B, g, nl, ng, h->gperm2.p, h->gown.p, h->gimg.p, h->ghost_arrays(), h->multiphase, h->gslot.p);
+    }
+  } else if (nl) {
+    CK(cudaMemsetAsync(h->gcount.p, 0, (nl + 2) * sizeof(int), h->st));
+  }
+  if (h->check && nl) { h->xhold.ensure((size_t)3 * nl); LAUNCH(h, k_store_xhold, nblk(nl, B), B, nl, h->C().xt.p, h->xhold.p); }
+  h->tend();
+  // 3. rows
+  h->tbegin(T_NEIGH_BUILD);
+  int na = h->nall();
+  for (int attempt = 0; attempt < 8 && na; attempt++) {
+    h->nbr.ensure((size_t)na * h->stride);
+    CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
+    BuildArgs A;
+    A.g = g; A.nlocal = nl; A.nghost = h->nghost; A.stride = h->stride; A.ntypes1 = h->ntypes + 1;
+    A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.cutneighsq = h->d_cutneighsq.p;
+    A.nbr = h->nbr.p; A.numneigh = h->numneigh.p; A.maxcount = h->d_flags;
+    LAUNCH(h, k_build, nblk(g.ncells, BUILD_WARPS), BUILD_WARPS * 32, A);
+    CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int mx = std::max(h->h_flags[0], h->h_flags[1]);
+    h->maxneigh = std::max<long long>(h->maxneigh, mx);
+    if (mx <= h->stride) break;
+    h->stride = ((int)(mx * 1.2) + 8 + 31) / 32 * 32;     // the reference's hard cap is oneatom = 2000 (neighbor.cpp:81)
+    if (attempt == 7) throw std::string("b200: neighbor row overflow");
+  }
+  h->tend();
+  h->ago = 0; h->nbuilds++;
+}
+
+// ------------------------------------------------------------- pair plan ----
+static int kind_of(int style)
+{
+  switch (style) {
+  case B200_PAIR_TAITWATER: return K_TAIT;
+  case B200_PAIR_TAITWATER_MORRIS: return K_MORRIS;
+  case B200_PAIR_TAITWATER_MULTIPHASE: return K_TAITMP;
+  case B200_PAIR_SURFACETENSION: return K_SURF;
+  case B200_PAIR_HEATCONDUCTION: return K_HEAT;
+  case B200_PAIR_HEATCONDUCTION_MULTIPHASE: return K_HEATMP;
+  case B200_PAIR_HEATCONDUCTION_PHASECHANGE: return K_HEATPC;
+  default: return 0;
+  }
+}
+static const int FUSED[] = {K_TAIT | K_HEAT, K_MORRIS | K_HEAT, K_TAITMP | K_SURF, K_TAITMP | K_SURF | K_HEATMP, K_TAITMP | K_SURF | K_HEATPC,
+                            K_TAITMP | K_HEATMP, K_TAITMP | K_HEATPC, K_SURF | K_HEATMP, K_SURF | K_HEATPC};
+static bool fusable(int kinds)
+{
+  for (int f : FUSED) if (f == kinds) return true;
+  return (kinds & (kinds - 1)) == 0;
+}
+static void build_plan(b200_sph *h)
+{
+  h->plan.clear();
+  int k = 0;
+  while (k < h->npair) {
+    int st = h->h_tab[k].style;
+    Pass p{}; p.nslots = 1; p.slots[0] = k;
+    if (st == B200_PAIR_RHOSUM) { p.type = 0; h->plan.push_back(p); k++; continue; }
+    if (st == B200_PAIR_RHOSUM_MULTIPHASE) { p.type = 1; h->plan.push_back(p); k++; continue; }
+    if (st == B200_PAIR_COLORGRADIENT) { p.type = 2; h->plan.push_back(p); k++; continue; }
+    // greedy group of consecutive force-type sub-styles that has a fused instantiation
+    p.type = 3; p.kinds = kind_of(st); k++;
+    while (k < h->npair && p.nslots < 3) {
+      int kk = kind_of(h->h_tab[k].style);
+      if (!kk || (p.kinds & kk) || !fusable(p.kinds | kk)) break;
+      p.kinds |= kk; p.slots[p.nslots++] = k; k++;
+    }
+    h->plan.push_back(p);
+  }
+}
+
+static PairArgs pair_args(b200_sph *h)
+{
+  PairArgs A{};
+  OwnedSet &c = h->C();
+  A.nlocal = h->nlocal; A.nall = h->nall(); A.stride = h->stride; A.dim = h->g.dim; A.multiphase = h->multiphase;
+  A.nbr = h->nbr.p; A.numneigh = h->numneigh.p;
+  A.xt = c.xt.p; A.vr = c.vr.p; A.vm = c.vm.p; A.cgm = c.cgm.p; A.dq = h->dq.p; A.e = c.e.p; A.cv = c.cv.p;
+  A.vr_out = c.vr.p; A.cg_out = c.cgm.p; A.fd = c.fd.p; A.de = c.de.p;
+  return A;
+}
+static int pair_grid(b200_sph *h, int rows)
+{
+  int need = nblk(rows, PAIR_WARPS);
+  return std::min(need, 148 * 8);       // persistent-ish: a multiple of the SM count, rows strided over the warps
+}
+
+template <int KINDS> static void launch_force(b200_sph *h, PairArgs &A)
+{
+  int grid = pair_grid(h, A.nall);
+  if (h->g.dim == 3) k_force<KINDS, true><<<grid, PAIR_WARPS * 32, 0, h->st>>>(A);
+  else k_force<KINDS, false><<<grid, PAIR_WARPS * 32, 0, h->st>>>(A);
+  h->launches++;
+}
+
+static void run_pass(b200_sph *h, const Pass &p)
+{
+  if (!h->nlocal) return;
+  PairArgs A = pair_args(h);
+  const int B = 256;
+  if (p.type <= 2) {
+    const PairTab &T = h->h_tab[p.slots[0]];
+    A.tab[0] = h->d_tab[p.slots[0]];
+    bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
+    int grid = pair_grid(h, A.nlocal);
+    if (p.type == 0) {
+      h->tbegin(T_DENSITY);
+      if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_WARPS * 32, A);
+      if (h->nghost) LAUNCH(h, k_ghost_rho, nblk(h->nghost, B), B, h->nlocal, h->nghost, h->gowner.p, h->C().vr.p);  // forward_comm_pair (:203)
+      h->tend();
+    } else if (p.type == 1) {
+      h->tbegin(T_DENSITY);
+      if (active) LAUNCH(h, k_rhosum<true>, grid, PAIR_WARPS * 32, A);
+      h->tend();
+    } else if (active) {
+      h->tbegin(T_DERIVE);
+      LAUNCH(h, k_derive, nblk(A.nall, B), B, A.nall, 1, (const PairTab *)nullptr, A.xt, A.vr, A.cgm, A.e, A.cv, h->dq.p);
+      h->tend();
+      h->tbegin(T_COLORGRAD);
+      LAUNCH(h, k_colorgradient, grid, PAIR_WARPS * 32, A);
+      h->tend();
+    }
+    return;
+  }
+  // force pass: canonical table order fluid, surf, heat
+  int nk = 0; const PairTab *fluid = nullptr;
+  const int wants[3] = {K_TAIT | K_MORRIS | K_TAITMP, K_SURF, K_HEAT | K_HEATMP | K_HEATPC};
+  for (int want : wants)
+    for (int s = 0; s < p.nslots; s++)
+      if (kind_of(h->h_tab[p.slots[s]].style) & want) { A.tab[nk++] = h->d_tab[p.slots[s]]; if (want & K_TAIT) fluid = h->d_tab[p.slots[s]]; }
+  h->tbegin(T_DERIVE);
+  LAUNCH(h, k_derive, nblk(A.nall, B), B, A.nall, h->multiphase, fluid, A.xt, A.vr, A.cgm, A.e, A.cv, h->dq.p);
+  h->tend();
+  h->tbegin(T_FORCE);
+  switch (p.kinds) {
+  case K_TAIT: launch_force<K_TAIT>(h, A); break;
+  case K_MORRIS: launch_force<K_MORRIS>(h, A); break;
+  case K_HEAT: launch_force<K_HEAT>(h, A); break;
+  case K_TAITMP: launch_force<K_TAITMP>(h, A); break;
+  case K_SURF: launch_force<K_SURF>(h, A); break;
+  case K_HEATMP: launch_force<K_HEATMP>(h, A); break;
+  case K_HEATPC: launch_force<K_HEATPC>(h, A); break;
+  case K_TAIT | K_HEAT: launch_force<K_TAIT | K_HEAT>(h, A); break;
+  case K_MORRIS | K_HEAT: launch_force<K_MORRIS | K_HEAT>(h, A); break;
+  case K_TAITMP | K_SURF: launch_force<K_TAITMP | K_SURF>(h, A); break;
+  case K_TAITMP | K_SURF | K_HEATMP: launch_force<K_TAITMP | K_SURF | K_HEATMP>(h, A); break;
+  case K_TAITMP | K_SURF | K_HEATPC: launch_force<K_TAITMP | K_SURF | K_HEATPC>(h, A); break;
+  case K_TAITMP | K_HEATMP: launch_force<K_TAITMP | K_HEATMP>(h, A); break;
+  case K_TAITMP | K_HEATPC: launch_force<K_TAITMP | K_HEATPC>(h, A); break;
+  case K_SURF | K_HEATMP: launch_force<K_SURF | K_HEATMP>(h, A); break;
+  case K_SURF | K_HEATPC: launch_force<K_SURF | K_HEATPC>(h, A); break;
+  default: throw std::string("b200: no force kernel instantiation for this sub-style group");
+  }
+  h->tend();
+}
+
+// ---------------------------------------------------------- Verlet stages ---
+static void force_clear(b200_sph *h)
+{
+  int na = h->nall();
+  if (!na) return;
+  CK(cudaMemsetAsync(h->C().fd.p, 0, (size_t)na * sizeof(double4), h->st));
+  CK(cudaMemsetAsync(h->C().de.p, 0, (size_t)na * sizeof(double), h->st));
+}
+static void pair_compute_all(b200_sph *h) { for (const Pass &p : h->plan) run_pass(h, p); }
+static void post_final(b200_sph *h, int rev, int post, int fin)
+{
+  if (!h->nlocal) return;
+  h->tbegin(T_FINAL);
+  LAUNCH(h, k_post_final, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, rev && h->nghost, post, fin,
+         h->gcount.p, h->gslot.p);
+  h->tend();
+}
+static void initial_integrate(b200_sph *h)
+{
+  if (!h->nlocal) return;
+  h->tbegin(T_INTEGRATE);
+  CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));
+  LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
+         h->xhold.p, h->triggersq, h->d_flags + 1);
+  h->tend();
+}
+static void forward_comm(b200_sph *h)
+{
+  if (!h->nghost) return;
+  h->tbegin(T_COMM);
+  LAUNCH(h, k_forward_comm, nblk(h->nghost, 256), 256, h->g, h->nlocal, h->nghost, h->ghost_arrays(), h->multiphase, h->ghost_velocity);
+  h->tend();
+}
+// Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
+static int neigh_decide(b200_sph *h)
+{
+  h->ago++;
+  if (h->ago >= h->delay && h->ago % h->every == 0) {
+    if (!h->check) return 1;
+    CK(cudaMemcpyAsync(h->h_flags + 1, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int flag = h->h_flags[1];
+    if (flag && h->ago == std::max(h->every, h->delay)) h->ndanger++;
+    return flag;
+  }
+  return 0;
+}
+static void reneighbor(b200_sph *h) { neighbor_build(h, true); }
+
+static void do_setup(b200_sph *h)
+{
+  if (!h->geom_ready) setup_geometry(h);
+  build_plan(h);
+  neighbor_build(h, true);
+  h->nbuilds = 0;
+  force_clear(h);
+  if (h->nlocal) LAUNCH(h, k_setup_pre_force, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays());
+  // ghosts carry vest of the border comm (before setup_pre_force), exactly as in Verlet::setup
+  pair_compute_all(h);
+  post_final(h, 1, 1, 0);
+  h->setup_done = true;
+}
+static void do_run(b200_sph *h, int n)
+{
+  if (!h->setup_done) throw std::string("b200_run called before b200_setup");
+  for (int s = 0; s < n; s++) {
+    h->ntimestep++;
+    initial_integrate(h);
+    if (neigh_decide(h)) reneighbor(h); else forward_comm(h);
+    force_clear(h);
+    pair_compute_all(h);
+    post_final(h, 1, 1, 1);
+    h->nsteps++;
+  }
+  if (h->timing) h->tflush();
+}
+
+// ------------------------------------------------------------ table fill ----
+static void fill_tab(b200_sph *h, const b200_pair_desc *d, PairTab &T)
+{
+  memset(&T, 0, sizeof T);
+  int n1 = h->ntypes + 1, dim = h->g.dim;
+  const double n3 = 0.0716197243913529, n2 = 0.04195297663091802;   // sph_kernel_quintic.cpp
+  const double nq = dim == 3 ? n3 : n2;
+  T.style = d->style; T.nstep = d->nstep; T.kind = kind_of(d->style);
+  for (int k = 0; k < MAXTT; k++) T.cutsq[k] = -1.0;
+  for (int t = 0; t < MAXT1; t++) { T.iskip[t] = 1; T.mass[t] = h->mass[t]; }
+  bool guni = true; double g0 = 0; bool gset = false;
+  for (int i = 1; i < n1; i++) {
+    if (d->rho0) T.rho0[i] = d->rho0[i];
+    if (d->B) T.B[i] = d->B[i];
+    if (d->soundspeed) T.cs[i] = d->soundspeed[i];
+    if (d->gamma) { T.gamma[i] = d->gamma[i]; }
+    if (d->rbackground) T.rb[i] = d->rbackground[i];
+    for (int j = 1; j < n1; j++) {
+      int s = i * n1 + j, k = i * MAXT1 + j;
+      if (!d->mapped[s]) continue;
+      T.iskip[i] = 0;
+      double hh = d->cut[s], ih = 1.0 / hh, ihsq = ih * ih;
+      T.cutsq[k] = d->cutsq[s]; T.h[k] = hh;
+      switch (d->style) {
+      case B200_PAIR_RHOSUM:
+        T.c1[k] = ihsq;
+        T.c0[k] = dim == 3 ? 2.1541870227086614782e0 * ihsq * ih : 1.5915494309189533576e0 * ihsq;
+        break;
+      case B200_PAIR_RHOSUM_MULTIPHASE:
+        T.c1[k] = ih; T.c0[k] = dim == 3 ? nq * ih * ih * ih : nq * ih * ih;
+        break;
+      case B200_PAIR_COLORGRADIENT: case B200_PAIR_SURFACETENSION:
+        T.c1[k] = ih; T.c0[k] = dim == 3 ? 3.0 * nq * ih * ih * ih * ih : 3.0 * nq * ih * ih * ih;
+        if (d->alpha) T.visc[k] = d->alpha[s];
+        break;
+      case B200_PAIR_TAITWATER: case B200_PAIR_TAITWATER_MORRIS: case B200_PAIR_HEATCONDUCTION:
+        T.c0[k] = dim == 3 ? -25.066903536973515383e0 * ihsq * ihsq * ihsq * ih : -19.098593171027440292e0 * ihsq * ihsq * ihsq;
+        T.visc[k] = d->style == B200_PAIR_HEATCONDUCTION ? (d->alpha ? d->alpha[s] : 0.0) : (d->viscosity ? d->viscosity[s] : 0.0);
+        break;
+      case B200_PAIR_TAITWATER_MULTIPHASE: case B200_PAIR_HEATCONDUCTION_MULTIPHASE: case B200_PAIR_HEATCONDUCTION_PHASECHANGE:
+        T.c1[k] = ih; T.c0[k] = dim == 3 ? 3.0 * nq * ih * ih * ih * ih : 3.0 * nq * ih * ih * ih;
+        T.visc[k] = d->style == B200_PAIR_TAITWATER_MULTIPHASE ? (d->viscosity ? d->viscosity[s] : 0.0) : (d->alpha ? d->alpha[s] : 0.0);
+        if (d->tc) T.tc[k] = d->tc[s];
+        if (d->fixflag) T.fixflag[k] = d->fixflag[s];
+        break;
+      default: throw std::string("b200_pair_add: unknown pair style");
+      }
+    }
+    // self terms use h = cut[itype][itype]
+    int sii = i * n1 + i;
+    if (d->mapped[sii]) {
+      double hh = d->cut[sii];
+      if (d->style == B200_PAIR_RHOSUM) T.self0[i] = dim == 3 ? 2.1541870227086614782 / (hh * hh * hh) : 1.5915494309189533576e0 / (hh * hh);
+      if (d->style == B200_PAIR_RHOSUM_MULTIPHASE) T.self0[i] = dim == 3 ? (nq * 66.0) / (hh * hh * hh) : (nq * 66.0) / (hh * hh);
+    }
+    if (d->gamma && !T.iskip[i]) { if (!gset) { g0 = d->gamma[i]; gset = true; } else if (d->gamma[i] != g0) guni = false; }
+  }
+  T.gamma_uniform = guni ? 1 : 0;
+}
+
+// =================================================================== ABI ====
+extern "C" {
+
+const char *b200_last_error(void) { return g_err.c_str(); }
+const char *b200_version(void) { return "b200sph 0.1 (sm_100a)"; }
+
+int b200_create(b200_sph **out, int device)
+{
+  API_BEGIN
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) throw std::string("b200_create: no CUDA device (the SPH hot path has no CPU fallback)");
+  if (device < 0 || device >= n) throw std::string("b200_create: bad device index");
+  CK(cudaSetDevice(device));
+  b200_sph *h = new b200_sph();
+  h->device = device;
+  CK(cudaMalloc(&h->d_flags, 16 * sizeof(int)));
+  CK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
+  CK(cudaMallocHost(&h->h_flags, 16 * sizeof(int)));
+  memset(&h->fl, 0, sizeof h->fl);
+  *out = h;
+  API_END
+}
+int b200_destroy(b200_sph *h)
+{
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  h->S[0].release(); h->S[1].release(); h->dq.release(); h->gowner.release(); h->gimage.release();
+  h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
+  h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
+  h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
+  for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
+  for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
+  delete h;
+  return 0;
+}
+
+int b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[3], const int periodicity[3], const double sublo[3],
+                const double subhi[3])
+{
+  API_BEGIN
+  if (dim != 2 && dim != 3) throw std::string("b200_domain: dimension must be 2 or 3");
+  h->g.dim = dim;
+  for (int d = 0; d < 3; d++) {
+    h->g.boxlo[d] = boxlo[d]; h->g.boxhi[d] = boxhi[d]; h->g.periodic[d] = periodicity[d];
+    h->g.sublo[d] = sublo ? sublo[d] : boxlo[d]; h->g.subhi[d] = subhi ? subhi[d] : boxhi[d];
+    if (h->g.sublo[d] != boxlo[d] || h->g.subhi[d] != boxhi[d]) throw std::string("b200_domain: sub-domains (multi-GPU bricks) are not implemented yet");
+  }
+  h->have_domain = true; h->geom_ready = false;
+  API_END
+}
+int b200_atom_style(b200_sph *h, int multiphase, int ntypes, const double *mass)
+{
+  API_BEGIN
+  if (ntypes < 1 || ntypes >= MAXT1) throw std::string("b200_atom_style: 1..7 atom types supported");
+  h->multiphase = multiphase; h->ntypes = ntypes;
+  for (int t = 0; t < MAXT1; t++) h->mass[t] = (mass && t <= ntypes) ? mass[t] : 0.0;
+  API_END
+}
+int b200_neighbor(b200_sph *h, double skin, int every, int delay, int check, const double *cutneighsq, double cutneighmax, double cutghost)
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  int n1 = h->ntypes + 1;
+  h->skin = skin; h->every = every; h->delay = delay; h->check = check;
+  memset(h->h_cutneighsq, 0, sizeof h->h_cutneighsq);
+  for (int i = 1; i < n1; i++) for (int j = 1; j < n1; j++) h->h_cutneighsq[i * MAXT1 + j] = cutneighsq[i * n1 + j];
+  h->d_cutneighsq.ensure(MAXTT);
+  CK(cudaMemcpy(h->d_cutneighsq.p, h->h_cutneighsq, sizeof h->h_cutneighsq, cudaMemcpyHostToDevice));
+  h->cutneighmax = cutneighmax; h->g.cutghost = cutghost;
+  h->triggersq = 0.25 * skin * skin;      // neighbor.cpp:240
+  h->have_neigh = true; h->geom_ready = false;
+  API_END
+}
+int b200_timestep(b200_sph *h, double dt, double ftm2v, long long ntimestep) { h->dt = dt; h->ftm2v = ftm2v; h->ntimestep = ntimestep; return 0; }
+int b200_comm_modify(b200_sph *h, int ghost_velocity) { h->ghost_velocity = ghost_velocity; return 0; }
+
+int b200_pair_clear(b200_sph *h) { h->npair = 0; h->plan.clear(); return 0; }
+int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
+{
+  int slot = -1;
+  try {
+    CK(cudaSetDevice(h->device));
+    if (h->npair == MAXPAIR) throw std::string("b200_pair_add: too many sub-styles");
+    if (!h->have_domain || !h->ntypes) throw std::string("b200_pair_add: call b200_domain and b200_atom_style first");
+    if (!d->mapped || !d->cut || !d->cutsq) throw std::string("b200_pair_add: mapped, cut and cutsq are required");
+    slot = h->npair;
+    fill_tab(h, d, h->h_tab[slot]);
+    if (!h->d_tab[slot]) CK(cudaMalloc(&h->d_tab[slot], sizeof(PairTab)));
+    CK(cudaMemcpy(h->d_tab[slot], &h->h_tab[slot], sizeof(PairTab), cudaMemcpyHostToDevice));
+    h->npair++;
+  } catch (const std::string &m) { return fail(m); }
+  return slot;
+}
+
+int b200_fix_clear(b200_sph *h) { memset(&h->fl, 0, sizeof h->fl); return 0; }
+static int add_fix(b200_sph *h, int kind, int bit, double ax, double ay, double az)
+{
+  if (h->fl.n == MAXFIX) return fail("too many fixes");
+  int k = h->fl.n++;
+  h->fl.kind[k] = kind; h->fl.bit[k] = bit; h->fl.acc[k][0] = ax; h->fl.acc[k][1] = ay; h->fl.acc[k][2] = az;
+  return 0;
+}
+int b200_fix_meso(b200_sph *h, int groupbit) { return add_fix(h, 1, groupbit, 0, 0, 0); }
+int b200_fix_meso_stationary(b200_sph *h, int groupbit) { return add_fix(h, 2, groupbit, 0, 0, 0); }
+int b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc) { return add_fix(h, 3, groupbit, xacc, yacc, zacc); }
+int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d) { (void)h; (void)d; return fail("b200_fix_phase_change: not implemented yet"); }
+
+int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  if (!a->x || !a->type) throw std::string("b200_set_atoms: x and type are required");
+  if (n > (int)NBR_INDEX_MASK / 2) throw std::string("b200_set_atoms: too many atoms for 30-bit neighbor indices");
+  h->nlocal = n; h->nghost = 0; h->cur = 0;
+  h->ensure_cap(n, false);
+  std::vector<double4> xt(n), vr(n), vm(n), fd(n), cgm(n);
+  std::vector<double> e(n), de(n), cv(n);
+  std::vector<int> tag(n), mask(n), orig(n);
+  for (int i = 0; i < n; i++) {
+    int t = a->type[i];
+    if (t < 1 || t > h->ntypes) throw std::string("b200_set_atoms: atom type out of range");
+    double m = a->rmass ? a->rmass[i] : h->mass[t];
+    if (!h->multiphase) m = h->mass[t];
+    const double *v = a->v ? a->v + 3 * i : nullptr, *ve = a->vest ? a->vest + 3 * i : v;
+    xt[i] = make_double4(a->x[3 * i], a->x[3 * i + 1], a->x[3 * i + 2], ll_as_double((long long)pack_tw(t, 0, 0, 0)));
+    vm[i] = make_double4(v ? v[0] : 0, v ? v[1] : 0, v ? v[2] : 0, m);
+    vr[i] = make_double4(ve ? ve[0] : 0, ve ? ve[1] : 0, ve ? ve[2] : 0, a->rho ? a->rho[i] : 0.0);
+    fd[i] = make_double4(a->f ? a->f[3 * i] : 0, a->f ? a->f[3 * i + 1] : 0, a->f ? a->f[3 * i + 2] : 0, a->drho ? a->drho[i] : 0.0);
+    const double *c = a->colorgradient ? a->colorgradient + 3 * i : nullptr;
+    cgm[i] = make_double4(c ? c[0] : 0, c ? c[1] : 0, c ? c[2] : 0, m);
+    e[i] = a->e ? a->e[i] : 0.0; de[i] = a->de ? a->de[i] : 0.0; cv[i] = a->cv ? a->cv[i] : 0.0;
+    tag[i] = a->tag ? a->tag[i] : i + 1; mask[i] = a->mask ? a->mask[i] : 1; orig[i] = i;
+  }
+  OwnedSet &c = h->C();
+  size_t n4 = (size_t)n * sizeof(double4), n1 = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+  if (n) {
+    CK(cudaMemcpyAsync(c.xt.p, xt.data(), n4, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.vr.p, vr.data(), n4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.vm.p, vm.data(), n4, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.fd.p, fd.data(), n4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.cgm.p, cgm.data(), n4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.e.p, e.data(), n1, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.de.p, de.data(), n1, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.cv.p, cv.data(), n1, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.tag.p, tag.data(), ni, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.mask.p, mask.data(), ni, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(c.orig.p, orig.data(), ni, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  h->setup_done = false;
+  API_END
+}
+int b200_get_natoms(b200_sph *h, int *nlocal, int *nghost) { if (nlocal) *nlocal = h->nlocal; if (nghost) *nghost = h->nghost; return 0; }
+
+int b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a)
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  int n = h->nlocal;
+  if (n > nmax) throw std::string("b200_get_atoms: buffer too small");
+  if (!n) return 0;
+  OwnedSet &c = h->C();
+  std::vector<double4> xt(n), vr(n), vm(n), fd(n), cgm(n);
+  std::vector<double> e(n), de(n), cv(n);
+  std::vector<int> tag(n), mask(n), orig(n);
+  size_t n4 = (size_t)n * sizeof(double4), n1 = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemcpy(xt.data(), c.xt.p, n4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(vr.data(), c.vr.p, n4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vm.data(), c.vm.p, n4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fd.data(), c.fd.p, n4, cudaMemcpyDeviceToHost));
+  if (h->multiphase) CK(cudaMemcpy(cgm.data(), c.cgm.p, n4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(e.data(), c.e.p, n1, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(de.data(), c.de.p, n1, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cv.data(), c.cv.p, n1, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tag.data(), c.tag.p, ni, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(mask.data(), c.mask.p, ni, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(orig.data(), c.orig.p, ni, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < n; s++) {
+    int i = orig[s];
+    if (i < 0 || i >= n) throw std::string("b200_get_atoms: corrupt index map");
+    if (a->x) { a->x[3 * i] = xt[s].x; a->x[3 * i + 1] = xt[s].y; a->x[3 * i + 2] = xt[s].z; }
+    if (a->v) { a->v[3 * i] = vm[s].x; a->v[3 * i + 1] = vm[s].y; a->v[3 * i + 2] = vm[s].z; }
+    if (a->vest) { a->vest[3 * i] = vr[s].x; a->vest[3 * i + 1] = vr[s].y; a->vest[3 * i + 2] = vr[s].z; }
+    if (a->f) { a->f[3 * i] = fd[s].x; a->f[3 * i + 1] = fd[s].y; a->f[3 * i + 2] = fd[s].z; }
+    if (a->colorgradient) { a->colorgradient[3 * i] = h->multiphase ? cgm[s].x : 0; a->colorgradient[3 * i + 1] = h->multiphase ? cgm[s].y : 0; a->colorgradient[3 * i + 2] = h->multiphase ? cgm[s].z : 0; }
+    if (a->rho) a->rho[i] = vr[s].w;
+    if (a->drho) a->drho[i] = fd[s].w;
+    if (a->e) a->e[i] = e[s];
+    if (a->de) a->de[i] = de[s];
+    if (a->cv) a->cv[i] = cv[s];
+    if (a->rmass) a->rmass[i] = vm[s].w;
+    if (a->type) a->type[i] = tw_type((unsigned long long)double_as_ll(xt[s].w));
+    if (a->mask) a->mask[i] = mask[s];
+    if (a->tag) a->tag[i] = tag[s];
+  }
+  API_END
+}
+
+int b200_setup(b200_sph *h) { API_BEGIN CK(cudaSetDevice(h->device)); do_setup(h); API_END }
+int b200_run(b200_sph *h, int nsteps) { API_BEGIN CK(cudaSetDevice(h->device)); do_run(h, nsteps); API_END }
+int b200_initial_integrate(b200_sph *h) { API_BEGIN initial_integrate(h); API_END }
+int b200_final_integrate(b200_sph *h) { API_BEGIN post_final(h, 0, 0, 1); API_END }
+int b200_neigh_decide(b200_sph *h, int *rebuild) { API_BEGIN *rebuild = neigh_decide(h); API_END }
+int b200_forward_comm(b200_sph *h) { API_BEGIN forward_comm(h); API_END }
+int b200_reneighbor(b200_sph *h) { API_BEGIN if (!h->geom_ready) setup_geometry(h); if (h->plan.empty()) build_plan(h); reneighbor(h); API_END }
+int b200_force_clear(b200_sph *h) { API_BEGIN force_clear(h); API_END }
+int b200_pair_compute(b200_sph *h, int slot)
+{
+  API_BEGIN
+  if (slot < 0 || slot >= h->npair) throw std::string("b200_pair_compute: bad slot");
+  Pass p{}; p.nslots = 1; p.slots[0] = slot;
+  int st = h->h_tab[slot].style;
+  p.type = st == B200_PAIR_RHOSUM ? 0 : st == B200_PAIR_RHOSUM_MULTIPHASE ? 1 : st == B200_PAIR_COLORGRADIENT ? 2 : 3;
+  p.kinds = kind_of(st);
+  run_pass(h, p);
+  API_END
+}
+int b200_pair_compute_all(b200_sph *h) { API_BEGIN if (h->plan.empty()) build_plan(h); pair_compute_all(h); API_END }
+int b200_reverse_comm(b200_sph *h) { API_BEGIN post_final(h, 1, 0, 0); API_END }
+int b200_post_force(b200_sph *h) { API_BEGIN post_final(h, 0, 1, 0); API_END }
+
+int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nentries, int *jtag, int *jimage)
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  if (nlocal != h->nlocal) throw std::string("b200_get_neighbor_list: nlocal mismatch");
+  int n = nlocal, na = h->nall();
+  if (!n) return 0;
+  CK(cudaStreamSynchronize(h->st));
+  std::vector<int> cnt(n), orig(n), tag(na), img(na);
+  CK(cudaMemcpy(cnt.data(), h->numneigh.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(orig.data(), h->C().orig.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < n; s++) numneigh[orig[s]] = cnt[s];
+  if (!jtag) return 0;
+  long long tot = 0;
+  std::vector<long long> off(n + 1);
+  for (int i = 0; i < n; i++) { off[i] = tot; tot += numneigh[i]; }
+  if (nentries < tot) throw std::string("b200_get_neighbor_list: buffer too small");
+  CK(cudaMemcpy(tag.data(), h->C().tag.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h->nghost) CK(cudaMemcpy(img.data() + n, h->gimage.p + n, (size_t)h->nghost * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < n; s++) img[s] = 13;
+  std::vector<unsigned> rows((size_t)n * h->stride);
+  CK(cudaMemcpy(rows.data(), h->nbr.p, rows.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<int, int>> tmp;
+  for (int s = 0; s < n; s++) {
+    tmp.clear();
+    for (int k = 0; k < cnt[s]; k++) { int j = rows[(size_t)s * h->stride + k] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]}); }
+    std::sort(tmp.begin(), tmp.end());
+    long long o = off[orig[s]];
+    for (int k = 0; k < cnt[s]; k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
+  }
+  API_END
+}
+
+int b200_get_counters(b200_sph *h, long long c[8])
+{ c[0] = h->launches; c[1] = h->nbuilds; c[2] = h->nsteps; c[3] = h->maxneigh; c[4] = h->nghost; c[5] = h->stride; c[6] = h->ninserted; c[7] = h->ndanger; return 0; }
+int b200_set_timing(b200_sph *h, int on)
+{ API_BEGIN h->tflush(); h->timing = on != 0; for (int k = 0; k < T_NTIMERS; k++) { h->t_ms[k] = 0; h->t_calls[k] = 0; } API_END }
+int b200_get_timers(b200_sph *h, int n, double *ms, long long *calls)
+{ API_BEGIN h->tflush(); for (int k = 0; k < n; k++) { ms[k] = k < T_NTIMERS ? h->t_ms[k] : 0.0; calls[k] = k < T_NTIMERS ? h->t_calls[k] : 0; } API_END }
+const char *b200_timer_name(int i) { return (i >= 0 && i < T_NTIMERS) ? timer_names[i] : ""; }
+int b200_sync(b200_sph *h) { API_BEGIN CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->st)); API_END }
+
+} // extern "C"
