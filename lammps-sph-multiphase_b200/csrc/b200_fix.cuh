@@ -106,3 +106,52 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
     if (ed) { a.e[i] = e; a.vr[i] = vr; }
   }
 }
+
+// ---- host <-> device layout conversion (LAMMPS AoS per-atom arrays <-> packed double4 records) ----
+struct HostMirror {            // device staging copies of the caller's arrays (NULL = field absent)
+  double *x, *v, *vest, *f, *cg, *rho, *drho, *e, *de, *cv, *rmass;
+  int *type, *mask, *tag;
+};
+struct PackArrays {
+  double4 *xt, *vr, *vm, *fd, *cgm;
+  double *e, *de, *cv;
+  int *tag, *mask, *orig;
+};
+__global__ void k_pack_atoms(int n, HostMirror m, PackArrays a, int multiphase, const double *mass, int ntypes, int *bad)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int t = m.type[i];
+  if (t < 1 || t > ntypes) { *bad = 1; t = 1; }
+  double ms = (multiphase && m.rmass) ? m.rmass[i] : mass[t];
+  const double *v = m.v ? m.v + 3 * i : nullptr, *ve = m.vest ? m.vest + 3 * i : v;
+  a.xt[i] = make_double4(m.x[3 * i], m.x[3 * i + 1], m.x[3 * i + 2], __longlong_as_double((long long)pack_tw(t, 0, 0, 0)));
+  a.vm[i] = make_double4(v ? v[0] : 0.0, v ? v[1] : 0.0, v ? v[2] : 0.0, ms);
+  a.vr[i] = make_double4(ve ? ve[0] : 0.0, ve ? ve[1] : 0.0, ve ? ve[2] : 0.0, m.rho ? m.rho[i] : 0.0);
+  a.fd[i] = make_double4(m.f ? m.f[3 * i] : 0.0, m.f ? m.f[3 * i + 1] : 0.0, m.f ? m.f[3 * i + 2] : 0.0, m.drho ? m.drho[i] : 0.0);
+  a.cgm[i] = make_double4(m.cg ? m.cg[3 * i] : 0.0, m.cg ? m.cg[3 * i + 1] : 0.0, m.cg ? m.cg[3 * i + 2] : 0.0, ms);
+  a.e[i] = m.e ? m.e[i] : 0.0; a.de[i] = m.de ? m.de[i] : 0.0; a.cv[i] = m.cv ? m.cv[i] : 0.0;
+  a.tag[i] = m.tag ? m.tag[i] : i + 1; a.mask[i] = m.mask ? m.mask[i] : 1; a.orig[i] = i;
+}
+// scatter back to LAMMPS local order (orig)
+__global__ void k_unpack_atoms(int n, HostMirror m, PackArrays a, int multiphase)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int i = a.orig[s];
+  double4 x = a.xt[s], vr = a.vr[s], v = a.vm[s], f = a.fd[s];
+  if (m.x) { m.x[3 * i] = x.x; m.x[3 * i + 1] = x.y; m.x[3 * i + 2] = x.z; }
+  if (m.v) { m.v[3 * i] = v.x; m.v[3 * i + 1] = v.y; m.v[3 * i + 2] = v.z; }
+  if (m.vest) { m.vest[3 * i] = vr.x; m.vest[3 * i + 1] = vr.y; m.vest[3 * i + 2] = vr.z; }
+  if (m.f) { m.f[3 * i] = f.x; m.f[3 * i + 1] = f.y; m.f[3 * i + 2] = f.z; }
+  if (m.cg) { double4 c = multiphase ? a.cgm[s] : make_double4(0, 0, 0, 0); m.cg[3 * i] = c.x; m.cg[3 * i + 1] = c.y; m.cg[3 * i + 2] = c.z; }
+  if (m.rho) m.rho[i] = vr.w;
+  if (m.drho) m.drho[i] = f.w;
+  if (m.e) m.e[i] = a.e[s];
+  if (m.de) m.de[i] = a.de[s];
+  if (m.cv) m.cv[i] = a.cv[s];
+  if (m.rmass) m.rmass[i] = v.w;
+  if (m.type) m.type[i] = tw_type(__double_as_longlong(x.w));
+  if (m.mask) m.mask[i] = a.mask[s];
+  if (m.tag) m.tag[i] = a.tag[s];
+}

@@ -7,8 +7,6 @@
 #include <algorithm>
 #include <cmath>
 
-static inline double ll_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
-static inline long long double_as_ll(double d) { long long v; memcpy(&v, &d, 8); return v; }
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return -1; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::string(#call) + ": " + cudaGetErrorString(e_); } while (0)
@@ -73,7 +71,8 @@ struct b200_sph {
   DevBuf<int> cellid, perm, perm2, gcount, gown, gimg, gcell, gperm, gperm2, gslot;
   DevBuf<unsigned long long> key, gkey;
   DevBuf<int> cso, csg, cellfill, scan_tmp;
-  DevBuf<double> xhold;
+  DevBuf<double> xhold, stage_d, d_mass;
+  DevBuf<int> stage_i;
   DevBuf<unsigned> nbr; DevBuf<int> numneigh; int stride = 32;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   bool setup_done = false, geom_ready = false;
@@ -555,7 +554,7 @@ int b200_destroy(b200_sph *h)
   h->S[0].release(); h->S[1].release(); h->dq.release(); h->gowner.release(); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
   h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
-  h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
+  h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
@@ -634,6 +633,29 @@ int b200_fix_meso_stationary(b200_sph *h, int groupbit) { return add_fix(h, 2, g
 int b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc) { return add_fix(h, 3, groupbit, xacc, yacc, zacc); }
 int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d) { (void)h; (void)d; return fail("b200_fix_phase_change: not implemented yet"); }
 
+// staging: the caller's AoS arrays are copied verbatim (DMA from pinned memory when the caller
+// pinned them) and converted to/from the packed device records by a kernel
+static HostMirror stage_layout(b200_sph *h, int n, const b200_atoms *a, size_t *nd_out, size_t *ni_out)
+{
+  // offsets first (so the buffers can be sized), then pointers
+  const size_t NONE = (size_t)-1;
+  size_t od = 0, oi = 0;
+  auto take = [&](const void *p, size_t &o, size_t w) { if (!p) return NONE; size_t r = o; o += w * (size_t)n; return r; };
+  size_t ox = take(a->x, od, 3), ov = take(a->v, od, 3), ove = take(a->vest, od, 3), of = take(a->f, od, 3), oc = take(a->colorgradient, od, 3);
+  size_t orho = take(a->rho, od, 1), odrho = take(a->drho, od, 1), oe = take(a->e, od, 1), ode = take(a->de, od, 1), ocv = take(a->cv, od, 1),
+         orm = take(a->rmass, od, 1);
+  size_t oty = take(a->type, oi, 1), oma = take(a->mask, oi, 1), ota = take(a->tag, oi, 1);
+  h->stage_d.ensure(od + 1); h->stage_i.ensure(oi + 1);
+  double *bd = h->stage_d.p; int *bi = h->stage_i.p;
+  auto D = [&](size_t o) { return o == NONE ? (double *)nullptr : bd + o; };
+  auto I = [&](size_t o) { return o == NONE ? (int *)nullptr : bi + o; };
+  HostMirror m{D(ox), D(ov), D(ove), D(of), D(oc), D(orho), D(odrho), D(oe), D(ode), D(ocv), D(orm), I(oty), I(oma), I(ota)};
+  *nd_out = od; *ni_out = oi;
+  return m;
+}
+static PackArrays pack_arrays(b200_sph *h) { OwnedSet &c = h->C(); return PackArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.cgm.p, c.e.p, c.de.p, c.cv.p, c.tag.p, c.mask.p, c.orig.p}; }
+#define FOR_FIELDS(X) X(x, x, 3) X(v, v, 3) X(vest, vest, 3) X(f, f, 3) X(cg, colorgradient, 3) X(rho, rho, 1) X(drho, drho, 1) X(e, e, 1) X(de, de, 1) X(cv, cv, 1) X(rmass, rmass, 1)
+
 int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
 {
   API_BEGIN
@@ -642,37 +664,23 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
   if (n > (int)NBR_INDEX_MASK / 2) throw std::string("b200_set_atoms: too many atoms for 30-bit neighbor indices");
   h->nlocal = n; h->nghost = 0; h->cur = 0;
   h->ensure_cap(n, false);
-  std::vector<double4> xt(n), vr(n), vm(n), fd(n), cgm(n);
-  std::vector<double> e(n), de(n), cv(n);
-  std::vector<int> tag(n), mask(n), orig(n);
-  for (int i = 0; i < n; i++) {
-    int t = a->type[i];
-    if (t < 1 || t > h->ntypes) throw std::string("b200_set_atoms: atom type out of range");
-    double m = a->rmass ? a->rmass[i] : h->mass[t];
-    if (!h->multiphase) m = h->mass[t];
-    const double *v = a->v ? a->v + 3 * i : nullptr, *ve = a->vest ? a->vest + 3 * i : v;
-    xt[i] = make_double4(a->x[3 * i], a->x[3 * i + 1], a->x[3 * i + 2], ll_as_double((long long)pack_tw(t, 0, 0, 0)));
-    vm[i] = make_double4(v ? v[0] : 0, v ? v[1] : 0, v ? v[2] : 0, m);
-    vr[i] = make_double4(ve ? ve[0] : 0, ve ? ve[1] : 0, ve ? ve[2] : 0, a->rho ? a->rho[i] : 0.0);
-    fd[i] = make_double4(a->f ? a->f[3 * i] : 0, a->f ? a->f[3 * i + 1] : 0, a->f ? a->f[3 * i + 2] : 0, a->drho ? a->drho[i] : 0.0);
-    const double *c = a->colorgradient ? a->colorgradient + 3 * i : nullptr;
-    cgm[i] = make_double4(c ? c[0] : 0, c ? c[1] : 0, c ? c[2] : 0, m);
-    e[i] = a->e ? a->e[i] : 0.0; de[i] = a->de ? a->de[i] : 0.0; cv[i] = a->cv ? a->cv[i] : 0.0;
-    tag[i] = a->tag ? a->tag[i] : i + 1; mask[i] = a->mask ? a->mask[i] : 1; orig[i] = i;
-  }
-  OwnedSet &c = h->C();
-  size_t n4 = (size_t)n * sizeof(double4), n1 = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
-  if (n) {
-    CK(cudaMemcpyAsync(c.xt.p, xt.data(), n4, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.vr.p, vr.data(), n4, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.vm.p, vm.data(), n4, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.fd.p, fd.data(), n4, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.cgm.p, cgm.data(), n4, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.e.p, e.data(), n1, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.de.p, de.data(), n1, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.cv.p, cv.data(), n1, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.tag.p, tag.data(), ni, cudaMemcpyHostToDevice, h->st)); CK(cudaMemcpyAsync(c.mask.p, mask.data(), ni, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(c.orig.p, orig.data(), ni, cudaMemcpyHostToDevice, h->st));
-    CK(cudaStreamSynchronize(h->st));
-  }
   h->setup_done = false;
+  if (!n) return 0;
+  size_t nd, ni;
+  HostMirror m = stage_layout(h, n, a, &nd, &ni);
+#define UP(dev, host, w) if (a->host) CK(cudaMemcpyAsync(m.dev, a->host, (size_t)(w) * n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  FOR_FIELDS(UP)
+#undef UP
+  if (a->type) CK(cudaMemcpyAsync(m.type, a->type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  if (a->mask) CK(cudaMemcpyAsync(m.mask, a->mask, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  if (a->tag) CK(cudaMemcpyAsync(m.tag, a->tag, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  h->d_mass.ensure(MAXT1);
+  CK(cudaMemcpyAsync(h->d_mass.p, h->mass, sizeof h->mass, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+  LAUNCH(h, k_pack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase, h->d_mass.p, h->ntypes, h->d_flags + 2);
+  CK(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (h->h_flags[2]) throw std::string("b200_set_atoms: atom type out of range");
   API_END
 }
 int b200_get_natoms(b200_sph *h, int *nlocal, int *nghost) { if (nlocal) *nlocal = h->nlocal; if (nghost) *nghost = h->nghost; return 0; }
@@ -684,37 +692,16 @@ int b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a)
   int n = h->nlocal;
   if (n > nmax) throw std::string("b200_get_atoms: buffer too small");
   if (!n) return 0;
-  OwnedSet &c = h->C();
-  std::vector<double4> xt(n), vr(n), vm(n), fd(n), cgm(n);
-  std::vector<double> e(n), de(n), cv(n);
-  std::vector<int> tag(n), mask(n), orig(n);
-  size_t n4 = (size_t)n * sizeof(double4), n1 = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+  size_t nd, ni;
+  HostMirror m = stage_layout(h, n, a, &nd, &ni);
+  LAUNCH(h, k_unpack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase);
+#define DOWN(dev, host, w) if (a->host) CK(cudaMemcpyAsync(a->host, m.dev, (size_t)(w) * n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  FOR_FIELDS(DOWN)
+#undef DOWN
+  if (a->type) CK(cudaMemcpyAsync(a->type, m.type, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (a->mask) CK(cudaMemcpyAsync(a->mask, m.mask, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (a->tag) CK(cudaMemcpyAsync(a->tag, m.tag, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  CK(cudaMemcpy(xt.data(), c.xt.p, n4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(vr.data(), c.vr.p, n4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(vm.data(), c.vm.p, n4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fd.data(), c.fd.p, n4, cudaMemcpyDeviceToHost));
-  if (h->multiphase) CK(cudaMemcpy(cgm.data(), c.cgm.p, n4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(e.data(), c.e.p, n1, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(de.data(), c.de.p, n1, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(cv.data(), c.cv.p, n1, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(tag.data(), c.tag.p, ni, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(mask.data(), c.mask.p, ni, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(orig.data(), c.orig.p, ni, cudaMemcpyDeviceToHost));
-  for (int s = 0; s < n; s++) {
-    int i = orig[s];
-    if (i < 0 || i >= n) throw std::string("b200_get_atoms: corrupt index map");
-    if (a->x) { a->x[3 * i] = xt[s].x; a->x[3 * i + 1] = xt[s].y; a->x[3 * i + 2] = xt[s].z; }
-    if (a->v) { a->v[3 * i] = vm[s].x; a->v[3 * i + 1] = vm[s].y; a->v[3 * i + 2] = vm[s].z; }
-    if (a->vest) { a->vest[3 * i] = vr[s].x; a->vest[3 * i + 1] = vr[s].y; a->vest[3 * i + 2] = vr[s].z; }
-    if (a->f) { a->f[3 * i] = fd[s].x; a->f[3 * i + 1] = fd[s].y; a->f[3 * i + 2] = fd[s].z; }
-    if (a->colorgradient) { a->colorgradient[3 * i] = h->multiphase ? cgm[s].x : 0; a->colorgradient[3 * i + 1] = h->multiphase ? cgm[s].y : 0; a->colorgradient[3 * i + 2] = h->multiphase ? cgm[s].z : 0; }
-    if (a->rho) a->rho[i] = vr[s].w;
-    if (a->drho) a->drho[i] = fd[s].w;
-    if (a->e) a->e[i] = e[s];
-    if (a->de) a->de[i] = de[s];
-    if (a->cv) a->cv[i] = cv[s];
-    if (a->rmass) a->rmass[i] = vm[s].w;
-    if (a->type) a->type[i] = tw_type((unsigned long long)double_as_ll(xt[s].w));
-    if (a->mask) a->mask[i] = mask[s];
-    if (a->tag) a->tag[i] = tag[s];
-  }
   API_END
 }
 
