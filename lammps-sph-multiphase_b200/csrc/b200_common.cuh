@@ -15,8 +15,11 @@
 #define MAXFIX 16
 #define WARP 32
 #define FULLMASK 0xffffffffu
-#define NBR_OWNER_BIT 0x80000000u   // entry bit: the row particle is the half-list owner of this pair
-#define NBR_INDEX_MASK 0x3fffffffu  // same 30-bit limit as the reference (src/lmptype.h:58-59)
+// neighbor entry: [31] the row particle is the half-list owner of this pair, [30:28] type of j, [27:0] index of j
+// (the reference reserves the top 2 bits of its int32 entries the same way, src/lmptype.h:58-59)
+#define NBR_OWNER_BIT 0x80000000u
+#define NBR_TYPE_SHIFT 28
+#define NBR_INDEX_MASK 0x0fffffffu
 
 // force-pass kinds (bit flags of the fused force kernel)
 enum { K_TAIT = 1, K_MORRIS = 2, K_TAITMP = 4, K_SURF = 8, K_HEAT = 16, K_HEATMP = 32, K_HEATPC = 64 };

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
       if (valid) { double4 p = A.xt[i]; xi = p.x; yi = p.y; zi = p.z; wi = (unsigned long long)__double_as_longlong(p.w); if (!pass) oi = A.orig[i]; }
       int ti = tw_type(wi), bxi = tw_bx(wi), byi = tw_by(wi), bzi = tw_bz(wi);
       int cnt = 0;
-      unsigned *row = A.nbr + (size_t)i * A.stride;
+      unsigned *row = A.nbr + (size_t)(i >> 5) * A.stride * 32 + (i & 31);   // rows interleaved by 32 (see b200_pair.cuh)
       int fill = 0;
 
       auto process = [&](int n) {
@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
             unsigned ent;
             if (!pass) {
               bool own = (j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj);
-              ent = (unsigned)j | (own ? NBR_OWNER_BIT : 0u);
+              ent = (unsigned)j | ((unsigned)tw_type(wj) << NBR_TYPE_SHIFT) | (own ? NBR_OWNER_BIT : 0u);
             } else {
               if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
-              ent = (unsigned)j | NBR_OWNER_BIT;
+              ent = (unsigned)j | ((unsigned)tw_type(wj) << NBR_TYPE_SHIFT) | NBR_OWNER_BIT;
             }
-            if (cnt < A.stride) row[cnt] = ent;
+            if (cnt < A.stride) row[(size_t)cnt * 32] = ent;
             cnt++;
           }
         }

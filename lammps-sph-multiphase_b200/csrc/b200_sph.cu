@@ -13,9 +13,9 @@ static int fail(const std::string &m) { g_err = m; return -1; }
 #define API_BEGIN try {
 #define API_END } catch (const std::string &m) { return fail(m); } catch (const std::exception &e) { return fail(e.what()); } return 0;
 
-enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_NTIMERS };
+enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_PRUNE, T_NTIMERS };
 static const char *timer_names[T_NTIMERS] = {"initial_integrate", "forward_comm", "neigh_bin_sort_ghost", "neigh_build", "density",
-                                             "colorgradient", "derive", "force", "reverse_post_final", "phase_change"};
+                                             "colorgradient", "records", "force", "reverse_post_final", "phase_change", "prune"};
 
 template <class T> struct DevBuf {
   T *p = nullptr; size_t cap = 0;
@@ -66,14 +66,16 @@ struct b200_sph {
   // particles
   int nlocal = 0, nghost = 0;
   OwnedSet S[2]; int cur = 0;
-  DevBuf<double4> dq;
+  DevBuf<double4> rec;
   DevBuf<int> gowner, gimage;
   DevBuf<int> cellid, perm, perm2, gcount, gown, gimg, gcell, gperm, gperm2, gslot;
   DevBuf<unsigned long long> key, gkey;
   DevBuf<int> cso, csg, cellfill, scan_tmp;
   DevBuf<double> xhold, stage_d, d_mass;
   DevBuf<int> stage_i;
-  DevBuf<unsigned> nbr; DevBuf<int> numneigh; int stride = 32;
+  DevBuf<unsigned> nbr, act; DevBuf<int> numneigh, nact; int stride = 32;
+  bool pruned = false; long long pruned_step = -1;
+  DevBuf<double> d_prunesq;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   bool setup_done = false, geom_ready = false;
   // instrumentation
@@ -87,8 +89,8 @@ struct b200_sph {
   void ensure_cap(size_t n, bool keep)
   {
     S[0].ensure(n, keep && cur == 0, st); S[1].ensure(n, keep && cur == 1, st);
-    dq.ensure(n, false, st); gowner.ensure(n, false, st); gimage.ensure(n, false, st);
-    numneigh.ensure(n, false, st);
+    rec.ensure(n * 4, false, st); gowner.ensure(n, false, st); gimage.ensure(n, false, st);
+    numneigh.ensure(n, false, st); nact.ensure(n, false, st);
   }
   StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p}; }
   GhostArrays ghost_arrays() { OwnedSet &c = C(); return GhostArrays{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.tag.p, c.mask.p, gowner.p, gimage.p}; }
@@ -120,7 +122,15 @@ struct b200_sph {
   }
 };
 
-#define LAUNCH(h, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (h)->st>>>(__VA_ARGS__); (h)->launches++; } while (0)
+static const bool g_sync_debug = getenv("B200_SYNC_DEBUG") != nullptr;   // synchronise + check after every launch
+static void post_launch(b200_sph *h, const char *name)
+{
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && g_sync_debug) e = cudaStreamSynchronize(h->st);
+  if (e != cudaSuccess) throw std::string(name) + ": " + cudaGetErrorString(e);
+}
+#define LAUNCH(h, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (h)->st>>>(__VA_ARGS__); post_launch(h, #kern); } while (0)
 static inline int nblk(long long n, int b) { return (int)std::max<long long>(1, (n + b - 1) / b); }
 
 // ------------------------------------------------------------------ scan ----
@@ -240,7 +250,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   h->tbegin(T_NEIGH_BUILD);
   int na = h->nall();
   for (int attempt = 0; attempt < 8 && na; attempt++) {
-    h->nbr.ensure((size_t)na * h->stride);
+    h->nbr.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
     BuildArgs A;
     A.g = g; A.nlocal = nl; A.nghost = h->nghost; A.stride = h->stride; A.ntypes1 = h->ntypes + 1;
@@ -256,7 +266,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     if (attempt == 7) throw std::string("b200: neighbor row overflow");
   }
   h->tend();
-  h->ago = 0; h->nbuilds++;
+  h->ago = 0; h->nbuilds++; h->pruned_step = -1;
 }
 
 // ------------------------------------------------------------- pair plan ----
@@ -283,6 +293,11 @@ static bool fusable(int kinds)
 static void build_plan(b200_sph *h)
 {
   h->plan.clear();
+  double psq[MAXTT];
+  for (int k = 0; k < MAXTT; k++) { psq[k] = -1.0; for (int s = 0; s < h->npair; s++) psq[k] = std::max(psq[k], h->h_tab[s].cutsq[k]); }
+  h->d_prunesq.ensure(MAXTT);
+  CK(cudaMemcpyAsync(h->d_prunesq.p, psq, sizeof psq, cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
   int k = 0;
   while (k < h->npair) {
     int st = h->h_tab[k].style;
@@ -301,68 +316,81 @@ static void build_plan(b200_sph *h)
   }
 }
 
+// rows the stage kernels walk this step: the Verlet rows, or (skin > 0) their per-step pruned copy
+static void ensure_pruned(b200_sph *h)
+{
+  if (!(h->skin > 0.0) || !h->nall()) { h->pruned = false; return; }
+  if (h->pruned_step == h->ntimestep && h->pruned) return;
+  int na = h->nall();
+  h->tbegin(T_PRUNE);
+  h->act.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
+  LAUNCH(h, k_prune, nblk(na, PAIR_THREADS), PAIR_THREADS, na, h->stride, h->C().xt.p, h->nbr.p, h->numneigh.p, h->d_prunesq.p, h->act.p, h->nact.p);
+  h->tend();
+  h->pruned = true; h->pruned_step = h->ntimestep;
+}
 static PairArgs pair_args(b200_sph *h)
 {
   PairArgs A{};
   OwnedSet &c = h->C();
-  A.nlocal = h->nlocal; A.nall = h->nall(); A.stride = h->stride; A.dim = h->g.dim; A.multiphase = h->multiphase;
-  A.nbr = h->nbr.p; A.numneigh = h->numneigh.p;
-  A.xt = c.xt.p; A.vr = c.vr.p; A.vm = c.vm.p; A.cgm = c.cgm.p; A.dq = h->dq.p; A.e = c.e.p; A.cv = c.cv.p;
+  A.nlocal = h->nlocal; A.nall = h->nall(); A.stride = h->stride; A.dim = h->g.dim; A.multiphase = h->multiphase; A.nrec = 1;
+  A.list = h->pruned ? h->act.p : h->nbr.p; A.cnt = h->pruned ? h->nact.p : h->numneigh.p;
+  A.xt = c.xt.p; A.vr = c.vr.p; A.vm = c.vm.p; A.cgm = c.cgm.p; A.rec = h->rec.p; A.e = c.e.p; A.cv = c.cv.p;
   A.vr_out = c.vr.p; A.cg_out = c.cgm.p; A.fd = c.fd.p; A.de = c.de.p;
   return A;
-}
-static int pair_grid(b200_sph *h, int rows)
-{
-  int need = nblk(rows, PAIR_WARPS);
-  return std::min(need, 148 * 8);       // persistent-ish: a multiple of the SM count, rows strided over the warps
 }
 
 template <int KINDS> static void launch_force(b200_sph *h, PairArgs &A)
 {
-  int grid = pair_grid(h, A.nall);
-  if (h->g.dim == 3) k_force<KINDS, true><<<grid, PAIR_WARPS * 32, 0, h->st>>>(A);
-  else k_force<KINDS, false><<<grid, PAIR_WARPS * 32, 0, h->st>>>(A);
-  h->launches++;
+  int grid = nblk(A.nall, PAIR_THREADS);
+  if (h->g.dim == 3) k_force<KINDS, true><<<grid, PAIR_THREADS, 0, h->st>>>(A);
+  else k_force<KINDS, false><<<grid, PAIR_THREADS, 0, h->st>>>(A);
+  post_launch(h, "k_force");
 }
 
 static void run_pass(b200_sph *h, const Pass &p)
 {
   if (!h->nlocal) return;
-  PairArgs A = pair_args(h);
   const int B = 256;
   if (p.type <= 2) {
     const PairTab &T = h->h_tab[p.slots[0]];
-    A.tab[0] = h->d_tab[p.slots[0]];
     bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
-    int grid = pair_grid(h, A.nlocal);
+    if (active) ensure_pruned(h);
+    PairArgs A = pair_args(h);
+    A.tab[0] = h->d_tab[p.slots[0]];
+    int grid = nblk(A.nlocal, PAIR_THREADS);
     if (p.type == 0) {
       h->tbegin(T_DENSITY);
-      if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_WARPS * 32, A);
+      if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_THREADS, A);
       if (h->nghost) LAUNCH(h, k_ghost_rho, nblk(h->nghost, B), B, h->nlocal, h->nghost, h->gowner.p, h->C().vr.p);  // forward_comm_pair (:203)
       h->tend();
     } else if (p.type == 1) {
       h->tbegin(T_DENSITY);
-      if (active) LAUNCH(h, k_rhosum<true>, grid, PAIR_WARPS * 32, A);
+      if (active) LAUNCH(h, k_rhosum<true>, grid, PAIR_THREADS, A);
       h->tend();
     } else if (active) {
       h->tbegin(T_DERIVE);
-      LAUNCH(h, k_derive, nblk(A.nall, B), B, A.nall, 1, (const PairTab *)nullptr, A.xt, A.vr, A.cgm, A.e, A.cv, h->dq.p);
+      LAUNCH(h, k_records, nblk(A.nall, B), B, A.nall, 2, 1, 0, (const PairTab *)nullptr, A.xt, A.vr, A.cgm, A.e, A.cv, h->rec.p);
       h->tend();
       h->tbegin(T_COLORGRAD);
-      LAUNCH(h, k_colorgradient, grid, PAIR_WARPS * 32, A);
+      LAUNCH(h, k_colorgradient, grid, PAIR_THREADS, A);
       h->tend();
     }
     return;
   }
   // force pass: canonical table order fluid, surf, heat
+  ensure_pruned(h);
+  PairArgs A = pair_args(h);
   int nk = 0; const PairTab *fluid = nullptr;
   const int wants[3] = {K_TAIT | K_MORRIS | K_TAITMP, K_SURF, K_HEAT | K_HEATMP | K_HEATPC};
   for (int want : wants)
     for (int s = 0; s < p.nslots; s++)
       if (kind_of(h->h_tab[p.slots[s]].style) & want) { A.tab[nk++] = h->d_tab[p.slots[s]]; if (want & K_TAIT) fluid = h->d_tab[p.slots[s]]; }
+  bool mp = (p.kinds & (K_TAITMP | K_SURF | K_HEATMP | K_HEATPC)) != 0;
+  int nrec = mp ? 4 : (((p.kinds & K_HEAT) && fluid) ? 3 : 2);
   h->tbegin(T_DERIVE);
-  LAUNCH(h, k_derive, nblk(A.nall, B), B, A.nall, h->multiphase, fluid, A.xt, A.vr, A.cgm, A.e, A.cv, h->dq.p);
+  LAUNCH(h, k_records, nblk(A.nall, B), B, A.nall, mp ? 1 : 0, nrec, (!mp && !fluid) ? 1 : 0, fluid, A.xt, A.vr, A.cgm, A.e, A.cv, h->rec.p);
   h->tend();
+  A.nrec = nrec;
   h->tbegin(T_FORCE);
   switch (p.kinds) {
   case K_TAIT: launch_force<K_TAIT>(h, A); break;
@@ -551,7 +579,7 @@ int b200_destroy(b200_sph *h)
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  h->S[0].release(); h->S[1].release(); h->dq.release(); h->gowner.release(); h->gimage.release();
+  h->S[0].release(); h->S[1].release(); h->rec.release(); h->act.release(); h->nact.release(); h->d_prunesq.release(); h->gowner.release(); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
   h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
@@ -748,12 +776,12 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   CK(cudaMemcpy(tag.data(), h->C().tag.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
   if (h->nghost) CK(cudaMemcpy(img.data() + n, h->gimage.p + n, (size_t)h->nghost * sizeof(int), cudaMemcpyDeviceToHost));
   for (int s = 0; s < n; s++) img[s] = 13;
-  std::vector<unsigned> rows((size_t)n * h->stride);
+  std::vector<unsigned> rows((size_t)((n + 31) / 32) * 32 * h->stride);
   CK(cudaMemcpy(rows.data(), h->nbr.p, rows.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
   std::vector<std::pair<int, int>> tmp;
   for (int s = 0; s < n; s++) {
     tmp.clear();
-    for (int k = 0; k < cnt[s]; k++) { int j = rows[(size_t)s * h->stride + k] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]}); }
+    for (int k = 0; k < cnt[s]; k++) { int j = rows[(size_t)(s >> 5) * h->stride * 32 + (size_t)k * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]}); }
     std::sort(tmp.begin(), tmp.end());
     long long o = off[orig[s]];
     for (int k = 0; k < cnt[s]; k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
