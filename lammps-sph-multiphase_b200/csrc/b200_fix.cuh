@@ -27,7 +27,7 @@ __global__ void k_setup_pre_force(int nlocal, FixList fl, StepArrays a)
 // FixMesoStationary::initial_integrate (fix_meso_stationary.cpp:71-92), fixes in deck order;
 // plus Neighbor::check_distance's per-atom test (neighbor.cpp:1396-1404) on the new positions.
 __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double dtv, double dtf, int check,
-                                    const double *xhold, double triggersq, int *flag)
+                                    const double *xhold, double triggersq, int *flag, int track, unsigned long long *dmaxsq)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
@@ -50,11 +50,19 @@ __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double
   }
   if (touched) { a.e[i] = e; a.vr[i] = vr; }
   if (moved) { a.vm[i] = v; a.xt[i] = x; }
-  if (check) {
+  if (check || track) {
     double dx = x.x - xhold[3 * i], dy = x.y - xhold[3 * i + 1], dz = x.z - xhold[3 * i + 2];
-    if (dx * dx + dy * dy + dz * dz > triggersq) *flag = 1;
+    double dsq = dx * dx + dy * dy + dz * dz;
+    if (check && dsq > triggersq) *flag = 1;
+    if (track && moved) {      // largest displacement since the build (non-negative doubles order like their bit patterns)
+      unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
+      if (b > *(volatile unsigned long long *)dmaxsq) atomicMax(dmaxsq, b);
+    }
   }
 }
+// far rows must be scanned once 2*dmax >= margin  (b200_neigh.cuh k_build)
+__global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, int *scan_far)
+{ *scan_far = 4.0 * __longlong_as_double((long long)*dmaxsq) >= 0.99 * marginsq; }
 
 // comm->reverse_comm (comm_brick.cpp:513-560: f, drho, de of ghosts added to their owners), then
 // modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate

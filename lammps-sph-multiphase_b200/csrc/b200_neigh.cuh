@@ -280,6 +280,9 @@ struct BuildArgs {
   const int *orig;
   const int *cso, *csg;          // cell starts: owned / ghost (ghost offsets relative to nlocal)
   const double *cutneighsq;      // [MAXTT]
+  const double *prunesq;         // [MAXTT] max over the sub-styles of cutsq(ti,tj): splits a row into an inner and an outer zone
+  const double *farsq;           // [MAXTT] (cut + margin)^2: entries beyond go to the far rows (see FAR_MARGIN_FRAC)
+  unsigned *far; int *numfar;
   unsigned *nbr;
   int *numneigh;
   int *maxcount;
@@ -299,6 +302,7 @@ __device__ __forceinline__ bool ghost_above(double xi, double yi, double zi, dou
 // One warp per engine cell.  Each lane owns one row particle; the candidates of the
 // 3x3x3 stencil are staged through shared memory in chunks and read back as
 // broadcasts (one wavefront per 32 pair tests); hits are collected as 32-bit masks.
+// Row entries k = 0..n_in-1 (inner zone) and k = stride-1 .. stride-n_out (outer zone); numneigh = n_in | n_out << 16.
 // Rows [0,nlocal): Neighbor::full_bin's list of the owned atom (rsq <= cutneighsq, and
 // j inside the reference's own bin stencil), each entry tagged with the half-list
 // ownership bit frozen at build time.  Rows [nlocal,nall): for a ghost g, the owned
@@ -307,8 +311,8 @@ __device__ __forceinline__ bool ghost_above(double xi, double yi, double zi, dou
 __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
 {
   __shared__ BuildSmem sm_all[BUILD_WARPS];
-  __shared__ double s_cut[MAXTT];
-  for (int k = threadIdx.x; k < MAXTT; k += blockDim.x) s_cut[k] = A.cutneighsq[k];
+  __shared__ double s_cut[MAXTT], s_in[MAXTT], s_far[MAXTT];
+  for (int k = threadIdx.x; k < MAXTT; k += blockDim.x) { s_cut[k] = A.cutneighsq[k]; s_in[k] = A.prunesq[k]; s_far[k] = A.farsq[k]; }
   __syncthreads();
   const Geom &g = A.g;
   int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,7 +333,8 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
       unsigned long long wi = 0; int oi = 0;
       if (valid) { double4 p = A.xt[i]; xi = p.x; yi = p.y; zi = p.z; wi = (unsigned long long)__double_as_longlong(p.w); if (!pass) oi = A.orig[i]; }
       int ti = tw_type(wi), bxi = tw_bx(wi), byi = tw_by(wi), bzi = tw_bz(wi);
-      int cnt = 0;
+      int cnt = 0, cin = 0, cout = 0, cfar = 0;
+      unsigned *frow = A.far + (size_t)(i >> 5) * A.stride * 32 + (i & 31);
       unsigned *row = A.nbr + (size_t)(i >> 5) * A.stride * 32 + (i & 31);   // rows interleaved by 32 (see b200_pair.cuh)
       int fill = 0;
 
@@ -349,7 +354,8 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
             unsigned long long wj = sm.w[idx];
             double xj = sm.x[idx], yj = sm.y[idx], zj = sm.z[idx];
             double rsq = rsq_nofma(xi - xj, yi - yj, zi - zj);
-            if (!(rsq <= s_cut[ti * MAXT1 + tw_type(wj)])) continue;
+            int tij = ti * MAXT1 + tw_type(wj);
+            if (!(rsq <= s_cut[tij])) continue;
             // j must sit in a bin of the reference's stencil around i's bin (neigh_stencil.cpp:434-448)
             int dbx = abs(tw_bx(wj) - bxi), dby = abs(tw_by(wj) - byi), dbz = abs(tw_bz(wj) - bzi);
             if (dbx > g.sx || dby > g.sy || dbz > g.sz) continue;
@@ -364,8 +370,20 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
               if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
               ent = (unsigned)j | ((unsigned)tw_type(wj) << NBR_TYPE_SHIFT) | NBR_OWNER_BIT;
             }
-            if (cnt < A.stride) row[(size_t)cnt * 32] = ent;
-            cnt++;
+            // inner zone (inside the pair cutoff now): filled from the front; outer zone (skin shell, or
+            // exactly on the cutoff): filled from the back.  The stage kernels test every entry each step,
+            // but hits and misses are clustered, so their warps do not diverge on the heavy pair body.
+            // Far rows: entries at least `margin` outside the cutoff.  They cannot come inside before some
+            // particle has moved margin/2 since the build, which the integrator tracks (dmaxsq), so the
+            // stage kernels skip them -- provably without changing any result -- until that happens.
+            if (rsq >= s_far[tij]) { if (cfar < A.stride) frow[(size_t)cfar * 32] = ent; cfar++; }
+            else {
+              if (cin + cout < A.stride) {
+                if (rsq < s_in[tij]) { row[(size_t)cin * 32] = ent; cin++; }
+                else { row[(size_t)(A.stride - 1 - cout) * 32] = ent; cout++; }
+              }
+              cnt++;
+            }
           }
         }
       };
@@ -395,7 +413,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
         }
       }
       if (fill) { __syncwarp(); process(fill); __syncwarp(); }
-      if (valid) { A.numneigh[i] = cnt; if (cnt > A.stride) atomicMax(A.maxcount, cnt); else atomicMax(A.maxcount + 1, cnt); }
+      if (valid) { A.numneigh[i] = cin | (cout << 16); A.numfar[i] = cfar; atomicMax(A.maxcount, max(cnt, cfar)); }
     }
   }
 }

@@ -11,8 +11,10 @@
 //   * gathers ONE contiguous record per neighbor (64 B single-phase, 128 B multiphase, written by
 //     k_records just before the pass) with 256-bit loads (LDG.E.ENL2.256 on sm_100a) instead of
 //     3-4 separate 32-byte arrays;
-//   * walks a per-step pruned copy of the Verlet list (k_prune: strict rsq < max cutsq) whenever
-//     the skin is non-zero, so no lane idles on a list entry that is outside the cutoff;
+//   * walks rows that k_build split into an inner zone (inside the pair cutoff at build time) and an
+//     outer zone (skin shell / exactly on the cutoff): every entry is still tested each step, but hits
+//     and misses are clustered, so a warp does not diverge on the heavy pair body (a per-step pruned
+//     copy of the list was tried first: its scattered 4-byte stores cost as much as the force pass);
 //   * keeps the partial sums of a particle in one thread: no shuffles, no atomics, and a summation
 //     order that is a pure function of the row.
 // The type of j travels in the list entry (3 bits), so the tests need no second gather.
@@ -79,8 +81,8 @@ __device__ __forceinline__ double quintic_dw(double q)
 
 struct PairArgs {
   int nlocal, nall, stride, dim, multiphase, nrec;
-  const unsigned *list;        // rows to walk (Verlet rows or the pruned copy)
-  const int *cnt;
+  const unsigned *list, *far;  // near rows (inner + outer zone) and far rows
+  const int *cnt, *numfar, *scan_far;
   const double4 *xt, *vr, *vm, *cgm;
   const double *e, *cv;
   double4 *rec;                // gather records, nrec double4 per particle
@@ -89,36 +91,29 @@ struct PairArgs {
   const PairTab *tab[4];
 };
 
-// ------------------------------------------------------------------- prune ---
-// per-step copy of the Verlet rows restricted to rsq < max_substyle cutsq(ti,tj) (strict, as every
-// PairSPH*::compute tests it).  The order of the surviving entries is unchanged.
-__global__ void __launch_bounds__(PAIR_THREADS) k_prune(int nall, int stride, const double4 *__restrict__ xt, const unsigned *__restrict__ nbr,
-                                                        const int *__restrict__ numneigh, const double *__restrict__ prunesq, unsigned *act, int *nact)
-{
-  __shared__ double s_cut[MAXTT];
-  for (int k = threadIdx.x; k < MAXTT; k += blockDim.x) s_cut[k] = prunesq[k];
-  __syncthreads();
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = row < nall;
-  int n = valid ? numneigh[row] : 0;
-  int nmax = warp_max(n);
-  if (!nmax) { if (valid) nact[row] = 0; return; }
-  double4 pi = valid ? xt[row] : make_double4(0, 0, 0, 0);
-  const double *cutrow = &s_cut[tw_type(__double_as_longlong(pi.w)) * MAXT1];
-  const unsigned *p = row_base(nbr, row, stride);
-  unsigned *q = act + (size_t)(row >> 5) * stride * 32 + (row & 31);
-  int m = 0;
-#pragma unroll 4
-  for (int k = 0; k < nmax; k++) {
-    if (k < n) {
-      unsigned ent = __ldg(p + (size_t)k * 32);
-      double4 pj = ld256(xt + (ent & NBR_INDEX_MASK));
-      double rsq = rsq_nofma(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-      if (rsq < cutrow[(ent >> NBR_TYPE_SHIFT) & 7]) { q[(size_t)m * 32] = ent; m++; }
-    }
+// ---- walking a row: inner zone front to back, then the outer zone (k_build) ----
+struct RowIter {
+  const unsigned *p, *pf; int n_in, n_out, n_far, m_in, m_near, m_tot, last;
+  __device__ __forceinline__ RowIter(const unsigned *list, const int *cnt, const unsigned *far, const int *numfar, const int *scan_far,
+                                     int row, int stride, bool valid)
+  {
+    int c = valid ? cnt[row] : 0;
+    n_in = c & 0xffff; n_out = c >> 16;
+    n_far = (valid && *scan_far) ? numfar[row] : 0;      // far rows only once a particle has moved margin/2 since the build
+    m_in = warp_max(n_in); m_near = m_in + warp_max(n_out); m_tot = m_near + warp_max(n_far);
+    p = row_base(list, row, stride); pf = row_base(far, row, stride); last = stride - 1;
   }
-  if (valid) nact[row] = m;
-}
+  // entry of step k (0 <= k < m_tot), or false if this lane has none at that step
+  __device__ __forceinline__ bool get(int k, unsigned &ent) const
+  {
+    const unsigned *q; bool has;
+    if (k < m_in) { q = p + (size_t)k * 32; has = k < n_in; }
+    else if (k < m_near) { q = p + (size_t)(last - (k - m_in)) * 32; has = k - m_in < n_out; }
+    else { q = pf + (size_t)(k - m_near) * 32; has = k - m_near < n_far; }
+    if (has) ent = __ldg(q);
+    return has;
+  }
+};
 
 // ------------------------------------------------------------------ density --
 // MP=false: PairSPHRhoSum::compute            pair_sph_rhosum.cpp:112-197   (quadric kernel, per-type mass)
@@ -134,15 +129,13 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_rhosum(PairArgs A)
   double4 pi = valid ? A.xt[row] : make_double4(0, 0, 0, 0);
   int ti = tw_type(__double_as_longlong(pi.w));
   if (valid && T.iskip[ti]) valid = false;           // atoms of skipped types keep their integrated rho
-  int n = valid ? A.cnt[row] : 0;
-  int nmax = warp_max(n);
-  if (!nmax && !valid) return;
-  const unsigned *p = row_base(A.list, row, A.stride);
+  RowIter it(A.list, A.cnt, A.far, A.numfar, A.scan_far, row, A.stride, valid);
+  if (!it.m_tot && !valid) return;
   double acc = 0.0;
 #pragma unroll 4
-  for (int k = 0; k < nmax; k++) {
-    if (k < n) {
-      unsigned ent = __ldg(p + (size_t)k * 32);
+  for (int k = 0; k < it.m_tot; k++) {
+    unsigned ent;
+    if (it.get(k, ent)) {
       double4 pj = ld256(A.xt + (ent & NBR_INDEX_MASK));
       int tj = (ent >> NBR_TYPE_SHIFT) & 7, ij = ti * MAXT1 + tj;
       double rsq = rsq_nofma(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
@@ -219,15 +212,13 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_colorgradient(PairArgs A)
   double4 pi = valid ? A.xt[row] : make_double4(0, 0, 0, 0);
   int ti = tw_type(__double_as_longlong(pi.w));
   if (valid && T.iskip[ti]) valid = false;
-  int n = valid ? A.cnt[row] : 0;
-  int nmax = warp_max(n);
-  if (!nmax && !valid) return;
-  const unsigned *p = row_base(A.list, row, A.stride);
+  RowIter it(A.list, A.cnt, A.far, A.numfar, A.scan_far, row, A.stride, valid);
+  if (!it.m_tot && !valid) return;
   double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll 2
-  for (int k = 0; k < nmax; k++) {
-    if (k < n) {
-      unsigned ent = __ldg(p + (size_t)k * 32);
+  for (int k = 0; k < it.m_tot; k++) {
+    unsigned ent;
+    if (it.get(k, ent)) {
       double4 pj = ld256(A.rec + (ent & NBR_INDEX_MASK));
       int ij = ti * MAXT1 + ((ent >> NBR_TYPE_SHIFT) & 7);
       double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
@@ -277,9 +268,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_force(PairArgs A)
 
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = row < A.nall;
-  int n = valid ? A.cnt[row] : 0;
-  int nmax = warp_max(n);
-  if (!nmax) return;                                 // fd / de of these rows stay as force_clear left them
+  RowIter it(A.list, A.cnt, A.far, A.numfar, A.scan_far, row, A.stride, valid);
+  if (!it.m_tot) return;                             // fd / de of these rows stay as force_clear left them
   const bool ghostrow = row >= A.nlocal;
   const double4 *ri = A.rec + (size_t)(valid ? row : 0) * NREC;
   double4 p0 = ri[0], p1 = ri[1], p2 = make_double4(0, 0, 0, 0), p3 = p2;
@@ -289,12 +279,11 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_force(PairArgs A)
   const double rhoi = p0.w;
   const double mi = MP ? p3.z : T[0].mass[ti];
   double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
-  const unsigned *p = row_base(A.list, row, A.stride);
 
 #pragma unroll 2
-  for (int k = 0; k < nmax; k++) {
-    if (k >= n) continue;
-    unsigned ent = __ldg(p + (size_t)k * 32);
+  for (int k = 0; k < it.m_tot; k++) {
+    unsigned ent;
+    if (!it.get(k, ent)) continue;
     int j = ent & NBR_INDEX_MASK;
     if (!ghostrow && j >= A.nlocal && !(ent & NBR_OWNER_BIT)) continue;     // the other side owns this ghost pair
     const bool row_owns = ghostrow ? false : ((ent & NBR_OWNER_BIT) != 0);   // is the row particle the reference's "i" of this pair?

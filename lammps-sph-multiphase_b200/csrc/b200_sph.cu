@@ -15,7 +15,7 @@ static int fail(const std::string &m) { g_err = m; return -1; }
 
 enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_PRUNE, T_NTIMERS };
 static const char *timer_names[T_NTIMERS] = {"initial_integrate", "forward_comm", "neigh_bin_sort_ghost", "neigh_build", "density",
-                                             "colorgradient", "records", "force", "reverse_post_final", "phase_change", "prune"};
+                                             "colorgradient", "records", "force", "reverse_post_final", "phase_change", "unused"};
 
 template <class T> struct DevBuf {
   T *p = nullptr; size_t cap = 0;
@@ -73,9 +73,9 @@ struct b200_sph {
   DevBuf<int> cso, csg, cellfill, scan_tmp;
   DevBuf<double> xhold, stage_d, d_mass;
   DevBuf<int> stage_i;
-  DevBuf<unsigned> nbr, act; DevBuf<int> numneigh, nact; int stride = 32;
-  bool pruned = false; long long pruned_step = -1;
-  DevBuf<double> d_prunesq;
+  DevBuf<unsigned> nbr, far; DevBuf<int> numneigh, numfar; int stride = 32;
+  DevBuf<double> d_prunesq, d_farsq; double far_margin = 0.0;
+  unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   bool setup_done = false, geom_ready = false;
   // instrumentation
@@ -90,7 +90,7 @@ struct b200_sph {
   {
     S[0].ensure(n, keep && cur == 0, st); S[1].ensure(n, keep && cur == 1, st);
     rec.ensure(n * 4, false, st); gowner.ensure(n, false, st); gimage.ensure(n, false, st);
-    numneigh.ensure(n, false, st); nact.ensure(n, false, st);
+    numneigh.ensure(n, false, st); numfar.ensure(n, false, st);
   }
   StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p}; }
   GhostArrays ghost_arrays() { OwnedSet &c = C(); return GhostArrays{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.tag.p, c.mask.p, gowner.p, gimage.p}; }
@@ -244,29 +244,31 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   } else if (nl) {
     CK(cudaMemsetAsync(h->gcount.p, 0, (nl + 2) * sizeof(int), h->st));
   }
-  if (h->check && nl) { h->xhold.ensure((size_t)3 * nl); LAUNCH(h, k_store_xhold, nblk(nl, B), B, nl, h->C().xt.p, h->xhold.p); }
+  if ((h->check || h->far_margin > 0.0) && nl) { h->xhold.ensure((size_t)3 * nl); LAUNCH(h, k_store_xhold, nblk(nl, B), B, nl, h->C().xt.p, h->xhold.p); }
   h->tend();
   // 3. rows
   h->tbegin(T_NEIGH_BUILD);
   int na = h->nall();
   for (int attempt = 0; attempt < 8 && na; attempt++) {
-    h->nbr.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
+    h->nbr.ensure((size_t)((na + 31) / 32) * 32 * h->stride); h->far.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
     BuildArgs A;
     A.g = g; A.nlocal = nl; A.nghost = h->nghost; A.stride = h->stride; A.ntypes1 = h->ntypes + 1;
-    A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.cutneighsq = h->d_cutneighsq.p;
+    A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.cutneighsq = h->d_cutneighsq.p; A.prunesq = h->d_prunesq.p; A.farsq = h->d_farsq.p; A.far = h->far.p; A.numfar = h->numfar.p;
     A.nbr = h->nbr.p; A.numneigh = h->numneigh.p; A.maxcount = h->d_flags;
     LAUNCH(h, k_build, nblk(g.ncells, BUILD_WARPS), BUILD_WARPS * 32, A);
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    int mx = std::max(h->h_flags[0], h->h_flags[1]);
+    int mx = h->h_flags[0];
     h->maxneigh = std::max<long long>(h->maxneigh, mx);
     if (mx <= h->stride) break;
     h->stride = ((int)(mx * 1.2) + 8 + 31) / 32 * 32;     // the reference's hard cap is oneatom = 2000 (neighbor.cpp:81)
     if (attempt == 7) throw std::string("b200: neighbor row overflow");
   }
   h->tend();
-  h->ago = 0; h->nbuilds++; h->pruned_step = -1;
+  CK(cudaMemsetAsync(h->d_dmaxsq, 0, sizeof(unsigned long long), h->st));
+  CK(cudaMemsetAsync(h->d_scan_far, 0, sizeof(int), h->st));
+  h->ago = 0; h->nbuilds++;
 }
 
 // ------------------------------------------------------------- pair plan ----
@@ -295,7 +297,12 @@ static void build_plan(b200_sph *h)
   h->plan.clear();
   double psq[MAXTT];
   for (int k = 0; k < MAXTT; k++) { psq[k] = -1.0; for (int s = 0; s < h->npair; s++) psq[k] = std::max(psq[k], h->h_tab[s].cutsq[k]); }
-  h->d_prunesq.ensure(MAXTT);
+  // far rows: entries at least skin/4 outside the largest pair cutoff (only when there is a skin)
+  double fsq[MAXTT];
+  h->far_margin = h->skin > 0.0 ? 0.25 * h->skin : 0.0;
+  for (int k = 0; k < MAXTT; k++) fsq[k] = (h->far_margin > 0.0 && psq[k] >= 0.0) ? (sqrt(psq[k]) + h->far_margin) * (sqrt(psq[k]) + h->far_margin) : 1e300;
+  h->d_prunesq.ensure(MAXTT); h->d_farsq.ensure(MAXTT);
+  CK(cudaMemcpyAsync(h->d_farsq.p, fsq, sizeof fsq, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->d_prunesq.p, psq, sizeof psq, cudaMemcpyHostToDevice, h->st));
   CK(cudaStreamSynchronize(h->st));
   int k = 0;
@@ -316,24 +323,12 @@ static void build_plan(b200_sph *h)
   }
 }
 
-// rows the stage kernels walk this step: the Verlet rows, or (skin > 0) their per-step pruned copy
-static void ensure_pruned(b200_sph *h)
-{
-  if (!(h->skin > 0.0) || !h->nall()) { h->pruned = false; return; }
-  if (h->pruned_step == h->ntimestep && h->pruned) return;
-  int na = h->nall();
-  h->tbegin(T_PRUNE);
-  h->act.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
-  LAUNCH(h, k_prune, nblk(na, PAIR_THREADS), PAIR_THREADS, na, h->stride, h->C().xt.p, h->nbr.p, h->numneigh.p, h->d_prunesq.p, h->act.p, h->nact.p);
-  h->tend();
-  h->pruned = true; h->pruned_step = h->ntimestep;
-}
 static PairArgs pair_args(b200_sph *h)
 {
   PairArgs A{};
   OwnedSet &c = h->C();
   A.nlocal = h->nlocal; A.nall = h->nall(); A.stride = h->stride; A.dim = h->g.dim; A.multiphase = h->multiphase; A.nrec = 1;
-  A.list = h->pruned ? h->act.p : h->nbr.p; A.cnt = h->pruned ? h->nact.p : h->numneigh.p;
+  A.list = h->nbr.p; A.cnt = h->numneigh.p; A.far = h->far.p; A.numfar = h->numfar.p; A.scan_far = h->d_scan_far;
   A.xt = c.xt.p; A.vr = c.vr.p; A.vm = c.vm.p; A.cgm = c.cgm.p; A.rec = h->rec.p; A.e = c.e.p; A.cv = c.cv.p;
   A.vr_out = c.vr.p; A.cg_out = c.cgm.p; A.fd = c.fd.p; A.de = c.de.p;
   return A;
@@ -354,7 +349,6 @@ static void run_pass(b200_sph *h, const Pass &p)
   if (p.type <= 2) {
     const PairTab &T = h->h_tab[p.slots[0]];
     bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
-    if (active) ensure_pruned(h);
     PairArgs A = pair_args(h);
     A.tab[0] = h->d_tab[p.slots[0]];
     int grid = nblk(A.nlocal, PAIR_THREADS);
@@ -378,7 +372,6 @@ static void run_pass(b200_sph *h, const Pass &p)
     return;
   }
   // force pass: canonical table order fluid, surf, heat
-  ensure_pruned(h);
   PairArgs A = pair_args(h);
   int nk = 0; const PairTab *fluid = nullptr;
   const int wants[3] = {K_TAIT | K_MORRIS | K_TAITMP, K_SURF, K_HEAT | K_HEATMP | K_HEATPC};
@@ -436,8 +429,10 @@ static void initial_integrate(b200_sph *h)
   if (!h->nlocal) return;
   h->tbegin(T_INTEGRATE);
   CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));
+  int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
-         h->xhold.p, h->triggersq, h->d_flags + 1);
+         h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq);
+  if (track) LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->d_scan_far);
   h->tend();
 }
 static void forward_comm(b200_sph *h)
@@ -569,6 +564,8 @@ int b200_create(b200_sph **out, int device)
   h->device = device;
   CK(cudaMalloc(&h->d_flags, 16 * sizeof(int)));
   CK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
+  CK(cudaMalloc(&h->d_dmaxsq, sizeof(unsigned long long))); CK(cudaMemset(h->d_dmaxsq, 0, sizeof(unsigned long long)));
+  h->d_scan_far = h->d_flags + 8;
   CK(cudaMallocHost(&h->h_flags, 16 * sizeof(int)));
   memset(&h->fl, 0, sizeof h->fl);
   *out = h;
@@ -579,7 +576,7 @@ int b200_destroy(b200_sph *h)
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  h->S[0].release(); h->S[1].release(); h->rec.release(); h->act.release(); h->nact.release(); h->d_prunesq.release(); h->gowner.release(); h->gimage.release();
+  h->S[0].release(); h->S[1].release(); h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gowner.release(); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
   h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
@@ -767,7 +764,9 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   std::vector<int> cnt(n), orig(n), tag(na), img(na);
   CK(cudaMemcpy(cnt.data(), h->numneigh.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(orig.data(), h->C().orig.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-  for (int s = 0; s < n; s++) numneigh[orig[s]] = cnt[s];
+  std::vector<int> cfar(n);
+  CK(cudaMemcpy(cfar.data(), h->numfar.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < n; s++) numneigh[orig[s]] = (cnt[s] & 0xffff) + (cnt[s] >> 16) + cfar[s];
   if (!jtag) return 0;
   long long tot = 0;
   std::vector<long long> off(n + 1);
@@ -778,13 +777,22 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   for (int s = 0; s < n; s++) img[s] = 13;
   std::vector<unsigned> rows((size_t)((n + 31) / 32) * 32 * h->stride);
   CK(cudaMemcpy(rows.data(), h->nbr.p, rows.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  std::vector<unsigned> frows(rows.size());
+  CK(cudaMemcpy(frows.data(), h->far.p, frows.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
   std::vector<std::pair<int, int>> tmp;
   for (int s = 0; s < n; s++) {
     tmp.clear();
-    for (int k = 0; k < cnt[s]; k++) { int j = rows[(size_t)(s >> 5) * h->stride * 32 + (size_t)k * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]}); }
+    int nin = cnt[s] & 0xffff, nout = cnt[s] >> 16;
+    for (int k = 0; k < nin + nout; k++) {
+      int kk = k < nin ? k : h->stride - 1 - (k - nin);
+      int j = rows[(size_t)(s >> 5) * h->stride * 32 + (size_t)kk * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]});
+    }
+    for (int k = 0; k < cfar[s]; k++) {
+      int j = frows[(size_t)(s >> 5) * h->stride * 32 + (size_t)k * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]});
+    }
     std::sort(tmp.begin(), tmp.end());
     long long o = off[orig[s]];
-    for (int k = 0; k < cnt[s]; k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
+    for (size_t k = 0; k < tmp.size(); k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
   }
   API_END
 }
