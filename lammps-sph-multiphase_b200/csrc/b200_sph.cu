@@ -4,6 +4,7 @@
 #include "b200_neigh.cuh"
 #include "b200_pair.cuh"
 #include "b200_fix.cuh"
+#include "b200_phase.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -45,7 +46,8 @@ struct OwnedSet {
   OwnedArrays view() { return OwnedArrays{xt.p, vr.p, vm.p, fd.p, cgm.p, e.p, de.p, cv.p, tag.p, mask.p, orig.p}; }
 };
 
-struct Pass { int type; int kinds; int nslots; int slots[4]; };   // type: 0 rhosum 1 rhosum/mp 2 colorgradient 3 force
+struct Pass { int type; int kinds; int nslots; int slots[4]; };
+struct PcFix { b200_phase_change_desc d; long long next; int *d_state; };   // type: 0 rhosum 1 rhosum/mp 2 colorgradient 3 force
 
 struct b200_sph {
   int device = 0;
@@ -63,6 +65,9 @@ struct b200_sph {
   int npair = 0; PairTab h_tab[MAXPAIR]; PairTab *d_tab[MAXPAIR] = {nullptr};
   std::vector<Pass> plan;
   FixList fl{};
+  std::vector<PcFix> pcs;
+  DevBuf<unsigned char> pc_flag; DevBuf<double> pc_thr, pc_dmass; DevBuf<int> pc_dev; DevBuf<PcNew> pc_new;
+  int maxtag = 0;
   // particles
   int nlocal = 0, nghost = 0;
   OwnedSet S[2]; int cur = 0;
@@ -445,6 +450,7 @@ static void forward_comm(b200_sph *h)
 // Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
 static int neigh_decide(b200_sph *h)
 {
+  for (const PcFix &f : h->pcs) if (h->ntimestep == f.next) return 1;   // fix->next_reneighbor (neighbor.cpp:1334-1338)
   h->ago++;
   if (h->ago >= h->delay && h->ago % h->every == 0) {
     if (!h->check) return 1;
@@ -456,7 +462,41 @@ static int neigh_decide(b200_sph *h)
   }
   return 0;
 }
-static void reneighbor(b200_sph *h) { neighbor_build(h, true); }
+// FixPhaseChange::pre_exchange (fix_phase_change.cpp:167-352); runs on the rows of the previous build
+static void phase_change(b200_sph *h, PcFix &f)
+{
+  if (f.next != h->ntimestep) return;
+  f.next += f.d.nfreq;
+  int nl = h->nlocal, na = h->nall();
+  if (!nl) return;
+  h->tbegin(T_PHASE);
+  h->pc_flag.ensure(nl); h->pc_thr.ensure(nl); h->pc_dev.ensure(nl); h->pc_dmass.ensure(na); h->pc_new.ensure(PC_MAXNEW);
+  PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.stride = h->stride; P.dt = h->dt;
+  for (int d = 0; d < 3; d++) { P.sublo[d] = h->g.sublo[d]; P.subhi[d] = h->g.subhi[d]; P.boxhi[d] = h->g.boxhi[d]; }
+  OwnedSet &c = h->C();
+  PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p};
+  LAUNCH(h, k_pc_candidates, nblk(na, 128), 128, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p);
+  CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
+  LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state);
+  CK(cudaMemcpyAsync(h->h_flags + 5, f.d_state + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p, h->gcount.p, h->gslot.p, h->nghost > 0);
+  CK(cudaStreamSynchronize(h->st));
+  int nins = h->h_flags[5];
+  if (h->h_flags[6]) throw std::string("fix phase_change: more than PC_MAXNEW insertions in one call");
+  if (nins > 0) {
+    h->ensure_cap((size_t)nl + nins, true);
+    OwnedSet &cc = h->C();
+    AppendArrays ap{cc.xt.p, cc.vr.p, cc.vm.p, cc.fd.p, cc.cgm.p, cc.e.p, cc.de.p, cc.cv.p, cc.tag.p, cc.mask.p, cc.orig.p};
+    LAUNCH(h, k_pc_append, nblk(nins, 128), 128, nl, nins, h->pc_new.p, ap, f.d.to_type, f.d.to_mass, f.d.groupbit, h->maxtag);
+    h->nlocal += nins; h->nghost = 0; h->maxtag += nins; h->ninserted += nins;
+  }
+  h->tend();
+}
+static void reneighbor(b200_sph *h)
+{
+  for (PcFix &f : h->pcs) phase_change(h, f);        // modify->pre_exchange (verlet.cpp:241)
+  neighbor_build(h, true);
+}
 
 static void do_setup(b200_sph *h)
 {
@@ -576,7 +616,8 @@ int b200_destroy(b200_sph *h)
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  h->S[0].release(); h->S[1].release(); h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gowner.release(); h->gimage.release();
+  h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state);
+  h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gowner.release(); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
   h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
@@ -645,7 +686,13 @@ int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
   return slot;
 }
 
-int b200_fix_clear(b200_sph *h) { memset(&h->fl, 0, sizeof h->fl); return 0; }
+int b200_fix_clear(b200_sph *h)
+{
+  memset(&h->fl, 0, sizeof h->fl);
+  for (PcFix &f : h->pcs) cudaFree(f.d_state);
+  h->pcs.clear();
+  return 0;
+}
 static int add_fix(b200_sph *h, int kind, int bit, double ax, double ay, double az)
 {
   if (h->fl.n == MAXFIX) return fail("too many fixes");
@@ -656,7 +703,19 @@ static int add_fix(b200_sph *h, int kind, int bit, double ax, double ay, double 
 int b200_fix_meso(b200_sph *h, int groupbit) { return add_fix(h, 1, groupbit, 0, 0, 0); }
 int b200_fix_meso_stationary(b200_sph *h, int groupbit) { return add_fix(h, 2, groupbit, 0, 0, 0); }
 int b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc) { return add_fix(h, 3, groupbit, xacc, yacc, zacc); }
-int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d) { (void)h; (void)d; return fail("b200_fix_phase_change: not implemented yet"); }
+int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d)
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  if (d->seed <= 0) throw std::string("Illegal value for seed");                   // fix_phase_change.cpp:70
+  if (!h->multiphase) throw std::string("fix phase_change requires atom_style meso/multiphase");
+  PcFix f; f.d = *d; f.next = d->first_step;
+  CK(cudaMalloc(&f.d_state, 4 * sizeof(int)));
+  int st[4] = {d->seed, 0, 0, 0};
+  CK(cudaMemcpy(f.d_state, st, sizeof st, cudaMemcpyHostToDevice));
+  h->pcs.push_back(f);
+  API_END
+}
 
 // staging: the caller's AoS arrays are copied verbatim (DMA from pinned memory when the caller
 // pinned them) and converted to/from the packed device records by a kernel
@@ -690,6 +749,8 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
   h->nlocal = n; h->nghost = 0; h->cur = 0;
   h->ensure_cap(n, false);
   h->setup_done = false;
+  h->maxtag = n;
+  if (a->tag) for (int i = 0; i < n; i++) h->maxtag = std::max(h->maxtag, a->tag[i]);
   if (!n) return 0;
   size_t nd, ni;
   HostMirror m = stage_layout(h, n, a, &nd, &ni);

@@ -16,16 +16,16 @@ pkg = importlib.import_module("lammps-sph-multiphase_b200")
 pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-10
-NO_PC = [n for n in cases.CASES if "phase_change" not in str(cases.CASES[n].cmds)]
+ALL = list(cases.CASES)
 
 
-@pytest.mark.parametrize("name", NO_PC)
+@pytest.mark.parametrize("name", ALL)
 def test_engine_matches_reference_fixture(name):
     e0, eN = harness.run_case(pkg.B200Sim, name, tol_step=TOL_STEP)
     print(name, "run0", {k: "%.1e" % v for k, v in e0.items()}, "runN", {k: "%.1e" % v for k, v in eN.items()})
 
 
-@pytest.mark.parametrize("name", ["dam3d", "droplet3d", "heat2d"])
+@pytest.mark.parametrize("name", ["dam3d", "droplet3d", "heat2d", "bubble3d"])
 def test_engine_matches_oracle_live(name):
     case = cases.CASES[name]
     g = harness.load_golden(name)
