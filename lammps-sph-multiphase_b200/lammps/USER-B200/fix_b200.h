@@ -1,0 +1,66 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   USER-B200 fix shells: fix meso/b200, meso/stationary/b200, gravity/b200, phase_change/b200.
+   Same arguments as the reference fixes; the per-step work runs inside the engine.
+------------------------------------------------------------------------- */
+#ifdef FIX_CLASS
+
+FixStyle(meso/b200,FixMesoB200)
+FixStyle(meso/stationary/b200,FixMesoStationaryB200)
+FixStyle(gravity/b200,FixGravityB200)
+FixStyle(phase_change/b200,FixPhaseChangeB200)
+
+#else
+
+#ifndef LMP_FIX_B200_H
+#define LMP_FIX_B200_H
+
+#include "b200_shell.h"
+#include "fix_meso.h"
+#include "fix_meso_stationary.h"
+#include "fix_gravity.h"
+
+namespace LAMMPS_NS {
+
+void b200_fix_guard(class LAMMPS *, const char *);
+
+class FixMesoB200 : public FixMeso, public B200FixShell {
+ public:
+  FixMesoB200(class LAMMPS *lmp, int narg, char **arg) : FixMeso(lmp, narg, arg) {}
+  void setup_pre_force(int) {}                         // vest = v happens in b200_setup (k_setup_pre_force)
+  void initial_integrate(int) { b200_fix_guard(lmp, "meso"); }
+  void final_integrate() { b200_fix_guard(lmp, "meso"); }
+  int b200_register(b200_sph *h) { return b200_fix_meso(h, groupbit); }
+};
+
+class FixMesoStationaryB200 : public FixMesoStationary, public B200FixShell {
+ public:
+  FixMesoStationaryB200(class LAMMPS *lmp, int narg, char **arg) : FixMesoStationary(lmp, narg, arg) {}
+  void initial_integrate(int) { b200_fix_guard(lmp, "meso/stationary"); }
+  void final_integrate() { b200_fix_guard(lmp, "meso/stationary"); }
+  int b200_register(b200_sph *h) { return b200_fix_meso_stationary(h, groupbit); }
+};
+
+class FixGravityB200 : public FixGravity, public B200FixShell {
+ public:
+  FixGravityB200(class LAMMPS *lmp, int narg, char **arg) : FixGravity(lmp, narg, arg) {}
+  void setup(int) {}
+  void post_force(int) { b200_fix_guard(lmp, "gravity"); }
+  int b200_register(b200_sph *h);
+};
+
+// FixPhaseChange keeps its parameters private (fix_phase_change.h:40-70), so the shell parses the same
+// argument list itself: fix ID grp phase_change Tc Tt Hwv dr to_mass cutoff from_type to_type nfreq seed
+//                       (prob | ENERGY rate) region ID [attempt N] [units box]   (fix_phase_change.cpp:57-79,358-390)
+class FixPhaseChangeB200 : public Fix, public B200FixShell {
+ public:
+  FixPhaseChangeB200(class LAMMPS *, int, char **);
+  int setmask();
+  void pre_exchange() { b200_fix_guard(lmp, "phase_change"); }
+  int b200_register(b200_sph *h);
+ private:
+  b200_phase_change_desc d;
+};
+
+}    // namespace LAMMPS_NS
+#endif
+#endif

@@ -1,0 +1,186 @@
+/* ----------------------------------------------------------------------
+   run_style verlet/b200 -- see verlet_b200.h.  Single MPI rank per engine instance.
+------------------------------------------------------------------------- */
+#include "string.h"
+#include "math.h"
+#include "verlet_b200.h"
+#include "pair_sph_b200.h"
+#include "fix_b200.h"
+#include "pair_hybrid.h"
+#include "neighbor.h"
+#include "domain.h"
+#include "comm.h"
+#include "atom.h"
+#include "atom_vec.h"
+#include "force.h"
+#include "pair.h"
+#include "modify.h"
+#include "fix.h"
+#include "output.h"
+#include "update.h"
+#include "timer.h"
+#include "memory.h"
+#include "error.h"
+
+using namespace LAMMPS_NS;
+
+VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), h(NULL), h_step(-1) {}
+
+VerletB200::~VerletB200() { if (h) b200_destroy(h); }
+
+void VerletB200::check(int rc) { if (rc < 0) error->all(FLERR, b200_last_error()); }
+
+void VerletB200::init()
+{
+  Verlet::init();
+  if (comm->nprocs != 1) error->all(FLERR, "run_style verlet/b200: one MPI rank per engine instance (multi-GPU bricks: see DESIGN.md)");
+  if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton on");
+  if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 supports orthogonal boxes");
+  if (!atom->rho_flag || !atom->e_flag) error->all(FLERR, "run_style verlet/b200 requires atom_style meso or meso/multiphase");
+}
+
+/* push everything LAMMPS parsed across the C-ABI (tables only, verbatim from the host objects) */
+void VerletB200::configure()
+{
+  if (!h) check(b200_create(&h, 0));
+  int n = atom->ntypes;
+  int multiphase = atom->rmass_flag ? 1 : 0;
+  check(b200_domain(h, domain->dimension, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi));
+  check(b200_atom_style(h, multiphase, n, atom->mass));
+  // Neighbor::init, neighbor.cpp:259-282 (cutneighsq itself is protected there)
+  std::vector<double> cn((n + 1) * (n + 1), 0.0);
+  for (int i = 1; i <= n; i++)
+    for (int j = 1; j <= n; j++) {
+      double cutoff = sqrt(force->pair->cutsq[i][j]);
+      double cut = cutoff + (cutoff > 0.0 ? neighbor->skin : 0.0);
+      cn[i * (n + 1) + j] = cut * cut;
+    }
+  check(b200_neighbor(h, neighbor->skin, neighbor->every, neighbor->delay, neighbor->dist_check, cn.data(), neighbor->cutneighmax,
+                      comm->cutghost[0]));
+  check(b200_timestep(h, update->dt, force->ftm2v, update->ntimestep));
+  check(b200_comm_modify(h, comm->ghost_velocity));
+
+  // pair sub-styles in PairHybrid::compute order (pair_hybrid.cpp:101-109)
+  check(b200_pair_clear(h));
+  int nsub = 1; Pair **subs = &force->pair;
+  PairHybrid *hyb = dynamic_cast<PairHybrid *>(force->pair);
+  if (hyb) { nsub = hyb->nstyles; subs = hyb->styles; }
+  for (int m = 0; m < nsub; m++) {
+    B200PairShell *shell = dynamic_cast<B200PairShell *>(subs[m]);
+    if (!shell) error->all(FLERR, "run_style verlet/b200: every pair (sub-)style must be a /b200 style");
+    b200_pair_desc d; std::vector<std::vector<double> > ds; std::vector<std::vector<int> > is;
+    ds.reserve(16); is.reserve(4);
+    shell->b200_describe(d, ds, is);
+    check(b200_pair_add(h, &d));
+  }
+
+  // fixes in Modify order; a fix with per-step hooks but no /b200 variant cannot run device-resident
+  if (h_step != update->ntimestep || true) {
+    check(b200_fix_clear(h));
+    for (int i = 0; i < modify->nfix; i++) {
+      Fix *f = modify->fix[i];
+      B200FixShell *shell = dynamic_cast<B200FixShell *>(f);
+      if (shell) { check(shell->b200_register(h)); continue; }
+      int mask = modify->fmask[i];
+      const int stepping = FixConst::INITIAL_INTEGRATE | FixConst::POST_INTEGRATE | FixConst::PRE_EXCHANGE | FixConst::PRE_NEIGHBOR |
+                           FixConst::PRE_FORCE | FixConst::POST_FORCE | FixConst::FINAL_INTEGRATE;
+      if (mask & stepping) {
+        char msg[256];
+        sprintf(msg, "run_style verlet/b200: fix %s (%s) has no /b200 variant", f->id, f->style);
+        error->all(FLERR, msg);
+      }
+    }
+    h_step = update->ntimestep;
+  }
+}
+
+void VerletB200::upload()
+{
+  b200_atoms a; memset(&a, 0, sizeof a);
+  int nl = atom->nlocal;
+  a.x = nl ? &atom->x[0][0] : NULL; a.v = nl ? &atom->v[0][0] : NULL; a.vest = nl ? &atom->vest[0][0] : NULL; a.f = nl ? &atom->f[0][0] : NULL;
+  a.rho = atom->rho; a.drho = atom->drho; a.e = atom->e; a.de = atom->de; a.cv = atom->cv; a.rmass = atom->rmass;
+  a.colorgradient = (atom->rmass_flag && nl) ? &atom->colorgradient[0][0] : NULL;
+  a.type = atom->type; a.mask = atom->mask;
+  std::vector<int> tag(nl);
+  for (int i = 0; i < nl; i++) tag[i] = (int)atom->tag[i];
+  a.tag = tag.data();
+  check(b200_set_atoms(h, nl, &a));
+}
+
+void VerletB200::download()
+{
+  int nl, ng;
+  check(b200_get_natoms(h, &nl, &ng));
+  if (nl != atom->nlocal) {                    // fix phase_change/b200 created atoms
+    while (nl > atom->nmax) atom->avec->grow(0);
+    atom->nlocal = nl; atom->natoms = nl; atom->nghost = 0;
+  }
+  b200_atoms a; memset(&a, 0, sizeof a);
+  a.x = &atom->x[0][0]; a.v = &atom->v[0][0]; a.vest = &atom->vest[0][0]; a.f = &atom->f[0][0];
+  a.rho = atom->rho; a.drho = atom->drho; a.e = atom->e; a.de = atom->de; a.cv = atom->cv; a.rmass = atom->rmass;
+  a.colorgradient = atom->rmass_flag ? &atom->colorgradient[0][0] : NULL;
+  a.type = atom->type; a.mask = atom->mask;
+  std::vector<int> tag(nl);
+  a.tag = tag.data();
+  check(b200_get_atoms(h, nl, &a));
+  for (int i = 0; i < nl; i++) atom->tag[i] = tag[i];
+  atom->nghost = 0;
+  if (atom->map_style) { atom->map_init(); atom->map_set(); }
+  long long c[8];
+  b200_get_counters(h, c);
+  neighbor->ncalls = c[1]; neighbor->ndanger = c[7];
+}
+
+/* Verlet::setup, verlet.cpp:88-142 */
+void VerletB200::setup()
+{
+  if (comm->me == 0 && screen) fprintf(screen, "Setting up run (B200 engine: %s) ...\n", b200_version());
+  update->setupflag = 1;
+  atom->setup();
+  modify->setup_pre_exchange();
+  domain->pbc();
+  domain->reset_box();
+  comm->setup();
+  comm->exchange();
+  if (atom->sortfreq > 0) atom->sort();
+  atom->nghost = 0;
+  configure();
+  upload();
+  check(b200_setup(h));
+  download();
+  ev_set(update->ntimestep);
+  modify->setup(vflag);
+  output->setup();
+  update->setupflag = 0;
+}
+
+void VerletB200::setup_minimal(int flag)
+{
+  if (flag) setup();
+}
+
+/* Verlet::run, verlet.cpp:207-309: device-resident segments between output steps */
+void VerletB200::run(int n)
+{
+  bigint nend = update->ntimestep + n;
+  while (update->ntimestep < nend) {
+    bigint next = output->next < nend ? output->next : nend;
+    if (next <= update->ntimestep) next = update->ntimestep + 1;
+    int k = (int)(next - update->ntimestep);
+    timer->stamp();
+    check(b200_run(h, k));
+    check(b200_sync(h));
+    update->ntimestep += k;
+    timer->stamp(TIME_PAIR);
+    if (update->ntimestep == output->next || update->ntimestep == nend) {
+      download();
+      timer->stamp(TIME_COMM);
+    }
+    if (update->ntimestep == output->next) {
+      ev_set(update->ntimestep);
+      output->write(update->ntimestep);
+      timer->stamp(TIME_OUTPUT);
+    }
+  }
+}

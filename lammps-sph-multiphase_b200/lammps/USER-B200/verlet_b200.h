@@ -1,0 +1,39 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   run_style verlet/b200: the Verlet loop (src/verlet.cpp:88-309) executed device-resident by
+   the engine.  Host arrays are refreshed on output steps and at the end of the run only.
+------------------------------------------------------------------------- */
+#ifdef INTEGRATE_CLASS
+
+IntegrateStyle(verlet/b200,VerletB200)
+
+#else
+
+#ifndef LMP_VERLET_B200_H
+#define LMP_VERLET_B200_H
+
+#include "verlet.h"
+#include "b200_sph.h"
+
+namespace LAMMPS_NS {
+
+class VerletB200 : public Verlet {
+ public:
+  VerletB200(class LAMMPS *, int, char **);
+  ~VerletB200();
+  void init();
+  void setup();
+  void setup_minimal(int);
+  void run(int);
+
+ private:
+  b200_sph *h;
+  long long h_step;              // engine timestep the fixes were registered for
+  void check(int rc);
+  void configure();
+  void upload();
+  void download();
+};
+
+}
+#endif
+#endif

@@ -1,0 +1,60 @@
+"""GPU: the drop-in itself.  The SAME deck text is run by the unmodified reference binary
+(oracle/_ref/lmp_serial) and by the reference + USER-B200 shells (lammps/_build/lmp_b200 -sf b200),
+and the final per-atom dumps (17 significant digits, sorted by id) are compared.
+Both binaries are built where /root/reference exists and travel to the GPU box."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from util import relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+B200 = os.path.join(ROOT, "lammps-sph-multiphase_b200", "lammps", "_build", "lmp_b200")
+pytestmark = pytest.mark.gpu
+
+COLS = "id type x y z vx vy vz fx fy fz c_crho c_ce"
+FMT = "%d %d " + " ".join(["%.17g"] * 11)
+
+
+def deck_text(case, nsteps):
+    return "\n".join([case.header_text().replace("atom_modify map array sort 0 0", "atom_modify map array"), case.create, case.lammps_text(),
+                      "compute crho all meso_rho/atom", "compute ce all meso_e/atom", "thermo 10",
+                      "dump dfin all custom %d dump.final %s" % (nsteps, COLS), 'dump_modify dfin sort id format "%s"' % FMT,
+                      "run %d" % nsteps, ""])
+
+
+def run(exe, args, workdir, text):
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "deck.lmp"), "w") as f:
+        f.write(text)
+    p = subprocess.run([exe] + args + ["-in", "deck.lmp", "-log", "log.lammps"], cwd=workdir, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ERROR" not in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+    rows = []
+    with open(os.path.join(workdir, "dump.final")) as f:
+        lines = f.read().splitlines()
+    start = [i for i, l in enumerate(lines) if l.startswith("ITEM: ATOMS")][-1]      # last snapshot = end of the run
+    for l in lines[start + 1:]:
+        rows.append([float(v) for v in l.split()])
+    return np.array(rows), p.stdout
+
+
+@pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8)])
+def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
+    case = cases.CASES[name]
+    text = deck_text(case, nsteps)
+    a, _ = run(REF, [], str(tmp_path / "ref"), text)
+    b, out = run(B200, ["-sf", "b200"], str(tmp_path / "b200"), text)
+    assert "B200 engine" in out
+    assert a.shape == b.shape, "particle counts differ: %s vs %s" % (a.shape, b.shape)
+    assert np.array_equal(a[:, :2], b[:, :2])
+    names = COLS.split()
+    errs = {}
+    for lo, hi, nm in ((2, 5, "x"), (5, 8, "v"), (8, 11, "f"), (11, 12, "rho"), (12, 13, "e")):
+        errs[nm] = relerr(b[:, lo:hi], a[:, lo:hi])
+    assert all(v <= tol for v in errs.values()), errs
