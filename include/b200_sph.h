@@ -91,6 +91,15 @@ int  b200_destroy(b200_sph *h);
 const char *b200_last_error(void);
 const char *b200_version(void);
 
+/* ---- multi-GPU: one engine instance per rank, LAMMPS-style brick decomposition ----
+ * (src/comm_brick.cpp, src/procmap.cpp).  Rank 0 creates an id, the host layer broadcasts it (MPI in
+ * LAMMPS, torch.distributed in the Python driver), every rank calls b200_comm_init BEFORE b200_domain.
+ * procgrid = comm->procgrid, myloc = comm->myloc, procneigh[2*dim+dir] = comm->procneigh[dim][dir].
+ * Ghost exchange, reverse accumulation and atom migration then run over NCCL send/recv (NVLink). */
+int  b200_comm_unique_id(char id[128]);
+int  b200_comm_init(b200_sph *h, int world, int rank, const int procgrid[3], const int myloc[3], const int procneigh[6],
+                    const char id[128]);
+
 /* ---- problem definition (host state LAMMPS already parsed) ---------------- */
 /* Domain: dimension, box, periodicity  (src/domain.h boxlo/boxhi/periodicity).
  * sublo/subhi = this rank's sub-domain (== box on one GPU), src/domain.h sublo. */
@@ -125,7 +134,8 @@ int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix
 int  b200_set_atoms(b200_sph *h, int nlocal, const b200_atoms *a);
 int  b200_get_natoms(b200_sph *h, int *nlocal, int *nghost);
 /* Download owned atoms back in LAMMPS local order (non-NULL fields only).
- * Atoms created by fix phase_change are appended in creation order.            */
+ * Atoms created by fix phase_change are appended in creation order.  With more than one rank
+ * the order is this rank's local order (migrated atoms appended on arrival); match ranks by tag. */
 int  b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a);
 
 /* ---- the hot path --------------------------------------------------------- */

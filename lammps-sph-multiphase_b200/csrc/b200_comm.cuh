@@ -1,0 +1,169 @@
+// b200_comm.cuh -- halo (ghost) exchange, reverse accumulation and atom migration kernels.
+//
+// Restates CommBrick::borders / forward_comm / reverse_comm / exchange
+// (/root/reference/src/comm_brick.cpp:444-864) with the AtomVecMeso[MultiPhase] wire formats
+// (src/USER-SPH/atom_vec_meso*.cpp pack_border/pack_comm/pack_reverse/pack_exchange), as
+// device pack/unpack kernels around an NCCL send/recv (NVLink 5) -- or a plain local copy when
+// the neighbour in that direction is this rank itself (periodic self-images).
+// Ghosts are stored behind the owned atoms in swap order, exactly like the reference, so each
+// swap's receive range is contiguous.
+#pragma once
+#include "b200_common.cuh"
+#include "b200_neigh.cuh"
+
+#define NB_BORDER 20    // x3 v3 vest3 rho cg3 rmass e cv tag type mask image
+#define NB_FORWARD 15   // x3 v3 vest3 rho cg3 rmass e
+#define NB_REVERSE 5    // f3 drho de
+#define NB_EXCHANGE 26  // every per-atom field
+
+struct CommArrays {
+  double4 *xt, *vr, *vm, *fd, *cgm;
+  double *e, *de, *cv;
+  int *tag, *mask, *orig, *gimage;
+};
+
+// atoms of [0,n) inside the slab lo <= x[dim] <= hi  (comm_brick.cpp:746-750)
+__global__ void k_slab_flag(int n, const double4 *xt, int dim, double lo, double hi, int *flag, int *pos)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = xt[i];
+  double c = dim == 0 ? p.x : (dim == 1 ? p.y : p.z);
+  int f = (c >= lo && c <= hi) ? 1 : 0;
+  flag[i] = f; pos[i] = f;
+}
+__global__ void k_compact(int n, const int *flag, const int *pos, int *list)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) list[pos[i]] = i;
+}
+
+__device__ __forceinline__ double shifted(double c, double shift) { return shift != 0.0 ? __dadd_rn(c, shift) : c; }
+
+// pack_border_vel: x + pbc shift, ... (atom_vec_meso_multiphase.cpp:555-721)
+__global__ void k_pack_border(int n, const int *list, CommArrays a, int dim, double shift, int imgstep, double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int j = list[k];
+  double4 x = a.xt[j], vr = a.vr[j], v = a.vm[j], c = a.cgm[j];
+  double *b = buf + (size_t)k * NB_BORDER;
+  b[0] = dim == 0 ? shifted(x.x, shift) : x.x; b[1] = dim == 1 ? shifted(x.y, shift) : x.y; b[2] = dim == 2 ? shifted(x.z, shift) : x.z;
+  b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
+  b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[j]; b[15] = a.cv[j];
+  b[16] = (double)a.tag[j]; b[17] = (double)tw_type(__double_as_longlong(x.w)); b[18] = (double)a.mask[j];
+  b[19] = (double)(a.gimage[j] + imgstep);
+}
+__global__ void k_unpack_border(Geom g, int n, int first, CommArrays a, const double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int i = first + k;
+  const double *b = buf + (size_t)k * NB_BORDER;
+  int type = (int)b[17];
+  a.xt[i] = make_double4(b[0], b[1], b[2], __longlong_as_double((long long)make_tw(g, type, b[0], b[1], b[2])));
+  a.vm[i] = make_double4(b[3], b[4], b[5], b[13]);
+  a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
+  a.cgm[i] = make_double4(b[10], b[11], b[12], b[13]);
+  a.e[i] = b[14]; a.cv[i] = b[15];
+  a.tag[i] = (int)b[16]; a.mask[i] = (int)b[18]; a.gimage[i] = (int)b[19];
+}
+// pack_comm[_vel] (atom_vec_meso_multiphase.cpp:319-465): cv, type, tag, mask are NOT resent
+__global__ void k_pack_forward(int n, const int *list, CommArrays a, int dim, double shift, double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int j = list[k];
+  double4 x = a.xt[j], vr = a.vr[j], v = a.vm[j], c = a.cgm[j];
+  double *b = buf + (size_t)k * NB_FORWARD;
+  b[0] = dim == 0 ? shifted(x.x, shift) : x.x; b[1] = dim == 1 ? shifted(x.y, shift) : x.y; b[2] = dim == 2 ? shifted(x.z, shift) : x.z;
+  b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
+  b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[j];
+}
+__global__ void k_unpack_forward(int n, int first, CommArrays a, const double *buf, int multiphase, int ghost_velocity)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int i = first + k;
+  const double *b = buf + (size_t)k * NB_FORWARD;
+  double4 x = a.xt[i], v = a.vm[i];
+  x.x = b[0]; x.y = b[1]; x.z = b[2];
+  a.xt[i] = x;
+  a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
+  if (ghost_velocity) { v.x = b[3]; v.y = b[4]; v.z = b[5]; }
+  if (multiphase) { v.w = b[13]; a.cgm[i] = make_double4(b[10], b[11], b[12], b[13]); }
+  a.vm[i] = v;
+  a.e[i] = b[14];
+}
+// pack_reverse / unpack_reverse (atom_vec_meso_multiphase.cpp:520-551): ghosts' f, drho, de added to the atoms that were sent
+__global__ void k_pack_reverse(int n, int first, CommArrays a, double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double4 f = a.fd[first + k];
+  double *b = buf + (size_t)k * NB_REVERSE;
+  b[0] = f.x; b[1] = f.y; b[2] = f.z; b[3] = f.w; b[4] = a.de[first + k];
+}
+__global__ void k_unpack_reverse(int n, const int *list, CommArrays a, const double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int j = list[k];                       // entries of one sendlist are distinct -> no atomics needed
+  const double *b = buf + (size_t)k * NB_REVERSE;
+  double4 f = a.fd[j];
+  f.x += b[0]; f.y += b[1]; f.z += b[2]; f.w += b[3];
+  a.fd[j] = f;
+  a.de[j] += b[4];
+}
+// one double per atom: forward (sph/rhosum's forward_comm_pair, pair_sph_rhosum.cpp:290-313) / reverse-add (fix phase_change dmass)
+__global__ void k_pack_rho(int n, const int *list, const double4 *vr, double *buf)
+{ int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) buf[k] = vr[list[k]].w; }
+__global__ void k_unpack_rho(int n, int first, double4 *vr, const double *buf)
+{ int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) vr[first + k].w = buf[k]; }
+__global__ void k_pack_scalar(int n, int first, const double *src, double *buf)
+{ int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) buf[k] = src[first + k]; }
+__global__ void k_unpack_scalar_add(int n, const int *list, double *dst, const double *buf)
+{ int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) dst[list[k]] += buf[k]; }
+
+// ---- migration: CommBrick::exchange (comm_brick.cpp:573-684) ----
+// atoms outside [lo,hi) in `dim` leave (flag) and are packed; slot is marked dead (mask = 0 convention: alive[] array)
+__global__ void k_exchange_flag(int n, const double4 *xt, const int *alive, int dim, double lo, double hi, int *flag, int *pos)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = xt[i];
+  double c = dim == 0 ? p.x : (dim == 1 ? p.y : p.z);
+  int f = (alive[i] && (c < lo || c >= hi)) ? 1 : 0;
+  flag[i] = f; pos[i] = f;
+}
+__global__ void k_pack_exchange(int n, const int *list, CommArrays a, int *alive, double *buf)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int j = list[k];
+  double4 x = a.xt[j], vr = a.vr[j], v = a.vm[j], f = a.fd[j], c = a.cgm[j];
+  double *b = buf + (size_t)k * NB_EXCHANGE;
+  b[0] = x.x; b[1] = x.y; b[2] = x.z; b[3] = (double)tw_type(__double_as_longlong(x.w));
+  b[4] = vr.x; b[5] = vr.y; b[6] = vr.z; b[7] = vr.w; b[8] = v.x; b[9] = v.y; b[10] = v.z; b[11] = v.w;
+  b[12] = f.x; b[13] = f.y; b[14] = f.z; b[15] = f.w; b[16] = c.x; b[17] = c.y; b[18] = c.z; b[19] = c.w;
+  b[20] = a.e[j]; b[21] = a.de[j]; b[22] = a.cv[j]; b[23] = (double)a.tag[j]; b[24] = (double)a.mask[j]; b[25] = 0.0;
+  alive[j] = 0;
+}
+// receiver keeps the atoms that fall inside its own [lo,hi) in `dim` (comm_brick.cpp:657-664)
+__global__ void k_unpack_exchange(int n, const double *buf, int dim, double lo, double hi, int first, CommArrays a, int *alive, int *counter, int orig0)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double *b = buf + (size_t)k * NB_EXCHANGE;
+  double c = b[dim];
+  int i = first + k;                      // every candidate gets a slot; the ones that are not mine stay dead
+  bool mine = c >= lo && c < hi;
+  alive[i] = mine ? 1 : 0;
+  if (!mine) return;
+  atomicAdd(counter, 1);
+  a.xt[i] = make_double4(b[0], b[1], b[2], __longlong_as_double((long long)pack_tw((int)b[3], 0, 0, 0)));
+  a.vr[i] = make_double4(b[4], b[5], b[6], b[7]); a.vm[i] = make_double4(b[8], b[9], b[10], b[11]);
+  a.fd[i] = make_double4(b[12], b[13], b[14], b[15]); a.cgm[i] = make_double4(b[16], b[17], b[18], b[19]);
+  a.e[i] = b[20]; a.de[i] = b[21]; a.cv[i] = b[22]; a.tag[i] = (int)b[23]; a.mask[i] = (int)b[24];
+  a.orig[i] = orig0 + k;                  // arrival order continues this rank's local-index sequence
+}

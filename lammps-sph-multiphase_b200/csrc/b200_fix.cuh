@@ -64,28 +64,16 @@ __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double
 __global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, int *scan_far)
 { *scan_far = 4.0 * __longlong_as_double((long long)*dmaxsq) >= 0.99 * marginsq; }
 
-// comm->reverse_comm (comm_brick.cpp:513-560: f, drho, de of ghosts added to their owners), then
-// modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
+// (comm->reverse_comm runs before this kernel: b200_comm.cuh) modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
 // (fix_meso.cpp:144-180, fix_meso_stationary.cpp:96-112).  The three stages can be run fused (one
 // pass over the owned atoms) or one by one for the stage-level ABI.
-__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_reverse, int do_post, int do_final,
-                             const int *goff, const int *gslot)
+__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_post, int do_final)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   double4 f = a.fd[i];
   double de = a.de[i];
   bool fdirty = false;
-  if (do_reverse) {
-    for (int q = goff[i]; q < goff[i + 1]; q++) {
-      int g = gslot[q];
-      double4 fg = a.fd[g];
-      f.x += fg.x; f.y += fg.y; f.z += fg.z; f.w += fg.w;
-      de += a.de[g];
-      fdirty = true;
-    }
-    if (fdirty) a.de[i] = de;
-  }
   int m = a.mask[i];
   double4 v = a.vm[i];
   if (do_post)
@@ -142,11 +130,11 @@ __global__ void k_pack_atoms(int n, HostMirror m, PackArrays a, int multiphase, 
   a.tag[i] = m.tag ? m.tag[i] : i + 1; a.mask[i] = m.mask ? m.mask[i] : 1; a.orig[i] = i;
 }
 // scatter back to LAMMPS local order (orig)
-__global__ void k_unpack_atoms(int n, HostMirror m, PackArrays a, int multiphase)
+__global__ void k_unpack_atoms(int n, HostMirror m, PackArrays a, int multiphase, const int *outpos)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  int i = a.orig[s];
+  int i = outpos ? outpos[s] : a.orig[s];
   double4 x = a.xt[s], vr = a.vr[s], v = a.vm[s], f = a.fd[s];
   if (m.x) { m.x[3 * i] = x.x; m.x[3 * i + 1] = x.y; m.x[3 * i + 2] = x.z; }
   if (m.v) { m.v[3 * i] = v.x; m.v[3 * i + 1] = v.y; m.v[3 * i + 2] = v.z; }
@@ -163,3 +151,5 @@ __global__ void k_unpack_atoms(int n, HostMirror m, PackArrays a, int multiphase
   if (m.mask) m.mask[i] = a.mask[s];
   if (m.tag) m.tag[i] = a.tag[s];
 }
+
+__global__ void k_fill_int(int n, int *p, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }

@@ -77,10 +77,11 @@ __global__ void k_scan_add(int *data, int n, const int *sums)
 
 // ------------------------------------------------------- owned: pbc + cells --
 // Domain::pbc (src/domain.cpp:476-560) then engine-cell id + histogram
-__global__ void k_owned_cells(Geom g, int nlocal, double4 *xt, int *cellid, int *cellcnt, int do_pbc)
+__global__ void k_owned_cells(Geom g, int nlocal, double4 *xt, int *cellid, int *cellcnt, int do_pbc, const int *alive)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
+  if (alive && !alive[i]) { cellid[i] = -1; return; }     // slot vacated by atom migration
   double4 p = xt[i];
   if (do_pbc) {
     double c[3] = {p.x, p.y, p.z};
@@ -98,12 +99,30 @@ __global__ void k_owned_cells(Geom g, int nlocal, double4 *xt, int *cellid, int 
   atomicAdd(&cellcnt[c], 1);
 }
 
+// Domain::pbc alone (the multi-rank path wraps before atoms migrate)
+__global__ void k_pbc(Geom g, int nlocal, double4 *xt)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  double c[3] = {p.x, p.y, p.z};
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    if (g.periodic[d]) {
+      if (c[d] < g.boxlo[d]) c[d] = __dadd_rn(c[d], g.prd[d]);
+      if (c[d] >= g.boxhi[d]) { c[d] = __dsub_rn(c[d], g.prd[d]); c[d] = fmax(c[d], g.boxlo[d]); }
+    }
+  p.x = c[0]; p.y = c[1]; p.z = c[2];
+  xt[i] = p;
+}
+
 // scatter element ids into their cell segment (arbitrary order inside a segment; fixed by k_sort_segments)
 __global__ void k_scatter(int n, const int *cellid, const int *cellstart, int *cellfill, int *perm)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = cellid[i];
+  if (c < 0) return;
   perm[cellstart[c] + atomicAdd(&cellfill[c], 1)] = i;
 }
 
@@ -158,111 +177,18 @@ __global__ void k_store_xhold(int nlocal, const double4 *xt, double *xhold)
 }
 
 // ---------------------------------------------------------------- ghosts ----
-// Image set of an owned atom on a 1x1x1 processor grid = what CommBrick::borders
-// creates through its x, y, z swap chain (comm_brick.cpp:713-851): per periodic
-// dimension +prd if x <= sublo+cutghost (sent "left"), -prd if x >= subhi-cutghost.
-__device__ __forceinline__ void image_flags(const Geom &g, double x, double y, double z, int lo[3], int hi[3])
-{
-  double c[3] = {x, y, z};
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    bool on = g.periodic[d] && !(g.dim == 2 && d == 2);
-    lo[d] = on && c[d] <= g.slab_lo_hi[d];
-    hi[d] = on && c[d] >= g.slab_hi_lo[d];
-  }
-}
-__global__ void k_ghost_count(Geom g, int nlocal, const double4 *xt, int *gcount)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nlocal) return;
-  double4 p = xt[i];
-  int lo[3], hi[3];
-  image_flags(g, p.x, p.y, p.z, lo, hi);
-  gcount[i] = (1 + lo[0] + hi[0]) * (1 + lo[1] + hi[1]) * (1 + lo[2] + hi[2]) - 1;
-}
-// descriptors (owner, image code) + ghost cell histogram
-__global__ void k_ghost_desc(Geom g, int nlocal, const double4 *xt, const int *tag, const int *goff, int *gown, int *gimg,
-                             int *gcell, int *gcellcnt, unsigned long long *gkey)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nlocal) return;
-  double4 p = xt[i];
-  int lo[3], hi[3];
-  image_flags(g, p.x, p.y, p.z, lo, hi);
-  int q = goff[i];
-  for (int pz = -1; pz <= 1; pz++) {
-    if ((pz == 1 && !lo[2]) || (pz == -1 && !hi[2])) continue;
-    for (int py = -1; py <= 1; py++) {
-      if ((py == 1 && !lo[1]) || (py == -1 && !hi[1])) continue;
-      for (int px = -1; px <= 1; px++) {
-        if ((px == 1 && !lo[0]) || (px == -1 && !hi[0])) continue;
-        if (!px && !py && !pz) continue;
-        double x = px ? __dadd_rn(p.x, px * g.prd[0]) : p.x;   // x[j][0] + pbc*xprd (pack_border)
-        double y = py ? __dadd_rn(p.y, py * g.prd[1]) : p.y;
-        double z = pz ? __dadd_rn(p.z, pz * g.prd[2]) : p.z;
-        int code = (px + 1) + 3 * (py + 1) + 9 * (pz + 1);
-        int c = cell_of(g, x, y, z);
-        gown[q] = i; gimg[q] = code; gcell[q] = c;
-        gkey[q] = ((unsigned long long)(unsigned)tag[i] << 5) | (unsigned)code;
-        atomicAdd(&gcellcnt[c], 1);
-        q++;
-      }
-    }
-  }
-}
-// materialise ghosts in cell order from their owners (pack_border[_vel] / unpack_border fields:
-// x+shift, tag, type, mask, rho, cg, rmass, e, cv, vest (+v); atom_vec_meso_multiphase.cpp:555-721)
-struct GhostArrays {
-  double4 *xt, *vr, *vm, *cgm;
-  double *e, *cv;
-  int *tag, *mask, *gowner, *gimage;
-};
-__global__ void k_ghost_fill(Geom g, int nlocal, int nghost, const int *gperm, const int *gown, const int *gimg,
-                             GhostArrays a, int multiphase, int *gslot)
+// Ghosts live behind the owned atoms in swap order (b200_comm.cuh).  For the build they are
+// addressed through a cell-ordered index list (gorder), sorted inside a cell by tag*32+image.
+__global__ void k_ghost_cells(Geom g, int nlocal, int nghost, const double4 *xt, const int *tag, const int *gimage, int *gcell, int *gcellcnt,
+                              unsigned long long *gkey)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nghost) return;
-  int q = gperm[s], i = gown[q], code = gimg[q], gi = nlocal + s;
-  int px = code % 3 - 1, py = (code / 3) % 3 - 1, pz = code / 9 - 1;
-  double4 p = a.xt[i];
-  if (px) p.x = __dadd_rn(p.x, px * g.prd[0]);
-  if (py) p.y = __dadd_rn(p.y, py * g.prd[1]);
-  if (pz) p.z = __dadd_rn(p.z, pz * g.prd[2]);
-  int type = tw_type(__double_as_longlong(p.w));
-  p.w = __longlong_as_double((long long)make_tw(g, type, p.x, p.y, p.z));
-  a.xt[gi] = p; a.vr[gi] = a.vr[i]; a.vm[gi] = a.vm[i];
-  if (multiphase) a.cgm[gi] = a.cgm[i];
-  a.e[gi] = a.e[i]; a.cv[gi] = a.cv[i];
-  a.tag[gi] = a.tag[i]; a.mask[gi] = a.mask[i]; a.gowner[gi] = i; a.gimage[gi] = code;
-  gslot[q] = gi;
-}
-// CommBrick::forward_comm with pack_comm[_vel] (atom_vec_meso_multiphase.cpp:319-465, atom_vec_meso.cpp:246-330):
-// x+shift, rho, [cg, rmass], e, vest (+v).  cv, type, tag, mask are NOT refreshed.
-__global__ void k_forward_comm(Geom g, int nlocal, int nghost, GhostArrays a, int multiphase, int ghost_velocity)
-{
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nghost) return;
-  int gi = nlocal + s, i = a.gowner[gi], code = a.gimage[gi];
-  int px = code % 3 - 1, py = (code / 3) % 3 - 1, pz = code / 9 - 1;
-  double4 p = a.xt[i], old = a.xt[gi];
-  if (px) p.x = __dadd_rn(p.x, px * g.prd[0]);
-  if (py) p.y = __dadd_rn(p.y, py * g.prd[1]);
-  if (pz) p.z = __dadd_rn(p.z, pz * g.prd[2]);
-  p.w = old.w;
-  a.xt[gi] = p; a.vr[gi] = a.vr[i];
-  double4 vo = a.vm[i], vg = a.vm[gi];
-  if (ghost_velocity) { vg.x = vo.x; vg.y = vo.y; vg.z = vo.z; }
-  if (multiphase) { vg.w = vo.w; a.cgm[gi] = a.cgm[i]; }
-  a.vm[gi] = vg;
-  a.e[gi] = a.e[i];
-}
-// CommBrick::forward_comm_pair for sph/rhosum (pair_sph_rhosum.cpp:203,290-313): ghost rho <- owner rho
-__global__ void k_ghost_rho(int nlocal, int nghost, const int *gowner, double4 *vr)
-{
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nghost) return;
-  int gi = nlocal + s;
-  vr[gi].w = vr[gowner[gi]].w;
+  double4 p = xt[nlocal + s];
+  int c = cell_of(g, p.x, p.y, p.z);
+  gcell[s] = c;
+  gkey[s] = ((unsigned long long)(unsigned)tag[nlocal + s] << 5) | (unsigned)gimage[nlocal + s];
+  atomicAdd(&gcellcnt[c], 1);
 }
 
 // ------------------------------------------------------------ the build -----
@@ -278,7 +204,8 @@ struct BuildArgs {
   int nlocal, nghost, stride, ntypes1;
   const double4 *xt;
   const int *orig;
-  const int *cso, *csg;          // cell starts: owned / ghost (ghost offsets relative to nlocal)
+  const int *cso, *csg;          // cell starts: owned / ghost (ghost cell segments index gorder)
+  const int *gorder;             // ghost slots in cell order (device index = nlocal + gorder[k])
   const double *cutneighsq;      // [MAXTT]
   const double *prunesq;         // [MAXTT] max over the sub-styles of cutsq(ti,tj): splits a row into an inner and an outer zone
   const double *farsq;           // [MAXTT] (cut + margin)^2: entries beyond go to the far rows (see FAR_MARGIN_FRAC)
@@ -325,10 +252,10 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
   const double cutmaxsq = g.cutneighmaxsq;
 
   for (int pass = 0; pass < 2; pass++) {          // 0: owned rows, 1: ghost rows
-    int nrow = pass ? nG : nO, r0 = pass ? A.nlocal + g0 : o0;
+    int nrow = pass ? nG : nO, r0 = o0;
     for (int rb = 0; rb < nrow; rb += 32) {
       bool valid = rb + lane < nrow;
-      int i = r0 + rb + lane;
+      int i = pass ? (valid ? A.nlocal + A.gorder[g0 + rb + lane] : 0) : r0 + rb + lane;
       double xi = 1e300, yi = 1e300, zi = 1e300;
       unsigned long long wi = 0; int oi = 0;
       if (valid) { double4 p = A.xt[i]; xi = p.x; yi = p.y; zi = p.z; wi = (unsigned long long)__double_as_longlong(p.w); if (!pass) oi = A.orig[i]; }
@@ -396,14 +323,15 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
             int nx = cx + dx; if (nx < 0 || nx >= g.nc[0]) continue;
             int n = (nz * g.nc[1] + ny) * g.nc[0] + nx;
             for (int rng = 0; rng < (pass ? 1 : 2); rng++) {
-              int s = rng ? A.nlocal + A.csg[n] : A.cso[n], e = rng ? A.nlocal + A.csg[n + 1] : A.cso[n + 1];
+              int s = rng ? A.csg[n] : A.cso[n], e = rng ? A.csg[n + 1] : A.cso[n + 1];
               while (s < e) {
                 int take = imin(BUILD_CH - fill, e - s);
                 for (int k = lane; k < take; k += 32) {
-                  double4 p = A.xt[s + k];
+                  int src = rng ? A.nlocal + A.gorder[s + k] : s + k;
+                  double4 p = A.xt[src];
                   sm.x[fill + k] = p.x; sm.y[fill + k] = p.y; sm.z[fill + k] = p.z;
                   sm.w[fill + k] = (unsigned long long)__double_as_longlong(p.w);
-                  sm.j[fill + k] = s + k; sm.o[fill + k] = (s + k < A.nlocal) ? A.orig[s + k] : 0;
+                  sm.j[fill + k] = src; sm.o[fill + k] = rng ? 0 : A.orig[src];
                 }
                 fill += take; s += take;
                 if (fill == BUILD_CH) { __syncwarp(); process(fill); __syncwarp(); fill = 0; }

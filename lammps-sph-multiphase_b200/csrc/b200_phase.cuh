@@ -23,7 +23,7 @@
 
 struct PcParams {
   b200_phase_change_desc d;
-  int dim, nlocal, nall, stride;
+  int dim, nlocal, nall, stride, norig;
   double dt;
   double sublo[3], subhi[3], boxhi[3];
 };
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const un
   const b200_phase_change_desc &d = P.d;
   const int lane = threadIdx.x;
   int seed = state[0], nins = 0;
-  for (int base = 0; base < P.nlocal; base += 32) {
+  for (int base = 0; base < P.norig; base += 32) {
     int o = base + lane;
-    unsigned char fl = o < P.nlocal ? flag[o] : 0;
+    unsigned char fl = o < P.norig ? flag[o] : 0;
     unsigned cand = __ballot_sync(FULLMASK, fl != 0);
     while (cand) {
       int b = __ffs(cand) - 1; cand &= cand - 1;
@@ -193,13 +193,12 @@ __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const un
   if (lane == 0) { state[0] = seed; state[1] = nins; }
 }
 
-// comm->reverse_comm_fix (dmass of ghosts -> owners) + the mass debit / energy renormalisation (:324-332)
-__global__ void k_pc_apply(int nlocal, PcArrays a, const double *dmass, const int *goff, const int *gslot, int have_ghosts)
+// (comm->reverse_comm_fix has already added the ghosts' dmass to their owners) the mass debit / energy renormalisation (:324-332)
+__global__ void k_pc_apply(int nlocal, PcArrays a, const double *dmass)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   double dm = dmass[i];
-  if (have_ghosts) for (int q = goff[i]; q < goff[i + 1]; q++) dm += dmass[gslot[q]];
   double4 v = a.vm[i];
   double mold = v.w;
   v.w = mold - dm;
@@ -211,7 +210,7 @@ __global__ void k_pc_apply(int nlocal, PcArrays a, const double *dmass, const in
 // append the new atoms behind the owned ones (AtomVecMesoMultiPhase::create_atom defaults,
 // atom_vec_meso_multiphase.cpp:968-997, then :301-317); tags = maxtag+1.. in creation order (Atom::tag_extend)
 struct AppendArrays { double4 *xt, *vr, *vm, *fd, *cgm; double *e, *de, *cv; int *tag, *mask, *orig; };
-__global__ void k_pc_append(int nlocal, int nins, const PcNew *newatoms, AppendArrays a, int to_type, double to_mass, int groupbit, int maxtag)
+__global__ void k_pc_append(int nlocal, int nins, const PcNew *newatoms, AppendArrays a, int to_type, double to_mass, int groupbit, int maxtag, int orig0)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nins) return;
@@ -223,5 +222,5 @@ __global__ void k_pc_append(int nlocal, int nins, const PcNew *newatoms, AppendA
   a.fd[m] = make_double4(0, 0, 0, 0);
   a.cgm[m] = make_double4(0, 0, 0, to_mass);
   a.e[m] = n.e; a.de[m] = 0.0; a.cv[m] = n.cv;
-  a.tag[m] = maxtag + 1 + k; a.mask[m] = 1 | groupbit; a.orig[m] = m;
+  a.tag[m] = maxtag + 1 + k; a.mask[m] = 1 | groupbit; a.orig[m] = orig0 + k;
 }

@@ -5,6 +5,9 @@
 #include "b200_pair.cuh"
 #include "b200_fix.cuh"
 #include "b200_phase.cuh"
+#include "b200_comm.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 
@@ -46,6 +49,46 @@ struct OwnedSet {
   OwnedArrays view() { return OwnedArrays{xt.p, vr.p, vm.p, fd.p, cgm.p, e.p, de.p, cv.p, tag.p, mask.p, orig.p}; }
 };
 
+// NCCL is bound at run time (dlopen) so that the library neither needs it on one GPU nor clashes with
+// the copy a host framework (torch) already loaded; only ncclSend/ncclRecv/ncclAllReduce/ncclAllGather are used.
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  void load()
+  {
+    if (lib) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int k = 0; names[k] && !lib; k++) lib = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) throw std::string("b200: cannot dlopen libnccl.so.2 (needed for multi-GPU runs)");
+#define BIND(f) *(void **)(&f) = dlsym(lib, "nccl" #f); if (!f) throw std::string("b200: libnccl lacks nccl" #f);
+    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(Send) BIND(Recv) BIND(AllReduce) BIND(AllGather) BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+#undef BIND
+  }
+};
+static NcclApi g_nccl;
+#define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) throw std::string(#call) + ": " + g_nccl.GetErrorString(r_); } while (0)
+
+// one direction of the 6-way staged ghost exchange (comm_brick.cpp:330-386): who I send to / receive from,
+// the slab of atoms I send, the periodic shift applied on sending
+struct Swap {
+  int dim, dir;                 // dir 0: send to the left neighbour (atoms near my lo face), 1: to the right
+  int sendproc, recvproc;
+  bool do_send, do_recv;
+  double shift, slablo, slabhi;
+  int imgstep;
+  DevBuf<int> sendlist;
+  int nsend = 0, nrecv = 0, firstrecv = 0;
+};
+
 struct Pass { int type; int kinds; int nslots; int slots[4]; };
 struct PcFix { b200_phase_change_desc d; long long next; int *d_state; };   // type: 0 rhosum 1 rhosum/mp 2 colorgradient 3 force
 
@@ -72,8 +115,15 @@ struct b200_sph {
   int nlocal = 0, nghost = 0;
   OwnedSet S[2]; int cur = 0;
   DevBuf<double4> rec;
-  DevBuf<int> gowner, gimage;
-  DevBuf<int> cellid, perm, perm2, gcount, gown, gimg, gcell, gperm, gperm2, gslot;
+  DevBuf<int> gimage;
+  DevBuf<int> cellid, perm, perm2, gcell, gperm, gorder, flag, pos, alive;
+  DevBuf<double> sendbuf, recvbuf;
+  // domain decomposition (one engine instance per rank / GPU)
+  int world = 1, rank = 0, procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0}, procneigh[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  ncclComm_t nccl = nullptr;
+  Swap swaps[6]; int nswap = 0;
+  int next_orig = 0;
+  double *d_red = nullptr, *h_red = nullptr;
   DevBuf<unsigned long long> key, gkey;
   DevBuf<int> cso, csg, cellfill, scan_tmp;
   DevBuf<double> xhold, stage_d, d_mass;
@@ -94,11 +144,11 @@ struct b200_sph {
   void ensure_cap(size_t n, bool keep)
   {
     S[0].ensure(n, keep && cur == 0, st); S[1].ensure(n, keep && cur == 1, st);
-    rec.ensure(n * 4, false, st); gowner.ensure(n, false, st); gimage.ensure(n, false, st);
+    rec.ensure(n * 4, false, st); gimage.ensure(n, true, st);
     numneigh.ensure(n, false, st); numfar.ensure(n, false, st);
   }
   StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p}; }
-  GhostArrays ghost_arrays() { OwnedSet &c = C(); return GhostArrays{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.tag.p, c.mask.p, gowner.p, gimage.p}; }
+  CommArrays comm_arrays() { OwnedSet &c = C(); return CommArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.cgm.p, c.e.p, c.de.p, c.cv.p, c.tag.p, c.mask.p, c.orig.p, gimage.p}; }
 
   // ---- timing helpers ----
   void tbegin(int which)
@@ -163,10 +213,10 @@ static void setup_geometry(b200_sph *h)
     g.prd[d] = g.boxhi[d] - g.boxlo[d];
     g.slab_lo_hi[d] = g.sublo[d] + g.cutghost;
     g.slab_hi_lo[d] = g.subhi[d] - g.cutghost;
-    bool swaps = g.periodic[d] && !(g.dim == 2 && d == 2);
+    bool swaps = (g.periodic[d] || h->procgrid[d] > 1) && !(g.dim == 2 && d == 2);
     if (swaps) {
-      int maxneed = (int)(g.cutghost * 1 / g.prd[d]) + 1;   // comm_brick.cpp:228-230 on a 1x1x1 grid
-      if (maxneed > 1) throw std::string("b200: ghost cutoff >= box length in a periodic dimension is not supported");
+      int maxneed = (int)(g.cutghost * h->procgrid[d] / g.prd[d]) + 1;   // comm_brick.cpp:228-230
+      if (maxneed > 1) throw std::string("b200: ghost cutoff >= sub-domain length is not supported (one ghost layer of neighbour ranks)");
     }
     double lo = swaps ? g.sublo[d] - g.cutghost : g.sublo[d];
     double hi = swaps ? g.subhi[d] + g.cutghost : g.subhi[d];
@@ -196,11 +246,185 @@ static void setup_geometry(b200_sph *h)
   g.cutneighmaxsq = cut * cut;
   h->cso.ensure(g.ncells + 2); h->csg.ensure(g.ncells + 2); h->cellfill.ensure(g.ncells + 2);
   CK(cudaMemsetAsync(h->csg.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+  // swaps: CommBrick::setup, comm_brick.cpp:330-386 (maxneed = 1)
+  h->nswap = 0;
+  for (int d = 0; d < 3; d++) {
+    bool any = (g.periodic[d] || h->procgrid[d] > 1) && !(g.dim == 2 && d == 2);
+    if (!any) continue;
+    for (int dir = 0; dir < 2; dir++) {
+      Swap &s = h->swaps[h->nswap++];
+      s.dim = d; s.dir = dir;
+      s.sendproc = h->procneigh[d][dir]; s.recvproc = h->procneigh[d][dir ^ 1];
+      int loc = h->myloc[d], pg = h->procgrid[d];
+      if (dir == 0) {
+        s.slablo = -1.0e300; s.slabhi = g.sublo[d] + g.cutghost;
+        s.do_send = g.periodic[d] || loc > 0; s.do_recv = g.periodic[d] || loc < pg - 1;
+        s.shift = (loc == 0) ? g.prd[d] : 0.0; s.imgstep = (loc == 0) ? 1 : 0;
+      } else {
+        s.slablo = g.subhi[d] - g.cutghost; s.slabhi = 1.0e300;
+        s.do_send = g.periodic[d] || loc < pg - 1; s.do_recv = g.periodic[d] || loc > 0;
+        s.shift = (loc == pg - 1) ? -g.prd[d] : 0.0; s.imgstep = (loc == pg - 1) ? -1 : 0;
+      }
+      s.imgstep *= (d == 0 ? 1 : (d == 1 ? 3 : 9));
+      s.nsend = s.nrecv = 0;
+    }
+  }
   h->geom_ready = true;
 }
 
-// ------------------------------------------------------------- reneighbor ---
+// ------------------------------------------------------------------ comm ----
+// buf_send -> (NCCL send/recv | local) -> buf the receiver unpacks from
+static double *swap_transfer(b200_sph *h, Swap &s, size_t nsend_d, size_t nrecv_d)
+{
+  if (s.sendproc == h->rank && s.recvproc == h->rank) return h->sendbuf.p;      // "if swapping with self, simply copy" (comm_brick.cpp:800)
+  h->recvbuf.ensure(nrecv_d + 1);
+  NCK(g_nccl.GroupStart());
+  if (nsend_d) NCK(g_nccl.Send(h->sendbuf.p, nsend_d, ncclDouble, s.sendproc, h->nccl, h->st));
+  if (nrecv_d) NCK(g_nccl.Recv(h->recvbuf.p, nrecv_d, ncclDouble, s.recvproc, h->nccl, h->st));
+  NCK(g_nccl.GroupEnd());
+  return h->recvbuf.p;
+}
+static void swap_counts(b200_sph *h, Swap &s)       // the 1-int MPI_Sendrecv of borders() (:819)
+{
+  if (s.sendproc == h->rank && s.recvproc == h->rank) { s.nrecv = s.nsend; return; }
+  h->h_red[0] = (double)s.nsend;
+  CK(cudaMemcpyAsync(h->d_red, h->h_red, sizeof(double), cudaMemcpyHostToDevice, h->st));
+  NCK(g_nccl.GroupStart());
+  NCK(g_nccl.Send(h->d_red, 1, ncclDouble, s.sendproc, h->nccl, h->st));
+  NCK(g_nccl.Recv(h->d_red + 1, 1, ncclDouble, s.recvproc, h->nccl, h->st));
+  NCK(g_nccl.GroupEnd());
+  CK(cudaMemcpyAsync(h->h_red + 1, h->d_red + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  s.nrecv = (int)h->h_red[1];
+}
+static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch);
 static void ensure_scan_tmp(b200_sph *h, size_t n) { h->scan_tmp.ensure(n / (SCAN_T * SCAN_E) * 2 + 4096); }
+
+// CommBrick::borders, comm_brick.cpp:696-864
+static void comm_borders(b200_sph *h)
+{
+  const int B = 256;
+  Geom &g = h->g;
+  h->nghost = 0;
+  int k = 0;
+  while (k < h->nswap) {
+    int dim = h->swaps[k].dim;
+    int nlast = h->nlocal + h->nghost;                 // both swaps of a dimension scan the atoms present before it (:722-725)
+    for (; k < h->nswap && h->swaps[k].dim == dim; k++) {
+      Swap &s = h->swaps[k];
+      s.nsend = 0;
+      if (s.do_send && nlast) {
+        h->flag.ensure(nlast + 2); h->pos.ensure(nlast + 2); ensure_scan_tmp(h, nlast + 2);
+        LAUNCH(h, k_slab_flag, nblk(nlast, B), B, nlast, h->C().xt.p, dim, s.slablo, s.slabhi, h->flag.p, h->pos.p);
+        scan_exclusive(h, h->pos.p, nlast, h->scan_tmp.p);
+        CK(cudaMemcpyAsync(h->h_flags + 4, h->pos.p + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        s.nsend = h->h_flags[4];
+        s.sendlist.ensure(s.nsend + 1);
+        if (s.nsend) LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, h->flag.p, h->pos.p, s.sendlist.p);
+      }
+      h->sendbuf.ensure((size_t)s.nsend * NB_BORDER + 1);
+      if (s.nsend) LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, h->sendbuf.p);
+      swap_counts(h, s);
+      if (!s.do_recv) s.nrecv = 0;
+      s.firstrecv = h->nlocal + h->nghost;
+      h->ensure_cap((size_t)s.firstrecv + s.nrecv, true);
+      double *buf = swap_transfer(h, s, (size_t)s.nsend * NB_BORDER, (size_t)s.nrecv * NB_BORDER);
+      if (s.nrecv) LAUNCH(h, k_unpack_border, nblk(s.nrecv, B), B, g, s.nrecv, s.firstrecv, h->comm_arrays(), buf);
+      h->nghost += s.nrecv;
+    }
+  }
+}
+// generic staged swap loop: forward direction
+template <class Pack, class Unpack> static void comm_forward_generic(b200_sph *h, int width, Pack pack, Unpack unpack)
+{
+  for (int k = 0; k < h->nswap; k++) {
+    Swap &s = h->swaps[k];
+    h->sendbuf.ensure((size_t)s.nsend * width + 1);
+    if (s.nsend) pack(s);
+    double *buf = swap_transfer(h, s, (size_t)s.nsend * width, (size_t)s.nrecv * width);
+    if (s.nrecv) unpack(s, buf);
+  }
+}
+// reverse direction: ghosts' values go back to the atoms they were copied from (comm_brick.cpp:513-560)
+template <class Pack, class Unpack> static void comm_reverse_generic(b200_sph *h, int width, Pack pack, Unpack unpack)
+{
+  for (int k = h->nswap - 1; k >= 0; k--) {
+    Swap &s = h->swaps[k];
+    h->sendbuf.ensure((size_t)s.nrecv * width + 1);
+    if (s.nrecv) pack(s);
+    double *buf;
+    if (s.sendproc == h->rank && s.recvproc == h->rank) buf = h->sendbuf.p;
+    else {
+      h->recvbuf.ensure((size_t)s.nsend * width + 1);
+      NCK(g_nccl.GroupStart());
+      if (s.nrecv) NCK(g_nccl.Send(h->sendbuf.p, (size_t)s.nrecv * width, ncclDouble, s.recvproc, h->nccl, h->st));
+      if (s.nsend) NCK(g_nccl.Recv(h->recvbuf.p, (size_t)s.nsend * width, ncclDouble, s.sendproc, h->nccl, h->st));
+      NCK(g_nccl.GroupEnd());
+      buf = h->recvbuf.p;
+    }
+    if (s.nsend) unpack(s, buf);
+  }
+}
+static void comm_reverse_scalar_add(b200_sph *h, double *arr)      // comm->reverse_comm_fix (dmass)
+{
+  const int B = 256;
+  comm_reverse_generic(h, 1,
+    [&](Swap &s) { LAUNCH(h, k_pack_scalar, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, arr, h->sendbuf.p); },
+    [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_scalar_add, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, arr, buf); });
+}
+// CommBrick::exchange, comm_brick.cpp:573-684: returns the number of slots now in use (dead ones included)
+static int comm_exchange(b200_sph *h, int nslots)
+{
+  const int B = 256;
+  Geom &g = h->g;
+  for (int d = 0; d < 3; d++) {
+    if (h->procgrid[d] == 1 || (g.dim == 2 && d == 2)) continue;
+    h->flag.ensure(nslots + 2); h->pos.ensure(nslots + 2); ensure_scan_tmp(h, nslots + 2);
+    LAUNCH(h, k_exchange_flag, nblk(nslots, B), B, nslots, h->C().xt.p, h->alive.p, d, g.sublo[d], g.subhi[d], h->flag.p, h->pos.p);
+    scan_exclusive(h, h->pos.p, nslots, h->scan_tmp.p);
+    CK(cudaMemcpyAsync(h->h_flags + 4, h->pos.p + nslots, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int nsend = h->h_flags[4];
+    h->perm.ensure(nsend + 1);
+    h->sendbuf.ensure((size_t)nsend * NB_EXCHANGE + 1);
+    if (nsend) {
+      LAUNCH(h, k_compact, nblk(nslots, B), B, nslots, h->flag.p, h->pos.p, h->perm.p);
+      LAUNCH(h, k_pack_exchange, nblk(nsend, B), B, nsend, h->perm.p, h->comm_arrays(), h->alive.p, h->sendbuf.p);
+    }
+    // the whole buffer goes to both neighbours; each keeps what falls inside its bounds (:640-664)
+    int left = h->procneigh[d][0], right = h->procneigh[d][1];
+    int nrecv[2] = {0, 0};
+    for (int side = 0; side < (left == right ? 1 : 2); side++) {
+      int to = side ? right : left, from = side ? left : right;
+      h->h_red[0] = (double)nsend;
+      CK(cudaMemcpyAsync(h->d_red, h->h_red, sizeof(double), cudaMemcpyHostToDevice, h->st));
+      NCK(g_nccl.GroupStart());
+      NCK(g_nccl.Send(h->d_red, 1, ncclDouble, to, h->nccl, h->st));
+      NCK(g_nccl.Recv(h->d_red + 1, 1, ncclDouble, from, h->nccl, h->st));
+      NCK(g_nccl.GroupEnd());
+      CK(cudaMemcpyAsync(h->h_red + 1, h->d_red + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      nrecv[side] = (int)h->h_red[1];
+      h->recvbuf.ensure((size_t)nrecv[side] * NB_EXCHANGE + 1);
+      NCK(g_nccl.GroupStart());
+      if (nsend) NCK(g_nccl.Send(h->sendbuf.p, (size_t)nsend * NB_EXCHANGE, ncclDouble, to, h->nccl, h->st));
+      if (nrecv[side]) NCK(g_nccl.Recv(h->recvbuf.p, (size_t)nrecv[side] * NB_EXCHANGE, ncclDouble, from, h->nccl, h->st));
+      NCK(g_nccl.GroupEnd());
+      if (nrecv[side]) {
+        h->ensure_cap((size_t)nslots + nrecv[side], true); h->alive.ensure((size_t)nslots + nrecv[side] + 1, true, h->st);
+        CK(cudaMemsetAsync(h->d_flags + 3, 0, sizeof(int), h->st));
+        LAUNCH(h, k_unpack_exchange, nblk(nrecv[side], B), B, nrecv[side], h->recvbuf.p, d, g.sublo[d], g.subhi[d], nslots, h->comm_arrays(), h->alive.p,
+               h->d_flags + 3, h->next_orig);
+        nslots += nrecv[side]; h->next_orig += nrecv[side];
+      }
+    }
+  }
+  return nslots;
+}
+
+
+// ------------------------------------------------------------- reneighbor ---
 
 static void neighbor_build(b200_sph *h, bool do_pbc)
 {
@@ -209,46 +433,54 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   int nl = h->nlocal;
   h->tbegin(T_NEIGH_BIN);
   h->ensure_cap(nl + h->nghost, true);
-  h->cellid.ensure(nl); h->perm.ensure(nl); h->perm2.ensure(nl); h->key.ensure(nl); h->gcount.ensure(nl + 2);
-  ensure_scan_tmp(h, std::max<size_t>(nl + 2, g.ncells + 2));
-  // 1. owned atoms -> cell order
+  // 0. multi-rank: wrap, then migrate atoms that left the sub-domain (verlet.cpp:243-250)
+  int nslots = nl;
+  const int *alive = nullptr;
+  if (h->world > 1) {
+    h->alive.ensure(nl + 1);
+    if (nl) {
+      LAUNCH(h, k_pbc, nblk(nl, B), B, g, nl, h->C().xt.p);
+      LAUNCH(h, k_fill_int, nblk(nl, B), B, nl, h->alive.p, 1);
+    }
+    nslots = comm_exchange(h, nl);
+    alive = h->alive.p; do_pbc = false;
+  }
+  h->cellid.ensure(nslots + 1); h->perm.ensure(nslots + 1); h->perm2.ensure(nslots + 1); h->key.ensure(nslots + 1);
+  ensure_scan_tmp(h, std::max<size_t>(nslots + 2, g.ncells + 2));
+  // 1. owned atoms -> cell order (dead slots drop out)
   CK(cudaMemsetAsync(h->cso.p, 0, (g.ncells + 2) * sizeof(int), h->st));
   CK(cudaMemsetAsync(h->cellfill.p, 0, (g.ncells + 2) * sizeof(int), h->st));
-  if (nl) {
-    LAUNCH(h, k_owned_cells, nblk(nl, B), B, g, nl, h->C().xt.p, h->cellid.p, h->cso.p, do_pbc ? 1 : 0);
+  if (nslots) {
+    LAUNCH(h, k_owned_cells, nblk(nslots, B), B, g, nslots, h->C().xt.p, h->cellid.p, h->cso.p, do_pbc ? 1 : 0, alive);
     scan_exclusive(h, h->cso.p, g.ncells, h->scan_tmp.p);
-    LAUNCH(h, k_scatter, nblk(nl, B), B, nl, h->cellid.p, h->cso.p, h->cellfill.p, h->perm.p);
-    LAUNCH(h, k_owned_keys, nblk(nl, B), B, nl, h->C().tag.p, h->key.p);
+    if (h->world > 1) {
+      CK(cudaMemcpyAsync(h->h_flags + 4, h->cso.p + g.ncells, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      nl = h->h_flags[4];
+    }
+    LAUNCH(h, k_scatter, nblk(nslots, B), B, nslots, h->cellid.p, h->cso.p, h->cellfill.p, h->perm.p);
+    LAUNCH(h, k_owned_keys, nblk(nslots, B), B, nslots, h->C().tag.p, h->key.p);
     LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->cso.p, h->perm.p, h->perm2.p, h->key.p);
     OwnedSet &a = h->S[h->cur], &b = h->S[h->cur ^ 1];
-    LAUNCH(h, k_permute_owned, nblk(nl, B), B, g, nl, h->perm2.p, a.view(), b.view(), h->multiphase, h->key.p);
+    b.ensure(std::max(nslots, nl), false, h->st);
+    if (nl) LAUNCH(h, k_permute_owned, nblk(nl, B), B, g, nl, h->perm2.p, a.view(), b.view(), h->multiphase, h->key.p);
     h->cur ^= 1;
   }
-  // 2. ghosts (periodic self-images)
-  bool any_swap = false;
-  for (int d = 0; d < 3; d++) any_swap |= g.periodic[d] && !(g.dim == 2 && d == 2);
-  h->nghost = 0;
+  h->nlocal = nl;
+  if (nl) LAUNCH(h, k_fill_int, nblk(nl, B), B, nl, h->gimage.p, 13);
+  // 2. ghosts: the staged x, y, z swaps of CommBrick::borders, then a cell-ordered index of them
+  comm_borders(h);
+  int ng = h->nghost;
   CK(cudaMemsetAsync(h->csg.p, 0, (g.ncells + 2) * sizeof(int), h->st));
-  if (any_swap && nl) {
-    LAUNCH(h, k_ghost_count, nblk(nl, B), B, g, nl, h->C().xt.p, h->gcount.p);
-    scan_exclusive(h, h->gcount.p, nl, h->scan_tmp.p);
-    CK(cudaMemcpyAsync(h->h_flags + 4, h->gcount.p + nl, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    int ng = h->h_flags[4];
-    h->nghost = ng;
-    if (ng) {
-      h->ensure_cap(nl + ng, true);
-      h->gown.ensure(ng); h->gimg.ensure(ng); h->gcell.ensure(ng); h->gperm.ensure(ng); h->gperm2.ensure(ng); h->gslot.ensure(ng); h->gkey.ensure(ng);
-      CK(cudaMemsetAsync(h->cellfill.p, 0, (g.ncells + 2) * sizeof(int), h->st));
-      LAUNCH(h, k_ghost_desc, nblk(nl, B), B, g, nl, h->C().xt.p, h->C().tag.p, h->gcount.p, h->gown.p, h->gimg.p, h->gcell.p, h->csg.p, h->gkey.p);
-      scan_exclusive(h, h->csg.p, g.ncells, h->scan_tmp.p);
-      LAUNCH(h, k_scatter, nblk(ng, B), B, ng, h->gcell.p, h->csg.p, h->cellfill.p, h->gperm.p);
-      LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->csg.p, h->gperm.p, h->gperm2.p, h->gkey.p);
-      LAUNCH(h, k_ghost_fill, nblk(ng, B), B, g, nl, ng, h->gperm2.p, h->gown.p, h->gimg.p, h->ghost_arrays(), h->multiphase, h->gslot.p);
-    }
-  } else if (nl) {
-    CK(cudaMemsetAsync(h->gcount.p, 0, (nl + 2) * sizeof(int), h->st));
+  if (ng) {
+    h->gcell.ensure(ng); h->gperm.ensure(ng); h->gorder.ensure(ng); h->gkey.ensure(ng);
+    CK(cudaMemsetAsync(h->cellfill.p, 0, (g.ncells + 2) * sizeof(int), h->st));
+    LAUNCH(h, k_ghost_cells, nblk(ng, B), B, g, nl, ng, h->C().xt.p, h->C().tag.p, h->gimage.p, h->gcell.p, h->csg.p, h->gkey.p);
+    scan_exclusive(h, h->csg.p, g.ncells, h->scan_tmp.p);
+    LAUNCH(h, k_scatter, nblk(ng, B), B, ng, h->gcell.p, h->csg.p, h->cellfill.p, h->gperm.p);
+    LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->csg.p, h->gperm.p, h->gorder.p, h->gkey.p);
   }
+  h->ensure_cap(nl + ng, true);
   if ((h->check || h->far_margin > 0.0) && nl) { h->xhold.ensure((size_t)3 * nl); LAUNCH(h, k_store_xhold, nblk(nl, B), B, nl, h->C().xt.p, h->xhold.p); }
   h->tend();
   // 3. rows
@@ -259,7 +491,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
     BuildArgs A;
     A.g = g; A.nlocal = nl; A.nghost = h->nghost; A.stride = h->stride; A.ntypes1 = h->ntypes + 1;
-    A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.cutneighsq = h->d_cutneighsq.p; A.prunesq = h->d_prunesq.p; A.farsq = h->d_farsq.p; A.far = h->far.p; A.numfar = h->numfar.p;
+    A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.gorder = h->gorder.p; A.cutneighsq = h->d_cutneighsq.p; A.prunesq = h->d_prunesq.p; A.farsq = h->d_farsq.p; A.far = h->far.p; A.numfar = h->numfar.p;
     A.nbr = h->nbr.p; A.numneigh = h->numneigh.p; A.maxcount = h->d_flags;
     LAUNCH(h, k_build, nblk(g.ncells, BUILD_WARPS), BUILD_WARPS * 32, A);
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -360,7 +592,10 @@ static void run_pass(b200_sph *h, const Pass &p)
     if (p.type == 0) {
       h->tbegin(T_DENSITY);
       if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_THREADS, A);
-      if (h->nghost) LAUNCH(h, k_ghost_rho, nblk(h->nghost, B), B, h->nlocal, h->nghost, h->gowner.p, h->C().vr.p);  // forward_comm_pair (:203)
+      if (h->nghost)       // comm->forward_comm_pair (:203)
+        comm_forward_generic(h, 1,
+          [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
+          [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
       h->tend();
     } else if (p.type == 1) {
       h->tbegin(T_DENSITY);
@@ -423,10 +658,14 @@ static void force_clear(b200_sph *h)
 static void pair_compute_all(b200_sph *h) { for (const Pass &p : h->plan) run_pass(h, p); }
 static void post_final(b200_sph *h, int rev, int post, int fin)
 {
-  if (!h->nlocal) return;
+  const int B = 256;
   h->tbegin(T_FINAL);
-  LAUNCH(h, k_post_final, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, rev && h->nghost, post, fin,
-         h->gcount.p, h->gslot.p);
+  if (rev && (h->nghost || h->world > 1))
+    comm_reverse_generic(h, NB_REVERSE,
+      [&](Swap &s) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), h->sendbuf.p); },
+      [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
+  if ((post || fin) && h->nlocal)
+    LAUNCH(h, k_post_final, nblk(h->nlocal, B), B, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, post, fin);
   h->tend();
 }
 static void initial_integrate(b200_sph *h)
@@ -437,14 +676,21 @@ static void initial_integrate(b200_sph *h)
   int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
          h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq);
-  if (track) LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->d_scan_far);
+  if (track) {
+    // ghosts move with their owners on other ranks: the displacement bound must be global (bit patterns of non-negative doubles order like uint64)
+    if (h->world > 1) NCK(g_nccl.AllReduce(h->d_dmaxsq, h->d_dmaxsq, 1, ncclUint64, ncclMax, h->nccl, h->st));
+    LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->d_scan_far);
+  }
   h->tend();
 }
 static void forward_comm(b200_sph *h)
 {
-  if (!h->nghost) return;
+  if (!h->nghost && h->world == 1) return;
+  const int B = 256;
   h->tbegin(T_COMM);
-  LAUNCH(h, k_forward_comm, nblk(h->nghost, 256), 256, h->g, h->nlocal, h->nghost, h->ghost_arrays(), h->multiphase, h->ghost_velocity);
+  comm_forward_generic(h, NB_FORWARD,
+    [&](Swap &s) { LAUNCH(h, k_pack_forward, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), s.dim, s.shift, h->sendbuf.p); },
+    [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_forward, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), buf, h->multiphase, h->ghost_velocity); });
   h->tend();
 }
 // Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
@@ -454,6 +700,7 @@ static int neigh_decide(b200_sph *h)
   h->ago++;
   if (h->ago >= h->delay && h->ago % h->every == 0) {
     if (!h->check) return 1;
+    if (h->world > 1) NCK(g_nccl.AllReduce(h->d_flags + 1, h->d_flags + 1, 1, ncclInt, ncclMax, h->nccl, h->st));   // MPI_Allreduce MAX (neighbor.cpp:1407)
     CK(cudaMemcpyAsync(h->h_flags + 1, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     int flag = h->h_flags[1];
@@ -470,8 +717,10 @@ static void phase_change(b200_sph *h, PcFix &f)
   int nl = h->nlocal, na = h->nall();
   if (!nl) return;
   h->tbegin(T_PHASE);
-  h->pc_flag.ensure(nl); h->pc_thr.ensure(nl); h->pc_dev.ensure(nl); h->pc_dmass.ensure(na); h->pc_new.ensure(PC_MAXNEW);
-  PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.stride = h->stride; P.dt = h->dt;
+  int norig = std::max(h->next_orig, nl);
+  h->pc_flag.ensure(norig); h->pc_thr.ensure(norig); h->pc_dev.ensure(norig); h->pc_dmass.ensure(na); h->pc_new.ensure(PC_MAXNEW);
+  CK(cudaMemsetAsync(h->pc_flag.p, 0, norig, h->st));
+  PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.norig = norig; P.stride = h->stride; P.dt = h->dt;
   for (int d = 0; d < 3; d++) { P.sublo[d] = h->g.sublo[d]; P.subhi[d] = h->g.subhi[d]; P.boxhi[d] = h->g.boxhi[d]; }
   OwnedSet &c = h->C();
   PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p};
@@ -479,17 +728,32 @@ static void phase_change(b200_sph *h, PcFix &f)
   CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
   LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state);
   CK(cudaMemcpyAsync(h->h_flags + 5, f.d_state + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p, h->gcount.p, h->gslot.p, h->nghost > 0);
+  if (h->nghost || h->world > 1) comm_reverse_scalar_add(h, h->pc_dmass.p);      // comm->reverse_comm_fix (:324)
+  LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p);
   CK(cudaStreamSynchronize(h->st));
   int nins = h->h_flags[5];
   if (h->h_flags[6]) throw std::string("fix phase_change: more than PC_MAXNEW insertions in one call");
+  int tag0 = h->maxtag, ninsall = nins;
+  if (h->world > 1) {        // Atom::tag_extend: MPI_Scan of the per-rank counts (atom.cpp:598-630)
+    std::vector<int> all(h->world);
+    h->h_flags[9] = nins;
+    CK(cudaMemcpyAsync(h->d_flags + 9, h->h_flags + 9, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    DevBuf<int> tmp; tmp.ensure(h->world);
+    NCK(g_nccl.AllGather(h->d_flags + 9, tmp.p, 1, ncclInt, h->nccl, h->st));
+    CK(cudaMemcpyAsync(all.data(), tmp.p, h->world * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    tmp.release();
+    ninsall = 0;
+    for (int r = 0; r < h->world; r++) { if (r < h->rank) tag0 += all[r]; ninsall += all[r]; }
+  }
   if (nins > 0) {
     h->ensure_cap((size_t)nl + nins, true);
     OwnedSet &cc = h->C();
     AppendArrays ap{cc.xt.p, cc.vr.p, cc.vm.p, cc.fd.p, cc.cgm.p, cc.e.p, cc.de.p, cc.cv.p, cc.tag.p, cc.mask.p, cc.orig.p};
-    LAUNCH(h, k_pc_append, nblk(nins, 128), 128, nl, nins, h->pc_new.p, ap, f.d.to_type, f.d.to_mass, f.d.groupbit, h->maxtag);
-    h->nlocal += nins; h->nghost = 0; h->maxtag += nins; h->ninserted += nins;
+    LAUNCH(h, k_pc_append, nblk(nins, 128), 128, nl, nins, h->pc_new.p, ap, f.d.to_type, f.d.to_mass, f.d.groupbit, tag0, h->next_orig);
+    h->nlocal += nins; h->next_orig += nins; h->ninserted += nins;
   }
+  if (ninsall > 0) { h->nghost = 0; h->maxtag += ninsall; }
   h->tend();
 }
 static void reneighbor(b200_sph *h)
@@ -606,6 +870,7 @@ int b200_create(b200_sph **out, int device)
   CK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
   CK(cudaMalloc(&h->d_dmaxsq, sizeof(unsigned long long))); CK(cudaMemset(h->d_dmaxsq, 0, sizeof(unsigned long long)));
   h->d_scan_far = h->d_flags + 8;
+  CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
   CK(cudaMallocHost(&h->h_flags, 16 * sizeof(int)));
   memset(&h->fl, 0, sizeof h->fl);
   *out = h;
@@ -617,15 +882,44 @@ int b200_destroy(b200_sph *h)
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state);
-  h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gowner.release(); h->gimage.release();
-  h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcount.release(); h->gown.release(); h->gimg.release(); h->gcell.release();
-  h->gperm.release(); h->gperm2.release(); h->gslot.release(); h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
+  h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gimage.release();
+  h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
+  h->sendbuf.release(); h->recvbuf.release(); for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
+  if (h->nccl) g_nccl.CommDestroy(h->nccl);
+  cudaFree(h->d_red); cudaFreeHost(h->h_red);
+  h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
   delete h;
   return 0;
+}
+
+int b200_comm_unique_id(char id[128])
+{
+  API_BEGIN
+  g_nccl.load();
+  static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId size");
+  ncclUniqueId u;
+  NCK(g_nccl.GetUniqueId(&u));
+  memset(id, 0, 128); memcpy(id, &u, sizeof u);
+  API_END
+}
+int b200_comm_init(b200_sph *h, int world, int rank, const int procgrid[3], const int myloc[3], const int procneigh[6], const char id[128])
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  if (world < 1 || rank < 0 || rank >= world || procgrid[0] * procgrid[1] * procgrid[2] != world) throw std::string("b200_comm_init: bad rank / processor grid");
+  h->world = world; h->rank = rank;
+  for (int d = 0; d < 3; d++) { h->procgrid[d] = procgrid[d]; h->myloc[d] = myloc[d]; h->procneigh[d][0] = procneigh[2 * d]; h->procneigh[d][1] = procneigh[2 * d + 1]; }
+  if (world > 1) {
+    g_nccl.load();
+    ncclUniqueId u; memcpy(&u, id, sizeof u);
+    NCK(g_nccl.CommInitRank(&h->nccl, world, u, rank));
+  }
+  h->geom_ready = false;
+  API_END
 }
 
 int b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[3], const int periodicity[3], const double sublo[3],
@@ -637,7 +931,7 @@ int b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[
   for (int d = 0; d < 3; d++) {
     h->g.boxlo[d] = boxlo[d]; h->g.boxhi[d] = boxhi[d]; h->g.periodic[d] = periodicity[d];
     h->g.sublo[d] = sublo ? sublo[d] : boxlo[d]; h->g.subhi[d] = subhi ? subhi[d] : boxhi[d];
-    if (h->g.sublo[d] != boxlo[d] || h->g.subhi[d] != boxhi[d]) throw std::string("b200_domain: sub-domains (multi-GPU bricks) are not implemented yet");
+    if ((h->g.sublo[d] != boxlo[d] || h->g.subhi[d] != boxhi[d]) && h->world == 1) throw std::string("b200_domain: a sub-domain smaller than the box needs b200_comm_init first");
   }
   h->have_domain = true; h->geom_ready = false;
   API_END
@@ -749,7 +1043,7 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
   h->nlocal = n; h->nghost = 0; h->cur = 0;
   h->ensure_cap(n, false);
   h->setup_done = false;
-  h->maxtag = n;
+  h->maxtag = n; h->next_orig = n;
   if (a->tag) for (int i = 0; i < n; i++) h->maxtag = std::max(h->maxtag, a->tag[i]);
   if (!n) return 0;
   size_t nd, ni;
@@ -771,6 +1065,22 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
 }
 int b200_get_natoms(b200_sph *h, int *nlocal, int *nghost) { if (nlocal) *nlocal = h->nlocal; if (nghost) *nghost = h->nghost; return 0; }
 
+// output index of every owned device slot: the LAMMPS local index (one rank), or the rank of that index
+// when migration has made the local-index sequence sparse (several ranks)
+static std::vector<int> out_positions(b200_sph *h)
+{
+  int n = h->nlocal;
+  std::vector<int> orig(n), pos(n);
+  CK(cudaStreamSynchronize(h->st));
+  if (n) CK(cudaMemcpy(orig.data(), h->C().orig.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h->world == 1) return orig;
+  std::vector<int> idx(n);
+  for (int s = 0; s < n; s++) idx[s] = s;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return orig[a] < orig[b]; });
+  for (int r = 0; r < n; r++) pos[idx[r]] = r;
+  return pos;
+}
+
 int b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a)
 {
   API_BEGIN
@@ -780,7 +1090,15 @@ int b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a)
   if (!n) return 0;
   size_t nd, ni;
   HostMirror m = stage_layout(h, n, a, &nd, &ni);
-  LAUNCH(h, k_unpack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase);
+  const int *outpos = nullptr;
+  if (h->world > 1) {
+    std::vector<int> pos = out_positions(h);
+    h->perm.ensure(n);
+    CK(cudaMemcpyAsync(h->perm.p, pos.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    outpos = h->perm.p;
+  }
+  LAUNCH(h, k_unpack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase, outpos);
 #define DOWN(dev, host, w) if (a->host) CK(cudaMemcpyAsync(a->host, m.dev, (size_t)(w) * n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   FOR_FIELDS(DOWN)
 #undef DOWN
@@ -822,9 +1140,9 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   int n = nlocal, na = h->nall();
   if (!n) return 0;
   CK(cudaStreamSynchronize(h->st));
-  std::vector<int> cnt(n), orig(n), tag(na), img(na);
+  std::vector<int> cnt(n), tag(na), img(na);
+  std::vector<int> orig = out_positions(h);
   CK(cudaMemcpy(cnt.data(), h->numneigh.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(orig.data(), h->C().orig.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<int> cfar(n);
   CK(cudaMemcpy(cfar.data(), h->numfar.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   for (int s = 0; s < n; s++) numneigh[orig[s]] = (cnt[s] & 0xffff) + (cnt[s] >> 16) + cfar[s];
@@ -834,8 +1152,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   for (int i = 0; i < n; i++) { off[i] = tot; tot += numneigh[i]; }
   if (nentries < tot) throw std::string("b200_get_neighbor_list: buffer too small");
   CK(cudaMemcpy(tag.data(), h->C().tag.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
-  if (h->nghost) CK(cudaMemcpy(img.data() + n, h->gimage.p + n, (size_t)h->nghost * sizeof(int), cudaMemcpyDeviceToHost));
-  for (int s = 0; s < n; s++) img[s] = 13;
+  CK(cudaMemcpy(img.data(), h->gimage.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<unsigned> rows((size_t)((n + 31) / 32) * 32 * h->stride);
   CK(cudaMemcpy(rows.data(), h->nbr.p, rows.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
   std::vector<unsigned> frows(rows.size());

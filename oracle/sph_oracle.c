@@ -140,6 +140,10 @@ int osph_destroy(osph_sph *s)
   return 0;
 }
 
+int osph_comm_unique_id(char id[128]) { memset(id, 0, 128); return 0; }
+int osph_comm_init(osph_sph *s, int world, int rank, const int procgrid[3], const int myloc[3], const int procneigh[6], const char id[128])
+{ (void)s; (void)rank; (void)procgrid; (void)myloc; (void)procneigh; (void)id; return world == 1 ? 0 : fail("the oracle is single-rank"); }
+
 int osph_domain(osph_sph *s, int dim, const double boxlo[3], const double boxhi[3], const int periodicity[3],
                 const double sublo[3], const double subhi[3])
 {

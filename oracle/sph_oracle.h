@@ -13,6 +13,8 @@
 #define b200_destroy           osph_destroy
 #define b200_last_error        osph_last_error
 #define b200_version           osph_version
+#define b200_comm_unique_id    osph_comm_unique_id
+#define b200_comm_init         osph_comm_init
 #define b200_domain            osph_domain
 #define b200_atom_style        osph_atom_style
 #define b200_neighbor          osph_neighbor
