@@ -12,6 +12,7 @@ import os
 from . import _abi
 from .deck import Deck, DeckError, PAIR_STYLES
 from .engine import Sim
+from . import parallel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200sph.so")
@@ -29,6 +30,6 @@ def load():
     return _api
 
 
-def B200Sim(deck, device=0):
-    """the product entry point: one engine instance on cuda:<device>"""
-    return Sim(load(), deck, device)
+def B200Sim(deck, device=0, brick=None, nccl_id=None):
+    """the product entry point: one engine instance on cuda:<device> (optionally one brick of a multi-GPU run)"""
+    return Sim(load(), deck, device, brick, nccl_id)

@@ -765,6 +765,14 @@ static void reneighbor(b200_sph *h)
 static void do_setup(b200_sph *h)
 {
   if (!h->geom_ready) setup_geometry(h);
+  if (h->world > 1) {      // new-atom tags continue after the GLOBAL maximum (Atom::tag_extend, atom.cpp:603-605)
+    h->h_flags[9] = h->maxtag;
+    CK(cudaMemcpyAsync(h->d_flags + 9, h->h_flags + 9, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    NCK(g_nccl.AllReduce(h->d_flags + 9, h->d_flags + 9, 1, ncclInt, ncclMax, h->nccl, h->st));
+    CK(cudaMemcpyAsync(h->h_flags + 9, h->d_flags + 9, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->maxtag = h->h_flags[9];
+  }
   build_plan(h);
   neighbor_build(h, true);
   h->nbuilds = 0;

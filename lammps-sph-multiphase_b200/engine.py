@@ -21,12 +21,16 @@ def _ip(a):
 class Sim:
     """One engine instance (one GPU / one MPI rank)."""
 
-    def __init__(self, api, deck, device=0):
-        self.api, self.deck = api, deck
+    def __init__(self, api, deck, device=0, brick=None, nccl_id=None):
+        """brick / nccl_id: this rank's place in a multi-GPU decomposition (parallel.Brick, parallel.nccl_id)"""
+        self.api, self.deck, self.brick = api, deck, brick
         h = C.c_void_p()
         api.check(api.create(C.byref(h), device))
         self.h = h
         self._keep = []
+        if brick is not None and brick.world > 1:
+            grid = np.array(brick.grid, np.int32); loc = np.array(brick.myloc, np.int32); nb = np.array(brick.procneigh, np.int32)
+            api.check(api.comm_init(h, brick.world, brick.rank, _ip(grid), _ip(loc), _ip(nb), nccl_id))
         self._configure()
 
     def close(self):
@@ -48,7 +52,9 @@ class Sim:
         ck = api.check
         lo = np.array(d.boxlo, np.float64); hi = np.array(d.boxhi, np.float64)
         per = np.array(d.periodicity, np.int32)
-        ck(api.domain(h, d.dimension, _dp(lo), _dp(hi), _ip(per), _dp(lo), _dp(hi)))
+        slo = np.array(self.brick.sublo, np.float64) if self.brick is not None else lo
+        shi = np.array(self.brick.subhi, np.float64) if self.brick is not None else hi
+        ck(api.domain(h, d.dimension, _dp(lo), _dp(hi), _ip(per), _dp(slo), _dp(shi)))
         mass = np.ascontiguousarray(d.mass_, np.float64)
         ck(api.atom_style(h, int(d.multiphase), d.ntypes, _dp(mass)))
         cn = np.ascontiguousarray(d.cutneighsq, np.float64)

@@ -208,7 +208,7 @@ _add(_dam("dam2d_morris", 2, 40, morris=True))
 
 
 # ---- C3 scaled down: periodic two-phase box (square_to_sphere/droplet.lmp + cube.lmp) ----
-def _droplet(name, dim, nx, nsteps, heat=None, skin=0.0, every=1, check="yes"):
+def _droplet(name, dim, nx, nsteps, heat=None, skin=0.0, every=1, check="yes", static=False):
     L = 1.0; dx = L / nx; h = 3.0 * dx; rho = 1.0; c = 10.0; eta = 5e-2; alpha = 0.2; a = 0.2
     m = dx ** dim * rho
     if dim == 2:
@@ -244,7 +244,7 @@ displace_atoms all random %s %s %s 4711 units box""" % (lat, _f(dx), rsq, _f(rho
     elif heat == "sph/heatconduction/phasechange":
         cmds += [("pair_coeff", "1 1", heat, 0.2, h), ("pair_coeff", "1 2", heat, 0.3, h, "NULL", 1.2),
                  ("pair_coeff", "2 2", heat, 0.6, h)]
-    dt = min(0.25 * dx / c, 0.125 * dx * dx / eta * rho)
+    dt = 0.0 if static else min(0.25 * dx / c, 0.125 * dx * dx / eta * rho)
     cmds += [("neighbor", skin), ("neigh_modify", dict(delay=0, every=every, check=check)), ("comm_modify", "yes"),
              ("timestep", dt), ("fix", "all", "meso")]
     return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps)
@@ -254,6 +254,10 @@ _add(_droplet("droplet2d", 2, 30, 40))
 _add(_droplet("droplet3d", 3, 12, 20))
 _add(_droplet("droplet3d_heat", 3, 12, 15, heat="sph/heatconduction/multiphase"))
 _add(_droplet("droplet2d_pcheat_skin", 2, 30, 40, heat="sph/heatconduction/phasechange", skin=0.002, every=2))
+# timestep 0: rho / colorgradient repeat every step, so the one-step-stale ghost values of the multiphase styles
+#  equal the fresh ones and the result does not depend on the domain decomposition (multi-GPU check)
+_add(_droplet("droplet3d_static", 3, 12, 3, heat="sph/heatconduction/phasechange", static=True))
+_add(_droplet("droplet2d_static", 2, 30, 3, static=True))
 
 
 # ---- C4 scaled down: random liquid box with a vapour seed, heat conduction + fix phase_change ----
