@@ -1,0 +1,22 @@
+"""GPU (needs >= 2 devices, else skipped): domain decomposition over NCCL vs the one-rank reference fixtures
+(tests/mgpu_check.py, launched with torchrun: one rank per GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_rank_decomposition_matches_fixtures():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
+    lines = [l for l in p.stdout.splitlines() if " grid " in l]
+    print("\n".join(lines))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert len(lines) >= 8 and not any("FAIL" in l for l in lines)
