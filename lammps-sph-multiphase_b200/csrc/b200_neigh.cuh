@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
   if (nO + nG == 0) return;
   int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
   const double cutmaxsq = g.cutneighmaxsq;
+  const double cutsafe = cutmaxsq * (1.0 - 1.0e-9);     // below this, round-off cannot move a pair across a bin-stencil boundary
 
   for (int pass = 0; pass < 2; pass++) {          // 0: owned rows, 1: ghost rows
     int nrow = pass ? nG : nO, r0 = o0;
@@ -266,51 +267,66 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
       int fill = 0;
 
       auto process = [&](int n) {
-        for (int base = 0; base < n; base += 32) {
-          unsigned mask = 0;
-          int m = imin(32, n - base);
-          for (int b = 0; b < m; b++) {
-            double dx = xi - sm.x[base + b], dy = yi - sm.y[base + b], dz = zi - sm.z[base + b];
-            double rsq = rsq_nofma(dx, dy, dz);
-            mask |= (unsigned)(rsq <= cutmaxsq) << b;
+        // 1. coarse test of the whole chunk (<= 128 candidates, broadcast reads): rsq <= cutneighmax^2 -> 128-bit hit mask
+        unsigned long long m0 = 0, m1 = 0;
+        {
+          int n0 = imin(n, 64);
+#pragma unroll 4
+          for (int b = 0; b < n0; b++) {
+            double rsq = rsq_nofma(xi - sm.x[b], yi - sm.y[b], zi - sm.z[b]);
+            m0 |= (unsigned long long)(rsq <= cutmaxsq) << b;
           }
-          while (mask) {
-            int b = __ffs(mask) - 1; mask &= mask - 1;
-            int idx = base + b, j = sm.j[idx];
-            if (j == i) continue;
-            unsigned long long wj = sm.w[idx];
-            double xj = sm.x[idx], yj = sm.y[idx], zj = sm.z[idx];
-            double rsq = rsq_nofma(xi - xj, yi - yj, zi - zj);
-            int tij = ti * MAXT1 + tw_type(wj);
-            if (!(rsq <= s_cut[tij])) continue;
-            // j must sit in a bin of the reference's stencil around i's bin (neigh_stencil.cpp:434-448)
+#pragma unroll 4
+          for (int b = 64; b < n; b++) {
+            double rsq = rsq_nofma(xi - sm.x[b], yi - sm.y[b], zi - sm.z[b]);
+            m1 |= (unsigned long long)(rsq <= cutmaxsq) << (b - 64);
+          }
+        }
+        // 2. one flattened loop over this lane's hits (a lane with few hits in the first half moves on to the
+        //    second half while others are still busy: the warp runs max-over-lanes iterations, not a sum of maxima)
+        while (m0 | m1) {
+          int idx;
+          if (m0) { idx = __ffsll((long long)m0) - 1; m0 &= m0 - 1; }
+          else { idx = 64 + __ffsll((long long)m1) - 1; m1 &= m1 - 1; }
+          int j = sm.j[idx];
+          if (j == i) continue;
+          unsigned long long wj = sm.w[idx];
+          double xj = sm.x[idx], yj = sm.y[idx], zj = sm.z[idx];
+          double rsq = rsq_nofma(xi - xj, yi - yj, zi - zj);
+          int tj = tw_type(wj), tij = ti * MAXT1 + tj;
+          if (!(rsq <= s_cut[tij])) continue;
+          // j must sit in a bin of the reference's stencil around i's bin (neigh_stencil.cpp:434-448).  A pair that is
+          // clearly inside the largest cutoff always does (closest bin distance <= pair distance < cutneighmax); only
+          // pairs within rounding distance of cutneighmax can be affected by where round-off put them, so only those
+          // are checked against the reference's integer bin coordinates.
+          if (rsq >= cutsafe) {
             int dbx = abs(tw_bx(wj) - bxi), dby = abs(tw_by(wj) - byi), dbz = abs(tw_bz(wj) - bzi);
             if (dbx > g.sx || dby > g.sy || dbz > g.sz) continue;
             double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0,
                    ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
             if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) continue;
-            unsigned ent;
-            if (!pass) {
-              bool own = (j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj);
-              ent = (unsigned)j | ((unsigned)tw_type(wj) << NBR_TYPE_SHIFT) | (own ? NBR_OWNER_BIT : 0u);
-            } else {
-              if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
-              ent = (unsigned)j | ((unsigned)tw_type(wj) << NBR_TYPE_SHIFT) | NBR_OWNER_BIT;
+          }
+          unsigned ent = (unsigned)j | ((unsigned)tj << NBR_TYPE_SHIFT);
+          if (!pass) {
+            bool own = (j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj);
+            if (own) ent |= NBR_OWNER_BIT;
+          } else {
+            if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
+            ent |= NBR_OWNER_BIT;
+          }
+          // inner zone (inside the pair cutoff now): filled from the front; outer zone (skin shell, or
+          // exactly on the cutoff): filled from the back.  The stage kernels test every entry each step,
+          // but hits and misses are clustered, so their warps do not diverge on the heavy pair body.
+          // Far rows: entries at least `margin` outside the cutoff.  They cannot come inside before some
+          // particle has moved margin/2 since the build, which the integrator tracks (dmaxsq), so the
+          // stage kernels skip them -- provably without changing any result -- until that happens.
+          if (rsq >= s_far[tij]) { if (cfar < A.stride) frow[(size_t)cfar * 32] = ent; cfar++; }
+          else {
+            if (cin + cout < A.stride) {
+              if (rsq < s_in[tij]) { row[(size_t)cin * 32] = ent; cin++; }
+              else { row[(size_t)(A.stride - 1 - cout) * 32] = ent; cout++; }
             }
-            // inner zone (inside the pair cutoff now): filled from the front; outer zone (skin shell, or
-            // exactly on the cutoff): filled from the back.  The stage kernels test every entry each step,
-            // but hits and misses are clustered, so their warps do not diverge on the heavy pair body.
-            // Far rows: entries at least `margin` outside the cutoff.  They cannot come inside before some
-            // particle has moved margin/2 since the build, which the integrator tracks (dmaxsq), so the
-            // stage kernels skip them -- provably without changing any result -- until that happens.
-            if (rsq >= s_far[tij]) { if (cfar < A.stride) frow[(size_t)cfar * 32] = ent; cfar++; }
-            else {
-              if (cin + cout < A.stride) {
-                if (rsq < s_in[tij]) { row[(size_t)cin * 32] = ent; cin++; }
-                else { row[(size_t)(A.stride - 1 - cout) * 32] = ent; cout++; }
-              }
-              cnt++;
-            }
+            cnt++;
           }
         }
       };

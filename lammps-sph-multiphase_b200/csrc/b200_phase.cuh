@@ -85,25 +85,33 @@ __global__ void k_pc_candidates(PcParams P, PcArrays a, unsigned char *flag, dou
   flag[o] = ok ? 3 : 1;
 }
 
+// candidates in ascending local index: flag != 0 -> position (exclusive scan done by the host) -> compact list
+__global__ void k_pc_mark(int norig, const unsigned char *flag, int *pos)
+{ int o = blockIdx.x * blockDim.x + threadIdx.x; if (o < norig) pos[o] = flag[o] != 0; }
+__global__ void k_pc_compact(int norig, const unsigned char *flag, const int *pos, int *list)
+{ int o = blockIdx.x * blockDim.x + threadIdx.x; if (o < norig && flag[o]) list[pos[o]] = o; }
+
 // ONE warp walks the RNG stream in LAMMPS local order and performs the insertions.
 // state[0] = RanPark seed (persistent), state[1] = number of insertions of this call (out)
 __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const unsigned char *flag, const double *thr, const int *dev,
-                                                double *dmass, PcNew *newatoms, int *state)
+                                                double *dmass, PcNew *newatoms, int *state, const int *clist, int ncand)
 {
   const b200_phase_change_desc &d = P.d;
   const int lane = threadIdx.x;
   int seed = state[0], nins = 0;
-  for (int base = 0; base < P.norig; base += 32) {
-    int o = base + lane;
-    unsigned char fl = o < P.norig ? flag[o] : 0;
+  for (int base = 0; base < ncand; base += 32) {
+    int oc_l = base + lane < ncand ? clist[base + lane] : 0;
+    unsigned char fl = base + lane < ncand ? flag[oc_l] : 0;
+    double thr_l = base + lane < ncand ? thr[oc_l] : 0.0;
     unsigned cand = __ballot_sync(FULLMASK, fl != 0);
     while (cand) {
       int b = __ffs(cand) - 1; cand &= cand - 1;
-      int oc = base + b;
+      int oc = __shfl_sync(FULLMASK, oc_l, b);
+      double thr_c = __shfl_sync(FULLMASK, thr_l, b);
       unsigned char f = __shfl_sync(FULLMASK, fl, b);
       // the draw happens for every candidate, before the other tests (:210,212)
       double u = ranpark(&seed);                     // all lanes advance the same stream redundantly
-      if (!(f == 3 && u < thr[oc])) continue;
+      if (!(f == 3 && u < thr_c)) continue;
       int i = dev[oc];
       double4 xi = a.xt[i], ci = a.cgm[i];
       double coord[3]; bool ok = false;

@@ -726,7 +726,15 @@ static void phase_change(b200_sph *h, PcFix &f)
   PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p};
   LAUNCH(h, k_pc_candidates, nblk(na, 128), 128, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p);
   CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
-  LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state);
+  // compact the candidates (ascending local index) so the serial walk touches only them
+  h->pos.ensure(norig + 2); h->flag.ensure(norig + 2); ensure_scan_tmp(h, norig + 2);
+  LAUNCH(h, k_pc_mark, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p);
+  scan_exclusive(h, h->pos.p, norig, h->scan_tmp.p);
+  CK(cudaMemcpyAsync(h->h_flags + 7, h->pos.p + norig, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  int ncand = h->h_flags[7];
+  if (ncand) LAUNCH(h, k_pc_compact, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p, h->flag.p);
+  LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state, h->flag.p, ncand);
   CK(cudaMemcpyAsync(h->h_flags + 5, f.d_state + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   if (h->nghost || h->world > 1) comm_reverse_scalar_add(h, h->pc_dmass.p);      // comm->reverse_comm_fix (:324)
   LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p);
