@@ -127,6 +127,11 @@ int  b200_fix_meso(b200_sph *h, int groupbit);                  /* fix_meso.cpp:
 int  b200_fix_meso_stationary(b200_sph *h, int groupbit);       /* fix_meso_stationary.cpp:71-112 */
 int  b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc); /* fix_gravity.cpp:244-295 */
 int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix_phase_change.cpp:167-352 */
+/* fix setmeso (src/USER-SPH/fix_setmeso.cpp:180-271), constant form: which = 0 meso_rho | 1 meso_e | 2 meso_t (e = cv*T);
+ * region_kind 0 none | 1 block (xlo xhi ylo yhi zlo zhi) | 2 sphere (xc yc zc radius); match_inside = 1 for `region`,
+ * 0 for `noregion` (apply outside).  Region tests as RegBlock/RegSphere::inside (region_block.cpp:114-119, region_sphere.cpp:96-105). */
+int  b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside);
+int  b200_fix_enforce2d(b200_sph *h, int groupbit);                          /* fix_enforce2d.cpp:77-89 */
 
 /* ---- per-atom data -------------------------------------------------------- */
 /* Upload nlocal owned atoms (LAMMPS local order).  x,v,rho,e,type,mask,tag are

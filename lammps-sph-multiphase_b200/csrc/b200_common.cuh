@@ -46,9 +46,11 @@ struct PairTab {
 
 struct FixList {
   int n;
-  int kind[MAXFIX];     // 1 meso, 2 meso/stationary, 3 gravity
+  int kind[MAXFIX];     // 1 meso, 2 meso/stationary, 3 gravity, 4 setmeso, 5 enforce2d
   int bit[MAXFIX];
   double acc[MAXFIX][3];
+  int ipar[MAXFIX][3];  // setmeso: which, region kind, match_inside
+  double par[MAXFIX][7];// setmeso: value, region[6]
 };
 
 // geometry handed to kernels by value

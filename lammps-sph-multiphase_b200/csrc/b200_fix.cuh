@@ -7,6 +7,7 @@ struct StepArrays {
   double4 *xt, *vr, *vm, *fd;
   double *e, *de;
   const int *mask;
+  const double *cv;
 };
 
 // FixMeso::setup_pre_force (fix_meso.cpp:68-85): vest = v for atoms of the fix group
@@ -76,13 +77,31 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
   bool fdirty = false;
   int m = a.mask[i];
   double4 v = a.vm[i];
+  bool vdirty = false;
   if (do_post)
-    for (int k = 0; k < fl.n; k++)
-      if (fl.kind[k] == 3 && (m & fl.bit[k])) {
+    for (int k = 0; k < fl.n; k++) {
+      if (!(m & fl.bit[k])) continue;
+      if (fl.kind[k] == 3) {                                  // FixGravity::post_force
         f.x += v.w * fl.acc[k][0]; f.y += v.w * fl.acc[k][1]; f.z += v.w * fl.acc[k][2];
         fdirty = true;
+      } else if (fl.kind[k] == 4) {                           // FixSetMeso::post_force, constant value (fix_setmeso.cpp:211-236)
+        int rk = fl.ipar[k][1];
+        if (rk) {
+          double4 x = a.xt[i];
+          const double *r = &fl.par[k][1];
+          bool in;
+          if (rk == 1) in = x.x >= r[0] && x.x <= r[1] && x.y >= r[2] && x.y <= r[3] && x.z >= r[4] && x.z <= r[5];
+          else { double dx = x.x - r[0], dy = x.y - r[1], dz = x.z - r[2]; in = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) <= r[3]; }
+          if (in != (fl.ipar[k][2] != 0)) continue;
+        }
+        if (fl.ipar[k][0] == 0) { double4 vr = a.vr[i]; vr.w = fl.par[k][0]; a.vr[i] = vr; }
+        else a.e[i] = fl.ipar[k][0] == 2 ? a.cv[i] * fl.par[k][0] : fl.par[k][0];
+      } else if (fl.kind[k] == 5) {                           // FixEnforce2D::post_force (fix_enforce2d.cpp:77-89)
+        v.z = 0.0; f.z = 0.0; fdirty = true; vdirty = true;
       }
+    }
   if (fdirty) a.fd[i] = f;
+  if (vdirty) a.vm[i] = v;
   if (do_final) {
     double4 vr = a.vr[i];
     double e = a.e[i];

@@ -147,7 +147,7 @@ struct b200_sph {
     rec.ensure(n * 4, false, st); gimage.ensure(n, true, st);
     numneigh.ensure(n, false, st); numfar.ensure(n, false, st);
   }
-  StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p}; }
+  StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p, c.cv.p}; }
   CommArrays comm_arrays() { OwnedSet &c = C(); return CommArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.cgm.p, c.e.p, c.de.p, c.cv.p, c.tag.p, c.mask.p, c.orig.p, gimage.p}; }
 
   // ---- timing helpers ----
@@ -1013,6 +1013,17 @@ static int add_fix(b200_sph *h, int kind, int bit, double ax, double ay, double 
 int b200_fix_meso(b200_sph *h, int groupbit) { return add_fix(h, 1, groupbit, 0, 0, 0); }
 int b200_fix_meso_stationary(b200_sph *h, int groupbit) { return add_fix(h, 2, groupbit, 0, 0, 0); }
 int b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc) { return add_fix(h, 3, groupbit, xacc, yacc, zacc); }
+int b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside)
+{
+  if (which < 0 || which > 2 || region_kind < 0 || region_kind > 2) return fail("b200_fix_setmeso: bad arguments");
+  if (add_fix(h, 4, groupbit, 0, 0, 0)) return -1;
+  int k = h->fl.n - 1;
+  h->fl.ipar[k][0] = which; h->fl.ipar[k][1] = region_kind; h->fl.ipar[k][2] = match_inside;
+  h->fl.par[k][0] = value;
+  for (int q = 0; q < 6; q++) h->fl.par[k][1 + q] = (region_kind && region) ? region[q] : 0.0;
+  return 0;
+}
+int b200_fix_enforce2d(b200_sph *h, int groupbit) { return add_fix(h, 5, groupbit, 0, 0, 0); }
 int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d)
 {
   API_BEGIN

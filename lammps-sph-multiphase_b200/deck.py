@@ -163,6 +163,7 @@ class Deck:
         self.dt, self.ntimestep = 0.005 if units == "lj" else 1.0e-8, 0   # Update::set_units (update.cpp)
         self.groups = {"all": 1}
         self.fixes = []
+        self.regions = {}
         self._initd = False
 
     # ---- simple commands ---------------------------------------------------
@@ -194,6 +195,21 @@ class Deck:
                 raise DeckError("Too many groups")
             self.groups[name] = 1 << len(self.groups)
         return self.groups[name]
+
+    def region(self, ID, style, *args):
+        """region ID block xlo xhi ylo yhi zlo zhi | sphere xc yc zc r  (units box, side in; EDGE = box bound)"""
+        if style == "block":
+            v = []
+            for k, a in enumerate(args[:6]):
+                if a == "EDGE":
+                    v.append(-1.0e20 if k % 2 == 0 else 1.0e20)      # region_block.cpp: EDGE -> -BIG / BIG
+                else:
+                    v.append(float(a))
+            self.regions[ID] = (1, v)
+        elif style == "sphere":
+            self.regions[ID] = (2, [float(a) for a in args[:4]] + [0.0, 0.0])
+        else:
+            raise DeckError("b200 SPH package: region styles block and sphere are supported")
 
     # ---- pair styles -------------------------------------------------------
     def pair_style(self, name, *sub):
@@ -249,6 +265,25 @@ class Deck:
             else:
                 ln = math.sqrt(xd * xd + yd * yd); g = (xd / ln, yd / ln, 0.0)
             self.fixes.append((style, bit, tuple(mag * c for c in g)))
+        elif style == "enforce2d":
+            if self.dimension == 3:
+                raise DeckError("Cannot use fix enforce2d with 3d simulation")
+            self.fixes.append((style, bit, None))
+        elif style == "setmeso":
+            which = {"meso_rho": 0, "meso_e": 1, "meso_t": 2}.get(args[0])
+            if which is None:
+                raise DeckError("Illegal fix setmeso command, meso_rho or meso_e must be given")
+            if str(args[1]).startswith("v_"):
+                raise DeckError("b200 SPH package: fix setmeso supports constant values")
+            kind, reg, inside = 0, [0.0] * 6, 1
+            if len(args) > 2:
+                if args[2] not in ("region", "noregion") or len(args) < 4:
+                    raise DeckError("Illegal fix setmesode command")
+                if args[3] not in self.regions:
+                    raise DeckError("Region ID for fix setmesode does not exist")
+                kind, reg = self.regions[args[3]]
+                inside = 1 if args[2] == "region" else 0
+            self.fixes.append((style, bit, (which, float(args[1]), kind, list(reg), inside)))
         elif style == "phase_change":
             a = list(args)
             if len(a) < 11:

@@ -79,6 +79,12 @@ class Sim:
                 ck(api.fix_meso_stationary(h, bit))
             elif style == "gravity":
                 ck(api.fix_gravity(h, bit, *arg))
+            elif style == "enforce2d":
+                ck(api.fix_enforce2d(h, bit))
+            elif style == "setmeso":
+                which, value, kind, reg, inside = arg
+                r = np.array(reg, np.float64)
+                ck(api.fix_setmeso(h, bit, which, value, kind, _dp(r), inside))
             elif style == "phase_change":
                 pc = PhaseChangeDesc(groupbit=bit, **arg)
                 ck(api.fix_phase_change(h, C.byref(pc)))

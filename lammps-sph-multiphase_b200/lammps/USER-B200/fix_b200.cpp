@@ -3,6 +3,7 @@
 #include "fix_b200.h"
 #include "atom.h"
 #include "domain.h"
+#include "region.h"
 #include "error.h"
 #include "update.h"
 
@@ -61,3 +62,51 @@ FixPhaseChangeB200::FixPhaseChangeB200(LAMMPS *lmp, int narg, char **arg) : Fix(
 
 int FixPhaseChangeB200::setmask() { return PRE_EXCHANGE; }
 int FixPhaseChangeB200::b200_register(b200_sph *h) { return b200_fix_phase_change(h, &d); }
+
+FixSetMesoB200::FixSetMesoB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), idregion(NULL)
+{
+  if (narg < 5) error->all(FLERR, "Illegal fix setmeso command");
+  if (strcmp(arg[3], "meso_rho") == 0) which = 0;
+  else if (strcmp(arg[3], "meso_e") == 0) which = 1;
+  else if (strcmp(arg[3], "meso_t") == 0) which = 2;
+  else error->all(FLERR, "Illegal fix setmeso command, meso_rho or meso_e must be given");
+  if (strstr(arg[4], "v_") == arg[4]) error->all(FLERR, "fix setmeso/b200 supports constant values only");
+  value = atof(arg[4]);
+  regionflag = 1;
+  int iarg = 5;
+  while (iarg < narg) {
+    if (strcmp(arg[iarg], "region") == 0 || strcmp(arg[iarg], "noregion") == 0) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal fix setmesode command");
+      if (domain->find_region(arg[iarg + 1]) == -1) error->all(FLERR, "Region ID for fix setmesode does not exist");
+      int n = strlen(arg[iarg + 1]) + 1;
+      idregion = new char[n];
+      strcpy(idregion, arg[iarg + 1]);
+      if (strcmp(arg[iarg], "noregion") == 0) regionflag = 0;
+      iarg += 2;
+    } else error->all(FLERR, "Illegal fix setmesode command");
+  }
+}
+
+int FixSetMesoB200::setmask() { return POST_FORCE; }
+
+int FixSetMesoB200::b200_register(b200_sph *h)
+{
+  int kind = 0;
+  double r[6] = {0, 0, 0, 0, 0, 0};
+  if (idregion) {
+    int ir = domain->find_region(idregion);
+    if (ir == -1) error->all(FLERR, "Region ID for fix setmesode does not exist");
+    Region *reg = domain->regions[ir];
+    if (reg->dynamic_check() || !reg->interior) error->all(FLERR, "fix setmeso/b200 supports static regions with side in");
+    // RegBlock / RegSphere keep their geometry private; their bounding box (region.h extent_*) carries it
+    if (strcmp(reg->style, "block") == 0) {
+      kind = 1;
+      r[0] = reg->extent_xlo; r[1] = reg->extent_xhi; r[2] = reg->extent_ylo; r[3] = reg->extent_yhi; r[4] = reg->extent_zlo; r[5] = reg->extent_zhi;
+    } else if (strcmp(reg->style, "sphere") == 0) {
+      kind = 2;
+      r[0] = 0.5 * (reg->extent_xlo + reg->extent_xhi); r[1] = 0.5 * (reg->extent_ylo + reg->extent_yhi); r[2] = 0.5 * (reg->extent_zlo + reg->extent_zhi);
+      r[3] = 0.5 * (reg->extent_xhi - reg->extent_xlo);
+    } else error->all(FLERR, "fix setmeso/b200 supports block and sphere regions");
+  }
+  return b200_fix_setmeso(h, groupbit, which, value, kind, r, regionflag);
+}

@@ -8,6 +8,8 @@ FixStyle(meso/b200,FixMesoB200)
 FixStyle(meso/stationary/b200,FixMesoStationaryB200)
 FixStyle(gravity/b200,FixGravityB200)
 FixStyle(phase_change/b200,FixPhaseChangeB200)
+FixStyle(setmeso/b200,FixSetMesoB200)
+FixStyle(enforce2d/b200,FixEnforce2DB200)
 
 #else
 
@@ -18,6 +20,7 @@ FixStyle(phase_change/b200,FixPhaseChangeB200)
 #include "fix_meso.h"
 #include "fix_meso_stationary.h"
 #include "fix_gravity.h"
+#include "fix_enforce2d.h"
 
 namespace LAMMPS_NS {
 
@@ -59,6 +62,29 @@ class FixPhaseChangeB200 : public Fix, public B200FixShell {
   int b200_register(b200_sph *h);
  private:
   b200_phase_change_desc d;
+};
+
+// FixSetMeso keeps its parameters private (fix_setmeso.h:42-53): same argument list re-parsed,
+//   fix ID grp setmeso meso_rho|meso_e|meso_t value [region|noregion ID]      (fix_setmeso.cpp:38-89), constant values only
+class FixSetMesoB200 : public Fix, public B200FixShell {
+ public:
+  FixSetMesoB200(class LAMMPS *, int, char **);
+  ~FixSetMesoB200() { delete [] idregion; }
+  int setmask();
+  void post_force(int) { b200_fix_guard(lmp, "setmeso"); }
+  int b200_register(b200_sph *h);
+ private:
+  int which, regionflag;
+  double value;
+  char *idregion;
+};
+
+class FixEnforce2DB200 : public FixEnforce2D, public B200FixShell {
+ public:
+  FixEnforce2DB200(class LAMMPS *lmp, int narg, char **arg) : FixEnforce2D(lmp, narg, arg) {}
+  void setup(int) {}
+  void post_force(int) { b200_fix_guard(lmp, "enforce2d"); }
+  int b200_register(b200_sph *h) { return b200_fix_enforce2d(h, groupbit); }
 };
 
 }    // namespace LAMMPS_NS

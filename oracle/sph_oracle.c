@@ -33,7 +33,7 @@
 #define EPSILON 1.0e-12 /* pair_sph_surfacetension.cpp */
 #define CG_SMALL 1.0e-20 /* fix_phase_change.cpp:42 */
 
-enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE };
+enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D };
 
 typedef struct {
   int style, nstep;
@@ -44,6 +44,7 @@ typedef struct {
 typedef struct {
   int kind, groupbit;
   double acc[3];
+  int which, region_kind, match_inside; double value, region[6];
   osph_phase_change_desc pc;
   long long next_reneighbor;
   int seed; /* RanPark state, random_park.cpp:22-47 */
@@ -215,6 +216,14 @@ int osph_fix_meso(osph_sph *s, int groupbit) { return newfix(s, FIX_MESO, groupb
 int osph_fix_meso_stationary(osph_sph *s, int groupbit) { return newfix(s, FIX_MESO_STATIONARY, groupbit) ? 0 : fail("too many fixes"); }
 int osph_fix_gravity(osph_sph *s, int groupbit, double xacc, double yacc, double zacc)
 { ofix *f = newfix(s, FIX_GRAVITY, groupbit); if (!f) return fail("too many fixes"); f->acc[0] = xacc; f->acc[1] = yacc; f->acc[2] = zacc; return 0; }
+int osph_fix_setmeso(osph_sph *s, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside)
+{
+  ofix *f = newfix(s, FIX_SETMESO, groupbit); if (!f) return fail("too many fixes");
+  f->which = which; f->value = value; f->region_kind = region_kind; f->match_inside = match_inside;
+  for (int q = 0; q < 6; q++) f->region[q] = (region_kind && region) ? region[q] : 0.0;
+  return 0;
+}
+int osph_fix_enforce2d(osph_sph *s, int groupbit) { return newfix(s, FIX_ENFORCE2D, groupbit) ? 0 : fail("too many fixes"); }
 int osph_fix_phase_change(osph_sph *s, const osph_phase_change_desc *d)
 {
   if (d->seed <= 0) return fail("Illegal value for seed"); /* fix_phase_change.cpp:70 */
@@ -880,6 +889,28 @@ static void fix_gravity(osph_sph *s, ofix *fx)
     }
 }
 
+/* FixSetMeso::post_force, constant value (fix_setmeso.cpp:180-236); Region::match with side in
+ * (region.cpp:127-131, region_block.cpp:114-119, region_sphere.cpp:96-105) */
+static void fix_setmeso(osph_sph *s, ofix *fx)
+{
+  for (int i = 0; i < s->nlocal; i++) {
+    if (!(s->mask[i] & fx->groupbit)) continue;
+    if (fx->region_kind) {
+      const double *x = &s->x[3*i], *r = fx->region; int in;
+      if (fx->region_kind == 1) in = x[0] >= r[0] && x[0] <= r[1] && x[1] >= r[2] && x[1] <= r[3] && x[2] >= r[4] && x[2] <= r[5];
+      else { double delx = x[0] - r[0], dely = x[1] - r[1], delz = x[2] - r[2]; in = sqrt(delx * delx + dely * dely + delz * delz) <= r[3]; }
+      if (fx->match_inside && !in) continue;
+      if (!fx->match_inside && in) continue;
+    }
+    if (fx->which == 0) s->rho[i] = fx->value;
+    else if (fx->which == 1) s->e[i] = fx->value;
+    else s->e[i] = s->cv[i] * fx->value;      /* sph_t2energy */
+  }
+}
+/* FixEnforce2D::post_force, fix_enforce2d.cpp:77-89 */
+static void fix_enforce2d(osph_sph *s, ofix *fx)
+{ for (int i = 0; i < s->nlocal; i++) if (s->mask[i] & fx->groupbit) { s->v[3*i+2] = 0.0; s->f[3*i+2] = 0.0; } }
+
 /* ---- fix phase_change, fix_phase_change.cpp:167-352 ---- */
 static int pc_isfromphasearound(osph_sph *s, ofix *fx, int i)
 { /* :540-563 */
@@ -1037,7 +1068,15 @@ int osph_pair_compute(osph_sph *s, int slot) { if (slot < 0 || slot >= s->npair)
 int osph_pair_compute_all(osph_sph *s) { for (int k = 0; k < s->npair; k++) if (pair_compute_slot(s, k)) return -1; return 0; } /* pair_hybrid.cpp:101-109 */
 int osph_reverse_comm(osph_sph *s) { comm_reverse(s); return 0; }
 int osph_forward_comm(osph_sph *s) { comm_forward(s); return 0; }
-int osph_post_force(osph_sph *s) { for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_GRAVITY) fix_gravity(s, &s->fix[i]); return 0; }
+int osph_post_force(osph_sph *s)
+{
+  for (int i = 0; i < s->nfix; i++) {
+    if (s->fix[i].kind == FIX_GRAVITY) fix_gravity(s, &s->fix[i]);
+    else if (s->fix[i].kind == FIX_SETMESO) fix_setmeso(s, &s->fix[i]);
+    else if (s->fix[i].kind == FIX_ENFORCE2D) fix_enforce2d(s, &s->fix[i]);
+  }
+  return 0;
+}
 int osph_initial_integrate(osph_sph *s)
 { for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_MESO || s->fix[i].kind == FIX_MESO_STATIONARY) fix_initial_integrate(s, &s->fix[i]); return 0; }
 int osph_final_integrate(osph_sph *s)

@@ -27,6 +27,8 @@
 #define b200_fix_meso_stationary osph_fix_meso_stationary
 #define b200_fix_gravity       osph_fix_gravity
 #define b200_fix_phase_change  osph_fix_phase_change
+#define b200_fix_setmeso       osph_fix_setmeso
+#define b200_fix_enforce2d     osph_fix_enforce2d
 #define b200_set_atoms         osph_set_atoms
 #define b200_get_natoms        osph_get_natoms
 #define b200_get_atoms         osph_get_atoms

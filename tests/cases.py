@@ -22,10 +22,10 @@ def _f(v):
 
 class Case:
     def __init__(self, name, dim, boundary, box, atom_style, ntypes, create, cmds, nsteps, units="si", groups=(),
-                 tol_traj=1e-9):
+                 tol_traj=1e-9, regions=()):
         self.name, self.dim, self.boundary, self.box = name, dim, boundary, box
         self.atom_style, self.ntypes, self.create, self.cmds, self.nsteps = atom_style, ntypes, create, cmds, nsteps
-        self.units, self.groups, self.tol_traj = units, groups, tol_traj
+        self.units, self.groups, self.tol_traj, self.regions = units, groups, tol_traj, regions
 
     @property
     def multiphase(self):
@@ -43,6 +43,8 @@ class Case:
         out = []
         for g, t in self.groups:
             out.append("group %s type %d" % (g, t))
+        for r in self.regions:
+            out.append("region %s %s %s units box" % (r[0], r[1], " ".join(_f(v) for v in r[2:])))
         nfix = 0
         for c in self.cmds:
             k, a = c[0], c[1:]
@@ -72,6 +74,8 @@ class Case:
                  ntypes=self.ntypes, units=self.units)
         for g, t in self.groups:
             d.group(g)
+        for r in self.regions:
+            d.region(*r)
         nfix = 0
         for c in self.cmds:
             k, a = c[0], c[1:]
@@ -261,7 +265,7 @@ _add(_droplet("droplet2d_static", 2, 30, 3, static=True))
 
 
 # ---- C4 scaled down: random liquid box with a vapour seed, heat conduction + fix phase_change ----
-def _bubble(name, dim, nx, nsteps):
+def _bubble(name, dim, nx, nsteps, thermostat=False):
     L = 1.0; dx = L / nx; h = 3.0 * dx
     rho_l, rho_v = 1.0, 0.1
     c_v, c_l = 200.0 / math.sqrt(rho_v), 200.0 / math.sqrt(rho_l)
@@ -303,8 +307,16 @@ set type 1 meso_rho %s""" % ("sc" if dim == 3 else "sq", _f(dx), "0.5" if dim ==
             ("neighbor", 0.0), ("neigh_modify", dict(delay=0, every=1)), ("comm_modify", "yes"), ("timestep", min(dts)),
             ("fix", "all", "meso"),
             ("fix", "bubble", "phase_change", Tc, Tt, Hwv, 0.5 * dx, m_v, h, 1, 2, 1, 123456, 0.05, "region", "box", "units", "box")]
-    return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps, groups=(("bubble", 2),), tol_traj=1e-8)
+    regions = ()
+    if thermostat:      # bubble.lmp:97-103: far-field thermostat outside a sphere, fixed density in a corner block, 2-D constraint
+        regions = (("rtemp", "sphere", 0.5, 0.5, zc, 0.5 - 2.6 * dx), ("rcorner", "block", "EDGE", 0.2, "EDGE", 0.2, "EDGE", "EDGE"))
+        cmds += [("fix", "all", "setmeso", "meso_t", Tinf, "noregion", "rtemp"), ("fix", "all", "setmeso", "meso_rho", rho_l, "region", "rcorner")]
+        if dim == 2:
+            cmds += [("fix", "all", "enforce2d")]
+    return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps, groups=(("bubble", 2),), tol_traj=1e-8, regions=regions)
 
 
 _add(_bubble("bubble2d", 2, 32, 30))
 _add(_bubble("bubble3d", 3, 12, 12))
+_add(_bubble("bubble2d_thermostat", 2, 32, 25, thermostat=True))
+_add(_bubble("bubble3d_thermostat", 3, 12, 10, thermostat=True))

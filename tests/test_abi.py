@@ -14,7 +14,7 @@ pkg = importlib.import_module("lammps-sph-multiphase_b200")
 def header_symbols():
     txt = open(os.path.join(ROOT, "include", "b200_sph.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_header():
