@@ -249,8 +249,12 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_colorgradient(PairArgs A)
 //  K_HEATMP PairSPHHeatConductionMultiPhase      pair_sph_heatconduction_multiphase.cpp:78-127
 //  K_HEATPC PairSPHHeatConductionPhaseChange     pair_sph_heatconduction_phasechange.cpp:83-139
 // Rows [0,nlocal) are owned particles, rows [nlocal,nall) ghosts (see k_build).
+// measured (profiles/r01_force_variants.txt): capping the single-phase kernels at 64 registers (8 blocks of 128 threads per
+// SM) gains ~4 %; the same cap on the multiphase kernels spills and loses 6 %; a depth-1 software prefetch of the next
+// gather raised the register count and lost 9 %.  The kernel sits between the L1 wavefront limit and gather latency.
+#define FORCE_MIN_BLOCKS(K) (((K) & (K_TAITMP | K_SURF | K_HEATMP | K_HEATPC)) ? 1 : 8)
 template <int KINDS, bool DIM3>
-__global__ void __launch_bounds__(PAIR_THREADS) k_force(PairArgs A)
+__global__ void __launch_bounds__(PAIR_THREADS, FORCE_MIN_BLOCKS(KINDS)) k_force(PairArgs A)
 {
   constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS | K_TAITMP)) != 0;
   constexpr bool HAS_SURF = (KINDS & K_SURF) != 0;
