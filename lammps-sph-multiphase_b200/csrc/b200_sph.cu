@@ -3,6 +3,7 @@
 #include "b200_common.cuh"
 #include "b200_neigh.cuh"
 #include "b200_pair.cuh"
+#include "b200_tile.cuh"
 #include "b200_fix.cuh"
 #include "b200_phase.cuh"
 #include "b200_comm.cuh"
@@ -132,6 +133,11 @@ struct b200_sph {
   DevBuf<double> d_prunesq, d_farsq; double far_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
+  // tile path (b200_tile.cuh): single-phase decks
+  bool tile_on = false, tile_ok = true, rows_tiled = false;
+  int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
+  DevBuf<TileDesc> tiles; DevBuf<double2> trec;
+  int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter
   bool setup_done = false, geom_ready = false;
   // instrumentation
   long long launches = 0, nbuilds = 0, nsteps = 0, maxneigh = 0, ndanger = 0, ninserted = 0;
@@ -424,6 +430,69 @@ static int comm_exchange(b200_sph *h, int nslots)
 }
 
 
+// ------------------------------------------------------------- tile path ----
+// persistent launch of a tile kernel: as many CTAs as fit on the device (or tiles), dynamic shared memory opted in once per kernel
+template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args)
+{
+  static std::vector<std::pair<const void *, size_t>> opted;     // kernel -> dynamic shared memory it may use
+  const void *fp = (const void *)kern;
+  size_t maxdyn = 0;
+  for (auto &o : opted) if (o.first == fp) maxdyn = o.second;
+  if (!maxdyn) {
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, fp));
+    maxdyn = TILE_SMEM_MAX - fa.sharedSizeBytes;
+    CK(cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxdyn));
+    opted.push_back({fp, maxdyn});
+  }
+  if (smem > maxdyn) throw std::string(name) + ": tile does not fit in shared memory";
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp, nthreads, smem));
+  if (occ < 1) throw std::string(name) + ": zero occupancy";
+  int grid = std::max(1, std::min(h->ntiles, h->nsm * occ));
+  CK(cudaMemsetAsync(h->d_tflags + 4, 0, sizeof(int), h->st));
+  kern<<<grid, nthreads, smem, h->st>>>(args);
+  post_launch(h, name);
+}
+
+// plan + rows of the tile path; false = a single cell's neighbourhood does not fit in shared memory (row path takes over)
+static bool tile_rows(b200_sph *h)
+{
+  Geom &g = h->g;
+  int nl = h->nlocal;
+  h->ntiles = 0;
+  if (!nl) return true;
+  h->tiles.ensure((size_t)g.ncells + 1);
+  CK(cudaMemsetAsync(h->d_tflags, 0, 8 * sizeof(int), h->st));
+  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
+  LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2], 128), 128, P);
+  CK(cudaMemcpyAsync(h->h_flags + 10, h->d_tflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (h->h_flags[12]) return false;
+  h->ntiles = h->h_flags[10];
+  h->tile_cap = std::max(2, (h->h_flags[11] + 1) & ~1);
+  for (int attempt = 0; attempt < 8; attempt++) {
+    size_t rows32 = (size_t)(nl + 31) / 32 * 32;
+    int ngrp = h->stride / 8;
+    h->nbr.ensure(rows32 * ngrp * 4); h->far.ensure(rows32 * ngrp * 4);
+    CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
+    TileBuildArgs B{};
+    B.g = g; B.nlocal = nl; B.ngrp = ngrp; B.cap = h->tile_cap;
+    B.xt = h->C().xt.p; B.gorder = h->gorder.p; B.cso = h->cso.p; B.csg = h->csg.p;
+    B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p;
+    B.tiles = h->tiles.p; B.ntiles = h->d_tflags; B.counter = h->d_tflags + 4;
+    B.near = (uint4 *)h->nbr.p; B.far = (uint4 *)h->far.p; B.numneigh = h->numneigh.p; B.numfar = h->numfar.p; B.maxcount = h->d_flags;
+    launch_tiles(h, k_tile_build, "k_tile_build", TILE_BUILD_NT, (size_t)(h->tile_cap + 2) * 32, B);
+    CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int mx = h->h_flags[0];
+    h->maxneigh = std::max<long long>(h->maxneigh, mx);
+    if (mx <= h->stride) break;
+    h->stride = ((int)(mx * 1.2) + 8 + 31) / 32 * 32;
+    if (attempt == 7) throw std::string("b200: neighbor row overflow");
+  }
+  return true;
+}
+
 // ------------------------------------------------------------- reneighbor ---
 
 static void neighbor_build(b200_sph *h, bool do_pbc)
@@ -486,7 +555,8 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   // 3. rows
   h->tbegin(T_NEIGH_BUILD);
   int na = h->nall();
-  for (int attempt = 0; attempt < 8 && na; attempt++) {
+  if (h->tile_on && !tile_rows(h)) { h->tile_on = false; h->tile_ok = false; }
+  for (int attempt = 0; attempt < 8 && na && !h->tile_on; attempt++) {
     h->nbr.ensure((size_t)((na + 31) / 32) * 32 * h->stride); h->far.ensure((size_t)((na + 31) / 32) * 32 * h->stride);
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
     BuildArgs A;
@@ -503,6 +573,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     if (attempt == 7) throw std::string("b200: neighbor row overflow");
   }
   h->tend();
+  h->rows_tiled = h->tile_on;
   CK(cudaMemsetAsync(h->d_dmaxsq, 0, sizeof(unsigned long long), h->st));
   CK(cudaMemsetAsync(h->d_scan_far, 0, sizeof(int), h->st));
   h->ago = 0; h->nbuilds++;
@@ -558,6 +629,20 @@ static void build_plan(b200_sph *h)
     }
     h->plan.push_back(p);
   }
+  // tile path (b200_tile.cuh): decks made of single-phase sub-styles only
+  bool ok = !h->multiphase && h->pcs.empty() && h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
+  int np = 2, nk = 1;
+  for (const Pass &p : h->plan) {
+    if (p.type == 0) continue;
+    if (p.type != 3 || (p.kinds & ~(K_TAIT | K_MORRIS | K_HEAT))) { ok = false; break; }
+    bool fluid = (p.kinds & (K_TAIT | K_MORRIS)) != 0, heat = (p.kinds & K_HEAT) != 0;
+    np = std::max(np, fluid ? (heat ? 5 : 4) : 3); nk = std::max(nk, (fluid ? 1 : 0) + (heat ? 1 : 0));
+  }
+  h->tile_on = ok; h->tile_nparts = np; h->tile_nk = nk;
+  long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - (long long)sizeof(TileDesc) - 64;
+  h->tile_slotcap = (int)std::min<long long>(std::min<long long>(TILE_MAXSLOTS, capb / (16 * np)), 7000) & ~1;    // 7000: k_tile_build stages 32 B per slot
+  if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
+  if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;
 }
 
 static PairArgs pair_args(b200_sph *h)
@@ -579,9 +664,92 @@ template <int KINDS> static void launch_force(b200_sph *h, PairArgs &A)
   post_launch(h, "k_force");
 }
 
+static TileArgs tile_args(b200_sph *h, int pstride)
+{
+  TileArgs A{};
+  OwnedSet &c = h->C();
+  A.nlocal = h->nlocal; A.ngrp = h->stride / 8; A.pstride = pstride; A.cap = h->tile_cap;
+  A.rec = h->trec.p; A.near = (const uint4 *)h->nbr.p; A.far = (const uint4 *)h->far.p; A.numneigh = h->numneigh.p; A.numfar = h->numfar.p;
+  A.scan_far = h->d_scan_far; A.tiles = h->tiles.p; A.ntiles = h->d_tflags; A.counter = h->d_tflags + 4;
+  A.xt = c.xt.p; A.vr_out = c.vr.p; A.fd = c.fd.p; A.de = c.de.p;
+  return A;
+}
+static int tile_records(b200_sph *h, int nparts, int force, int epart, const PairTab *fluid)
+{
+  int na = h->nall(), pstride = (na + 7) & ~7;
+  h->trec.ensure((size_t)pstride * nparts);
+  OwnedSet &c = h->C();
+  TileRecArgs R{h->nlocal, na, pstride, force, epart, h->gorder.p, c.xt.p, c.vr.p, c.e.p, fluid, h->trec.p};
+  LAUNCH(h, k_tile_records, nblk(na, 256), 256, R);
+  return pstride;
+}
+template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A)
+{
+  constexpr bool F = (KINDS & (K_TAIT | K_MORRIS)) != 0, H = (KINDS & K_HEAT) != 0;
+  constexpr int NP = F ? (H ? 5 : 4) : 3, NK = (F ? 1 : 0) + (H ? 1 : 0);
+  size_t smem = TileSmem<NP, NK>::bytes(h->tile_cap);
+  switch (h->tile_split) {
+  case 1: launch_tiles(h, k_tile_force<KINDS, 1>, "k_tile_force", TILE_ROWS, smem, A); break;
+  case 2: launch_tiles(h, k_tile_force<KINDS, 2>, "k_tile_force", TILE_ROWS * 2, smem, A); break;
+  default: launch_tiles(h, k_tile_force<KINDS, 4>, "k_tile_force", TILE_ROWS * 4, smem, A); break;
+  }
+}
+static void run_pass_tile(b200_sph *h, const Pass &p)
+{
+  const int B = 256;
+  if (p.type == 0) {
+    const PairTab &T = h->h_tab[p.slots[0]];
+    bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
+    h->tbegin(T_DENSITY);
+    if (active) {
+      int pstride = tile_records(h, 2, 0, -1, nullptr);
+      TileArgs A = tile_args(h, pstride);
+      A.tab[0] = h->d_tab[p.slots[0]];
+      size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
+      switch (h->tile_split) {
+      case 1: launch_tiles(h, k_tile_rhosum<1>, "k_tile_rhosum", TILE_ROWS, smem, A); break;
+      case 2: launch_tiles(h, k_tile_rhosum<2>, "k_tile_rhosum", TILE_ROWS * 2, smem, A); break;
+      default: launch_tiles(h, k_tile_rhosum<4>, "k_tile_rhosum", TILE_ROWS * 4, smem, A); break;
+      }
+    }
+    if (h->nghost)       // comm->forward_comm_pair (:203)
+      comm_forward_generic(h, 1,
+        [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
+        [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
+    h->tend();
+    return;
+  }
+  const PairTab *fluid = nullptr, *heat = nullptr;
+  for (int s = 0; s < p.nslots; s++) {
+    int kk = kind_of(h->h_tab[p.slots[s]].style);
+    if (kk & (K_TAIT | K_MORRIS)) fluid = h->d_tab[p.slots[s]];
+    if (kk & K_HEAT) heat = h->d_tab[p.slots[s]];
+  }
+  int nparts = fluid ? (heat ? 5 : 4) : 3;
+  h->tbegin(T_DERIVE);
+  int pstride = tile_records(h, nparts, fluid ? 1 : 0, heat ? (fluid ? 4 : 2) : -1, fluid);
+  h->tend();
+  TileArgs A = tile_args(h, pstride);
+  int nk = 0;
+  if (fluid) A.tab[nk++] = fluid;
+  if (heat) A.tab[nk++] = heat;
+  h->tbegin(T_FORCE);
+  switch (p.kinds) {
+  case K_TAIT: launch_tile_force<K_TAIT>(h, A); break;
+  case K_MORRIS: launch_tile_force<K_MORRIS>(h, A); break;
+  case K_HEAT: launch_tile_force<K_HEAT>(h, A); break;
+  case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, A); break;
+  case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, A); break;
+  default: throw std::string("b200: no tile force kernel for this sub-style group");
+  }
+  h->tend();
+}
+
 static void run_pass(b200_sph *h, const Pass &p)
 {
   if (!h->nlocal) return;
+  if (h->tile_on != h->rows_tiled) throw std::string("b200: the neighbor rows were built for another pair plan (call b200_setup / b200_reneighbor)");
+  if (h->tile_on) { run_pass_tile(h, p); return; }
   const int B = 256;
   if (p.type <= 2) {
     const PairTab &T = h->h_tab[p.slots[0]];
@@ -660,7 +828,7 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
 {
   const int B = 256;
   h->tbegin(T_FINAL);
-  if (rev && (h->nghost || h->world > 1))
+  if (rev && (h->nghost || h->world > 1) && !h->tile_on)      // the tile path puts nothing on ghosts (b200_tile.cuh)
     comm_reverse_generic(h, NB_REVERSE,
       [&](Swap &s) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), h->sendbuf.p); },
       [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
@@ -886,6 +1054,9 @@ int b200_create(b200_sph **out, int device)
   CK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
   CK(cudaMalloc(&h->d_dmaxsq, sizeof(unsigned long long))); CK(cudaMemset(h->d_dmaxsq, 0, sizeof(unsigned long long)));
   h->d_scan_far = h->d_flags + 8;
+  CK(cudaMalloc(&h->d_tflags, 8 * sizeof(int))); CK(cudaMemset(h->d_tflags, 0, 8 * sizeof(int)));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  h->nsm = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
   CK(cudaMallocHost(&h->h_flags, 16 * sizeof(int)));
   memset(&h->fl, 0, sizeof h->fl);
@@ -908,6 +1079,7 @@ int b200_destroy(b200_sph *h)
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
+  h->tiles.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
   return 0;
 }
@@ -978,7 +1150,7 @@ int b200_neighbor(b200_sph *h, double skin, int every, int delay, int check, con
 int b200_timestep(b200_sph *h, double dt, double ftm2v, long long ntimestep) { h->dt = dt; h->ftm2v = ftm2v; h->ntimestep = ntimestep; return 0; }
 int b200_comm_modify(b200_sph *h, int ghost_velocity) { h->ghost_velocity = ghost_velocity; return 0; }
 
-int b200_pair_clear(b200_sph *h) { h->npair = 0; h->plan.clear(); return 0; }
+int b200_pair_clear(b200_sph *h) { h->npair = 0; h->plan.clear(); h->tile_on = false; return 0; }
 int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
 {
   int slot = -1;
@@ -1172,6 +1344,33 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   CK(cudaMemcpy(cnt.data(), h->numneigh.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<int> cfar(n);
   CK(cudaMemcpy(cfar.data(), h->numfar.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h->rows_tiled) {        // slot lists of the tile path -> particle indices on the device, then as below
+    for (int s = 0; s < n; s++) numneigh[orig[s]] = cnt[s] + cfar[s];
+    if (!jtag) return 0;
+    long long tot = 0;
+    std::vector<long long> off(n + 1);
+    for (int i = 0; i < n; i++) { off[i] = tot; tot += numneigh[i]; }
+    if (nentries < tot) throw std::string("b200_get_neighbor_list: buffer too small");
+    CK(cudaMemcpy(tag.data(), h->C().tag.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(img.data(), h->gimage.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
+    int width = 2 * h->stride;
+    DevBuf<int> out; out.ensure((size_t)n * width);
+    TileExportArgs X{n, h->stride / 8, width, h->gorder.p, h->tiles.p, h->d_tflags, (const uint4 *)h->nbr.p, (const uint4 *)h->far.p, h->numneigh.p, h->numfar.p, out.p};
+    LAUNCH(h, k_tile_export, std::max(1, std::min(h->ntiles, 1024)), 128, X);
+    std::vector<int> rows((size_t)n * width);
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaMemcpy(rows.data(), out.p, rows.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    out.release();
+    std::vector<std::pair<int, int>> tmp;
+    for (int s = 0; s < n; s++) {
+      tmp.clear();
+      for (int k = 0; k < cnt[s] + cfar[s]; k++) { int j = rows[(size_t)s * width + k]; tmp.push_back({tag[j], img[j]}); }
+      std::sort(tmp.begin(), tmp.end());
+      long long o = off[orig[s]];
+      for (size_t k = 0; k < tmp.size(); k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
+    }
+    return 0;
+  }
   for (int s = 0; s < n; s++) numneigh[orig[s]] = (cnt[s] & 0xffff) + (cnt[s] >> 16) + cfar[s];
   if (!jtag) return 0;
   long long tot = 0;

@@ -1,0 +1,551 @@
+// b200_tile.cuh -- the shared-memory tile path of the single-phase pair stages.
+//
+// Why (profiles/r01_*): with one global gather per neighbor the stage kernels were bound by L1
+// wavefronts -- a 32-lane gather touches ~17 distinct 128-byte lines and L1 replays one line per
+// ~2 cycles, so 13.4 M gathers cost the whole 1.8 ms of k_force while the fp64 pipe sat at 18 %.
+// Here a CTA owns a *tile* = a run of consecutive engine cells of one x-row (<= TILE_ROWS owned
+// particles).  Everything its rows can touch lives in the 3x3 (2-D) / 3x3x3 (3-D) cell
+// neighbourhood of the run, i.e. in at most 9 contiguous ranges of the cell-sorted particle order:
+//   * k_tile_plan   cuts the cell grid into tiles whose candidate set fits in shared memory;
+//   * k_tile_build  stages the candidates' positions, tests every (row, candidate) pair by
+//                   broadcast reads and writes each row's neighbors as 16-bit *slot ids*
+//                   (position inside the tile's staged set) -- Neighbor::full_bin's list
+//                   (neigh_full.cpp:241-340), same pair set bit for bit, half the bytes;
+//   * k_tile_rhosum / k_tile_force  stage the per-particle records of the tile with TMA bulk
+//                   copies (cp.async.bulk + mbarrier), then every lane walks its own row and
+//                   reads its neighbors' records from shared memory (LDS.128, ~29 cycles,
+//                   no tag lookups) instead of from L1/L2.
+// Records are stored as 16-byte parts in separate arrays (P0 = x,y  P1 = z,rho  P2 = vx,vy
+// P3 = vz, Tait term  [P4 = e]) so that lanes reading random slots spread over all banks.
+//
+// Single-phase styles only (sph/rhosum, sph/taitwater, sph/taitwater/morris, sph/heatconduction):
+// every row evaluates its own side of each pair, ghosts included -- ghost x, vest, rho, e are
+// fresh copies of their owners (AtomVecMeso::pack_comm, atom_vec_meso.cpp:139-203, and the
+// forward_comm_pair of rho, pair_sph_rhosum.cpp:203) and the pair formulas are symmetric, so
+// no ghost rows and no reverse communication are needed.  The multiphase styles keep the
+// row path of b200_pair.cuh (their ghost data can be one step stale).
+#pragma once
+#include "b200_common.cuh"
+#include "b200_neigh.cuh"
+#include "b200_pair.cuh"
+
+#define TILE_ROWS 256            // owned particles per tile (target; a single denser cell is looped over)
+#define TILE_MAXRANGE 9
+#define TILE_MAXSEG 18
+#define TILE_SLOT_BITS 13
+#define TILE_SLOT_MASK 0x1fffu
+#define TILE_MAXSLOTS 8190
+#define TILE_BUILD_NT 256
+#define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+struct TileDesc {
+  int row0, nrows;               // owned rows [row0, row0 + nrows)
+  int c0, ncell;                 // its cells: linear ids c0 .. c0+ncell-1 (one x-row of the engine grid)
+  int nrange, nslots, center, pad;
+  int rcell[TILE_MAXRANGE];      // range r = one (dy,dz) x-row of candidate cells: first cell (linear id) ...
+  int rncell[TILE_MAXRANGE];     // ... number of cells ...
+  int rdx[TILE_MAXRANGE];        // ... and x index of its first cell minus x index of c0 (-1 or 0)
+  int seg_src[TILE_MAXSEG];      // segment 2r = owned part of range r, 2r+1 = its ghosts: first record (tile order)
+  int seg_slot[TILE_MAXSEG + 1]; // first slot of each segment; seg_slot[2*nrange] = nslots
+};
+
+// ------------------------------------------------------------------ plan ----
+struct TilePlanArgs {
+  Geom g; int nlocal, rowcap, slotcap;
+  const int *cso, *csg;
+  TileDesc *tiles;
+  int *flags;                    // [0] ntiles  [1] max slots  [2] a single cell does not fit  [3] max rows
+};
+
+__device__ __forceinline__ int tile_fill(const Geom &g, int nlocal, const int *cso, const int *csg, int cy, int cz, int x0, int x1, TileDesc *d)
+{
+  int xa = imax(x0 - 1, 0), xb = imin(x1 + 1, g.nc[0] - 1);
+  int nr = 0, slots = 0;
+  for (int dz = -1; dz <= 1; dz++) {
+    int nz = cz + dz; if (nz < 0 || nz >= g.nc[2]) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      int ny = cy + dy; if (ny < 0 || ny >= g.nc[1]) continue;
+      int base = (nz * g.nc[1] + ny) * g.nc[0], a = base + xa, b = base + xb;
+      int no = cso[b + 1] - cso[a], ng = csg[b + 1] - csg[a];
+      if (d) {
+        d->rcell[nr] = a; d->rncell[nr] = xb - xa + 1; d->rdx[nr] = xa - x0;
+        d->seg_src[2 * nr] = cso[a]; d->seg_slot[2 * nr] = slots;
+        d->seg_src[2 * nr + 1] = nlocal + csg[a]; d->seg_slot[2 * nr + 1] = slots + no;
+        if (dy == 0 && dz == 0) d->center = nr;
+      }
+      slots += no + ng; nr++;
+    }
+  }
+  if (d) { d->nrange = nr; d->nslots = slots; d->seg_slot[2 * nr] = slots; }
+  return slots;
+}
+
+// one thread per x-row of cells: greedy runs of cells while rows <= rowcap and candidates <= slotcap
+__global__ void k_tile_plan(TilePlanArgs A)
+{
+  const Geom &g = A.g;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.nc[1] * g.nc[2]) return;
+  int cy = r % g.nc[1], cz = r / g.nc[1], base = r * g.nc[0];
+  int x0 = 0;
+  while (x0 < g.nc[0]) {
+    if (A.cso[base + x0 + 1] == A.cso[base + x0]) { x0++; continue; }
+    int x1 = x0;
+    int slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr);
+    while (x1 + 1 < g.nc[0]) {
+      if (A.cso[base + x1 + 2] - A.cso[base + x0] > A.rowcap) break;
+      int s2 = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1 + 1, nullptr);
+      if (s2 > A.slotcap) break;
+      x1++; slots = s2;
+    }
+    while (x1 > x0 && A.cso[base + x1 + 1] == A.cso[base + x1]) x1--;          // no trailing empty cells
+    if (slots > A.slotcap) atomicExch(&A.flags[2], 1);
+    int t = atomicAdd(&A.flags[0], 1);
+    TileDesc *d = A.tiles + t;
+    d->row0 = A.cso[base + x0]; d->nrows = A.cso[base + x1 + 1] - A.cso[base + x0]; d->c0 = base + x0; d->ncell = x1 - x0 + 1; d->pad = 0;
+    slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, d);
+    atomicMax(&A.flags[1], slots); atomicMax(&A.flags[3], d->nrows);
+    x0 = x1 + 1;
+  }
+}
+
+// ----------------------------------------------------------------- build ----
+struct TileBuildArgs {
+  Geom g; int nlocal, ngrp, cap;           // ngrp = groups of 8 entries per row; cap = slots the shared-memory staging holds
+  const double4 *xt; const int *gorder; const int *cso, *csg;
+  const double *cutneighsq, *farsq;
+  const TileDesc *tiles; const int *ntiles; int *counter;
+  uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
+};
+
+// 8 consecutive 16-bit entries of a row are one uint4; group g of row r sits at [((r >> 5) * ngrp + g) * 32 + (r & 31)],
+// so a warp of consecutive rows reads one group of each of its rows as 512 contiguous bytes.
+struct RowWriter {
+  uint4 acc; int n;
+  __device__ __forceinline__ RowWriter() : acc(make_uint4(0, 0, 0, 0)), n(0) {}
+  __device__ __forceinline__ void push(unsigned ent, uint4 *base, int ngrp)
+  {
+    unsigned v = ent << ((n & 1) * 16); int w = (n & 7) >> 1;
+    acc.x |= w == 0 ? v : 0u; acc.y |= w == 1 ? v : 0u; acc.z |= w == 2 ? v : 0u; acc.w |= w == 3 ? v : 0u;
+    if ((n & 7) == 7) { if ((n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; acc = make_uint4(0, 0, 0, 0); }
+    n++;
+  }
+  __device__ __forceinline__ void finish(uint4 *base, int ngrp) { if ((n & 7) && (n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; }
+};
+
+__global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_constant__ TileBuildArgs A)
+{
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  const int cap = A.cap + 2;                                  // +2: the paired reads may touch one slot past the end
+  double *sx = (double *)tile_smem, *sy = sx + cap, *sz = sy + cap;
+  unsigned long long *sw = (unsigned long long *)(sz + cap);
+  __shared__ TileDesc D;
+  __shared__ int s_tile;
+  __shared__ double s_cut[MAXTT], s_far[MAXTT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TILE_BUILD_NT / 32;
+  for (int k = tid; k < MAXTT; k += TILE_BUILD_NT) { s_cut[k] = A.cutneighsq[k]; s_far[k] = A.farsq[k]; }
+  const Geom &g = A.g;
+  const double cutmaxsq = g.cutneighmaxsq;
+  const double cutsafe = cutmaxsq * (1.0 - 1.0e-9);           // below this, round-off cannot move a pair across a bin-stencil boundary (k_build)
+  const int ntiles = *A.ntiles;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= ntiles) break;
+    for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += TILE_BUILD_NT) ((int *)&D)[k] = ((const int *)(A.tiles + t))[k];
+    __syncthreads();
+    // stage positions + (type | reference bin) words of every candidate
+    for (int s = 0; s < 2 * D.nrange; s++) {
+      int s0 = D.seg_slot[s], n = D.seg_slot[s + 1] - s0, src0 = D.seg_src[s];
+      for (int k = tid; k < n; k += TILE_BUILD_NT) {
+        int src = src0 + k;
+        if (s & 1) src = A.nlocal + A.gorder[src - A.nlocal];
+        double4 p = A.xt[src];
+        sx[s0 + k] = p.x; sy[s0 + k] = p.y; sz[s0 + k] = p.z; sw[s0 + k] = (unsigned long long)__double_as_longlong(p.w);
+      }
+    }
+    __syncthreads();
+    // work items: (cell of the tile, chunk of 32 of its rows); item -> warp round robin
+    int item = 0;
+    for (int ci = 0; ci < D.ncell; ci++) {
+      const int cr0 = A.cso[D.c0 + ci], cnr = A.cso[D.c0 + ci + 1] - cr0;
+      for (int rb = 0; rb < cnr; rb += 32, item++) {
+        if (item % nwarp != warp) continue;
+        const bool valid = rb + lane < cnr;
+        const int row = cr0 + rb + lane;
+        const int myslot = valid ? D.seg_slot[2 * D.center] + (row - D.seg_src[2 * D.center]) : -1;
+        double xi = 1e300, yi = 1e300, zi = 1e300; unsigned long long wi = 0;
+        if (valid) { xi = sx[myslot]; yi = sy[myslot]; zi = sz[myslot]; wi = sw[myslot]; }
+        const int ti = tw_type(wi), bxi = tw_bx(wi), byi = tw_by(wi), bzi = tw_bz(wi);
+        const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+        uint4 *nrow = A.near + rbase, *frow = A.far + rbase;
+        RowWriter wn, wf;
+
+        auto interval = [&](int s0, int s1) {      // candidates in slots [s0, s1)
+          for (int b0 = s0 & ~1; b0 < s1; b0 += 64) {
+            const int n = imin(64, s1 - b0);
+            unsigned long long m = 0;
+#pragma unroll 4
+            for (int b = 0; b < n; b += 2) {
+              double2 X = *(const double2 *)(sx + b0 + b), Y = *(const double2 *)(sy + b0 + b), Z = *(const double2 *)(sz + b0 + b);
+              double r0 = rsq_nofma(xi - X.x, yi - Y.x, zi - Z.x), r1 = rsq_nofma(xi - X.y, yi - Y.y, zi - Z.y);
+              m |= (unsigned long long)(r0 <= cutmaxsq) << b;
+              m |= (unsigned long long)(r1 <= cutmaxsq) << (b + 1);
+            }
+            if (b0 < s0) m &= ~1ull;                             // slot s0-1 belongs to the previous interval
+            if (n < 64) m &= (1ull << n) - 1;                    // (n odd: the pair read one slot too far)
+            while (m) {
+              const int idx = __ffsll((long long)m) - 1; m &= m - 1;
+              const int slot = b0 + idx;
+              if (slot == myslot) continue;
+              const unsigned long long wj = sw[slot];
+              const double rsq = rsq_nofma(xi - sx[slot], yi - sy[slot], zi - sz[slot]);
+              const int tj = tw_type(wj), tij = ti * MAXT1 + tj;
+              if (!(rsq <= s_cut[tij])) continue;
+              if (rsq >= cutsafe) {                              // the reference's own bin stencil (neigh_stencil.cpp:434-448), see k_build
+                int dbx = abs(tw_bx(wj) - bxi), dby = abs(tw_by(wj) - byi), dbz = abs(tw_bz(wj) - bzi);
+                if (dbx > g.sx || dby > g.sy || dbz > g.sz) continue;
+                double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0,
+                       ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
+                if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) continue;
+              }
+              const unsigned ent = ((unsigned)tj << TILE_SLOT_BITS) | (unsigned)slot;
+              if (rsq >= s_far[tij]) wf.push(ent, frow, A.ngrp); else wn.push(ent, nrow, A.ngrp);
+            }
+          }
+        };
+
+        for (int r = 0; r < D.nrange; r++) {
+          int k0 = imax(ci - 1 - D.rdx[r], 0), k1 = imin(ci + 1 - D.rdx[r], D.rncell[r] - 1);
+          if (k0 > k1) continue;
+          int ca = D.rcell[r] + k0, cb = D.rcell[r] + k1, cr = D.rcell[r];
+          interval(D.seg_slot[2 * r] + A.cso[ca] - A.cso[cr], D.seg_slot[2 * r] + A.cso[cb + 1] - A.cso[cr]);
+          int ga = A.csg[ca] - A.csg[cr], gb = A.csg[cb + 1] - A.csg[cr];
+          if (gb > ga) interval(D.seg_slot[2 * r + 1] + ga, D.seg_slot[2 * r + 1] + gb);
+        }
+        if (valid) {
+          wn.finish(nrow, A.ngrp); wf.finish(frow, A.ngrp);
+          A.numneigh[row] = wn.n; A.numfar[row] = wf.n;
+          atomicMax(A.maxcount, max(wn.n, wf.n));
+        }
+      }
+    }
+  }
+}
+
+// slot ids -> device particle indices, row-major [row][width] (tests / b200_get_neighbor_list only)
+struct TileExportArgs {
+  int nlocal, ngrp, width;
+  const int *gorder; const TileDesc *tiles; const int *ntiles;
+  const uint4 *near, *far; const int *numneigh, *numfar;
+  int *out;
+};
+__global__ void k_tile_export(TileExportArgs A)
+{
+  __shared__ TileDesc D;
+  const int ntiles = *A.ntiles;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < (int)(sizeof(TileDesc) / 4); k += blockDim.x) ((int *)&D)[k] = ((const int *)(A.tiles + t))[k];
+    __syncthreads();
+    for (int rt = threadIdx.x; rt < D.nrows; rt += blockDim.x) {
+      int row = D.row0 + rt, nn = A.numneigh[row], nf = A.numfar[row], o = 0;
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      for (int pass = 0; pass < 2; pass++) {
+        const unsigned short *p = (const unsigned short *)((pass ? A.far : A.near) + rbase);
+        int n = pass ? nf : nn;
+        for (int k = 0; k < n; k++) {
+          int slot = p[(size_t)(k >> 3) * 32 * 8 + (k & 7)] & TILE_SLOT_MASK;
+          int s = 0;
+          while (slot >= D.seg_slot[s + 1]) s++;
+          int src = D.seg_src[s] + (slot - D.seg_slot[s]);
+          if (s & 1) src = A.nlocal + A.gorder[src - A.nlocal];
+          if (o < A.width) A.out[(size_t)row * A.width + o] = src;
+          o++;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------- records ----
+// Per-pass records in tile order (owned atoms in device order, then the ghosts in cell order = gorder), one
+// double2 array per part: P0 = x,y   P1 = z,rho   [P2 = vest.x,vest.y   P3 = vest.z, Tait term]   [Pe = e,0]
+struct TileRecArgs {
+  int nlocal, nall, pstride, force, epart;   // epart < 0: no energy part
+  const int *gorder; const double4 *xt, *vr; const double *e; const PairTab *fluid;
+  double2 *rec;
+};
+__global__ void k_tile_records(TileRecArgs A)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.nall) return;
+  int src = i < A.nlocal ? i : A.nlocal + A.gorder[i - A.nlocal];
+  double4 x = A.xt[src], v = A.vr[src];
+  A.rec[i] = make_double2(x.x, x.y);
+  A.rec[(size_t)A.pstride + i] = make_double2(x.z, v.w);
+  if (A.force) {
+    double pf = 0.0;
+    if (A.fluid) {                     // B((rho/rho0)^7 - 1)/rho^2, pair_sph_taitwater.cpp:118-120
+      int t = tw_type(__double_as_longlong(x.w));
+      double tmp = v.w / A.fluid->rho0[t], fi = tmp * tmp * tmp;
+      pf = A.fluid->B[t] * (fi * fi * tmp - 1.0) / (v.w * v.w);
+    }
+    A.rec[(size_t)2 * A.pstride + i] = make_double2(v.x, v.y);
+    A.rec[(size_t)3 * A.pstride + i] = make_double2(v.z, pf);
+  }
+  if (A.epart >= 0) A.rec[(size_t)A.epart * A.pstride + i] = make_double2(A.e[src], 0.0);
+}
+
+// ---------------------------------------------------- TMA / mbarrier glue ---
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{ // 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (UBLKCP in SASS)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p)
+{
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+struct TileArgs {
+  int nlocal, ngrp, pstride, cap;            // cap = slots per part in shared memory
+  const double2 *rec;
+  const uint4 *near, *far; const int *numneigh, *numfar; const int *scan_far;
+  const TileDesc *tiles; const int *ntiles; int *counter;
+  const double4 *xt;
+  double4 *vr_out, *fd; double *de;
+  const PairTab *tab[2];
+};
+
+// shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc | mbarrier | tile id
+template <int NPARTS, int NK> struct TileSmem {
+  double2 *part; PairTab *T; TileDesc *D; unsigned long long *bar; int *tile;
+  __device__ __forceinline__ TileSmem(unsigned char *base, int cap)
+  {
+    part = (double2 *)base;
+    T = (PairTab *)(base + (size_t)NPARTS * cap * 16);
+    D = (TileDesc *)(T + NK);
+    bar = (unsigned long long *)(D + 1);
+    tile = (int *)(bar + 1);
+  }
+  static size_t bytes(int cap) { return (size_t)NPARTS * cap * 16 + NK * sizeof(PairTab) + sizeof(TileDesc) + 16; }
+};
+
+// fetch the next tile and start the bulk copies of its records; returns false when the tiles are used up
+template <int NPARTS, int NK, int NT>
+__device__ __forceinline__ bool tile_begin(const TileArgs &A, TileSmem<NPARTS, NK> &S, int ntiles)
+{
+  const int tid = threadIdx.x;
+  __syncthreads();                                   // everyone is done with the previous tile's records
+  if (tid == 0) *S.tile = atomicAdd(A.counter, 1);
+  __syncthreads();
+  const int t = *S.tile;
+  if (t >= ntiles) return false;
+  for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += NT) ((int *)S.D)[k] = ((const int *)(A.tiles + t))[k];
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) mbar_expect_tx(S.bar, (unsigned)S.D->nslots * 16u * NPARTS);
+    __syncwarp();
+    for (int s = tid; s < 2 * S.D->nrange; s += 32) {
+      int s0 = S.D->seg_slot[s], n = S.D->seg_slot[s + 1] - s0;
+      if (n > 0)
+#pragma unroll
+        for (int p = 0; p < NPARTS; p++)
+          bulk_g2s(S.part + (size_t)p * A.cap + s0, A.rec + (size_t)p * A.pstride + S.D->seg_src[s], (unsigned)n * 16u, S.bar);
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- density ---
+// PairSPHRhoSum::compute, pair_sph_rhosum.cpp:112-197 (full list; quadric kernel, per-type mass)
+template <int SPLIT>
+__global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __grid_constant__ TileArgs A)
+{
+  constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;        // LPW rows per warp, SPLIT lanes per row
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  TileSmem<2, 1> S(tile_smem, A.cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane / LPW, rl = lane % LPW;
+  load_tab(S.T, A.tab[0]);
+  if (tid == 0) mbar_init(S.bar, 1);
+  const PairTab &T = S.T[0];
+  const double2 *P0 = S.part, *P1 = S.part + A.cap;
+  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  unsigned phase = 0;
+  while (tile_begin<2, 1, NT>(A, S, ntiles)) {
+    const TileDesc &D = *S.D;
+    mbar_wait(S.bar, phase); phase ^= 1;
+    for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
+      const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
+      bool valid = rt < D.nrows;
+      const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
+      double2 a = make_double2(0, 0), b = a; int ti = 1;
+      if (valid) { a = P0[myslot]; b = P1[myslot]; ti = tw_type(__double_as_longlong(A.xt[row].w)); }
+      if (valid && T.iskip[ti]) valid = false;                    // atoms of skipped types keep their integrated rho
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      double acc = 0.0;
+      for (int pass = 0; pass < 1 + scan_far; pass++) {
+        const uint4 *lp = (pass ? A.far : A.near) + rbase;
+        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        for (int gi = sub; gi < ng; gi += SPLIT) {
+          const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
+          const int m = nn - gi * 8;
+          const unsigned w[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            if (e < m) {
+              const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+              const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
+              const double2 qa = P0[slot], qb = P1[slot];
+              const double rsq = rsq_nofma(a.x - qa.x, a.y - qa.y, b.x - qb.x);
+              if (rsq < T.cutsq[ij]) {
+                double wf = 1.0 - rsq * T.c1[ij];                 // 1 - r^2/h^2
+                wf = wf * wf; wf = wf * wf;
+                acc += T.mass[tj] * (T.c0[ij] * wf);              // C_d (1-r^2/h^2)^4 / h^d
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPW; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+      if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------ fused forces --
+//  K_TAIT   PairSPHTaitwater::compute        pair_sph_taitwater.cpp:101-196
+//  K_MORRIS PairSPHTaitwaterMorris::compute  pair_sph_taitwater_morris.cpp:102-196
+//  K_HEAT   PairSPHHeatConduction::compute   pair_sph_heatconduction.cpp:76-132
+template <int KINDS, int SPLIT>
+__global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __grid_constant__ TileArgs A)
+{
+  constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS)) != 0;
+  constexpr bool HAS_HEAT = (KINDS & K_HEAT) != 0;
+  constexpr int NK = (HAS_FLUID ? 1 : 0) + (HAS_HEAT ? 1 : 0);
+  constexpr int NPARTS = HAS_FLUID ? (HAS_HEAT ? 5 : 4) : 3;
+  constexpr int PE = HAS_FLUID ? 4 : 2;                           // part holding e
+  constexpr int I_HEAT = HAS_FLUID ? 1 : 0;
+  constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  TileSmem<NPARTS, NK> S(tile_smem, A.cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane / LPW, rl = lane % LPW;
+  for (int t = 0; t < NK; t++) load_tab(S.T + t, A.tab[t]);
+  if (tid == 0) mbar_init(S.bar, 1);
+  const double2 *P0 = S.part, *P1 = P0 + A.cap, *P2 = P1 + A.cap, *P3 = P2 + A.cap, *PEp = S.part + (size_t)PE * A.cap;
+  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  unsigned phase = 0;
+  while (tile_begin<NPARTS, NK, NT>(A, S, ntiles)) {
+    const TileDesc &D = *S.D;
+    mbar_wait(S.bar, phase); phase ^= 1;
+    for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
+      const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
+      const bool valid = rt < D.nrows;
+      const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
+      double2 a = make_double2(0, 0), b = a, c = a, d = a; double ei = 0.0; int ti = 1;
+      if (valid) {
+        a = P0[myslot]; b = P1[myslot];
+        if (HAS_FLUID) { c = P2[myslot]; d = P3[myslot]; }
+        if (HAS_HEAT) ei = PEp[myslot].x;
+        ti = tw_type(__double_as_longlong(A.xt[row].w));
+      }
+      const double rhoi = b.y, mi = S.T[0].mass[ti];
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
+      for (int pass = 0; pass < 1 + scan_far; pass++) {
+        const uint4 *lp = (pass ? A.far : A.near) + rbase;
+        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        for (int gi = sub; gi < ng; gi += SPLIT) {
+          const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
+          const int m = nn - gi * 8;
+          const unsigned w[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            if (e >= m) continue;
+            const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
+            const double2 qa = P0[slot], qb = P1[slot];
+            const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
+            const double rsq = rsq_nofma(dx, dy, dz);
+            bool any = false;
+#pragma unroll
+            for (int t = 0; t < NK; t++) any |= rsq < S.T[t].cutsq[ij];
+            if (!any) continue;
+            const double rhoj = qb.y, mj = S.T[0].mass[tj];
+            const double rinv = rsqrt(rsq), r = rsq * rinv;
+            if (HAS_FLUID) {
+              const PairTab &P = S.T[0];
+              if (rsq < P.cutsq[ij]) {
+                const double2 qc = P2[slot], qd = P3[slot];
+                const double h = P.h[ij];
+                double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;              // Lucy (dW/dr)/r  (:135-151)
+                const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
+                const double dvdr = dx * dvx + dy * dvy + dz * dvz;
+                const double mm = mi * mj;
+                if (KINDS & K_TAIT) {
+                  double fvisc = 0.0;
+                  if (dvdr < 0.0)                                             // Monaghan artificial viscosity (:163-169), one division
+                    fvisc = -P.visc[ij] * (P.cs[ti] + P.cs[tj]) * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+                  const double fpair = -mm * (d.y + qd.y + fvisc) * wfd;
+                  fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                  ade += -0.5 * fpair * dvdr;
+                } else {                                                      // Morris viscosity (morris :165-176)
+                  const double fvisc = 2.0 * P.visc[ij] / (rhoi * rhoj) * mm * wfd;
+                  const double fpair = -mm * (d.y + qd.y) * wfd;
+                  fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
+                  ade += -0.5 * (fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz));
+                }
+                adrho += mj * dvdr * wfd;
+              }
+            }
+            if (HAS_HEAT) {
+              const PairTab &P = S.T[I_HEAT];
+              if (rsq < P.cutsq[ij]) {
+                const double h = P.h[ij];
+                double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;
+                const double ej = PEp[slot].x;
+                // 2 mi mj/(mi+mj) (rho_i+rho_j)/(rho_i rho_j) D (e_i - e_j) W'/r  (:122-125), one division
+                ade += 2.0 * mi * mj * (rhoi + rhoj) * P.visc[ij] * (ei - ej) * wfd / ((mi + mj) * (rhoi * rhoj));
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPW; o < 32; o <<= 1) {
+        fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
+        adrho += __shfl_xor_sync(FULLMASK, adrho, o); ade += __shfl_xor_sync(FULLMASK, ade, o);
+      }
+      if (valid && sub == 0) {
+        double4 f = A.fd[row];
+        f.x += fx; f.y += fy; f.z += fz; f.w += adrho;
+        A.fd[row] = f;
+        A.de[row] += ade;
+      }
+    }
+  }
+}
