@@ -103,7 +103,7 @@ struct b200_sph {
   double mass[MAXT1] = {0};
   double skin = 0.3, cutneighmax = 0, triggersq = 0;
   int every = 1, delay = 10, check = 1, ago = 0;
-  double h_cutneighsq[MAXTT] = {0};
+  double h_cutneighsq[MAXTT] = {0}, h_farsq[MAXTT] = {0};
   DevBuf<double> d_cutneighsq;
   double dt = 0, ftm2v = 1; long long ntimestep = 0;
   int npair = 0; PairTab h_tab[MAXPAIR]; PairTab *d_tab[MAXPAIR] = {nullptr};
@@ -134,7 +134,7 @@ struct b200_sph {
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   // tile path (b200_tile.cuh): single-phase decks
-  bool tile_on = false, tile_ok = true, rows_tiled = false;
+  bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
   DevBuf<TileDesc> tiles; DevBuf<double2> trec;
   int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter
@@ -481,7 +481,13 @@ static bool tile_rows(b200_sph *h)
     B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p;
     B.tiles = h->tiles.p; B.ntiles = h->d_tflags; B.counter = h->d_tflags + 4;
     B.near = (uint4 *)h->nbr.p; B.far = (uint4 *)h->far.p; B.numneigh = h->numneigh.p; B.numfar = h->numfar.p; B.maxcount = h->d_flags;
-    launch_tiles(h, k_tile_build, "k_tile_build", TILE_BUILD_NT, (size_t)(h->tile_cap + 2) * 32, B);
+    // one cutoff for every type pair (the common deck) -> scalar thresholds in the fp32 phase
+    B.uni = 1; B.cutsq_u = h->h_cutneighsq[1 * MAXT1 + 1]; B.farsq_u = h->h_farsq[1 * MAXT1 + 1];
+    for (int i = 1; i <= h->ntypes; i++) for (int j = 1; j <= h->ntypes; j++)
+      if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u) B.uni = 0;
+    size_t bsm = (size_t)13 * (((h->tile_cap + 3) & ~3) + 4);
+    if (B.uni) launch_tiles(h, k_tile_build<true>, "k_tile_build", TILE_BUILD_NT, bsm, B);
+    else launch_tiles(h, k_tile_build<false>, "k_tile_build", TILE_BUILD_NT, bsm, B);
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     int mx = h->h_flags[0];
@@ -610,6 +616,7 @@ static void build_plan(b200_sph *h)
   h->far_margin = h->skin > 0.0 ? 0.25 * h->skin : 0.0;
   for (int k = 0; k < MAXTT; k++) fsq[k] = (h->far_margin > 0.0 && psq[k] >= 0.0) ? (sqrt(psq[k]) + h->far_margin) * (sqrt(psq[k]) + h->far_margin) : 1e300;
   h->d_prunesq.ensure(MAXTT); h->d_farsq.ensure(MAXTT);
+  memcpy(h->h_farsq, fsq, sizeof fsq);
   CK(cudaMemcpyAsync(h->d_farsq.p, fsq, sizeof fsq, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->d_prunesq.p, psq, sizeof psq, cudaMemcpyHostToDevice, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -640,9 +647,9 @@ static void build_plan(b200_sph *h)
   }
   h->tile_on = ok; h->tile_nparts = np; h->tile_nk = nk;
   long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - (long long)sizeof(TileDesc) - 64;
-  h->tile_slotcap = (int)std::min<long long>(std::min<long long>(TILE_MAXSLOTS, capb / (16 * np)), 7000) & ~1;    // 7000: k_tile_build stages 32 B per slot
+  h->tile_slotcap = (int)std::min<long long>(std::min<long long>(TILE_MAXSLOTS, capb / (16 * np)), TILE_MAXSLOTS) & ~1;
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
-  if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;
+  if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
 }
 
 static PairArgs pair_args(b200_sph *h)
@@ -683,15 +690,40 @@ static int tile_records(b200_sph *h, int nparts, int force, int epart, const Pai
   LAUNCH(h, k_tile_records, nblk(na, 256), 256, R);
   return pstride;
 }
-template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A)
+// constants of a sub-style whose coefficients do not depend on the type pair (TileUni); false if they do
+static bool tile_uni(const b200_sph *h, const PairTab &T, TileUni &U)
+{
+  memset(&U, 0, sizeof U);
+  bool first = true, ok = true;
+  unsigned used = 0;
+  for (int i = 1; i <= h->ntypes; i++)
+    for (int j = 1; j <= h->ntypes; j++) {
+      int k = i * MAXT1 + j;
+      if (T.cutsq[k] < 0.0) continue;
+      U.mapmask |= 1ull << k; used |= (1u << i) | (1u << j);
+      if (first) { U.cutsq = T.cutsq[k]; U.h = T.h[k]; U.c0 = T.c0[k]; U.c1 = T.c1[k]; U.visc = T.visc[k]; first = false; }
+      else if (U.cutsq != T.cutsq[k] || U.h != T.h[k] || U.c0 != T.c0[k] || U.c1 != T.c1[k] || U.visc != T.visc[k]) ok = false;
+    }
+  if (first) return false;
+  bool f2 = true;
+  for (int i = 1; i <= h->ntypes; i++) {
+    if (!(used & (1u << i))) continue;
+    if (f2) { U.mass = T.mass[i]; U.cs = T.cs[i]; U.self = T.self0[i]; f2 = false; }
+    else if (U.mass != T.mass[i] || U.cs != T.cs[i] || U.self != T.self0[i]) ok = false;
+  }
+  return ok;
+}
+template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A, bool uni)
 {
   constexpr bool F = (KINDS & (K_TAIT | K_MORRIS)) != 0, H = (KINDS & K_HEAT) != 0;
   constexpr int NP = F ? (H ? 5 : 4) : 3, NK = (F ? 1 : 0) + (H ? 1 : 0);
   size_t smem = TileSmem<NP, NK>::bytes(h->tile_cap);
-  switch (h->tile_split) {
-  case 1: launch_tiles(h, k_tile_force<KINDS, 1>, "k_tile_force", TILE_ROWS, smem, A); break;
-  case 2: launch_tiles(h, k_tile_force<KINDS, 2>, "k_tile_force", TILE_ROWS * 2, smem, A); break;
-  default: launch_tiles(h, k_tile_force<KINDS, 4>, "k_tile_force", TILE_ROWS * 4, smem, A); break;
+  if (h->tile_split == 1) {
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true>, "k_tile_force", TILE_ROWS, smem, A);
+    else launch_tiles(h, k_tile_force<KINDS, 1, false>, "k_tile_force", TILE_ROWS, smem, A);
+  } else {
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true>, "k_tile_force", TILE_ROWS * 2, smem, A);
+    else launch_tiles(h, k_tile_force<KINDS, 2, false>, "k_tile_force", TILE_ROWS * 2, smem, A);
   }
 }
 static void run_pass_tile(b200_sph *h, const Pass &p)
@@ -705,11 +737,17 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
       int pstride = tile_records(h, 2, 0, -1, nullptr);
       TileArgs A = tile_args(h, pstride);
       A.tab[0] = h->d_tab[p.slots[0]];
+      bool uni = tile_uni(h, T, A.uni[0]) && !h->tile_nouni;
       size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
-      switch (h->tile_split) {
-      case 1: launch_tiles(h, k_tile_rhosum<1>, "k_tile_rhosum", TILE_ROWS, smem, A); break;
-      case 2: launch_tiles(h, k_tile_rhosum<2>, "k_tile_rhosum", TILE_ROWS * 2, smem, A); break;
-      default: launch_tiles(h, k_tile_rhosum<4>, "k_tile_rhosum", TILE_ROWS * 4, smem, A); break;
+      if (h->tile_split == 1) {
+        if (uni) launch_tiles(h, k_tile_rhosum<1, true>, "k_tile_rhosum", TILE_ROWS, smem, A);
+        else launch_tiles(h, k_tile_rhosum<1, false>, "k_tile_rhosum", TILE_ROWS, smem, A);
+      } else if (h->tile_split == 2) {
+        if (uni) launch_tiles(h, k_tile_rhosum<2, true>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
+        else launch_tiles(h, k_tile_rhosum<2, false>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
+      } else {
+        if (uni) launch_tiles(h, k_tile_rhosum<4, true>, "k_tile_rhosum", TILE_ROWS * 4, smem, A);
+        else launch_tiles(h, k_tile_rhosum<4, false>, "k_tile_rhosum", TILE_ROWS * 4, smem, A);
       }
     }
     if (h->nghost)       // comm->forward_comm_pair (:203)
@@ -719,11 +757,11 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
     h->tend();
     return;
   }
-  const PairTab *fluid = nullptr, *heat = nullptr;
+  const PairTab *fluid = nullptr, *heat = nullptr, *hfluid = nullptr, *hheat = nullptr;
   for (int s = 0; s < p.nslots; s++) {
     int kk = kind_of(h->h_tab[p.slots[s]].style);
-    if (kk & (K_TAIT | K_MORRIS)) fluid = h->d_tab[p.slots[s]];
-    if (kk & K_HEAT) heat = h->d_tab[p.slots[s]];
+    if (kk & (K_TAIT | K_MORRIS)) { fluid = h->d_tab[p.slots[s]]; hfluid = &h->h_tab[p.slots[s]]; }
+    if (kk & K_HEAT) { heat = h->d_tab[p.slots[s]]; hheat = &h->h_tab[p.slots[s]]; }
   }
   int nparts = fluid ? (heat ? 5 : 4) : 3;
   h->tbegin(T_DERIVE);
@@ -731,15 +769,17 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
   h->tend();
   TileArgs A = tile_args(h, pstride);
   int nk = 0;
-  if (fluid) A.tab[nk++] = fluid;
-  if (heat) A.tab[nk++] = heat;
+  bool uni = !h->tile_nouni;
+  if (fluid) { uni = tile_uni(h, *hfluid, A.uni[nk]) && uni; A.tab[nk++] = fluid; }
+  if (heat) { uni = tile_uni(h, *hheat, A.uni[nk]) && uni; A.tab[nk++] = heat; }
+  if (fluid && heat && (A.uni[0].mass != A.uni[1].mass)) uni = false;
   h->tbegin(T_FORCE);
   switch (p.kinds) {
-  case K_TAIT: launch_tile_force<K_TAIT>(h, A); break;
-  case K_MORRIS: launch_tile_force<K_MORRIS>(h, A); break;
-  case K_HEAT: launch_tile_force<K_HEAT>(h, A); break;
-  case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, A); break;
-  case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, A); break;
+  case K_TAIT: launch_tile_force<K_TAIT>(h, A, uni); break;
+  case K_MORRIS: launch_tile_force<K_MORRIS>(h, A, uni); break;
+  case K_HEAT: launch_tile_force<K_HEAT>(h, A, uni); break;
+  case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, A, uni); break;
+  case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, A, uni); break;
   default: throw std::string("b200: no tile force kernel for this sub-style group");
   }
   h->tend();

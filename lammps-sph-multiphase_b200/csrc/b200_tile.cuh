@@ -111,21 +111,22 @@ __global__ void k_tile_plan(TilePlanArgs A)
 
 // ----------------------------------------------------------------- build ----
 struct TileBuildArgs {
-  Geom g; int nlocal, ngrp, cap;           // ngrp = groups of 8 entries per row; cap = slots the shared-memory staging holds
+  Geom g; int nlocal, ngrp, cap, uni;      // ngrp = groups of 8 entries per row; cap = slots the shared-memory staging holds
+  double cutsq_u, farsq_u;                 // uni: the one cutneighsq / far threshold of every type pair
   const double4 *xt; const int *gorder; const int *cso, *csg;
   const double *cutneighsq, *farsq;
   const TileDesc *tiles; const int *ntiles; int *counter;
   uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
 };
 
-// 8 consecutive 16-bit entries of a row are one uint4; group g of row r sits at [((r >> 5) * ngrp + g) * 32 + (r & 31)],
-// so a warp of consecutive rows reads one group of each of its rows as 512 contiguous bytes.
+// 8 entries of a row are one uint4 (16 bits each: [15:13] type of j, [12:0] slot; 0 = empty); group g of row r sits at
+// [((r >> 5) * ngrp + g) * 32 + (r & 31)], so a warp of consecutive rows reads one group of each of its rows as 512 contiguous bytes.
 struct RowWriter {
   uint4 acc; int n;
   __device__ __forceinline__ RowWriter() : acc(make_uint4(0, 0, 0, 0)), n(0) {}
   __device__ __forceinline__ void push(unsigned ent, uint4 *base, int ngrp)
   {
-    unsigned v = ent << ((n & 1) * 16); int w = (n & 7) >> 1;
+    const unsigned v = ent << ((n & 1) * 16); const int w = (n & 7) >> 1;
     acc.x |= w == 0 ? v : 0u; acc.y |= w == 1 ? v : 0u; acc.z |= w == 2 ? v : 0u; acc.w |= w == 3 ? v : 0u;
     if ((n & 7) == 7) { if ((n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; acc = make_uint4(0, 0, 0, 0); }
     n++;
@@ -133,40 +134,137 @@ struct RowWriter {
   __device__ __forceinline__ void finish(uint4 *base, int ngrp) { if ((n & 7) && (n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; }
 };
 
+// Near rows are written in a bank-aware order.  The stage kernels read a neighbor's record parts with 128-bit LDS, served per
+// quarter-warp (8 lanes x 16 B): conflict-free iff the 8 slots differ mod 8.  The order of a row's entries is free, so the k-th
+// entry of residue class c = slot mod 8 of lane q (= row & 7 inside its tile) goes to position 8 k + ((c - q) mod 8): at step t
+// the 8 lanes of a quarter-warp then read 8 different bank groups.  Classes are not equally full; finish() moves the entries
+// that stick out beyond ceil(n / 8) groups into the holes of the shorter classes (~10 % of a row, the only possible conflicts)
+// and zeroes what stays empty.  (profiles/r01_tile_*: in natural order conflicts were 54 % of k_tile_force's smem wavefronts.)
+struct NearWriter {
+  unsigned long long cnt; int n;          // 8 x 8-bit class counters
+  __device__ __forceinline__ NearWriter() : cnt(0), n(0) {}
+  __device__ __forceinline__ int count(int c) const { return (int)(cnt >> (8 * c)) & 0xff; }
+  __device__ __forceinline__ static int pos_of(int c, int k, int q) { return 8 * k + ((c - q) & 7); }
+  __device__ __forceinline__ void push(unsigned ent, int q, unsigned short *base, int stride)
+  {
+    const int c = ent & 7, k = count(c);
+    if (k < 255) cnt += 1ull << (8 * c);
+    const int pos = pos_of(c, k, q);
+    if (pos < stride) base[(size_t)(pos >> 3) * 256 + (pos & 7)] = (unsigned short)ent;
+    n++;
+  }
+  // returns the extent the row needed (in entries); the row is valid iff that is <= stride
+  __device__ __forceinline__ int finish(int q, unsigned short *base, int stride)
+  {
+    int mx = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) mx = max(mx, count(c));
+    if (mx >= 255) return 1 << 20;
+    if (8 * mx > stride) return 8 * mx;
+    const int D = (n + 7) >> 3;
+    int ch = 0, kh = count(0);
+    for (int c = 0; c < 8; c++)
+      for (int k = D; k < count(c); k++) {
+        while (kh >= D) { ch++; kh = count(ch); }
+        const int src = pos_of(c, k, q), dst = pos_of(ch, kh, q);
+        base[(size_t)(dst >> 3) * 256 + (dst & 7)] = base[(size_t)(src >> 3) * 256 + (src & 7)];
+        kh++;
+      }
+    for (;;) {
+      while (kh >= D) { if (++ch == 8) return 8 * mx; kh = count(ch); }
+      const int dst = pos_of(ch, kh, q);
+      base[(size_t)(dst >> 3) * 256 + (dst & 7)] = 0;
+      kh++;
+    }
+  }
+};
+
+__device__ __forceinline__ int tile_slot_src(const TileDesc &D, int slot, int nlocal, const int *gorder)
+{
+  int s = 0;
+  while (slot >= D.seg_slot[s + 1]) s++;
+  int src = D.seg_src[s] + (slot - D.seg_slot[s]);
+  return (s & 1) ? nlocal + gorder[src - nlocal] : src;
+}
+
+// the exact pair test of Neighbor::full_bin (neigh_full.cpp:241-340) as k_build restates it: 0 = not a neighbor, 1 = near row, 2 = far row
+__device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int j)
+{
+  const Geom &g = A.g;
+  const double4 pi = A.xt[i], pj = A.xt[j];
+  const unsigned long long wi = (unsigned long long)__double_as_longlong(pi.w), wj = (unsigned long long)__double_as_longlong(pj.w);
+  const double rsq = rsq_nofma(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+  const int tij = tw_type(wi) * MAXT1 + tw_type(wj);
+  if (!(rsq <= A.cutneighsq[tij])) return 0;
+  const double cutmaxsq = g.cutneighmaxsq;
+  if (rsq >= cutmaxsq * (1.0 - 1.0e-9)) {          // the reference's own bin stencil (neigh_stencil.cpp:434-448), see k_build
+    int dbx = abs(tw_bx(wj) - tw_bx(wi)), dby = abs(tw_by(wj) - tw_by(wi)), dbz = abs(tw_bz(wj) - tw_bz(wi));
+    if (dbx > g.sx || dby > g.sy || dbz > g.sz) return 0;
+    double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0, ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
+    if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) return 0;
+  }
+  return rsq >= A.farsq[tij] ? 2 : 1;
+}
+
+// One CTA per tile.  Candidate positions are staged as fp32 offsets from the tile's corner; every (row, candidate) pair is decided in
+// fp32 against thresholds widened by a proven error band (|rsq32 - rsq| <= 2^-23 (2 sqrt(3) r (2E + r) + 4 r^2), E = largest offset),
+// and only pairs inside the band -- a ~1e-5 fraction -- take the exact fp64 test, so the list is bit-for-bit the one the fp64 test gives.
+// Phase A: 32 candidates x 4 compares -> bit masks (broadcast float4 reads).  Phase B: entries straight from the masks.
+template <bool UNI>
 __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
   extern __shared__ __align__(128) unsigned char tile_smem[];
-  const int cap = A.cap + 2;                                  // +2: the paired reads may touch one slot past the end
-  double *sx = (double *)tile_smem, *sy = sx + cap, *sz = sy + cap;
-  unsigned long long *sw = (unsigned long long *)(sz + cap);
+  const int cap4 = ((A.cap + 3) & ~3) + 4;
+  float *fx = (float *)tile_smem, *fy = fx + cap4, *fz = fy + cap4;
+  unsigned char *ty = (unsigned char *)(fz + cap4);
   __shared__ TileDesc D;
   __shared__ int s_tile;
-  __shared__ double s_cut[MAXTT], s_far[MAXTT];
+  __shared__ unsigned s_emax;
+  __shared__ float s_thr[MAXTT][4];                            // non-uniform cutoffs: far_lo, far_hi, cut_lo, cut_hi per type pair
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TILE_BUILD_NT / 32;
-  for (int k = tid; k < MAXTT; k += TILE_BUILD_NT) { s_cut[k] = A.cutneighsq[k]; s_far[k] = A.farsq[k]; }
   const Geom &g = A.g;
-  const double cutmaxsq = g.cutneighmaxsq;
-  const double cutsafe = cutmaxsq * (1.0 - 1.0e-9);           // below this, round-off cannot move a pair across a bin-stencil boundary (k_build)
   const int ntiles = *A.ntiles;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_tile = atomicAdd(A.counter, 1);
+    if (tid == 0) { s_tile = atomicAdd(A.counter, 1); s_emax = 0; }
     __syncthreads();
     const int t = s_tile;
     if (t >= ntiles) break;
     for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += TILE_BUILD_NT) ((int *)&D)[k] = ((const int *)(A.tiles + t))[k];
     __syncthreads();
-    // stage positions + (type | reference bin) words of every candidate
+    // corner of the tile's candidate region (cell c0 shifted by one cell in every direction)
+    const int cx0 = D.c0 % g.nc[0], cy0 = (D.c0 / g.nc[0]) % g.nc[1], cz0 = D.c0 / (g.nc[0] * g.nc[1]);
+    const double ox = g.clo[0] + (cx0 - 1) / g.cinv[0], oy = g.clo[1] + (cy0 - 1) / g.cinv[1], oz = g.clo[2] + (cz0 - 1) / g.cinv[2];
+    float emax = 0.f;
     for (int s = 0; s < 2 * D.nrange; s++) {
       int s0 = D.seg_slot[s], n = D.seg_slot[s + 1] - s0, src0 = D.seg_src[s];
       for (int k = tid; k < n; k += TILE_BUILD_NT) {
         int src = src0 + k;
         if (s & 1) src = A.nlocal + A.gorder[src - A.nlocal];
         double4 p = A.xt[src];
-        sx[s0 + k] = p.x; sy[s0 + k] = p.y; sz[s0 + k] = p.z; sw[s0 + k] = (unsigned long long)__double_as_longlong(p.w);
+        float x = (float)(p.x - ox), y = (float)(p.y - oy), z = (float)(p.z - oz);
+        fx[s0 + k] = x; fy[s0 + k] = y; fz[s0 + k] = z; ty[s0 + k] = (unsigned char)tw_type(__double_as_longlong(p.w));
+        emax = fmaxf(emax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
       }
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(FULLMASK, emax, o));
+    if (lane == 0) atomicMax(&s_emax, __float_as_uint(emax));
     __syncthreads();
+    const double E = (double)__uint_as_float(s_emax) * 1.0001;
+    // thresholds with the error band: a pair is "sure inside" below lo, "sure outside" at or above hi
+    auto band = [&](double thr, float &lo, float &hi) {
+      double r = sqrt(fmax(thr, 0.0));
+      double err = 2.4e-7 * (3.4642 * r * (2.0 * E + r) + 4.0 * r * r) + 1e-37;      // 2^-22: twice the bound
+      lo = __double2float_rd(thr - err); hi = __double2float_ru(thr + err);
+    };
+    float far_lo, far_hi, cut_lo, cut_hi;
+    if (UNI) { band(A.farsq_u, far_lo, far_hi); band(A.cutsq_u, cut_lo, cut_hi); }
+    else {
+      band(g.cutneighmaxsq, cut_lo, cut_hi); far_lo = far_hi = 0.f;
+      for (int k = tid; k < MAXTT; k += TILE_BUILD_NT) { band(fmin(A.farsq[k], 1e30), s_thr[k][0], s_thr[k][1]); band(A.cutneighsq[k], s_thr[k][2], s_thr[k][3]); }
+      __syncthreads();
+    }
     // work items: (cell of the tile, chunk of 32 of its rows); item -> warp round robin
     int item = 0;
     for (int ci = 0; ci < D.ncell; ci++) {
@@ -176,43 +274,65 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
         const bool valid = rb + lane < cnr;
         const int row = cr0 + rb + lane;
         const int myslot = valid ? D.seg_slot[2 * D.center] + (row - D.seg_src[2 * D.center]) : -1;
-        double xi = 1e300, yi = 1e300, zi = 1e300; unsigned long long wi = 0;
-        if (valid) { xi = sx[myslot]; yi = sy[myslot]; zi = sz[myslot]; wi = sw[myslot]; }
-        const int ti = tw_type(wi), bxi = tw_bx(wi), byi = tw_by(wi), bzi = tw_bz(wi);
+        float xi = 1e30f, yi = 1e30f, zi = 1e30f; int ti = 0;
+        if (valid) { xi = fx[myslot]; yi = fy[myslot]; zi = fz[myslot]; ti = ty[myslot]; }
         const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
         uint4 *nrow = A.near + rbase, *frow = A.far + rbase;
-        RowWriter wn, wf;
+        NearWriter wn; RowWriter wf;
+        unsigned short *nrow16 = (unsigned short *)nrow;
+        const int q = (row - D.row0) & 7, stride = A.ngrp * 8;
 
         auto interval = [&](int s0, int s1) {      // candidates in slots [s0, s1)
-          for (int b0 = s0 & ~1; b0 < s1; b0 += 64) {
-            const int n = imin(64, s1 - b0);
-            unsigned long long m = 0;
-#pragma unroll 4
-            for (int b = 0; b < n; b += 2) {
-              double2 X = *(const double2 *)(sx + b0 + b), Y = *(const double2 *)(sy + b0 + b), Z = *(const double2 *)(sz + b0 + b);
-              double r0 = rsq_nofma(xi - X.x, yi - Y.x, zi - Z.x), r1 = rsq_nofma(xi - X.y, yi - Y.y, zi - Z.y);
-              m |= (unsigned long long)(r0 <= cutmaxsq) << b;
-              m |= (unsigned long long)(r1 <= cutmaxsq) << (b + 1);
-            }
-            if (b0 < s0) m &= ~1ull;                             // slot s0-1 belongs to the previous interval
-            if (n < 64) m &= (1ull << n) - 1;                    // (n odd: the pair read one slot too far)
-            while (m) {
-              const int idx = __ffsll((long long)m) - 1; m &= m - 1;
-              const int slot = b0 + idx;
-              if (slot == myslot) continue;
-              const unsigned long long wj = sw[slot];
-              const double rsq = rsq_nofma(xi - sx[slot], yi - sy[slot], zi - sz[slot]);
-              const int tj = tw_type(wj), tij = ti * MAXT1 + tj;
-              if (!(rsq <= s_cut[tij])) continue;
-              if (rsq >= cutsafe) {                              // the reference's own bin stencil (neigh_stencil.cpp:434-448), see k_build
-                int dbx = abs(tw_bx(wj) - bxi), dby = abs(tw_by(wj) - byi), dbz = abs(tw_bz(wj) - bzi);
-                if (dbx > g.sx || dby > g.sy || dbz > g.sz) continue;
-                double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0,
-                       ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
-                if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) continue;
+          for (int b0 = s0 & ~3; b0 < s1; b0 += 32) {
+            unsigned ns = 0, nm = 0, as = 0, am = 0;     // near sure / near maybe / all sure / all maybe
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const float4 X = *(const float4 *)(fx + b0 + 4 * k), Y = *(const float4 *)(fy + b0 + 4 * k), Z = *(const float4 *)(fz + b0 + 4 * k);
+              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
+                const float rsq = dx * dx + dy * dy + dz * dz;
+                const unsigned bit = 1u << (4 * k + c);
+                if (UNI) { ns |= rsq < far_lo ? bit : 0u; nm |= rsq < far_hi ? bit : 0u; }
+                as |= rsq < cut_lo ? bit : 0u; am |= rsq < cut_hi ? bit : 0u;
               }
-              const unsigned ent = ((unsigned)tj << TILE_SLOT_BITS) | (unsigned)slot;
-              if (rsq >= s_far[tij]) wf.push(ent, frow, A.ngrp); else wn.push(ent, nrow, A.ngrp);
+              if (b0 + 4 * k + 4 >= s1) break;
+            }
+            // only the slots of [s0, s1), and never the row particle itself
+            unsigned vm = (s1 - b0 >= 32) ? 0xffffffffu : ((1u << (s1 - b0)) - 1u);
+            if (b0 < s0) vm &= ~((1u << (s0 - b0)) - 1u);
+            if (myslot >= b0 && myslot < b0 + 32) vm &= ~(1u << (myslot - b0));
+            if (!valid) vm = 0;
+            ns &= vm; nm &= vm; as &= vm; am &= vm;
+            unsigned nearm, farm, border;
+            if (UNI) { nearm = as & ns; farm = as & ~nm; border = (as & (nm ^ ns)) | (am ^ as); }
+            else { nearm = 0; farm = 0; border = am; }            // per-type thresholds: classify every coarse hit below
+            while (border) {
+              const int idx = __ffs((int)border) - 1; border &= border - 1;
+              const int slot = b0 + idx;
+              int cls = -1;
+              if (!UNI) {
+                const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
+                const float rsq = dx * dx + dy * dy + dz * dz;
+                const float *th = s_thr[ti * MAXT1 + ty[slot]];
+                if (rsq >= th[3]) cls = 0;                       // surely outside the neighbor cutoff
+                else if (rsq < th[2]) {                          // surely inside: near or far row?
+                  if (rsq < th[0]) cls = 1; else if (rsq >= th[1]) cls = 2;
+                }
+              }
+              if (cls < 0) cls = tile_exact_class(A, row, tile_slot_src(D, slot, A.nlocal, A.gorder));
+              if (cls == 1) nearm |= 1u << idx; else if (cls == 2) farm |= 1u << idx;
+            }
+            while (nearm) {
+              const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
+              const int slot = b0 + idx;
+              wn.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, q, nrow16, stride);
+            }
+            while (farm) {
+              const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
+              const int slot = b0 + idx;
+              wf.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, frow, A.ngrp);
             }
           }
         };
@@ -226,9 +346,10 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
           if (gb > ga) interval(D.seg_slot[2 * r + 1] + ga, D.seg_slot[2 * r + 1] + gb);
         }
         if (valid) {
-          wn.finish(nrow, A.ngrp); wf.finish(frow, A.ngrp);
+          const int ext = wn.finish(q, nrow16, stride);
+          wf.finish(frow, A.ngrp);
           A.numneigh[row] = wn.n; A.numfar[row] = wf.n;
-          atomicMax(A.maxcount, max(wn.n, wf.n));
+          atomicMax(A.maxcount, max(ext, wf.n));
         }
       }
     }
@@ -255,9 +376,11 @@ __global__ void k_tile_export(TileExportArgs A)
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       for (int pass = 0; pass < 2; pass++) {
         const unsigned short *p = (const unsigned short *)((pass ? A.far : A.near) + rbase);
-        int n = pass ? nf : nn;
+        int n = ((pass ? nf : nn) + 7) & ~7;
         for (int k = 0; k < n; k++) {
-          int slot = p[(size_t)(k >> 3) * 32 * 8 + (k & 7)] & TILE_SLOT_MASK;
+          int ent = p[(size_t)(k >> 3) * 32 * 8 + (k & 7)];
+          if (!ent) continue;
+          int slot = ent & TILE_SLOT_MASK;
           int s = 0;
           while (slot >= D.seg_slot[s + 1]) s++;
           int src = D.seg_src[s] + (slot - D.seg_slot[s]);
@@ -330,6 +453,13 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p)
   return v;
 }
 
+// Per-table constants of a sub-style whose coefficients are the same for every mapped type pair (the common deck:
+// `pair_coeff * *`): they travel as kernel parameters (constant bank -> registers) instead of shared-memory table reads.
+struct TileUni {
+  unsigned long long mapmask;   // bit ti*8+tj: the sub-style acts on the pair (type 0 = empty entry is never mapped)
+  double cutsq, h, c0, c1, visc, mass, cs, self;
+};
+
 struct TileArgs {
   int nlocal, ngrp, pstride, cap;            // cap = slots per part in shared memory
   const double2 *rec;
@@ -338,6 +468,7 @@ struct TileArgs {
   const double4 *xt;
   double4 *vr_out, *fd; double *de;
   const PairTab *tab[2];
+  TileUni uni[2];
 };
 
 // shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc | mbarrier | tile id
@@ -380,9 +511,34 @@ __device__ __forceinline__ bool tile_begin(const TileArgs &A, TileSmem<NPARTS, N
   return true;
 }
 
+// branch-free fp64 sqrt and division (MUFU seed + Newton steps, <= 1-2 ulp): the CUDA built-ins carry a slow-path branch
+// that splits the pair body into basic blocks and keeps ptxas from interleaving the 8 unrolled neighbors of a group
+__device__ __forceinline__ double fast_sqrt(double a)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, hh = 0.5 * y;
+  double e = fma(-hh, g, 0.5);
+  g = fma(g, e, g); hh = fma(hh, e, hh);
+  e = fma(-hh, g, 0.5);
+  g = fma(g, e, g); hh = fma(hh, e, hh);
+  return fma(fma(-g, g, a), hh, g);
+}
+__device__ __forceinline__ double fast_div(double n, double d)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  double q = n * y;
+  return fma(fma(-d, q, n), y, q);
+}
+
 // ---------------------------------------------------------------- density ---
 // PairSPHRhoSum::compute, pair_sph_rhosum.cpp:112-197 (full list; quadric kernel, per-type mass)
-template <int SPLIT>
+template <int SPLIT, bool UNI>
 __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __grid_constant__ TileArgs A)
 {
   constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;        // LPW rows per warp, SPLIT lanes per row
@@ -392,6 +548,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
   load_tab(S.T, A.tab[0]);
   if (tid == 0) mbar_init(S.bar, 1);
   const PairTab &T = S.T[0];
+  const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
   unsigned phase = 0;
@@ -402,9 +559,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
-      double2 a = make_double2(0, 0), b = a; int ti = 1;
+      double2 a = make_double2(0, 0), b = a; int ti = 0;
       if (valid) { a = P0[myslot]; b = P1[myslot]; ti = tw_type(__double_as_longlong(A.xt[row].w)); }
       if (valid && T.iskip[ti]) valid = false;                    // atoms of skipped types keep their integrated rho
+      const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double acc = 0.0;
       for (int pass = 0; pass < 1 + scan_far; pass++) {
@@ -412,17 +570,22 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
         const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
-          const int m = nn - gi * 8;
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            if (e < m) {
-              const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-              const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
-              const double2 qa = P0[slot], qb = P1[slot];
-              const double rsq = rsq_nofma(a.x - qa.x, a.y - qa.y, b.x - qb.x);
+            const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS;
+            const double2 qa = P0[slot], qb = P1[slot];
+            const double rsq = rsq_nofma(a.x - qa.x, a.y - qa.y, b.x - qb.x);
+            if (UNI) {
+              const bool hit = (rsq < U.cutsq) & ((rowmask >> tj) & 1u);
+              double wf = fma(-rsq, U.c1, 1.0);                   // 1 - r^2/h^2
+              wf = wf * wf; wf = wf * wf;
+              acc += hit ? wf : 0.0;                              // x mass C_d / h^d at the end
+            } else {
+              const int ij = ti * MAXT1 + tj;                     // empty entries: cutsq[ti][0] = -1
               if (rsq < T.cutsq[ij]) {
-                double wf = 1.0 - rsq * T.c1[ij];                 // 1 - r^2/h^2
+                double wf = 1.0 - rsq * T.c1[ij];
                 wf = wf * wf; wf = wf * wf;
                 acc += T.mass[tj] * (T.c0[ij] * wf);              // C_d (1-r^2/h^2)^4 / h^d
               }
@@ -432,6 +595,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
       }
 #pragma unroll
       for (int o = LPW; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+      if (UNI) acc *= U.mass * U.c0;
       if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
     }
   }
@@ -441,7 +605,9 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
 //  K_TAIT   PairSPHTaitwater::compute        pair_sph_taitwater.cpp:101-196
 //  K_MORRIS PairSPHTaitwaterMorris::compute  pair_sph_taitwater_morris.cpp:102-196
 //  K_HEAT   PairSPHHeatConduction::compute   pair_sph_heatconduction.cpp:76-132
-template <int KINDS, int SPLIT>
+// UNI: both tables are uniform (TileUni) -> a branch-free body on register constants that ptxas interleaves across the
+// 8 neighbors of a group; otherwise the per-type tables are read from shared memory.
+template <int KINDS, int SPLIT, bool UNI>
 __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __grid_constant__ TileArgs A)
 {
   constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS)) != 0;
@@ -457,6 +623,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   for (int t = 0; t < NK; t++) load_tab(S.T + t, A.tab[t]);
   if (tid == 0) mbar_init(S.bar, 1);
   const double2 *P0 = S.part, *P1 = P0 + A.cap, *P2 = P1 + A.cap, *P3 = P2 + A.cap, *PEp = S.part + (size_t)PE * A.cap;
+  const TileUni &UF = A.uni[0], &UH = A.uni[I_HEAT];
+  // register constants of the uniform body
+  const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_mm = UF.mass * UF.mass;
+  const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) : 0.0;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
   unsigned phase = 0;
   while (tile_begin<NPARTS, NK, NT>(A, S, ntiles)) {
@@ -466,7 +636,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       const bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
-      double2 a = make_double2(0, 0), b = a, c = a, d = a; double ei = 0.0; int ti = 1;
+      double2 a = make_double2(0, 0), b = make_double2(0, 1), c = a, d = a; double ei = 0.0; int ti = 0;
       if (valid) {
         a = P0[myslot]; b = P1[myslot];
         if (HAS_FLUID) { c = P2[myslot]; d = P3[myslot]; }
@@ -474,6 +644,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         ti = tw_type(__double_as_longlong(A.xt[row].w));
       }
       const double rhoi = b.y, mi = S.T[0].mass[ti];
+      const unsigned maskf = (unsigned)(UF.mapmask >> (ti * 8)) & 0xffu, maskh = (unsigned)(UH.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
       for (int pass = 0; pass < 1 + scan_far; pass++) {
@@ -481,55 +652,87 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
-          const int m = nn - gi * 8;
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            if (e >= m) continue;
             const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-            const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
+            const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS;
             const double2 qa = P0[slot], qb = P1[slot];
             const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
             const double rsq = rsq_nofma(dx, dy, dz);
-            bool any = false;
-#pragma unroll
-            for (int t = 0; t < NK; t++) any |= rsq < S.T[t].cutsq[ij];
-            if (!any) continue;
-            const double rhoj = qb.y, mj = S.T[0].mass[tj];
-            const double rinv = rsqrt(rsq), r = rsq * rinv;
-            if (HAS_FLUID) {
-              const PairTab &P = S.T[0];
-              if (rsq < P.cutsq[ij]) {
+            const double rhoj = qb.y;
+            if (UNI) {
+              const double r = fast_sqrt(fmax(rsq, 1.0e-300));
+              if (HAS_FLUID) {
+                const bool hit = (rsq < UF.cutsq) & ((maskf >> tj) & 1u);
                 const double2 qc = P2[slot], qd = P3[slot];
-                const double h = P.h[ij];
-                double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;              // Lucy (dW/dr)/r  (:135-151)
+                double wfd = UF.h - r; wfd = UF.c0 * wfd * wfd;             // Lucy (dW/dr)/r  (:135-151)
+                wfd = hit ? wfd : 0.0;
                 const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
                 const double dvdr = dx * dvx + dy * dvy + dz * dvz;
-                const double mm = mi * mj;
                 if (KINDS & K_TAIT) {
-                  double fvisc = 0.0;
-                  if (dvdr < 0.0)                                             // Monaghan artificial viscosity (:163-169), one division
-                    fvisc = -P.visc[ij] * (P.cs[ti] + P.cs[tj]) * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
-                  const double fpair = -mm * (d.y + qd.y + fvisc) * wfd;
+                  double fvisc = fast_div(u_vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
+                  fvisc = dvdr < 0.0 ? fvisc : 0.0;
+                  const double fpair = -u_mm * (d.y + qd.y + fvisc) * wfd;
                   fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
                   ade += -0.5 * fpair * dvdr;
                 } else {                                                      // Morris viscosity (morris :165-176)
-                  const double fvisc = 2.0 * P.visc[ij] / (rhoi * rhoj) * mm * wfd;
-                  const double fpair = -mm * (d.y + qd.y) * wfd;
+                  const double fvisc = fast_div(2.0 * UF.visc * u_mm * wfd, rhoi * rhoj);
+                  const double fpair = -u_mm * (d.y + qd.y) * wfd;
                   fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
                   ade += -0.5 * (fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz));
                 }
-                adrho += mj * dvdr * wfd;
+                adrho += UF.mass * dvdr * wfd;
               }
-            }
-            if (HAS_HEAT) {
-              const PairTab &P = S.T[I_HEAT];
-              if (rsq < P.cutsq[ij]) {
-                const double h = P.h[ij];
-                double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;
+              if (HAS_HEAT) {
+                const bool hit = (rsq < UH.cutsq) & ((maskh >> tj) & 1u);
+                double wfd = UH.h - r; wfd = UH.c0 * wfd * wfd;
+                wfd = hit ? wfd : 0.0;
                 const double ej = PEp[slot].x;
                 // 2 mi mj/(mi+mj) (rho_i+rho_j)/(rho_i rho_j) D (e_i - e_j) W'/r  (:122-125), one division
-                ade += 2.0 * mi * mj * (rhoi + rhoj) * P.visc[ij] * (ei - ej) * wfd / ((mi + mj) * (rhoi * rhoj));
+                ade += fast_div(u_heat * (rhoi + rhoj) * (ei - ej) * wfd, rhoi * rhoj);
+              }
+            } else {
+              const int ij = ti * MAXT1 + tj;                                 // empty entries: cutsq[ti][0] = -1
+              bool any = false;
+#pragma unroll
+              for (int t = 0; t < NK; t++) any |= rsq < S.T[t].cutsq[ij];
+              if (!any) continue;
+              const double mj = S.T[0].mass[tj];
+              const double rinv = rsqrt(rsq), r = rsq * rinv;
+              if (HAS_FLUID) {
+                const PairTab &P = S.T[0];
+                if (rsq < P.cutsq[ij]) {
+                  const double2 qc = P2[slot], qd = P3[slot];
+                  const double h = P.h[ij];
+                  double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;
+                  const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
+                  const double dvdr = dx * dvx + dy * dvy + dz * dvz;
+                  const double mm = mi * mj;
+                  if (KINDS & K_TAIT) {
+                    double fvisc = 0.0;
+                    if (dvdr < 0.0)
+                      fvisc = -P.visc[ij] * (P.cs[ti] + P.cs[tj]) * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+                    const double fpair = -mm * (d.y + qd.y + fvisc) * wfd;
+                    fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                    ade += -0.5 * fpair * dvdr;
+                  } else {
+                    const double fvisc = 2.0 * P.visc[ij] / (rhoi * rhoj) * mm * wfd;
+                    const double fpair = -mm * (d.y + qd.y) * wfd;
+                    fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
+                    ade += -0.5 * (fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz));
+                  }
+                  adrho += mj * dvdr * wfd;
+                }
+              }
+              if (HAS_HEAT) {
+                const PairTab &P = S.T[I_HEAT];
+                if (rsq < P.cutsq[ij]) {
+                  const double h = P.h[ij];
+                  double wfd = h - r; wfd = P.c0[ij] * wfd * wfd;
+                  const double ej = PEp[slot].x;
+                  ade += 2.0 * mi * mj * (rhoi + rhoj) * P.visc[ij] * (ei - ej) * wfd / ((mi + mj) * (rhoi * rhoj));
+                }
               }
             }
           }
