@@ -511,16 +511,15 @@ __device__ __forceinline__ bool tile_begin(const TileArgs &A, TileSmem<NPARTS, N
   return true;
 }
 
-// branch-free fp64 sqrt and division (MUFU seed + Newton steps, <= 1-2 ulp): the CUDA built-ins carry a slow-path branch
-// that splits the pair body into basic blocks and keeps ptxas from interleaving the 8 unrolled neighbors of a group
+// branch-free fp64 sqrt and division: MUFU seed (~2^-22), one coupled Newton step (~2^-43), one residual correction
+// (error ~ the square of that, i.e. below 1 ulp).  The CUDA built-ins carry a slow-path branch that splits the pair body
+// into basic blocks and keeps ptxas from interleaving the 8 unrolled neighbors of a group.
 __device__ __forceinline__ double fast_sqrt(double a)
 {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
   double g = a * y, hh = 0.5 * y;
-  double e = fma(-hh, g, 0.5);
-  g = fma(g, e, g); hh = fma(hh, e, hh);
-  e = fma(-hh, g, 0.5);
+  const double e = fma(-hh, g, 0.5);
   g = fma(g, e, g); hh = fma(hh, e, hh);
   return fma(fma(-g, g, a), hh, g);
 }
@@ -528,13 +527,15 @@ __device__ __forceinline__ double fast_div(double n, double d)
 {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  double q = n * y;
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  const double q = n * y;
   return fma(fma(-d, q, n), y, q);
 }
+// the cutoff tests of the stage kernels may contract to FMA: every kernel and its derivative vanish at the cutoff, so a
+// pair within an ulp of it contributes nothing either way (the neighbor *lists* are decided without FMA, see k_tile_build)
+__device__ __forceinline__ double rsq_fma(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
+__device__ __forceinline__ bool dpos(double a) { return (__double2hiint(a) | __double2loint(a)) != 0; }   // a > 0 for a >= 0, on the integer pipe
 
 // ---------------------------------------------------------------- density ---
 // PairSPHRhoSum::compute, pair_sph_rhosum.cpp:112-197 (full list; quadric kernel, per-type mass)
@@ -568,15 +569,18 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
       for (int pass = 0; pass < 1 + scan_far; pass++) {
         const uint4 *lp = (pass ? A.far : A.near) + rbase;
         const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        uint4 En = make_uint4(0, 0, 0, 0);
+        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
         for (int gi = sub; gi < ng; gi += SPLIT) {
-          const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
+          const uint4 E = En;
+          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (size_t)(gi + SPLIT) * 32);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
             const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS;
             const double2 qa = P0[slot], qb = P1[slot];
-            const double rsq = rsq_nofma(a.x - qa.x, a.y - qa.y, b.x - qb.x);
+            const double rsq = rsq_fma(a.x - qa.x, a.y - qa.y, b.x - qb.x);
             if (UNI) {
               const bool hit = (rsq < U.cutsq) & ((rowmask >> tj) & 1u);
               double wf = fma(-rsq, U.c1, 1.0);                   // 1 - r^2/h^2
@@ -625,8 +629,9 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double2 *P0 = S.part, *P1 = P0 + A.cap, *P2 = P1 + A.cap, *P3 = P2 + A.cap, *PEp = S.part + (size_t)PE * A.cap;
   const TileUni &UF = A.uni[0], &UH = A.uni[I_HEAT];
   // register constants of the uniform body
-  const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_mm = UF.mass * UF.mass;
-  const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) : 0.0;
+  const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h;
+  const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
+  const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
   unsigned phase = 0;
   while (tile_begin<NPARTS, NK, NT>(A, S, ntiles)) {
@@ -647,11 +652,15 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       const unsigned maskf = (unsigned)(UF.mapmask >> (ti * 8)) & 0xffu, maskh = (unsigned)(UH.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
+      double u_drho = 0, u_de = 0, u_deh = 0;                                 // uniform body: raw sums, scaled after the loop
       for (int pass = 0; pass < 1 + scan_far; pass++) {
         const uint4 *lp = (pass ? A.far : A.near) + rbase;
         const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        uint4 En = make_uint4(0, 0, 0, 0);
+        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
         for (int gi = sub; gi < ng; gi += SPLIT) {
-          const uint4 E = ldg_nc_u4(lp + (size_t)gi * 32);
+          const uint4 E = En;
+          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (size_t)(gi + SPLIT) * 32);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -659,40 +668,41 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
             const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS;
             const double2 qa = P0[slot], qb = P1[slot];
             const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
-            const double rsq = rsq_nofma(dx, dy, dz);
             const double rhoj = qb.y;
             if (UNI) {
-              const double r = fast_sqrt(fmax(rsq, 1.0e-300));
+              const double rsq = rsq_fma(dx, dy, dz);
+              const double r = fast_sqrt(rsq);                                // NaN for coincident particles: masked by dpos()
               if (HAS_FLUID) {
-                const bool hit = (rsq < UF.cutsq) & ((maskf >> tj) & 1u);
+                const bool hit = (rsq < UF.cutsq) & ((maskf >> tj) & 1u) & dpos(rsq);
                 const double2 qc = P2[slot], qd = P3[slot];
-                double wfd = UF.h - r; wfd = UF.c0 * wfd * wfd;             // Lucy (dW/dr)/r  (:135-151)
+                double wfd = UF.h - r; wfd = wfd * wfd;                       // Lucy (dW/dr)/r = c0 (h - r)^2  (:135-151), c0 folded into the constants
                 wfd = hit ? wfd : 0.0;
                 const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
                 const double dvdr = dx * dvx + dy * dvy + dz * dvz;
                 if (KINDS & K_TAIT) {
                   double fvisc = fast_div(u_vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
                   fvisc = dvdr < 0.0 ? fvisc : 0.0;
-                  const double fpair = -u_mm * (d.y + qd.y + fvisc) * wfd;
+                  const double fpair = u_k1 * (d.y + qd.y + fvisc) * wfd;     // -m m c0 (...) (h - r)^2
                   fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                  ade += -0.5 * fpair * dvdr;
+                  u_de += fpair * dvdr;                                       // x -0.5 at the end
                 } else {                                                      // Morris viscosity (morris :165-176)
-                  const double fvisc = fast_div(2.0 * UF.visc * u_mm * wfd, rhoi * rhoj);
-                  const double fpair = -u_mm * (d.y + qd.y) * wfd;
+                  const double fvisc = fast_div(u_k2 * wfd, rhoi * rhoj);     // 2 mu m m c0 (h - r)^2 / (rho_i rho_j)
+                  const double fpair = u_k1 * (d.y + qd.y) * wfd;
                   fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
-                  ade += -0.5 * (fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz));
+                  u_de += fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz);
                 }
-                adrho += UF.mass * dvdr * wfd;
+                u_drho += dvdr * wfd;                                         // x m c0 at the end
               }
               if (HAS_HEAT) {
-                const bool hit = (rsq < UH.cutsq) & ((maskh >> tj) & 1u);
-                double wfd = UH.h - r; wfd = UH.c0 * wfd * wfd;
+                const bool hit = (rsq < UH.cutsq) & ((maskh >> tj) & 1u) & dpos(rsq);
+                double wfd = UH.h - r; wfd = wfd * wfd;
                 wfd = hit ? wfd : 0.0;
                 const double ej = PEp[slot].x;
                 // 2 mi mj/(mi+mj) (rho_i+rho_j)/(rho_i rho_j) D (e_i - e_j) W'/r  (:122-125), one division
-                ade += fast_div(u_heat * (rhoi + rhoj) * (ei - ej) * wfd, rhoi * rhoj);
+                u_deh += fast_div((rhoi + rhoj) * (ei - ej) * wfd, rhoi * rhoj);
               }
             } else {
+              const double rsq = rsq_fma(dx, dy, dz);
               const int ij = ti * MAXT1 + tj;                                 // empty entries: cutsq[ti][0] = -1
               bool any = false;
 #pragma unroll
@@ -738,6 +748,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
           }
         }
       }
+      if (UNI) { adrho = u_k3 * u_drho; ade = -0.5 * u_de + u_heat * u_deh; }
 #pragma unroll
       for (int o = LPW; o < 32; o <<= 1) {
         fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
