@@ -141,16 +141,18 @@ struct RowWriter {
 // that stick out beyond ceil(n / 8) groups into the holes of the shorter classes (~10 % of a row, the only possible conflicts)
 // and zeroes what stays empty.  (profiles/r01_tile_*: in natural order conflicts were 54 % of k_tile_force's smem wavefronts.)
 struct NearWriter {
-  unsigned long long cnt; int n;          // 8 x 8-bit class counters
-  __device__ __forceinline__ NearWriter() : cnt(0), n(0) {}
-  __device__ __forceinline__ int count(int c) const { return (int)(cnt >> (8 * c)) & 0xff; }
-  __device__ __forceinline__ static int pos_of(int c, int k, int q) { return 8 * k + ((c - q) & 7); }
+  unsigned clo, chi; int n;               // 8 x 8-bit class counters (classes 0-3 | 4-7)
+  __device__ __forceinline__ NearWriter() : clo(0), chi(0), n(0) {}
+  __device__ __forceinline__ int count(int c) const { return (int)(((c & 4) ? chi : clo) >> ((c & 3) * 8)) & 0xff; }
+  __device__ __forceinline__ static int off_of(int c, int k, int q) { int pos = 8 * k + ((c - q) & 7); return (pos >> 3) * 256 + (pos & 7); }
   __device__ __forceinline__ void push(unsigned ent, int q, unsigned short *base, int stride)
   {
-    const int c = ent & 7, k = count(c);
-    if (k < 255) cnt += 1ull << (8 * c);
-    const int pos = pos_of(c, k, q);
-    if (pos < stride) base[(size_t)(pos >> 3) * 256 + (pos & 7)] = (unsigned short)ent;
+    const int c = ent & 7, sh = (c & 3) * 8;
+    const bool hi = (c & 4) != 0;
+    const int k = (int)((hi ? chi : clo) >> sh) & 0xff;
+    const unsigned inc = k < 255 ? 1u << sh : 0u;
+    clo += hi ? 0u : inc; chi += hi ? inc : 0u;
+    if (8 * k + 8 <= stride) base[off_of(c, k, q)] = (unsigned short)ent;
     n++;
   }
   // returns the extent the row needed (in entries); the row is valid iff that is <= stride
@@ -166,14 +168,12 @@ struct NearWriter {
     for (int c = 0; c < 8; c++)
       for (int k = D; k < count(c); k++) {
         while (kh >= D) { ch++; kh = count(ch); }
-        const int src = pos_of(c, k, q), dst = pos_of(ch, kh, q);
-        base[(size_t)(dst >> 3) * 256 + (dst & 7)] = base[(size_t)(src >> 3) * 256 + (src & 7)];
+        base[off_of(ch, kh, q)] = base[off_of(c, k, q)];
         kh++;
       }
     for (;;) {
       while (kh >= D) { if (++ch == 8) return 8 * mx; kh = count(ch); }
-      const int dst = pos_of(ch, kh, q);
-      base[(size_t)(dst >> 3) * 256 + (dst & 7)] = 0;
+      base[off_of(ch, kh, q)] = 0;
       kh++;
     }
   }
@@ -283,55 +283,57 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
         const int q = (row - D.row0) & 7, stride = A.ngrp * 8;
 
         auto interval = [&](int s0, int s1) {      // candidates in slots [s0, s1)
-          for (int b0 = s0 & ~3; b0 < s1; b0 += 32) {
-            unsigned ns = 0, nm = 0, as = 0, am = 0;     // near sure / near maybe / all sure / all maybe
+          for (int bj = s0 & ~3; bj < s1; bj += 32) {
+            // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
+            // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
+            unsigned in = 0, mb = 0, fr = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              const float4 X = *(const float4 *)(fx + b0 + 4 * k), Y = *(const float4 *)(fy + b0 + 4 * k), Z = *(const float4 *)(fz + b0 + 4 * k);
+              const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
               const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
               for (int c = 0; c < 4; c++) {
                 const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
                 const float rsq = dx * dx + dy * dy + dz * dz;
                 const unsigned bit = 1u << (4 * k + c);
-                if (UNI) { ns |= rsq < far_lo ? bit : 0u; nm |= rsq < far_hi ? bit : 0u; }
-                as |= rsq < cut_lo ? bit : 0u; am |= rsq < cut_hi ? bit : 0u;
+                in |= rsq < cut_lo ? bit : 0u; mb |= rsq < cut_hi ? bit : 0u;
+                if (UNI) fr |= rsq >= far_hi ? bit : 0u;
               }
-              if (b0 + 4 * k + 4 >= s1) break;
+              if (bj + 4 * k + 4 >= s1) break;
             }
             // only the slots of [s0, s1), and never the row particle itself
-            unsigned vm = (s1 - b0 >= 32) ? 0xffffffffu : ((1u << (s1 - b0)) - 1u);
-            if (b0 < s0) vm &= ~((1u << (s0 - b0)) - 1u);
-            if (myslot >= b0 && myslot < b0 + 32) vm &= ~(1u << (myslot - b0));
+            unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
+            if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
+            if (myslot >= bj && myslot < bj + 32) vm &= ~(1u << (myslot - bj));
             if (!valid) vm = 0;
-            ns &= vm; nm &= vm; as &= vm; am &= vm;
-            unsigned nearm, farm, border;
-            if (UNI) { nearm = as & ns; farm = as & ~nm; border = (as & (nm ^ ns)) | (am ^ as); }
-            else { nearm = 0; farm = 0; border = am; }            // per-type thresholds: classify every coarse hit below
+            in &= vm; mb &= vm;
+            unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
+            if (!UNI) in = 0;
             while (border) {
               const int idx = __ffs((int)border) - 1; border &= border - 1;
-              const int slot = b0 + idx;
+              const int slot = bj + idx;
               int cls = -1;
               if (!UNI) {
                 const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
                 const float rsq = dx * dx + dy * dy + dz * dz;
                 const float *th = s_thr[ti * MAXT1 + ty[slot]];
-                if (rsq >= th[3]) cls = 0;                       // surely outside the neighbor cutoff
-                else if (rsq < th[2]) {                          // surely inside: near or far row?
-                  if (rsq < th[0]) cls = 1; else if (rsq >= th[1]) cls = 2;
-                }
+                if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
+                else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : 1;    // surely inside: far row only if surely beyond the far threshold
               }
               if (cls < 0) cls = tile_exact_class(A, row, tile_slot_src(D, slot, A.nlocal, A.gorder));
-              if (cls == 1) nearm |= 1u << idx; else if (cls == 2) farm |= 1u << idx;
+              if (cls) in |= 1u << idx;
+              if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
             }
+            // phase B: entries straight from the masks
+            unsigned nearm = in & ~fr, farm = in & fr;
             while (nearm) {
               const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
-              const int slot = b0 + idx;
+              const int slot = bj + idx;
               wn.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, q, nrow16, stride);
             }
             while (farm) {
               const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
-              const int slot = b0 + idx;
+              const int slot = bj + idx;
               wf.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, frow, A.ngrp);
             }
           }
