@@ -32,6 +32,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "particle-steps/sec (SPH rho+force+heat loop)"
 UNIT = "particle-steps/s"
