@@ -133,11 +133,13 @@ struct b200_sph {
   DevBuf<double> d_prunesq, d_farsq; double far_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
+  int h_tflags2[4] = {0, 0, 0, 0};
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
-  DevBuf<TileDesc> tiles; DevBuf<double2> trec;
-  int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter
+  DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
+  int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
+  int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter; [8..11] the same for the ghost-row tiles
   bool setup_done = false, geom_ready = false;
   // instrumentation
   long long launches = 0, nbuilds = 0, nsteps = 0, maxneigh = 0, ndanger = 0, ninserted = 0;
@@ -432,8 +434,10 @@ static int comm_exchange(b200_sph *h, int nslots)
 
 // ------------------------------------------------------------- tile path ----
 // persistent launch of a tile kernel: as many CTAs as fit on the device (or tiles), dynamic shared memory opted in once per kernel
-template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args)
+template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args, int ntiles = -1)
 {
+  if (ntiles < 0) ntiles = h->ntiles;
+  if (!ntiles) return;
   static std::vector<std::pair<const void *, size_t>> opted;     // kernel -> dynamic shared memory it may use
   const void *fp = (const void *)kern;
   size_t maxdyn = 0;
@@ -448,7 +452,7 @@ template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const 
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp, nthreads, smem));
   if (occ < 1) throw std::string(name) + ": zero occupancy";
-  int grid = std::max(1, std::min(h->ntiles, h->nsm * occ));
+  int grid = std::max(1, std::min(ntiles, h->nsm * occ));
   CK(cudaMemsetAsync(h->d_tflags + 4, 0, sizeof(int), h->st));
   kern<<<grid, nthreads, smem, h->st>>>(args);
   post_launch(h, name);
@@ -458,20 +462,29 @@ template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const 
 static bool tile_rows(b200_sph *h)
 {
   Geom &g = h->g;
-  int nl = h->nlocal;
-  h->ntiles = 0;
+  int nl = h->nlocal, na = h->nall();
+  const bool mp = h->multiphase != 0;
+  h->ntiles = h->ngtiles = 0;
   if (!nl) return true;
   h->tiles.ensure((size_t)g.ncells + 1);
-  CK(cudaMemsetAsync(h->d_tflags, 0, 8 * sizeof(int), h->st));
-  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
+  CK(cudaMemsetAsync(h->d_tflags, 0, 16 * sizeof(int), h->st));
+  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
   LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2], 128), 128, P);
+  if (mp && h->nghost) {       // ghost rows: what the reference accumulates on ghost atoms (then reverse-communicates)
+    h->gtiles.ensure((size_t)g.ncells + 1);
+    TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
+    LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2], 128), 128, G);
+  }
   CK(cudaMemcpyAsync(h->h_flags + 10, h->d_tflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_tflags2, h->d_tflags + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  if (h->h_flags[12]) return false;
-  h->ntiles = h->h_flags[10];
-  h->tile_cap = std::max(2, (h->h_flags[11] + 1) & ~1);
+  if (h->h_flags[12] || h->h_tflags2[2]) return false;
+  h->ntiles = h->h_flags[10]; h->ngtiles = h->h_tflags2[0];
+  h->tile_cap = std::max(2, (std::max(h->h_flags[11], h->h_tflags2[1]) + 1) & ~1);
+  const int nrows = mp ? na : nl;
+  if (mp) h->rowtile.ensure(nl + 1);
   for (int attempt = 0; attempt < 8; attempt++) {
-    size_t rows32 = (size_t)(nl + 31) / 32 * 32;
+    size_t rows32 = (size_t)(nrows + 31) / 32 * 32;
     int ngrp = h->stride / 8;
     h->nbr.ensure(rows32 * ngrp * 4); h->far.ensure(rows32 * ngrp * 4);
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
@@ -481,13 +494,22 @@ static bool tile_rows(b200_sph *h)
     B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p;
     B.tiles = h->tiles.p; B.ntiles = h->d_tflags; B.counter = h->d_tflags + 4;
     B.near = (uint4 *)h->nbr.p; B.far = (uint4 *)h->far.p; B.numneigh = h->numneigh.p; B.numfar = h->numfar.p; B.maxcount = h->d_flags;
+    B.orig = h->C().orig.p; B.rowtile = mp ? h->rowtile.p : nullptr;
     // one cutoff for every type pair (the common deck) -> scalar thresholds in the fp32 phase
     B.uni = 1; B.cutsq_u = h->h_cutneighsq[1 * MAXT1 + 1]; B.farsq_u = h->h_farsq[1 * MAXT1 + 1];
     for (int i = 1; i <= h->ntypes; i++) for (int j = 1; j <= h->ntypes; j++)
       if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u) B.uni = 0;
-    size_t bsm = (size_t)13 * (((h->tile_cap + 3) & ~3) + 4);
-    if (B.uni) launch_tiles(h, k_tile_build<true>, "k_tile_build", TILE_BUILD_NT, bsm, B);
-    else launch_tiles(h, k_tile_build<false>, "k_tile_build", TILE_BUILD_NT, bsm, B);
+    size_t bsm = (size_t)(mp ? 17 : 13) * (((h->tile_cap + 3) & ~3) + 4);
+    for (int set = 0; set < (mp ? 2 : 1); set++) {
+      if (set) { B.tiles = h->gtiles.p; B.ntiles = h->d_tflags + 8; }
+      int nt = set ? h->ngtiles : h->ntiles;
+      const bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
+#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
+                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm, B, nt); } while (0)
+      if (mp) { if (B.uni) BUILD_LAUNCH(true, true); else BUILD_LAUNCH(false, true); }
+      else { if (B.uni) BUILD_LAUNCH(true, false); else BUILD_LAUNCH(false, false); }
+#undef BUILD_LAUNCH
+    }
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     int mx = h->h_flags[0];
@@ -636,18 +658,27 @@ static void build_plan(b200_sph *h)
     }
     h->plan.push_back(p);
   }
-  // tile path (b200_tile.cuh): decks made of single-phase sub-styles only
-  bool ok = !h->multiphase && h->pcs.empty() && h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
+  // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
+  bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
+  if (h->multiphase && (getenv("B200_NO_TILE_MP") || !h->pcs.empty())) ok = false;
   int np = 2, nk = 1;
+  const int SP = K_TAIT | K_MORRIS | K_HEAT, MPK = K_TAITMP | K_SURF | K_HEATMP | K_HEATPC;
   for (const Pass &p : h->plan) {
-    if (p.type == 0) continue;
-    if (p.type != 3 || (p.kinds & ~(K_TAIT | K_MORRIS | K_HEAT))) { ok = false; break; }
-    bool fluid = (p.kinds & (K_TAIT | K_MORRIS)) != 0, heat = (p.kinds & K_HEAT) != 0;
-    np = std::max(np, fluid ? (heat ? 5 : 4) : 3); nk = std::max(nk, (fluid ? 1 : 0) + (heat ? 1 : 0));
+    if (p.type == 0) { if (h->multiphase) ok = false; continue; }
+    if (p.type == 1 || p.type == 2) { if (!h->multiphase) ok = false; continue; }
+    if (p.type != 3) { ok = false; break; }
+    if (!h->multiphase && !(p.kinds & ~SP)) {
+      bool fluid = (p.kinds & (K_TAIT | K_MORRIS)) != 0, heat = (p.kinds & K_HEAT) != 0;
+      np = std::max(np, fluid ? (heat ? 5 : 4) : 3); nk = std::max(nk, (fluid ? 1 : 0) + (heat ? 1 : 0));
+    } else if (h->multiphase && !(p.kinds & ~MPK)) {
+      int mask = 0x03 | ((p.kinds & K_TAITMP) ? 0x1c : 0) | ((p.kinds & K_SURF) ? 0x70 : 0) | ((p.kinds & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
+      np = std::max(np, __builtin_popcount(mask));
+      nk = std::max(nk, ((p.kinds & K_TAITMP) ? 1 : 0) + ((p.kinds & K_SURF) ? 1 : 0) + ((p.kinds & (K_HEATMP | K_HEATPC)) ? 1 : 0));
+    } else { ok = false; break; }
   }
   h->tile_on = ok; h->tile_nparts = np; h->tile_nk = nk;
   long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - (long long)sizeof(TileDesc) - 64;
-  h->tile_slotcap = (int)std::min<long long>(std::min<long long>(TILE_MAXSLOTS, capb / (16 * np)), TILE_MAXSLOTS) & ~1;
+  h->tile_slotcap = (int)std::min<long long>(std::min<long long>(h->multiphase ? TMP_MAXSLOTS : TILE_MAXSLOTS, capb / (16 * np)), TILE_MAXSLOTS) & ~1;
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
   if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
 }
@@ -679,6 +710,7 @@ static TileArgs tile_args(b200_sph *h, int pstride)
   A.rec = h->trec.p; A.near = (const uint4 *)h->nbr.p; A.far = (const uint4 *)h->far.p; A.numneigh = h->numneigh.p; A.numfar = h->numfar.p;
   A.scan_far = h->d_scan_far; A.tiles = h->tiles.p; A.ntiles = h->d_tflags; A.counter = h->d_tflags + 4;
   A.xt = c.xt.p; A.vr_out = c.vr.p; A.fd = c.fd.p; A.de = c.de.p;
+  A.vm = c.vm.p; A.cg_out = c.cgm.p; A.gorder = h->gorder.p; A.dim = h->g.dim;
   return A;
 }
 static int tile_records(b200_sph *h, int nparts, int force, int epart, const PairTab *fluid)
@@ -726,9 +758,107 @@ template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &
     else launch_tiles(h, k_tile_force<KINDS, 2, false>, "k_tile_force", TILE_ROWS * 2, smem, A);
   }
 }
+static int tile_records_mp(b200_sph *h, int mode, const PairTab *fluid)
+{
+  int na = h->nall(), pstride = (na + 7) & ~7;
+  h->trec.ensure((size_t)pstride * (mode ? 8 : 2));
+  OwnedSet &c = h->C();
+  TileRecMpArgs R{h->nlocal, na, pstride, mode, h->gorder.p, c.xt.p, c.vr.p, c.cgm.p, c.e.p, c.cv.p, fluid, h->trec.p};
+  LAUNCH(h, k_tile_records_mp, nblk(na, 256), 256, R);
+  return pstride;
+}
+// cutoff / kernel constants of a sub-style that are the same for all its mapped type pairs (viscosity, alpha, D may still differ)
+static bool tile_uni_geo(const b200_sph *h, const PairTab &T, TileUni &U)
+{
+  memset(&U, 0, sizeof U);
+  bool first = true, ok = true;
+  for (int i = 1; i <= h->ntypes; i++)
+    for (int j = 1; j <= h->ntypes; j++) {
+      int k = i * MAXT1 + j;
+      if (T.cutsq[k] < 0.0) continue;
+      U.mapmask |= 1ull << k;
+      if (first) { U.cutsq = T.cutsq[k]; U.h = T.h[k]; U.c0 = T.c0[k]; U.c1 = T.c1[k]; first = false; }
+      else if (U.cutsq != T.cutsq[k] || U.h != T.h[k] || U.c0 != T.c0[k] || U.c1 != T.c1[k]) ok = false;
+    }
+  return ok && !first;
+}
+template <int KINDS> static void launch_tile_force_mp(b200_sph *h, TileArgs &A, bool gu)
+{
+  using MP = MpParts<KINDS>;
+  size_t smem = TileSmem<MP::n, MP::nk>::bytes(h->tile_cap);
+  const bool d3 = h->g.dim == 3 || !(KINDS & K_SURF);
+  for (int set = 0; set < 2; set++) {          // owned rows, then the ghost rows
+    int nt = set ? h->ngtiles : h->ntiles;
+    if (set) { A.tiles = h->gtiles.p; A.ntiles = h->d_tflags + 8; }
+    if (d3) {
+      if (gu) launch_tiles(h, k_tile_force_mp<KINDS, true, true>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
+      else launch_tiles(h, k_tile_force_mp<KINDS, true, false>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
+    } else {
+      if (gu) launch_tiles(h, k_tile_force_mp<KINDS, false, true>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
+      else launch_tiles(h, k_tile_force_mp<KINDS, false, false>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
+    }
+  }
+}
+static void run_pass_tile_mp(b200_sph *h, const Pass &p)
+{
+  if (p.type == 1 || p.type == 2) {
+    const PairTab &T = h->h_tab[p.slots[0]];
+    bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;
+    if (!active) return;
+    h->tbegin(p.type == 1 ? T_DENSITY : T_COLORGRAD);
+    int pstride = p.type == 1 ? tile_records(h, 2, 0, -1, nullptr) : tile_records_mp(h, 0, nullptr);
+    TileArgs A = tile_args(h, pstride);
+    A.tab[0] = h->d_tab[p.slots[0]];
+    const bool gu = tile_uni_geo(h, T, A.uni[0]) && !h->tile_nouni;
+    size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
+    if (p.type == 1) {
+      if (gu) launch_tiles(h, k_tile_full_mp<0, true>, "k_tile_rhosum_mp", TILE_MP_NT, smem, A);
+      else launch_tiles(h, k_tile_full_mp<0, false>, "k_tile_rhosum_mp", TILE_MP_NT, smem, A);
+    } else {
+      if (gu) launch_tiles(h, k_tile_full_mp<1, true>, "k_tile_colorgradient", TILE_MP_NT, smem, A);
+      else launch_tiles(h, k_tile_full_mp<1, false>, "k_tile_colorgradient", TILE_MP_NT, smem, A);
+    }
+    h->tend();
+    return;
+  }
+  // force pass: canonical table order fluid, surf, heat
+  int nk = 0; const PairTab *fluid = nullptr;
+  TileArgs A = tile_args(h, 0);
+  const int wants[3] = {K_TAITMP, K_SURF, K_HEATMP | K_HEATPC};
+  bool gu = !h->tile_nouni;
+  for (int want : wants)
+    for (int s = 0; s < p.nslots; s++)
+      if (kind_of(h->h_tab[p.slots[s]].style) & want) {
+        gu = tile_uni_geo(h, h->h_tab[p.slots[s]], A.uni[nk]) && gu;
+        if (nk && A.uni[nk].c1 != A.uni[0].c1) gu = false;      // one kernel-derivative evaluation serves all sub-styles only if they share h
+        A.tab[nk++] = h->d_tab[p.slots[s]]; if (want & K_TAITMP) fluid = h->d_tab[p.slots[s]];
+      }
+  h->tbegin(T_DERIVE);
+  A.pstride = tile_records_mp(h, 1, fluid);
+  A.rec = h->trec.p;
+  h->tend();
+  h->tbegin(T_FORCE);
+  switch (p.kinds) {
+  case K_TAITMP: launch_tile_force_mp<K_TAITMP>(h, A, gu); break;
+  case K_SURF: launch_tile_force_mp<K_SURF>(h, A, gu); break;
+  case K_HEATMP: launch_tile_force_mp<K_HEATMP>(h, A, gu); break;
+  case K_HEATPC: launch_tile_force_mp<K_HEATPC>(h, A, gu); break;
+  case K_TAITMP | K_SURF: launch_tile_force_mp<K_TAITMP | K_SURF>(h, A, gu); break;
+  case K_TAITMP | K_SURF | K_HEATMP: launch_tile_force_mp<K_TAITMP | K_SURF | K_HEATMP>(h, A, gu); break;
+  case K_TAITMP | K_SURF | K_HEATPC: launch_tile_force_mp<K_TAITMP | K_SURF | K_HEATPC>(h, A, gu); break;
+  case K_TAITMP | K_HEATMP: launch_tile_force_mp<K_TAITMP | K_HEATMP>(h, A, gu); break;
+  case K_TAITMP | K_HEATPC: launch_tile_force_mp<K_TAITMP | K_HEATPC>(h, A, gu); break;
+  case K_SURF | K_HEATMP: launch_tile_force_mp<K_SURF | K_HEATMP>(h, A, gu); break;
+  case K_SURF | K_HEATPC: launch_tile_force_mp<K_SURF | K_HEATPC>(h, A, gu); break;
+  default: throw std::string("b200: no tile force kernel for this multiphase sub-style group");
+  }
+  h->tend();
+}
+
 static void run_pass_tile(b200_sph *h, const Pass &p)
 {
   const int B = 256;
+  if (h->multiphase) { run_pass_tile_mp(h, p); return; }
   if (p.type == 0) {
     const PairTab &T = h->h_tab[p.slots[0]];
     bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
@@ -868,7 +998,7 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
 {
   const int B = 256;
   h->tbegin(T_FINAL);
-  if (rev && (h->nghost || h->world > 1) && !h->tile_on)      // the tile path puts nothing on ghosts (b200_tile.cuh)
+  if (rev && (h->nghost || h->world > 1) && (!h->tile_on || h->multiphase))      // the single-phase tile path puts nothing on ghosts (b200_tile.cuh)
     comm_reverse_generic(h, NB_REVERSE,
       [&](Swap &s) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), h->sendbuf.p); },
       [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
@@ -1094,7 +1224,7 @@ int b200_create(b200_sph **out, int device)
   CK(cudaMemset(h->d_flags, 0, 16 * sizeof(int)));
   CK(cudaMalloc(&h->d_dmaxsq, sizeof(unsigned long long))); CK(cudaMemset(h->d_dmaxsq, 0, sizeof(unsigned long long)));
   h->d_scan_far = h->d_flags + 8;
-  CK(cudaMalloc(&h->d_tflags, 8 * sizeof(int))); CK(cudaMemset(h->d_tflags, 0, 8 * sizeof(int)));
+  CK(cudaMalloc(&h->d_tflags, 16 * sizeof(int))); CK(cudaMemset(h->d_tflags, 0, 16 * sizeof(int)));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   h->nsm = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
@@ -1119,7 +1249,7 @@ int b200_destroy(b200_sph *h)
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
-  h->tiles.release(); h->trec.release(); cudaFree(h->d_tflags);
+  h->tiles.release(); h->gtiles.release(); h->rowtile.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
   return 0;
 }
@@ -1395,7 +1525,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
     CK(cudaMemcpy(img.data(), h->gimage.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
     int width = 2 * h->stride;
     DevBuf<int> out; out.ensure((size_t)n * width);
-    TileExportArgs X{n, h->stride / 8, width, h->gorder.p, h->tiles.p, h->d_tflags, (const uint4 *)h->nbr.p, (const uint4 *)h->far.p, h->numneigh.p, h->numfar.p, out.p};
+    TileExportArgs X{n, h->stride / 8, width, h->multiphase ? (int)TMP_SLOT_MASK : (int)TILE_SLOT_MASK, h->gorder.p, h->tiles.p, h->d_tflags, (const uint4 *)h->nbr.p, (const uint4 *)h->far.p, h->numneigh.p, h->numfar.p, out.p};
     LAUNCH(h, k_tile_export, std::max(1, std::min(h->ntiles, 1024)), 128, X);
     std::vector<int> rows((size_t)n * width);
     CK(cudaStreamSynchronize(h->st));

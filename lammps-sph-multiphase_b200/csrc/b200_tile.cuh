@@ -35,13 +35,19 @@
 #define TILE_SLOT_BITS 13
 #define TILE_SLOT_MASK 0x1fffu
 #define TILE_MAXSLOTS 8190
-#define TILE_BUILD_NT 256
 #define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
+// multiphase entries carry two more flags (their records are 64-128 B, so a tile never holds more than 2047 slots):
+//   [15:13] type of j | [12] the row particle is the reference's "i" of the pair (half-list owner, frozen at build time)
+//   | [11] j is a ghost | [10:0] slot
+#define TMP_OWNER 0x1000u
+#define TMP_GHOST 0x0800u
+#define TMP_SLOT_MASK 0x07ffu
+#define TMP_MAXSLOTS 2046
 
 struct TileDesc {
   int row0, nrows;               // owned rows [row0, row0 + nrows)
   int c0, ncell;                 // its cells: linear ids c0 .. c0+ncell-1 (one x-row of the engine grid)
-  int nrange, nslots, center, pad;
+  int nrange, nslots, center, ghost;   // ghost: the rows are ghost particles (tile-order indices >= nlocal), candidates owned only
   int rcell[TILE_MAXRANGE];      // range r = one (dy,dz) x-row of candidate cells: first cell (linear id) ...
   int rncell[TILE_MAXRANGE];     // ... number of cells ...
   int rdx[TILE_MAXRANGE];        // ... and x index of its first cell minus x index of c0 (-1 or 0)
@@ -51,13 +57,13 @@ struct TileDesc {
 
 // ------------------------------------------------------------------ plan ----
 struct TilePlanArgs {
-  Geom g; int nlocal, rowcap, slotcap;
+  Geom g; int nlocal, rowcap, slotcap, ghostrows, shrink;   // ghostrows: plan the tiles of the ghost rows (multiphase styles); shrink: see k_tile_plan
   const int *cso, *csg;
   TileDesc *tiles;
   int *flags;                    // [0] ntiles  [1] max slots  [2] a single cell does not fit  [3] max rows
 };
 
-__device__ __forceinline__ int tile_fill(const Geom &g, int nlocal, const int *cso, const int *csg, int cy, int cz, int x0, int x1, TileDesc *d)
+__device__ __forceinline__ int tile_fill(const Geom &g, int nlocal, const int *cso, const int *csg, int cy, int cz, int x0, int x1, TileDesc *d, int ghostrows = 0)
 {
   int xa = imax(x0 - 1, 0), xb = imin(x1 + 1, g.nc[0] - 1);
   int nr = 0, slots = 0;
@@ -66,7 +72,7 @@ __device__ __forceinline__ int tile_fill(const Geom &g, int nlocal, const int *c
     for (int dy = -1; dy <= 1; dy++) {
       int ny = cy + dy; if (ny < 0 || ny >= g.nc[1]) continue;
       int base = (nz * g.nc[1] + ny) * g.nc[0], a = base + xa, b = base + xb;
-      int no = cso[b + 1] - cso[a], ng = csg[b + 1] - csg[a];
+      int no = cso[b + 1] - cso[a], ng = ghostrows ? 0 : csg[b + 1] - csg[a];
       if (d) {
         d->rcell[nr] = a; d->rncell[nr] = xb - xa + 1; d->rdx[nr] = xa - x0;
         d->seg_src[2 * nr] = cso[a]; d->seg_slot[2 * nr] = slots;
@@ -87,23 +93,28 @@ __global__ void k_tile_plan(TilePlanArgs A)
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= g.nc[1] * g.nc[2]) return;
   int cy = r % g.nc[1], cz = r / g.nc[1], base = r * g.nc[0];
+  const int *rows = A.ghostrows ? A.csg : A.cso;       // whose rows: owned particles, or the ghosts of the same cells
+  const int gr = A.ghostrows;
   int x0 = 0;
   while (x0 < g.nc[0]) {
-    if (A.cso[base + x0 + 1] == A.cso[base + x0]) { x0++; continue; }
+    if (rows[base + x0 + 1] == rows[base + x0]) { x0++; continue; }
     int x1 = x0;
-    int slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr);
+    int slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr, gr);
     while (x1 + 1 < g.nc[0]) {
-      if (A.cso[base + x1 + 2] - A.cso[base + x0] > A.rowcap) break;
-      int s2 = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1 + 1, nullptr);
+      if (rows[base + x1 + 2] - rows[base + x0] > A.rowcap) break;
+      int s2 = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1 + 1, nullptr, gr);
       if (s2 > A.slotcap) break;
       x1++; slots = s2;
     }
-    while (x1 > x0 && A.cso[base + x1 + 1] == A.cso[base + x1]) x1--;          // no trailing empty cells
+    if (A.shrink)      // (kernels with a run-time lane split) 512 threads serve 256 rows x 2 lanes or 128 rows x 4 lanes: a tile of 129..191 rows wastes more lanes than a shorter one
+      while (x1 > x0 && rows[base + x1 + 1] - rows[base + x0] > TILE_ROWS / 2 && rows[base + x1 + 1] - rows[base + x0] < 3 * TILE_ROWS / 4) x1--;
+    while (x1 > x0 && rows[base + x1 + 1] == rows[base + x1]) x1--;          // no trailing empty cells
+    slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr, gr);
     if (slots > A.slotcap) atomicExch(&A.flags[2], 1);
     int t = atomicAdd(&A.flags[0], 1);
     TileDesc *d = A.tiles + t;
-    d->row0 = A.cso[base + x0]; d->nrows = A.cso[base + x1 + 1] - A.cso[base + x0]; d->c0 = base + x0; d->ncell = x1 - x0 + 1; d->pad = 0;
-    slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, d);
+    d->row0 = (gr ? A.nlocal : 0) + rows[base + x0]; d->nrows = rows[base + x1 + 1] - rows[base + x0]; d->c0 = base + x0; d->ncell = x1 - x0 + 1; d->ghost = gr;
+    tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, d, gr);
     atomicMax(&A.flags[1], slots); atomicMax(&A.flags[3], d->nrows);
     x0 = x1 + 1;
   }
@@ -117,6 +128,7 @@ struct TileBuildArgs {
   const double *cutneighsq, *farsq;
   const TileDesc *tiles; const int *ntiles; int *counter;
   uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
+  const int *orig; int *rowtile;           // multiphase: LAMMPS local indices (half-list ownership); tile of every owned row (fix phase_change)
 };
 
 // 8 entries of a row are one uint4 (16 bits each: [15:13] type of j, [12:0] slot; 0 = empty); group g of row r sits at
@@ -209,29 +221,37 @@ __device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int 
 // One CTA per tile.  Candidate positions are staged as fp32 offsets from the tile's corner; every (row, candidate) pair is decided in
 // fp32 against thresholds widened by a proven error band (|rsq32 - rsq| <= 2^-23 (2 sqrt(3) r (2E + r) + 4 r^2), E = largest offset),
 // and only pairs inside the band -- a ~1e-5 fraction -- take the exact fp64 test, so the list is bit-for-bit the one the fp64 test gives.
-// Phase A: 32 candidates x 4 compares -> bit masks (broadcast float4 reads).  Phase B: entries straight from the masks.
-template <bool UNI>
-__global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_constant__ TileBuildArgs A)
+// Phase A: 32 candidates x 3 compares -> bit masks (broadcast float4 reads).  Phase B: entries straight from the masks.
+// MP (multiphase styles): entries also carry the half-list ownership of the pair (neigh_derive.cpp:83-145: local index order
+// among owned atoms, the "above/right" rule for a ghost) and a ghost flag; tiles of ghost rows list, for a ghost g, the owned
+// atoms whose half list holds (i,g) -- what the reference adds to ghost atoms and reverse-communicates.
+// NT: 256 threads for big tiles (C2: 8 chunks of 32 rows per tile), 128 when the tiles are small (more CTAs per SM to overlap the
+// per-tile barriers); the (cell, chunk) work items of a tile are handed to the warps through a shared counter.
+template <bool UNI, bool MP, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
+  constexpr int TILE_BUILD_NT = NT;
   extern __shared__ __align__(128) unsigned char tile_smem[];
   const int cap4 = ((A.cap + 3) & ~3) + 4;
   float *fx = (float *)tile_smem, *fy = fx + cap4, *fz = fy + cap4;
-  unsigned char *ty = (unsigned char *)(fz + cap4);
+  int *so = (int *)(fz + cap4);                                // MP: LAMMPS local index of the owned candidates
+  unsigned char *ty = (unsigned char *)(MP ? (void *)(so + cap4) : (void *)so);
   __shared__ TileDesc D;
-  __shared__ int s_tile;
+  __shared__ int s_tile, s_item;
   __shared__ unsigned s_emax;
   __shared__ float s_thr[MAXTT][4];                            // non-uniform cutoffs: far_lo, far_hi, cut_lo, cut_hi per type pair
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TILE_BUILD_NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31;
   const Geom &g = A.g;
   const int ntiles = *A.ntiles;
   for (;;) {
     __syncthreads();
-    if (tid == 0) { s_tile = atomicAdd(A.counter, 1); s_emax = 0; }
+    if (tid == 0) { s_tile = atomicAdd(A.counter, 1); s_emax = 0; s_item = 0; }
     __syncthreads();
     const int t = s_tile;
     if (t >= ntiles) break;
     for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += TILE_BUILD_NT) ((int *)&D)[k] = ((const int *)(A.tiles + t))[k];
     __syncthreads();
+    const bool gt = MP && D.ghost;
     // corner of the tile's candidate region (cell c0 shifted by one cell in every direction)
     const int cx0 = D.c0 % g.nc[0], cy0 = (D.c0 / g.nc[0]) % g.nc[1], cz0 = D.c0 / (g.nc[0] * g.nc[1]);
     const double ox = g.clo[0] + (cx0 - 1) / g.cinv[0], oy = g.clo[1] + (cy0 - 1) / g.cinv[1], oz = g.clo[2] + (cz0 - 1) / g.cinv[2];
@@ -244,14 +264,21 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
         double4 p = A.xt[src];
         float x = (float)(p.x - ox), y = (float)(p.y - oy), z = (float)(p.z - oz);
         fx[s0 + k] = x; fy[s0 + k] = y; fz[s0 + k] = z; ty[s0 + k] = (unsigned char)tw_type(__double_as_longlong(p.w));
+        if (MP) so[s0 + k] = (s & 1) ? 0 : A.orig[src];
         emax = fmaxf(emax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
       }
     }
+    if (gt)                                                    // ghost rows are not among the candidates: their offsets count too
+      for (int k = tid; k < D.nrows; k += TILE_BUILD_NT) {
+        double4 p = A.xt[A.nlocal + A.gorder[D.row0 + k - A.nlocal]];
+        emax = fmaxf(emax, fmaxf(fabsf((float)(p.x - ox)), fmaxf(fabsf((float)(p.y - oy)), fabsf((float)(p.z - oz)))));
+      }
 #pragma unroll
     for (int o = 16; o; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(FULLMASK, emax, o));
     if (lane == 0) atomicMax(&s_emax, __float_as_uint(emax));
     __syncthreads();
     const double E = (double)__uint_as_float(s_emax) * 1.0001;
+    const float ztol = (float)(E * 2.4e-7);                   // two fp32 roundings of an offset <= E, doubled
     // thresholds with the error band: a pair is "sure inside" below lo, "sure outside" at or above hi
     auto band = [&](double thr, float &lo, float &hi) {
       double r = sqrt(fmax(thr, 0.0));
@@ -266,23 +293,55 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
       __syncthreads();
     }
     // work items: (cell of the tile, chunk of 32 of its rows); item -> warp round robin
-    int item = 0;
+    const int *rowstart = gt ? A.csg : A.cso;
+    constexpr bool DYN = NT < 256;                               // big tiles: one chunk per warp and round, static is cheaper
+    int item = 0, mine = tid >> 5;
+    if (DYN) { if (lane == 0) mine = atomicAdd(&s_item, 1); mine = __shfl_sync(FULLMASK, mine, 0); }
     for (int ci = 0; ci < D.ncell; ci++) {
-      const int cr0 = A.cso[D.c0 + ci], cnr = A.cso[D.c0 + ci + 1] - cr0;
+      const int cr0 = (gt ? A.nlocal : 0) + rowstart[D.c0 + ci], cnr = rowstart[D.c0 + ci + 1] - rowstart[D.c0 + ci];
       for (int rb = 0; rb < cnr; rb += 32, item++) {
-        if (item % nwarp != warp) continue;
+        if (item != mine) continue;
         const bool valid = rb + lane < cnr;
-        const int row = cr0 + rb + lane;
-        const int myslot = valid ? D.seg_slot[2 * D.center] + (row - D.seg_src[2 * D.center]) : -1;
-        float xi = 1e30f, yi = 1e30f, zi = 1e30f; int ti = 0;
-        if (valid) { xi = fx[myslot]; yi = fy[myslot]; zi = fz[myslot]; ti = ty[myslot]; }
+        const int row = cr0 + rb + lane;                                      // tile-order index
+        const int dev = !valid ? 0 : (gt ? A.nlocal + A.gorder[row - A.nlocal] : row);   // device index
+        const int myslot = (valid && !gt) ? D.seg_slot[2 * D.center] + (row - D.seg_src[2 * D.center]) : -1;
+        float xi = 1e30f, yi = 1e30f, zi = 1e30f; int ti = 0, oi = 0;
+        double4 pI = make_double4(0, 0, 0, 0);
+        if (valid && (MP || gt)) pI = A.xt[dev];
+        if (valid) {
+          if (!gt) { xi = fx[myslot]; yi = fy[myslot]; zi = fz[myslot]; ti = ty[myslot]; if (MP) oi = so[myslot]; }
+          else { xi = (float)(pI.x - ox); yi = (float)(pI.y - oy); zi = (float)(pI.z - oz); ti = tw_type(__double_as_longlong(pI.w)); }
+        }
         const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
         uint4 *nrow = A.near + rbase, *frow = A.far + rbase;
         NearWriter wn; RowWriter wf;
         unsigned short *nrow16 = (unsigned short *)nrow;
         const int q = (row - D.row0) & 7, stride = A.ngrp * 8;
 
-        auto interval = [&](int s0, int s1) {      // candidates in slots [s0, s1)
+        // candidates in slots [s0, s1) of the segment that starts at slot slot0 / record src0 (jghost: a ghost segment)
+        auto interval = [&](int s0, int s1, int slot0, int src0, bool jghost) {
+          auto dev_of = [&](int slot) { int src = src0 + (slot - slot0); return jghost ? A.nlocal + A.gorder[src - A.nlocal] : src; };
+          // "is b above/right of a" (neigh_derive.cpp:121-134) from the staged fp32 offsets when z differs by more than their
+          // rounding error, else from the fp64 coordinates (ties in z, then y, then x must be exact)
+          auto above = [&](bool row_is_a, int slot) {
+            const float za = row_is_a ? zi : fz[slot], zb = row_is_a ? fz[slot] : zi;
+            if (zb > za + ztol) return true;
+            if (zb < za - ztol) return false;
+            const double4 pj = A.xt[dev_of(slot)];
+            return row_is_a ? ghost_above(pI.x, pI.y, pI.z, pj.x, pj.y, pj.z) : ghost_above(pj.x, pj.y, pj.z, pI.x, pI.y, pI.z);
+          };
+          // multiphase: ownership / ghost flags of an entry; false = the pair does not belong in this row
+          auto flags = [&](int slot, unsigned &ent) {
+            if (!MP) return true;
+            if (gt) {                                           // (owned j, ghost row i): kept by j's half list iff i is above/right of j
+              if (!above(false, slot)) return false;
+              ent |= TMP_OWNER;
+            } else if (jghost) {
+              if (above(true, slot)) ent |= TMP_OWNER;
+              ent |= TMP_GHOST;
+            } else if (oi < so[slot]) ent |= TMP_OWNER;
+            return true;
+          };
           for (int bj = s0 & ~3; bj < s1; bj += 32) {
             // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
             // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
@@ -320,7 +379,7 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
                 if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
                 else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : 1;    // surely inside: far row only if surely beyond the far threshold
               }
-              if (cls < 0) cls = tile_exact_class(A, row, tile_slot_src(D, slot, A.nlocal, A.gorder));
+              if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
               if (cls) in |= 1u << idx;
               if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
             }
@@ -329,12 +388,14 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
             while (nearm) {
               const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
               const int slot = bj + idx;
-              wn.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, q, nrow16, stride);
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wn.push(ent, q, nrow16, stride);
             }
             while (farm) {
               const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
               const int slot = bj + idx;
-              wf.push(((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot, frow, A.ngrp);
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wf.push(ent, frow, A.ngrp);
             }
           }
         };
@@ -343,16 +404,20 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
           int k0 = imax(ci - 1 - D.rdx[r], 0), k1 = imin(ci + 1 - D.rdx[r], D.rncell[r] - 1);
           if (k0 > k1) continue;
           int ca = D.rcell[r] + k0, cb = D.rcell[r] + k1, cr = D.rcell[r];
-          interval(D.seg_slot[2 * r] + A.cso[ca] - A.cso[cr], D.seg_slot[2 * r] + A.cso[cb + 1] - A.cso[cr]);
+          interval(D.seg_slot[2 * r] + A.cso[ca] - A.cso[cr], D.seg_slot[2 * r] + A.cso[cb + 1] - A.cso[cr], D.seg_slot[2 * r], D.seg_src[2 * r], false);
+          if (gt) continue;
           int ga = A.csg[ca] - A.csg[cr], gb = A.csg[cb + 1] - A.csg[cr];
-          if (gb > ga) interval(D.seg_slot[2 * r + 1] + ga, D.seg_slot[2 * r + 1] + gb);
+          if (gb > ga) interval(D.seg_slot[2 * r + 1] + ga, D.seg_slot[2 * r + 1] + gb, D.seg_slot[2 * r + 1], D.seg_src[2 * r + 1], true);
         }
         if (valid) {
           const int ext = wn.finish(q, nrow16, stride);
           wf.finish(frow, A.ngrp);
           A.numneigh[row] = wn.n; A.numfar[row] = wf.n;
+          if (A.rowtile && !gt) A.rowtile[row] = t;
           atomicMax(A.maxcount, max(ext, wf.n));
         }
+        if (DYN) { if (lane == 0) mine = atomicAdd(&s_item, 1); mine = __shfl_sync(FULLMASK, mine, 0); }
+        else mine += NT / 32;
       }
     }
   }
@@ -360,7 +425,7 @@ __global__ void __launch_bounds__(TILE_BUILD_NT) k_tile_build(const __grid_const
 
 // slot ids -> device particle indices, row-major [row][width] (tests / b200_get_neighbor_list only)
 struct TileExportArgs {
-  int nlocal, ngrp, width;
+  int nlocal, ngrp, width, slot_mask;
   const int *gorder; const TileDesc *tiles; const int *ntiles;
   const uint4 *near, *far; const int *numneigh, *numfar;
   int *out;
@@ -382,7 +447,7 @@ __global__ void k_tile_export(TileExportArgs A)
         for (int k = 0; k < n; k++) {
           int ent = p[(size_t)(k >> 3) * 32 * 8 + (k & 7)];
           if (!ent) continue;
-          int slot = ent & TILE_SLOT_MASK;
+          int slot = ent & A.slot_mask;
           int s = 0;
           while (slot >= D.seg_slot[s + 1]) s++;
           int src = D.seg_src[s] + (slot - D.seg_slot[s]);
@@ -469,8 +534,10 @@ struct TileArgs {
   const TileDesc *tiles; const int *ntiles; int *counter;
   const double4 *xt;
   double4 *vr_out, *fd; double *de;
-  const PairTab *tab[2];
-  TileUni uni[2];
+  const PairTab *tab[3];
+  TileUni uni[3];
+  // multiphase styles
+  const double4 *vm; double4 *cg_out; const int *gorder; int dim;
 };
 
 // shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc | mbarrier | tile id
@@ -761,6 +828,347 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         f.x += fx; f.y += fy; f.z += fz; f.w += adrho;
         A.fd[row] = f;
         A.de[row] += ade;
+      }
+    }
+  }
+}
+
+// ======================================================================= multiphase styles on tiles ====
+// Record parts (tile order, ghosts keep their possibly one-step-stale rho / colorgradient):
+//   P0 x,y   P1 z,rho   P2 vest.x,vest.y   P3 vest.z, pressure   P4 V^2 = (m/rho)^2, T = e/cv   P5 cg.x,cg.y   P6 cg.z, 1/|cg| or 0   P7 m,0
+// colorgradient pass: P0 x,y   P1 z, V^2
+struct TileRecMpArgs {
+  int nlocal, nall, pstride, mode;       // mode 0: colorgradient records, 1: force records
+  const int *gorder; const double4 *xt, *vr, *cgm; const double *e, *cv; const PairTab *fluid;
+  double2 *rec;
+};
+__global__ void k_tile_records_mp(TileRecMpArgs A)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.nall) return;
+  int src = i < A.nlocal ? i : A.nlocal + A.gorder[i - A.nlocal];
+  double4 x = A.xt[src], v = A.vr[src], c = A.cgm[src];
+  const double rho = v.w, V = c.w / rho;
+  const size_t ps = A.pstride;
+  A.rec[i] = make_double2(x.x, x.y);
+  if (A.mode == 0) { A.rec[ps + i] = make_double2(x.z, V * V); return; }
+  int t = tw_type(__double_as_longlong(x.w));
+  // pair_sph_taitwater_multiphase.cpp:289-292
+  double P = A.fluid ? A.fluid->B[t] * (pow(rho / A.fluid->rho0[t], A.fluid->gamma[t]) - A.fluid->rb[t]) : 0.0;
+  double a = sqrt(c.x * c.x + c.y * c.y + c.z * c.z);
+  A.rec[ps + i] = make_double2(x.z, rho);
+  A.rec[2 * ps + i] = make_double2(v.x, v.y);
+  A.rec[3 * ps + i] = make_double2(v.z, P);
+  A.rec[4 * ps + i] = make_double2(V * V, A.e[src] / A.cv[src]);
+  A.rec[5 * ps + i] = make_double2(c.x, c.y);
+  A.rec[6 * ps + i] = make_double2(c.z, a > EPSILON_CG ? 1.0 / a : 0.0);
+  A.rec[7 * ps + i] = make_double2(c.w, 0.0);
+}
+
+// like tile_begin, for a subset PM of the record parts (bit p = part p), packed densely in shared memory
+template <int PM, int NK, int NT>
+__device__ __forceinline__ bool tile_begin_mask(const TileArgs &A, TileSmem<__builtin_popcount(PM), NK> &S, int ntiles)
+{
+  constexpr int NP = __builtin_popcount(PM);
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) *S.tile = atomicAdd(A.counter, 1);
+  __syncthreads();
+  const int t = *S.tile;
+  if (t >= ntiles) return false;
+  for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += NT) ((int *)S.D)[k] = ((const int *)(A.tiles + t))[k];
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) mbar_expect_tx(S.bar, (unsigned)S.D->nslots * 16u * NP);
+    __syncwarp();
+    for (int s = tid; s < 2 * S.D->nrange; s += 32) {
+      int s0 = S.D->seg_slot[s], n = S.D->seg_slot[s + 1] - s0;
+      if (n > 0) {
+        int q = 0;
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+          if (PM & (1 << p)) { bulk_g2s(S.part + (size_t)q * A.cap + s0, A.rec + (size_t)p * A.pstride + S.D->seg_src[s], (unsigned)n * 16u, S.bar); q++; }
+      }
+    }
+  }
+  return true;
+}
+
+// branch-free quintic spline (sph_kernel_quintic.cpp:17-73, argument q = 3 r / h, without the norm): the clamped form
+// max(3-q,0)^5 - 6 max(2-q,0)^5 + 15 max(1-q,0)^5 is the same piecewise polynomial as quintic_w / quintic_dw
+__device__ __forceinline__ double quintic_w_bf(double q)
+{
+  const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);
+  const double a2 = a * a, b2 = b * b, c2 = c * c;
+  return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a * (a2 * a2)));
+}
+__device__ __forceinline__ double quintic_dw_bf(double q)
+{
+  const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);
+  const double a2 = a * a, b2 = b * b, c2 = c * c;
+  return fma(-75.0 * c2, c2, fma(30.0 * b2, b2, -5.0 * (a2 * a2)));
+}
+// r = sqrt(a) and 1/r, branch-free (see fast_sqrt); NaN / inf for a = 0, which the callers mask with dpos()
+__device__ __forceinline__ void fast_sqrt_rinv(double a, double &r, double &rinv)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, hh = 0.5 * y;
+  double e = fma(-hh, g, 0.5);
+  g = fma(g, e, g); hh = fma(hh, e, hh);
+  g = fma(fma(-g, g, a), hh, g);
+  e = fma(-hh, g, 0.5);
+  hh = fma(hh, e, hh);
+  r = g; rinv = hh + hh;
+}
+
+// rows per pass and lanes per row of a 512-thread stage CTA: 256 rows x 2 lanes, or 128 rows x 4 lanes for small tiles
+#define TILE_MP_NT (TILE_ROWS * 2)
+
+// MPK = 0: PairSPHRhoSumMultiphase::compute  pair_sph_rhosum_multiphase.cpp:113-168 (quintic, number density * own mass)
+// MPK = 1: PairSPHColorGradient::compute    pair_sph_colorgradient.cpp:119-184
+// Full lists: every entry of an owned row counts, whatever its ownership flags.
+// GU: cutoff and kernel constants are the same for every mapped type pair (TileUni) -> registers; else the per-pair tables.
+template <int MPK, bool GU>
+__global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_constant__ TileArgs A)
+{
+  constexpr int NT = TILE_MP_NT;
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  TileSmem<2, 1> S(tile_smem, A.cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_tab(S.T, A.tab[0]);
+  if (tid == 0) mbar_init(S.bar, 1);
+  const PairTab &T = S.T[0];
+  const TileUni &U = A.uni[0];
+  const double2 *P0 = S.part, *P1 = S.part + A.cap;
+  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  unsigned phase = 0;
+  while (tile_begin<2, 1, NT>(A, S, ntiles)) {
+    const TileDesc &D = *S.D;
+    const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
+    const int sub = lane / lpw, rl = lane % lpw;
+    mbar_wait(S.bar, phase); phase ^= 1;
+    for (int rb = 0; rb < D.nrows; rb += rpp) {
+      const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
+      bool valid = rt < D.nrows;
+      const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
+      double2 a = make_double2(0, 0), b = a; int ti = 0;
+      if (valid) { a = P0[myslot]; b = P1[myslot]; ti = tw_type(__double_as_longlong(A.xt[row].w)); }
+      if (valid && T.iskip[ti]) valid = false;
+      const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      double acc = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
+      for (int pass = 0; pass < 1 + scan_far; pass++) {
+        const uint4 *lp = (pass ? A.far : A.near) + rbase;
+        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        uint4 En = make_uint4(0, 0, 0, 0);
+        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        for (int gi = sub; gi < ng; gi += split) {
+          const uint4 E = En;
+          if (gi + split < ng) En = ldg_nc_u4(lp + (size_t)(gi + split) * 32);
+          const unsigned w[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            const int slot = ent & TMP_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
+            const double2 qa = P0[slot], qb = P1[slot];
+            const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
+            const double rsq = rsq_fma(dx, dy, dz);
+            const bool hit = GU ? ((rsq < U.cutsq) & ((rowmask >> tj) & 1u) & dpos(rsq)) : ((rsq < T.cutsq[ij]) & dpos(rsq));   // empty entries: type 0 is never mapped
+            const double c0 = GU ? U.c0 : T.c0[ij], c1 = GU ? U.c1 : T.c1[ij];
+            if (MPK == 0) {
+              const double wv = quintic_w_bf(3.0 * (fast_sqrt(rsq) * c1));
+              acc += hit ? (GU ? wv : c0 * wv) : 0.0;
+            } else {
+              double r, rinv; fast_sqrt_rinv(rsq, r, rinv);
+              const double wfd = quintic_dw_bf(3.0 * (r * c1)) * c0;                 // dW/dr
+              double sc = -wfd * T.visc[ij] * qb.y * rinv;                           // -W' alpha / sigma_j^2 / r   (sigma_i applied at the end)
+              sc = hit ? sc : 0.0;
+              ax += sc * dx; ay += sc * dy; az += sc * dz;
+            }
+          }
+        }
+      }
+      for (int o = lpw; o < 32; o <<= 1) {
+        if (MPK == 0) acc += __shfl_xor_sync(FULLMASK, acc, o);
+        else { ax += __shfl_xor_sync(FULLMASK, ax, o); ay += __shfl_xor_sync(FULLMASK, ay, o); az += __shfl_xor_sync(FULLMASK, az, o); }
+      }
+      if (valid && sub == 0) {
+        if (MPK == 0) A.vr_out[row].w = (T.self0[ti] + (GU ? U.c0 * acc : acc)) * A.vm[row].w;   // rho[i] *= imass (:170)
+        else {
+          const double sigmai = A.vr_out[row].w / A.vm[row].w;
+          double4 c = A.cg_out[row];
+          c.x = ax * sigmai; c.y = ay * sigmai; c.z = (A.dim == 3) ? az * sigmai : 0.0;
+          A.cg_out[row] = c;
+        }
+      }
+    }
+  }
+}
+
+//  K_TAITMP PairSPHTaitwaterMultiphase::compute  pair_sph_taitwater_multiphase.cpp:103-182
+//  K_SURF   PairSPHSurfaceTension::compute       pair_sph_surfacetension.cpp:81-190
+//  K_HEATMP PairSPHHeatConductionMultiPhase      pair_sph_heatconduction_multiphase.cpp:78-127
+//  K_HEATPC PairSPHHeatConductionPhaseChange     pair_sph_heatconduction_phasechange.cpp:83-139
+// Tiles of owned rows and tiles of ghost rows (D.ghost) run through the same kernel: a ghost row accumulates what the
+// reference adds to the ghost atom (reverse-communicated afterwards); an owned row skips the pairs with a ghost that the
+// other side owns.  See b200_pair.cuh for the two orientation quirks that use the ownership bit.
+// The body is branch-free (predicated contributions) so that ptxas interleaves the neighbors of a group.
+// GU: every sub-style has one cutoff / one set of kernel constants for all its mapped type pairs AND all sub-styles share
+// the smoothing length (the usual deck) -> one kernel-derivative evaluation per pair on register constants.
+template <int KINDS> struct MpParts {
+  static constexpr int mask = 0x03 | ((KINDS & K_TAITMP) ? 0x1c : 0) | ((KINDS & K_SURF) ? 0x70 : 0) | ((KINDS & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
+  static constexpr int n = __builtin_popcount(mask);
+  static constexpr int nk = ((KINDS & K_TAITMP) ? 1 : 0) + ((KINDS & K_SURF) ? 1 : 0) + ((KINDS & (K_HEATMP | K_HEATPC)) ? 1 : 0);
+  __host__ __device__ static constexpr int idx(int p) { return __builtin_popcount(mask & ((1 << p) - 1)); }
+};
+template <int KINDS, bool DIM3, bool GU>
+__global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_constant__ TileArgs A)
+{
+  using MP = MpParts<KINDS>;
+  constexpr bool HAS_FLUID = (KINDS & K_TAITMP) != 0, HAS_SURF = (KINDS & K_SURF) != 0, HAS_HEAT = (KINDS & (K_HEATMP | K_HEATPC)) != 0;
+  constexpr int NK = MP::nk, NP = MP::n;
+  constexpr int I_FLUID = 0, I_SURF = HAS_FLUID ? 1 : 0, I_HEAT = I_SURF + (HAS_SURF ? 1 : 0);
+  constexpr bool WRITES_DE = HAS_HEAT;
+  constexpr int NT = TILE_MP_NT;
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  TileSmem<NP, NK> S(tile_smem, A.cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = 0; t < NK; t++) load_tab(S.T + t, A.tab[t]);
+  if (tid == 0) mbar_init(S.bar, 1);
+  const PairTab *T = S.T;
+  auto part = [&](int p) { return S.part + (size_t)MP::idx(p) * A.cap; };
+  const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7);
+  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  const size_t ps = A.pstride;
+  unsigned phase = 0;
+  while (tile_begin_mask<MP::mask, NK, NT>(A, S, ntiles)) {
+    const TileDesc &D = *S.D;
+    const bool ghostrow = D.ghost != 0;
+    const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
+    const int sub = lane / lpw, rl = lane % lpw;
+    mbar_wait(S.bar, phase); phase ^= 1;
+    for (int rb = 0; rb < D.nrows; rb += rpp) {
+      const int rt = rb + warp * lpw + rl, row = D.row0 + rt;                  // tile-order index
+      const bool valid = rt < D.nrows;
+      const int rr = valid ? row : D.row0;
+      // the row particle's own record (global, coalesced): ghost rows are not among the staged candidates
+      const double2 a = A.rec[rr], b = A.rec[ps + rr];
+      double2 c = make_double2(0, 0), d = c, v4 = c, g5 = c, g6 = c;
+      if (HAS_FLUID) { c = A.rec[2 * ps + rr]; d = A.rec[3 * ps + rr]; }
+      v4 = A.rec[4 * ps + rr];
+      if (HAS_SURF) { g5 = A.rec[5 * ps + rr]; g6 = A.rec[6 * ps + rr]; }
+      const int dev = ghostrow ? A.nlocal + A.gorder[rr - A.nlocal] : rr;     // device index
+      const int ti = valid ? tw_type(__double_as_longlong(A.xt[dev].w)) : 0;
+      const double rhoi = b.y;
+      unsigned rmask[3] = {0, 0, 0};
+#pragma unroll
+      for (int t = 0; t < NK; t++) rmask[t] = (unsigned)(A.uni[t].mapmask >> (ti * 8)) & 0xffu;
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      double fx = 0, fy = 0, fz = 0, ade = 0;
+      for (int pass = 0; pass < 1 + scan_far; pass++) {
+        const uint4 *lp = (pass ? A.far : A.near) + rbase;
+        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+        uint4 En = make_uint4(0, 0, 0, 0);
+        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        for (int gi = sub; gi < ng; gi += split) {
+          const uint4 E = En;
+          if (gi + split < ng) En = ldg_nc_u4(lp + (size_t)(gi + split) * 32);
+          const unsigned w[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll 4
+          for (int e = 0; e < 8; e++) {
+            const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            // an owned row skips the ghost pairs the other side owns; empty entries have type 0 (mapped nowhere, cutsq = -1)
+            const bool live = ghostrow | ((ent & (TMP_GHOST | TMP_OWNER)) != TMP_GHOST);
+            const bool row_owns = !ghostrow & ((ent & TMP_OWNER) != 0);
+            const int slot = ent & TMP_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
+            const double2 qa = P0[slot], qb = P1[slot], q4 = P4[slot];
+            const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
+            const double rsq = rsq_fma(dx, dy, dz);
+            const bool ok = live & dpos(rsq);
+            const double rhoj = qb.y;
+            double r, rinv; fast_sqrt_rinv(rsq, r, rinv);
+            double dwq = 0.0;                                                  // dW/dq without the norm, shared by the sub-styles when GU
+            if (GU) dwq = quintic_dw_bf(3.0 * (r * A.uni[0].c1));
+            if (HAS_FLUID) {
+              const PairTab &P = T[I_FLUID];
+              const bool hit = ok & (GU ? ((rsq < A.uni[I_FLUID].cutsq) & ((rmask[I_FLUID] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const double2 qc = P2[slot], qd = P3[slot];
+              double wfd = (GU ? dwq * A.uni[I_FLUID].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij]) * rinv;   // (dW/dr)/r (:137-143)
+              wfd = hit ? wfd : 0.0;
+              double Pi = d.y, Pj = qd.y;
+              if (!P.gamma_uniform) {                                      // p_j uses gamma of the list owner (:148)
+                const int to = row_owns ? ti : tj;
+                Pi = P.B[ti] * (pow(rhoi / P.rho0[ti], P.gamma[to]) - P.rb[ti]);
+                Pj = P.B[tj] * (pow(rhoj / P.rho0[tj], P.gamma[to]) - P.rb[tj]);
+              }
+              const double pij = fast_div(rhoj * Pi + rhoi * Pj, rhoi + rhoj);
+              const double V2 = v4.x + q4.x;
+              const double fvisc = V2 * P.visc[ij] * wfd, fpair = -V2 * pij * wfd;
+              const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
+              fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
+            }
+            if (HAS_SURF) {
+              const PairTab &P = T[I_SURF];
+              const bool hit = ok & (GU ? ((rsq < A.uni[I_SURF].cutsq) & ((rmask[I_SURF] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const double2 q5 = P5[slot], q6 = P6[slot];
+              double wfd = GU ? dwq * A.uni[I_SURF].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij];    // dW/dr (:117-123)
+              wfd = hit ? wfd : 0.0;
+              const double ex = dx * rinv, ey = dy * rinv, ez = dz * rinv;
+              double six, siy, siz = 0.0, sjx, sjy, sjz = 0.0;
+              if (DIM3) {                                                  // (:153-169)
+                const double o3 = 0.3333333333333333, t3 = 0.6666666666666666;
+                double cxx = g5.x * g5.x, cyy = g5.y * g5.y, czz = g6.x * g6.x;
+                six = (ex * (o3 * czz + o3 * cyy - t3 * cxx) - g5.x * ez * g6.x - g5.x * ey * g5.y) * g6.y;
+                siy = (ey * (o3 * czz - t3 * cyy + o3 * cxx) - g5.y * ez * g6.x - ex * g5.x * g5.y) * g6.y;
+                siz = (ez * (-t3 * czz + o3 * cyy + o3 * cxx) - ey * g5.y * g6.x - ex * g5.x * g6.x) * g6.y;
+                cxx = q5.x * q5.x; cyy = q5.y * q5.y; czz = q6.x * q6.x;
+                sjx = (ex * (o3 * czz + o3 * cyy - t3 * cxx) - q5.x * ez * q6.x - q5.x * ey * q5.y) * q6.y;
+                sjy = (ey * (o3 * czz - t3 * cyy + o3 * cxx) - q5.y * ez * q6.x - ex * q5.x * q5.y) * q6.y;
+                sjz = (ez * (-t3 * czz + o3 * cyy + o3 * cxx) - ey * q5.y * q6.x - ex * q5.x * q6.x) * q6.y;
+              } else {                                                     // (:140-151); |cg| is the 2-D norm there
+                const double ni = sqrt(g5.x * g5.x + g5.y * g5.y), nj = sqrt(q5.x * q5.x + q5.y * q5.y);
+                const double ii = ni > EPSILON_CG ? 1.0 / ni : 0.0, jj = nj > EPSILON_CG ? 1.0 / nj : 0.0;
+                const double hi2 = (g5.y * g5.y + g5.x * g5.x) / 2, hj2 = (q5.y * q5.y + q5.x * q5.x) / 2;
+                six = (ex * (hi2 - g5.x * g5.x) - g5.x * ey * g5.y) * ii;
+                siy = (ey * (hi2 - g5.y * g5.y) - ex * g5.x * g5.y) * ii;
+                sjx = (ex * (hj2 - q5.x * q5.x) - q5.x * ey * q5.y) * jj;
+                sjy = (ey * (hj2 - q5.y * q5.y) - ex * q5.x * q5.y) * jj;
+              }
+              // rinv is inf for a coincident pair: keep 0 * inf out of the sums
+              fx += hit ? (six * v4.x + sjx * q4.x) * wfd : 0.0;
+              fy += hit ? (siy * v4.x + sjy * q4.x) * wfd : 0.0;
+              if (DIM3) fz += hit ? (siz * v4.x + sjz * q4.x) * wfd : 0.0;
+            }
+            if (HAS_HEAT) {
+              const PairTab &P = T[I_HEAT];
+              const bool hit = ok & (GU ? ((rsq < A.uni[I_HEAT].cutsq) & ((rmask[I_HEAT] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const double mj = P7[slot].x;
+              double wfd = (GU ? dwq * A.uni[I_HEAT].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij]) * rinv;
+              double Ti = v4.y, Tj = q4.y;
+              if (KINDS & K_HEATPC) {                                      // (:124-129), in half-list orientation
+                const int ff = P.fixflag[ij]; const double tc = P.tc[ij];
+                double Ta = row_owns ? Ti : Tj, Tb = row_owns ? Tj : Ti;
+                const int ta = row_owns ? ti : tj, tb = row_owns ? tj : ti;
+                Ta = (ff == ta && Ta < Tb) ? tc : Ta;
+                Tb = (ff == tb && Tb < Ta) ? tc : Tb;
+                Ti = row_owns ? Ta : Tb; Tj = row_owns ? Tb : Ta;
+              }
+              const double term = fast_div(2.0 * P.visc[ij] * (Ti - Tj) * wfd * mj, rhoi * rhoj);
+              ade += hit ? term : 0.0;
+            }
+          }
+        }
+      }
+      for (int o = lpw; o < 32; o <<= 1) {
+        fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
+        if (WRITES_DE) ade += __shfl_xor_sync(FULLMASK, ade, o);
+      }
+      if (valid && sub == 0) {
+        double4 f = A.fd[dev];
+        f.x += fx; f.y += fy; f.z += fz;
+        A.fd[dev] = f;
+        if (WRITES_DE) A.de[dev] += ade;
       }
     }
   }
