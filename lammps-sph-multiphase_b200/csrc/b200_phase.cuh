@@ -17,6 +17,7 @@
 #pragma once
 #include "b200_common.cuh"
 #include "b200_pair.cuh"
+#include "b200_tile.cuh"
 
 #define CG_SMALL 1.0e-20
 #define PC_MAXNEW 262144
@@ -33,6 +34,41 @@ struct PcArrays {
   const int *orig;
   const unsigned *nbr, *far;
   const int *numneigh, *numfar;
+  // tile path (b200_tile.cuh): the rows hold 16-bit slot entries of the row's tile
+  int tiled, ngrp; const TileDesc *tiles; const int *rowtile, *gorder;
+};
+// the neighbor row of owned atom i, whichever path built it: positions 0..n-1, some of which may be empty
+struct PcRow {
+  const PcArrays &a; int i, nlocal, stride;
+  int nin, nout, nfar, n;
+  const unsigned *p, *pf; const unsigned short *tn, *tf; const TileDesc *D;
+  __device__ __forceinline__ PcRow(const PcArrays &a_, const PcParams &P, int i_) : a(a_), i(i_), nlocal(P.nlocal), stride(P.stride)
+  {
+    if (a.tiled) {
+      const size_t rbase = (size_t)(i >> 5) * a.ngrp * 32 + (i & 31);
+      tn = (const unsigned short *)((const uint4 *)a.nbr + rbase); tf = (const unsigned short *)((const uint4 *)a.far + rbase);
+      nin = ((a.numneigh[i] + 7) >> 3) * 8; nout = 0; nfar = ((a.numfar[i] + 7) >> 3) * 8;
+      D = a.tiles + a.rowtile[i];
+    } else {
+      int c = a.numneigh[i]; nin = c & 0xffff; nout = c >> 16; nfar = a.numfar[i];
+      p = row_base(a.nbr, i, stride); pf = row_base(a.far, i, stride);
+    }
+    n = nin + nout + nfar;
+  }
+  // entry k: false if the position is empty; j = device index, tj = type
+  __device__ __forceinline__ bool get(int k, int &j, int &tj) const
+  {
+    if (a.tiled) {
+      const unsigned short *q = k < nin ? tn : tf; if (k >= nin) k -= nin;
+      unsigned ent = q[(size_t)(k >> 3) * 256 + (k & 7)];
+      if (!ent) return false;
+      tj = ent >> TILE_SLOT_BITS; j = tile_slot_src(*D, ent & TMP_SLOT_MASK, nlocal, a.gorder);
+      return true;
+    }
+    unsigned ent = k < nin ? p[(size_t)k * 32] : (k < nin + nout ? p[(size_t)(stride - 1 - (k - nin)) * 32] : pf[(size_t)(k - nin - nout) * 32]);
+    tj = (ent >> NBR_TYPE_SHIFT) & 7; j = ent & NBR_INDEX_MASK;
+    return true;
+  }
 };
 struct PcNew { double x[3], v[3], vest[3], rho, cv, e; int parent; int pad; };
 
@@ -70,12 +106,11 @@ __global__ void k_pc_candidates(PcParams P, PcArrays a, unsigned char *flag, dou
   if (ok) {   // isfromphasearound(i): any from_type neighbour of the LAST build within the fix cutoff (rsq <= cutoff^2)
     bool around = false;
     double cutoff2 = d.cutoff * d.cutoff;
-    int c = a.numneigh[i], nin = c & 0xffff, nout = c >> 16, nfar = a.numfar[i];
-    const unsigned *p = row_base(a.nbr, i, P.stride), *pf = row_base(a.far, i, P.stride);
-    for (int k = 0; k < nin + nout + nfar && !around; k++) {
-      unsigned ent = k < nin ? p[(size_t)k * 32] : (k < nin + nout ? p[(size_t)(P.stride - 1 - (k - nin)) * 32] : pf[(size_t)(k - nin - nout) * 32]);
-      if (((ent >> NBR_TYPE_SHIFT) & 7) != (unsigned)d.from_type) continue;
-      double4 xj = a.xt[ent & NBR_INDEX_MASK];
+    PcRow R(a, P, i);
+    for (int k = 0; k < R.n && !around; k++) {
+      int j, tj;
+      if (!R.get(k, j, tj) || tj != d.from_type) continue;
+      double4 xj = a.xt[j];
       double rsq = rsq_nofma(x.x - xj.x, x.y - xj.y, x.z - xj.z);
       if (rsq <= cutoff2) around = true;
     }
@@ -154,13 +189,12 @@ __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const un
       if (!ok) continue;
       if (nins >= PC_MAXNEW) { state[2] = 1; continue; }
       // mass / momentum taken from from_type neighbours, weights w = W_quintic(r * cutoff) (:252-300)
-      int c = a.numneigh[i], nin = c & 0xffff, nout = c >> 16, ntot = nin + nout + a.numfar[i];
-      const unsigned *p = row_base(a.nbr, i, P.stride), *pf = row_base(a.far, i, P.stride);
-      auto entry = [&](int k) { return k < nin ? p[(size_t)k * 32] : (k < nin + nout ? p[(size_t)(P.stride - 1 - (k - nin)) * 32] : pf[(size_t)(k - nin - nout) * 32]); };
+      PcRow R(a, P, i);
+      const int ntot = R.n;
       double wtot = 0.0;
       for (int k = lane; k < ntot; k += 32) {
-        unsigned ent = entry(k); int j = ent & NBR_INDEX_MASK;
-        if (((ent >> NBR_TYPE_SHIFT) & 7) == (unsigned)d.from_type && a.vm[j].w > 0.5 * d.to_mass) {
+        int j, tj;
+        if (R.get(k, j, tj) && tj == d.from_type && a.vm[j].w > 0.5 * d.to_mass) {
           double4 xj = a.xt[j];
           double rsq = rsq_nofma(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
           wtot += pc_kernel_quintic(P.dim, sqrt(rsq) * d.cutoff);
@@ -170,9 +204,10 @@ __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const un
       for (int s = 16; s; s >>= 1) wtot += __shfl_xor_sync(FULLMASK, wtot, s);
       double mom[6] = {0, 0, 0, 0, 0, 0};
       for (int k = lane; k < ntot; k += 32) {
-        unsigned ent = entry(k); int j = ent & NBR_INDEX_MASK;
+        int j, tj;
+        if (!R.get(k, j, tj)) continue;
         double4 vj = a.vm[j];
-        if (((ent >> NBR_TYPE_SHIFT) & 7) == (unsigned)d.from_type && vj.w > 0.5 * d.to_mass) {
+        if (tj == d.from_type && vj.w > 0.5 * d.to_mass) {
           double4 xj = a.xt[j], vej = a.vr[j];
           double rsq = rsq_nofma(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
           double dm = d.to_mass * pc_kernel_quintic(P.dim, sqrt(rsq) * d.cutoff) / wtot;

@@ -660,7 +660,7 @@ static void build_plan(b200_sph *h)
   }
   // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
-  if (h->multiphase && (getenv("B200_NO_TILE_MP") || !h->pcs.empty())) ok = false;
+  if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
   int np = 2, nk = 1;
   const int SP = K_TAIT | K_MORRIS | K_HEAT, MPK = K_TAITMP | K_SURF | K_HEATMP | K_HEATPC;
   for (const Pass &p : h->plan) {
@@ -1061,7 +1061,8 @@ static void phase_change(b200_sph *h, PcFix &f)
   PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.norig = norig; P.stride = h->stride; P.dt = h->dt;
   for (int d = 0; d < 3; d++) { P.sublo[d] = h->g.sublo[d]; P.subhi[d] = h->g.subhi[d]; P.boxhi[d] = h->g.boxhi[d]; }
   OwnedSet &c = h->C();
-  PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p};
+  PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p,
+             h->rows_tiled ? 1 : 0, h->stride / 8, h->tiles.p, h->rowtile.p, h->gorder.p};
   LAUNCH(h, k_pc_candidates, nblk(na, 128), 128, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p);
   CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
   // compact the candidates (ascending local index) so the serial walk touches only them

@@ -50,6 +50,21 @@ def test_tile_path_equals_row_path(name, nsteps, variant):
         assert harness.relerr(a[k], b[k]) < 1e-12, (name, k, harness.relerr(a[k], b[k]))
 
 
+@pytest.mark.parametrize("name,nsteps", [("droplet3d", 10), ("droplet2d", 20), ("droplet3d_heat", 8), ("droplet2d_pcheat_skin", 20), ("bubble3d", 8),
+                                         ("bubble2d_thermostat", 12), ("kat_surfacetension", 1)])
+@pytest.mark.parametrize("variant", [{}, {"B200_TILE_NOUNI": "1"}])
+def test_multiphase_tile_path_equals_row_path(name, nsteps, variant):
+    """multiphase styles (ownership flags, ghost-row tiles, reverse halo, fix phase_change reading tile rows)"""
+    a, na, ca = _run(name, nsteps, dict(variant))
+    b, nb, cb = _run(name, nsteps, {"B200_NO_TILE_MP": "1"})
+    assert ca["builds"] == cb["builds"] and ca["inserted"] == cb["inserted"]
+    assert ca["launches"] != cb["launches"]
+    for p, q in zip(na, nb):
+        assert np.array_equal(p, q), "neighbor lists differ"
+    for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de", "colorgradient", "rmass"):
+        assert harness.relerr(a[k], b[k]) < 1e-10, (name, k, harness.relerr(a[k], b[k]))
+
+
 def test_tile_path_is_the_one_that_runs():
     """single-phase decks must take the tile kernels (the launch counter differs from the row path's)"""
     a, _, ca = _run("dam3d", 5, {})
