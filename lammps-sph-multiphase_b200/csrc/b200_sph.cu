@@ -677,7 +677,7 @@ static void build_plan(b200_sph *h)
     } else { ok = false; break; }
   }
   h->tile_on = ok; h->tile_nparts = np; h->tile_nk = nk;
-  long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - (long long)sizeof(TileDesc) - 64;
+  long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - 2 * (long long)sizeof(TileDesc) - 64;
   h->tile_slotcap = (int)std::min<long long>(std::min<long long>(h->multiphase ? TMP_MAXSLOTS : TILE_MAXSLOTS, capb / (16 * np)), TILE_MAXSLOTS) & ~1;
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
   if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
@@ -869,10 +869,11 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
       A.tab[0] = h->d_tab[p.slots[0]];
       bool uni = tile_uni(h, T, A.uni[0]) && !h->tile_nouni;
       size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
-      if (h->tile_split == 1) {
+      const int dsplit = getenv("B200_TILE_SPLIT") ? h->tile_split : 4;      // measured: 4 lanes per row (32 warps per SM) is fastest for the density pass
+      if (dsplit == 1) {
         if (uni) launch_tiles(h, k_tile_rhosum<1, true>, "k_tile_rhosum", TILE_ROWS, smem, A);
         else launch_tiles(h, k_tile_rhosum<1, false>, "k_tile_rhosum", TILE_ROWS, smem, A);
-      } else if (h->tile_split == 2) {
+      } else if (dsplit == 2) {
         if (uni) launch_tiles(h, k_tile_rhosum<2, true>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
         else launch_tiles(h, k_tile_rhosum<2, false>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
       } else {

@@ -228,7 +228,7 @@ __device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int 
 // NT: 256 threads for big tiles (C2: 8 chunks of 32 rows per tile), 128 when the tiles are small (more CTAs per SM to overlap the
 // per-tile barriers); the (cell, chunk) work items of a tile are handed to the warps through a shared counter.
 template <bool UNI, bool MP, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k_tile_build(const __grid_constant__ TileBuildArgs A)
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
   constexpr int TILE_BUILD_NT = NT;
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -540,7 +540,7 @@ struct TileArgs {
   const double4 *vm; double4 *cg_out; const int *gorder; int dim;
 };
 
-// shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc | mbarrier | tile id
+// shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc[2] | mbarrier | tile id[2]
 template <int NPARTS, int NK> struct TileSmem {
   double2 *part; PairTab *T; TileDesc *D; unsigned long long *bar; int *tile;
   __device__ __forceinline__ TileSmem(unsigned char *base, int cap)
@@ -548,37 +548,63 @@ template <int NPARTS, int NK> struct TileSmem {
     part = (double2 *)base;
     T = (PairTab *)(base + (size_t)NPARTS * cap * 16);
     D = (TileDesc *)(T + NK);
-    bar = (unsigned long long *)(D + 1);
+    bar = (unsigned long long *)(D + 2);
     tile = (int *)(bar + 1);
   }
-  static size_t bytes(int cap) { return (size_t)NPARTS * cap * 16 + NK * sizeof(PairTab) + sizeof(TileDesc) + 16; }
+  static size_t bytes(int cap) { return (size_t)NPARTS * cap * 16 + NK * sizeof(PairTab) + 2 * sizeof(TileDesc) + 16; }
 };
 
-// fetch the next tile and start the bulk copies of its records; returns false when the tiles are used up
-template <int NPARTS, int NK, int NT>
-__device__ __forceinline__ bool tile_begin(const TileArgs &A, TileSmem<NPARTS, NK> &S, int ntiles)
-{
-  const int tid = threadIdx.x;
-  __syncthreads();                                   // everyone is done with the previous tile's records
-  if (tid == 0) *S.tile = atomicAdd(A.counter, 1);
-  __syncthreads();
-  const int t = *S.tile;
-  if (t >= ntiles) return false;
-  for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += NT) ((int *)S.D)[k] = ((const int *)(A.tiles + t))[k];
-  __syncthreads();
-  if (tid < 32) {
-    if (tid == 0) mbar_expect_tx(S.bar, (unsigned)S.D->nslots * 16u * NPARTS);
+// The tile loop of a persistent stage CTA.  One barrier per tile: while tile t is evaluated, warp 1 draws the next tile id
+// and copies its descriptor into the other descriptor slot; release() (all rows of t done) lets warp 0 issue the bulk copies
+// of tile t+1 at once.  PM = record parts to stage (bit p = part p of A.rec), packed densely in shared memory.
+template <int PM, int NK, int NT> struct TileLoop {
+  static constexpr int NP = __builtin_popcount(PM);
+  const TileArgs &A; TileSmem<NP, NK> &S; int ntiles, cur; unsigned phase;
+  __device__ __forceinline__ TileLoop(const TileArgs &A_, TileSmem<NP, NK> &S_, int ntiles_) : A(A_), S(S_), ntiles(ntiles_), cur(0), phase(0) {}
+  __device__ __forceinline__ void issue(const TileDesc &D)      // warp 0
+  {
+    const int lane = threadIdx.x;
+    if (lane == 0) mbar_expect_tx(S.bar, (unsigned)D.nslots * 16u * NP);
     __syncwarp();
-    for (int s = tid; s < 2 * S.D->nrange; s += 32) {
-      int s0 = S.D->seg_slot[s], n = S.D->seg_slot[s + 1] - s0;
-      if (n > 0)
+    for (int s = lane; s < 2 * D.nrange; s += 32) {
+      int s0 = D.seg_slot[s], n = D.seg_slot[s + 1] - s0;
+      if (n > 0) {
+        int q = 0;
 #pragma unroll
-        for (int p = 0; p < NPARTS; p++)
-          bulk_g2s(S.part + (size_t)p * A.cap + s0, A.rec + (size_t)p * A.pstride + S.D->seg_src[s], (unsigned)n * 16u, S.bar);
+        for (int p = 0; p < 8; p++)
+          if (PM & (1 << p)) { bulk_g2s(S.part + (size_t)q * A.cap + s0, A.rec + (size_t)p * A.pstride + D.seg_src[s], (unsigned)n * 16u, S.bar); q++; }
+      }
     }
   }
-  return true;
-}
+  __device__ __forceinline__ void fetch(int slot, int lane)       // one warp: next tile id + descriptor -> slot
+  {
+    int t = 0;
+    if (lane == 0) { t = atomicAdd(A.counter, 1); S.tile[slot] = t; }
+    t = __shfl_sync(FULLMASK, t, 0);
+    if (t < ntiles)
+      for (int k = lane; k < (int)(sizeof(TileDesc) / 4); k += 32) ((int *)(S.D + slot))[k] = ((const int *)(A.tiles + t))[k];
+  }
+  __device__ __forceinline__ void start()
+  {
+    if (threadIdx.x < 32) fetch(0, threadIdx.x);
+    __syncthreads();                                     // also: tables loaded, mbarrier initialised
+    if (S.tile[0] < ntiles && threadIdx.x < 32) issue(S.D[0]);
+  }
+  // the descriptor of the current tile once its records have landed, or nullptr when the tiles are used up
+  __device__ __forceinline__ const TileDesc *acquire()
+  {
+    if (S.tile[cur] >= ntiles) return nullptr;
+    if ((threadIdx.x >> 5) == 1) fetch(cur ^ 1, threadIdx.x & 31);
+    mbar_wait(S.bar, phase); phase ^= 1;
+    return S.D + cur;
+  }
+  __device__ __forceinline__ void release()
+  {
+    __syncthreads();                                     // everyone is done with this tile's records; the next descriptor is visible
+    cur ^= 1;
+    if (S.tile[cur] < ntiles && threadIdx.x < 32) issue(S.D[cur]);
+  }
+};
 
 // branch-free fp64 sqrt and division: MUFU seed (~2^-22), one coupled Newton step (~2^-43), one residual correction
 // (error ~ the square of that, i.e. below 1 ulp).  The CUDA built-ins carry a slow-path branch that splits the pair body
@@ -608,8 +634,9 @@ __device__ __forceinline__ bool dpos(double a) { return (__double2hiint(a) | __d
 
 // ---------------------------------------------------------------- density ---
 // PairSPHRhoSum::compute, pair_sph_rhosum.cpp:112-197 (full list; quadric kernel, per-type mass)
+// (SPLIT <= 2: 64 registers, so that two CTAs share an SM when their tiles fit -- one stages while the other computes)
 template <int SPLIT, bool UNI>
-__global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __grid_constant__ TileArgs A)
+__global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_rhosum(const __grid_constant__ TileArgs A)
 {
   constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;        // LPW rows per warp, SPLIT lanes per row
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -621,10 +648,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
-  unsigned phase = 0;
-  while (tile_begin<2, 1, NT>(A, S, ntiles)) {
-    const TileDesc &D = *S.D;
-    mbar_wait(S.bar, phase); phase ^= 1;
+  TileLoop<0x3, 1, NT> L(A, S, ntiles);
+  L.start();
+  while (const TileDesc *Dp = L.acquire()) {
+    const TileDesc &D = *Dp;
     for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
@@ -671,6 +698,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_rhosum(const __gr
       if (UNI) acc *= U.mass * U.c0;
       if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
     }
+    L.release();
   }
 }
 
@@ -702,10 +730,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
   const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
-  unsigned phase = 0;
-  while (tile_begin<NPARTS, NK, NT>(A, S, ntiles)) {
-    const TileDesc &D = *S.D;
-    mbar_wait(S.bar, phase); phase ^= 1;
+  TileLoop<(1 << NPARTS) - 1, NK, NT> L(A, S, ntiles);
+  L.start();
+  while (const TileDesc *Dp = L.acquire()) {
+    const TileDesc &D = *Dp;
     for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       const bool valid = rt < D.nrows;
@@ -830,6 +858,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         A.de[row] += ade;
       }
     }
+    L.release();
   }
 }
 
@@ -863,35 +892,6 @@ __global__ void k_tile_records_mp(TileRecMpArgs A)
   A.rec[5 * ps + i] = make_double2(c.x, c.y);
   A.rec[6 * ps + i] = make_double2(c.z, a > EPSILON_CG ? 1.0 / a : 0.0);
   A.rec[7 * ps + i] = make_double2(c.w, 0.0);
-}
-
-// like tile_begin, for a subset PM of the record parts (bit p = part p), packed densely in shared memory
-template <int PM, int NK, int NT>
-__device__ __forceinline__ bool tile_begin_mask(const TileArgs &A, TileSmem<__builtin_popcount(PM), NK> &S, int ntiles)
-{
-  constexpr int NP = __builtin_popcount(PM);
-  const int tid = threadIdx.x;
-  __syncthreads();
-  if (tid == 0) *S.tile = atomicAdd(A.counter, 1);
-  __syncthreads();
-  const int t = *S.tile;
-  if (t >= ntiles) return false;
-  for (int k = tid; k < (int)(sizeof(TileDesc) / 4); k += NT) ((int *)S.D)[k] = ((const int *)(A.tiles + t))[k];
-  __syncthreads();
-  if (tid < 32) {
-    if (tid == 0) mbar_expect_tx(S.bar, (unsigned)S.D->nslots * 16u * NP);
-    __syncwarp();
-    for (int s = tid; s < 2 * S.D->nrange; s += 32) {
-      int s0 = S.D->seg_slot[s], n = S.D->seg_slot[s + 1] - s0;
-      if (n > 0) {
-        int q = 0;
-#pragma unroll
-        for (int p = 0; p < 8; p++)
-          if (PM & (1 << p)) { bulk_g2s(S.part + (size_t)q * A.cap + s0, A.rec + (size_t)p * A.pstride + S.D->seg_src[s], (unsigned)n * 16u, S.bar); q++; }
-      }
-    }
-  }
-  return true;
 }
 
 // branch-free quintic spline (sph_kernel_quintic.cpp:17-73, argument q = 3 r / h, without the norm): the clamped form
@@ -942,12 +942,12 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
-  unsigned phase = 0;
-  while (tile_begin<2, 1, NT>(A, S, ntiles)) {
-    const TileDesc &D = *S.D;
+  TileLoop<0x3, 1, NT> L(A, S, ntiles);
+  L.start();
+  while (const TileDesc *Dp = L.acquire()) {
+    const TileDesc &D = *Dp;
     const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
     const int sub = lane / lpw, rl = lane % lpw;
-    mbar_wait(S.bar, phase); phase ^= 1;
     for (int rb = 0; rb < D.nrows; rb += rpp) {
       const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
@@ -1003,6 +1003,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
         }
       }
     }
+    L.release();
   }
 }
 
@@ -1041,13 +1042,13 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
   const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7);
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
   const size_t ps = A.pstride;
-  unsigned phase = 0;
-  while (tile_begin_mask<MP::mask, NK, NT>(A, S, ntiles)) {
-    const TileDesc &D = *S.D;
+  TileLoop<MP::mask, NK, NT> L(A, S, ntiles);
+  L.start();
+  while (const TileDesc *Dp = L.acquire()) {
+    const TileDesc &D = *Dp;
     const bool ghostrow = D.ghost != 0;
     const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
     const int sub = lane / lpw, rl = lane % lpw;
-    mbar_wait(S.bar, phase); phase ^= 1;
     for (int rb = 0; rb < D.nrows; rb += rpp) {
       const int rt = rb + warp * lpw + rl, row = D.row0 + rt;                  // tile-order index
       const bool valid = rt < D.nrows;
@@ -1171,5 +1172,6 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
         if (WRITES_DE) A.de[dev] += ade;
       }
     }
+    L.release();
   }
 }
