@@ -156,15 +156,16 @@ struct NearWriter {
   unsigned clo, chi; int n;               // 8 x 8-bit class counters (classes 0-3 | 4-7)
   __device__ __forceinline__ NearWriter() : clo(0), chi(0), n(0) {}
   __device__ __forceinline__ int count(int c) const { return (int)(((c & 4) ? chi : clo) >> ((c & 3) * 8)) & 0xff; }
-  __device__ __forceinline__ static int off_of(int c, int k, int q) { int pos = 8 * k + ((c - q) & 7); return (pos >> 3) * 256 + (pos & 7); }
+  // position 8 k + ((c - q) mod 8) = group k, element (c - q) mod 8; a group is 32 rows x 8 entries = 256 shorts apart
+  __device__ __forceinline__ static int off_of(int c, int k, int q) { return k * 256 + ((c - q) & 7); }
   __device__ __forceinline__ void push(unsigned ent, int q, unsigned short *base, int stride)
   {
     const int c = ent & 7, sh = (c & 3) * 8;
     const bool hi = (c & 4) != 0;
     const int k = (int)((hi ? chi : clo) >> sh) & 0xff;
-    const unsigned inc = k < 255 ? 1u << sh : 0u;
-    clo += hi ? 0u : inc; chi += hi ? inc : 0u;
-    if (8 * k + 8 <= stride) base[off_of(c, k, q)] = (unsigned short)ent;
+    const unsigned inc = (unsigned)(k < 255) << sh;
+    if (hi) chi += inc; else clo += inc;
+    if (8 * k < stride) base[off_of(c, k, q)] = (unsigned short)ent;
     n++;
   }
   // returns the extent the row needed (in entries); the row is valid iff that is <= stride
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
           for (int bj = s0 & ~3; bj < s1; bj += 32) {
             // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
             // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
-            unsigned in = 0, mb = 0, fr = 0;
+            // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
+            unsigned in = 0, mb = 0, fr = 0; int nq = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
@@ -353,13 +355,16 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
 #pragma unroll
               for (int c = 0; c < 4; c++) {
                 const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
-                const float rsq = dx * dx + dy * dy + dz * dz;
-                const unsigned bit = 1u << (4 * k + c);
-                in |= rsq < cut_lo ? bit : 0u; mb |= rsq < cut_hi ? bit : 0u;
-                if (UNI) fr |= rsq >= far_hi ? bit : 0u;
+                const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
+                mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
+                if (UNI) fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1);      // 1 = NOT surely far
               }
+              nq = k + 1;
               if (bj + 4 * k + 4 >= s1) break;
             }
+            // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
+            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq));
             // only the slots of [s0, s1), and never the row particle itself
             unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
             if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
