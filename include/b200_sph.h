@@ -35,7 +35,8 @@ enum {
   B200_PAIR_SURFACETENSION = 7,     /* sph/surfacetension            pair_sph_surfacetension.cpp:50-192 */
   B200_PAIR_HEATCONDUCTION = 8,     /* sph/heatconduction            pair_sph_heatconduction.cpp:47-134 */
   B200_PAIR_HEATCONDUCTION_MULTIPHASE = 9,  /* sph/heatconduction/multiphase  ..._multiphase.cpp:49-129 */
-  B200_PAIR_HEATCONDUCTION_PHASECHANGE = 10 /* sph/heatconduction/phasechange ..._phasechange.cpp:52-141 */
+  B200_PAIR_HEATCONDUCTION_PHASECHANGE = 10,/* sph/heatconduction/phasechange ..._phasechange.cpp:52-141 */
+  B200_PAIR_IDEALGAS = 11           /* sph/idealgas                  pair_sph_idealgas.cpp:48-175 (coeff: I J viscosity h) */
 };
 
 /* One sub-style of `pair_style hybrid/overlay` (or the single pair style),
@@ -132,6 +133,8 @@ int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix
  * 0 for `noregion` (apply outside).  Region tests as RegBlock/RegSphere::inside (region_block.cpp:114-119, region_sphere.cpp:96-105). */
 int  b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside);
 int  b200_fix_enforce2d(b200_sph *h, int groupbit);                          /* fix_enforce2d.cpp:77-89 */
+/* fix setforce with constant values (fix_setforce.cpp:215-251): set[d] != 0 -> f[d] = value[d] (set[d] = 0 is the NULL keyword) */
+int  b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3]);
 
 /* ---- per-atom data -------------------------------------------------------- */
 /* Upload nlocal owned atoms (LAMMPS local order).  x,v,rho,e,type,mask,tag are

@@ -98,6 +98,11 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
         else a.e[i] = fl.ipar[k][0] == 2 ? a.cv[i] * fl.par[k][0] : fl.par[k][0];
       } else if (fl.kind[k] == 5) {                           // FixEnforce2D::post_force (fix_enforce2d.cpp:77-89)
         v.z = 0.0; f.z = 0.0; fdirty = true; vdirty = true;
+      } else if (fl.kind[k] == 6) {                           // FixSetForce::post_force, constant values (fix_setforce.cpp:241-251)
+        if (fl.ipar[k][0]) f.x = fl.par[k][0];
+        if (fl.ipar[k][1]) f.y = fl.par[k][1];
+        if (fl.ipar[k][2]) f.z = fl.par[k][2];
+        fdirty = true;
       }
     }
   if (fdirty) a.fd[i] = f;

@@ -182,7 +182,8 @@ __global__ void k_records(int nall, int mode, int nrec, int heat_only, const Pai
   st256(r, make_double4(x.x, x.y, x.z, rho));
   if (mode == 0) {
     double pf = 0.0;
-    if (fluid) {
+    if (fluid && fluid->style == B200_PAIR_IDEALGAS) pf = 0.4 * e[i] / fluid->mass[t] / rho;      // p / rho^2, pair_sph_idealgas.cpp:94
+    else if (fluid) {
       double tmp = rho / fluid->rho0[t], fi = tmp * tmp * tmp;
       pf = fluid->B[t] * (fi * fi * tmp - 1.0) / (rho * rho);
     }
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_colorgradient(PairArgs A)
 template <int KINDS, bool DIM3>
 __global__ void __launch_bounds__(PAIR_THREADS, FORCE_MIN_BLOCKS(KINDS)) k_force(PairArgs A)
 {
-  constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS | K_TAITMP)) != 0;
+  constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS | K_TAITMP | K_IDEAL)) != 0;
   constexpr bool HAS_SURF = (KINDS & K_SURF) != 0;
   constexpr bool HAS_HEAT = (KINDS & (K_HEAT | K_HEATMP | K_HEATPC)) != 0;
   constexpr int NK = (HAS_FLUID ? 1 : 0) + (HAS_SURF ? 1 : 0) + (HAS_HEAT ? 1 : 0);
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, FORCE_MIN_BLOCKS(KINDS)) k_force
     const double mj = MP ? q3.z : T[0].mass[tj];
     const double rinv = rsqrt(rsq), r = rsq * rinv;
 
-    if (KINDS & (K_TAIT | K_MORRIS)) {
+    if (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) {
       const PairTab &P = T[I_FLUID];
       if (rsq < P.cutsq[ij]) {
         double h = P.h[ij];
@@ -315,10 +316,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, FORCE_MIN_BLOCKS(KINDS)) k_force
         double dvx = p1.x - q1.x, dvy = p1.y - q1.y, dvz = p1.z - q1.z;
         double dvdr = dx * dvx + dy * dvy + dz * dvz;
         double mm = mi * mj;
-        if (KINDS & K_TAIT) {
+        if (KINDS & (K_TAIT | K_IDEAL)) {
           double fvisc = 0.0;
-          if (dvdr < 0.0)                                             // Monaghan artificial viscosity (:163-169), one division
-            fvisc = -P.visc[ij] * (P.cs[ti] + P.cs[tj]) * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+          if (dvdr < 0.0) {                                           // Monaghan artificial viscosity (:163-169), one division
+            // sph/idealgas: c = sqrt(0.4 e / m) = sqrt((p/rho^2) rho)  (pair_sph_idealgas.cpp:95,141)
+            const double cc = (KINDS & K_IDEAL) ? sqrt(p1.w * rhoi) + sqrt(q1.w * rhoj) : P.cs[ti] + P.cs[tj];
+            // sph/idealgas never mirrors viscosity[i][j] into [j][i] (pair_sph_idealgas.cpp:244-253): the half-list owner's type comes first
+            const int iv = ((KINDS & K_IDEAL) && !row_owns) ? tj * MAXT1 + ti : ij;
+            fvisc = -P.visc[iv] * cc * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+          }
           double fpair = -mm * (p1.w + q1.w + fvisc) * wfd;
           fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
           ade += -0.5 * fpair * dvdr;

@@ -469,11 +469,11 @@ static bool tile_rows(b200_sph *h)
   h->tiles.ensure((size_t)g.ncells + 1);
   CK(cudaMemsetAsync(h->d_tflags, 0, 16 * sizeof(int), h->st));
   TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
-  LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2], 128), 128, P);
+  LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
   if (mp && h->nghost) {       // ghost rows: what the reference accumulates on ghost atoms (then reverse-communicates)
     h->gtiles.ensure((size_t)g.ncells + 1);
     TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
-    LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2], 128), 128, G);
+    LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, G);
   }
   CK(cudaMemcpyAsync(h->h_flags + 10, h->d_tflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(h->h_tflags2, h->d_tflags + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -618,6 +618,7 @@ static int kind_of(int style)
   case B200_PAIR_HEATCONDUCTION: return K_HEAT;
   case B200_PAIR_HEATCONDUCTION_MULTIPHASE: return K_HEATMP;
   case B200_PAIR_HEATCONDUCTION_PHASECHANGE: return K_HEATPC;
+  case B200_PAIR_IDEALGAS: return K_IDEAL;
   default: return 0;
   }
 }
@@ -662,13 +663,17 @@ static void build_plan(b200_sph *h)
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
   if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
   int np = 2, nk = 1;
-  const int SP = K_TAIT | K_MORRIS | K_HEAT, MPK = K_TAITMP | K_SURF | K_HEATMP | K_HEATPC;
+  const int SP = K_TAIT | K_MORRIS | K_HEAT | K_IDEAL, MPK = K_TAITMP | K_SURF | K_HEATMP | K_HEATPC;
   for (const Pass &p : h->plan) {
     if (p.type == 0) { if (h->multiphase) ok = false; continue; }
     if (p.type == 1 || p.type == 2) { if (!h->multiphase) ok = false; continue; }
     if (p.type != 3) { ok = false; break; }
+    if (!h->multiphase && (p.kinds & K_IDEAL)) {      // asymmetric viscosity table (see k_force): needs the half-list orientation, which the single-phase tile rows do not carry
+      const PairTab &T = h->h_tab[p.slots[0]];
+      for (int i = 1; i <= h->ntypes; i++) for (int j = 1; j <= h->ntypes; j++) if (T.visc[i * MAXT1 + j] != T.visc[j * MAXT1 + i]) ok = false;
+    }
     if (!h->multiphase && !(p.kinds & ~SP)) {
-      bool fluid = (p.kinds & (K_TAIT | K_MORRIS)) != 0, heat = (p.kinds & K_HEAT) != 0;
+      bool fluid = (p.kinds & (K_TAIT | K_MORRIS | K_IDEAL)) != 0, heat = (p.kinds & K_HEAT) != 0;
       np = std::max(np, fluid ? (heat ? 5 : 4) : 3); nk = std::max(nk, (fluid ? 1 : 0) + (heat ? 1 : 0));
     } else if (h->multiphase && !(p.kinds & ~MPK)) {
       int mask = 0x03 | ((p.kinds & K_TAITMP) ? 0x1c : 0) | ((p.kinds & K_SURF) ? 0x70 : 0) | ((p.kinds & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
@@ -747,7 +752,7 @@ static bool tile_uni(const b200_sph *h, const PairTab &T, TileUni &U)
 }
 template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A, bool uni)
 {
-  constexpr bool F = (KINDS & (K_TAIT | K_MORRIS)) != 0, H = (KINDS & K_HEAT) != 0;
+  constexpr bool F = (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) != 0, H = (KINDS & K_HEAT) != 0;
   constexpr int NP = F ? (H ? 5 : 4) : 3, NK = (F ? 1 : 0) + (H ? 1 : 0);
   size_t smem = TileSmem<NP, NK>::bytes(h->tile_cap);
   if (h->tile_split == 1) {
@@ -891,7 +896,7 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
   const PairTab *fluid = nullptr, *heat = nullptr, *hfluid = nullptr, *hheat = nullptr;
   for (int s = 0; s < p.nslots; s++) {
     int kk = kind_of(h->h_tab[p.slots[s]].style);
-    if (kk & (K_TAIT | K_MORRIS)) { fluid = h->d_tab[p.slots[s]]; hfluid = &h->h_tab[p.slots[s]]; }
+    if (kk & (K_TAIT | K_MORRIS | K_IDEAL)) { fluid = h->d_tab[p.slots[s]]; hfluid = &h->h_tab[p.slots[s]]; }
     if (kk & K_HEAT) { heat = h->d_tab[p.slots[s]]; hheat = &h->h_tab[p.slots[s]]; }
   }
   int nparts = fluid ? (heat ? 5 : 4) : 3;
@@ -909,6 +914,7 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
   case K_TAIT: launch_tile_force<K_TAIT>(h, A, uni); break;
   case K_MORRIS: launch_tile_force<K_MORRIS>(h, A, uni); break;
   case K_HEAT: launch_tile_force<K_HEAT>(h, A, uni); break;
+  case K_IDEAL: launch_tile_force<K_IDEAL>(h, A, uni); break;
   case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, A, uni); break;
   case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, A, uni); break;
   default: throw std::string("b200: no tile force kernel for this sub-style group");
@@ -953,7 +959,7 @@ static void run_pass(b200_sph *h, const Pass &p)
   // force pass: canonical table order fluid, surf, heat
   PairArgs A = pair_args(h);
   int nk = 0; const PairTab *fluid = nullptr;
-  const int wants[3] = {K_TAIT | K_MORRIS | K_TAITMP, K_SURF, K_HEAT | K_HEATMP | K_HEATPC};
+  const int wants[3] = {K_TAIT | K_MORRIS | K_TAITMP | K_IDEAL, K_SURF, K_HEAT | K_HEATMP | K_HEATPC};
   for (int want : wants)
     for (int s = 0; s < p.nslots; s++)
       if (kind_of(h->h_tab[p.slots[s]].style) & want) { A.tab[nk++] = h->d_tab[p.slots[s]]; if (want & K_TAIT) fluid = h->d_tab[p.slots[s]]; }
@@ -972,6 +978,7 @@ static void run_pass(b200_sph *h, const Pass &p)
   case K_SURF: launch_force<K_SURF>(h, A); break;
   case K_HEATMP: launch_force<K_HEATMP>(h, A); break;
   case K_HEATPC: launch_force<K_HEATPC>(h, A); break;
+  case K_IDEAL: launch_force<K_IDEAL>(h, A); break;
   case K_TAIT | K_HEAT: launch_force<K_TAIT | K_HEAT>(h, A); break;
   case K_MORRIS | K_HEAT: launch_force<K_MORRIS | K_HEAT>(h, A); break;
   case K_TAITMP | K_SURF: launch_force<K_TAITMP | K_SURF>(h, A); break;
@@ -1181,7 +1188,7 @@ static void fill_tab(b200_sph *h, const b200_pair_desc *d, PairTab &T)
         T.c1[k] = ih; T.c0[k] = dim == 3 ? 3.0 * nq * ih * ih * ih * ih : 3.0 * nq * ih * ih * ih;
         if (d->alpha) T.visc[k] = d->alpha[s];
         break;
-      case B200_PAIR_TAITWATER: case B200_PAIR_TAITWATER_MORRIS: case B200_PAIR_HEATCONDUCTION:
+      case B200_PAIR_TAITWATER: case B200_PAIR_TAITWATER_MORRIS: case B200_PAIR_HEATCONDUCTION: case B200_PAIR_IDEALGAS:
         T.c0[k] = dim == 3 ? -25.066903536973515383e0 * ihsq * ihsq * ihsq * ih : -19.098593171027440292e0 * ihsq * ihsq * ihsq;
         T.visc[k] = d->style == B200_PAIR_HEATCONDUCTION ? (d->alpha ? d->alpha[s] : 0.0) : (d->viscosity ? d->viscosity[s] : 0.0);
         break;
@@ -1368,6 +1375,13 @@ int b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int reg
   return 0;
 }
 int b200_fix_enforce2d(b200_sph *h, int groupbit) { return add_fix(h, 5, groupbit, 0, 0, 0); }
+int b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3])
+{
+  if (add_fix(h, 6, groupbit, 0, 0, 0)) return -1;
+  int k = h->fl.n - 1;
+  for (int d = 0; d < 3; d++) { h->fl.ipar[k][d] = set[d] != 0; h->fl.par[k][d] = value[d]; }
+  return 0;
+}
 int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d)
 {
   API_BEGIN

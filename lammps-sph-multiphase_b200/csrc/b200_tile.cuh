@@ -63,59 +63,72 @@ struct TilePlanArgs {
   int *flags;                    // [0] ntiles  [1] max slots  [2] a single cell does not fit  [3] max rows
 };
 
-__device__ __forceinline__ int tile_fill(const Geom &g, int nlocal, const int *cso, const int *csg, int cy, int cz, int x0, int x1, TileDesc *d, int ghostrows = 0)
-{
-  int xa = imax(x0 - 1, 0), xb = imin(x1 + 1, g.nc[0] - 1);
-  int nr = 0, slots = 0;
-  for (int dz = -1; dz <= 1; dz++) {
-    int nz = cz + dz; if (nz < 0 || nz >= g.nc[2]) continue;
-    for (int dy = -1; dy <= 1; dy++) {
-      int ny = cy + dy; if (ny < 0 || ny >= g.nc[1]) continue;
-      int base = (nz * g.nc[1] + ny) * g.nc[0], a = base + xa, b = base + xb;
-      int no = cso[b + 1] - cso[a], ng = ghostrows ? 0 : csg[b + 1] - csg[a];
-      if (d) {
-        d->rcell[nr] = a; d->rncell[nr] = xb - xa + 1; d->rdx[nr] = xa - x0;
-        d->seg_src[2 * nr] = cso[a]; d->seg_slot[2 * nr] = slots;
-        d->seg_src[2 * nr + 1] = nlocal + csg[a]; d->seg_slot[2 * nr + 1] = slots + no;
-        if (dy == 0 && dz == 0) d->center = nr;
-      }
-      slots += no + ng; nr++;
-    }
-  }
-  if (d) { d->nrange = nr; d->nslots = slots; d->seg_slot[2 * nr] = slots; }
-  return slots;
-}
-
-// one thread per x-row of cells: greedy runs of cells while rows <= rowcap and candidates <= slotcap
+// one warp per x-row of cells: greedy runs of cells while rows <= rowcap and candidates <= slotcap.
+// Lane r < 9 owns candidate range r = the x-row at (dy, dz) = (r % 3 - 1, r / 3 - 1); counts are summed over the lanes.
 __global__ void k_tile_plan(TilePlanArgs A)
 {
   const Geom &g = A.g;
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g.nc[1] * g.nc[2]) return;
-  int cy = r % g.nc[1], cz = r / g.nc[1], base = r * g.nc[0];
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= g.nc[1] * g.nc[2]) return;
+  const int cy = w % g.nc[1], cz = w / g.nc[1], base = w * g.nc[0];
   const int *rows = A.ghostrows ? A.csg : A.cso;       // whose rows: owned particles, or the ghosts of the same cells
   const int gr = A.ghostrows;
+  const int ny = cy + lane % 3 - 1, nz = cz + lane / 3 - 1;
+  const bool rvalid = lane < 9 && ny >= 0 && ny < g.nc[1] && nz >= 0 && nz < g.nc[2];
+  const int rbase = rvalid ? (nz * g.nc[1] + ny) * g.nc[0] : 0;
+  const unsigned rmask = __ballot_sync(FULLMASK, rvalid);
+  const int rrank = __popc(rmask & ((1u << lane) - 1));            // index of this lane's range among the valid ones
+  // candidates of this lane's range for the run of cells [x0, x1]: owned, ghost
+  auto counts = [&](int x0, int x1, int &no, int &ng) {
+    no = ng = 0;
+    if (rvalid) {
+      int a = rbase + imax(x0 - 1, 0), b = rbase + imin(x1 + 1, g.nc[0] - 1);
+      no = A.cso[b + 1] - A.cso[a]; ng = gr ? 0 : A.csg[b + 1] - A.csg[a];
+    }
+  };
+  auto total = [&](int x0, int x1) {
+    int no, ng; counts(x0, x1, no, ng);
+    int v = no + ng;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+  };
   int x0 = 0;
   while (x0 < g.nc[0]) {
     if (rows[base + x0 + 1] == rows[base + x0]) { x0++; continue; }
     int x1 = x0;
-    int slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr, gr);
     while (x1 + 1 < g.nc[0]) {
       if (rows[base + x1 + 2] - rows[base + x0] > A.rowcap) break;
-      int s2 = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1 + 1, nullptr, gr);
-      if (s2 > A.slotcap) break;
-      x1++; slots = s2;
+      if (total(x0, x1 + 1) > A.slotcap) break;
+      x1++;
     }
     if (A.shrink)      // (kernels with a run-time lane split) 512 threads serve 256 rows x 2 lanes or 128 rows x 4 lanes: a tile of 129..191 rows wastes more lanes than a shorter one
       while (x1 > x0 && rows[base + x1 + 1] - rows[base + x0] > TILE_ROWS / 2 && rows[base + x1 + 1] - rows[base + x0] < 3 * TILE_ROWS / 4) x1--;
     while (x1 > x0 && rows[base + x1 + 1] == rows[base + x1]) x1--;          // no trailing empty cells
-    slots = tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, nullptr, gr);
-    if (slots > A.slotcap) atomicExch(&A.flags[2], 1);
-    int t = atomicAdd(&A.flags[0], 1);
+    int no, ng; counts(x0, x1, no, ng);
+    int incl = no + ng;                                               // inclusive scan over the lanes -> slot offsets of the ranges
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += v; }
+    const int slots = __shfl_sync(FULLMASK, incl, 31), first = incl - (no + ng);
+    int t = 0;
+    if (lane == 0) {
+      if (slots > A.slotcap) atomicExch(&A.flags[2], 1);
+      t = atomicAdd(&A.flags[0], 1);
+      atomicMax(&A.flags[1], slots); atomicMax(&A.flags[3], rows[base + x1 + 1] - rows[base + x0]);
+    }
+    t = __shfl_sync(FULLMASK, t, 0);
     TileDesc *d = A.tiles + t;
-    d->row0 = (gr ? A.nlocal : 0) + rows[base + x0]; d->nrows = rows[base + x1 + 1] - rows[base + x0]; d->c0 = base + x0; d->ncell = x1 - x0 + 1; d->ghost = gr;
-    tile_fill(g, A.nlocal, A.cso, A.csg, cy, cz, x0, x1, d, gr);
-    atomicMax(&A.flags[1], slots); atomicMax(&A.flags[3], d->nrows);
+    if (lane == 0) {
+      d->row0 = (gr ? A.nlocal : 0) + rows[base + x0]; d->nrows = rows[base + x1 + 1] - rows[base + x0]; d->c0 = base + x0; d->ncell = x1 - x0 + 1; d->ghost = gr;
+      d->nrange = __popc(rmask); d->nslots = slots; d->seg_slot[2 * __popc(rmask)] = slots;
+    }
+    if (rvalid) {
+      const int xa = imax(x0 - 1, 0), xb = imin(x1 + 1, g.nc[0] - 1), a = rbase + xa;
+      d->rcell[rrank] = a; d->rncell[rrank] = xb - xa + 1; d->rdx[rrank] = xa - x0;
+      d->seg_src[2 * rrank] = A.cso[a]; d->seg_slot[2 * rrank] = first;
+      d->seg_src[2 * rrank + 1] = A.nlocal + A.csg[a]; d->seg_slot[2 * rrank + 1] = first + no;
+      if (lane == 4) d->center = rrank;                              // (dy, dz) = (0, 0)
+    }
     x0 = x1 + 1;
   }
 }
@@ -483,10 +496,13 @@ __global__ void k_tile_records(TileRecArgs A)
   A.rec[(size_t)A.pstride + i] = make_double2(x.z, v.w);
   if (A.force) {
     double pf = 0.0;
-    if (A.fluid) {                     // B((rho/rho0)^7 - 1)/rho^2, pair_sph_taitwater.cpp:118-120
+    if (A.fluid) {
       int t = tw_type(__double_as_longlong(x.w));
-      double tmp = v.w / A.fluid->rho0[t], fi = tmp * tmp * tmp;
-      pf = A.fluid->B[t] * (fi * fi * tmp - 1.0) / (v.w * v.w);
+      if (A.fluid->style == B200_PAIR_IDEALGAS) pf = 0.4 * A.e[src] / A.fluid->mass[t] / v.w;     // p / rho^2, pair_sph_idealgas.cpp:94
+      else {                           // B((rho/rho0)^7 - 1)/rho^2, pair_sph_taitwater.cpp:118-120
+        double tmp = v.w / A.fluid->rho0[t], fi = tmp * tmp * tmp;
+        pf = A.fluid->B[t] * (fi * fi * tmp - 1.0) / (v.w * v.w);
+      }
     }
     A.rec[(size_t)2 * A.pstride + i] = make_double2(v.x, v.y);
     A.rec[(size_t)3 * A.pstride + i] = make_double2(v.z, pf);
@@ -711,12 +727,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
 //  K_TAIT   PairSPHTaitwater::compute        pair_sph_taitwater.cpp:101-196
 //  K_MORRIS PairSPHTaitwaterMorris::compute  pair_sph_taitwater_morris.cpp:102-196
 //  K_HEAT   PairSPHHeatConduction::compute   pair_sph_heatconduction.cpp:76-132
+//  K_IDEAL  PairSPHIdealGas::compute         pair_sph_idealgas.cpp:48-175 (taitwater with p/rho^2 = 0.4 e/(m rho), c = sqrt(0.4 e/m))
 // UNI: both tables are uniform (TileUni) -> a branch-free body on register constants that ptxas interleaves across the
 // 8 neighbors of a group; otherwise the per-type tables are read from shared memory.
 template <int KINDS, int SPLIT, bool UNI>
 __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __grid_constant__ TileArgs A)
 {
-  constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS)) != 0;
+  constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) != 0;
   constexpr bool HAS_HEAT = (KINDS & K_HEAT) != 0;
   constexpr int NK = (HAS_FLUID ? 1 : 0) + (HAS_HEAT ? 1 : 0);
   constexpr int NPARTS = HAS_FLUID ? (HAS_HEAT ? 5 : 4) : 3;
@@ -731,7 +748,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double2 *P0 = S.part, *P1 = P0 + A.cap, *P2 = P1 + A.cap, *P3 = P2 + A.cap, *PEp = S.part + (size_t)PE * A.cap;
   const TileUni &UF = A.uni[0], &UH = A.uni[I_HEAT];
   // register constants of the uniform body
-  const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h;
+  const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_vci = -UF.visc * UF.h;
   const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
   const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
   const int ntiles = *A.ntiles, scan_far = *A.scan_far;
@@ -751,6 +768,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         ti = tw_type(__double_as_longlong(A.xt[row].w));
       }
       const double rhoi = b.y, mi = S.T[0].mass[ti];
+      const double ci = (KINDS & K_IDEAL) ? sqrt(fmax(d.y * rhoi, 0.0)) : 0.0;
       const unsigned maskf = (unsigned)(UF.mapmask >> (ti * 8)) & 0xffu, maskh = (unsigned)(UH.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
@@ -781,8 +799,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                 wfd = hit ? wfd : 0.0;
                 const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
                 const double dvdr = dx * dvx + dy * dvy + dz * dvz;
-                if (KINDS & K_TAIT) {
-                  double fvisc = fast_div(u_vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
+                if (KINDS & (K_TAIT | K_IDEAL)) {
+                  // sph/idealgas: the sound speeds are per particle, c = sqrt(0.4 e / m) = sqrt((p/rho^2) rho)
+                  const double vch = (KINDS & K_IDEAL) ? u_vci * (ci + fast_sqrt(fmax(qd.y * rhoj, 0.0))) : u_vch;
+                  double fvisc = fast_div(vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
                   fvisc = dvdr < 0.0 ? fvisc : 0.0;
                   const double fpair = u_k1 * (d.y + qd.y + fvisc) * wfd;     // -m m c0 (...) (h - r)^2
                   fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
@@ -821,10 +841,12 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                   const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
                   const double dvdr = dx * dvx + dy * dvy + dz * dvz;
                   const double mm = mi * mj;
-                  if (KINDS & K_TAIT) {
+                  if (KINDS & (K_TAIT | K_IDEAL)) {
                     double fvisc = 0.0;
-                    if (dvdr < 0.0)
-                      fvisc = -P.visc[ij] * (P.cs[ti] + P.cs[tj]) * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+                    if (dvdr < 0.0) {
+                      const double cc = (KINDS & K_IDEAL) ? ci + sqrt(qd.y * rhoj) : P.cs[ti] + P.cs[tj];
+                      fvisc = -P.visc[ij] * cc * (h * dvdr) / ((rsq + 0.01 * h * h) * (rhoi + rhoj));
+                    }
                     const double fpair = -mm * (d.y + qd.y + fvisc) * wfd;
                     fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
                     ade += -0.5 * fpair * dvdr;

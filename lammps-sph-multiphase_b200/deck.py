@@ -20,10 +20,10 @@ import numpy as np
 PAIR_STYLES = {
     "sph/rhosum": 1, "sph/rhosum/multiphase": 2, "sph/taitwater": 3, "sph/taitwater/morris": 4,
     "sph/taitwater/multiphase": 5, "sph/colorgradient": 6, "sph/surfacetension": 7,
-    "sph/heatconduction": 8, "sph/heatconduction/multiphase": 9, "sph/heatconduction/phasechange": 10,
+    "sph/heatconduction": 8, "sph/heatconduction/multiphase": 9, "sph/heatconduction/phasechange": 10, "sph/idealgas": 11,
 }
 _NSETTINGS = {1: 1, 2: 1, 6: 1}           # styles whose settings() takes Nstep
-_NCOEFF = {1: (1,), 2: (1,), 3: (4,), 4: (4,), 5: (6,), 6: (2,), 7: (1,), 8: (2,), 9: (2,), 10: (2, 4)}
+_NCOEFF = {1: (1,), 2: (1,), 3: (4,), 4: (4,), 5: (6,), 6: (2,), 7: (1,), 8: (2,), 9: (2,), 10: (2, 4), 11: (2,)}
 
 
 class DeckError(RuntimeError):
@@ -77,7 +77,8 @@ class SubStyle:
         colorgradient        h alpha                pair_sph_colorgradient.cpp:216-252
         surfacetension       h                      pair_sph_surfacetension.cpp:225-250
         heatconduction[/mp]  D h                    pair_sph_heatconduction.cpp:168-195
-        heatconduction/phasechange D h [Ti|NULL Tj|NULL]  ..._phasechange.cpp:177-225"""
+        heatconduction/phasechange D h [Ti|NULL Tj|NULL]  ..._phasechange.cpp:177-225
+        idealgas             nu h                   pair_sph_idealgas.cpp:210-238"""
         if len(args) not in _NCOEFF[self.style]:
             raise DeckError("Incorrect args for pair_style %s coefficients" % self.name)
         ilo, ihi = bounds(I, self.n); jlo, jhi = bounds(J, self.n)
@@ -92,6 +93,8 @@ class SubStyle:
         elif st == 5:
             rho0, c0, nu, gam, cut_one, rb = f
             B_one = c0 * c0 * rho0 / gam
+        elif st == 11:
+            nu, cut_one = f
         elif st == 6:
             cut_one, alpha_one = f
         else:
@@ -111,7 +114,7 @@ class SubStyle:
                     self.gamma[i], self.rbackground[i] = gam, rb
             for j in range(max(jlo, i), jhi + 1):
                 self.cut[i, j] = cut_one
-                if st in (3, 4, 5):
+                if st in (3, 4, 5, 11):
                     self.viscosity[i, j] = nu
                 if st in (6, 8, 9, 10):
                     self.alpha[i, j] = alpha_one
@@ -129,7 +132,8 @@ class SubStyle:
         if not self.setflag[i, j]:
             raise DeckError("All pair %s coeffs are not set" % self.name)
         self.cut[j, i] = self.cut[i, j]
-        self.viscosity[j, i] = self.viscosity[i, j]
+        if self.style != 11:      # PairSPHIdealGas::init_one (pair_sph_idealgas.cpp:244-253) mirrors only cut: viscosity[j][i] stays
+            self.viscosity[j, i] = self.viscosity[i, j]       # as allocated (zero) for j > i -- SURVEY Appendix B style quirk, reproduced
         self.alpha[j, i] = self.alpha[i, j]
         self.tc[j, i] = self.tc[i, j]
         self.fixflag[j, i] = self.fixflag[i, j]
@@ -269,6 +273,14 @@ class Deck:
             if self.dimension == 3:
                 raise DeckError("Cannot use fix enforce2d with 3d simulation")
             self.fixes.append((style, bit, None))
+        elif style == "setforce":      # fix_setforce.cpp:40-110, constant values or NULL
+            if len(args) != 3:
+                raise DeckError("Illegal fix setforce command")
+            if any(str(a).startswith("v_") for a in args):
+                raise DeckError("b200 SPH package: fix setforce supports constant values")
+            sets = [0 if str(a) == "NULL" else 1 for a in args]
+            vals = [0.0 if str(a) == "NULL" else float(a) for a in args]
+            self.fixes.append((style, bit, (sets, vals)))
         elif style == "setmeso":
             which = {"meso_rho": 0, "meso_e": 1, "meso_t": 2}.get(args[0])
             if which is None:

@@ -110,3 +110,15 @@ int FixSetMesoB200::b200_register(b200_sph *h)
   }
   return b200_fix_setmeso(h, groupbit, which, value, kind, r, regionflag);
 }
+
+FixSetForceB200::FixSetForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
+{
+  if (narg != 6) error->all(FLERR, "Illegal fix setforce command (fix setforce/b200: constant values or NULL, no region)");
+  for (int d = 0; d < 3; d++) {
+    const char *a = arg[3 + d];
+    if (strstr(a, "v_") == a) error->all(FLERR, "fix setforce/b200 supports constant values only");
+    set[d] = strcmp(a, "NULL") != 0;
+    value[d] = set[d] ? atof(a) : 0.0;
+  }
+}
+int FixSetForceB200::setmask() { return POST_FORCE; }

@@ -10,6 +10,7 @@ FixStyle(gravity/b200,FixGravityB200)
 FixStyle(phase_change/b200,FixPhaseChangeB200)
 FixStyle(setmeso/b200,FixSetMesoB200)
 FixStyle(enforce2d/b200,FixEnforce2DB200)
+FixStyle(setforce/b200,FixSetForceB200)
 
 #else
 
@@ -85,6 +86,18 @@ class FixEnforce2DB200 : public FixEnforce2D, public B200FixShell {
   void setup(int) {}
   void post_force(int) { b200_fix_guard(lmp, "enforce2d"); }
   int b200_register(b200_sph *h) { return b200_fix_enforce2d(h, groupbit); }
+};
+
+// FixSetForce keeps its parameters private (fix_setforce.h:41-46): same argument list re-parsed,
+//   fix ID grp setforce fx fy fz     (fix_setforce.cpp:40-110), constant values or NULL, no region
+class FixSetForceB200 : public Fix, public B200FixShell {
+ public:
+  FixSetForceB200(class LAMMPS *, int, char **);
+  int setmask();
+  void post_force(int) { b200_fix_guard(lmp, "setforce"); }
+  int b200_register(b200_sph *h) { return b200_fix_setforce(h, groupbit, set, value); }
+ private:
+  int set[3]; double value[3];
 };
 
 }    // namespace LAMMPS_NS

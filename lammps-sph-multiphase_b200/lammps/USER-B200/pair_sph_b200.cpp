@@ -63,6 +63,11 @@ void PairSPHHeatConductionB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
   COMMON(B200_PAIR_HEATCONDUCTION, 0)
   d.alpha = b200_flat2(ds, alpha, setflag, n);
 }
+void PairSPHIdealGasB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
+{
+  COMMON(B200_PAIR_IDEALGAS, 0)
+  d.viscosity = b200_flat2(ds, viscosity, setflag, n);
+}
 void PairSPHHeatConductionMultiPhaseB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
 {
   COMMON(B200_PAIR_HEATCONDUCTION_MULTIPHASE, 0)

@@ -14,6 +14,7 @@ PairStyle(sph/surfacetension/b200,PairSPHSurfaceTensionB200)
 PairStyle(sph/heatconduction/b200,PairSPHHeatConductionB200)
 PairStyle(sph/heatconduction/multiphase/b200,PairSPHHeatConductionMultiPhaseB200)
 PairStyle(sph/heatconduction/phasechange/b200,PairSPHHeatConductionPhaseChangeB200)
+PairStyle(sph/idealgas/b200,PairSPHIdealGasB200)
 
 #else
 
@@ -31,6 +32,7 @@ PairStyle(sph/heatconduction/phasechange/b200,PairSPHHeatConductionPhaseChangeB2
 #include "pair_sph_heatconduction.h"
 #include "pair_sph_heatconduction_multiphase.h"
 #include "pair_sph_heatconduction_phasechange.h"
+#include "pair_sph_idealgas.h"
 
 namespace LAMMPS_NS {
 
@@ -57,6 +59,7 @@ B200_PAIR_SHELL(PairSPHColorGradientB200, PairSPHColorGradient)
 B200_PAIR_SHELL(PairSPHSurfaceTensionB200, PairSPHSurfaceTension)
 B200_PAIR_SHELL(PairSPHHeatConductionB200, PairSPHHeatConduction)
 B200_PAIR_SHELL(PairSPHHeatConductionMultiPhaseB200, PairSPHHeatConductionMultiPhase)
+B200_PAIR_SHELL(PairSPHIdealGasB200, PairSPHIdealGas)
 
 // heatconduction/phasechange leaves tc/fixflag uninitialised for the 4-argument coeff form
 // (pair_sph_heatconduction_phasechange.cpp:191-218); the shell zeroes them at allocation.

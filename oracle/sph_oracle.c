@@ -33,7 +33,7 @@
 #define EPSILON 1.0e-12 /* pair_sph_surfacetension.cpp */
 #define CG_SMALL 1.0e-20 /* fix_phase_change.cpp:42 */
 
-enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D };
+enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE };
 
 typedef struct {
   int style, nstep;
@@ -45,6 +45,7 @@ typedef struct {
   int kind, groupbit;
   double acc[3];
   int which, region_kind, match_inside; double value, region[6];
+  int fset[3]; double fvalue[3];   /* fix setforce */
   osph_phase_change_desc pc;
   long long next_reneighbor;
   int seed; /* RanPark state, random_park.cpp:22-47 */
@@ -224,6 +225,13 @@ int osph_fix_setmeso(osph_sph *s, int groupbit, int which, double value, int reg
   return 0;
 }
 int osph_fix_enforce2d(osph_sph *s, int groupbit) { return newfix(s, FIX_ENFORCE2D, groupbit) ? 0 : fail("too many fixes"); }
+int osph_fix_setforce(osph_sph *s, int groupbit, const int set[3], const double value[3])
+{
+  ofix *f = newfix(s, FIX_SETFORCE, groupbit);
+  if (!f) return fail("too many fixes");
+  for (int d = 0; d < 3; d++) { f->fset[d] = set[d] != 0; f->fvalue[d] = value[d]; }
+  return 0;
+}
 int osph_fix_phase_change(osph_sph *s, const osph_phase_change_desc *d)
 {
   if (d->seed <= 0) return fail("Illegal value for seed"); /* fix_phase_change.cpp:70 */
@@ -711,6 +719,34 @@ static void pair_taitwater(osph_sph *s, opair *p, int morris)
   NB_END
 }
 
+/* PairSPHIdealGas::compute, pair_sph_idealgas.cpp:48-175 */
+static void pair_idealgas(osph_sph *s, opair *p)
+{
+  int nlocal = s->nlocal, nt = s->ntypes + 1; const double *x = s->x, *v = s->vest, *rho = s->rho, *mass = s->mass, *e = s->e;
+  double *f = s->f, *de = s->de, *drho = s->drho;
+  NB_LOOP_BEGIN(0)
+    double vxtmp = v[3*i], vytmp = v[3*i+1], vztmp = v[3*i+2], imass = mass[itype];
+    double fi = 0.4 * e[i] / imass / rho[i];      /* ideal gas EOS: pressure / rho^2 (:94) */
+    double ci = sqrt(0.4 * e[i] / imass);         /* speed of sound, gamma = 1.4 (:95) */
+    NB_FOR_J(0)
+      double jmass = mass[jtype], wfd = lucy_wfd(s->dim, h, rsq);
+      double fj = 0.4 * e[j] / jmass / rho[j];
+      double delVdotDelR = delx * (vxtmp - v[3*j]) + dely * (vytmp - v[3*j+1]) + delz * (vztmp - v[3*j+2]), fvisc;
+      if (delVdotDelR < 0.) {
+        double cj = sqrt(0.4 * e[j] / jmass);
+        double mu = h * delVdotDelR / (rsq + 0.01 * h * h);
+        fvisc = -p->viscosity[itype * nt + jtype] * (ci + cj) * mu / (rho[i] + rho[j]);
+      } else fvisc = 0.;
+      double fpair = -imass * jmass * (fi + fj + fvisc) * wfd, deltaE = -0.5 * fpair * delVdotDelR;
+      f[3*i] += delx * fpair; f[3*i+1] += dely * fpair; f[3*i+2] += delz * fpair;
+      drho[i] += jmass * delVdotDelR * wfd;
+      de[i] += deltaE;
+      f[3*j] -= delx * fpair; f[3*j+1] -= dely * fpair; f[3*j+2] -= delz * fpair;
+      de[j] += deltaE;
+      drho[j] += imass * delVdotDelR * wfd;
+  NB_END
+}
+
 /* PairSPHTaitwaterMultiphase::compute, pair_sph_taitwater_multiphase.cpp:55-186 */
 static void pair_taitwater_multiphase(osph_sph *s, opair *p)
 {
@@ -829,6 +865,7 @@ static int pair_compute_slot(osph_sph *s, int k)
   case B200_PAIR_HEATCONDUCTION: pair_heatconduction(s, p); break;
   case B200_PAIR_HEATCONDUCTION_MULTIPHASE: pair_heatconduction_multiphase(s, p, 0); break;
   case B200_PAIR_HEATCONDUCTION_PHASECHANGE: pair_heatconduction_multiphase(s, p, 1); break;
+  case B200_PAIR_IDEALGAS: pair_idealgas(s, p); break;
   default: return fail("unknown pair style");
   }
   return 0;
@@ -910,6 +947,13 @@ static void fix_setmeso(osph_sph *s, ofix *fx)
 /* FixEnforce2D::post_force, fix_enforce2d.cpp:77-89 */
 static void fix_enforce2d(osph_sph *s, ofix *fx)
 { for (int i = 0; i < s->nlocal; i++) if (s->mask[i] & fx->groupbit) { s->v[3*i+2] = 0.0; s->f[3*i+2] = 0.0; } }
+/* FixSetForce::post_force, constant values, fix_setforce.cpp:241-251 */
+static void fix_setforce(osph_sph *s, ofix *fx)
+{
+  for (int i = 0; i < s->nlocal; i++)
+    if (s->mask[i] & fx->groupbit)
+      for (int d = 0; d < 3; d++) if (fx->fset[d]) s->f[3*i+d] = fx->fvalue[d];
+}
 
 /* ---- fix phase_change, fix_phase_change.cpp:167-352 ---- */
 static int pc_isfromphasearound(osph_sph *s, ofix *fx, int i)
@@ -1074,6 +1118,7 @@ int osph_post_force(osph_sph *s)
     if (s->fix[i].kind == FIX_GRAVITY) fix_gravity(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_SETMESO) fix_setmeso(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_ENFORCE2D) fix_enforce2d(s, &s->fix[i]);
+    else if (s->fix[i].kind == FIX_SETFORCE) fix_setforce(s, &s->fix[i]);
   }
   return 0;
 }

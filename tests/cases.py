@@ -211,6 +211,50 @@ _add(_dam("dam3d", 3, 25))
 _add(_dam("dam2d_morris", 2, 40, morris=True))
 
 
+# ---- shock tube (examples/USER/sph/shock_tube/shock{2,3}d.lmp): sph/rhosum + sph/idealgas, per-type masses, fix setforce;
+#      the shipped deck shrink-wraps x (boundary s p p); here the tube is shortened and periodic in x (a second contact at the wrap)
+def _shock(name, dim, nsteps, onetype=False):
+    if dim == 3:
+        box = ((-12, -4, -4), (18, 4, 4)); lat = "sc"; bnd = "p p p"
+        right = "region right block 1 EDGE EDGE EDGE EDGE EDGE units box"
+        sf = ("setforce", "NULL", 0.0, 0.0)
+    else:
+        box = ((-30, -4, -0.05), (45, 4, 0.05)); lat = "sq"; bnd = "p p p"
+        right = "region right block 1 EDGE EDGE EDGE EDGE EDGE units box"
+        sf = ("setforce", "NULL", 0.0, 0.0)
+    create = """lattice %s 1.0
+create_atoms 1 box
+%s
+set region right type 2
+set type 1 meso_e 2.5
+set type 2 meso_e 0.625
+set type 1 meso_rho 1.0
+set type 2 meso_rho 0.25""" % (lat, right)
+    if onetype:      # one atom type (symmetric coefficient tables -> the tile path), a hot and a cold half
+        create = """lattice %s 1.0
+create_atoms 1 box
+%s
+set group all meso_e 2.5
+set region right meso_e 0.625
+set group all meso_rho 1.0
+displace_atoms all random 0.05 0.05 %s 4711 units box""" % (lat, right, "0.05" if dim == 3 else "0.0")
+        cmds = [("mass", "1", 1.0), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/idealgas"),
+                ("pair_coeff", "* *", "sph/rhosum", 4.0), ("pair_coeff", "* *", "sph/idealgas", 0.75, 4.0),
+                ("neighbor", 0.5), ("neigh_modify", dict(every=5, delay=0, check="yes")), ("timestep", 0.05),
+                ("fix", "all", "meso"), ("fix", "all", *sf)]
+        return Case(name, dim, bnd, box, "meso", 1, create, cmds, nsteps, units="lj")
+    cmds = [("mass", "1", 1.0), ("mass", "2", 0.25), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/idealgas"),
+            ("pair_coeff", "* *", "sph/rhosum", 4.0), ("pair_coeff", "* *", "sph/idealgas", 0.75, 4.0),
+            ("neighbor", 0.5), ("neigh_modify", dict(every=5, delay=0, check="yes")), ("timestep", 0.05),
+            ("fix", "all", "meso"), ("fix", "all", *sf)]
+    return Case(name, dim, bnd, box, "meso", 2, create, cmds, nsteps, units="lj")
+
+
+_add(_shock("shock3d", 3, 20))
+_add(_shock("shock2d", 2, 40))
+_add(_shock("gas3d", 3, 15, onetype=True))
+
+
 # ---- C3 scaled down: periodic two-phase box (square_to_sphere/droplet.lmp + cube.lmp) ----
 def _droplet(name, dim, nx, nsteps, heat=None, skin=0.0, every=1, check="yes", static=False):
     L = 1.0; dx = L / nx; h = 3.0 * dx; rho = 1.0; c = 10.0; eta = 5e-2; alpha = 0.2; a = 0.2

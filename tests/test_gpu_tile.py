@@ -38,7 +38,7 @@ def _run(name, nsteps, env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("name,nsteps", [("dam3d", 12), ("dam2d", 20), ("dam2d_morris", 20), ("heat3d", 25), ("heat2d_rhosum", 20)])
+@pytest.mark.parametrize("name,nsteps", [("dam3d", 12), ("dam2d", 20), ("dam2d_morris", 20), ("heat3d", 25), ("heat2d_rhosum", 20), ("gas3d", 10)])
 @pytest.mark.parametrize("variant", [{}, {"B200_TILE_NOUNI": "1"}, {"B200_TILE_SPLIT": "1"}, {"B200_TILE_SPLIT": "4"}])
 def test_tile_path_equals_row_path(name, nsteps, variant):
     a, na, ca = _run(name, nsteps, dict(variant))
