@@ -62,8 +62,12 @@ __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double
   }
 }
 // far rows must be scanned once 2*dmax >= margin  (b200_neigh.cuh k_build)
-__global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, int *scan_far)
-{ *scan_far = 4.0 * __longlong_as_double((long long)*dmaxsq) >= 0.99 * marginsq; }
+// (tile rows: a mid zone between cut + margin/4 and cut + margin is scanned once 2*dmax >= margin/4; flag at scan_far[2])
+__global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, double midmarginsq, int *scan_far)
+{
+  const double d = 4.0 * __longlong_as_double((long long)*dmaxsq);
+  scan_far[0] = d >= 0.99 * marginsq; scan_far[2] = d >= 0.99 * midmarginsq;
+}
 
 // (comm->reverse_comm runs before this kernel: b200_comm.cuh) modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
 // (fix_meso.cpp:144-180, fix_meso_stationary.cpp:96-112).  The three stages can be run fused (one

@@ -47,7 +47,7 @@ struct PcRow {
     if (a.tiled) {
       const size_t rbase = (size_t)(i >> 5) * a.ngrp * 32 + (i & 31);
       tn = (const unsigned short *)((const uint4 *)a.nbr + rbase); tf = (const unsigned short *)((const uint4 *)a.far + rbase);
-      nin = ((a.numneigh[i] + 7) >> 3) * 8; nout = 0; nfar = ((a.numfar[i] + 7) >> 3) * 8;
+      nin = ((a.numneigh[i] + 7) >> 3) * 8; nout = (((a.numfar[i] >> 16) + 7) >> 3) * 8; nfar = (((a.numfar[i] & 0xffff) + 7) >> 3) * 8;   // nout: the mid zone, stored from the back of the far row
       D = a.tiles + a.rowtile[i];
     } else {
       int c = a.numneigh[i]; nin = c & 0xffff; nout = c >> 16; nfar = a.numfar[i];
@@ -59,8 +59,10 @@ struct PcRow {
   __device__ __forceinline__ bool get(int k, int &j, int &tj) const
   {
     if (a.tiled) {
-      const unsigned short *q = k < nin ? tn : tf; if (k >= nin) k -= nin;
-      unsigned ent = q[(size_t)(k >> 3) * 256 + (k & 7)];
+      unsigned ent;
+      if (k < nin) ent = tn[(size_t)(k >> 3) * 256 + (k & 7)];
+      else if (k < nin + nout) { k -= nin; ent = tf[(size_t)(a.ngrp - 1 - (k >> 3)) * 256 + (k & 7)]; }
+      else { k -= nin + nout; ent = tf[(size_t)(k >> 3) * 256 + (k & 7)]; }
       if (!ent) return false;
       tj = ent >> TILE_SLOT_BITS; j = tile_slot_src(*D, ent & TMP_SLOT_MASK, nlocal, a.gorder);
       return true;

@@ -103,7 +103,7 @@ struct b200_sph {
   double mass[MAXT1] = {0};
   double skin = 0.3, cutneighmax = 0, triggersq = 0;
   int every = 1, delay = 10, check = 1, ago = 0;
-  double h_cutneighsq[MAXTT] = {0}, h_farsq[MAXTT] = {0};
+  double h_cutneighsq[MAXTT] = {0}, h_farsq[MAXTT] = {0}, h_midsq[MAXTT] = {0};
   DevBuf<double> d_cutneighsq;
   double dt = 0, ftm2v = 1; long long ntimestep = 0;
   int npair = 0; PairTab h_tab[MAXPAIR]; PairTab *d_tab[MAXPAIR] = {nullptr};
@@ -130,7 +130,7 @@ struct b200_sph {
   DevBuf<double> xhold, stage_d, d_mass;
   DevBuf<int> stage_i;
   DevBuf<unsigned> nbr, far; DevBuf<int> numneigh, numfar; int stride = 32;
-  DevBuf<double> d_prunesq, d_farsq; double far_margin = 0.0;
+  DevBuf<double> d_prunesq, d_farsq, d_midsq; double far_margin = 0.0, mid_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   int h_tflags2[4] = {0, 0, 0, 0};
@@ -491,14 +491,14 @@ static bool tile_rows(b200_sph *h)
     TileBuildArgs B{};
     B.g = g; B.nlocal = nl; B.ngrp = ngrp; B.cap = h->tile_cap;
     B.xt = h->C().xt.p; B.gorder = h->gorder.p; B.cso = h->cso.p; B.csg = h->csg.p;
-    B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p;
+    B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p; B.midsq = h->d_midsq.p;
     B.tiles = h->tiles.p; B.ntiles = h->d_tflags; B.counter = h->d_tflags + 4;
     B.near = (uint4 *)h->nbr.p; B.far = (uint4 *)h->far.p; B.numneigh = h->numneigh.p; B.numfar = h->numfar.p; B.maxcount = h->d_flags;
     B.orig = h->C().orig.p; B.rowtile = mp ? h->rowtile.p : nullptr;
     // one cutoff for every type pair (the common deck) -> scalar thresholds in the fp32 phase
-    B.uni = 1; B.cutsq_u = h->h_cutneighsq[1 * MAXT1 + 1]; B.farsq_u = h->h_farsq[1 * MAXT1 + 1];
+    B.uni = 1; B.cutsq_u = h->h_cutneighsq[1 * MAXT1 + 1]; B.farsq_u = h->h_farsq[1 * MAXT1 + 1]; B.midsq_u = h->h_midsq[1 * MAXT1 + 1];
     for (int i = 1; i <= h->ntypes; i++) for (int j = 1; j <= h->ntypes; j++)
-      if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u) B.uni = 0;
+      if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u || h->h_midsq[i * MAXT1 + j] != B.midsq_u) B.uni = 0;
     size_t bsm = (size_t)(mp ? 17 : 13) * (((h->tile_cap + 3) & ~3) + 4);
     for (int set = 0; set < (mp ? 2 : 1); set++) {
       if (set) { B.tiles = h->gtiles.p; B.ntiles = h->d_tflags + 8; }
@@ -603,7 +603,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   h->tend();
   h->rows_tiled = h->tile_on;
   CK(cudaMemsetAsync(h->d_dmaxsq, 0, sizeof(unsigned long long), h->st));
-  CK(cudaMemsetAsync(h->d_scan_far, 0, sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->d_scan_far, 0, 3 * sizeof(int), h->st));
   h->ago = 0; h->nbuilds++;
 }
 
@@ -638,6 +638,13 @@ static void build_plan(b200_sph *h)
   double fsq[MAXTT];
   h->far_margin = h->skin > 0.0 ? 0.25 * h->skin : 0.0;
   for (int k = 0; k < MAXTT; k++) fsq[k] = (h->far_margin > 0.0 && psq[k] >= 0.0) ? (sqrt(psq[k]) + h->far_margin) * (sqrt(psq[k]) + h->far_margin) : 1e300;
+  // tile rows: a mid zone from cut + skin/16 to cut + skin/4 (b200_tile.cuh)
+  double msq[MAXTT];
+  h->mid_margin = 0.25 * h->far_margin;
+  for (int k = 0; k < MAXTT; k++) msq[k] = (h->mid_margin > 0.0 && psq[k] >= 0.0) ? (sqrt(psq[k]) + h->mid_margin) * (sqrt(psq[k]) + h->mid_margin) : 1e300;
+  memcpy(h->h_midsq, msq, sizeof msq);
+  h->d_midsq.ensure(MAXTT);
+  CK(cudaMemcpyAsync(h->d_midsq.p, msq, sizeof msq, cudaMemcpyHostToDevice, h->st));
   h->d_prunesq.ensure(MAXTT); h->d_farsq.ensure(MAXTT);
   memcpy(h->h_farsq, fsq, sizeof fsq);
   CK(cudaMemcpyAsync(h->d_farsq.p, fsq, sizeof fsq, cudaMemcpyHostToDevice, h->st));
@@ -1025,7 +1032,7 @@ static void initial_integrate(b200_sph *h)
   if (track) {
     // ghosts move with their owners on other ranks: the displacement bound must be global (bit patterns of non-negative doubles order like uint64)
     if (h->world > 1) NCK(g_nccl.AllReduce(h->d_dmaxsq, h->d_dmaxsq, 1, ncclUint64, ncclMax, h->nccl, h->st));
-    LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->d_scan_far);
+    LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->d_scan_far);
   }
   h->tend();
 }
@@ -1248,7 +1255,7 @@ int b200_destroy(b200_sph *h)
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state);
-  h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); cudaFree(h->d_dmaxsq); h->gimage.release();
+  h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); h->d_midsq.release(); cudaFree(h->d_dmaxsq); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
   h->sendbuf.release(); h->recvbuf.release(); for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
   if (h->nccl) g_nccl.CommDestroy(h->nccl);
@@ -1531,7 +1538,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   std::vector<int> cfar(n);
   CK(cudaMemcpy(cfar.data(), h->numfar.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   if (h->rows_tiled) {        // slot lists of the tile path -> particle indices on the device, then as below
-    for (int s = 0; s < n; s++) numneigh[orig[s]] = cnt[s] + cfar[s];
+    for (int s = 0; s < n; s++) { cfar[s] = (cfar[s] & 0xffff) + (cfar[s] >> 16); numneigh[orig[s]] = cnt[s] + cfar[s]; }   // far + mid zone
     if (!jtag) return 0;
     long long tot = 0;
     std::vector<long long> off(n + 1);

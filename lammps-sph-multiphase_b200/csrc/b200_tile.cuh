@@ -136,9 +136,9 @@ __global__ void k_tile_plan(TilePlanArgs A)
 // ----------------------------------------------------------------- build ----
 struct TileBuildArgs {
   Geom g; int nlocal, ngrp, cap, uni;      // ngrp = groups of 8 entries per row; cap = slots the shared-memory staging holds
-  double cutsq_u, farsq_u;                 // uni: the one cutneighsq / far threshold of every type pair
+  double cutsq_u, farsq_u, midsq_u;        // uni: the one cutneighsq / far / mid threshold of every type pair
   const double4 *xt; const int *gorder; const int *cso, *csg;
-  const double *cutneighsq, *farsq;
+  const double *cutneighsq, *farsq, *midsq;
   const TileDesc *tiles; const int *ntiles; int *counter;
   uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
   const int *orig; int *rowtile;           // multiphase: LAMMPS local indices (half-list ownership); tile of every owned row (fix phase_change)
@@ -157,6 +157,19 @@ struct RowWriter {
     n++;
   }
   __device__ __forceinline__ void finish(uint4 *base, int ngrp) { if ((n & 7) && (n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; }
+};
+// the same from the back of the row: entry k at element 7 - (k & 7) of group ngrp - 1 - (k >> 3)  (the mid zone shares the far array)
+struct RowWriterBack {
+  uint4 acc; int n;
+  __device__ __forceinline__ RowWriterBack() : acc(make_uint4(0, 0, 0, 0)), n(0) {}
+  __device__ __forceinline__ void push(unsigned ent, uint4 *base, int ngrp)
+  {
+    const int e = 7 - (n & 7); const unsigned v = ent << ((e & 1) * 16); const int w = e >> 1;
+    acc.x |= w == 0 ? v : 0u; acc.y |= w == 1 ? v : 0u; acc.z |= w == 2 ? v : 0u; acc.w |= w == 3 ? v : 0u;
+    if ((n & 7) == 7) { const int g = ngrp - 1 - (n >> 3); if (g >= 0) base[(size_t)g * 32] = acc; acc = make_uint4(0, 0, 0, 0); }
+    n++;
+  }
+  __device__ __forceinline__ void finish(uint4 *base, int ngrp) { const int g = ngrp - 1 - (n >> 3); if ((n & 7) && g >= 0) base[(size_t)g * 32] = acc; }
 };
 
 // Near rows are written in a bank-aware order.  The stage kernels read a neighbor's record parts with 128-bit LDS, served per
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
   __shared__ TileDesc D;
   __shared__ int s_tile, s_item;
   __shared__ unsigned s_emax;
-  __shared__ float s_thr[MAXTT][4];                            // non-uniform cutoffs: far_lo, far_hi, cut_lo, cut_hi per type pair
+  __shared__ float s_thr[MAXTT][6];                            // non-uniform cutoffs: far_lo, far_hi, cut_lo, cut_hi, mid_lo, mid_hi per type pair
   const int tid = threadIdx.x, lane = tid & 31;
   const Geom &g = A.g;
   const int ntiles = *A.ntiles;
@@ -299,11 +312,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
       double err = 2.4e-7 * (3.4642 * r * (2.0 * E + r) + 4.0 * r * r) + 1e-37;      // 2^-22: twice the bound
       lo = __double2float_rd(thr - err); hi = __double2float_ru(thr + err);
     };
-    float far_lo, far_hi, cut_lo, cut_hi;
-    if (UNI) { band(A.farsq_u, far_lo, far_hi); band(A.cutsq_u, cut_lo, cut_hi); }
+    float far_lo, far_hi, cut_lo, cut_hi, mid_lo, mid_hi;
+    if (UNI) { band(A.farsq_u, far_lo, far_hi); band(A.cutsq_u, cut_lo, cut_hi); band(A.midsq_u, mid_lo, mid_hi); }
     else {
-      band(g.cutneighmaxsq, cut_lo, cut_hi); far_lo = far_hi = 0.f;
-      for (int k = tid; k < MAXTT; k += TILE_BUILD_NT) { band(fmin(A.farsq[k], 1e30), s_thr[k][0], s_thr[k][1]); band(A.cutneighsq[k], s_thr[k][2], s_thr[k][3]); }
+      band(g.cutneighmaxsq, cut_lo, cut_hi); far_lo = far_hi = mid_lo = mid_hi = 0.f;
+      for (int k = tid; k < MAXTT; k += TILE_BUILD_NT) {
+        band(fmin(A.farsq[k], 1e30), s_thr[k][0], s_thr[k][1]); band(A.cutneighsq[k], s_thr[k][2], s_thr[k][3]); band(fmin(A.midsq[k], 1e30), s_thr[k][4], s_thr[k][5]);
+      }
       __syncthreads();
     }
     // work items: (cell of the tile, chunk of 32 of its rows); item -> warp round robin
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
         }
         const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
         uint4 *nrow = A.near + rbase, *frow = A.far + rbase;
-        NearWriter wn; RowWriter wf;
+        NearWriter wn; RowWriter wf; RowWriterBack wm;
         unsigned short *nrow16 = (unsigned short *)nrow;
         const int q = (row - D.row0) & 7, stride = A.ngrp * 8;
 
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
             // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
             // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
             // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
-            unsigned in = 0, mb = 0, fr = 0; int nq = 0;
+            unsigned in = 0, mb = 0, fr = 0, md = 0; int nq = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
@@ -371,13 +386,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
                 const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
                 mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
-                if (UNI) fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1);      // 1 = NOT surely far
+                if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
               }
               nq = k + 1;
               if (bj + 4 * k + 4 >= s1) break;
             }
             // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
-            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq));
+            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
             // only the slots of [s0, s1), and never the row particle itself
             unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
             if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
@@ -395,19 +410,26 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
                 const float rsq = dx * dx + dy * dy + dz * dz;
                 const float *th = s_thr[ti * MAXT1 + ty[slot]];
                 if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
-                else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : 1;    // surely inside: far row only if surely beyond the far threshold
+                else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
               }
               if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
               if (cls) in |= 1u << idx;
               if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
+              if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
             }
-            // phase B: entries straight from the masks
-            unsigned nearm = in & ~fr, farm = in & fr;
+            // phase B: entries straight from the masks (one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin)
+            unsigned nearm = in & ~fr & ~md, midm = in & ~fr & md, farm = in & fr;
             while (nearm) {
               const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
               const int slot = bj + idx;
               unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
               if (flags(slot, ent)) wn.push(ent, q, nrow16, stride);
+            }
+            while (midm) {
+              const int idx = __ffs((int)midm) - 1; midm &= midm - 1;
+              const int slot = bj + idx;
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wm.push(ent, frow, A.ngrp);
             }
             while (farm) {
               const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
@@ -429,10 +451,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
         }
         if (valid) {
           const int ext = wn.finish(q, nrow16, stride);
-          wf.finish(frow, A.ngrp);
-          A.numneigh[row] = wn.n; A.numfar[row] = wf.n;
+          wf.finish(frow, A.ngrp); wm.finish(frow, A.ngrp);
+          A.numneigh[row] = wn.n; A.numfar[row] = wf.n | (wm.n << 16);
           if (A.rowtile && !gt) A.rowtile[row] = t;
-          atomicMax(A.maxcount, max(ext, wf.n));
+          atomicMax(A.maxcount, max(ext, ((wf.n + 7) & ~7) + ((wm.n + 7) & ~7)));     // far groups from the front and mid groups from the back must not meet
         }
         if (DYN) { if (lane == 0) mine = atomicAdd(&s_item, 1); mine = __shfl_sync(FULLMASK, mine, 0); }
         else mine += NT / 32;
@@ -459,11 +481,11 @@ __global__ void k_tile_export(TileExportArgs A)
     for (int rt = threadIdx.x; rt < D.nrows; rt += blockDim.x) {
       int row = D.row0 + rt, nn = A.numneigh[row], nf = A.numfar[row], o = 0;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
-      for (int pass = 0; pass < 2; pass++) {
+      for (int pass = 0; pass < 3; pass++) {           // near | far | mid (from the back of the far row)
         const unsigned short *p = (const unsigned short *)((pass ? A.far : A.near) + rbase);
-        int n = ((pass ? nf : nn) + 7) & ~7;
+        int n = ((pass == 0 ? nn : (pass == 1 ? (nf & 0xffff) : (nf >> 16))) + 7) & ~7;
         for (int k = 0; k < n; k++) {
-          int ent = p[(size_t)(k >> 3) * 32 * 8 + (k & 7)];
+          int ent = pass == 2 ? p[(size_t)(A.ngrp - 1 - (k >> 3)) * 32 * 8 + (k & 7)] : p[(size_t)(k >> 3) * 32 * 8 + (k & 7)];
           if (!ent) continue;
           int slot = ent & A.slot_mask;
           int s = 0;
@@ -668,7 +690,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
   const PairTab &T = S.T[0];
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
-  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -683,14 +705,17 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
       const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double acc = 0.0;
-      for (int pass = 0; pass < 1 + scan_far; pass++) {
-        const uint4 *lp = (pass ? A.far : A.near) + rbase;
-        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+      for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
+        if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
+        const int nf = (pass && valid) ? A.numfar[row] : 0;
+        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const ptrdiff_t dir = pass == 1 ? -32 : 32;
+        const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = En;
-          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (size_t)(gi + SPLIT) * 32);     // next group in flight while this one is evaluated
+          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -751,7 +776,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_vci = -UF.visc * UF.h;
   const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
   const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
-  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<(1 << NPARTS) - 1, NK, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -773,14 +798,17 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
       double u_drho = 0, u_de = 0, u_deh = 0;                                 // uniform body: raw sums, scaled after the loop
-      for (int pass = 0; pass < 1 + scan_far; pass++) {
-        const uint4 *lp = (pass ? A.far : A.near) + rbase;
-        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+      for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
+        if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
+        const int nf = (pass && valid) ? A.numfar[row] : 0;
+        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const ptrdiff_t dir = pass == 1 ? -32 : 32;
+        const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = En;
-          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (size_t)(gi + SPLIT) * 32);     // next group in flight while this one is evaluated
+          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -968,7 +996,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
   const PairTab &T = S.T[0];
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
-  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -985,14 +1013,17 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
       const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double acc = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
-      for (int pass = 0; pass < 1 + scan_far; pass++) {
-        const uint4 *lp = (pass ? A.far : A.near) + rbase;
-        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+      for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
+        if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
+        const int nf = (pass && valid) ? A.numfar[row] : 0;
+        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const ptrdiff_t dir = pass == 1 ? -32 : 32;
+        const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
-          if (gi + split < ng) En = ldg_nc_u4(lp + (size_t)(gi + split) * 32);
+          if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -1067,7 +1098,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
   const PairTab *T = S.T;
   auto part = [&](int p) { return S.part + (size_t)MP::idx(p) * A.cap; };
   const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7);
-  const int ntiles = *A.ntiles, scan_far = *A.scan_far;
+  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   const size_t ps = A.pstride;
   TileLoop<MP::mask, NK, NT> L(A, S, ntiles);
   L.start();
@@ -1094,14 +1125,17 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
       for (int t = 0; t < NK; t++) rmask[t] = (unsigned)(A.uni[t].mapmask >> (ti * 8)) & 0xffu;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, ade = 0;
-      for (int pass = 0; pass < 1 + scan_far; pass++) {
-        const uint4 *lp = (pass ? A.far : A.near) + rbase;
-        const int nn = valid ? (pass ? A.numfar[row] : A.numneigh[row]) : 0, ng = (nn + 7) >> 3;
+      for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
+        if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
+        const int nf = (pass && valid) ? A.numfar[row] : 0;
+        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const ptrdiff_t dir = pass == 1 ? -32 : 32;
+        const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + (size_t)sub * 32);
+        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
-          if (gi + split < ng) En = ldg_nc_u4(lp + (size_t)(gi + split) * 32);
+          if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll 4
           for (int e = 0; e < 8; e++) {
