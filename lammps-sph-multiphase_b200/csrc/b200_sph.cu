@@ -133,7 +133,6 @@ struct b200_sph {
   DevBuf<double> d_prunesq, d_farsq, d_midsq; double far_margin = 0.0, mid_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
-  int h_tflags2[4] = {0, 0, 0, 0};
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
@@ -475,12 +474,12 @@ static bool tile_rows(b200_sph *h)
     TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
     LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, G);
   }
-  CK(cudaMemcpyAsync(h->h_flags + 10, h->d_tflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaMemcpyAsync(h->h_tflags2, h->d_tflags + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  int *hf = h->h_flags + 16;                       // pinned: [0..3] owned-row tiles, [8..11] ghost-row tiles
+  CK(cudaMemcpyAsync(hf, h->d_tflags, 12 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  if (h->h_flags[12] || h->h_tflags2[2]) return false;
-  h->ntiles = h->h_flags[10]; h->ngtiles = h->h_tflags2[0];
-  h->tile_cap = std::max(2, (std::max(h->h_flags[11], h->h_tflags2[1]) + 1) & ~1);
+  if (hf[2] || hf[10]) return false;
+  h->ntiles = hf[0]; h->ngtiles = hf[8];
+  h->tile_cap = std::max(2, (std::max(hf[1], hf[9]) + 1) & ~1);
   const int nrows = mp ? na : nl;
   if (mp) h->rowtile.ensure(nl + 1);
   for (int attempt = 0; attempt < 8; attempt++) {
@@ -488,7 +487,9 @@ static bool tile_rows(b200_sph *h)
     int ngrp = h->stride / 8;
     h->nbr.ensure(rows32 * ngrp * 4); h->far.ensure(rows32 * ngrp * 4);
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->st));
+    CK(cudaMemsetAsync(h->d_flags + 11, 0, sizeof(int), h->st));
     TileBuildArgs B{};
+    B.maxn = h->d_flags + 11;
     B.g = g; B.nlocal = nl; B.ngrp = ngrp; B.cap = h->tile_cap;
     B.xt = h->C().xt.p; B.gorder = h->gorder.p; B.cso = h->cso.p; B.csg = h->csg.p;
     B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p; B.midsq = h->d_midsq.p;
@@ -511,10 +512,10 @@ static bool tile_rows(b200_sph *h)
 #undef BUILD_LAUNCH
     }
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->h_flags + 11, h->d_flags + 11, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     int mx = h->h_flags[0];
-    h->maxneigh = std::max<long long>(h->maxneigh, mx);
-    if (mx <= h->stride) break;
+    if (mx <= h->stride) { h->maxneigh = std::max<long long>(h->maxneigh, h->h_flags[11]); break; }
     h->stride = ((int)(mx * 1.2) + 8 + 31) / 32 * 32;
     if (attempt == 7) throw std::string("b200: neighbor row overflow");
   }
@@ -1244,7 +1245,7 @@ int b200_create(b200_sph **out, int device)
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   h->nsm = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
-  CK(cudaMallocHost(&h->h_flags, 16 * sizeof(int)));
+  CK(cudaMallocHost(&h->h_flags, 32 * sizeof(int)));
   memset(&h->fl, 0, sizeof h->fl);
   *out = h;
   API_END

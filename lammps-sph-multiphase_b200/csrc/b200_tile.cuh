@@ -141,6 +141,7 @@ struct TileBuildArgs {
   const double *cutneighsq, *farsq, *midsq;
   const TileDesc *tiles; const int *ntiles; int *counter;
   uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
+  int *maxn;                               // longest row (entries), for the counters
   const int *orig; int *rowtile;           // multiphase: LAMMPS local indices (half-list ownership); tile of every owned row (fix phase_change)
 };
 
@@ -454,7 +455,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
           wf.finish(frow, A.ngrp); wm.finish(frow, A.ngrp);
           A.numneigh[row] = wn.n; A.numfar[row] = wf.n | (wm.n << 16);
           if (A.rowtile && !gt) A.rowtile[row] = t;
-          atomicMax(A.maxcount, max(ext, ((wf.n + 7) & ~7) + ((wm.n + 7) & ~7)));     // far groups from the front and mid groups from the back must not meet
+          atomicMax(A.maxcount, max(ext, ((wf.n + 7) & ~7) + ((wm.n + 7) & ~7)));
+          atomicMax(A.maxn, wn.n + wf.n + wm.n);     // far groups from the front and mid groups from the back must not meet
         }
         if (DYN) { if (lane == 0) mine = atomicAdd(&s_item, 1); mine = __shfl_sync(FULLMASK, mine, 0); }
         else mine += NT / 32;
