@@ -168,7 +168,7 @@ class ClockSampler:
             return
         fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
         os.close(fd)
-        self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+        self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                   stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
     def stop(self):
@@ -269,7 +269,9 @@ def main():
     # ---- device-resident timed region: K Verlet steps, CUDA events on the launching (default) stream ----
     sim.set_timing(True)
     c0 = sim.counters()
-    clocks = ClockSampler(local); clocks.start()
+    clocks = ClockSampler(local)
+    if rank == 0:          # one sampler per job: concurrent nvidia-smi pollers contend for the driver lock and stall the ranks' API calls
+        clocks.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
