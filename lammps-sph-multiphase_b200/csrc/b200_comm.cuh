@@ -80,7 +80,10 @@ __global__ void k_pack_forward(int n, const int *list, CommArrays a, int dim, do
   b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
   b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[j];
 }
-__global__ void k_unpack_forward(int n, int first, CommArrays a, const double *buf, int multiphase, int ghost_velocity)
+// xhold / dmaxsq (track): the ghosts' displacement since the build enters the same bound as the owned atoms' (k_initial_integrate),
+// so the far / mid zone flags need no all-reduce: every candidate of this rank's rows is an owned atom or one of its ghosts
+__global__ void k_unpack_forward(int n, int first, CommArrays a, const double *buf, int multiphase, int ghost_velocity,
+                                 const double *xhold, unsigned long long *dmaxsq)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -89,6 +92,11 @@ __global__ void k_unpack_forward(int n, int first, CommArrays a, const double *b
   double4 x = a.xt[i], v = a.vm[i];
   x.x = b[0]; x.y = b[1]; x.z = b[2];
   a.xt[i] = x;
+  if (xhold) {
+    double dx = x.x - xhold[3 * i], dy = x.y - xhold[3 * i + 1], dz = x.z - xhold[3 * i + 2];
+    unsigned long long bits = (unsigned long long)__double_as_longlong(dx * dx + dy * dy + dz * dz);
+    if (bits > *(volatile unsigned long long *)dmaxsq) atomicMax(dmaxsq, bits);
+  }
   a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
   if (ghost_velocity) { v.x = b[3]; v.y = b[4]; v.z = b[5]; }
   if (multiphase) { v.w = b[13]; a.cgm[i] = make_double4(b[10], b[11], b[12], b[13]); }

@@ -579,7 +579,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->csg.p, h->gperm.p, h->gorder.p, h->gkey.p);
   }
   h->ensure_cap(nl + ng, true);
-  if ((h->check || h->far_margin > 0.0) && nl) { h->xhold.ensure((size_t)3 * nl); LAUNCH(h, k_store_xhold, nblk(nl, B), B, nl, h->C().xt.p, h->xhold.p); }
+  if ((h->check || h->far_margin > 0.0) && nl) { h->xhold.ensure((size_t)3 * (nl + ng)); LAUNCH(h, k_store_xhold, nblk(nl + ng, B), B, nl + ng, h->C().xt.p, h->xhold.p); }
   h->tend();
   // 3. rows
   h->tbegin(T_NEIGH_BUILD);
@@ -1030,11 +1030,6 @@ static void initial_integrate(b200_sph *h)
   int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
          h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq);
-  if (track) {
-    // ghosts move with their owners on other ranks: the displacement bound must be global (bit patterns of non-negative doubles order like uint64)
-    if (h->world > 1) NCK(g_nccl.AllReduce(h->d_dmaxsq, h->d_dmaxsq, 1, ncclUint64, ncclMax, h->nccl, h->st));
-    LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->d_scan_far);
-  }
   h->tend();
 }
 static void forward_comm(b200_sph *h)
@@ -1044,8 +1039,16 @@ static void forward_comm(b200_sph *h)
   h->tbegin(T_COMM);
   comm_forward_generic(h, NB_FORWARD,
     [&](Swap &s) { LAUNCH(h, k_pack_forward, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), s.dim, s.shift, h->sendbuf.p); },
-    [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_forward, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), buf, h->multiphase, h->ghost_velocity); });
+    [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_forward, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), buf, h->multiphase, h->ghost_velocity,
+                                       h->far_margin > 0.0 ? h->xhold.p : (const double *)nullptr, h->d_dmaxsq); });
   h->tend();
+}
+// far / mid rows must be scanned once 2 * dmax reaches their margin; dmax = largest displacement since the build over the owned atoms
+// (k_initial_integrate) and the ghosts (k_unpack_forward): every candidate of a row is one of the two, so the bound is rank-local
+static void far_flags(b200_sph *h)
+{
+  if (h->far_margin > 0.0 && h->nlocal)
+    LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->d_scan_far);
 }
 // Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
 static int neigh_decide(b200_sph *h)
@@ -1152,7 +1155,7 @@ static void do_run(b200_sph *h, int n)
   for (int s = 0; s < n; s++) {
     h->ntimestep++;
     initial_integrate(h);
-    if (neigh_decide(h)) reneighbor(h); else forward_comm(h);
+    if (neigh_decide(h)) reneighbor(h); else { forward_comm(h); far_flags(h); }
     force_clear(h);
     pair_compute_all(h);
     post_final(h, 1, 1, 1);
@@ -1507,7 +1510,7 @@ int b200_run(b200_sph *h, int nsteps) { API_BEGIN CK(cudaSetDevice(h->device)); 
 int b200_initial_integrate(b200_sph *h) { API_BEGIN initial_integrate(h); API_END }
 int b200_final_integrate(b200_sph *h) { API_BEGIN post_final(h, 0, 0, 1); API_END }
 int b200_neigh_decide(b200_sph *h, int *rebuild) { API_BEGIN *rebuild = neigh_decide(h); API_END }
-int b200_forward_comm(b200_sph *h) { API_BEGIN forward_comm(h); API_END }
+int b200_forward_comm(b200_sph *h) { API_BEGIN forward_comm(h); far_flags(h); API_END }
 int b200_reneighbor(b200_sph *h) { API_BEGIN if (!h->geom_ready) setup_geometry(h); if (h->plan.empty()) build_plan(h); reneighbor(h); API_END }
 int b200_force_clear(b200_sph *h) { API_BEGIN force_clear(h); API_END }
 int b200_pair_compute(b200_sph *h, int slot)
