@@ -692,6 +692,7 @@ static void build_plan(b200_sph *h)
   h->tile_on = ok; h->tile_nparts = np; h->tile_nk = nk;
   long long capb = (long long)TILE_SMEM_MAX - nk * (long long)sizeof(PairTab) - 2 * (long long)sizeof(TileDesc) - 64;
   h->tile_slotcap = (int)std::min<long long>(std::min<long long>(h->multiphase ? TMP_MAXSLOTS : TILE_MAXSLOTS, capb / (16 * np)), TILE_MAXSLOTS) & ~1;
+  if (const char *e = getenv("B200_TILE_SLOTCAP")) h->tile_slotcap = std::max(2, std::min(h->tile_slotcap, atoi(e)) & ~1);   // tests: force small tiles / the row-path fall-back
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
   if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
 }

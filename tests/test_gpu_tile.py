@@ -65,6 +65,19 @@ def test_multiphase_tile_path_equals_row_path(name, nsteps, variant):
         assert harness.relerr(a[k], b[k]) < 1e-10, (name, k, harness.relerr(a[k], b[k]))
 
 
+@pytest.mark.parametrize("name,nsteps,cap", [("dam3d", 12, 900), ("dam3d", 12, 64), ("droplet3d", 10, 400), ("droplet3d", 10, 64), ("heat2d_rhosum", 20, 40)])
+def test_small_tiles_and_fallback(name, nsteps, cap):
+    """a shared-memory budget that allows only one or two cells per tile, or (cap 64 / 40) not even one cell:
+    the plan must cut smaller tiles, or hand the deck to the row path, without changing the results"""
+    a, na, ca = _run(name, nsteps, {"B200_TILE_SLOTCAP": str(cap)})
+    b, nb, cb = _run(name, nsteps, {})
+    assert ca["builds"] == cb["builds"]
+    for p, q in zip(na, nb):
+        assert np.array_equal(p, q), "neighbor lists differ"
+    for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de"):
+        assert harness.relerr(a[k], b[k]) < 1e-10, (name, k, harness.relerr(a[k], b[k]))
+
+
 def test_tile_path_is_the_one_that_runs():
     """single-phase decks must take the tile kernels (the launch counter differs from the row path's)"""
     a, _, ca = _run("dam3d", 5, {})
