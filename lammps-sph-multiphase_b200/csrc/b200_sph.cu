@@ -138,6 +138,9 @@ struct b200_sph {
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
   DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
   int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
+  // halo overlap (single-phase tile path): tiles [0, nint) neither read ghosts nor feed a send list and run while the halo flies
+  int nint = 0; bool comm_pending = false, no_overlap = getenv("B200_OVERLAP") == nullptr;     // measured slower than the plain order at C2 scale: opt-in
+  cudaStream_t st2 = 0; cudaEvent_t ev_main = 0, ev_comm = 0;
   int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter; [8..11] the same for the ghost-row tiles
   bool setup_done = false, geom_ready = false;
   // instrumentation
@@ -433,7 +436,7 @@ static int comm_exchange(b200_sph *h, int nslots)
 
 // ------------------------------------------------------------- tile path ----
 // persistent launch of a tile kernel: as many CTAs as fit on the device (or tiles), dynamic shared memory opted in once per kernel
-template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args, int ntiles = -1)
+template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args, int ntiles = -1, int reserve_sms = 0)
 {
   if (ntiles < 0) ntiles = h->ntiles;
   if (!ntiles) return;
@@ -451,7 +454,7 @@ template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const 
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp, nthreads, smem));
   if (occ < 1) throw std::string(name) + ": zero occupancy";
-  int grid = std::max(1, std::min(ntiles, h->nsm * occ));
+  int grid = std::max(1, std::min(ntiles, (h->nsm - reserve_sms) * occ));     // reserve_sms: leave room for the halo's NCCL / pack kernels
   CK(cudaMemsetAsync(h->d_tflags + 4, 0, sizeof(int), h->st));
   kern<<<grid, nthreads, smem, h->st>>>(args);
   post_launch(h, name);
@@ -467,18 +470,28 @@ static bool tile_rows(b200_sph *h)
   if (!nl) return true;
   h->tiles.ensure((size_t)g.ncells + 1);
   CK(cudaMemsetAsync(h->d_tflags, 0, 16 * sizeof(int), h->st));
-  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
+  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
+  bool classes = !mp && h->nswap > 0 && !h->no_overlap;
+  for (int k = 0; k < h->nswap; k++)       // the interior criterion of k_tile_plan needs cells at least one ghost cutoff wide
+    if (1.0 / g.cinv[h->swaps[k].dim] < g.cutghost) classes = false;
+  if (classes) {             // interior tiles first, then the boundary tiles (k_tile_plan)
+    for (int k = 0; k < h->nswap; k++) P.swapdim[h->swaps[k].dim] = 1;
+    P.want = 0;
+    LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
+    CK(cudaMemcpyAsync(h->d_tflags + 5, h->d_tflags, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+    P.want = 1;
+  }
   LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
   if (mp && h->nghost) {       // ghost rows: what the reference accumulates on ghost atoms (then reverse-communicates)
     h->gtiles.ensure((size_t)g.ncells + 1);
-    TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
+    TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
     LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, G);
   }
   int *hf = h->h_flags + 16;                       // pinned: [0..3] owned-row tiles, [8..11] ghost-row tiles
   CK(cudaMemcpyAsync(hf, h->d_tflags, 12 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   if (hf[2] || hf[10]) return false;
-  h->ntiles = hf[0]; h->ngtiles = hf[8];
+  h->ntiles = hf[0]; h->ngtiles = hf[8]; h->nint = classes ? hf[5] : 0;
   h->tile_cap = std::max(2, (std::max(hf[1], hf[9]) + 1) & ~1);
   const int nrows = mp ? na : nl;
   if (mp) h->rowtile.ensure(nl + 1);
@@ -493,7 +506,7 @@ static bool tile_rows(b200_sph *h)
     B.g = g; B.nlocal = nl; B.ngrp = ngrp; B.cap = h->tile_cap;
     B.xt = h->C().xt.p; B.gorder = h->gorder.p; B.cso = h->cso.p; B.csg = h->csg.p;
     B.cutneighsq = h->d_cutneighsq.p; B.farsq = h->d_farsq.p; B.midsq = h->d_midsq.p;
-    B.tiles = h->tiles.p; B.ntiles = h->d_tflags; B.counter = h->d_tflags + 4;
+    B.tiles = h->tiles.p; B.ntiles = h->ntiles; B.counter = h->d_tflags + 4;
     B.near = (uint4 *)h->nbr.p; B.far = (uint4 *)h->far.p; B.numneigh = h->numneigh.p; B.numfar = h->numfar.p; B.maxcount = h->d_flags;
     B.orig = h->C().orig.p; B.rowtile = mp ? h->rowtile.p : nullptr;
     // one cutoff for every type pair (the common deck) -> scalar thresholds in the fp32 phase
@@ -502,7 +515,7 @@ static bool tile_rows(b200_sph *h)
       if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u || h->h_midsq[i * MAXT1 + j] != B.midsq_u) B.uni = 0;
     size_t bsm = (size_t)(mp ? 17 : 13) * (((h->tile_cap + 3) & ~3) + 4);
     for (int set = 0; set < (mp ? 2 : 1); set++) {
-      if (set) { B.tiles = h->gtiles.p; B.ntiles = h->d_tflags + 8; }
+      if (set) { B.tiles = h->gtiles.p; B.ntiles = h->ngtiles; }
       int nt = set ? h->ngtiles : h->ntiles;
       const bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
 #define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
@@ -722,19 +735,54 @@ static TileArgs tile_args(b200_sph *h, int pstride)
   OwnedSet &c = h->C();
   A.nlocal = h->nlocal; A.ngrp = h->stride / 8; A.pstride = pstride; A.cap = h->tile_cap;
   A.rec = h->trec.p; A.near = (const uint4 *)h->nbr.p; A.far = (const uint4 *)h->far.p; A.numneigh = h->numneigh.p; A.numfar = h->numfar.p;
-  A.scan_far = h->d_scan_far; A.tiles = h->tiles.p; A.ntiles = h->d_tflags; A.counter = h->d_tflags + 4;
+  A.scan_far = h->d_scan_far; A.tiles = h->tiles.p; A.ntiles = h->ntiles; A.counter = h->d_tflags + 4;
   A.xt = c.xt.p; A.vr_out = c.vr.p; A.fd = c.fd.p; A.de = c.de.p;
   A.vm = c.vm.p; A.cg_out = c.cgm.p; A.gorder = h->gorder.p; A.dim = h->g.dim;
   return A;
 }
-static int tile_records(b200_sph *h, int nparts, int force, int epart, const PairTab *fluid)
+// which: 0 all records, 1 owned atoms only, 2 ghosts only (halo overlap: the ghosts' records wait for the halo)
+static int tile_records(b200_sph *h, int nparts, int force, int epart, const PairTab *fluid, int which = 0)
 {
   int na = h->nall(), pstride = (na + 7) & ~7;
   h->trec.ensure((size_t)pstride * nparts);
   OwnedSet &c = h->C();
-  TileRecArgs R{h->nlocal, na, pstride, force, epart, h->gorder.p, c.xt.p, c.vr.p, c.e.p, fluid, h->trec.p};
-  LAUNCH(h, k_tile_records, nblk(na, 256), 256, R);
+  int i0 = which == 2 ? h->nlocal : 0, i1 = which == 1 ? h->nlocal : na;
+  TileRecArgs R{h->nlocal, na, pstride, force, epart, i0, i1, h->gorder.p, c.xt.p, c.vr.p, c.e.p, fluid, h->trec.p};
+  if (i1 > i0) LAUNCH(h, k_tile_records, nblk(i1 - i0, 256), 256, R);
   return pstride;
+}
+// ---- halo overlap: the halo runs on a second stream between two events; the pair pass that follows evaluates the interior
+//      tiles first and only then waits for it (far_flags: the ghosts' displacement enters the zone flags after the wait)
+static void far_flags(b200_sph *h);
+static void halo_wait(b200_sph *h)
+{
+  if (!h->comm_pending) return;
+  CK(cudaStreamWaitEvent(h->st, h->ev_comm, 0));
+  h->comm_pending = false;
+  far_flags(h);
+}
+template <class F> static void halo_async(b200_sph *h, F comm)
+{
+  CK(cudaEventRecord(h->ev_main, h->st));
+  CK(cudaStreamWaitEvent(h->st2, h->ev_main, 0));
+  std::swap(h->st, h->st2);                 // every launch / NCCL call of `comm` goes to the halo stream
+  try { comm(); } catch (...) { std::swap(h->st, h->st2); throw; }
+  std::swap(h->st, h->st2);
+  CK(cudaEventRecord(h->ev_comm, h->st2));
+  h->comm_pending = true;
+}
+static bool overlap_ok(const b200_sph *h) { return h->rows_tiled && !h->multiphase && h->nint > 0 && !h->no_overlap && (h->nghost || h->world > 1); }
+// one pair pass over the tiles: all at once, or interior tiles | wait for the halo | ghost records | boundary tiles
+template <class Launch, class Rec> static void tile_pass(b200_sph *h, TileArgs &A, Launch launch, Rec records)
+{
+  if (!h->comm_pending) { A.pstride = records(0); A.rec = h->trec.p; A.tiles = h->tiles.p; A.ntiles = h->ntiles; launch(A, 0); return; }
+  A.pstride = records(1); A.rec = h->trec.p;
+  A.tiles = h->tiles.p; A.ntiles = h->nint;
+  launch(A, h->world > 1 ? 8 : 2);           // a few SMs stay free for the halo's kernels (NCCL send/recv, pack, unpack)
+  halo_wait(h);
+  records(2);
+  A.tiles = h->tiles.p + h->nint; A.ntiles = h->ntiles - h->nint;
+  launch(A, 0);
 }
 // constants of a sub-style whose coefficients do not depend on the type pair (TileUni); false if they do
 static bool tile_uni(const b200_sph *h, const PairTab &T, TileUni &U)
@@ -759,17 +807,17 @@ static bool tile_uni(const b200_sph *h, const PairTab &T, TileUni &U)
   }
   return ok;
 }
-template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A, bool uni)
+template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &A, bool uni, int reserve)
 {
   constexpr bool F = (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) != 0, H = (KINDS & K_HEAT) != 0;
   constexpr int NP = F ? (H ? 5 : 4) : 3, NK = (F ? 1 : 0) + (H ? 1 : 0);
   size_t smem = TileSmem<NP, NK>::bytes(h->tile_cap);
   if (h->tile_split == 1) {
-    if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true>, "k_tile_force", TILE_ROWS, smem, A);
-    else launch_tiles(h, k_tile_force<KINDS, 1, false>, "k_tile_force", TILE_ROWS, smem, A);
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
+    else launch_tiles(h, k_tile_force<KINDS, 1, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
   } else {
-    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true>, "k_tile_force", TILE_ROWS * 2, smem, A);
-    else launch_tiles(h, k_tile_force<KINDS, 2, false>, "k_tile_force", TILE_ROWS * 2, smem, A);
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+    else launch_tiles(h, k_tile_force<KINDS, 2, false>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
   }
 }
 static int tile_records_mp(b200_sph *h, int mode, const PairTab *fluid)
@@ -803,7 +851,7 @@ template <int KINDS> static void launch_tile_force_mp(b200_sph *h, TileArgs &A, 
   const bool d3 = h->g.dim == 3 || !(KINDS & K_SURF);
   for (int set = 0; set < 2; set++) {          // owned rows, then the ghost rows
     int nt = set ? h->ngtiles : h->ntiles;
-    if (set) { A.tiles = h->gtiles.p; A.ntiles = h->d_tflags + 8; }
+    if (set) { A.tiles = h->gtiles.p; A.ntiles = h->ngtiles; }
     if (d3) {
       if (gu) launch_tiles(h, k_tile_force_mp<KINDS, true, true>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
       else launch_tiles(h, k_tile_force_mp<KINDS, true, false>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
@@ -815,6 +863,7 @@ template <int KINDS> static void launch_tile_force_mp(b200_sph *h, TileArgs &A, 
 }
 static void run_pass_tile_mp(b200_sph *h, const Pass &p)
 {
+  halo_wait(h);
   if (p.type == 1 || p.type == 2) {
     const PairTab &T = h->h_tab[p.slots[0]];
     bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;
@@ -878,27 +927,34 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
     bool active = T.nstep != 0 && (h->ntimestep % T.nstep) == 0;     // pair_sph_rhosum.cpp:112-113
     h->tbegin(T_DENSITY);
     if (active) {
-      int pstride = tile_records(h, 2, 0, -1, nullptr);
-      TileArgs A = tile_args(h, pstride);
+      TileArgs A = tile_args(h, 0);
       A.tab[0] = h->d_tab[p.slots[0]];
       bool uni = tile_uni(h, T, A.uni[0]) && !h->tile_nouni;
       size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
       const int dsplit = getenv("B200_TILE_SPLIT") ? h->tile_split : 4;      // measured: 4 lanes per row (32 warps per SM) is fastest for the density pass
-      if (dsplit == 1) {
-        if (uni) launch_tiles(h, k_tile_rhosum<1, true>, "k_tile_rhosum", TILE_ROWS, smem, A);
-        else launch_tiles(h, k_tile_rhosum<1, false>, "k_tile_rhosum", TILE_ROWS, smem, A);
-      } else if (dsplit == 2) {
-        if (uni) launch_tiles(h, k_tile_rhosum<2, true>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
-        else launch_tiles(h, k_tile_rhosum<2, false>, "k_tile_rhosum", TILE_ROWS * 2, smem, A);
-      } else {
-        if (uni) launch_tiles(h, k_tile_rhosum<4, true>, "k_tile_rhosum", TILE_ROWS * 4, smem, A);
-        else launch_tiles(h, k_tile_rhosum<4, false>, "k_tile_rhosum", TILE_ROWS * 4, smem, A);
-      }
+      tile_pass(h, A,
+        [&](TileArgs &a, int reserve) {
+          if (dsplit == 1) {
+            if (uni) launch_tiles(h, k_tile_rhosum<1, true>, "k_tile_rhosum", TILE_ROWS, smem, a, a.ntiles, reserve);
+            else launch_tiles(h, k_tile_rhosum<1, false>, "k_tile_rhosum", TILE_ROWS, smem, a, a.ntiles, reserve);
+          } else if (dsplit == 2) {
+            if (uni) launch_tiles(h, k_tile_rhosum<2, true>, "k_tile_rhosum", TILE_ROWS * 2, smem, a, a.ntiles, reserve);
+            else launch_tiles(h, k_tile_rhosum<2, false>, "k_tile_rhosum", TILE_ROWS * 2, smem, a, a.ntiles, reserve);
+          } else {
+            if (uni) launch_tiles(h, k_tile_rhosum<4, true>, "k_tile_rhosum", TILE_ROWS * 4, smem, a, a.ntiles, reserve);
+            else launch_tiles(h, k_tile_rhosum<4, false>, "k_tile_rhosum", TILE_ROWS * 4, smem, a, a.ntiles, reserve);
+          }
+        },
+        [&](int which) { return tile_records(h, 2, 0, -1, nullptr, which); });
+    } else halo_wait(h);
+    if (h->nghost) {      // comm->forward_comm_pair (:203): the ghosts' new rho
+      auto rho_halo = [&]() {
+        comm_forward_generic(h, 1,
+          [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
+          [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
+      };
+      if (overlap_ok(h)) halo_async(h, rho_halo); else rho_halo();
     }
-    if (h->nghost)       // comm->forward_comm_pair (:203)
-      comm_forward_generic(h, 1,
-        [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
-        [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
     h->tend();
     return;
   }
@@ -909,25 +965,26 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
     if (kk & K_HEAT) { heat = h->d_tab[p.slots[s]]; hheat = &h->h_tab[p.slots[s]]; }
   }
   int nparts = fluid ? (heat ? 5 : 4) : 3;
-  h->tbegin(T_DERIVE);
-  int pstride = tile_records(h, nparts, fluid ? 1 : 0, heat ? (fluid ? 4 : 2) : -1, fluid);
-  h->tend();
-  TileArgs A = tile_args(h, pstride);
+  TileArgs A = tile_args(h, 0);
   int nk = 0;
   bool uni = !h->tile_nouni;
   if (fluid) { uni = tile_uni(h, *hfluid, A.uni[nk]) && uni; A.tab[nk++] = fluid; }
   if (heat) { uni = tile_uni(h, *hheat, A.uni[nk]) && uni; A.tab[nk++] = heat; }
   if (fluid && heat && (A.uni[0].mass != A.uni[1].mass)) uni = false;
   h->tbegin(T_FORCE);
-  switch (p.kinds) {
-  case K_TAIT: launch_tile_force<K_TAIT>(h, A, uni); break;
-  case K_MORRIS: launch_tile_force<K_MORRIS>(h, A, uni); break;
-  case K_HEAT: launch_tile_force<K_HEAT>(h, A, uni); break;
-  case K_IDEAL: launch_tile_force<K_IDEAL>(h, A, uni); break;
-  case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, A, uni); break;
-  case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, A, uni); break;
-  default: throw std::string("b200: no tile force kernel for this sub-style group");
-  }
+  tile_pass(h, A,
+    [&](TileArgs &a, int reserve) {
+      switch (p.kinds) {
+      case K_TAIT: launch_tile_force<K_TAIT>(h, a, uni, reserve); break;
+      case K_MORRIS: launch_tile_force<K_MORRIS>(h, a, uni, reserve); break;
+      case K_HEAT: launch_tile_force<K_HEAT>(h, a, uni, reserve); break;
+      case K_IDEAL: launch_tile_force<K_IDEAL>(h, a, uni, reserve); break;
+      case K_TAIT | K_HEAT: launch_tile_force<K_TAIT | K_HEAT>(h, a, uni, reserve); break;
+      case K_MORRIS | K_HEAT: launch_tile_force<K_MORRIS | K_HEAT>(h, a, uni, reserve); break;
+      default: throw std::string("b200: no tile force kernel for this sub-style group");
+      }
+    },
+    [&](int which) { return tile_records(h, nparts, fluid ? 1 : 0, heat ? (fluid ? 4 : 2) : -1, fluid, which); });
   h->tend();
 }
 
@@ -936,6 +993,7 @@ static void run_pass(b200_sph *h, const Pass &p)
   if (!h->nlocal) return;
   if (h->tile_on != h->rows_tiled) throw std::string("b200: the neighbor rows were built for another pair plan (call b200_setup / b200_reneighbor)");
   if (h->tile_on) { run_pass_tile(h, p); return; }
+  halo_wait(h);
   const int B = 256;
   if (p.type <= 2) {
     const PairTab &T = h->h_tab[p.slots[0]];
@@ -1014,6 +1072,7 @@ static void pair_compute_all(b200_sph *h) { for (const Pass &p : h->plan) run_pa
 static void post_final(b200_sph *h, int rev, int post, int fin)
 {
   const int B = 256;
+  halo_wait(h);
   h->tbegin(T_FINAL);
   if (rev && (h->nghost || h->world > 1) && (!h->tile_on || h->multiphase))      // the single-phase tile path puts nothing on ghosts (b200_tile.cuh)
     comm_reverse_generic(h, NB_REVERSE,
@@ -1156,7 +1215,9 @@ static void do_run(b200_sph *h, int n)
   for (int s = 0; s < n; s++) {
     h->ntimestep++;
     initial_integrate(h);
-    if (neigh_decide(h)) reneighbor(h); else { forward_comm(h); far_flags(h); }
+    if (neigh_decide(h)) reneighbor(h);
+    else if (overlap_ok(h)) { far_flags(h); halo_async(h, [&]() { forward_comm(h); }); }     // interior tiles start on the owned atoms' displacement bound
+    else { forward_comm(h); far_flags(h); }
     force_clear(h);
     pair_compute_all(h);
     post_final(h, 1, 1, 1);
@@ -1246,6 +1307,8 @@ int b200_create(b200_sph **out, int device)
   CK(cudaMalloc(&h->d_dmaxsq, sizeof(unsigned long long))); CK(cudaMemset(h->d_dmaxsq, 0, sizeof(unsigned long long)));
   h->d_scan_far = h->d_flags + 8;
   CK(cudaMalloc(&h->d_tflags, 16 * sizeof(int))); CK(cudaMemset(h->d_tflags, 0, 16 * sizeof(int)));
+  CK(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   h->nsm = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
@@ -1270,6 +1333,7 @@ int b200_destroy(b200_sph *h)
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
+  if (h->st2) cudaStreamDestroy(h->st2); if (h->ev_main) cudaEventDestroy(h->ev_main); if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   h->tiles.release(); h->gtiles.release(); h->rowtile.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
   return 0;
@@ -1553,7 +1617,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
     CK(cudaMemcpy(img.data(), h->gimage.p, (size_t)na * sizeof(int), cudaMemcpyDeviceToHost));
     int width = 2 * h->stride;
     DevBuf<int> out; out.ensure((size_t)n * width);
-    TileExportArgs X{n, h->stride / 8, width, h->multiphase ? (int)TMP_SLOT_MASK : (int)TILE_SLOT_MASK, h->gorder.p, h->tiles.p, h->d_tflags, (const uint4 *)h->nbr.p, (const uint4 *)h->far.p, h->numneigh.p, h->numfar.p, out.p};
+    TileExportArgs X{n, h->stride / 8, width, h->multiphase ? (int)TMP_SLOT_MASK : (int)TILE_SLOT_MASK, h->gorder.p, h->tiles.p, h->ntiles, (const uint4 *)h->nbr.p, (const uint4 *)h->far.p, h->numneigh.p, h->numfar.p, out.p};
     LAUNCH(h, k_tile_export, std::max(1, std::min(h->ntiles, 1024)), 128, X);
     std::vector<int> rows((size_t)n * width);
     CK(cudaStreamSynchronize(h->st));

@@ -58,6 +58,7 @@ struct TileDesc {
 // ------------------------------------------------------------------ plan ----
 struct TilePlanArgs {
   Geom g; int nlocal, rowcap, slotcap, ghostrows, shrink;   // ghostrows: plan the tiles of the ghost rows (multiphase styles); shrink: see k_tile_plan
+  int want, swapdim[3];          // want: -1 all tiles | 0 interior tiles only | 1 boundary tiles only (halo overlap); swapdim[d]: ghosts are exchanged along d
   const int *cso, *csg;
   TileDesc *tiles;
   int *flags;                    // [0] ntiles  [1] max slots  [2] a single cell does not fit  [3] max rows
@@ -93,11 +94,17 @@ __global__ void k_tile_plan(TilePlanArgs A)
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
     return v;
   };
+  // Interior tiles (halo overlap): ghosts live in the first / last cell of a swapped dimension and the atoms a halo sends in the
+  // first / last two (cell edge >= ghost cutoff), so a tile whose own cells keep to [2, nc-3] there neither reads a ghost nor owns
+  // an atom of a send list: it can run while the halo is in flight.
+  auto inner1 = [&](int d, int c) { return !A.swapdim[d] || (c >= 2 && c <= g.nc[d] - 3); };
+  const bool row_inner = inner1(1, cy) && inner1(2, cz);
   int x0 = 0;
   while (x0 < g.nc[0]) {
     if (rows[base + x0 + 1] == rows[base + x0]) { x0++; continue; }
     int x1 = x0;
     while (x1 + 1 < g.nc[0]) {
+      if (A.want >= 0 && inner1(0, x1 + 1) != inner1(0, x0)) break;      // tiles do not straddle the interior / boundary line
       if (rows[base + x1 + 2] - rows[base + x0] > A.rowcap) break;
       if (total(x0, x1 + 1) > A.slotcap) break;
       x1++;
@@ -105,6 +112,7 @@ __global__ void k_tile_plan(TilePlanArgs A)
     if (A.shrink)      // (kernels with a run-time lane split) 512 threads serve 256 rows x 2 lanes or 128 rows x 4 lanes: a tile of 129..191 rows wastes more lanes than a shorter one
       while (x1 > x0 && rows[base + x1 + 1] - rows[base + x0] > TILE_ROWS / 2 && rows[base + x1 + 1] - rows[base + x0] < 3 * TILE_ROWS / 4) x1--;
     while (x1 > x0 && rows[base + x1 + 1] == rows[base + x1]) x1--;          // no trailing empty cells
+    if (A.want >= 0 && (int)!(row_inner && inner1(0, x0)) != A.want) { x0 = x1 + 1; continue; }
     int no, ng; counts(x0, x1, no, ng);
     int incl = no + ng;                                               // inclusive scan over the lanes -> slot offsets of the ranges
 #pragma unroll
@@ -139,7 +147,7 @@ struct TileBuildArgs {
   double cutsq_u, farsq_u, midsq_u;        // uni: the one cutneighsq / far / mid threshold of every type pair
   const double4 *xt; const int *gorder; const int *cso, *csg;
   const double *cutneighsq, *farsq, *midsq;
-  const TileDesc *tiles; const int *ntiles; int *counter;
+  const TileDesc *tiles; int ntiles; int *counter;
   uint4 *near, *far; int *numneigh, *numfar; int *maxcount;
   int *maxn;                               // longest row (entries), for the counters
   const int *orig; int *rowtile;           // multiphase: LAMMPS local indices (half-list ownership); tile of every owned row (fix phase_change)
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
   __shared__ float s_thr[MAXTT][6];                            // non-uniform cutoffs: far_lo, far_hi, cut_lo, cut_hi, mid_lo, mid_hi per type pair
   const int tid = threadIdx.x, lane = tid & 31;
   const Geom &g = A.g;
-  const int ntiles = *A.ntiles;
+  const int ntiles = A.ntiles;
   for (;;) {
     __syncthreads();
     if (tid == 0) { s_tile = atomicAdd(A.counter, 1); s_emax = 0; s_item = 0; }
@@ -468,14 +476,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
 // slot ids -> device particle indices, row-major [row][width] (tests / b200_get_neighbor_list only)
 struct TileExportArgs {
   int nlocal, ngrp, width, slot_mask;
-  const int *gorder; const TileDesc *tiles; const int *ntiles;
+  const int *gorder; const TileDesc *tiles; int ntiles;
   const uint4 *near, *far; const int *numneigh, *numfar;
   int *out;
 };
 __global__ void k_tile_export(TileExportArgs A)
 {
   __shared__ TileDesc D;
-  const int ntiles = *A.ntiles;
+  const int ntiles = A.ntiles;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     __syncthreads();
     for (int k = threadIdx.x; k < (int)(sizeof(TileDesc) / 4); k += blockDim.x) ((int *)&D)[k] = ((const int *)(A.tiles + t))[k];
@@ -507,13 +515,14 @@ __global__ void k_tile_export(TileExportArgs A)
 // double2 array per part: P0 = x,y   P1 = z,rho   [P2 = vest.x,vest.y   P3 = vest.z, Tait term]   [Pe = e,0]
 struct TileRecArgs {
   int nlocal, nall, pstride, force, epart;   // epart < 0: no energy part
+  int i0, i1;                                // records [i0, i1) of the tile order (owned first, then ghosts)
   const int *gorder; const double4 *xt, *vr; const double *e; const PairTab *fluid;
   double2 *rec;
 };
 __global__ void k_tile_records(TileRecArgs A)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.nall) return;
+  int i = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.i1) return;
   int src = i < A.nlocal ? i : A.nlocal + A.gorder[i - A.nlocal];
   double4 x = A.xt[src], v = A.vr[src];
   A.rec[i] = make_double2(x.x, x.y);
@@ -576,7 +585,7 @@ struct TileArgs {
   int nlocal, ngrp, pstride, cap;            // cap = slots per part in shared memory
   const double2 *rec;
   const uint4 *near, *far; const int *numneigh, *numfar; const int *scan_far;
-  const TileDesc *tiles; const int *ntiles; int *counter;
+  const TileDesc *tiles; int ntiles; int *counter;      // tiles[0 .. ntiles): the launch's share of the plan
   const double4 *xt;
   double4 *vr_out, *fd; double *de;
   const PairTab *tab[3];
@@ -692,7 +701,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
   const PairTab &T = S.T[0];
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
-  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -778,7 +787,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_vci = -UF.visc * UF.h;
   const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
   const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
-  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<(1 << NPARTS) - 1, NK, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -998,7 +1007,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
   const PairTab &T = S.T[0];
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
-  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
@@ -1100,7 +1109,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
   const PairTab *T = S.T;
   auto part = [&](int p) { return S.part + (size_t)MP::idx(p) * A.cap; };
   const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7);
-  const int ntiles = *A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   const size_t ps = A.pstride;
   TileLoop<MP::mask, NK, NT> L(A, S, ntiles);
   L.start();

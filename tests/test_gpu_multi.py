@@ -20,3 +20,18 @@ def test_two_rank_decomposition_matches_fixtures():
     print("\n".join(lines))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert len(lines) >= 8 and not any("FAIL" in l for l in lines)
+
+
+def test_two_rank_halo_overlap_matches_fixtures():
+    """the same check with B200_OVERLAP=1: interior tiles of the single-phase decks run while the NCCL halo is in flight"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    env = dict(os.environ, B200_OVERLAP="1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29534", os.path.join(ROOT, "tests", "mgpu_check.py"), "dam3d", "dam2d", "heat3d", "heat2d_rhosum"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    lines = [l for l in p.stdout.splitlines() if " grid " in l]
+    print("\n".join(lines))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert len(lines) >= 4 and not any("FAIL" in l for l in lines)

@@ -78,6 +78,18 @@ def test_small_tiles_and_fallback(name, nsteps, cap):
         assert harness.relerr(a[k], b[k]) < 1e-10, (name, k, harness.relerr(a[k], b[k]))
 
 
+@pytest.mark.parametrize("name,nsteps", [("heat3d", 25), ("heat2d_rhosum", 20), ("gas3d", 10)])
+def test_halo_overlap_equals_plain_order(name, nsteps):
+    """B200_OVERLAP=1: interior tiles run while the (here: periodic self-) halo is in flight on a second stream"""
+    a, na, ca = _run(name, nsteps, {"B200_OVERLAP": "1"})
+    b, nb, cb = _run(name, nsteps, {})
+    assert ca["launches"] > cb["launches"]
+    for p, q in zip(na, nb):
+        assert np.array_equal(p, q)
+    for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de"):
+        assert harness.relerr(a[k], b[k]) < 1e-12, (name, k, harness.relerr(a[k], b[k]))
+
+
 def test_tile_path_is_the_one_that_runs():
     """single-phase decks must take the tile kernels (the launch counter differs from the row path's)"""
     a, _, ca = _run("dam3d", 5, {})
