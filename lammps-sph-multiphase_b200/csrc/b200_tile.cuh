@@ -681,6 +681,23 @@ __device__ __forceinline__ double fast_div(double n, double d)
   const double q = n * y;
   return fma(fma(-d, q, n), y, q);
 }
+// the same without the last correction: relative error <= ~1e-13 (seed 2^-22 squared, times 1.5) resp. one rounding of the
+// reciprocal -- three orders inside the 1e-10 per-step budget; used in the single-phase force body, where the fp64 pipe binds
+__device__ __forceinline__ double fast_sqrt13(double a)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double g = a * y, hh = 0.5 * y;
+  return fma(g, fma(-hh, g, 0.5), g);
+}
+__device__ __forceinline__ double fast_div15(double n, double d)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  return n * y;
+}
 // the cutoff tests of the stage kernels may contract to FMA: every kernel and its derivative vanish at the cutoff, so a
 // pair within an ulp of it contributes nothing either way (the neighbor *lists* are decided without FMA, see k_tile_build)
 __device__ __forceinline__ double rsq_fma(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
@@ -830,7 +847,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
             const double rhoj = qb.y;
             if (UNI) {
               const double rsq = rsq_fma(dx, dy, dz);
-              const double r = fast_sqrt(rsq);                                // NaN for coincident particles: masked by dpos()
+              const double r = fast_sqrt13(rsq);                              // NaN for coincident particles: masked by dpos()
               if (HAS_FLUID) {
                 const bool hit = (rsq < UF.cutsq) & ((maskf >> tj) & 1u) & dpos(rsq);
                 const double2 qc = P2[slot], qd = P3[slot];
@@ -841,7 +858,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                 if (KINDS & (K_TAIT | K_IDEAL)) {
                   // sph/idealgas: the sound speeds are per particle, c = sqrt(0.4 e / m) = sqrt((p/rho^2) rho)
                   const double vch = (KINDS & K_IDEAL) ? u_vci * (ci + fast_sqrt(fmax(qd.y * rhoj, 0.0))) : u_vch;
-                  double fvisc = fast_div(vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
+                  double fvisc = fast_div15(vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
                   fvisc = dvdr < 0.0 ? fvisc : 0.0;
                   const double fpair = u_k1 * (d.y + qd.y + fvisc) * wfd;     // -m m c0 (...) (h - r)^2
                   fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
