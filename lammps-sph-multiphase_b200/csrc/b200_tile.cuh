@@ -993,16 +993,12 @@ __device__ __forceinline__ double quintic_dw_bf(double q)
 }
 // r = sqrt(a) and 1/r, branch-free (see fast_sqrt); NaN / inf for a = 0, which the callers mask with dpos()
 __device__ __forceinline__ void fast_sqrt_rinv(double a, double &r, double &rinv)
-{
+{ // one coupled Newton step from the 2^-22 seed: both results to ~1e-13 (see fast_sqrt13)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y, hh = 0.5 * y;
-  double e = fma(-hh, g, 0.5);
-  g = fma(g, e, g); hh = fma(hh, e, hh);
-  g = fma(fma(-g, g, a), hh, g);
-  e = fma(-hh, g, 0.5);
-  hh = fma(hh, e, hh);
-  r = g; rinv = hh + hh;
+  const double g = a * y, hh = 0.5 * y;
+  const double e = fma(-hh, g, 0.5);
+  r = fma(g, e, g); rinv = 2.0 * fma(hh, e, hh);
 }
 
 // rows per pass and lanes per row of a 512-thread stage CTA: 256 rows x 2 lanes, or 128 rows x 4 lanes for small tiles
@@ -1063,7 +1059,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
             const bool hit = GU ? ((rsq < U.cutsq) & ((rowmask >> tj) & 1u) & dpos(rsq)) : ((rsq < T.cutsq[ij]) & dpos(rsq));   // empty entries: type 0 is never mapped
             const double c0 = GU ? U.c0 : T.c0[ij], c1 = GU ? U.c1 : T.c1[ij];
             if (MPK == 0) {
-              const double wv = quintic_w_bf(3.0 * (fast_sqrt(rsq) * c1));
+              const double wv = quintic_w_bf(3.0 * (fast_sqrt13(rsq) * c1));
               acc += hit ? (GU ? wv : c0 * wv) : 0.0;
             } else {
               double r, rinv; fast_sqrt_rinv(rsq, r, rinv);
@@ -1192,7 +1188,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
                 Pi = P.B[ti] * (pow(rhoi / P.rho0[ti], P.gamma[to]) - P.rb[ti]);
                 Pj = P.B[tj] * (pow(rhoj / P.rho0[tj], P.gamma[to]) - P.rb[tj]);
               }
-              const double pij = fast_div(rhoj * Pi + rhoi * Pj, rhoi + rhoj);
+              const double pij = fast_div15(rhoj * Pi + rhoi * Pj, rhoi + rhoj);
               const double V2 = v4.x + q4.x;
               const double fvisc = V2 * P.visc[ij] * wfd, fpair = -V2 * pij * wfd;
               const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
@@ -1244,7 +1240,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
                 Tb = (ff == tb && Tb < Ta) ? tc : Tb;
                 Ti = row_owns ? Ta : Tb; Tj = row_owns ? Tb : Ta;
               }
-              const double term = fast_div(2.0 * P.visc[ij] * (Ti - Tj) * wfd * mj, rhoi * rhoj);
+              const double term = fast_div15(2.0 * P.visc[ij] * (Ti - Tj) * wfd * mj, rhoi * rhoj);
               ade += hit ? term : 0.0;
             }
           }
