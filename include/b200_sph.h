@@ -133,6 +133,9 @@ int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix
  * 0 for `noregion` (apply outside).  Region tests as RegBlock/RegSphere::inside (region_block.cpp:114-119, region_sphere.cpp:96-105). */
 int  b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside);
 int  b200_fix_enforce2d(b200_sph *h, int groupbit);                          /* fix_enforce2d.cpp:77-89 */
+/* fix setmesode value [region ID] (fix_setmesode.cpp:38-78,171-199): de = value for the group's atoms (inside the region); constant value,
+ * region as for b200_fix_setmeso */
+int  b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind, const double region[6]);
 /* fix setforce with constant values (fix_setforce.cpp:215-251): set[d] != 0 -> f[d] = value[d] (set[d] = 0 is the NULL keyword) */
 int  b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3]);
 

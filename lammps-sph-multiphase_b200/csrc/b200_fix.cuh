@@ -111,6 +111,20 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
     }
   if (fdirty) a.fd[i] = f;
   if (vdirty) a.vm[i] = v;
+  if (do_post)
+    for (int k = 0; k < fl.n; k++)
+      if (fl.kind[k] == 7 && (m & fl.bit[k])) {             // FixSetMesodE::post_force, constant value (fix_setmesode.cpp:171-199)
+        int rk = fl.ipar[k][1];
+        if (rk) {
+          double4 x = a.xt[i];
+          const double *r = &fl.par[k][1];
+          bool in;
+          if (rk == 1) in = x.x >= r[0] && x.x <= r[1] && x.y >= r[2] && x.y <= r[3] && x.z >= r[4] && x.z <= r[5];
+          else { double dx = x.x - r[0], dy = x.y - r[1], dz = x.z - r[2]; in = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) <= r[3]; }
+          if (!in) continue;
+        }
+        de = fl.par[k][0]; a.de[i] = de;
+      }
   if (do_final) {
     double4 vr = a.vr[i];
     double e = a.e[i];

@@ -1451,6 +1451,15 @@ int b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int reg
   return 0;
 }
 int b200_fix_enforce2d(b200_sph *h, int groupbit) { return add_fix(h, 5, groupbit, 0, 0, 0); }
+int b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind, const double region[6])
+{
+  if (region_kind < 0 || region_kind > 2) return fail("b200_fix_setmesode: bad arguments");
+  if (add_fix(h, 7, groupbit, 0, 0, 0)) return -1;
+  int k = h->fl.n - 1;
+  h->fl.ipar[k][1] = region_kind; h->fl.par[k][0] = value;
+  for (int q = 0; q < 6; q++) h->fl.par[k][1 + q] = (region_kind && region) ? region[q] : 0.0;
+  return 0;
+}
 int b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3])
 {
   if (add_fix(h, 6, groupbit, 0, 0, 0)) return -1;

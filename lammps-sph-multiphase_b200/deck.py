@@ -273,6 +273,17 @@ class Deck:
             if self.dimension == 3:
                 raise DeckError("Cannot use fix enforce2d with 3d simulation")
             self.fixes.append((style, bit, None))
+        elif style == "setmesode":     # fix_setmesode.cpp:38-78: value [region ID], constant value
+            if not args or str(args[0]).startswith("v_") or str(args[0]) == "NULL":
+                raise DeckError("b200 SPH package: fix setmesode supports a constant value")
+            kind, reg = 0, [0.0] * 6
+            if len(args) > 1:
+                if args[1] != "region" or len(args) < 3:
+                    raise DeckError("Illegal fix setmesode command")
+                if args[2] not in self.regions:
+                    raise DeckError("Region ID for fix setmesode does not exist")
+                kind, reg = self.regions[args[2]]
+            self.fixes.append((style, bit, (float(args[0]), kind, list(reg))))
         elif style == "setforce":      # fix_setforce.cpp:40-110, constant values or NULL
             if len(args) != 3:
                 raise DeckError("Illegal fix setforce command")

@@ -81,6 +81,10 @@ class Sim:
                 ck(api.fix_gravity(h, bit, *arg))
             elif style == "enforce2d":
                 ck(api.fix_enforce2d(h, bit))
+            elif style == "setmesode":
+                value, kind, reg = arg
+                r = np.array(reg, np.float64)
+                ck(api.fix_setmesode(h, bit, value, kind, _dp(r)))
             elif style == "setforce":
                 sets = np.array(arg[0], np.int32); vals = np.array(arg[1], np.float64)
                 ck(api.fix_setforce(h, bit, _ip(sets), _dp(vals)))

@@ -122,3 +122,35 @@ FixSetForceB200::FixSetForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, n
   }
 }
 int FixSetForceB200::setmask() { return POST_FORCE; }
+
+FixSetMesodEB200::FixSetMesodEB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), idregion(NULL)
+{
+  if (narg < 4) error->all(FLERR, "Illegal fix setmesode command");
+  if (strstr(arg[3], "v_") == arg[3] || strcmp(arg[3], "NULL") == 0) error->all(FLERR, "fix setmesode/b200 supports a constant value only");
+  value = atof(arg[3]);
+  int iarg = 4;
+  while (iarg < narg) {
+    if (strcmp(arg[iarg], "region") == 0) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal fix setmesode command");
+      if (domain->find_region(arg[iarg + 1]) == -1) error->all(FLERR, "Region ID for fix setmesode does not exist");
+      idregion = new char[strlen(arg[iarg + 1]) + 1];
+      strcpy(idregion, arg[iarg + 1]);
+      iarg += 2;
+    } else error->all(FLERR, "Illegal fix setmesode command");
+  }
+}
+int FixSetMesodEB200::setmask() { return POST_FORCE; }
+int FixSetMesodEB200::b200_register(b200_sph *h)
+{
+  int kind = 0; double r[6] = {0, 0, 0, 0, 0, 0};
+  if (idregion) {
+    int ir = domain->find_region(idregion);
+    if (ir == -1) error->all(FLERR, "Region ID for fix setmesode does not exist");
+    Region *reg = domain->regions[ir];
+    if (reg->dynamic_check() || !reg->interior) error->all(FLERR, "fix setmesode/b200 supports static regions with side in");
+    if (strcmp(reg->style, "block") == 0) { kind = 1; r[0] = reg->extent_xlo; r[1] = reg->extent_xhi; r[2] = reg->extent_ylo; r[3] = reg->extent_yhi; r[4] = reg->extent_zlo; r[5] = reg->extent_zhi; }
+    else if (strcmp(reg->style, "sphere") == 0) { kind = 2; r[0] = 0.5 * (reg->extent_xlo + reg->extent_xhi); r[1] = 0.5 * (reg->extent_ylo + reg->extent_yhi); r[2] = 0.5 * (reg->extent_zlo + reg->extent_zhi); r[3] = 0.5 * (reg->extent_xhi - reg->extent_xlo); }
+    else error->all(FLERR, "fix setmesode/b200 supports block and sphere regions");
+  }
+  return b200_fix_setmesode(h, groupbit, value, kind, r);
+}

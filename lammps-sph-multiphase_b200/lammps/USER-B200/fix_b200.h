@@ -11,6 +11,7 @@ FixStyle(phase_change/b200,FixPhaseChangeB200)
 FixStyle(setmeso/b200,FixSetMesoB200)
 FixStyle(enforce2d/b200,FixEnforce2DB200)
 FixStyle(setforce/b200,FixSetForceB200)
+FixStyle(setmesode/b200,FixSetMesodEB200)
 
 #else
 
@@ -98,6 +99,17 @@ class FixSetForceB200 : public Fix, public B200FixShell {
   int b200_register(b200_sph *h) { return b200_fix_setforce(h, groupbit, set, value); }
  private:
   int set[3]; double value[3];
+};
+
+// FixSetMesodE (fix_setmesode.cpp:38-78): fix ID grp setmesode value [region ID], constant value, static block / sphere region
+class FixSetMesodEB200 : public Fix, public B200FixShell {
+ public:
+  FixSetMesodEB200(class LAMMPS *, int, char **);
+  int setmask();
+  void post_force(int) { b200_fix_guard(lmp, "setmesode"); }
+  int b200_register(b200_sph *h);
+ private:
+  double value; char *idregion;
 };
 
 }    // namespace LAMMPS_NS

@@ -33,7 +33,7 @@
 #define EPSILON 1.0e-12 /* pair_sph_surfacetension.cpp */
 #define CG_SMALL 1.0e-20 /* fix_phase_change.cpp:42 */
 
-enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE };
+enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE, FIX_SETMESODE };
 
 typedef struct {
   int style, nstep;
@@ -225,6 +225,14 @@ int osph_fix_setmeso(osph_sph *s, int groupbit, int which, double value, int reg
   return 0;
 }
 int osph_fix_enforce2d(osph_sph *s, int groupbit) { return newfix(s, FIX_ENFORCE2D, groupbit) ? 0 : fail("too many fixes"); }
+int osph_fix_setmesode(osph_sph *s, int groupbit, double value, int region_kind, const double region[6])
+{
+  ofix *f = newfix(s, FIX_SETMESODE, groupbit);
+  if (!f) return fail("too many fixes");
+  f->value = value; f->region_kind = region_kind; f->match_inside = 1;
+  for (int q = 0; q < 6; q++) f->region[q] = (region_kind && region) ? region[q] : 0.0;
+  return 0;
+}
 int osph_fix_setforce(osph_sph *s, int groupbit, const int set[3], const double value[3])
 {
   ofix *f = newfix(s, FIX_SETFORCE, groupbit);
@@ -947,6 +955,20 @@ static void fix_setmeso(osph_sph *s, ofix *fx)
 /* FixEnforce2D::post_force, fix_enforce2d.cpp:77-89 */
 static void fix_enforce2d(osph_sph *s, ofix *fx)
 { for (int i = 0; i < s->nlocal; i++) if (s->mask[i] & fx->groupbit) { s->v[3*i+2] = 0.0; s->f[3*i+2] = 0.0; } }
+/* FixSetMesodE::post_force, constant value, fix_setmesode.cpp:171-199 */
+static void fix_setmesode(osph_sph *s, ofix *fx)
+{
+  for (int i = 0; i < s->nlocal; i++) {
+    if (!(s->mask[i] & fx->groupbit)) continue;
+    if (fx->region_kind) {
+      const double *x = &s->x[3*i], *r = fx->region; int in;
+      if (fx->region_kind == 1) in = x[0] >= r[0] && x[0] <= r[1] && x[1] >= r[2] && x[1] <= r[3] && x[2] >= r[4] && x[2] <= r[5];
+      else { double dx = x[0] - r[0], dy = x[1] - r[1], dz = x[2] - r[2]; in = sqrt(dx * dx + dy * dy + dz * dz) <= r[3]; }
+      if (!in) continue;
+    }
+    s->de[i] = fx->value;
+  }
+}
 /* FixSetForce::post_force, constant values, fix_setforce.cpp:241-251 */
 static void fix_setforce(osph_sph *s, ofix *fx)
 {
@@ -1119,6 +1141,7 @@ int osph_post_force(osph_sph *s)
     else if (s->fix[i].kind == FIX_SETMESO) fix_setmeso(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_ENFORCE2D) fix_enforce2d(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_SETFORCE) fix_setforce(s, &s->fix[i]);
+    else if (s->fix[i].kind == FIX_SETMESODE) fix_setmesode(s, &s->fix[i]);
   }
   return 0;
 }

@@ -30,6 +30,7 @@
 #define b200_fix_setmeso       osph_fix_setmeso
 #define b200_fix_enforce2d     osph_fix_enforce2d
 #define b200_fix_setforce      osph_fix_setforce
+#define b200_fix_setmesode     osph_fix_setmesode
 #define b200_set_atoms         osph_set_atoms
 #define b200_get_natoms        osph_get_natoms
 #define b200_get_atoms         osph_get_atoms

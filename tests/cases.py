@@ -162,6 +162,11 @@ _add(Case("heat2d_rhosum", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso", 1
           [("mass", "1", 1.0e-5), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/heatconduction"),
            ("pair_coeff", "1 1", "sph/rhosum", 2.0e-2), ("pair_coeff", "1 1", "sph/heatconduction", 1.0e-4, 2.0e-2),
            ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso")], 40))
+# fix setmesode: a constant heating rate inside a block region of the C1 deck (fix_setmesode.cpp)
+_add(Case("heat2d_setmesode", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso", 1, _heat2d_create,
+          [("mass", "1", 1.0e-5), ("pair_style", "sph/heatconduction"), ("pair_coeff", "1 1", 1.0e-4, 2.0e-2),
+           ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso/stationary"), ("fix", "all", "setmesode", 0.5, "region", "rheat")],
+          40, regions=(("rheat", "block", 0.3, 0.7, "EDGE", "EDGE", "EDGE", "EDGE"),)))
 _add(Case("heat3d", 3, "f p p", ((0, 0, 0), (0.4, 0.08, 0.08)), "meso", 1,
           """lattice sc 0.01
 create_atoms 1 box
