@@ -136,6 +136,11 @@ int  b200_fix_enforce2d(b200_sph *h, int groupbit);                          /* 
 /* fix setmesode value [region ID] (fix_setmesode.cpp:38-78,171-199): de = value for the group's atoms (inside the region); constant value,
  * region as for b200_fix_setmeso */
 int  b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind, const double region[6]);
+/* fix dt/reset N Tmin Tmax Xmax units box (fix_dt_reset.cpp:40-186): every N steps (and at setup) the timestep becomes the largest one
+ * that moves no atom of the group further than xmax, clamped to [tmin, tmax] where minbound / maxbound != 0.  The timestep then lives on
+ * the device; b200_get_timestep returns the current value (update->dt). */
+int  b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax);
+int  b200_get_timestep(b200_sph *h, double *dt);
 /* fix setforce with constant values (fix_setforce.cpp:215-251): set[d] != 0 -> f[d] = value[d] (set[d] = 0 is the NULL keyword) */
 int  b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3]);
 

@@ -69,6 +69,8 @@ _PROTOS = {
     "fix_enforce2d": (C.c_int, [_H, C.c_int]),
     "fix_setforce": (C.c_int, [_H, C.c_int, c_int_p, c_double_p]),
     "fix_setmesode": (C.c_int, [_H, C.c_int, C.c_double, C.c_int, c_double_p]),
+    "fix_dt_reset": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "get_timestep": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "set_atoms": (C.c_int, [_H, C.c_int, C.POINTER(Atoms)]),
     "get_natoms": (C.c_int, [_H, c_int_p, c_int_p]),
     "get_atoms": (C.c_int, [_H, C.c_int, C.POINTER(Atoms)]),

@@ -27,11 +27,13 @@ __global__ void k_setup_pre_force(int nlocal, FixList fl, StepArrays a)
 // modify->initial_integrate: FixMeso::initial_integrate (fix_meso.cpp:91-140) and
 // FixMesoStationary::initial_integrate (fix_meso_stationary.cpp:71-92), fixes in deck order;
 // plus Neighbor::check_distance's per-atom test (neighbor.cpp:1396-1404) on the new positions.
+// dtp != NULL: the timestep lives on the device (fix dt/reset); dtp[0] = dt, dtf_per_dt = 0.5 ftm2v
 __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double dtv, double dtf, int check,
-                                    const double *xhold, double triggersq, int *flag, int track, unsigned long long *dmaxsq)
+                                    const double *xhold, double triggersq, int *flag, int track, unsigned long long *dmaxsq, const double *dtp, double dtf_per_dt)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
+  if (dtp) { dtv = *dtp; dtf = dtf_per_dt * dtv; }      // dtf = 0.5 dt ftm2v
   int m = a.mask[i];
   double4 x = a.xt[i], vr = a.vr[i], v = a.vm[i], f = a.fd[i];
   double e = a.e[i], de = a.de[i];
@@ -72,10 +74,11 @@ __global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, do
 // (comm->reverse_comm runs before this kernel: b200_comm.cuh) modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
 // (fix_meso.cpp:144-180, fix_meso_stationary.cpp:96-112).  The three stages can be run fused (one
 // pass over the owned atoms) or one by one for the stage-level ABI.
-__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_post, int do_final)
+__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_post, int do_final, const double *dtp, double dtf_per_dt)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
+  if (dtp) dtf = dtf_per_dt * *dtp;
   double4 f = a.fd[i];
   double de = a.de[i];
   bool fdirty = false;
@@ -143,6 +146,38 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
     if (vd) a.vm[i] = v;
     if (ed) { a.e[i] = e; a.vr[i] = vr; }
   }
+}
+
+// FixDtReset::end_of_step (fix_dt_reset.cpp:131-186): per-atom largest timestep that keeps the displacement below xmax; the minimum over
+// the group is taken on the bit patterns (positive doubles order like uint64)
+__global__ void k_dt_min(int nlocal, int groupbit, const int *mask, const double4 *vm, const double4 *fd, double xmax, double ftm2v,
+                         unsigned long long *dtmin_bits)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal || !(mask[i] & groupbit)) return;
+  const double4 v = vm[i], f = fd[i];
+  const double massinv = 1.0 / v.w;
+  const double vsq = __dadd_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)), __dmul_rn(v.z, v.z));
+  const double fsq = __dadd_rn(__dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y)), __dmul_rn(f.z, f.z));
+  double dtv = 1.0e20, dtf = 1.0e20;
+  if (vsq > 0.0) dtv = xmax / sqrt(vsq);
+  if (fsq > 0.0) dtf = sqrt(2.0 * xmax / (ftm2v * sqrt(fsq) * massinv));
+  double dt = fmin(dtv, dtf);
+  const double dtsq = dt * dt;
+  const double delx = __dadd_rn(__dmul_rn(dt, v.x), __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(0.5, dtsq), massinv), f.x), ftm2v));
+  const double dely = __dadd_rn(__dmul_rn(dt, v.y), __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(0.5, dtsq), massinv), f.y), ftm2v));
+  const double delz = __dadd_rn(__dmul_rn(dt, v.z), __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(0.5, dtsq), massinv), f.z), ftm2v));
+  const double delr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(delx, delx), __dmul_rn(dely, dely)), __dmul_rn(delz, delz)));
+  if (delr > xmax) dt *= xmax / delr;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(dt);
+  if (b < *(volatile unsigned long long *)dtmin_bits) atomicMin(dtmin_bits, b);
+}
+__global__ void k_dt_apply(const unsigned long long *dtmin_bits, int minbound, double tmin, int maxbound, double tmax, double *dtp)
+{
+  double dt = __longlong_as_double((long long)*dtmin_bits);
+  if (minbound) dt = fmax(dt, tmin);
+  if (maxbound) dt = fmin(dt, tmax);
+  dtp[0] = dt;
 }
 
 // ---- host <-> device layout conversion (LAMMPS AoS per-atom arrays <-> packed double4 records) ----

@@ -133,6 +133,9 @@ struct b200_sph {
   DevBuf<double> d_prunesq, d_farsq, d_midsq; double far_margin = 0.0, mid_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
+  // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
+  bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
+  double *d_dt = nullptr;
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
@@ -680,6 +683,9 @@ static void build_plan(b200_sph *h)
     }
     h->plan.push_back(p);
   }
+  // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
+  bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
+  double *d_dt = nullptr;
   // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
   if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
@@ -1079,7 +1085,8 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
       [&](Swap &s) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), h->sendbuf.p); },
       [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
   if ((post || fin) && h->nlocal)
-    LAUNCH(h, k_post_final, nblk(h->nlocal, B), B, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, post, fin);
+    LAUNCH(h, k_post_final, nblk(h->nlocal, B), B, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, post, fin,
+           h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v);
   h->tend();
 }
 static void initial_integrate(b200_sph *h)
@@ -1089,7 +1096,7 @@ static void initial_integrate(b200_sph *h)
   CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));
   int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
-         h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq);
+         h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq, h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v);
   h->tend();
 }
 static void forward_comm(b200_sph *h)
@@ -1126,6 +1133,7 @@ static int neigh_decide(b200_sph *h)
   }
   return 0;
 }
+static void dt_download(b200_sph *h);
 // FixPhaseChange::pre_exchange (fix_phase_change.cpp:167-352); runs on the rows of the previous build
 static void phase_change(b200_sph *h, PcFix &f)
 {
@@ -1133,6 +1141,7 @@ static void phase_change(b200_sph *h, PcFix &f)
   f.next += f.d.nfreq;
   int nl = h->nlocal, na = h->nall();
   if (!nl) return;
+  dt_download(h);
   h->tbegin(T_PHASE);
   int norig = std::max(h->next_orig, nl);
   h->pc_flag.ensure(norig); h->pc_thr.ensure(norig); h->pc_dev.ensure(norig); h->pc_dmass.ensure(na); h->pc_new.ensure(PC_MAXNEW);
@@ -1182,6 +1191,23 @@ static void phase_change(b200_sph *h, PcFix &f)
   if (ninsall > 0) { h->nghost = 0; h->maxtag += ninsall; }
   h->tend();
 }
+// FixDtReset::end_of_step
+static void dt_reset(b200_sph *h)
+{
+  const unsigned long long big = 0x7ff0000000000000ull;     // +inf: larger than any timestep
+  CK(cudaMemcpyAsync((unsigned long long *)h->d_dt + 1, &big, sizeof big, cudaMemcpyHostToDevice, h->st));
+  if (h->nlocal) LAUNCH(h, k_dt_min, nblk(h->nlocal, 256), 256, h->nlocal, h->dtr_bit, h->C().mask.p, h->C().vm.p, h->C().fd.p, h->dtr_xmax, h->ftm2v,
+                        (unsigned long long *)h->d_dt + 1);
+  if (h->world > 1) NCK(g_nccl.AllReduce((unsigned long long *)h->d_dt + 1, (unsigned long long *)h->d_dt + 1, 1, ncclUint64, ncclMin, h->nccl, h->st));   // MPI_Allreduce MIN (:171)
+  LAUNCH(h, k_dt_apply, 1, 1, (const unsigned long long *)h->d_dt + 1, h->dtr_minbound, h->dtr_tmin, h->dtr_maxbound, h->dtr_tmax, h->d_dt);
+}
+static void dt_download(b200_sph *h)
+{
+  if (!h->dtreset) return;
+  CK(cudaMemcpyAsync(h->h_red + 4, h->d_dt, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  h->dt = h->h_red[4];
+}
 static void reneighbor(b200_sph *h)
 {
   for (PcFix &f : h->pcs) phase_change(h, f);        // modify->pre_exchange (verlet.cpp:241)
@@ -1207,6 +1233,10 @@ static void do_setup(b200_sph *h)
   // ghosts carry vest of the border comm (before setup_pre_force), exactly as in Verlet::setup
   pair_compute_all(h);
   post_final(h, 1, 1, 0);
+  if (h->dtreset) {            // FixDtReset::setup -> end_of_step
+    CK(cudaMemcpyAsync(h->d_dt, &h->dt, sizeof(double), cudaMemcpyHostToDevice, h->st));
+    dt_reset(h); dt_download(h);
+  }
   h->setup_done = true;
 }
 static void do_run(b200_sph *h, int n)
@@ -1221,8 +1251,10 @@ static void do_run(b200_sph *h, int n)
     force_clear(h);
     pair_compute_all(h);
     post_final(h, 1, 1, 1);
+    if (h->dtreset && h->ntimestep % h->dtr_every == 0) dt_reset(h);      // modify->end_of_step
     h->nsteps++;
   }
+  dt_download(h);
   if (h->timing) h->tflush();
 }
 
@@ -1327,7 +1359,7 @@ int b200_destroy(b200_sph *h)
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
   h->sendbuf.release(); h->recvbuf.release(); for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
   if (h->nccl) g_nccl.CommDestroy(h->nccl);
-  cudaFree(h->d_red); cudaFreeHost(h->h_red);
+  cudaFree(h->d_red); cudaFreeHost(h->h_red); if (h->d_dt) cudaFree(h->d_dt);
   h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
@@ -1428,6 +1460,7 @@ int b200_fix_clear(b200_sph *h)
   memset(&h->fl, 0, sizeof h->fl);
   for (PcFix &f : h->pcs) cudaFree(f.d_state);
   h->pcs.clear();
+  h->dtreset = false;
   return 0;
 }
 static int add_fix(b200_sph *h, int kind, int bit, double ax, double ay, double az)
@@ -1451,6 +1484,18 @@ int b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int reg
   return 0;
 }
 int b200_fix_enforce2d(b200_sph *h, int groupbit) { return add_fix(h, 5, groupbit, 0, 0, 0); }
+int b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax)
+{
+  API_BEGIN
+  if (nevery <= 0 || xmax <= 0.0 || (minbound && tmin < 0.0) || (maxbound && tmax < 0.0) || (minbound && maxbound && tmin >= tmax))
+    throw std::string("Illegal fix dt/reset command");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_dt) CK(cudaMalloc(&h->d_dt, 4 * sizeof(double)));
+  h->dtreset = true; h->dtr_bit = groupbit; h->dtr_every = nevery; h->dtr_minbound = minbound; h->dtr_tmin = tmin;
+  h->dtr_maxbound = maxbound; h->dtr_tmax = tmax; h->dtr_xmax = xmax;
+  API_END
+}
+int b200_get_timestep(b200_sph *h, double *dt) { *dt = h->dt; return 0; }
 int b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind, const double region[6])
 {
   if (region_kind < 0 || region_kind > 2) return fail("b200_fix_setmesode: bad arguments");

@@ -273,6 +273,18 @@ class Deck:
             if self.dimension == 3:
                 raise DeckError("Cannot use fix enforce2d with 3d simulation")
             self.fixes.append((style, bit, None))
+        elif style == "dt/reset":      # fix_dt_reset.cpp:40-98: N Tmin Tmax Xmax [units box]
+            if len(args) < 4:
+                raise DeckError("Illegal fix dt/reset command")
+            nevery = int(args[0])
+            minb, tmin = (0, 0.0) if str(args[1]) == "NULL" else (1, float(args[1]))
+            maxb, tmax = (0, 0.0) if str(args[2]) == "NULL" else (1, float(args[2]))
+            xmax = float(args[3])
+            if list(args[4:]) != ["units", "box"]:
+                raise DeckError("b200 SPH package: fix dt/reset needs `units box`")
+            if nevery <= 0 or xmax <= 0.0 or (minb and tmin < 0.0) or (maxb and tmax < 0.0) or (minb and maxb and tmin >= tmax):
+                raise DeckError("Illegal fix dt/reset command")
+            self.fixes.append((style, bit, (nevery, minb, tmin, maxb, tmax, xmax)))
         elif style == "setmesode":     # fix_setmesode.cpp:38-78: value [region ID], constant value
             if not args or str(args[0]).startswith("v_") or str(args[0]) == "NULL":
                 raise DeckError("b200 SPH package: fix setmesode supports a constant value")

@@ -33,6 +33,12 @@ class Sim:
             api.check(api.comm_init(h, brick.world, brick.rank, _ip(grid), _ip(loc), _ip(nb), nccl_id))
         self._configure()
 
+    def timestep(self):
+        """update->dt as the engine holds it (changes under fix dt/reset)"""
+        dt = C.c_double()
+        self.api.check(self.api.get_timestep(self.h, C.byref(dt)))
+        return dt.value
+
     def close(self):
         if self.h:
             self.api.destroy(self.h)
@@ -81,6 +87,8 @@ class Sim:
                 ck(api.fix_gravity(h, bit, *arg))
             elif style == "enforce2d":
                 ck(api.fix_enforce2d(h, bit))
+            elif style == "dt/reset":
+                ck(api.fix_dt_reset(h, bit, *arg))
             elif style == "setmesode":
                 value, kind, reg = arg
                 r = np.array(reg, np.float64)

@@ -154,3 +154,18 @@ int FixSetMesodEB200::b200_register(b200_sph *h)
   }
   return b200_fix_setmesode(h, groupbit, value, kind, r);
 }
+
+FixDtResetB200::FixDtResetB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
+{
+  if (narg < 7) error->all(FLERR, "Illegal fix dt/reset command");
+  time_depend = 1;
+  nevery_ = atoi(arg[3]);
+  minbound = maxbound = 1; tmin = tmax = 0.0;
+  if (strcmp(arg[4], "NULL") == 0) minbound = 0; else tmin = atof(arg[4]);
+  if (strcmp(arg[5], "NULL") == 0) maxbound = 0; else tmax = atof(arg[5]);
+  xmax = atof(arg[6]);
+  if (narg != 9 || strcmp(arg[7], "units") != 0 || strcmp(arg[8], "box") != 0) error->all(FLERR, "fix dt/reset/b200 needs `units box`");
+  if (nevery_ <= 0 || xmax <= 0.0 || (minbound && tmin < 0.0) || (maxbound && tmax < 0.0) || (minbound && maxbound && tmin >= tmax))
+    error->all(FLERR, "Illegal fix dt/reset command");
+}
+int FixDtResetB200::setmask() { return END_OF_STEP; }

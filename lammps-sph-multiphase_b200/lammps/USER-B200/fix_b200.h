@@ -12,6 +12,7 @@ FixStyle(setmeso/b200,FixSetMesoB200)
 FixStyle(enforce2d/b200,FixEnforce2DB200)
 FixStyle(setforce/b200,FixSetForceB200)
 FixStyle(setmesode/b200,FixSetMesodEB200)
+FixStyle(dt/reset/b200,FixDtResetB200)
 
 #else
 
@@ -110,6 +111,18 @@ class FixSetMesodEB200 : public Fix, public B200FixShell {
   int b200_register(b200_sph *h);
  private:
   double value; char *idregion;
+};
+
+// FixDtReset (fix_dt_reset.cpp:40-98, members private): fix ID grp dt/reset N Tmin Tmax Xmax units box.  The timestep lives on the
+// device during a run; VerletB200 copies it back into update->dt after every b200_run segment.
+class FixDtResetB200 : public Fix, public B200FixShell {
+ public:
+  FixDtResetB200(class LAMMPS *, int, char **);
+  int setmask();
+  void end_of_step() { b200_fix_guard(lmp, "dt/reset"); }
+  int b200_register(b200_sph *h) { return b200_fix_dt_reset(h, groupbit, nevery_, minbound, tmin, maxbound, tmax, xmax); }
+ private:
+  int nevery_, minbound, maxbound; double tmin, tmax, xmax;
 };
 
 }    // namespace LAMMPS_NS

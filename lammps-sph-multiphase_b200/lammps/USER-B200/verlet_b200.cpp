@@ -148,6 +148,7 @@ void VerletB200::setup()
   configure();
   upload();
   check(b200_setup(h));
+  { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // FixDtReset::setup may already have changed it
   download();
   ev_set(update->ntimestep);
   modify->setup(vflag);
@@ -172,6 +173,7 @@ void VerletB200::run(int n)
     check(b200_run(h, k));
     check(b200_sync(h));
     update->ntimestep += k;
+    { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // fix dt/reset/b200 changes it on the device
     timer->stamp(TIME_PAIR);
     if (update->ntimestep == output->next || update->ntimestep == nend) {
       download();

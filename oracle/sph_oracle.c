@@ -33,7 +33,7 @@
 #define EPSILON 1.0e-12 /* pair_sph_surfacetension.cpp */
 #define CG_SMALL 1.0e-20 /* fix_phase_change.cpp:42 */
 
-enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE, FIX_SETMESODE };
+enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE, FIX_SETMESODE, FIX_DT_RESET };
 
 typedef struct {
   int style, nstep;
@@ -46,6 +46,7 @@ typedef struct {
   double acc[3];
   int which, region_kind, match_inside; double value, region[6];
   int fset[3]; double fvalue[3];   /* fix setforce */
+  int nevery, minbound, maxbound; double tmin, tmax, xmax;   /* fix dt/reset */
   osph_phase_change_desc pc;
   long long next_reneighbor;
   int seed; /* RanPark state, random_park.cpp:22-47 */
@@ -225,6 +226,16 @@ int osph_fix_setmeso(osph_sph *s, int groupbit, int which, double value, int reg
   return 0;
 }
 int osph_fix_enforce2d(osph_sph *s, int groupbit) { return newfix(s, FIX_ENFORCE2D, groupbit) ? 0 : fail("too many fixes"); }
+int osph_fix_dt_reset(osph_sph *s, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax)
+{
+  if (nevery <= 0 || xmax <= 0.0 || (minbound && tmin < 0.0) || (maxbound && tmax < 0.0) || (minbound && maxbound && tmin >= tmax))
+    return fail("Illegal fix dt/reset command");
+  ofix *f = newfix(s, FIX_DT_RESET, groupbit);
+  if (!f) return fail("too many fixes");
+  f->nevery = nevery; f->minbound = minbound; f->tmin = tmin; f->maxbound = maxbound; f->tmax = tmax; f->xmax = xmax;
+  return 0;
+}
+int osph_get_timestep(osph_sph *s, double *dt) { *dt = s->dt; return 0; }
 int osph_fix_setmesode(osph_sph *s, int groupbit, double value, int region_kind, const double region[6])
 {
   ofix *f = newfix(s, FIX_SETMESODE, groupbit);
@@ -955,6 +966,31 @@ static void fix_setmeso(osph_sph *s, ofix *fx)
 /* FixEnforce2D::post_force, fix_enforce2d.cpp:77-89 */
 static void fix_enforce2d(osph_sph *s, ofix *fx)
 { for (int i = 0; i < s->nlocal; i++) if (s->mask[i] & fx->groupbit) { s->v[3*i+2] = 0.0; s->f[3*i+2] = 0.0; } }
+/* FixDtReset::end_of_step, fix_dt_reset.cpp:131-186 */
+static void fix_dt_reset(osph_sph *s, ofix *fx)
+{
+  const double BIGDT = 1.0e20;
+  double dtmin = BIGDT;
+  for (int i = 0; i < s->nlocal; i++)
+    if (s->mask[i] & fx->groupbit) {
+      const double *v = &s->v[3*i], *f = &s->f[3*i];
+      double massinv = s->multiphase ? 1.0 / s->rmass[i] : 1.0 / s->mass[s->type[i]];
+      double vsq = v[0]*v[0] + v[1]*v[1] + v[2]*v[2], fsq = f[0]*f[0] + f[1]*f[1] + f[2]*f[2];
+      double dtv = BIGDT, dtf = BIGDT;
+      if (vsq > 0.0) dtv = fx->xmax / sqrt(vsq);
+      if (fsq > 0.0) dtf = sqrt(2.0 * fx->xmax / (s->ftm2v * sqrt(fsq) * massinv));
+      double dt = dtv < dtf ? dtv : dtf, dtsq = dt * dt;
+      double delx = dt*v[0] + 0.5*dtsq*massinv*f[0] * s->ftm2v, dely = dt*v[1] + 0.5*dtsq*massinv*f[1] * s->ftm2v,
+             delz = dt*v[2] + 0.5*dtsq*massinv*f[2] * s->ftm2v;
+      double delr = sqrt(delx*delx + dely*dely + delz*delz);
+      if (delr > fx->xmax) dt *= fx->xmax / delr;
+      if (dt < dtmin) dtmin = dt;
+    }
+  double dt = dtmin;
+  if (fx->minbound && dt < fx->tmin) dt = fx->tmin;
+  if (fx->maxbound && dt > fx->tmax) dt = fx->tmax;
+  s->dt = dt;
+}
 /* FixSetMesodE::post_force, constant value, fix_setmesode.cpp:171-199 */
 static void fix_setmesode(osph_sph *s, ofix *fx)
 {
@@ -1178,6 +1214,7 @@ int osph_setup(osph_sph *s)
   if (osph_pair_compute_all(s)) return -1;
   comm_reverse(s);
   osph_post_force(s); /* modify->setup: FixGravity::setup -> post_force */
+  for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_DT_RESET) fix_dt_reset(s, &s->fix[i]);   /* FixDtReset::setup -> end_of_step */
   s->setup_done = 1;
   return 0;
 }
@@ -1196,6 +1233,8 @@ int osph_run(osph_sph *s, int nsteps)
     comm_reverse(s);
     osph_post_force(s);
     osph_final_integrate(s);
+    for (int i = 0; i < s->nfix; i++)   /* modify->end_of_step */
+      if (s->fix[i].kind == FIX_DT_RESET && s->ntimestep % s->fix[i].nevery == 0) fix_dt_reset(s, &s->fix[i]);
     s->nsteps_done++;
   }
   return 0;

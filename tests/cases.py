@@ -212,6 +212,10 @@ set group all meso_e 0.0""" % (lat, _f(dx), "0.5" if dim == 3 else "0", water, i
 
 
 _add(_dam("dam2d", 2, 60))
+# examples/USER/sph/water_collapse/water_collapse.lmp:32: the shipped 2-D dam break runs with a variable timestep
+_c = _dam("dam2d_dtreset", 2, 60)
+_c.cmds = _c.cmds + [("fix", "all", "dt/reset", 1, "NULL", 0.1 * 0.03 / 30.0, 2.0e-8, "units", "box")]      # xmax small enough to bite from step 0
+_add(_c)
 _add(_dam("dam3d", 3, 25))
 _add(_dam("dam2d_morris", 2, 40, morris=True))
 

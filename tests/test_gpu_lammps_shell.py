@@ -42,7 +42,7 @@ def run(exe, args, workdir, text):
     return np.array(rows), p.stdout
 
 
-@pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10)])
+@pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10), ("dam2d_dtreset", 30, 1e-9)])
 def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
