@@ -41,7 +41,7 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle per launch of the dominant kernel (single-phase):
 #   sph/taitwater stage: R x24 + vest24 + rho8 + type4, W f24 + drho8 + de8 = 100 B
 BYTES_FORCE = 100
-FP64_NOTE = "profiles/r01_tile_v4_pipelined_full.txt: sm__pipe_fp64_cycles_active 57.3 % of peak for k_tile_force<K_TAIT> (ncu --set full, 1 028 768 particles, 0.66 ms)"
+FP64_NOTE = "profiles/r01_tile_v5_final_full.txt: sm__pipe_fp64_cycles_active 50.6 %, shared-memory data pipe 57.6 % of peak for k_tile_force<K_TAIT> (ncu --set full, 1 028 768 particles, 0.54 ms; 42 fp64 instructions per neighbor)"
 BYTES_STEP = 464          # whole single-phase step (rhosum 36 + taitwater 100 + fix meso 200 + 128)
 
 
