@@ -1,4 +1,4 @@
-// b200_tile.cuh -- the shared-memory tile path of the single-phase pair stages.
+// b200_tile.cuh -- the shared-memory tile path of the pair stages (single-phase and multiphase styles).
 //
 // Why (profiles/r01_*): with one global gather per neighbor the stage kernels were bound by L1
 // wavefronts -- a 32-lane gather touches ~17 distinct 128-byte lines and L1 replays one line per
@@ -7,10 +7,11 @@
 // particles).  Everything its rows can touch lives in the 3x3 (2-D) / 3x3x3 (3-D) cell
 // neighbourhood of the run, i.e. in at most 9 contiguous ranges of the cell-sorted particle order:
 //   * k_tile_plan   cuts the cell grid into tiles whose candidate set fits in shared memory;
-//   * k_tile_build  stages the candidates' positions, tests every (row, candidate) pair by
-//                   broadcast reads and writes each row's neighbors as 16-bit *slot ids*
-//                   (position inside the tile's staged set) -- Neighbor::full_bin's list
-//                   (neigh_full.cpp:241-340), same pair set bit for bit, half the bytes;
+//   * k_tile_build  stages the candidates' positions as fp32 offsets, decides every (row, candidate)
+//                   pair by broadcast reads (fp64 only inside a proven error band) and writes each
+//                   row's neighbors as 16-bit *slot ids* (position inside the tile's staged set) --
+//                   Neighbor::full_bin's list (neigh_full.cpp:241-340), same pair set bit for bit,
+//                   half the bytes, in an order that keeps the later LDS.128 reads conflict-free;
 //   * k_tile_rhosum / k_tile_force  stage the per-particle records of the tile with TMA bulk
 //                   copies (cp.async.bulk + mbarrier), then every lane walks its own row and
 //                   reads its neighbors' records from shared memory (LDS.128, ~29 cycles,
@@ -18,12 +19,15 @@
 // Records are stored as 16-byte parts in separate arrays (P0 = x,y  P1 = z,rho  P2 = vx,vy
 // P3 = vz, Tait term  [P4 = e]) so that lanes reading random slots spread over all banks.
 //
-// Single-phase styles only (sph/rhosum, sph/taitwater, sph/taitwater/morris, sph/heatconduction):
-// every row evaluates its own side of each pair, ghosts included -- ghost x, vest, rho, e are
-// fresh copies of their owners (AtomVecMeso::pack_comm, atom_vec_meso.cpp:139-203, and the
-// forward_comm_pair of rho, pair_sph_rhosum.cpp:203) and the pair formulas are symmetric, so
-// no ghost rows and no reverse communication are needed.  The multiphase styles keep the
-// row path of b200_pair.cuh (their ghost data can be one step stale).
+// Single-phase styles (sph/rhosum, sph/taitwater, sph/taitwater/morris, sph/heatconduction,
+// sph/idealgas): every row evaluates its own side of each pair, ghosts included -- ghost x, vest,
+// rho, e are fresh copies of their owners (AtomVecMeso::pack_comm, atom_vec_meso.cpp:139-203, and
+// the forward_comm_pair of rho, pair_sph_rhosum.cpp:203) and the pair formulas are symmetric, so
+// no ghost rows and no reverse communication are needed.
+// Multiphase styles (second half of this file): their ghost rho / colorgradient can be one step
+// stale in the reference, so entries carry the half-list ownership and a
+// ghost flag, tiles of ghost rows accumulate what the reference adds to ghost atoms, and the
+// reverse halo stays.
 #pragma once
 #include "b200_common.cuh"
 #include "b200_neigh.cuh"
