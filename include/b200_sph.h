@@ -141,6 +141,11 @@ int  b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind
  * the device; b200_get_timestep returns the current value (update->dt). */
 int  b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax);
 int  b200_get_timestep(b200_sph *h, double *dt);
+/* Pair virial (Pair::virial_fdotr_compute, pair.cpp:1403-1451: sum of x (x) f over owned + ghost atoms of the pair forces, before the
+ * reverse halo; xx yy zz xy xz yz, this rank's share).  b200_request_virial arms it for the next force evaluation that ends a call:
+ * the one of b200_setup, or the LAST step of the next b200_run (Verlet's ev_set on thermo steps, integrate.cpp:120-150). */
+int  b200_request_virial(b200_sph *h);
+int  b200_get_virial(b200_sph *h, double v[6]);
 /* fix setforce with constant values (fix_setforce.cpp:215-251): set[d] != 0 -> f[d] = value[d] (set[d] = 0 is the NULL keyword) */
 int  b200_fix_setforce(b200_sph *h, int groupbit, const int set[3], const double value[3]);
 

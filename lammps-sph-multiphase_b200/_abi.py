@@ -71,6 +71,8 @@ _PROTOS = {
     "fix_setmesode": (C.c_int, [_H, C.c_int, C.c_double, C.c_int, c_double_p]),
     "fix_dt_reset": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "get_timestep": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "request_virial": (C.c_int, [_H]),
+    "get_virial": (C.c_int, [_H, c_double_p]),
     "set_atoms": (C.c_int, [_H, C.c_int, C.POINTER(Atoms)]),
     "get_natoms": (C.c_int, [_H, c_int_p, c_int_p]),
     "get_atoms": (C.c_int, [_H, C.c_int, C.POINTER(Atoms)]),

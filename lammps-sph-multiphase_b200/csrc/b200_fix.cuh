@@ -180,6 +180,39 @@ __global__ void k_dt_apply(const unsigned long long *dtmin_bits, int minbound, d
   dtp[0] = dt;
 }
 
+// Pair::virial_fdotr_compute (pair.cpp:1403-1451): sum over owned + ghost atoms of x (x) f (xx yy zz xy xz yz), taken before
+// the reverse halo.  Deterministic two-stage reduction: fixed thread -> element assignment, fixed tree, then the block partials in order.
+// v6 != NULL: sum the rows of v6[n][6] instead (per-row pair sums of the single-phase tile path).
+#define VIR_BLOCKS 256
+#define VIR_THREADS 256
+__global__ void __launch_bounds__(VIR_THREADS) k_virial_partial(int n, const double4 *xt, const double4 *fd, const double *v6, double *partial)
+{
+  __shared__ double sh[6][VIR_THREADS];
+  double w[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * VIR_THREADS + threadIdx.x; i < n; i += VIR_BLOCKS * VIR_THREADS) {
+    if (v6) { for (int k = 0; k < 6; k++) w[k] += v6[(size_t)i * 6 + k]; }
+    else {
+      const double4 x = xt[i], f = fd[i];
+      w[0] += x.x * f.x; w[1] += x.y * f.y; w[2] += x.z * f.z; w[3] += x.x * f.y; w[4] += x.x * f.z; w[5] += x.y * f.z;
+    }
+  }
+  for (int k = 0; k < 6; k++) sh[k][threadIdx.x] = w[k];
+  __syncthreads();
+  for (int o = VIR_THREADS / 2; o; o >>= 1) {
+    if (threadIdx.x < o) for (int k = 0; k < 6; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void k_virial_final(const double *partial, double *out)
+{
+  int k = threadIdx.x;
+  if (k >= 6) return;
+  double s = 0.0;
+  for (int b = 0; b < VIR_BLOCKS; b++) s += partial[b * 6 + k];
+  out[k] = s;
+}
+
 // ---- host <-> device layout conversion (LAMMPS AoS per-atom arrays <-> packed double4 records) ----
 struct HostMirror {            // device staging copies of the caller's arrays (NULL = field absent)
   double *x, *v, *vest, *f, *cg, *rho, *drho, *e, *de, *cv, *rmass;

@@ -133,6 +133,8 @@ struct b200_sph {
   DevBuf<double> d_prunesq, d_farsq, d_midsq; double far_margin = 0.0, mid_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
+  // pair virial (Pair::virial_fdotr_compute) on request: the next force evaluation of b200_setup / the last step of b200_run
+  bool vir_request = false, vir_now = false; DevBuf<double> virow, virpart; double *h_vir = nullptr;
   // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
   bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
   double *d_dt = nullptr;
@@ -683,6 +685,8 @@ static void build_plan(b200_sph *h)
     }
     h->plan.push_back(p);
   }
+  // pair virial (Pair::virial_fdotr_compute) on request: the next force evaluation of b200_setup / the last step of b200_run
+  bool vir_request = false, vir_now = false; DevBuf<double> virow, virpart; double *h_vir = nullptr;
   // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
   bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
   double *d_dt = nullptr;
@@ -744,6 +748,7 @@ static TileArgs tile_args(b200_sph *h, int pstride)
   A.scan_far = h->d_scan_far; A.tiles = h->tiles.p; A.ntiles = h->ntiles; A.counter = h->d_tflags + 4;
   A.xt = c.xt.p; A.vr_out = c.vr.p; A.fd = c.fd.p; A.de = c.de.p;
   A.vm = c.vm.p; A.cg_out = c.cgm.p; A.gorder = h->gorder.p; A.dim = h->g.dim;
+  A.virow = h->virow.p;
   return A;
 }
 // which: 0 all records, 1 owned atoms only, 2 ghosts only (halo overlap: the ghosts' records wait for the halo)
@@ -818,12 +823,15 @@ template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &
   constexpr bool F = (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) != 0, H = (KINDS & K_HEAT) != 0;
   constexpr int NP = F ? (H ? 5 : 4) : 3, NK = (F ? 1 : 0) + (H ? 1 : 0);
   size_t smem = TileSmem<NP, NK>::bytes(h->tile_cap);
-  if (h->tile_split == 1) {
-    if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
-    else launch_tiles(h, k_tile_force<KINDS, 1, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
+  if (h->vir_now && F) {            // thermo step: the instantiation that also sums the rows' virial
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+    else launch_tiles(h, k_tile_force<KINDS, 2, false, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+  } else if (h->tile_split == 1) {
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
+    else launch_tiles(h, k_tile_force<KINDS, 1, false, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
   } else {
-    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
-    else launch_tiles(h, k_tile_force<KINDS, 2, false>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+    if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true, false>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+    else launch_tiles(h, k_tile_force<KINDS, 2, false, false>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
   }
 }
 static int tile_records_mp(b200_sph *h, int mode, const PairTab *fluid)
@@ -1074,7 +1082,21 @@ static void force_clear(b200_sph *h)
   CK(cudaMemsetAsync(h->C().fd.p, 0, (size_t)na * sizeof(double4), h->st));
   CK(cudaMemsetAsync(h->C().de.p, 0, (size_t)na * sizeof(double), h->st));
 }
-static void pair_compute_all(b200_sph *h) { for (const Pass &p : h->plan) run_pass(h, p); }
+// Pair::virial_fdotr_compute (pair.cpp:1403-1451) of the pair forces just computed, before the reverse halo
+static void pair_compute_all(b200_sph *h)
+{
+  const bool rowsum = h->vir_now && h->rows_tiled && !h->multiphase;      // single-phase tile path: no forces on ghosts, the rows sum their pairs (k_tile_force VIR)
+  if (rowsum && h->nlocal) { h->virow.ensure((size_t)h->nlocal * 6); CK(cudaMemsetAsync(h->virow.p, 0, (size_t)h->nlocal * 6 * sizeof(double), h->st)); }
+  for (const Pass &p : h->plan) run_pass(h, p);
+  if (!h->vir_now) return;
+  halo_wait(h);
+  h->virpart.ensure(VIR_BLOCKS * 6 + 8);
+  if (rowsum) LAUNCH(h, k_virial_partial, VIR_BLOCKS, VIR_THREADS, h->nlocal, (const double4 *)nullptr, (const double4 *)nullptr, (const double *)h->virow.p, h->virpart.p);
+  else LAUNCH(h, k_virial_partial, VIR_BLOCKS, VIR_THREADS, h->nall(), (const double4 *)h->C().xt.p, (const double4 *)h->C().fd.p, (const double *)nullptr, h->virpart.p);
+  LAUNCH(h, k_virial_final, 1, 32, h->virpart.p, h->virpart.p + VIR_BLOCKS * 6);
+  CK(cudaMemcpyAsync(h->h_vir, h->virpart.p + VIR_BLOCKS * 6, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  h->vir_now = false;
+}
 static void post_final(b200_sph *h, int rev, int post, int fin)
 {
   const int B = 256;
@@ -1228,6 +1250,7 @@ static void do_setup(b200_sph *h)
   build_plan(h);
   neighbor_build(h, true);
   h->nbuilds = 0;
+  h->vir_now = h->vir_request; h->vir_request = false;
   force_clear(h);
   if (h->nlocal) LAUNCH(h, k_setup_pre_force, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays());
   // ghosts carry vest of the border comm (before setup_pre_force), exactly as in Verlet::setup
@@ -1248,6 +1271,7 @@ static void do_run(b200_sph *h, int n)
     if (neigh_decide(h)) reneighbor(h);
     else if (overlap_ok(h)) { far_flags(h); halo_async(h, [&]() { forward_comm(h); }); }     // interior tiles start on the owned atoms' displacement bound
     else { forward_comm(h); far_flags(h); }
+    if (s == n - 1 && h->vir_request) { h->vir_now = true; h->vir_request = false; }
     force_clear(h);
     pair_compute_all(h);
     post_final(h, 1, 1, 1);
@@ -1345,6 +1369,7 @@ int b200_create(b200_sph **out, int device)
   h->nsm = prop.multiProcessorCount;
   CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
   CK(cudaMallocHost(&h->h_flags, 32 * sizeof(int)));
+  CK(cudaMallocHost(&h->h_vir, 8 * sizeof(double))); memset(h->h_vir, 0, 8 * sizeof(double));
   memset(&h->fl, 0, sizeof h->fl);
   *out = h;
   API_END
@@ -1364,7 +1389,7 @@ int b200_destroy(b200_sph *h)
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  cudaFree(h->d_flags); cudaFreeHost(h->h_flags);
+  cudaFree(h->d_flags); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_vir); h->virow.release(); h->virpart.release();
   if (h->st2) cudaStreamDestroy(h->st2); if (h->ev_main) cudaEventDestroy(h->ev_main); if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   h->tiles.release(); h->gtiles.release(); h->rowtile.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
@@ -1496,6 +1521,15 @@ int b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, doubl
   API_END
 }
 int b200_get_timestep(b200_sph *h, double *dt) { *dt = h->dt; return 0; }
+int b200_request_virial(b200_sph *h) { h->vir_request = true; return 0; }
+int b200_get_virial(b200_sph *h, double v[6])
+{
+  API_BEGIN
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < 6; k++) v[k] = h->h_vir[k];
+  API_END
+}
 int b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind, const double region[6])
 {
   if (region_kind < 0 || region_kind > 2) return fail("b200_fix_setmesode: bad arguments");

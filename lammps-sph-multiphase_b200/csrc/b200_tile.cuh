@@ -596,6 +596,7 @@ struct TileArgs {
   TileUni uni[3];
   // multiphase styles
   const double4 *vm; double4 *cg_out; const int *gorder; int dim;
+  double *virow;                             // VIR kernels: per-row virial sums [row][6]
 };
 
 // shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc[2] | mbarrier | tile id[2]
@@ -787,7 +788,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
 //  K_IDEAL  PairSPHIdealGas::compute         pair_sph_idealgas.cpp:48-175 (taitwater with p/rho^2 = 0.4 e/(m rho), c = sqrt(0.4 e/m))
 // UNI: both tables are uniform (TileUni) -> a branch-free body on register constants that ptxas interleaves across the
 // 8 neighbors of a group; otherwise the per-type tables are read from shared memory.
-template <int KINDS, int SPLIT, bool UNI>
+// VIR (thermo steps only): every row also sums 1/2 (x_i - x_j) (x) F_ij over its entries.  Summed over all rows this is
+// Pair::virial_fdotr_compute's sum of x (x) f over owned + ghost atoms (pair.cpp:1403-1451): a pair of two owned atoms appears in
+// both rows, a pair with a ghost contributes its other half on the rank (or periodic image) that owns the ghost.
+template <int KINDS, int SPLIT, bool UNI, bool VIR>
 __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __grid_constant__ TileArgs A)
 {
   constexpr bool HAS_FLUID = (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) != 0;
@@ -830,6 +834,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
       double u_drho = 0, u_de = 0, u_deh = 0;                                 // uniform body: raw sums, scaled after the loop
+      double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;                   // VIR: xx yy zz xy xz yz
+      auto vir = [&](double dx, double dy, double dz, double Fx, double Fy, double Fz) {
+        w0 += dx * Fx; w1 += dy * Fy; w2 += dz * Fz; w3 += dx * Fy; w4 += dx * Fz; w5 += dy * Fz;
+      };
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
         const int nf = (pass && valid) ? A.numfar[row] : 0;
@@ -866,11 +874,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                   fvisc = dvdr < 0.0 ? fvisc : 0.0;
                   const double fpair = u_k1 * (d.y + qd.y + fvisc) * wfd;     // -m m c0 (...) (h - r)^2
                   fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                  if (VIR) vir(dx, dy, dz, dx * fpair, dy * fpair, dz * fpair);
                   u_de += fpair * dvdr;                                       // x -0.5 at the end
                 } else {                                                      // Morris viscosity (morris :165-176)
                   const double fvisc = fast_div(u_k2 * wfd, rhoi * rhoj);     // 2 mu m m c0 (h - r)^2 / (rho_i rho_j)
                   const double fpair = u_k1 * (d.y + qd.y) * wfd;
                   fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
+                  if (VIR) vir(dx, dy, dz, dx * fpair + dvx * fvisc, dy * fpair + dvy * fvisc, dz * fpair + dvz * fvisc);
                   u_de += fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz);
                 }
                 u_drho += dvdr * wfd;                                         // x m c0 at the end
@@ -909,11 +919,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                     }
                     const double fpair = -mm * (d.y + qd.y + fvisc) * wfd;
                     fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                    if (VIR) vir(dx, dy, dz, dx * fpair, dy * fpair, dz * fpair);
                     ade += -0.5 * fpair * dvdr;
                   } else {
                     const double fvisc = 2.0 * P.visc[ij] / (rhoi * rhoj) * mm * wfd;
                     const double fpair = -mm * (d.y + qd.y) * wfd;
                     fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
+                    if (VIR) vir(dx, dy, dz, dx * fpair + dvx * fvisc, dy * fpair + dvy * fvisc, dz * fpair + dvz * fvisc);
                     ade += -0.5 * (fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz));
                   }
                   adrho += mj * dvdr * wfd;
@@ -937,12 +949,20 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       for (int o = LPW; o < 32; o <<= 1) {
         fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
         adrho += __shfl_xor_sync(FULLMASK, adrho, o); ade += __shfl_xor_sync(FULLMASK, ade, o);
+        if (VIR) {
+          w0 += __shfl_xor_sync(FULLMASK, w0, o); w1 += __shfl_xor_sync(FULLMASK, w1, o); w2 += __shfl_xor_sync(FULLMASK, w2, o);
+          w3 += __shfl_xor_sync(FULLMASK, w3, o); w4 += __shfl_xor_sync(FULLMASK, w4, o); w5 += __shfl_xor_sync(FULLMASK, w5, o);
+        }
       }
       if (valid && sub == 0) {
         double4 f = A.fd[row];
         f.x += fx; f.y += fy; f.z += fz; f.w += adrho;
         A.fd[row] = f;
         A.de[row] += ade;
+        if (VIR) {
+          double *w = A.virow + (size_t)row * 6;
+          w[0] += 0.5 * w0; w[1] += 0.5 * w1; w[2] += 0.5 * w2; w[3] += 0.5 * w3; w[4] += 0.5 * w4; w[5] += 0.5 * w5;
+        }
       }
     }
     L.release();

@@ -33,6 +33,16 @@ class Sim:
             api.check(api.comm_init(h, brick.world, brick.rank, _ip(grid), _ip(loc), _ip(nb), nccl_id))
         self._configure()
 
+    def request_virial(self):
+        """arm Pair::virial_fdotr_compute for the force evaluation that ends the next setup() / run()"""
+        self.api.check(self.api.request_virial(self.h))
+
+    def virial(self):
+        """pair virial xx yy zz xy xz yz of that evaluation (this rank's share)"""
+        v = np.zeros(6)
+        self.api.check(self.api.get_virial(self.h, _dp(v)))
+        return v
+
     def timestep(self):
         """update->dt as the engine holds it (changes under fix dt/reset)"""
         dt = C.c_double()

@@ -147,10 +147,12 @@ void VerletB200::setup()
   atom->nghost = 0;
   configure();
   upload();
+  ev_set(update->ntimestep);
+  if (vflag) check(b200_request_virial(h));       // thermo output of step 0 needs the pair virial (Pair::virial_fdotr_compute)
   check(b200_setup(h));
   { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // FixDtReset::setup may already have changed it
   download();
-  ev_set(update->ntimestep);
+  if (vflag && force->pair) check(b200_get_virial(h, force->pair->virial));
   modify->setup(vflag);
   output->setup();
   update->setupflag = 0;
@@ -170,6 +172,8 @@ void VerletB200::run(int n)
     if (next <= update->ntimestep) next = update->ntimestep + 1;
     int k = (int)(next - update->ntimestep);
     timer->stamp();
+    ev_set(next);                                   // does the step that ends this segment tally the virial? (integrate.cpp:120-150)
+    if (vflag) check(b200_request_virial(h));
     check(b200_run(h, k));
     check(b200_sync(h));
     update->ntimestep += k;
@@ -181,6 +185,7 @@ void VerletB200::run(int n)
     }
     if (update->ntimestep == output->next) {
       ev_set(update->ntimestep);
+      if (vflag && force->pair) check(b200_get_virial(h, force->pair->virial));
       output->write(update->ntimestep);
       timer->stamp(TIME_OUTPUT);
     }

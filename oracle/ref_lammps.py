@@ -46,6 +46,7 @@ def _load():
         _lib.refshim_cutneigh.restype = None
         _lib.refshim_cutneigh.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         _lib.refshim_has_full.restype = C.c_int; _lib.refshim_has_full.argtypes = [C.c_void_p]
+        _lib.refshim_virial.restype = None; _lib.refshim_virial.argtypes = [C.c_void_p, C.c_void_p]
         _lib.refshim_neigh_full.restype = C.c_longlong
         _lib.refshim_neigh_full.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     return _lib
@@ -110,6 +111,12 @@ class RefLammps:
         if multiphase:
             names += ["colorgradient", "rmass"]
         return {k: self.get(k, ghost) for k in names}
+
+    def virial(self):
+        """force->pair->virial (xx yy zz xy xz yz) of the last thermo step"""
+        v = np.zeros(6)
+        self.lib.refshim_virial(self.p, v.ctypes.data_as(C.c_void_p))
+        return v
 
     def cutneigh(self):
         n1 = self.ntypes + 1

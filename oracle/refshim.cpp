@@ -120,6 +120,8 @@ static NeighList *half_list(LAMMPS *l)
   }
   return NULL;
 }
+// force->pair->virial of the last step on which the virial was tallied (thermo steps), xx yy zz xy xz yz
+void refshim_virial(void *p, double *v) { memcpy(v, ((LAMMPS *)p)->force->pair->virial, 6 * sizeof(double)); }
 int refshim_has_full(void *p) { return full_list((LAMMPS *)p) != NULL; }
 // numneigh[nlocal]; if j != NULL also fills entries (local indices incl. ghosts) in list order; returns total or -1
 long long refshim_neigh_full(void *p, int *numneigh, long long nentries, int *j)

@@ -80,6 +80,7 @@ struct osph_sph {
   double dt, ftm2v; long long ntimestep;
   long long nsteps_done, ninserted, maxneighseen;
   int setup_done;
+  int vir_request; double virial[6];
 };
 
 static char errbuf[512] = "";
@@ -1197,6 +1198,20 @@ int osph_reneighbor(osph_sph *s)
   return neighbor_build(s);
 }
 
+/* Pair::virial_fdotr_compute, pair.cpp:1403-1451 (newton on: owned + ghost atoms, before the reverse halo) */
+static void virial_fdotr(osph_sph *s)
+{
+  int nall = s->nlocal + s->nghost;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nall; i++) {
+    const double *x = &s->x[3*i], *f = &s->f[3*i];
+    v[0] += x[0]*f[0]; v[1] += x[1]*f[1]; v[2] += x[2]*f[2]; v[3] += x[0]*f[1]; v[4] += x[0]*f[2]; v[5] += x[1]*f[2];
+  }
+  memcpy(s->virial, v, sizeof v);
+}
+int osph_request_virial(osph_sph *s) { s->vir_request = 1; return 0; }
+int osph_get_virial(osph_sph *s, double v[6]) { memcpy(v, s->virial, 6 * sizeof(double)); return 0; }
+
 /* Verlet::setup, verlet.cpp:88-142 */
 int osph_setup(osph_sph *s)
 {
@@ -1212,6 +1227,7 @@ int osph_setup(osph_sph *s)
     if (s->fix[i].kind == FIX_MESO)
       for (int a = 0; a < s->nlocal; a++) if (s->mask[a] & s->fix[i].groupbit) for (int d = 0; d < 3; d++) s->vest[3*a+d] = s->v[3*a+d];
   if (osph_pair_compute_all(s)) return -1;
+  if (s->vir_request) { virial_fdotr(s); s->vir_request = 0; }
   comm_reverse(s);
   osph_post_force(s); /* modify->setup: FixGravity::setup -> post_force */
   for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_DT_RESET) fix_dt_reset(s, &s->fix[i]);   /* FixDtReset::setup -> end_of_step */
@@ -1230,6 +1246,7 @@ int osph_run(osph_sph *s, int nsteps)
     else if (osph_reneighbor(s)) return -1;
     osph_force_clear(s);
     if (osph_pair_compute_all(s)) return -1;
+    if (it == nsteps - 1 && s->vir_request) { virial_fdotr(s); s->vir_request = 0; }
     comm_reverse(s);
     osph_post_force(s);
     osph_final_integrate(s);

@@ -33,6 +33,8 @@
 #define b200_fix_setmesode     osph_fix_setmesode
 #define b200_fix_dt_reset      osph_fix_dt_reset
 #define b200_get_timestep      osph_get_timestep
+#define b200_request_virial    osph_request_virial
+#define b200_get_virial        osph_get_virial
 #define b200_set_atoms         osph_set_atoms
 #define b200_get_natoms        osph_get_natoms
 #define b200_get_atoms         osph_get_atoms

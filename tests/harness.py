@@ -83,15 +83,21 @@ def run_case(make_sim, name, tol_step=1e-10, tol_traj=None):
         assert np.array_equal(deck.mass_[1:], g["mass"][1:])
     sim = make_sim(deck)
     sim.set_atoms(**state_from(g, "init_", case.multiphase))
+    sim.request_virial()          # thermo output at step 0 and at the last step: the reference tallies the pair virial there
     sim.setup()
     e0 = compare_state(sim.get_atoms(), g, "s0_", case.multiphase, tol_step, name + " run 0")
+    e0["virial"] = relerr(sim.virial(), g["s0_virial"])
+    assert e0["virial"] <= 10 * tol_step, "%s run 0: pair virial off by %g" % (name, e0["virial"])
     compare_neighbors(sim, g)
     assert sim.natoms()[1] == int(g["s0_nghost"]), "ghost count"
     sim.setup()
+    sim.request_virial()
     sim.run(case.nsteps)
     got = sim.get_atoms()
     assert len(got["type"]) == len(g["sN_type"]), "particle count after run"
     eN = compare_state(got, g, "sN_", case.multiphase, tol_traj or case.tol_traj, name + " run N")
+    eN["virial"] = relerr(sim.virial(), g["sN_virial"])
+    assert eN["virial"] <= 10 * (tol_traj or case.tol_traj), "%s run N: pair virial off by %g" % (name, eN["virial"])
     compare_neighbors(sim, g, "nlN_num", "nlN_hash")
     c = sim.counters()
     assert c["builds"] == int(g["sN_nbuilds"]), "neighbor builds %d vs reference %d" % (c["builds"], int(g["sN_nbuilds"]))

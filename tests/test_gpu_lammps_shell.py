@@ -23,6 +23,7 @@ FMT = "%d %d " + " ".join(["%.17g"] * 11)
 def deck_text(case, nsteps):
     return "\n".join([case.header_text().replace("atom_modify map array sort 0 0", "atom_modify map array"), case.create, case.lammps_text(),
                       "compute crho all meso_rho/atom", "compute ce all meso_e/atom", "thermo 10",
+                      "thermo_style custom step press pxx pyy pxy", "thermo_modify format float %.15g norm no",
                       "dump dfin all custom %d dump.final %s" % (nsteps, COLS), 'dump_modify dfin sort id format "%s"' % FMT,
                       "run %d" % nsteps, ""])
 
@@ -42,13 +43,29 @@ def run(exe, args, workdir, text):
     return np.array(rows), p.stdout
 
 
+def thermo_rows(stdout):
+    """the numeric rows under the `Step Press Pxx Pyy Pxy` header"""
+    rows, on = [], False
+    for l in stdout.splitlines():
+        t = l.split()
+        if t[:2] == ["Step", "Press"]:
+            on = True; continue
+        if on:
+            try:
+                rows.append([float(v) for v in t])
+                assert len(t) == 5
+            except (ValueError, AssertionError):
+                on = False
+    return np.array(rows)
+
+
 @pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10), ("dam2d_dtreset", 30, 1e-9)])
 def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
     case = cases.CASES[name]
     text = deck_text(case, nsteps)
-    a, _ = run(REF, [], str(tmp_path / "ref"), text)
+    a, a_out = run(REF, [], str(tmp_path / "ref"), text)
     b, out = run(B200, ["-sf", "b200"], str(tmp_path / "b200"), text)
     assert "B200 engine" in out
     assert a.shape == b.shape, "particle counts differ: %s vs %s" % (a.shape, b.shape)
@@ -58,3 +75,9 @@ def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     for lo, hi, nm in ((2, 5, "x"), (5, 8, "v"), (8, 11, "f"), (11, 12, "rho"), (12, 13, "e")):
         errs[nm] = relerr(b[:, lo:hi], a[:, lo:hi])
     assert all(v <= tol for v in errs.values()), errs
+    # thermo pressure (needs the pair virial of the engine on thermo steps): every printed line must agree
+    pa, pb = thermo_rows(a_out), thermo_rows(out)
+    assert pa.shape == pb.shape and len(pa) >= 2, (pa.shape, pb.shape)
+    assert np.array_equal(pa[:, 0], pb[:, 0])
+    scale = np.abs(pa[:, 1:]).max()
+    assert np.abs(pa[:, 1:] - pb[:, 1:]).max() <= 100 * tol * max(scale, 1e-300), (pa[-1], pb[-1])
