@@ -106,6 +106,15 @@ int  b200_comm_init(b200_sph *h, int world, int rank, const int procgrid[3], con
  * sublo/subhi = this rank's sub-domain (== box on one GPU), src/domain.h sublo. */
 int  b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[3],
                  const int periodicity[3], const double sublo[3], const double subhi[3]);
+/* boundary command styles per face, boundary[2*dim+side] = 0 p, 1 f, 2 s, 3 m (src/domain.h:32, Domain::set_boundary
+ * domain.cpp:1440-1492).  Optional: only decks with a shrink-wrapped face (s or m) need it.  The engine then re-fits the box to the
+ * owned atoms at setup and on every rebuild, exactly as Domain::reset_box (domain.cpp:338-406) + comm->setup + setup_bins
+ * (verlet.cpp:102, 244-248) do.  small = Domain::small (domain.cpp:184-186: 1e-4 x the box lengths when the box was created),
+ * minbox[2*dim+side] = minxlo, minxhi, minylo, ... (the box given by the deck, the floor of an m face, domain.cpp:192-207).
+ * Call after b200_domain; with several ranks the engine also re-derives sublo/subhi (Domain::set_local_box, domain.cpp:301-330,
+ * uniform xsplit).  b200_get_box returns the current box (for thermo volume and dumps). */
+int  b200_boundary(b200_sph *h, const int boundary[6], const double small[3], const double minbox[6]);
+int  b200_get_box(b200_sph *h, double boxlo[3], double boxhi[3]);
 /* atom_style meso (multiphase=0, atom_vec_meso.cpp) or meso/multiphase (=1);
  * mass = atom->mass [ntypes+1] (may be NULL for multiphase: rmass is used).    */
 int  b200_atom_style(b200_sph *h, int multiphase, int ntypes, const double *mass);

@@ -54,6 +54,8 @@ _PROTOS = {
     "comm_unique_id": (C.c_int, [C.c_char_p]),
     "comm_init": (C.c_int, [_H, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, C.c_char_p]),
     "domain": (C.c_int, [_H, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p, c_double_p]),
+    "boundary": (C.c_int, [_H, c_int_p, c_double_p, c_double_p]),
+    "get_box": (C.c_int, [_H, c_double_p, c_double_p]),
     "atom_style": (C.c_int, [_H, C.c_int, C.c_int, c_double_p]),
     "neighbor": (C.c_int, [_H, C.c_double, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double, C.c_double]),
     "timestep": (C.c_int, [_H, C.c_double, C.c_double, C.c_longlong]),

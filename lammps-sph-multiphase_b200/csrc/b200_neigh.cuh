@@ -116,6 +116,33 @@ __global__ void k_pbc(Geom g, int nlocal, double4 *xt)
   xt[i] = p;
 }
 
+// extent of the owned atoms for Domain::reset_box (domain.cpp:344-370): max(-x) and max(x) per dimension, reduced on order-preserving
+// 64-bit keys (min / max of doubles are exact, so the order of the reduction does not matter)
+__device__ __forceinline__ unsigned long long ext_key(double v)
+{
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_extent_init(unsigned long long *keys) { if (threadIdx.x < 6) keys[threadIdx.x] = ext_key(-1.0e20); }   // BIG, domain.cpp:39
+__global__ void k_extent(int nlocal, const double4 *xt, unsigned long long *keys)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[6];
+  if (i < nlocal) { double4 p = xt[i]; v[0] = -p.x; v[1] = p.x; v[2] = -p.y; v[3] = p.y; v[4] = -p.z; v[5] = p.z; }
+  else { for (int k = 0; k < 6; k++) v[k] = -1.0e20; }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 6; k++) { unsigned long long b = ext_key(v[k]); if (b > *(volatile unsigned long long *)(keys + k)) atomicMax(keys + k, b); }
+}
+__global__ void k_extent_decode(const unsigned long long *keys, double *out)
+{
+  if (threadIdx.x < 6) { unsigned long long k = keys[threadIdx.x]; out[threadIdx.x] = __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k)); }
+}
+
 // scatter element ids into their cell segment (arbitrary order inside a segment; fixed by k_sort_segments)
 __global__ void k_scatter(int n, const int *cellid, const int *cellstart, int *cellfill, int *perm)
 {

@@ -124,7 +124,9 @@ struct b200_sph {
   ncclComm_t nccl = nullptr;
   Swap swaps[6]; int nswap = 0;
   int next_orig = 0;
-  double *d_red = nullptr, *h_red = nullptr;
+  double *d_red = nullptr, *h_red = nullptr;   // [0..7] scalars, [8..13] atom extent (-min, max per dimension), d_red[16..21] its ordered keys
+  // boundary s / m (Domain::boundary, small, minxlo..): the box is re-fitted to the owned atoms on every rebuild
+  int boundary[3][2] = {{0, 0}, {0, 0}, {0, 0}}; bool shrink = false; double small[3] = {0, 0, 0}, minbox[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   DevBuf<unsigned long long> key, gkey;
   DevBuf<int> cso, csg, cellfill, scan_tmp;
   DevBuf<double> xhold, stage_d, d_mass;
@@ -285,6 +287,36 @@ static void setup_geometry(b200_sph *h)
     }
   }
   h->geom_ready = true;
+}
+
+// Domain::reset_box (domain.cpp:338-406): shrink-wrapped faces follow the extent of the owned atoms of ALL ranks; then set_global_box /
+// set_local_box (:268-330, uniform xsplit) and everything derived from the box: comm->setup, neighbor->setup_bins (verlet.cpp:102, 244-248)
+static void refit_box(b200_sph *h)
+{
+  Geom &g = h->g;
+  unsigned long long *keys = (unsigned long long *)(h->d_red + 16);
+  LAUNCH(h, k_extent_init, 1, 32, keys);
+  if (h->nlocal) LAUNCH(h, k_extent, nblk(h->nlocal, 256), 256, h->nlocal, h->C().xt.p, keys);
+  LAUNCH(h, k_extent_decode, 1, 32, keys, h->d_red + 8);
+  if (h->world > 1) NCK(g_nccl.AllReduce(h->d_red + 8, h->d_red + 8, 6, ncclDouble, ncclMax, h->nccl, h->st));
+  CK(cudaMemcpyAsync(h->h_red + 8, h->d_red + 8, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  const double *all = h->h_red + 8;
+  for (int d = 0; d < 3; d++) {
+    if (g.periodic[d]) continue;
+    if (h->boundary[d][0] == 2) g.boxlo[d] = -all[2 * d] - h->small[d];
+    else if (h->boundary[d][0] == 3) g.boxlo[d] = std::min(-all[2 * d] - h->small[d], h->minbox[d][0]);
+    if (h->boundary[d][1] == 2) g.boxhi[d] = all[2 * d + 1] + h->small[d];
+    else if (h->boundary[d][1] == 3) g.boxhi[d] = std::max(all[2 * d + 1] + h->small[d], h->minbox[d][1]);
+    if (g.boxlo[d] > g.boxhi[d]) throw std::string("Illegal simulation box");
+  }
+  for (int d = 0; d < 3; d++) {
+    double prd = g.boxhi[d] - g.boxlo[d];
+    int loc = h->myloc[d], pg = h->procgrid[d];
+    g.sublo[d] = g.boxlo[d] + prd * (loc * 1.0 / pg);
+    g.subhi[d] = loc < pg - 1 ? g.boxlo[d] + prd * ((loc + 1) * 1.0 / pg) : g.boxhi[d];
+  }
+  setup_geometry(h);
 }
 
 // ------------------------------------------------------------------ comm ----
@@ -548,6 +580,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   const int B = 256;
   int nl = h->nlocal;
   h->tbegin(T_NEIGH_BIN);
+  if (h->shrink) refit_box(h);       // shrink-wrapped dimensions are not periodic, so Domain::pbc (below) and the extent commute
   h->ensure_cap(nl + h->nghost, true);
   // 0. multi-rank: wrap, then migrate atoms that left the sub-domain (verlet.cpp:243-250)
   int nslots = nl;
@@ -1367,7 +1400,7 @@ int b200_create(b200_sph **out, int device)
   CK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   h->nsm = prop.multiProcessorCount;
-  CK(cudaMalloc(&h->d_red, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 8 * sizeof(double)));
+  CK(cudaMalloc(&h->d_red, 24 * sizeof(double))); CK(cudaMallocHost(&h->h_red, 16 * sizeof(double)));
   CK(cudaMallocHost(&h->h_flags, 32 * sizeof(int)));
   CK(cudaMallocHost(&h->h_vir, 8 * sizeof(double))); memset(h->h_vir, 0, 8 * sizeof(double));
   memset(&h->fl, 0, sizeof h->fl);
@@ -1434,6 +1467,30 @@ int b200_domain(b200_sph *h, int dim, const double boxlo[3], const double boxhi[
     if ((h->g.sublo[d] != boxlo[d] || h->g.subhi[d] != boxhi[d]) && h->world == 1) throw std::string("b200_domain: a sub-domain smaller than the box needs b200_comm_init first");
   }
   h->have_domain = true; h->geom_ready = false;
+  API_END
+}
+int b200_boundary(b200_sph *h, const int boundary[6], const double small[3], const double minbox[6])
+{
+  API_BEGIN
+  if (!h->have_domain) throw std::string("b200_boundary: call b200_domain first");
+  h->shrink = false;
+  for (int d = 0; d < 3; d++) {
+    for (int k = 0; k < 2; k++) {
+      int b = boundary[2 * d + k];
+      if (b < 0 || b > 3) throw std::string("b200_boundary: style must be 0 (p), 1 (f), 2 (s) or 3 (m)");
+      if ((b == 0) != (h->g.periodic[d] != 0)) throw std::string("b200_boundary: styles disagree with the periodicity given to b200_domain");
+      h->boundary[d][k] = b; h->minbox[d][k] = minbox ? minbox[2 * d + k] : 0.0;
+      if (b >= 2) h->shrink = true;
+    }
+    h->small[d] = small ? small[d] : 0.0;
+  }
+  h->geom_ready = false;
+  API_END
+}
+int b200_get_box(b200_sph *h, double boxlo[3], double boxhi[3])
+{
+  API_BEGIN
+  for (int d = 0; d < 3; d++) { boxlo[d] = h->g.boxlo[d]; boxhi[d] = h->g.boxhi[d]; }
   API_END
 }
 int b200_atom_style(b200_sph *h, int multiphase, int ntypes, const double *mass)

@@ -149,12 +149,27 @@ class Deck:
             raise DeckError("the b200 SPH package requires newton on")
         self.dimension = int(dimension)
         b = boundary.split()
-        if len(b) != 3 or any(c not in ("p", "f") for c in b):
-            raise DeckError("Illegal boundary command (b200: only p and f are supported)")
-        self.periodicity = [1 if c == "p" else 0 for c in b]
+        if len(b) != 3:
+            raise DeckError("Illegal boundary command")
+        self.boundary = []        # Domain::set_boundary (domain.cpp:1440-1492): one letter = both faces, two = lo then hi
+        for word in b:
+            if len(word) not in (1, 2) or any(c not in "pfsm" for c in word):
+                raise DeckError("Illegal boundary command")
+            faces = [("pfsm").index(c) for c in (word if len(word) == 2 else word * 2)]
+            if (faces[0] == 0) != (faces[1] == 0):
+                raise DeckError("Both sides of boundary must be periodic")
+            self.boundary.append(faces)
+        self.periodicity = [1 if f[0] == 0 else 0 for f in self.boundary]
+        self.shrink = any(v >= 2 for f in self.boundary for v in f)
         if self.dimension == 2 and not self.periodicity[2]:
             raise DeckError("Cannot use nonperiodic boundares with 2d simulation")  # sic, src/domain.cpp
         self.boxlo = [float(v) for v in box[0]]; self.boxhi = [float(v) for v in box[1]]
+        # Domain::set_initial_box (domain.cpp:181-207): small from the box as given, s faces pushed out by it, m faces remember it
+        self.small = [1.0e-4 * (hi - lo) for lo, hi in zip(self.boxlo, self.boxhi)]
+        self.minbox = [[self.boxlo[d], self.boxhi[d]] for d in range(3)]
+        for d in range(3):
+            if self.boundary[d][0] == 2: self.boxlo[d] -= self.small[d]
+            if self.boundary[d][1] == 2: self.boxhi[d] += self.small[d]
         self.multiphase = atom_style == "meso/multiphase"
         self.ntypes = int(ntypes)
         self.ftm2v = 1.0 if units in ("si", "lj", "cgs") else None

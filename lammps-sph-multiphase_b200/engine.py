@@ -43,6 +43,12 @@ class Sim:
         self.api.check(self.api.get_virial(self.h, _dp(v)))
         return v
 
+    def box(self):
+        """domain->boxlo / boxhi as the engine holds them (move under boundary s / m)"""
+        lo, hi = np.zeros(3), np.zeros(3)
+        self.api.check(self.api.get_box(self.h, _dp(lo), _dp(hi)))
+        return lo, hi
+
     def timestep(self):
         """update->dt as the engine holds it (changes under fix dt/reset)"""
         dt = C.c_double()
@@ -71,6 +77,10 @@ class Sim:
         slo = np.array(self.brick.sublo, np.float64) if self.brick is not None else lo
         shi = np.array(self.brick.subhi, np.float64) if self.brick is not None else hi
         ck(api.domain(h, d.dimension, _dp(lo), _dp(hi), _ip(per), _dp(slo), _dp(shi)))
+        if d.shrink:       # boundary s / m: the engine re-fits the box on every rebuild (Domain::reset_box)
+            bnd = np.array(d.boundary, np.int32).reshape(6); small = np.array(d.small, np.float64)
+            mb = np.array(d.minbox, np.float64).reshape(6)
+            ck(api.boundary(h, _ip(bnd), _dp(small), _dp(mb)))
         mass = np.ascontiguousarray(d.mass_, np.float64)
         ck(api.atom_style(h, int(d.multiphase), d.ntypes, _dp(mass)))
         cn = np.ascontiguousarray(d.cutneighsq, np.float64)

@@ -28,6 +28,13 @@ VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, ar
 
 VerletB200::~VerletB200() { if (h) b200_destroy(h); }
 
+// Domain::small (domain.h:148) is protected; the engine needs it to re-fit shrink-wrapped faces exactly as Domain::reset_box does
+namespace {
+struct DomainPeek : public Domain {
+  static const double *small_of(const Domain *d) { return d->*(&DomainPeek::small); }
+};
+}
+
 void VerletB200::check(int rc) { if (rc < 0) error->all(FLERR, b200_last_error()); }
 
 void VerletB200::init()
@@ -46,6 +53,10 @@ void VerletB200::configure()
   int n = atom->ntypes;
   int multiphase = atom->rmass_flag ? 1 : 0;
   check(b200_domain(h, domain->dimension, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi));
+  if (domain->nonperiodic == 2) {                 // boundary s / m: the engine owns the box between output steps
+    const double minbox[6] = {domain->minxlo, domain->minxhi, domain->minylo, domain->minyhi, domain->minzlo, domain->minzhi};
+    check(b200_boundary(h, &domain->boundary[0][0], DomainPeek::small_of(domain), minbox));
+  }
   check(b200_atom_style(h, multiphase, n, atom->mass));
   // Neighbor::init, neighbor.cpp:259-282 (cutneighsq itself is protected there)
   std::vector<double> cn((n + 1) * (n + 1), 0.0);
@@ -130,6 +141,11 @@ void VerletB200::download()
   long long c[8];
   b200_get_counters(h, c);
   neighbor->ncalls = c[1]; neighbor->ndanger = c[7];
+  if (domain->nonperiodic == 2) {                 // thermo volume, dumps: the box as the last rebuild left it
+    check(b200_get_box(h, domain->boxlo, domain->boxhi));
+    domain->set_global_box();
+    domain->set_local_box();
+  }
 }
 
 /* Verlet::setup, verlet.cpp:88-142 */

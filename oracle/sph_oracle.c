@@ -55,6 +55,7 @@ typedef struct {
 struct osph_sph {
   int dim, periodic[3], multiphase, ntypes, ghost_velocity;
   double boxlo[3], boxhi[3], prd[3], sublo[3], subhi[3];
+  int boundary[3][2], shrink; double small[3], minbox[3][2];   /* Domain::boundary / small / minxlo.. (domain.h:32,62,148) */
   double *mass;
   int nlocal, nghost, nmax;
   double *x, *v, *vest, *f, *cg;            /* [nmax][3] */
@@ -161,6 +162,25 @@ int osph_domain(osph_sph *s, int dim, const double boxlo[3], const double boxhi[
   }
   return 0;
 }
+
+/* boundary s / m: Domain::set_boundary (domain.cpp:1486-1491, nonperiodic = 2) */
+int osph_boundary(osph_sph *s, const int boundary[6], const double small[3], const double minbox[6])
+{
+  s->shrink = 0;
+  for (int d = 0; d < 3; d++) {
+    for (int k = 0; k < 2; k++) {
+      int b = boundary[2*d+k];
+      if (b < 0 || b > 3) return fail("boundary style must be 0 (p), 1 (f), 2 (s) or 3 (m)");
+      if ((b == 0) != (s->periodic[d] != 0)) return fail("boundary styles disagree with the periodicity given to b200_domain");
+      s->boundary[d][k] = b; s->minbox[d][k] = minbox ? minbox[2*d+k] : 0.0;
+      if (b >= 2) s->shrink = 1;
+    }
+    s->small[d] = small ? small[d] : 0.0;
+  }
+  return 0;
+}
+int osph_get_box(osph_sph *s, double boxlo[3], double boxhi[3])
+{ for (int d = 0; d < 3; d++) { boxlo[d] = s->boxlo[d]; boxhi[d] = s->boxhi[d]; } return 0; }
 
 int osph_atom_style(osph_sph *s, int multiphase, int ntypes, const double *mass)
 {
@@ -322,6 +342,26 @@ static void domain_pbc(osph_sph *s)
       if (*xc < s->boxlo[d]) *xc += s->prd[d];
       if (*xc >= s->boxhi[d]) { *xc -= s->prd[d]; if (*xc < s->boxlo[d]) *xc = s->boxlo[d]; /* MAX(x,lo) */ }
     }
+}
+
+/* Domain::reset_box, src/domain.cpp:338-406 (orthogonal box): shrink-wrapped faces follow the extent of the owned atoms,
+ * then set_global_box / set_local_box (:268-330) refresh prd and the (single-rank) sub-domain. */
+static int domain_reset_box(osph_sph *s)
+{
+  if (!s->shrink) return 0;
+  double lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
+  for (int i = 0; i < s->nlocal; i++)
+    for (int d = 0; d < 3; d++) { double c = s->x[3*i+d]; if (c < lo[d]) lo[d] = c; if (c > hi[d]) hi[d] = c; }
+  for (int d = 0; d < 3; d++) {
+    if (s->periodic[d]) continue;
+    if (s->boundary[d][0] == 2) s->boxlo[d] = lo[d] - s->small[d];
+    else if (s->boundary[d][0] == 3) { double c = lo[d] - s->small[d]; s->boxlo[d] = c < s->minbox[d][0] ? c : s->minbox[d][0]; }
+    if (s->boundary[d][1] == 2) s->boxhi[d] = hi[d] + s->small[d];
+    else if (s->boundary[d][1] == 3) { double c = hi[d] + s->small[d]; s->boxhi[d] = c > s->minbox[d][1] ? c : s->minbox[d][1]; }
+    if (s->boxlo[d] > s->boxhi[d]) return fail("Illegal simulation box");
+  }
+  for (int d = 0; d < 3; d++) { s->prd[d] = s->boxhi[d] - s->boxlo[d]; s->sublo[d] = s->boxlo[d]; s->subhi[d] = s->boxhi[d]; }
+  return 0;
 }
 
 /* CommBrick::setup for a 1x1x1 processor grid, comm_brick.cpp:150-386.
@@ -1193,6 +1233,11 @@ int osph_reneighbor(osph_sph *s)
 {
   for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_PHASE_CHANGE) if (fix_phase_change_pre_exchange(s, &s->fix[i])) return -1;
   domain_pbc(s);
+  if (s->shrink) {    /* verlet.cpp:244-248: if (domain->box_change) reset_box, comm->setup, neighbor->setup_bins */
+    if (domain_reset_box(s)) return -1;
+    if (comm_setup(s)) return -1;
+    if (setup_bins(s)) return -1;
+  }
   /* comm->exchange(): no-op on a 1x1x1 grid (comm_brick.cpp:596 "if (procgrid[dim] == 1) continue") */
   comm_borders(s);
   return neighbor_build(s);
@@ -1217,6 +1262,7 @@ int osph_setup(osph_sph *s)
 {
   if (!s->cutneighsq) return fail("setup: b200_neighbor not called");
   domain_pbc(s);
+  if (domain_reset_box(s)) return -1;   /* verlet.cpp:102 */
   if (comm_setup(s)) return -1;
   if (setup_bins(s)) return -1;
   comm_borders(s);

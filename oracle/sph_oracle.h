@@ -17,6 +17,8 @@
 #define b200_comm_init         osph_comm_init
 #define b200_domain            osph_domain
 #define b200_atom_style        osph_atom_style
+#define b200_boundary          osph_boundary
+#define b200_get_box           osph_get_box
 #define b200_neighbor          osph_neighbor
 #define b200_timestep          osph_timestep
 #define b200_comm_modify       osph_comm_modify

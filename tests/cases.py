@@ -222,31 +222,36 @@ _add(_dam("dam2d_morris", 2, 40, morris=True))
 
 # ---- shock tube (examples/USER/sph/shock_tube/shock{2,3}d.lmp): sph/rhosum + sph/idealgas, per-type masses, fix setforce;
 #      the shipped deck shrink-wraps x (boundary s p p); here the tube is shortened and periodic in x (a second contact at the wrap)
-def _shock(name, dim, nsteps, onetype=False):
+def _shock(name, dim, nsteps, onetype=False, bnd="p p p", fill="box"):
     if dim == 3:
-        box = ((-12, -4, -4), (18, 4, 4)); lat = "sc"; bnd = "p p p"
+        box = ((-12, -4, -4), (18, 4, 4)); lat = "sc"
         right = "region right block 1 EDGE EDGE EDGE EDGE EDGE units box"
         sf = ("setforce", "NULL", 0.0, 0.0)
     else:
-        box = ((-30, -4, -0.05), (45, 4, 0.05)); lat = "sq"; bnd = "p p p"
+        box = ((-30, -4, -0.05), (45, 4, 0.05)); lat = "sq"
         right = "region right block 1 EDGE EDGE EDGE EDGE EDGE units box"
         sf = ("setforce", "NULL", 0.0, 0.0)
-    create = """lattice %s 1.0
-create_atoms 1 box
+    if fill != "box":      # atoms start short of the low-x face (an m face keeps the box there until the gas reaches it)
+        lat += " 1.0\nregion fill block %s EDGE EDGE EDGE EDGE EDGE units box" % fill
+        fill = "region fill"
+    else:
+        lat += " 1.0"
+    create = """lattice %s
+create_atoms 1 %s
 %s
 set region right type 2
 set type 1 meso_e 2.5
 set type 2 meso_e 0.625
 set type 1 meso_rho 1.0
-set type 2 meso_rho 0.25""" % (lat, right)
+set type 2 meso_rho 0.25""" % (lat, fill, right)
     if onetype:      # one atom type (symmetric coefficient tables -> the tile path), a hot and a cold half
-        create = """lattice %s 1.0
-create_atoms 1 box
+        create = """lattice %s
+create_atoms 1 %s
 %s
 set group all meso_e 2.5
 set region right meso_e 0.625
 set group all meso_rho 1.0
-displace_atoms all random 0.05 0.05 %s 4711 units box""" % (lat, right, "0.05" if dim == 3 else "0.0")
+displace_atoms all random 0.05 0.05 %s 4711 units box""" % (lat, fill, right, "0.05" if dim == 3 else "0.0")
         cmds = [("mass", "1", 1.0), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/idealgas"),
                 ("pair_coeff", "* *", "sph/rhosum", 4.0), ("pair_coeff", "* *", "sph/idealgas", 0.75, 4.0),
                 ("neighbor", 0.5), ("neigh_modify", dict(every=5, delay=0, check="yes")), ("timestep", 0.05),
@@ -262,6 +267,10 @@ displace_atoms all random 0.05 0.05 %s 4711 units box""" % (lat, right, "0.05" i
 _add(_shock("shock3d", 3, 20))
 _add(_shock("shock2d", 2, 40))
 _add(_shock("gas3d", 3, 15, onetype=True))
+# the shipped shock-tube decks as they are: shrink-wrapped x (examples/USER/sph/shock_tube/shock{2d,3d}.lmp:2-3, boundary s p p)
+_add(_shock("shock3d_shrink", 3, 45, bnd="s p p"))
+_add(_shock("shock2d_shrink", 2, 40, bnd="ms p p", fill="-25.5"))
+_add(_shock("gas3d_shrink", 3, 45, onetype=True, bnd="s p p"))
 
 
 # ---- C3 scaled down: periodic two-phase box (square_to_sphere/droplet.lmp + cube.lmp) ----

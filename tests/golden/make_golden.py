@@ -40,6 +40,9 @@ def generate(case):
     if len(jt) <= FULL_LIST_MAX:
         d["nl_jtag"] = jt; d["nl_jimage"] = ji
     d["s0_nghost"] = np.array(ref.nghost)
+    shrink = any(c in case.boundary for c in "sm")
+    if shrink:
+        d["s0_box"] = np.array(ref.box()[:2])
     d["s0_virial"] = ref.virial()      # thermo prints at step 0 and at the last step: the pair virial is tallied there (integrate.cpp ev_set)
     cn = ref.cutneigh()
     d["cutneighsq"] = cn["cutneighsq"]; d["cutneighmax"] = np.array(cn["cutneighmax"]); d["cutghost"] = np.array(cn["cutghost"])
@@ -50,6 +53,8 @@ def generate(case):
     num, jt, ji = ref.neighbor_list()
     d["nlN_num"] = num; d["nlN_hash"] = row_hashes(num, jt, ji)
     d["sN_virial"] = ref.virial()
+    if shrink:
+        d["sN_box"] = np.array(ref.box()[:2])
     d["sN_nbuilds"] = np.array(ref.nbuilds); d["sN_ndanger"] = np.array(ref.ndanger)
     d["nsteps"] = np.array(case.nsteps)
     ref.close()

@@ -90,6 +90,8 @@ def run_case(make_sim, name, tol_step=1e-10, tol_traj=None):
     assert e0["virial"] <= 10 * tol_step, "%s run 0: pair virial off by %g" % (name, e0["virial"])
     compare_neighbors(sim, g)
     assert sim.natoms()[1] == int(g["s0_nghost"]), "ghost count"
+    if "s0_box" in g:             # boundary s / m: the box Domain::reset_box fitted, bit for bit
+        assert np.array_equal(np.array(sim.box()), g["s0_box"]), "%s run 0: shrink-wrapped box %s vs %s" % (name, sim.box(), g["s0_box"])
     sim.setup()
     sim.request_virial()
     sim.run(case.nsteps)
@@ -99,6 +101,8 @@ def run_case(make_sim, name, tol_step=1e-10, tol_traj=None):
     eN["virial"] = relerr(sim.virial(), g["sN_virial"])
     assert eN["virial"] <= 10 * (tol_traj or case.tol_traj), "%s run N: pair virial off by %g" % (name, eN["virial"])
     compare_neighbors(sim, g, "nlN_num", "nlN_hash")
+    if "sN_box" in g:
+        assert relerr(np.array(sim.box()), g["sN_box"]) <= (tol_traj or case.tol_traj), "%s run N: shrink-wrapped box" % name
     c = sim.counters()
     assert c["builds"] == int(g["sN_nbuilds"]), "neighbor builds %d vs reference %d" % (c["builds"], int(g["sN_nbuilds"]))
     sim.close()

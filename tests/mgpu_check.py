@@ -26,7 +26,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
-    names = sys.argv[1:] or ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin", "bubble3d"]
+    names = sys.argv[1:] or ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin", "bubble3d", "shock3d_shrink"]
     api = pkg.load()
     failed = 0
     for name in names:
