@@ -718,11 +718,6 @@ static void build_plan(b200_sph *h)
     }
     h->plan.push_back(p);
   }
-  // pair virial (Pair::virial_fdotr_compute) on request: the next force evaluation of b200_setup / the last step of b200_run
-  bool vir_request = false, vir_now = false; DevBuf<double> virow, virpart; double *h_vir = nullptr;
-  // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
-  bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
-  double *d_dt = nullptr;
   // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
   if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
