@@ -43,3 +43,28 @@ def test_oracle_exports_same_abi():
     import harness
     api = harness.oracle_api()
     assert api.version().startswith(b"sph_oracle")
+
+
+def test_package_install_script(tmp_path):
+    """USER-B200/Install.sh in a mock LAMMPS src/: install twice (idempotent), then uninstall"""
+    import shutil
+    import subprocess
+    pk = os.path.join(ROOT, "lammps-sph-multiphase_b200", "lammps", "USER-B200")
+    src = tmp_path / "src"
+    shutil.copytree(pk, src / "USER-B200")
+    (src / "Makefile.package").write_text("PKG_INC = -DX \nPKG_PATH = \nPKG_LIB = -lz \n")
+    (src / "Makefile.package.settings").write_text("# settings\n")
+    run = lambda mode: subprocess.run(["sh", "Install.sh", str(mode)], cwd=src / "USER-B200", capture_output=True, text=True)
+    assert run(1).returncode != 0 and not (src / "verlet_b200.cpp").exists()       # USER-SPH (multiphase) must be there first
+    (src / "pair_sph_taitwater_multiphase.cpp").write_text("")
+    for _ in range(2):
+        assert run(1).returncode == 0
+    shells = sorted(f for f in os.listdir(pk) if f.endswith((".h", ".cpp")))
+    assert all((src / f).exists() for f in shells) and len(shells) == 7
+    mk = (src / "Makefile.package").read_text()
+    assert mk.count("$(b200sph_INC)") == 1 and mk.count("$(b200sph_LIB)") == 1 and "-DX" in mk and "-lz" in mk
+    assert (src / "Makefile.package.settings").read_text().count("Makefile.b200sph") == 1
+    assert run(0).returncode == 0
+    assert not any((src / f).exists() for f in shells)
+    assert "b200sph" not in (src / "Makefile.package").read_text() + (src / "Makefile.package.settings").read_text()
+    assert "-DX" in (src / "Makefile.package").read_text()
