@@ -1,0 +1,146 @@
+"""GPU: the BASELINE configurations at (or near) their full sizes.
+
+  C2 (1 028 768 particles, the bench workload): the oracle still finishes in ~30 s, so the check is the direct one --
+      every field to 1e-10 after a rebuild cycle, neighbor rows bit for bit (digest of the sorted (tag, image) rows).
+  C3 at 1 M particles (nx = 100): direct oracle check of setup + one step (4 multiphase sub-styles, rebuilt every step).
+  C3 at its full 4.1 M (nx = 160) and C4 at its full 16 M (nx = 252): the oracle would need many minutes, so size-independent
+      properties instead: sampled neighbor-row lengths against a numpy brute force over ALL particles and periodic images,
+      pair forces sum to zero (newton's third law over the whole periodic box), particle bookkeeping, finite fields.
+"""
+import ctypes as C
+import hashlib
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cases      # noqa: E402
+import harness    # noqa: E402
+from util import relerr  # noqa: E402
+
+pkg = importlib.import_module("lammps-sph-multiphase_b200")
+pytestmark = pytest.mark.gpu
+TOL = 1e-10       # per step, fp64 fields (north_star)
+
+
+def _digest(sim):
+    num, jt, ji = sim.neighbor_list()
+    h = hashlib.sha1(memoryview(np.ascontiguousarray(num)))
+    h.update(memoryview(np.ascontiguousarray(jt))); h.update(memoryview(np.ascontiguousarray(ji)))
+    return h.hexdigest(), int(num.sum()), int(num.max())
+
+
+def _both(deck_of, atoms, nsteps, fields):
+    out = []
+    for mk in (pkg.B200Sim, harness.oracle_sim):
+        sim = mk(deck_of())
+        sim.set_atoms(**atoms)
+        sim.setup(); sim.run(nsteps)
+        out.append((sim.get_atoms(), _digest(sim), sim.counters()))
+        sim.close()
+    (a, da, ca), (b, db, cb) = out
+    assert np.array_equal(a["tag"], b["tag"]) and np.array_equal(a["type"], b["type"])
+    errs = {k: relerr(a[k], b[k]) for k in fields}
+    assert all(v <= TOL * max(nsteps, 1) for v in errs.values()), errs
+    assert da == db, "neighbor rows differ: %s vs %s" % (da[1:], db[1:])
+    assert ca["builds"] == cb["builds"]
+    return errs, da, ca
+
+
+def test_c2_full_size_against_oracle():
+    import bench
+    atoms, params = bench.dam_break_3d(1.0)
+    assert len(atoms["type"]) == 1028768
+    errs, dig, c = _both(lambda: bench.make_deck(pkg, params), atoms, 6, ("x", "v", "f", "rho", "e", "de", "drho"))     # rebuild at step 5
+    print("C2 full size: %d neighbor entries (max row %d), builds %d, errors %s" % (dig[1], dig[2], c["builds"], {k: "%.1e" % v for k, v in errs.items()}))
+
+
+def _mp_atoms(nx, kind):
+    import dev_bench
+    if kind == "c3":
+        return dev_bench.lattice_atoms(nx, jitter=0.2)
+    atoms = dev_bench.lattice_atoms(nx, 0.12, jitter=0.2)
+    dx = 1.0 / nx
+    atoms["rho"] = np.where(atoms["type"] == 2, 0.1, 1.0); atoms["rmass"] = atoms["rho"] * dx ** 3
+    atoms["cv"] = np.where(atoms["type"] == 2, 0.06, 0.04); atoms["e"] = np.where(atoms["type"] == 2, 0.06 * 0.6, 0.04)
+    atoms["mask"] = np.where(atoms["type"] == 2, 3, 1).astype(np.int32)
+    return atoms
+
+
+def test_c3_one_million_against_oracle():
+    nx = 100
+    atoms = _mp_atoms(nx, "c3")
+    errs, dig, c = _both(lambda: cases._droplet("c3", 3, nx, 1).deck(), atoms, 1,
+                         ("x", "v", "f", "rho", "e", "de", "drho", "colorgradient", "rmass"))
+    print("C3 1 M: %d neighbor entries, errors %s" % (dig[1], {k: "%.1e" % v for k, v in errs.items()}))
+
+
+def brute_rows(x, tag, lo, hi, cutsq, sample):
+    """the reference's pair test (neigh_full.cpp:241-340: rsq = dx*dx + dy*dy + dz*dz <= cutneighsq, fp64, no FMA) for the sampled
+    atoms against every particle and every periodic image (a ghost sits at x + shift, comm_brick.cpp:368); image code = 13 + sx + 3 sy + 9 sz"""
+    prd = hi - lo
+    rows = []
+    cut = np.sqrt(cutsq) * (1.0 + 1e-9)
+    for i in sample:
+        d = x - x[i]
+        d -= prd * np.round(d / prd)                              # coarse minimum image, only to pre-select candidates
+        cand = np.nonzero((np.abs(d) <= cut).all(1))[0]
+        got = []
+        for sx in (-1, 0, 1):
+            for sy in (-1, 0, 1):
+                for sz in (-1, 0, 1):
+                    xg = x[cand] + np.array([sx, sy, sz]) * prd   # one rounding per coordinate, as the border comm does
+                    dx, dy, dz = x[i, 0] - xg[:, 0], x[i, 1] - xg[:, 1], x[i, 2] - xg[:, 2]
+                    rsq = dx * dx + dy * dy + dz * dz
+                    ok = rsq <= cutsq
+                    if sx == 0 and sy == 0 and sz == 0:
+                        ok &= cand != i
+                    code = 13 + sx + 3 * sy + 9 * sz
+                    got += [(int(t), code) for t in tag[cand[ok]]]
+        rows.append(sorted(got))
+    return rows
+
+
+@pytest.mark.parametrize("kind,nx,nsteps", [("c3", 160, 4), ("c4", 252, 3)])
+def test_multiphase_full_size_properties(kind, nx, nsteps):
+    case = cases._droplet("c3", 3, nx, nsteps) if kind == "c3" else cases._bubble("c4", 3, nx, nsteps)
+    atoms = _mp_atoms(nx, kind)
+    n0 = len(atoms["type"])
+    assert n0 == nx ** 3
+    deck = case.deck()
+    cutsq = float(deck.cutneighsq[1, 1])
+    assert np.all(deck.cutneighsq[1:, 1:] == cutsq)
+    sim = pkg.B200Sim(deck)
+    sim.set_atoms(**atoms)
+    sim.setup(); sim.run(nsteps)
+    got = sim.get_atoms()
+    num = np.zeros(sim.natoms()[0], np.int32)          # counts only: the sorted (tag, image) export of 16 M rows would need tens of GB
+    sim.api.check(sim.api.get_neighbor_list(sim.h, len(num), num.ctypes.data_as(C.POINTER(C.c_int)), 0, None, None))
+    c = sim.counters()
+    sim.close()
+    n = len(got["type"])
+    assert n == n0 + c["inserted"] and len(np.unique(got["tag"])) == n
+    if kind == "c3":
+        assert c["inserted"] == 0
+    for k in ("x", "v", "f", "rho", "e", "de", "colorgradient", "rmass"):
+        assert np.isfinite(got[k]).all(), k
+    # Newton's third law over the whole periodic box (no external force in these decks): the pair forces cancel
+    f = got["f"]
+    assert np.abs(f.sum(0)).max() <= 1e-9 * np.abs(f).sum(0).max(), (f.sum(0), np.abs(f).sum(0))
+    # every pair is listed from both sides
+    assert int(num.sum()) % 2 == 0
+    # sampled rows: as many entries as a brute force over all particles and images finds (the rows themselves are compared entry by
+    # entry in the 1 M-particle oracle test above).  These decks rebuild every step (skin 0), so the list belongs to the final positions.
+    assert c["builds"] == nsteps
+    rng = np.random.default_rng(7)
+    sample = rng.choice(n, 24, replace=False)
+    lo, hi = np.array(deck.boxlo), np.array(deck.boxhi)
+    want = brute_rows(got["x"], got["tag"], lo, hi, cutsq, sample)
+    for i, w in zip(sample, want):
+        assert int(num[i]) == len(w), "row of atom %d (tag %d): %d vs %d entries" % (i, got["tag"][i], int(num[i]), len(w))
+    print("%s nx=%d: %d particles (+%d inserted), %d neighbor entries, sum f / sum |f| = %.1e" % (
+        kind, nx, n, c["inserted"], int(num.sum()), np.abs(f.sum(0)).max() / np.abs(f).sum(0).max()))
