@@ -83,7 +83,7 @@ __global__ void k_pack_forward(int n, const int *list, CommArrays a, int dim, do
 // xhold / dmaxsq (track): the ghosts' displacement since the build enters the same bound as the owned atoms' (k_initial_integrate),
 // so the far / mid zone flags need no all-reduce: every candidate of this rank's rows is an owned atom or one of its ghosts
 __global__ void k_unpack_forward(int n, int first, CommArrays a, const double *buf, int multiphase, int ghost_velocity,
-                                 const double *xhold, unsigned long long *dmaxsq)
+                                 const double *xhold, unsigned long long *dmaxsq, const int *gcell, unsigned *celld, int nlocal)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -94,8 +94,10 @@ __global__ void k_unpack_forward(int n, int first, CommArrays a, const double *b
   a.xt[i] = x;
   if (xhold) {
     double dx = x.x - xhold[3 * i], dy = x.y - xhold[3 * i + 1], dz = x.z - xhold[3 * i + 2];
-    unsigned long long bits = (unsigned long long)__double_as_longlong(dx * dx + dy * dy + dz * dz);
+    const double dsq = dx * dx + dy * dy + dz * dz;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(dsq);
     if (bits > *(volatile unsigned long long *)dmaxsq) atomicMax(dmaxsq, bits);
+    if (celld) cell_disp_max(celld, gcell[i - nlocal], dsq);
   }
   a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
   if (ghost_velocity) { v.x = b[3]; v.y = b[4]; v.z = b[5]; }

@@ -25,11 +25,19 @@ __global__ void k_setup_pre_force(int nlocal, FixList fl, StepArrays a)
 }
 
 // modify->initial_integrate: FixMeso::initial_integrate (fix_meso.cpp:91-140) and
+// largest squared displacement since the build of the atoms (owned or ghost) a cell held at the build, as fp32 bits rounded up
+// (non-negative floats order like their bit patterns): the tile path decides per tile whether its mid / far rows are due
+__device__ __forceinline__ void cell_disp_max(unsigned *celld, int cell, double dsq)
+{
+  const unsigned b = __float_as_uint(__double2float_ru(dsq));
+  if (b > *(volatile unsigned *)(celld + cell)) atomicMax(celld + cell, b);
+}
 // FixMesoStationary::initial_integrate (fix_meso_stationary.cpp:71-92), fixes in deck order;
 // plus Neighbor::check_distance's per-atom test (neighbor.cpp:1396-1404) on the new positions.
 // dtp != NULL: the timestep lives on the device (fix dt/reset); dtp[0] = dt, dtf_per_dt = 0.5 ftm2v
 __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double dtv, double dtf, int check,
-                                    const double *xhold, double triggersq, int *flag, int track, unsigned long long *dmaxsq, const double *dtp, double dtf_per_dt)
+                                    const double *xhold, double triggersq, int *flag, int track, unsigned long long *dmaxsq, const double *dtp, double dtf_per_dt,
+                                    const int *rowcell, unsigned *celld)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
@@ -60,6 +68,7 @@ __global__ void k_initial_integrate(int nlocal, FixList fl, StepArrays a, double
     if (track && moved) {      // largest displacement since the build (non-negative doubles order like their bit patterns)
       unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
       if (b > *(volatile unsigned long long *)dmaxsq) atomicMax(dmaxsq, b);
+      if (celld) cell_disp_max(celld, rowcell[i], dsq);
     }
   }
 }

@@ -134,6 +134,8 @@ struct b200_sph {
   DevBuf<unsigned> nbr, far; DevBuf<int> numneigh, numfar; int stride = 32;
   DevBuf<double> d_prunesq, d_farsq, d_midsq; double far_margin = 0.0, mid_margin = 0.0;
   unsigned long long *d_dmaxsq = nullptr; int *d_scan_far = nullptr;
+  // per-cell displacement bound -> per-tile zone flags (single-phase tile path; B200_ZONE_GLOBAL=1 keeps the one global flag)
+  DevBuf<unsigned> celld; DevBuf<int> rowcell; DevBuf<unsigned char> tzone; bool zone_local = !getenv("B200_ZONE_GLOBAL");
   int *d_flags = nullptr, *h_flags = nullptr;   // [0] maxcount [1] moved flag [2] scratch
   // pair virial (Pair::virial_fdotr_compute) on request: the next force evaluation of b200_setup / the last step of b200_run
   bool vir_request = false, vir_now = false; DevBuf<double> virow, virpart; double *h_vir = nullptr;
@@ -219,6 +221,8 @@ static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch)
     CK(cudaMemcpyAsync(data + n, scratch + nb, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
   }
 }
+
+static bool zones_on(const b200_sph *h) { return h->zone_local && h->far_margin > 0.0 && h->rows_tiled && !h->multiphase && h->ntiles > 0; }
 
 // -------------------------------------------------------------- geometry ----
 static void setup_geometry(b200_sph *h)
@@ -654,6 +658,12 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
   }
   h->tend();
   h->rows_tiled = h->tile_on;
+  if (zones_on(h)) {       // cell of every row, displacement bounds of the cells back to zero, every tile back to its near rows
+    h->rowcell.ensure(nl + 1); h->celld.ensure(g.ncells + 2); h->tzone.ensure(h->ntiles + 1);
+    if (nl) LAUNCH(h, k_row_cells, nblk(nl, B), B, nl, h->perm2.p, h->cellid.p, h->rowcell.p);
+    CK(cudaMemsetAsync(h->celld.p, 0, (g.ncells + 2) * sizeof(unsigned), h->st));
+    CK(cudaMemsetAsync(h->tzone.p, 0, h->ntiles + 1, h->st));
+  }
   CK(cudaMemsetAsync(h->d_dmaxsq, 0, sizeof(unsigned long long), h->st));
   CK(cudaMemsetAsync(h->d_scan_far, 0, 3 * sizeof(int), h->st));
   h->ago = 0; h->nbuilds++;
@@ -814,13 +824,15 @@ static bool overlap_ok(const b200_sph *h) { return h->rows_tiled && !h->multipha
 // one pair pass over the tiles: all at once, or interior tiles | wait for the halo | ghost records | boundary tiles
 template <class Launch, class Rec> static void tile_pass(b200_sph *h, TileArgs &A, Launch launch, Rec records)
 {
+  const unsigned char *tz = zones_on(h) ? h->tzone.p : nullptr;
+  A.tzone = tz;
   if (!h->comm_pending) { A.pstride = records(0); A.rec = h->trec.p; A.tiles = h->tiles.p; A.ntiles = h->ntiles; launch(A, 0); return; }
   A.pstride = records(1); A.rec = h->trec.p;
   A.tiles = h->tiles.p; A.ntiles = h->nint;
   launch(A, h->world > 1 ? 8 : 2);           // a few SMs stay free for the halo's kernels (NCCL send/recv, pack, unpack)
   halo_wait(h);
   records(2);
-  A.tiles = h->tiles.p + h->nint; A.ntiles = h->ntiles - h->nint;
+  A.tiles = h->tiles.p + h->nint; A.ntiles = h->ntiles - h->nint; A.tzone = tz ? tz + h->nint : nullptr;
   launch(A, 0);
 }
 // constants of a sub-style whose coefficients do not depend on the type pair (TileUni); false if they do
@@ -1146,7 +1158,8 @@ static void initial_integrate(b200_sph *h)
   CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));
   int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
-         h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq, h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v);
+         h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq, h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v,
+         h->rowcell.p, zones_on(h) ? h->celld.p : (unsigned *)nullptr);
   h->tend();
 }
 static void forward_comm(b200_sph *h)
@@ -1157,7 +1170,8 @@ static void forward_comm(b200_sph *h)
   comm_forward_generic(h, NB_FORWARD,
     [&](Swap &s) { LAUNCH(h, k_pack_forward, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), s.dim, s.shift, h->sendbuf.p); },
     [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_forward, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), buf, h->multiphase, h->ghost_velocity,
-                                       h->far_margin > 0.0 ? h->xhold.p : (const double *)nullptr, h->d_dmaxsq); });
+                                       h->far_margin > 0.0 ? h->xhold.p : (const double *)nullptr, h->d_dmaxsq, h->gcell.p,
+                                       zones_on(h) ? h->celld.p : (unsigned *)nullptr, h->nlocal); });
   h->tend();
 }
 // far / mid rows must be scanned once 2 * dmax reaches their margin; dmax = largest displacement since the build over the owned atoms
@@ -1166,6 +1180,8 @@ static void far_flags(b200_sph *h)
 {
   if (h->far_margin > 0.0 && h->nlocal)
     LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->d_scan_far);
+  if (zones_on(h))
+    LAUNCH(h, k_tile_zone, nblk(h->ntiles, 128), 128, h->tiles.p, h->ntiles, h->celld.p, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->tzone.p);
 }
 // Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
 static int neigh_decide(b200_sph *h)
@@ -1419,6 +1435,7 @@ int b200_destroy(b200_sph *h)
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_vir); h->virow.release(); h->virpart.release();
   if (h->st2) cudaStreamDestroy(h->st2); if (h->ev_main) cudaEventDestroy(h->ev_main); if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+  h->celld.release(); h->rowcell.release(); h->tzone.release();
   h->tiles.release(); h->gtiles.release(); h->rowtile.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
   return 0;

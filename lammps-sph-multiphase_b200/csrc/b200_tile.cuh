@@ -514,6 +514,28 @@ __global__ void k_tile_export(TileExportArgs A)
   }
 }
 
+// ------------------------------------------------------------------ zones ----
+// cell of every owned row (rows are the owned atoms in cell order; perm2 = row -> slot before the sort)
+__global__ void k_row_cells(int n, const int *perm2, const int *cellid, int *rowcell)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rowcell[i] = cellid[perm2[i]];
+}
+// A tile's mid / far rows are due once 2 * dmax reaches their margin, dmax = largest displacement since the build over the tile's
+// rows AND candidates, i.e. over the atoms of the cells of its candidate ranges (celld).  A handful of fast atoms (a jet, a free
+// surface) then no longer switches the far rows on for the whole domain.
+__global__ void k_tile_zone(const TileDesc *tiles, int ntiles, const unsigned *celld, double marginsq, double midmarginsq, unsigned char *tzone)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const TileDesc &D = tiles[t];
+  unsigned m = 0;
+  for (int r = 0; r < D.nrange; r++)
+    for (int k = 0; k < D.rncell[r]; k++) m = max(m, celld[D.rcell[r] + k]);
+  const double d = 4.0 * (double)__uint_as_float(m);
+  tzone[t] = (unsigned char)((d >= 0.99 * marginsq ? 1 : 0) | (d >= 0.99 * midmarginsq ? 2 : 0));
+}
+
 // --------------------------------------------------------------- records ----
 // Per-pass records in tile order (owned atoms in device order, then the ghosts in cell order = gorder), one
 // double2 array per part: P0 = x,y   P1 = z,rho   [P2 = vest.x,vest.y   P3 = vest.z, Tait term]   [Pe = e,0]
@@ -597,6 +619,7 @@ struct TileArgs {
   // multiphase styles
   const double4 *vm; double4 *cg_out; const int *gorder; int dim;
   double *virow;                             // VIR kernels: per-row virial sums [row][6]
+  const unsigned char *tzone;                // single-phase stage kernels: per-tile zone flags (bit 0 far, bit 1 mid), or NULL -> scan_far
 };
 
 // shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc[2] | mbarrier | tile id[2]
@@ -723,11 +746,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
   const PairTab &T = S.T[0];
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
-  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, g_far = A.scan_far[0], g_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
     const TileDesc &D = *Dp;
+    const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
+    const int scan_far = zone & 1, scan_mid = zone & 2;
     for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
@@ -812,11 +837,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const double u_eta = 0.01 * UF.h * UF.h, u_vch = -UF.visc * (UF.cs + UF.cs) * UF.h, u_vci = -UF.visc * UF.h;
   const double u_k1 = -UF.mass * UF.mass * UF.c0, u_k2 = 2.0 * UF.visc * UF.mass * UF.mass * UF.c0, u_k3 = UF.mass * UF.c0;
   const double u_heat = HAS_HEAT ? 2.0 * UH.mass * UH.mass * UH.visc / (UH.mass + UH.mass) * UH.c0 : 0.0;
-  const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
+  const int ntiles = A.ntiles, g_far = A.scan_far[0], g_mid = A.scan_far[2];
   TileLoop<(1 << NPARTS) - 1, NK, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.acquire()) {
     const TileDesc &D = *Dp;
+    const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
+    const int scan_far = zone & 1, scan_mid = zone & 2;
     for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       const bool valid = rt < D.nrows;

@@ -95,3 +95,38 @@ def test_tile_path_is_the_one_that_runs():
     a, _, ca = _run("dam3d", 5, {})
     b, _, cb = _run("dam3d", 5, {"B200_NO_TILE": "1"})
     assert ca["launches"] != cb["launches"]
+
+
+def _run_c2(scale, nsteps, env):
+    import bench
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        atoms, params = bench.dam_break_3d(scale)
+        sim = pkg.B200Sim(bench.make_deck(pkg, params))
+        sim.set_atoms(**atoms)
+        sim.setup(); sim.run(nsteps)
+        out = sim.get_atoms()
+        sim.close()
+        return out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name,nsteps", [("dam3d", 12), ("dam2d", 40), ("gas3d", 15), ("gas3d_shrink", 45), ("c2@0.35", 14)])
+def test_per_tile_zone_flags_equal_the_global_flag(name, nsteps):
+    """Mid / far rows hold only pairs beyond the cutoff until 2 * dmax reaches their margin, and such pairs add exactly 0.0:
+    switching them on per tile (local displacement bound, the default) or for all tiles at once (B200_ZONE_GLOBAL=1) must give
+    bitwise identical fields."""
+    if name.startswith("c2@"):
+        a = _run_c2(float(name[3:]), nsteps, {})
+        b = _run_c2(float(name[3:]), nsteps, {"B200_ZONE_GLOBAL": "1"})
+    else:
+        a = _run(name, nsteps, {})[0]
+        b = _run(name, nsteps, {"B200_ZONE_GLOBAL": "1"})[0]
+    for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de"):
+        assert np.array_equal(a[k], b[k]), (name, k, harness.relerr(a[k], b[k]))
