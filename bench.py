@@ -161,7 +161,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.p, self.path = gpu, None, None
+        self.gpu, self.p, self.path, self.skip = gpu, None, None, 0
 
     def start(self):
         if not shutil.which("nvidia-smi"):
@@ -170,6 +170,17 @@ class ClockSampler:
         os.close(fd)
         self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                   stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def ready(self, timeout=5.0):
+        """wait for the sampler's first line: nvidia-smi has attached to the devices and only polls from here on"""
+        t0 = time.time()
+        while self.p and time.time() - t0 < timeout and os.path.getsize(self.path) == 0:
+            time.sleep(0.02)
+
+    def mark(self):
+        """the timed region starts here: samples written so far (nvidia-smi's start-up, the warm-up) do not count"""
+        if self.p:
+            self.skip = sum(1 for _ in open(self.path))
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -181,7 +192,9 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         sm, mx, reasons = [], [], set()
-        for line in open(self.path):
+        lines = open(self.path).read().splitlines()
+        lines = lines[self.skip:] or lines[-1:]          # a region shorter than one sampling period: the sample just before it
+        for line in lines:
             c = [v.strip() for v in line.split(",")]
             if len(c) < 9:
                 continue
@@ -263,16 +276,20 @@ def main():
     sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=nid)
     sim.set_atoms(**atoms)
     sim.setup()
+    # one sampler per job (concurrent nvidia-smi pollers contend for the driver lock and stall the ranks' API calls), started before the
+    # warm-up so that its start-up (device attach, ~1 s) is over when the timed region begins; only samples taken inside the region count
+    clocks = ClockSampler(local)
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
+        clocks.start()
     sim.run(max(args.warmup, 3))
     sim.sync()
 
     # ---- device-resident timed region: K Verlet steps, CUDA events on the launching (default) stream ----
     sim.set_timing(True)
     c0 = sim.counters()
-    clocks = ClockSampler(local)
-    if rank == 0:          # one sampler per job: concurrent nvidia-smi pollers contend for the driver lock and stall the ranks' API calls
-        clocks.start()
+    clocks.ready()
     barrier()
+    clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     sim.run(args.steps)
