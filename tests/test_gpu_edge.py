@@ -88,3 +88,51 @@ def test_dense_cluster_regrows_rows_and_falls_back():
     outs = _both(deck, _atoms(x), 0)          # setup only: the pressure of such a cluster throws atoms out of the box within a step
     _check(outs, tol=1e-8)
     assert outs[0][3]["max_neighbors"] >= 1400
+
+
+def test_shrink_wrapped_box_follows_a_free_cluster():
+    """boundary s s s around a small cloud that expands: the box is re-fitted at every rebuild (Domain::reset_box), engine == oracle"""
+    rng = np.random.default_rng(5)
+    x = 0.5 + 0.12 * rng.uniform(-1, 1, (400, 3))
+    deck = _deck(boundary="s s s", h=0.06, skin=0.02, every=1)
+    outs = []
+    for mk in (pkg.B200Sim, harness.oracle_sim):
+        s = mk(deck)
+        s.set_atoms(**_atoms(x))
+        s.setup(); s.run(30)
+        outs.append((s.get_atoms(), s.neighbor_list(), s.natoms(), s.counters(), s.box()))
+        s.close()
+    _check([o[:4] for o in outs])
+    (lo_a, hi_a), (lo_b, hi_b) = outs[0][4], outs[1][4]
+    assert harness.relerr(np.array([lo_a, hi_a]), np.array([lo_b, hi_b])) < 1e-12
+    assert outs[0][3]["builds"] >= 2
+    got = outs[0][0]["x"]             # the box was fitted at the last rebuild; since then nobody moved further than half the skin
+    assert (got.min(0) > np.array(lo_a) - 0.01).all() and (got.max(0) < np.array(hi_a) + 0.01).all()
+
+
+@pytest.mark.parametrize("mk", ["engine", "oracle"])
+def test_misuse_is_refused_with_a_message(mk):
+    """error behaviour of the boundary: every entry returns < 0 and b200_last_error() names the reason (no silent fallback)"""
+    import ctypes as C
+    api = pkg.load() if mk == "engine" else harness.oracle_api()
+    make = pkg.B200Sim if mk == "engine" else harness.oracle_sim
+    sim = make(_deck())
+    # run before setup
+    assert api.run(sim.h, 1) < 0 and b"setup" in api.last_error()
+    # boundary styles that contradict the periodicity handed to b200_domain
+    bnd = (C.c_int * 6)(2, 2, 0, 0, 0, 0); small = (C.c_double * 3)(0, 0, 0)
+    assert api.boundary(sim.h, bnd, small, None) < 0 and b"periodic" in api.last_error()
+    # an unknown boundary style
+    bnd = (C.c_int * 6)(7, 7, 0, 0, 0, 0)
+    assert api.boundary(sim.h, bnd, small, None) < 0
+    # dimension other than 2 or 3
+    lo = (C.c_double * 3)(0, 0, 0); hi = (C.c_double * 3)(1, 1, 1); per = (C.c_int * 3)(1, 1, 1)
+    assert api.domain(sim.h, 4, lo, hi, per, None, None) < 0 and b"dimension" in api.last_error()
+    sim.close()
+    # a periodic box thinner than the ghost cutoff needs more than one ghost layer: refused at setup by both
+    sim = make(_deck(box=((0, 0, 0), (0.1, 1, 1)), h=0.1, skin=0.03))
+    sim.set_atoms(**_atoms([[0.05, 0.5, 0.5], [0.06, 0.5, 0.5]]))
+    with pytest.raises(Exception) as e:
+        sim.setup()
+    assert "cutoff" in str(e.value) or "cutghost" in str(e.value)
+    sim.close()
