@@ -75,6 +75,8 @@ struct osph_sph {
   /* comm: up to 6 swaps for P=1 (comm_brick.cpp:330-386) */
   int nswap, swapdim[6], swappbc[6], sendnum[6], firstrecv[6], *sendlist[6], maxsend[6];
   double slablo[6], slabhi[6];
+  /* P > 1 emulated in one process (osph_world_*): this rank's place in the brick grid (comm.h procgrid/myloc/procneigh) */
+  int inworld, me, procgrid[3], myloc[3], procneigh[3][2], sendproc[6], recvproc[6], dosend[6];
   /* styles */
   int npair; opair pair[MAXPAIR];
   int nfix; ofix fix[MAXFIX];
@@ -146,8 +148,17 @@ int osph_destroy(osph_sph *s)
 }
 
 int osph_comm_unique_id(char id[128]) { memset(id, 0, 128); return 0; }
+/* world > 1: the instance becomes one rank of an emulated brick decomposition; it can then only be driven through
+ * osph_world_setup / osph_world_run together with its peers (oracle-only entry points, sph_oracle.h) */
 int osph_comm_init(osph_sph *s, int world, int rank, const int procgrid[3], const int myloc[3], const int procneigh[6], const char id[128])
-{ (void)s; (void)rank; (void)procgrid; (void)myloc; (void)procneigh; (void)id; return world == 1 ? 0 : fail("the oracle is single-rank"); }
+{
+  (void)id;
+  if (world == 1) return 0;
+  if (procgrid[0] * procgrid[1] * procgrid[2] != world) return fail("comm_init: procgrid does not match the world size");
+  s->inworld = 1; s->me = rank;
+  for (int d = 0; d < 3; d++) { s->procgrid[d] = procgrid[d]; s->myloc[d] = myloc[d]; s->procneigh[d][0] = procneigh[2*d]; s->procneigh[d][1] = procneigh[2*d+1]; }
+  return 0;
+}
 
 int osph_domain(osph_sph *s, int dim, const double boxlo[3], const double boxhi[3], const int periodicity[3],
                 const double sublo[3], const double subhi[3])
@@ -158,7 +169,7 @@ int osph_domain(osph_sph *s, int dim, const double boxlo[3], const double boxhi[
     s->boxlo[d] = boxlo[d]; s->boxhi[d] = boxhi[d]; s->prd[d] = boxhi[d] - boxlo[d]; /* domain.cpp set_global_box */
     s->periodic[d] = periodicity[d];
     s->sublo[d] = sublo ? sublo[d] : boxlo[d]; s->subhi[d] = subhi ? subhi[d] : boxhi[d];
-    if (s->sublo[d] != boxlo[d] || s->subhi[d] != boxhi[d]) return fail("oracle is single-rank: sub-domain must equal box");
+    if ((s->sublo[d] != boxlo[d] || s->subhi[d] != boxhi[d]) && !s->inworld) return fail("oracle: a sub-domain smaller than the box needs osph_comm_init (world mode) first");
   }
   return 0;
 }
@@ -684,7 +695,7 @@ static void pair_rhosum(osph_sph *s, opair *p)
         rho[i] += s->mass[jtype] * wf;
     NB_END
   }
-  comm_forward_rho(s); /* :203 */
+  if (!s->inworld) comm_forward_rho(s); /* :203 (world mode: w_forward_rho after the style has run on every rank) */
 }
 
 /* PairSPHRhoSumMultiphase::compute, pair_sph_rhosum_multiphase.cpp:68-174.
@@ -1261,6 +1272,7 @@ int osph_get_virial(osph_sph *s, double v[6]) { memcpy(v, s->virial, 6 * sizeof(
 int osph_setup(osph_sph *s)
 {
   if (!s->cutneighsq) return fail("setup: b200_neighbor not called");
+  if (s->inworld) return fail("a rank of an emulated world is driven by osph_world_setup / osph_world_run");
   domain_pbc(s);
   if (domain_reset_box(s)) return -1;   /* verlet.cpp:102 */
   if (comm_setup(s)) return -1;
@@ -1285,6 +1297,7 @@ int osph_setup(osph_sph *s)
 int osph_run(osph_sph *s, int nsteps)
 {
   if (!s->setup_done) return fail("run before setup");
+  if (s->inworld) return fail("a rank of an emulated world is driven by osph_world_setup / osph_world_run");
   for (int it = 0; it < nsteps; it++) {
     s->ntimestep++;
     osph_initial_integrate(s);
@@ -1299,6 +1312,263 @@ int osph_run(osph_sph *s, int nsteps)
     for (int i = 0; i < s->nfix; i++)   /* modify->end_of_step */
       if (s->fix[i].kind == FIX_DT_RESET && s->ntimestep % s->fix[i].nevery == 0) fix_dt_reset(s, &s->fix[i]);
     s->nsteps_done++;
+  }
+  return 0;
+}
+
+/* ======================================================================
+   P ranks in one process (test infrastructure for the multi-GPU path): every rank is an osph_sph of its own with a brick
+   sub-domain; the collective steps of CommBrick run in lock step over the array of ranks, reading the sender's arrays
+   directly where MPI would move a buffer.  Restated for maxneed = 1 (one ghost layer), uniform bricks, no fix phase_change
+   (it draws one RNG stream per rank) and no shrink-wrapped faces.
+   ====================================================================== */
+
+/* CommBrick::setup, comm_brick.cpp:150-386, for this rank's place in the grid */
+static int w_comm_setup(osph_sph *s)
+{
+  s->nswap = 0;
+  for (int d = 0; d < 3; d++) {
+    const int pg = s->procgrid[d], loc = s->myloc[d];
+    int maxneed = (int)(s->cutghost * pg / s->prd[d]) + 1;                 /* :225-227 */
+    if (s->dim == 2 && d == 2) maxneed = 0;
+    if (!s->periodic[d] && maxneed > pg - 1) maxneed = pg - 1;             /* :229-231 */
+    if (maxneed > 1) return fail("oracle world: cutghost >= sub-domain length is not restated");
+    int sendneed[2] = {maxneed, maxneed};
+    if (!s->periodic[d]) {                                                  /* :233-243 */
+      int left = loc - 1; if (left < 0) left = pg - 1;
+      int right = loc + 1; if (right == pg) right = 0;
+      sendneed[0] = maxneed < pg - left - 1 ? maxneed : pg - left - 1;
+      sendneed[1] = maxneed < right ? maxneed : right;
+    }
+    for (int ineed = 0; ineed < 2 * maxneed; ineed++) {
+      int k = s->nswap++;
+      s->swapdim[k] = d; s->swappbc[k] = 0;
+      if (ineed % 2 == 0) {
+        s->sendproc[k] = s->procneigh[d][0]; s->recvproc[k] = s->procneigh[d][1];
+        s->slablo[k] = -BIG; s->slabhi[k] = s->sublo[d] + s->cutghost;
+        if (loc == 0) s->swappbc[k] = 1;
+      } else {
+        s->sendproc[k] = s->procneigh[d][1]; s->recvproc[k] = s->procneigh[d][0];
+        s->slablo[k] = s->subhi[d] - s->cutghost; s->slabhi[k] = BIG;
+        if (loc == pg - 1) s->swappbc[k] = -1;
+      }
+      s->dosend[k] = (ineed / 2 < sendneed[ineed % 2]);                     /* borders(): sendflag, :741-742 */
+    }
+  }
+  return 0;
+}
+
+static void copy_atom(osph_sph *dst, int di, const osph_sph *src, int si)
+{
+  for (int d = 0; d < 3; d++) {
+    dst->x[3*di+d] = src->x[3*si+d]; dst->v[3*di+d] = src->v[3*si+d]; dst->vest[3*di+d] = src->vest[3*si+d];
+    dst->f[3*di+d] = src->f[3*si+d]; dst->cg[3*di+d] = src->cg[3*si+d];
+  }
+  dst->rho[di] = src->rho[si]; dst->drho[di] = src->drho[si]; dst->e[di] = src->e[si]; dst->de[di] = src->de[si];
+  dst->cv[di] = src->cv[si]; dst->rmass[di] = src->rmass[si];
+  dst->type[di] = src->type[si]; dst->mask[di] = src->mask[si]; dst->tag[di] = src->tag[si]; dst->img[di] = src->img[si];
+}
+
+/* CommBrick::exchange, comm_brick.cpp:575-680: atoms that left the sub-domain go to the neighbours of each dimension in turn */
+static void w_exchange(osph_sph **R, int n)
+{
+  const int dimension = R[0]->dim;
+  int **out = calloc(n, sizeof(int *)); int *nout = calloc(n, sizeof(int));
+  osph_sph *tmp = NULL;        /* the senders' buf_send: atoms leave their rank before anybody receives */
+  osph_create(&tmp, -1);
+  for (int r = 0; r < n; r++) R[r]->nghost = 0;
+  for (int dim = 0; dim < dimension; dim++) {
+    int total = 0;
+    for (int r = 0; r < n; r++) {
+      osph_sph *s = R[r];
+      const double lo = s->sublo[dim], hi = s->subhi[dim];
+      out[r] = xrealloc(out[r], sizeof(int) * (s->nlocal + 1)); nout[r] = 0;
+      int nlocal = s->nlocal, i = 0;
+      while (i < nlocal) {
+        if (s->x[3*i+dim] < lo || s->x[3*i+dim] >= hi) {
+          grow(tmp, total + 1); copy_atom(tmp, total, s, i); out[r][nout[r]++] = total++;
+          copy_atom(s, i, s, nlocal - 1);                                   /* avec->copy(nlocal-1,i,1) */
+          nlocal--;
+        } else i++;
+      }
+      s->nlocal = nlocal;
+    }
+    for (int r = 0; r < n; r++) {
+      osph_sph *s = R[r];
+      if (s->procgrid[dim] == 1) continue;                                  /* the leavers are lost, as in the reference */
+      const double lo = s->sublo[dim], hi = s->subhi[dim];
+      const int from[2] = {s->procneigh[dim][1], s->procneigh[dim][0]};     /* recv from the right, then (more than 2 procs) from the left */
+      for (int side = 0; side < (s->procgrid[dim] > 2 ? 2 : 1); side++) {
+        const int q = from[side];
+        for (int k = 0; k < nout[q]; k++) {
+          const double value = tmp->x[3*out[q][k]+dim];
+          if (value >= lo && value < hi) { grow(s, s->nlocal + 1); copy_atom(s, s->nlocal, tmp, out[q][k]); s->nlocal++; }
+        }
+      }
+    }
+  }
+  for (int r = 0; r < n; r++) free(out[r]);
+  free(out); free(nout); osph_destroy(tmp);
+}
+
+/* CommBrick::borders, comm_brick.cpp:696-864 */
+static void w_borders(osph_sph **R, int n)
+{
+  int *nlast = calloc(n, sizeof(int));
+  for (int r = 0; r < n; r++) R[r]->nghost = 0;
+  int iswap = 0; const int nswap = R[0]->nswap;
+  while (iswap < nswap) {
+    const int dim = R[0]->swapdim[iswap];
+    for (int r = 0; r < n; r++) nlast[r] = R[r]->nlocal + R[r]->nghost;
+    for (int half = 0; half < 2 && iswap < nswap && R[0]->swapdim[iswap] == dim; half++, iswap++) {
+      for (int r = 0; r < n; r++) {                                          /* everybody lists what it sends */
+        osph_sph *s = R[r];
+        const double lo = s->slablo[iswap], hi = s->slabhi[iswap];
+        int nsend = 0;
+        if (s->dosend[iswap])
+          for (int i = 0; i < nlast[r]; i++)
+            if (s->x[3*i+dim] >= lo && s->x[3*i+dim] <= hi) {
+              if (nsend == s->maxsend[iswap]) { s->maxsend[iswap] = nsend * 2 + 1024; s->sendlist[iswap] = xrealloc(s->sendlist[iswap], sizeof(int) * s->maxsend[iswap]); }
+              s->sendlist[iswap][nsend++] = i;
+            }
+        s->sendnum[iswap] = nsend;
+      }
+      for (int r = 0; r < n; r++) {                                          /* ... and unpacks what its recvproc sent */
+        osph_sph *s = R[r]; const osph_sph *src = R[s->recvproc[iswap]];
+        const int nrecv = src->sendnum[iswap], first = s->nlocal + s->nghost;
+        grow(s, first + nrecv);
+        src = R[s->recvproc[iswap]];
+        const double shift = src->swappbc[iswap] * src->prd[dim];
+        const int imgmul = dim == 0 ? 1 : (dim == 1 ? 3 : 9);
+        for (int k = 0; k < nrecv; k++) {
+          const int j = src->sendlist[iswap][k], g = first + k;
+          for (int d = 0; d < 3; d++) {
+            s->x[3*g+d] = (d == dim && src->swappbc[iswap]) ? src->x[3*j+d] + shift : src->x[3*j+d];
+            s->cg[3*g+d] = src->cg[3*j+d]; s->vest[3*g+d] = src->vest[3*j+d];
+            if (s->ghost_velocity) s->v[3*g+d] = src->v[3*j+d];
+          }
+          s->tag[g] = src->tag[j]; s->type[g] = src->type[j]; s->mask[g] = src->mask[j];
+          s->rho[g] = src->rho[j]; s->rmass[g] = src->rmass[j]; s->e[g] = src->e[j]; s->cv[g] = src->cv[j];
+          s->img[g] = src->img[j] + src->swappbc[iswap] * imgmul;
+        }
+        s->firstrecv[iswap] = first; s->nghost += nrecv;
+      }
+    }
+  }
+  free(nlast);
+}
+
+/* CommBrick::forward_comm, comm_brick.cpp:444-506 */
+static void w_forward(osph_sph **R, int n)
+{
+  for (int iswap = 0; iswap < R[0]->nswap; iswap++) {
+    const int dim = R[0]->swapdim[iswap];
+    for (int r = 0; r < n; r++) {
+      osph_sph *s = R[r]; const osph_sph *src = R[s->recvproc[iswap]];
+      const double shift = src->swappbc[iswap] * src->prd[dim];
+      for (int k = 0; k < src->sendnum[iswap]; k++) {
+        const int j = src->sendlist[iswap][k], g = s->firstrecv[iswap] + k;
+        for (int d = 0; d < 3; d++) {
+          s->x[3*g+d] = (d == dim && src->swappbc[iswap]) ? src->x[3*j+d] + shift : src->x[3*j+d];
+          s->vest[3*g+d] = src->vest[3*j+d];
+          if (s->multiphase) s->cg[3*g+d] = src->cg[3*j+d];
+          if (s->ghost_velocity) s->v[3*g+d] = src->v[3*j+d];
+        }
+        s->rho[g] = src->rho[j]; s->e[g] = src->e[j];
+        if (s->multiphase) s->rmass[g] = src->rmass[j];
+      }
+    }
+  }
+}
+/* CommBrick::reverse_comm, comm_brick.cpp:513-560: swaps in reverse order; the ghost of swap k on rank r adds into its sender */
+static void w_reverse(osph_sph **R, int n)
+{
+  for (int iswap = R[0]->nswap - 1; iswap >= 0; iswap--)
+    for (int r = 0; r < n; r++) {
+      osph_sph *s = R[r]; osph_sph *src = R[s->recvproc[iswap]];
+      for (int k = 0; k < src->sendnum[iswap]; k++) {
+        const int j = src->sendlist[iswap][k], g = s->firstrecv[iswap] + k;
+        for (int d = 0; d < 3; d++) src->f[3*j+d] += s->f[3*g+d];
+        src->drho[j] += s->drho[g]; src->de[j] += s->de[g];
+      }
+    }
+}
+/* CommBrick::forward_comm_pair with PairSPHRhoSum::pack_forward_comm, comm_brick.cpp:871-904 */
+static void w_forward_rho(osph_sph **R, int n)
+{
+  for (int iswap = 0; iswap < R[0]->nswap; iswap++)
+    for (int r = 0; r < n; r++) {
+      osph_sph *s = R[r]; const osph_sph *src = R[s->recvproc[iswap]];
+      for (int k = 0; k < src->sendnum[iswap]; k++) s->rho[s->firstrecv[iswap] + k] = src->rho[src->sendlist[iswap][k]];
+    }
+}
+
+static int w_check(osph_sph **R, int n)
+{
+  if (n < 1) return fail("world: no ranks");
+  for (int r = 0; r < n; r++) {
+    if (!R[r]->inworld || R[r]->me != r) return fail("world: rank r must have been given osph_comm_init(world, r, ...)");
+    if (!R[r]->cutneighsq) return fail("world setup: b200_neighbor not called");
+    if (R[r]->shrink) return fail("world: shrink-wrapped boundaries are not restated for P > 1");
+    for (int i = 0; i < R[r]->nfix; i++) if (R[r]->fix[i].kind == FIX_PHASE_CHANGE) return fail("world: fix phase_change is not restated for P > 1");
+  }
+  return 0;
+}
+/* pair_hybrid.cpp:101-109 over all ranks, sub-style by sub-style (PairSPHRhoSum ends with its forward_comm_pair) */
+static int w_pair_compute_all(osph_sph **R, int n)
+{
+  for (int k = 0; k < R[0]->npair; k++) {
+    for (int r = 0; r < n; r++) if (pair_compute_slot(R[r], k)) return -1;
+    if (R[0]->pair[k].style == B200_PAIR_RHOSUM) w_forward_rho(R, n);
+  }
+  return 0;
+}
+static int w_rebuild(osph_sph **R, int n)
+{
+  for (int r = 0; r < n; r++) domain_pbc(R[r]);
+  w_exchange(R, n);
+  w_borders(R, n);
+  for (int r = 0; r < n; r++) if (neighbor_build(R[r])) return -1;
+  return 0;
+}
+
+/* Verlet::setup, verlet.cpp:88-142, on every rank */
+int osph_world_setup(osph_sph **R, int n)
+{
+  if (w_check(R, n)) return -1;
+  for (int r = 0; r < n; r++) { domain_pbc(R[r]); if (w_comm_setup(R[r])) return -1; if (setup_bins(R[r])) return -1; }
+  w_exchange(R, n);
+  w_borders(R, n);
+  for (int r = 0; r < n; r++) {
+    osph_sph *s = R[r];
+    if (neighbor_build(s)) return -1;
+    s->nbuilds = 0;
+    osph_force_clear(s);
+    for (int i = 0; i < s->nfix; i++)
+      if (s->fix[i].kind == FIX_MESO)
+        for (int a = 0; a < s->nlocal; a++) if (s->mask[a] & s->fix[i].groupbit) for (int d = 0; d < 3; d++) s->vest[3*a+d] = s->v[3*a+d];
+  }
+  if (w_pair_compute_all(R, n)) return -1;
+  w_reverse(R, n);
+  for (int r = 0; r < n; r++) { osph_post_force(R[r]); R[r]->setup_done = 1; }
+  return 0;
+}
+
+/* Verlet::run, verlet.cpp:207-309, on every rank */
+int osph_world_run(osph_sph **R, int n, int nsteps)
+{
+  if (w_check(R, n)) return -1;
+  for (int r = 0; r < n; r++) if (!R[r]->setup_done) return fail("run before setup");
+  for (int it = 0; it < nsteps; it++) {
+    int rebuild = 0;
+    for (int r = 0; r < n; r++) { R[r]->ntimestep++; osph_initial_integrate(R[r]); }
+    for (int r = 0; r < n; r++) rebuild |= neighbor_decide(R[r]);            /* MPI_Allreduce MAX, neighbor.cpp:1407 */
+    if (!rebuild) w_forward(R, n);
+    else if (w_rebuild(R, n)) return -1;
+    for (int r = 0; r < n; r++) osph_force_clear(R[r]);
+    if (w_pair_compute_all(R, n)) return -1;
+    w_reverse(R, n);
+    for (int r = 0; r < n; r++) { osph_post_force(R[r]); osph_final_integrate(R[r]); R[r]->nsteps_done++; }
   }
   return 0;
 }

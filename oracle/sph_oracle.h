@@ -70,6 +70,10 @@ extern "C" {
 #endif
 /* copy owned+ghost arrays in the oracle's own (= reference) order */
 int osph_get_all(osph_sph *h, int nmax, osph_atoms *a);
+/* P ranks emulated in one process: ranks[r] was given osph_comm_init(n, r, procgrid, myloc, procneigh) before osph_domain.
+ * Verlet::setup / Verlet::run in lock step, CommBrick's collectives between the ranks' arrays (sph_oracle.c "P ranks in one process") */
+int osph_world_setup(osph_sph **ranks, int n);
+int osph_world_run(osph_sph **ranks, int n, int nsteps);
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
-    names = sys.argv[1:] or ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin", "bubble3d", "shock3d_shrink"]
+    names = sys.argv[1:] or ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin", "droplet3d_heat", "bubble3d", "shock3d_shrink"]
     api = pkg.load()
     failed = 0
     for name in names:
@@ -54,7 +54,8 @@ def main():
             ref_order = np.argsort(g["sN_tag"])
             # The multiphase styles read one-step-stale ghost rho / colorgradient, so a moving multiphase
             # deck depends on WHERE the ghosts are, i.e. on the decomposition -- in the reference too.  Exact checks:
-            # single-phase decks and static multiphase decks; moving multiphase decks only have to stay close;
+            # single-phase decks and static multiphase decks against the 1-rank fixtures; moving multiphase decks against the CPU oracle
+            # emulating the same ranks (below);
             # fix phase_change draws one RNG stream per rank (fix_phase_change.cpp:116), so only counts are sane-checked.
             moving_mp = case.multiphase and "static" not in name
             pc = "phase_change" in str(case.cmds)
@@ -74,10 +75,26 @@ def main():
                     a = np.concatenate([o[0][k] for o in gathered])[order]
                     errs[k] = relerr(a, g["sN_" + k][ref_order])
                 ok = all(v <= tol for v in errs.values())
-            verdict = "OK" if ok else ("INFO (decomposition-dependent by design, not counted)" if moving_mp else "FAIL")
+            wline = None
+            if moving_mp and len(tags) == len(g["sN_tag"]):
+                # what the reference's algorithm gives on THIS brick grid: the CPU oracle emulating the same P ranks (tests/pworld.py,
+                # pinned against the 1-rank fixtures by tests/test_world_cpu.py).  This is the check that counts for these decks.
+                from pworld import OracleWorld
+                w = OracleWorld(case.deck(), world, brick.grid)
+                w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
+                w.setup(); w.setup(); w.run(case.nsteps)
+                want = w.get_atoms(); w.close()
+                wfields = ["x", "v", "f", "rho", "e", "de", "drho", "colorgradient", "rmass"]
+                werrs = {k: relerr(np.concatenate([o[0][k] for o in gathered])[order], want[k]) for k in wfields}
+                wok = np.array_equal(tags[order], want["tag"]) and all(v <= 100 * case.tol_traj for v in werrs.values())
+                wline = "%-24s grid %s vs the oracle emulating the same %d ranks: %s  %s" % (name, brick.grid, world, "OK" if wok else "FAIL", {k: "%.1e" % v for k, v in werrs.items()})
+                failed += 0 if wok else 1
+            verdict = "OK" if ok else ("INFO (1 rank vs %d ranks: decomposition-dependent by design, not counted)" % world if moving_mp else "FAIL")
             print("%-24s grid %s atoms/rank %s ghosts %s builds %s  %s  %s" % (
                 name, brick.grid, [o[1] for o in gathered], [o[2] for o in gathered], [o[3] for o in gathered],
                 verdict, {k: "%.1e" % v for k, v in errs.items()}), flush=True)
+            if wline:
+                print(wline, flush=True)
             failed += 0 if (ok or moving_mp) else 1
         if rank != 0 and "phase_change" in str(case.cmds):
             sim.close(); dist.barrier()
