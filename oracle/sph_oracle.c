@@ -6,10 +6,15 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this port
+ * Parity status: PINNED (one rank).  tests/test_oracle_golden.py checks this port
  * against (a) the six multiphase_two_atoms known-answer decks and (b) stage and
  * trajectory dumps of the real reference (oracle/_ref/liblammps_ref.so, built
  * from /root/reference by oracle/Makefile), committed under tests/golden/.
+ * The P-rank emulation at the end of the file ("P ranks in one process") cannot
+ * be run against the real reference here (the image has no MPI): it is pinned
+ * through the decks whose result does not depend on the decomposition, which must
+ * reproduce the 1-rank reference fixtures on 2-4 ranks (tests/test_world_cpu.py);
+ * for decomposition-dependent decks at P > 1 it is a restatement only.
  *
  * It is a deliberately plain, sequential, single-rank restatement that follows
  * the reference's own data structures (AoS per-atom arrays with ghosts behind
