@@ -36,7 +36,10 @@ enum {
   B200_PAIR_HEATCONDUCTION = 8,     /* sph/heatconduction            pair_sph_heatconduction.cpp:47-134 */
   B200_PAIR_HEATCONDUCTION_MULTIPHASE = 9,  /* sph/heatconduction/multiphase  ..._multiphase.cpp:49-129 */
   B200_PAIR_HEATCONDUCTION_PHASECHANGE = 10,/* sph/heatconduction/phasechange ..._phasechange.cpp:52-141 */
-  B200_PAIR_IDEALGAS = 11           /* sph/idealgas                  pair_sph_idealgas.cpp:48-175 (coeff: I J viscosity h) */
+  B200_PAIR_IDEALGAS = 11,          /* sph/idealgas                  pair_sph_idealgas.cpp:48-175 (coeff: I J viscosity h) */
+  B200_PAIR_LJ = 12                 /* sph/lj                        pair_sph_lj.cpp:48-182 (coeff: I J viscosity h).  Reserved: the oracle restates it
+                                       (tests/golden/lj3d.npz); the engine does not implement it yet and b200_pair_add refuses it (< 0) -- its
+                                       `fi += lrc` inside the neighbor loop (:139) makes every pair force depend on the reference's list order */
 };
 
 /* One sub-style of `pair_style hybrid/overlay` (or the single pair style),

@@ -21,9 +21,10 @@ PAIR_STYLES = {
     "sph/rhosum": 1, "sph/rhosum/multiphase": 2, "sph/taitwater": 3, "sph/taitwater/morris": 4,
     "sph/taitwater/multiphase": 5, "sph/colorgradient": 6, "sph/surfacetension": 7,
     "sph/heatconduction": 8, "sph/heatconduction/multiphase": 9, "sph/heatconduction/phasechange": 10, "sph/idealgas": 11,
+    "sph/lj": 12,        # restated by the oracle only: the engine's b200_pair_add refuses it (include/b200_sph.h B200_PAIR_LJ)
 }
 _NSETTINGS = {1: 1, 2: 1, 6: 1}           # styles whose settings() takes Nstep
-_NCOEFF = {1: (1,), 2: (1,), 3: (4,), 4: (4,), 5: (6,), 6: (2,), 7: (1,), 8: (2,), 9: (2,), 10: (2, 4), 11: (2,)}
+_NCOEFF = {1: (1,), 2: (1,), 3: (4,), 4: (4,), 5: (6,), 6: (2,), 7: (1,), 8: (2,), 9: (2,), 10: (2, 4), 11: (2,), 12: (2,)}
 
 
 class DeckError(RuntimeError):
@@ -78,7 +79,8 @@ class SubStyle:
         surfacetension       h                      pair_sph_surfacetension.cpp:225-250
         heatconduction[/mp]  D h                    pair_sph_heatconduction.cpp:168-195
         heatconduction/phasechange D h [Ti|NULL Tj|NULL]  ..._phasechange.cpp:177-225
-        idealgas             nu h                   pair_sph_idealgas.cpp:210-238"""
+        idealgas             nu h                   pair_sph_idealgas.cpp:210-238
+        lj                   nu h                   pair_sph_lj.cpp:217-247"""
         if len(args) not in _NCOEFF[self.style]:
             raise DeckError("Incorrect args for pair_style %s coefficients" % self.name)
         ilo, ihi = bounds(I, self.n); jlo, jhi = bounds(J, self.n)
@@ -93,7 +95,7 @@ class SubStyle:
         elif st == 5:
             rho0, c0, nu, gam, cut_one, rb = f
             B_one = c0 * c0 * rho0 / gam
-        elif st == 11:
+        elif st in (11, 12):
             nu, cut_one = f
         elif st == 6:
             cut_one, alpha_one = f
@@ -114,7 +116,7 @@ class SubStyle:
                     self.gamma[i], self.rbackground[i] = gam, rb
             for j in range(max(jlo, i), jhi + 1):
                 self.cut[i, j] = cut_one
-                if st in (3, 4, 5, 11):
+                if st in (3, 4, 5, 11, 12):
                     self.viscosity[i, j] = nu
                 if st in (6, 8, 9, 10):
                     self.alpha[i, j] = alpha_one

@@ -823,6 +823,56 @@ static void pair_idealgas(osph_sph *s, opair *p)
   NB_END
 }
 
+/* PairSPHLJ::LJEOS2, pair_sph_lj.cpp:303-333 (Ree 1980) */
+static void ljeos2(double rho, double e, double cv, double *p, double *c)
+{
+  double T = e / cv, beta = 1.0 / T, beta_sqrt = sqrt(beta), x = rho * sqrt(beta_sqrt);
+  double xsq = x * x, xpow3 = xsq * x, xpow4 = xsq * xsq;
+  double diff_A_NkT = 3.629 + 7.264*x - beta*(3.492 - 18.698*x + 35.505*xsq - 31.816*xpow3 + 11.195*xpow4)
+                    - beta_sqrt*(5.369 + 13.16*x + 18.525*xsq - 17.076*xpow3 + 9.32*xpow4)
+                    + 10.4925*xsq + 11.46*xpow3 + 2.176*xpow4*xpow4*x;
+  double d2A_dx2 = 7.264 + 20.985*x
+                 + beta*(18.698 - 71.01*x + 95.448*xsq - 44.78*xpow3)
+                 - beta_sqrt*(13.16 + 37.05*x - 51.228*xsq + 37.28*xpow3)
+                 + 34.38*xsq + 19.584*xpow4*xpow4;
+  *p = rho * T * (1.0 + diff_A_NkT * x);
+  double csq = T * (1.0 + 2.0 * diff_A_NkT * x + d2A_dx2 * x * x);
+  *c = csq > 0.0 ? sqrt(csq) : 0.0;
+}
+/* PairSPHLJ::compute, pair_sph_lj.cpp:48-182.  Note `fi += lrc` INSIDE the neighbor loop (:139): the long-range correction piles up
+ * on fi, so the force of a pair depends on how many in-cutoff neighbors of i the half list visited before it -- the list order is
+ * part of the result, which is why this oracle walks the list in the reference's own order. */
+static void pair_lj(osph_sph *s, opair *p)
+{
+  int nlocal = s->nlocal, nt = s->ntypes + 1; const double *x = s->x, *v = s->vest, *rho = s->rho, *mass = s->mass, *e = s->e, *cv = s->cv;
+  double *f = s->f, *de = s->de, *drho = s->drho;
+  NB_LOOP_BEGIN(0)
+    double vxtmp = v[3*i], vytmp = v[3*i+1], vztmp = v[3*i+2], imass = mass[itype], fi, ci;
+    ljeos2(rho[i], e[i], cv[i], &fi, &ci);
+    fi /= (rho[i] * rho[i]);
+    NB_FOR_J(0)
+      double jmass = mass[jtype], ih = 1.0 / h, ihsq = ih * ih, ihcub = ihsq * ih, wfd = h - sqrt(rsq), fj, cj;
+      if (s->dim == 3) wfd = -25.066903536973515383e0 * wfd * wfd * ihsq * ihsq * ihsq * ih;
+      else wfd = -19.098593171027440292e0 * wfd * wfd * ihsq * ihsq * ihsq;
+      ljeos2(rho[j], e[j], cv[j], &fj, &cj);
+      fj /= (rho[j] * rho[j]);
+      double lrc = -11.1701 * (ihcub * ihcub * ihcub - 1.5 * ihcub);
+      fi += lrc; fj += lrc;
+      double delVdotDelR = delx * (vxtmp - v[3*j]) + dely * (vytmp - v[3*j+1]) + delz * (vztmp - v[3*j+2]), fvisc;
+      if (delVdotDelR < 0.) {
+        double mu = h * delVdotDelR / (rsq + 0.01 * h * h);
+        fvisc = -p->viscosity[itype * nt + jtype] * (ci + cj) * mu / (rho[i] + rho[j]);
+      } else fvisc = 0.;
+      double fpair = -imass * jmass * (fi + fj + fvisc) * wfd, deltaE = -0.5 * fpair * delVdotDelR;
+      f[3*i] += delx * fpair; f[3*i+1] += dely * fpair; f[3*i+2] += delz * fpair;
+      drho[i] += jmass * delVdotDelR * wfd;
+      de[i] += deltaE;
+      f[3*j] -= delx * fpair; f[3*j+1] -= dely * fpair; f[3*j+2] -= delz * fpair;
+      de[j] += deltaE;
+      drho[j] += imass * delVdotDelR * wfd;
+  NB_END
+}
+
 /* PairSPHTaitwaterMultiphase::compute, pair_sph_taitwater_multiphase.cpp:55-186 */
 static void pair_taitwater_multiphase(osph_sph *s, opair *p)
 {
@@ -942,6 +992,7 @@ static int pair_compute_slot(osph_sph *s, int k)
   case B200_PAIR_HEATCONDUCTION_MULTIPHASE: pair_heatconduction_multiphase(s, p, 0); break;
   case B200_PAIR_HEATCONDUCTION_PHASECHANGE: pair_heatconduction_multiphase(s, p, 1); break;
   case B200_PAIR_IDEALGAS: pair_idealgas(s, p); break;
+  case B200_PAIR_LJ: pair_lj(s, p); break;
   default: return fail("unknown pair style");
   }
   return 0;

@@ -26,6 +26,7 @@ class Case:
         self.name, self.dim, self.boundary, self.box = name, dim, boundary, box
         self.atom_style, self.ntypes, self.create, self.cmds, self.nsteps = atom_style, ntypes, create, cmds, nsteps
         self.units, self.groups, self.tol_traj, self.regions = units, groups, tol_traj, regions
+        self.engine = True         # False: restated by the oracle only (the engine refuses the deck with a message)
 
     @property
     def multiphase(self):
@@ -267,6 +268,30 @@ displace_atoms all random 0.05 0.05 %s 4711 units box""" % (lat, fill, right, "0
 _add(_shock("shock3d", 3, 20))
 _add(_shock("shock2d", 2, 40))
 _add(_shock("gas3d", 3, 15, onetype=True))
+
+
+# ---- sph/lj: Lennard-Jones EOS fluid; oracle only (the engine refuses the style) ----
+def _lj(name, dim, nsteps):
+    box = ((0, 0, 0), (12, 12, 12)) if dim == 3 else ((0, 0, -0.05), (20.5, 20.5, 0.05))
+    create = """lattice %s %s
+create_atoms 1 box
+set group all meso_e 1.5
+set group all meso_cv 1.0
+set group all meso_rho 0.6
+displace_atoms all random 0.08 0.08 %s 4711 units box
+mass 1 1.0
+velocity all create 0.05 4711 dist gaussian""" % ("sc" if dim == 3 else "sq", "0.3" if dim == 3 else "0.6", "0.08" if dim == 3 else "0.0")
+    cmds = [("mass", "1", 1.0), ("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/lj"),
+            ("pair_coeff", "* *", "sph/rhosum", 2.5), ("pair_coeff", "* *", "sph/lj", 0.5, 2.5),
+            ("neighbor", 0.1 if dim == 2 else 0.3), ("neigh_modify", dict(every=2, delay=0, check="yes")), ("timestep", 0.005 if dim == 2 else 0.001),
+            ("fix", "all", "meso")]
+    c = Case(name, dim, "p p p", box, "meso", 1, create, cmds, nsteps, units="lj")
+    c.engine = False
+    return c
+
+
+_add(_lj("lj3d", 3, 8))
+_add(_lj("lj2d", 2, 80))
 # the shipped shock-tube decks as they are: shrink-wrapped x (examples/USER/sph/shock_tube/shock{2d,3d}.lmp:2-3, boundary s p p)
 _add(_shock("shock3d_shrink", 3, 45, bnd="s p p"))
 _add(_shock("shock2d_shrink", 2, 40, bnd="ms p p", fill="-25.5"))

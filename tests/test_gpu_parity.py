@@ -16,13 +16,21 @@ pkg = importlib.import_module("lammps-sph-multiphase_b200")
 pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-10
-ALL = list(cases.CASES)
+ALL = [n for n, c in cases.CASES.items() if c.engine]      # sph/lj decks are restated by the oracle only (the engine refuses the style)
 
 
 @pytest.mark.parametrize("name", ALL)
 def test_engine_matches_reference_fixture(name):
     e0, eN = harness.run_case(pkg.B200Sim, name, tol_step=TOL_STEP)
     print(name, "run0", {k: "%.1e" % v for k, v in e0.items()}, "runN", {k: "%.1e" % v for k, v in eN.items()})
+
+
+@pytest.mark.parametrize("name", [n for n, c in cases.CASES.items() if not c.engine])
+def test_engine_refuses_what_it_does_not_implement(name):
+    """no silent fallback: a deck with a sub-style the engine lacks (sph/lj) fails at b200_pair_add with a message"""
+    with pytest.raises(RuntimeError) as e:
+        pkg.B200Sim(cases.CASES[name].deck())
+    assert "unknown pair style" in str(e.value)
 
 
 @pytest.mark.parametrize("name", ["dam3d", "droplet3d", "heat2d", "bubble3d"])
