@@ -135,7 +135,7 @@ int  b200_pair_clear(b200_sph *h);
 int  b200_pair_add(b200_sph *h, const b200_pair_desc *d);      /* returns slot >= 0 */
 
 /* Fixes, in deck order (Modify hook order, src/modify.cpp).                    */
-int  b200_fix_clear(b200_sph *h);
+int  b200_fix_clear(b200_sph *h);                               /* forget the registered fixes; a fix phase_change registered again with the same arguments keeps its next step and RNG position (fix_phase_change.cpp:116,345) */
 int  b200_fix_meso(b200_sph *h, int groupbit);                  /* fix_meso.cpp:91-180 */
 int  b200_fix_meso_stationary(b200_sph *h, int groupbit);       /* fix_meso_stationary.cpp:71-112 */
 int  b200_fix_gravity(b200_sph *h, int groupbit, double xacc, double yacc, double zacc); /* fix_gravity.cpp:244-295 */

@@ -18,9 +18,9 @@ static int fail(const std::string &m) { g_err = m; return -1; }
 #define API_BEGIN try {
 #define API_END } catch (const std::string &m) { return fail(m); } catch (const std::exception &e) { return fail(e.what()); } return 0;
 
-enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_PRUNE, T_NTIMERS };
+enum { T_INTEGRATE = 0, T_COMM, T_NEIGH_BIN, T_NEIGH_BUILD, T_DENSITY, T_COLORGRAD, T_DERIVE, T_FORCE, T_FINAL, T_PHASE, T_NTIMERS };
 static const char *timer_names[T_NTIMERS] = {"initial_integrate", "forward_comm", "neigh_bin_sort_ghost", "neigh_build", "density",
-                                             "colorgradient", "records", "force", "reverse_post_final", "phase_change", "unused"};
+                                             "colorgradient", "records", "force", "reverse_post_final", "phase_change"};
 
 template <class T> struct DevBuf {
   T *p = nullptr; size_t cap = 0;
@@ -109,7 +109,7 @@ struct b200_sph {
   int npair = 0; PairTab h_tab[MAXPAIR]; PairTab *d_tab[MAXPAIR] = {nullptr};
   std::vector<Pass> plan;
   FixList fl{};
-  std::vector<PcFix> pcs;
+  std::vector<PcFix> pcs, pcs_old;             // pcs_old: the fixes of the previous registration (b200_fix_clear) -- an unchanged fix phase_change keeps its state
   DevBuf<unsigned char> pc_flag; DevBuf<double> pc_thr, pc_dmass; DevBuf<int> pc_dev; DevBuf<PcNew> pc_new;
   int maxtag = 0;
   // particles
@@ -508,30 +508,39 @@ static bool tile_rows(b200_sph *h)
   int nl = h->nlocal, na = h->nall();
   const bool mp = h->multiphase != 0;
   h->ntiles = h->ngtiles = 0;
-  if (!nl) return true;
-  h->tiles.ensure((size_t)g.ncells + 1);
   CK(cudaMemsetAsync(h->d_tflags, 0, 16 * sizeof(int), h->st));
-  TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
-  bool classes = !mp && h->nswap > 0 && !h->no_overlap;
-  for (int k = 0; k < h->nswap; k++)       // the interior criterion of k_tile_plan needs cells at least one ghost cutoff wide
-    if (1.0 / g.cinv[h->swaps[k].dim] < g.cutghost) classes = false;
-  if (classes) {             // interior tiles first, then the boundary tiles (k_tile_plan)
-    for (int k = 0; k < h->nswap; k++) P.swapdim[h->swaps[k].dim] = 1;
-    P.want = 0;
+  bool classes = false;
+  if (nl) {
+    h->tiles.ensure((size_t)g.ncells + 1);
+    TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
+    classes = !mp && h->nswap > 0 && !h->no_overlap;
+    for (int k = 0; k < h->nswap; k++)       // the interior criterion of k_tile_plan needs cells at least one ghost cutoff wide
+      if (1.0 / g.cinv[h->swaps[k].dim] < g.cutghost) classes = false;
+    if (classes) {             // interior tiles first, then the boundary tiles (k_tile_plan)
+      for (int k = 0; k < h->nswap; k++) P.swapdim[h->swaps[k].dim] = 1;
+      P.want = 0;
+      LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
+      CK(cudaMemcpyAsync(h->d_tflags + 5, h->d_tflags, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+      P.want = 1;
+    }
     LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
-    CK(cudaMemcpyAsync(h->d_tflags + 5, h->d_tflags, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
-    P.want = 1;
+    if (mp && h->nghost) {       // ghost rows: what the reference accumulates on ghost atoms (then reverse-communicates)
+      h->gtiles.ensure((size_t)g.ncells + 1);
+      TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
+      LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, G);
+    }
   }
-  LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, P);
-  if (mp && h->nghost) {       // ghost rows: what the reference accumulates on ghost atoms (then reverse-communicates)
-    h->gtiles.ensure((size_t)g.ncells + 1);
-    TilePlanArgs G{g, nl, TILE_ROWS, h->tile_slotcap, 1, 1, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->gtiles.p, h->d_tflags + 8};
-    LAUNCH(h, k_tile_plan, nblk((long long)g.nc[1] * g.nc[2] * 32, 128), 128, G);
+  // tiles or rows is a collective decision: the single-phase tile path sends no reverse halo, the row path does, so a rank
+  // falling back alone would leave its peers waiting in ncclRecv
+  if (h->world > 1) {
+    NCK(g_nccl.AllReduce(h->d_tflags + 2, h->d_tflags + 2, 1, ncclInt, ncclMax, h->nccl, h->st));
+    NCK(g_nccl.AllReduce(h->d_tflags + 10, h->d_tflags + 10, 1, ncclInt, ncclMax, h->nccl, h->st));
   }
   int *hf = h->h_flags + 16;                       // pinned: [0..3] owned-row tiles, [8..11] ghost-row tiles
   CK(cudaMemcpyAsync(hf, h->d_tflags, 12 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   if (hf[2] || hf[10]) return false;
+  if (!nl) return true;
   h->ntiles = hf[0]; h->ngtiles = hf[8]; h->nint = classes ? hf[5] : 0;
   h->tile_cap = std::max(2, (std::max(hf[1], hf[9]) + 1) & ~1);
   const int nrows = mp ? na : nl;
@@ -1001,7 +1010,7 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
         },
         [&](int which) { return tile_records(h, 2, 0, -1, nullptr, which); });
     } else halo_wait(h);
-    if (h->nghost) {      // comm->forward_comm_pair (:203): the ghosts' new rho
+    if (h->nghost || h->world > 1) {      // comm->forward_comm_pair (:203): the ghosts' new rho (decided from global state: peers may wait for this rank)
       auto rho_halo = [&]() {
         comm_forward_generic(h, 1,
           [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
@@ -1044,7 +1053,8 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
 
 static void run_pass(b200_sph *h, const Pass &p)
 {
-  if (!h->nlocal) return;
+  // a rank without owned atoms still takes part in every halo of the pass (it may hold ghosts and send lists);
+  // only its local kernels have nothing to do (launch_tiles / the row kernels return on empty ranges)
   if (h->tile_on != h->rows_tiled) throw std::string("b200: the neighbor rows were built for another pair plan (call b200_setup / b200_reneighbor)");
   if (h->tile_on) { run_pass_tile(h, p); return; }
   halo_wait(h);
@@ -1058,7 +1068,7 @@ static void run_pass(b200_sph *h, const Pass &p)
     if (p.type == 0) {
       h->tbegin(T_DENSITY);
       if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_THREADS, A);
-      if (h->nghost)       // comm->forward_comm_pair (:203)
+      if (h->nghost || h->world > 1)       // comm->forward_comm_pair (:203)
         comm_forward_generic(h, 1,
           [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
           [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
@@ -1153,9 +1163,9 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
 }
 static void initial_integrate(b200_sph *h)
 {
+  CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));      // the moved flag feeds an all-reduce (neigh_decide): reset it on empty ranks too
   if (!h->nlocal) return;
   h->tbegin(T_INTEGRATE);
-  CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), h->st));
   int track = h->far_margin > 0.0;
   LAUNCH(h, k_initial_integrate, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->dt, 0.5 * h->dt * h->ftm2v, h->check,
          h->xhold.p, h->triggersq, h->d_flags + 1, track, h->d_dmaxsq, h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v,
@@ -1206,41 +1216,49 @@ static void phase_change(b200_sph *h, PcFix &f)
   if (f.next != h->ntimestep) return;
   f.next += f.d.nfreq;
   int nl = h->nlocal, na = h->nall();
-  if (!nl) return;
+  if (!nl && h->world == 1) return;
   dt_download(h);
   h->tbegin(T_PHASE);
-  int norig = std::max(h->next_orig, nl);
-  h->pc_flag.ensure(norig); h->pc_thr.ensure(norig); h->pc_dev.ensure(norig); h->pc_dmass.ensure(na); h->pc_new.ensure(PC_MAXNEW);
-  CK(cudaMemsetAsync(h->pc_flag.p, 0, norig, h->st));
-  PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.norig = norig; P.stride = h->stride; P.dt = h->dt;
-  for (int d = 0; d < 3; d++) { P.sublo[d] = h->g.sublo[d]; P.subhi[d] = h->g.subhi[d]; P.boxhi[d] = h->g.boxhi[d]; }
+  // a rank without owned atoms has no candidates, but its ghosts' (zero) dmass still travels back and it
+  // takes part in the tag_extend gather below: only the local kernels are skipped
+  int nins = 0;
+  h->pc_dmass.ensure(na + 1);
   OwnedSet &c = h->C();
   PcArrays a{c.xt.p, c.vr.p, c.vm.p, c.cgm.p, c.e.p, c.cv.p, c.orig.p, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p,
              h->rows_tiled ? 1 : 0, h->stride / 8, h->tiles.p, h->rowtile.p, h->gorder.p};
-  LAUNCH(h, k_pc_candidates, nblk(na, 128), 128, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p);
-  CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
-  // compact the candidates (ascending local index) so the serial walk touches only them
-  h->pos.ensure(norig + 2); h->flag.ensure(norig + 2); ensure_scan_tmp(h, norig + 2);
-  LAUNCH(h, k_pc_mark, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p);
-  scan_exclusive(h, h->pos.p, norig, h->scan_tmp.p);
-  CK(cudaMemcpyAsync(h->h_flags + 7, h->pos.p + norig, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
-  int ncand = h->h_flags[7];
-  if (ncand) LAUNCH(h, k_pc_compact, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p, h->flag.p);
-  LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state, h->flag.p, ncand);
-  CK(cudaMemcpyAsync(h->h_flags + 5, f.d_state + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (nl) {
+    int norig = std::max(h->next_orig, nl);
+    h->pc_flag.ensure(norig); h->pc_thr.ensure(norig); h->pc_dev.ensure(norig); h->pc_new.ensure(PC_MAXNEW);
+    CK(cudaMemsetAsync(h->pc_flag.p, 0, norig, h->st));
+    PcParams P; P.d = f.d; P.dim = h->g.dim; P.nlocal = nl; P.nall = na; P.norig = norig; P.stride = h->stride; P.dt = h->dt;
+    for (int d = 0; d < 3; d++) { P.sublo[d] = h->g.sublo[d]; P.subhi[d] = h->g.subhi[d]; P.boxhi[d] = h->g.boxhi[d]; }
+    LAUNCH(h, k_pc_candidates, nblk(na, 128), 128, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p);
+    CK(cudaMemsetAsync(f.d_state + 1, 0, 2 * sizeof(int), h->st));
+    // compact the candidates (ascending local index) so the serial walk touches only them
+    h->pos.ensure(norig + 2); h->flag.ensure(norig + 2); ensure_scan_tmp(h, norig + 2);
+    LAUNCH(h, k_pc_mark, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p);
+    scan_exclusive(h, h->pos.p, norig, h->scan_tmp.p);
+    CK(cudaMemcpyAsync(h->h_flags + 7, h->pos.p + norig, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int ncand = h->h_flags[7];
+    if (ncand) LAUNCH(h, k_pc_compact, nblk(norig, 256), 256, norig, h->pc_flag.p, h->pos.p, h->flag.p);
+    LAUNCH(h, k_pc_walk, 1, 32, P, a, h->pc_flag.p, h->pc_thr.p, h->pc_dev.p, h->pc_dmass.p, h->pc_new.p, f.d_state, h->flag.p, ncand);
+    CK(cudaMemcpyAsync(h->h_flags + 5, f.d_state + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  } else if (na) CK(cudaMemsetAsync(h->pc_dmass.p, 0, (size_t)na * sizeof(double), h->st));
   if (h->nghost || h->world > 1) comm_reverse_scalar_add(h, h->pc_dmass.p);      // comm->reverse_comm_fix (:324)
-  LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p);
-  CK(cudaStreamSynchronize(h->st));
-  int nins = h->h_flags[5];
-  if (h->h_flags[6]) throw std::string("fix phase_change: more than PC_MAXNEW insertions in one call");
+  if (nl) {
+    LAUNCH(h, k_pc_apply, nblk(nl, 256), 256, nl, a, h->pc_dmass.p);
+    CK(cudaStreamSynchronize(h->st));
+    nins = h->h_flags[5];
+    if (h->h_flags[6]) throw std::string("fix phase_change: more than PC_MAXNEW insertions in one call");
+  }
   int tag0 = h->maxtag, ninsall = nins;
   if (h->world > 1) {        // Atom::tag_extend: MPI_Scan of the per-rank counts (atom.cpp:598-630)
     std::vector<int> all(h->world);
-    h->h_flags[9] = nins;
-    CK(cudaMemcpyAsync(h->d_flags + 9, h->h_flags + 9, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    h->h_flags[12] = nins;
+    CK(cudaMemcpyAsync(h->d_flags + 12, h->h_flags + 12, sizeof(int), cudaMemcpyHostToDevice, h->st));
     DevBuf<int> tmp; tmp.ensure(h->world);
-    NCK(g_nccl.AllGather(h->d_flags + 9, tmp.p, 1, ncclInt, h->nccl, h->st));
+    NCK(g_nccl.AllGather(h->d_flags + 12, tmp.p, 1, ncclInt, h->nccl, h->st));
     CK(cudaMemcpyAsync(all.data(), tmp.p, h->world * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     tmp.release();
@@ -1284,12 +1302,12 @@ static void do_setup(b200_sph *h)
 {
   if (!h->geom_ready) setup_geometry(h);
   if (h->world > 1) {      // new-atom tags continue after the GLOBAL maximum (Atom::tag_extend, atom.cpp:603-605)
-    h->h_flags[9] = h->maxtag;
-    CK(cudaMemcpyAsync(h->d_flags + 9, h->h_flags + 9, sizeof(int), cudaMemcpyHostToDevice, h->st));
-    NCK(g_nccl.AllReduce(h->d_flags + 9, h->d_flags + 9, 1, ncclInt, ncclMax, h->nccl, h->st));
-    CK(cudaMemcpyAsync(h->h_flags + 9, h->d_flags + 9, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    h->h_flags[12] = h->maxtag;
+    CK(cudaMemcpyAsync(h->d_flags + 12, h->h_flags + 12, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    NCK(g_nccl.AllReduce(h->d_flags + 12, h->d_flags + 12, 1, ncclInt, ncclMax, h->nccl, h->st));
+    CK(cudaMemcpyAsync(h->h_flags + 12, h->d_flags + 12, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    h->maxtag = h->h_flags[9];
+    h->maxtag = h->h_flags[12];
   }
   build_plan(h);
   neighbor_build(h, true);
@@ -1423,7 +1441,7 @@ int b200_destroy(b200_sph *h)
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state);
+  h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state); for (PcFix &f : h->pcs_old) cudaFree(f.d_state);
   h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); h->d_midsq.release(); cudaFree(h->d_dmaxsq); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
   h->sendbuf.release(); h->recvbuf.release(); for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
@@ -1552,7 +1570,10 @@ int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
 int b200_fix_clear(b200_sph *h)
 {
   memset(&h->fl, 0, sizeof h->fl);
-  for (PcFix &f : h->pcs) cudaFree(f.d_state);
+  // FixPhaseChange keeps next_reneighbor and its RanPark stream across `run` commands (fix_phase_change.cpp:116,345): when the
+  // caller re-registers the same fix (VerletB200::configure runs per `run`), b200_fix_phase_change adopts that state again
+  for (PcFix &f : h->pcs_old) cudaFree(f.d_state);
+  h->pcs_old = h->pcs;
   h->pcs.clear();
   h->dtreset = false;
   return 0;
@@ -1621,10 +1642,23 @@ int b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d)
   CK(cudaSetDevice(h->device));
   if (d->seed <= 0) throw std::string("Illegal value for seed");                   // fix_phase_change.cpp:70
   if (!h->multiphase) throw std::string("fix phase_change requires atom_style meso/multiphase");
-  PcFix f; f.d = *d; f.next = d->first_step;
-  CK(cudaMalloc(&f.d_state, 4 * sizeof(int)));
-  int st[4] = {d->seed, 0, 0, 0};
-  CK(cudaMemcpy(f.d_state, st, sizeof st, cudaMemcpyHostToDevice));
+  PcFix f; f.d = *d; f.next = d->first_step; f.d_state = nullptr;
+  auto same = [](b200_phase_change_desc a, b200_phase_change_desc b) {
+    return a.groupbit == b.groupbit && a.Tc == b.Tc && a.Tt == b.Tt && a.Hwv == b.Hwv && a.dr == b.dr && a.to_mass == b.to_mass && a.cutoff == b.cutoff &&
+           a.from_type == b.from_type && a.to_type == b.to_type && a.nfreq == b.nfreq && a.seed == b.seed && a.energy_chance_flag == b.energy_chance_flag &&
+           a.change_chance == b.change_chance && a.phase_change_rate == b.phase_change_rate && a.maxattempt == b.maxattempt && a.first_step == b.first_step;
+  };
+  for (size_t k = 0; k < h->pcs_old.size(); k++)
+    if (same(h->pcs_old[k].d, *d)) {          // the same fix registered again: keep its next step and RNG position
+      f.next = h->pcs_old[k].next; f.d_state = h->pcs_old[k].d_state;
+      h->pcs_old.erase(h->pcs_old.begin() + k);
+      break;
+    }
+  if (!f.d_state) {
+    CK(cudaMalloc(&f.d_state, 4 * sizeof(int)));
+    int st[4] = {d->seed, 0, 0, 0};
+    CK(cudaMemcpy(f.d_state, st, sizeof st, cudaMemcpyHostToDevice));
+  }
   h->pcs.push_back(f);
   API_END
 }

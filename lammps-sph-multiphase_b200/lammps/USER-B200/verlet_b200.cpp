@@ -24,7 +24,7 @@
 
 using namespace LAMMPS_NS;
 
-VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), h(NULL), h_step(-1) {}
+VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), h(NULL) {}
 
 VerletB200::~VerletB200() { if (h) b200_destroy(h); }
 
@@ -85,23 +85,29 @@ void VerletB200::configure()
     check(b200_pair_add(h, &d));
   }
 
-  // fixes in Modify order; a fix with per-step hooks but no /b200 variant cannot run device-resident
-  if (h_step != update->ntimestep || true) {
-    check(b200_fix_clear(h));
-    for (int i = 0; i < modify->nfix; i++) {
-      Fix *f = modify->fix[i];
-      B200FixShell *shell = dynamic_cast<B200FixShell *>(f);
-      if (shell) { check(shell->b200_register(h)); continue; }
-      int mask = modify->fmask[i];
-      const int stepping = FixConst::INITIAL_INTEGRATE | FixConst::POST_INTEGRATE | FixConst::PRE_EXCHANGE | FixConst::PRE_NEIGHBOR |
-                           FixConst::PRE_FORCE | FixConst::POST_FORCE | FixConst::FINAL_INTEGRATE;
-      if (mask & stepping) {
-        char msg[256];
-        sprintf(msg, "run_style verlet/b200: fix %s (%s) has no /b200 variant", f->id, f->style);
-        error->all(FLERR, msg);
-      }
+  // fixes in Modify order.  A fix with per-step hooks but no /b200 variant cannot run device-resident: it is refused, with one
+  // exception -- read-only END_OF_STEP fixes (fix print, fix ave/*): the run is cut into segments that end on their `nevery`,
+  // the host arrays are refreshed there and modify->end_of_step() is called exactly as Verlet::run does (verlet.cpp:300).
+  // b200_fix_clear keeps the state of an unchanged fix phase_change (next step, RNG position) across `run` commands, as
+  // FixPhaseChange itself does (fix_phase_change.cpp:116,345).
+  check(b200_fix_clear(h));
+  host_every.clear();
+  for (int i = 0; i < modify->nfix; i++) {
+    Fix *f = modify->fix[i];
+    B200FixShell *shell = dynamic_cast<B200FixShell *>(f);
+    if (shell) { check(shell->b200_register(h)); continue; }
+    int mask = modify->fmask[i];
+    const int stepping = FixConst::INITIAL_INTEGRATE | FixConst::POST_INTEGRATE | FixConst::PRE_EXCHANGE | FixConst::PRE_NEIGHBOR |
+                         FixConst::PRE_FORCE | FixConst::POST_FORCE | FixConst::FINAL_INTEGRATE |
+                         FixConst::INITIAL_INTEGRATE_RESPA | FixConst::POST_INTEGRATE_RESPA | FixConst::PRE_FORCE_RESPA |
+                         FixConst::POST_FORCE_RESPA | FixConst::FINAL_INTEGRATE_RESPA;
+    bool readonly_eos = strcmp(f->style, "print") == 0 || strncmp(f->style, "ave/", 4) == 0;
+    if ((mask & stepping) || ((mask & FixConst::END_OF_STEP) && !readonly_eos)) {
+      char msg[256];
+      sprintf(msg, "run_style verlet/b200: fix %s (%s) has no /b200 variant", f->id, f->style);
+      error->all(FLERR, msg);
     }
-    h_step = update->ntimestep;
+    if (mask & FixConst::END_OF_STEP) host_every.push_back(f->nevery > 0 ? f->nevery : 1);
   }
 }
 
@@ -179,12 +185,17 @@ void VerletB200::setup_minimal(int flag)
   if (flag) setup();
 }
 
-/* Verlet::run, verlet.cpp:207-309: device-resident segments between output steps */
+/* Verlet::run, verlet.cpp:207-309: device-resident segments between output steps and the steps on which a host-side
+   END_OF_STEP fix (fix print, fix ave/...) is due */
 void VerletB200::run(int n)
 {
   bigint nend = update->ntimestep + n;
   while (update->ntimestep < nend) {
     bigint next = output->next < nend ? output->next : nend;
+    for (size_t q = 0; q < host_every.size(); q++) {
+      bigint due = (update->ntimestep / host_every[q] + 1) * host_every[q];
+      if (due < next) next = due;
+    }
     if (next <= update->ntimestep) next = update->ntimestep + 1;
     int k = (int)(next - update->ntimestep);
     timer->stamp();
@@ -195,13 +206,16 @@ void VerletB200::run(int n)
     update->ntimestep += k;
     { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // fix dt/reset/b200 changes it on the device
     timer->stamp(TIME_PAIR);
-    if (update->ntimestep == output->next || update->ntimestep == nend) {
+    bool host_due = false;
+    for (size_t q = 0; q < host_every.size(); q++) if (update->ntimestep % host_every[q] == 0) host_due = true;
+    if (update->ntimestep == output->next || update->ntimestep == nend || host_due) {
       download();
+      if (vflag && force->pair) check(b200_get_virial(h, force->pair->virial));
       timer->stamp(TIME_COMM);
     }
+    if (host_due) modify->end_of_step();            // the /b200 shells' own end_of_step hooks are no-ops under verlet/b200
     if (update->ntimestep == output->next) {
       ev_set(update->ntimestep);
-      if (vflag && force->pair) check(b200_get_virial(h, force->pair->virial));
       output->write(update->ntimestep);
       timer->stamp(TIME_OUTPUT);
     }

@@ -12,6 +12,7 @@ IntegrateStyle(verlet/b200,VerletB200)
 #define LMP_VERLET_B200_H
 
 #include "verlet.h"
+#include <vector>
 #include "b200_sph.h"
 
 namespace LAMMPS_NS {
@@ -27,7 +28,7 @@ class VerletB200 : public Verlet {
 
  private:
   b200_sph *h;
-  long long h_step;              // engine timestep the fixes were registered for
+  std::vector<int> host_every;   // nevery of the host-side END_OF_STEP fixes (fix print, fix ave/...): segment boundaries of run()
   void check(int rc);
   void configure();
   void upload();

@@ -82,3 +82,55 @@ def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     assert np.array_equal(pa[:, 0], pb[:, 0])
     scale = np.abs(pa[:, 1:]).max()
     assert np.abs(pa[:, 1:] - pb[:, 1:]).max() <= 100 * tol * max(scale, 1e-300), (pa[-1], pb[-1])
+
+
+def _both(tmp_path, text):
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
+    a, a_out = run(REF, [], str(tmp_path / "ref"), text)
+    b, b_out = run(B200, ["-sf", "b200"], str(tmp_path / "b200"), text)
+    assert "B200 engine" in b_out
+    return a, a_out, b, b_out
+
+
+def test_host_end_of_step_fixes_fire(tmp_path):
+    """fix print (END_OF_STEP, no /b200 variant) must fire on its steps with the values of THAT step: VerletB200::run ends a
+    device-resident segment on every `nevery`, refreshes the host arrays and calls modify->end_of_step() (verlet.cpp:300)"""
+    case = cases.CASES["dam2d"]
+    nsteps = 30
+    extra = "\n".join(["variable s equal step", "variable k equal ke", "variable xc equal xcm(all,x)",
+                       'fix pr all print 7 "PRINTED ${s} ${k} ${xc}"'])
+    text = deck_text(case, nsteps).replace("run %d" % nsteps, extra + "\nrun %d" % nsteps)
+    a, a_out, b, b_out = _both(tmp_path, text)
+    pa = [l.split()[1:] for l in a_out.splitlines() if l.startswith("PRINTED")]
+    pb = [l.split()[1:] for l in b_out.splitlines() if l.startswith("PRINTED")]
+    assert len(pa) == len(pb) and len(pa) >= 4, (pa, pb)
+    for ra, rb in zip(pa, pb):
+        assert ra[0] == rb[0]
+        assert relerr(np.array([float(v) for v in rb[1:]]), np.array([float(v) for v in ra[1:]])) <= 1e-5     # fix print writes %g-style 6 digits... compare at that precision
+    assert relerr(b[:, 2:5], a[:, 2:5]) <= 1e-9
+
+
+def test_unsupported_stepping_fix_is_refused(tmp_path):
+    """a fix with per-step hooks and no /b200 variant is an error, not a silent no-op"""
+    if not os.path.exists(B200):
+        pytest.skip("lmp_b200 not built")
+    case = cases.CASES["dam2d"]
+    text = deck_text(case, 5).replace("run 5", "fix bad all momentum 1 linear 1 1 1\nrun 5")
+    os.makedirs(str(tmp_path / "b"), exist_ok=True)
+    with open(str(tmp_path / "b" / "deck.lmp"), "w") as f:
+        f.write(text)
+    p = subprocess.run([B200, "-sf", "b200", "-in", "deck.lmp", "-log", "none"], cwd=str(tmp_path / "b"), capture_output=True, text=True, timeout=300)
+    assert "has no /b200 variant" in p.stdout + p.stderr
+
+
+def test_phase_change_state_survives_a_second_run(tmp_path):
+    """`run 10` twice == what the reference does with the same two commands: fix phase_change keeps next_reneighbor and its
+    RNG stream across runs (fix_phase_change.cpp:116,345), so must the engine behind VerletB200::configure"""
+    case = cases.CASES["bubble2d"]
+    text = deck_text(case, 20).replace("run 20", "run 10\nrun 10")
+    a, a_out, b, b_out = _both(tmp_path, text)
+    assert a.shape == b.shape, "particle counts differ: %s vs %s" % (a.shape, b.shape)
+    assert np.array_equal(a[:, :2], b[:, :2])
+    for lo, hi in ((2, 5), (5, 8), (8, 11), (11, 12), (12, 13)):
+        assert relerr(b[:, lo:hi], a[:, lo:hi]) <= 1e-8
