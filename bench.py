@@ -15,6 +15,15 @@ Tait force + viscosity, gravity, velocity-Verlet update of x, v, rho, e).
 For N > 1 the tank is tiled N times along x (one C2-sized water column per GPU) and decomposed into
 N bricks: ghost exchange, reverse accumulation and atom migration run over NCCL (weak scaling).
 
+Besides the headline (`value`, C2) every line carries
+  "configs": C3 (two-phase droplet box, nx = 160: 4.1 M particles, 1 GPU) at N = 1; C5_strong (the same periodic multiphase box at
+             nx = 400: 64 M particles, brick grid from ProcMap::onelevel_grid, SAME total at every N incl. N = 1 -> strong scaling);
+             C4 (16 M particles, + heat/phasechange and fix phase_change) at N = 2, 4 -- each with ms_per_step, stage_ms,
+             particle_steps_s, roofline (228 / 572 B per particle-step, SURVEY 8d) and sum f / sum |f| over the periodic box;
+  "parity":  at N > 1, AFTER the timed regions: the fixtures dam3d, heat3d, droplet3d_static on the N ranks against the 1-rank
+             reference fixtures and droplet3d, droplet3d_heat against the CPU oracle emulating the same brick grid (2x2x2 at
+             N = 8) -- tests/mgpu_lib.py, checker role only.  The run exits non-zero if parity is not ok.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
 import argparse
@@ -43,6 +52,10 @@ UNIT = "particle-steps/s"
 BYTES_FORCE = 100
 FP64_NOTE = "profiles/r01_tile_v5_final_full.txt: sm__pipe_fp64_cycles_active 50.6 %, shared-memory data pipe 57.6 % of peak for k_tile_force<K_TAIT> (ncu --set full, 1 028 768 particles, 0.54 ms; 42 fp64 instructions per neighbor)"
 BYTES_STEP = 464          # whole single-phase step (rhosum 36 + taitwater 100 + fix meso 200 + 128)
+BYTES_MP_LOOP, BYTES_MP_STEP = 228, 572        # multiphase density + colorgradient + force loop / whole step
+BYTES_C4_LOOP, BYTES_C4_STEP = 252, 596        # + heat/phasechange in the fused force pass
+FP64_LANES_PER_SM = 64    # B200: 64 fp64 FMA lanes per SM and clock
+PARITY_CASES = ("dam3d", "heat3d", "droplet3d_static", "droplet3d", "droplet3d_heat")
 
 
 # ----------------------------------------------------------------------------- workload ----
@@ -155,6 +168,121 @@ def run_reference(atoms, params, nsteps, warmup, replicas):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+
+# ------------------------------------------------------------- multiphase configs ----
+def lattice_brick(nx, brick, cube=0.2, jitter=0.0, c4=False):
+    """this rank's part of the nx^3 simple-cubic lattice of the unit periodic box (the square_to_sphere / bubble decks at scale):
+    type 2 inside the centred cube.  Per-dimension ownership tests on the 1-D coordinates, so the ranks' parts tile the box
+    exactly; tags are the global lattice index + 1; the jitter is a hash of the tag (the same on any decomposition)."""
+    dx = 1.0 / nx
+    c1 = np.arange(nx) * dx
+    sel = []
+    for d in range(3):
+        lo, hi = (brick.sublo[d], brick.subhi[d]) if brick is not None else (0.0, 1.0)
+        sel.append(np.nonzero((c1 >= lo) & (c1 < hi))[0])
+    ix, iy, iz = np.meshgrid(sel[0], sel[1], sel[2], indexing="ij")
+    ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
+    n = len(ix)
+    gid = (ix.astype(np.int64) * nx + iy) * nx + iz
+    x = np.stack([c1[ix], c1[iy], c1[iz]], axis=1)
+    if jitter:
+        for d in range(3):
+            u = ((gid * np.int64(2654435761) + np.int64(40503 * (d + 1))) % np.int64(1 << 20)).astype(np.float64) / float(1 << 20)
+            x[:, d] += (2.0 * u - 1.0) * jitter * dx
+        x %= 1.0
+        if brick is not None:      # a jittered atom may have left the brick by a hair: put it back (ownership stays a partition)
+            for d in range(3):
+                x[:, d] = np.clip(x[:, d], brick.sublo[d], np.nextafter(brick.subhi[d], -1.0))
+    typ = np.where((np.abs(x - 0.5) <= cube).all(1), 2, 1).astype(np.int32)
+    a = dict(x=np.ascontiguousarray(x), v=np.zeros((n, 3)), rho=np.ones(n), e=np.where(typ == 1, 1.0, 1.5), cv=np.where(typ == 1, 1.0, 2.0),
+             rmass=np.full(n, dx ** 3), type=typ, mask=np.ones(n, np.int32), tag=(gid + 1).astype(np.int32))
+    if c4:
+        a["rho"] = np.where(typ == 2, 0.1, 1.0); a["rmass"] = a["rho"] * dx ** 3
+        a["cv"] = np.where(typ == 2, 0.06, 0.04); a["e"] = np.where(typ == 2, 0.06 * 0.6, 0.04)
+        a["mask"] = np.where(typ == 2, 3, 1).astype(np.int32)
+    return a
+
+
+def run_mp_config(pkg, kind, nx, steps, warmup, rank, world, local, dist, torch, peak):
+    """one multiphase config: the tests' own deck generators (tests/cases.py: _droplet = examples/USER/sph/square_to_sphere,
+    _bubble = bubble_random with fix phase_change) at nx^3 particles on `world` bricks; device-timed K steps, max over ranks"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    c4 = kind == "C4"
+    case = cases._bubble("c4", 3, nx, steps) if c4 else cases._droplet("c3", 3, nx, steps)
+    deck = case.deck()
+    brick = nid = None
+    if world > 1:
+        brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, 3)
+        nid = pkg.parallel.nccl_id(pkg.load(), dist)
+    t0 = time.perf_counter()
+    atoms = lattice_brick(nx, brick, 0.12 if c4 else 0.2, 0.2 if c4 else 0.0, c4)
+    n = len(atoms["type"])
+    sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=nid)
+    sim.set_atoms(**atoms)
+    del atoms
+    sim.setup()
+    sim.run(max(warmup, 3))
+    sim.sync()
+    t_setup = time.perf_counter() - t0
+    sim.set_timing(True)
+    c0 = sim.counters()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sim.run(steps)
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    nl, ng = sim.natoms()
+    f = sim.get_atoms(("f",))["f"]
+    red = torch.tensor([n, nl, ng] + list(f.sum(0)) + list(np.abs(f).sum(0)), dtype=torch.float64, device="cuda")
+    mx = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(red); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    red = red.cpu().numpy(); ms = float(mx.item())
+    c1 = sim.counters(); timers = sim.timers()
+    sim.close()
+    ntot = int(red[0])
+    rate = ntot * steps / (ms * 1e-3)
+    loop_ms = sum(timers.get(k, (0.0, 0))[0] for k in ("density", "colorgradient", "records", "force"))
+    bl, bs = (BYTES_C4_LOOP, BYTES_C4_STEP) if c4 else (BYTES_MP_LOOP, BYTES_MP_STEP)
+    out = {"workload": ("C4: evaporating two-phase box, 5 multiphase sub-styles incl. heatconduction/phasechange + fix phase_change" if c4 else
+                        "periodic two-phase box (square_to_sphere deck): rhosum/multiphase + colorgradient + taitwater/multiphase + surfacetension, rebuilt every step"),
+           "nx": nx, "particles_total": ntot, "particles_end": int(red[1]), "ghosts_total": int(red[2]), "n_gpus": world,
+           "grid": list(brick.grid) if brick is not None else [1, 1, 1], "steps": steps, "warmup": max(warmup, 3),
+           "ms_per_step": ms / steps, "particle_steps_s": rate, "stage_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]},
+           "neighbor_builds": c1["builds"] - c0["builds"], "gpu_launches": c1["launches"] - c0["launches"], "inserted": c1["inserted"],
+           "sum_f_over_sum_abs_f": float(np.abs(red[3:6]).max() / max(red[6:9].max(), 1e-300)),
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "bytes_per_particle_loop": bl, "bytes_per_particle_step": bs,
+                        "step_GBs": bs * rate / 1e9, "step_frac": bs * rate / 1e9 / (peak * world),
+                        "loop_GBs": (bl * ntot * steps / (loop_ms * 1e-3) / 1e9) if loop_ms else None,
+                        "loop_frac": (bl * ntot * steps / (loop_ms * 1e-3) / 1e9 / (peak * world)) if loop_ms else None,
+                        "note": "loop = density + colorgradient + records + force stage timers of rank 0 (per-rank work, whole-job bytes)"},
+           "setup_seconds": round(t_setup, 2)}
+    return out
+
+
+def run_parity(dist, rank, world, local):
+    """fixtures on the N ranks (tests/mgpu_lib.py); 2x2x2 bricks at N = 8"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mgpu_lib
+    prefer = {8: (2, 2, 2), 4: (2, 2, 1), 2: (2, 1, 1)}.get(world)
+    cases_out, ok, worst = [], True, 0.0
+    for name in PARITY_CASES:
+        r = mgpu_lib.check_case(name, dist, rank, world, local, prefer)
+        if rank == 0:
+            cases_out.append({k: r.get(k) for k in ("name", "grid", "against", "ok", "err", "err_elem")})
+            ok = ok and bool(r["ok"]); worst = max(worst, float(r.get("err", 0.0)))
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    return {"ok": bool(flag[0]), "max_err": worst, "grid": list(prefer) if prefer else None, "cases": cases_out,
+            "tolerance": "10x the case's trajectory tolerance (1e-8) vs fixtures, 100x (1e-7) vs the P-rank oracle; norm-wise max|a-b|/max|b|, element-wise figure alongside"}
+
 # ------------------------------------------------------------------------------- clocks ----
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -221,6 +349,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="edge scale of the C2 geometry (1.0 = 1M particles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5_strong sub-records")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (N > 1)")
+    ap.add_argument("--c3-nx", type=int, default=160)
+    ap.add_argument("--c4-nx", type=int, default=252)
+    ap.add_argument("--c5-nx", type=int, default=400)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = importlib.import_module("lammps-sph-multiphase_b200")
@@ -369,6 +502,50 @@ def main():
             "clocks": clk, "gpu_launches": c1["launches"] - c0["launches"], "neighbor_builds": c1["builds"] - c0["builds"],
             "stage_ms": {k: round(v[0], 3) for k, v in timers.items() if v[1]}, "e2e": e2e, "roofline": roof}
 
+    # ---- fp64-pipe fraction of the dominant kernel: fp64 thread-instructions of one launch (ncu, profiles/r02_force_fp64.json:
+    #      smsp__sass_thread_inst_executed_op_fp64_pred_on of the same kernel on the same workload) / launch time measured live
+    #      / (SMs x 64 fp64 lanes x SM clock under load) ----
+    if roof is not None:
+        fp = os.path.join(ROOT, "profiles", "r02_force_fp64.json")
+        sm_hz = 1e6 * float((clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        nsm = torch.cuda.get_device_properties(local).multi_processor_count
+        try:
+            rec = json.load(open(fp))
+            per_particle = float(rec["fp64_thread_inst_per_launch"]) / float(rec["particles"])
+            roof["fp64_frac"] = per_particle * n / (roof["avg_launch_ms"] * 1e-3) / (nsm * FP64_LANES_PER_SM * sm_hz)
+            roof["fp64_thread_inst_per_particle"] = per_particle
+            roof["fp64_source"] = "profiles/r02_force_fp64.json (ncu count) x live launch time; peak = %d SMs x 64 lanes x %.0f MHz" % (nsm, sm_hz / 1e6)
+        except Exception:
+            roof["fp64_frac"] = None
+
+    # ---- the other BASELINE configs as sub-records (device-timed the same way; C2 stays the headline) ----
+    configs = {}
+    if not args.no_configs:
+        plan = []
+        if world == 1:
+            plan.append(("C3", "C3", args.c3_nx, 20, 5))
+        if world in (2, 4):
+            plan.append(("C4", "C4", args.c4_nx, 10, 3))
+        plan.append(("C5_strong", "C5", args.c5_nx, 5, 3))
+        sim.close(); sim = None
+        torch.cuda.empty_cache()
+        for key, kind, nx, k, w in plan:
+            try:
+                configs[key] = run_mp_config(pkg, kind, nx, k, w, rank, world, local, dist, torch, peak)
+            except Exception as e:          # e.g. out of memory on a smaller device: report, keep the headline
+                configs[key] = {"error": str(e)[:300], "nx": nx}
+                if world > 1:
+                    raise
+    line["configs"] = configs
+
+    # ---- multi-GPU parity, driver-visible (N > 1): fixtures / P-rank oracle on the same ranks, after every timed region ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        if sim is not None:
+            sim.close(); sim = None
+        parity = run_parity(dist, rank, world, local)
+    line["parity"] = parity
+
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         # bounded CPU sample: same deck at 0.5 edge scale, 1 replica (1 core), ~10-30 s
         a2, p2 = dam_break_3d(0.5 * args.scale)
@@ -381,9 +558,12 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     if rank == 0:
         print(json.dumps(line))
-    sim.close()
+    if sim is not None:
+        sim.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,6 @@
 #include "b200_neigh.cuh"
 
 #define NB_BORDER 20    // x3 v3 vest3 rho cg3 rmass e cv tag type mask image
-#define NB_FORWARD 15   // x3 v3 vest3 rho cg3 rmass e
 #define NB_REVERSE 5    // f3 drho de
 #define NB_EXCHANGE 26  // every per-atom field
 
@@ -68,17 +67,46 @@ __global__ void k_unpack_border(Geom g, int n, int first, CommArrays a, const do
   a.e[i] = b[14]; a.cv[i] = b[15];
   a.tag[i] = (int)b[16]; a.mask[i] = (int)b[18]; a.gimage[i] = (int)b[19];
 }
-// pack_comm[_vel] (atom_vec_meso_multiphase.cpp:319-465): cv, type, tag, mask are NOT resent
-__global__ void k_pack_forward(int n, const int *list, CommArrays a, int dim, double shift, double *buf)
+// borders without a host round trip per swap: one thread per atom of [0, nlast); a flagged atom k = pos[i] < cap is packed into
+// record k and entered in the send list; buf[0] (the message header) carries the true count pos[nlast], so the receiver -- who
+// posted a receive of the same cap, derived from the count of the previous build on both sides -- learns how many records are
+// valid, and both sides learn about an overflow (count > cap) from the same number.
+__global__ void k_pack_border_compact(int nlast, const int *flag, const int *pos, int cap, int *list, CommArrays a, int dim, double shift,
+                                      int imgstep, double *buf)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) buf[0] = (double)pos[nlast];
+  if (i >= nlast || !flag[i]) return;
+  int k = pos[i];
+  if (k >= cap) return;
+  list[k] = i;
+  double4 x = a.xt[i], vr = a.vr[i], v = a.vm[i], c = a.cgm[i];
+  double *b = buf + 1 + (size_t)k * NB_BORDER;
+  b[0] = dim == 0 ? shifted(x.x, shift) : x.x; b[1] = dim == 1 ? shifted(x.y, shift) : x.y; b[2] = dim == 2 ? shifted(x.z, shift) : x.z;
+  b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
+  b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[i]; b[15] = a.cv[i];
+  b[16] = (double)a.tag[i]; b[17] = (double)tw_type(__double_as_longlong(x.w)); b[18] = (double)a.mask[i];
+  b[19] = (double)(a.gimage[i] + imgstep);
+}
+// pack_comm[_vel] (atom_vec_meso.cpp:139-245, atom_vec_meso_multiphase.cpp:319-465): cv, type, tag, mask are NOT resent.
+// Message layout (doubles per ghost): x3 vest3 rho e | v3 if comm_modify vel yes | cg3 rmass if atom_style meso/multiphase
+// -> 8 for the plain single-phase deck (the reference's own pack_comm size), 15 for the multiphase decks.
+__host__ __device__ __forceinline__ int fwd_width(int multiphase, int ghost_velocity) { return 8 + (ghost_velocity ? 3 : 0) + (multiphase ? 4 : 0); }
+__global__ void k_pack_forward(int n, const int *list, CommArrays a, int dim, double shift, double *buf, int multiphase, int ghost_velocity)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   int j = list[k];
-  double4 x = a.xt[j], vr = a.vr[j], v = a.vm[j], c = a.cgm[j];
-  double *b = buf + (size_t)k * NB_FORWARD;
+  double4 x = a.xt[j], vr = a.vr[j];
+  double *b = buf + (size_t)k * fwd_width(multiphase, ghost_velocity);
   b[0] = dim == 0 ? shifted(x.x, shift) : x.x; b[1] = dim == 1 ? shifted(x.y, shift) : x.y; b[2] = dim == 2 ? shifted(x.z, shift) : x.z;
-  b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
-  b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[j];
+  b[3] = vr.x; b[4] = vr.y; b[5] = vr.z; b[6] = vr.w; b[7] = a.e[j];
+  int o = 8;
+  if (ghost_velocity | multiphase) {
+    double4 v = a.vm[j];
+    if (ghost_velocity) { b[o] = v.x; b[o + 1] = v.y; b[o + 2] = v.z; o += 3; }
+    if (multiphase) { double4 c = a.cgm[j]; b[o] = c.x; b[o + 1] = c.y; b[o + 2] = c.z; b[o + 3] = v.w; }
+  }
 }
 // xhold / dmaxsq (track): the ghosts' displacement since the build enters the same bound as the owned atoms' (k_initial_integrate),
 // so the far / mid zone flags need no all-reduce: every candidate of this rank's rows is an owned atom or one of its ghosts
@@ -88,8 +116,8 @@ __global__ void k_unpack_forward(int n, int first, CommArrays a, const double *b
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   int i = first + k;
-  const double *b = buf + (size_t)k * NB_FORWARD;
-  double4 x = a.xt[i], v = a.vm[i];
+  const double *b = buf + (size_t)k * fwd_width(multiphase, ghost_velocity);
+  double4 x = a.xt[i];
   x.x = b[0]; x.y = b[1]; x.z = b[2];
   a.xt[i] = x;
   if (xhold) {
@@ -99,11 +127,15 @@ __global__ void k_unpack_forward(int n, int first, CommArrays a, const double *b
     if (bits > *(volatile unsigned long long *)dmaxsq) atomicMax(dmaxsq, bits);
     if (celld) cell_disp_max(celld, gcell[i - nlocal], dsq);
   }
-  a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
-  if (ghost_velocity) { v.x = b[3]; v.y = b[4]; v.z = b[5]; }
-  if (multiphase) { v.w = b[13]; a.cgm[i] = make_double4(b[10], b[11], b[12], b[13]); }
-  a.vm[i] = v;
-  a.e[i] = b[14];
+  a.vr[i] = make_double4(b[3], b[4], b[5], b[6]);
+  a.e[i] = b[7];
+  int o = 8;
+  if (ghost_velocity | multiphase) {
+    double4 v = a.vm[i];
+    if (ghost_velocity) { v.x = b[o]; v.y = b[o + 1]; v.z = b[o + 2]; o += 3; }
+    if (multiphase) { v.w = b[o + 3]; a.cgm[i] = make_double4(b[o], b[o + 1], b[o + 2], b[o + 3]); }
+    a.vm[i] = v;
+  }
 }
 // pack_reverse / unpack_reverse (atom_vec_meso_multiphase.cpp:520-551): ghosts' f, drho, de added to the atoms that were sent
 __global__ void k_pack_reverse(int n, int first, CommArrays a, double *buf)

@@ -232,12 +232,17 @@ struct PackArrays {
   double *e, *de, *cv;
   int *tag, *mask, *orig;
 };
+// bad[0]: a type is out of range; bad[1]: largest tag (warp maximum first, one atomic per warp)
 __global__ void k_pack_atoms(int n, HostMirror m, PackArrays a, int multiphase, const double *mass, int ntypes, int *bad)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tg = (i < n) ? (m.tag ? m.tag[i] : i + 1) : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) tg = max(tg, __shfl_xor_sync(FULLMASK, tg, o));
+  if ((threadIdx.x & 31) == 0 && tg > *(volatile int *)(bad + 1)) atomicMax(bad + 1, tg);
   if (i >= n) return;
   int t = m.type[i];
-  if (t < 1 || t > ntypes) { *bad = 1; t = 1; }
+  if (t < 1 || t > ntypes) { bad[0] = 1; t = 1; }
   double ms = (multiphase && m.rmass) ? m.rmass[i] : mass[t];
   const double *v = m.v ? m.v + 3 * i : nullptr, *ve = m.vest ? m.vest + 3 * i : v;
   a.xt[i] = make_double4(m.x[3 * i], m.x[3 * i + 1], m.x[3 * i + 2], __longlong_as_double((long long)pack_tw(t, 0, 0, 0)));

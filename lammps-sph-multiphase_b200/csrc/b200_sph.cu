@@ -88,6 +88,7 @@ struct Swap {
   int imgstep;
   DevBuf<int> sendlist;
   int nsend = 0, nrecv = 0, firstrecv = 0;
+  int last_nsend = -1, last_nrecv = -1;   // counts of the previous borders() (the caps of the next one), -1 = none
 };
 
 struct Pass { int type; int kinds; int nslots; int slots[4]; };
@@ -118,7 +119,7 @@ struct b200_sph {
   DevBuf<double4> rec;
   DevBuf<int> gimage;
   DevBuf<int> cellid, perm, perm2, gcell, gperm, gorder, flag, pos, alive;
-  DevBuf<double> sendbuf, recvbuf;
+  DevBuf<double> sendbuf, recvbuf, xs[2], xr[2];      // xs / xr: exact-size border messages of a swap without (or beyond) its cap
   // domain decomposition (one engine instance per rank / GPU)
   int world = 1, rank = 0, procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0}, procneigh[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   ncclComm_t nccl = nullptr;
@@ -152,6 +153,7 @@ struct b200_sph {
   cudaStream_t st2 = 0; cudaEvent_t ev_main = 0, ev_comm = 0;
   int *d_tflags = nullptr;                      // [0] ntiles [1] max slots [2] overflow [3] max rows [4] work counter; [8..11] the same for the ghost-row tiles
   bool setup_done = false, geom_ready = false;
+  bool f_clean = false;                         // f, drho, de are all zero (force_clear just ran): the first tile force pass stores instead of adding
   // instrumentation
   long long launches = 0, nbuilds = 0, nsteps = 0, maxneigh = 0, ndanger = 0, ninserted = 0;
   bool timing = false;
@@ -225,7 +227,7 @@ static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch)
 static bool zones_on(const b200_sph *h) { return h->zone_local && h->far_margin > 0.0 && h->rows_tiled && !h->multiphase && h->ntiles > 0; }
 
 // -------------------------------------------------------------- geometry ----
-static void setup_geometry(b200_sph *h)
+static void setup_geometry(b200_sph *h, bool keep_comm_history = false)
 {
   Geom &g = h->g;
   if (!h->have_domain || !h->have_neigh) throw std::string("b200_domain / b200_neighbor must be called before setup");
@@ -288,6 +290,7 @@ static void setup_geometry(b200_sph *h)
       }
       s.imgstep *= (d == 0 ? 1 : (d == 1 ? 3 : 9));
       s.nsend = s.nrecv = 0;
+      if (!keep_comm_history) s.last_nsend = s.last_nrecv = -1;      // a new domain / decomposition: the swaps' message caps start over (on every rank alike)
     }
   }
   h->geom_ready = true;
@@ -320,108 +323,192 @@ static void refit_box(b200_sph *h)
     g.sublo[d] = g.boxlo[d] + prd * (loc * 1.0 / pg);
     g.subhi[d] = loc < pg - 1 ? g.boxlo[d] + prd * ((loc + 1) * 1.0 / pg) : g.boxhi[d];
   }
-  setup_geometry(h);
+  setup_geometry(h, true);
 }
 
 // ------------------------------------------------------------------ comm ----
-// buf_send -> (NCCL send/recv | local) -> buf the receiver unpacks from
-static double *swap_transfer(b200_sph *h, Swap &s, size_t nsend_d, size_t nrecv_d)
-{
-  if (s.sendproc == h->rank && s.recvproc == h->rank) return h->sendbuf.p;      // "if swapping with self, simply copy" (comm_brick.cpp:800)
-  h->recvbuf.ensure(nrecv_d + 1);
-  NCK(g_nccl.GroupStart());
-  if (nsend_d) NCK(g_nccl.Send(h->sendbuf.p, nsend_d, ncclDouble, s.sendproc, h->nccl, h->st));
-  if (nrecv_d) NCK(g_nccl.Recv(h->recvbuf.p, nrecv_d, ncclDouble, s.recvproc, h->nccl, h->st));
-  NCK(g_nccl.GroupEnd());
-  return h->recvbuf.p;
-}
-static void swap_counts(b200_sph *h, Swap &s)       // the 1-int MPI_Sendrecv of borders() (:819)
-{
-  if (s.sendproc == h->rank && s.recvproc == h->rank) { s.nrecv = s.nsend; return; }
-  h->h_red[0] = (double)s.nsend;
-  CK(cudaMemcpyAsync(h->d_red, h->h_red, sizeof(double), cudaMemcpyHostToDevice, h->st));
-  NCK(g_nccl.GroupStart());
-  NCK(g_nccl.Send(h->d_red, 1, ncclDouble, s.sendproc, h->nccl, h->st));
-  NCK(g_nccl.Recv(h->d_red + 1, 1, ncclDouble, s.recvproc, h->nccl, h->st));
-  NCK(g_nccl.GroupEnd());
-  CK(cudaMemcpyAsync(h->h_red + 1, h->d_red + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
-  s.nrecv = (int)h->h_red[1];
-}
 static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch);
 static void ensure_scan_tmp(b200_sph *h, size_t n) { h->scan_tmp.ensure(n / (SCAN_T * SCAN_E) * 2 + 4096); }
+static bool swap_self(const b200_sph *h, const Swap &s) { return s.sendproc == h->rank && s.recvproc == h->rank; }   // "if swapping with self, simply copy" (comm_brick.cpp:800)
 
-// CommBrick::borders, comm_brick.cpp:696-864
+// The two swaps of one dimension are independent of each other (both scan the atoms present before the dimension, comm_brick.cpp:722-725),
+// so they travel together: swaps [k0, k1) pack into consecutive regions of sendbuf, ONE grouped NCCL call moves both directions,
+// then both are unpacked.  nsend_d / nrecv_d: doubles per swap.  Returns the buffers the receivers unpack from (rbuf[k - k0]).
+static void dim_transfer(b200_sph *h, int k0, int k1, const size_t *nsend_d, const size_t *nrecv_d, const size_t *soff, const size_t *roff, double **rbuf, bool reverse)
+{
+  bool any = false;
+  for (int k = k0; k < k1; k++) {
+    Swap &s = h->swaps[k];
+    if (swap_self(h, s)) { rbuf[k - k0] = h->sendbuf.p + soff[k - k0]; continue; }
+    rbuf[k - k0] = h->recvbuf.p + roff[k - k0];
+    if (nsend_d[k - k0] || nrecv_d[k - k0]) any = true;
+  }
+  if (!any) return;
+  NCK(g_nccl.GroupStart());
+  for (int k = k0; k < k1; k++) {
+    Swap &s = h->swaps[k];
+    if (swap_self(h, s)) continue;
+    // forward: my slab goes to sendproc, ghosts come from recvproc; reverse: the ghosts' sums go back to recvproc
+    if (nsend_d[k - k0]) NCK(g_nccl.Send(h->sendbuf.p + soff[k - k0], nsend_d[k - k0], ncclDouble, reverse ? s.recvproc : s.sendproc, h->nccl, h->st));
+    if (nrecv_d[k - k0]) NCK(g_nccl.Recv(h->recvbuf.p + roff[k - k0], nrecv_d[k - k0], ncclDouble, reverse ? s.sendproc : s.recvproc, h->nccl, h->st));
+  }
+  NCK(g_nccl.GroupEnd());
+}
+static int dim_end(const b200_sph *h, int k0) { int k = k0; while (k < h->nswap && h->swaps[k].dim == h->swaps[k0].dim) k++; return k; }
+
+// CommBrick::borders, comm_brick.cpp:696-864.  One host synchronisation per DIMENSION: the counts travel in the message headers
+// (k_pack_border_compact) and the messages are sized by a cap both sides derive from the previous build's count of the same swap;
+// a swap without history (first build) or whose count outgrew the cap takes the exact two-step exchange (count, then data).
 static void comm_borders(b200_sph *h)
 {
   const int B = 256;
   Geom &g = h->g;
   h->nghost = 0;
-  int k = 0;
-  while (k < h->nswap) {
-    int dim = h->swaps[k].dim;
-    int nlast = h->nlocal + h->nghost;                 // both swaps of a dimension scan the atoms present before it (:722-725)
-    for (; k < h->nswap && h->swaps[k].dim == dim; k++) {
-      Swap &s = h->swaps[k];
-      s.nsend = 0;
-      if (s.do_send && nlast) {
-        h->flag.ensure(nlast + 2); h->pos.ensure(nlast + 2); ensure_scan_tmp(h, nlast + 2);
-        LAUNCH(h, k_slab_flag, nblk(nlast, B), B, nlast, h->C().xt.p, dim, s.slablo, s.slabhi, h->flag.p, h->pos.p);
-        scan_exclusive(h, h->pos.p, nlast, h->scan_tmp.p);
-        CK(cudaMemcpyAsync(h->h_flags + 4, h->pos.p + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        CK(cudaStreamSynchronize(h->st));
-        s.nsend = h->h_flags[4];
-        s.sendlist.ensure(s.nsend + 1);
-        if (s.nsend) LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, h->flag.p, h->pos.p, s.sendlist.p);
+  for (int k0 = 0; k0 < h->nswap; k0 = dim_end(h, k0)) {
+    const int k1 = dim_end(h, k0), dim = h->swaps[k0].dim, ns = k1 - k0;
+    const int nlast = h->nlocal + h->nghost;                 // both swaps of a dimension scan the atoms present before it (:722-725)
+    int *flag[2], *pos[2]; int capS[2], capR[2]; size_t soff[2], roff[2], nsd[2], nrd[2]; double *rbuf[2];
+    h->flag.ensure((size_t)2 * (nlast + 2)); h->pos.ensure((size_t)2 * (nlast + 2)); ensure_scan_tmp(h, nlast + 2);
+    size_t so = 0, ro = 0;
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      flag[q] = h->flag.p + (size_t)q * (nlast + 2); pos[q] = h->pos.p + (size_t)q * (nlast + 2);
+      // cap from the last count of this swap: the sender's last nsend IS the receiver's last nrecv, so both sides size alike
+      capS[q] = (s.do_send && s.last_nsend >= 0) ? s.last_nsend + s.last_nsend / 4 + 64 : -1;
+      capR[q] = (s.do_recv && s.last_nrecv >= 0) ? s.last_nrecv + s.last_nrecv / 4 + 64 : -1;
+      if (swap_self(h, s)) capR[q] = capS[q];
+      soff[q] = so; roff[q] = ro;
+      so += (size_t)std::max(capS[q], 0) * NB_BORDER + 1; ro += (size_t)std::max(capR[q], 0) * NB_BORDER + 1;
+      s.nsend = s.nrecv = 0;
+    }
+    h->sendbuf.ensure(so + 1); h->recvbuf.ensure(ro + 1);
+    // senders: flag + scan (+ compacting pack where a cap exists)
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      if (!s.do_send) continue;
+      if (nlast) {
+        LAUNCH(h, k_slab_flag, nblk(nlast, B), B, nlast, h->C().xt.p, dim, s.slablo, s.slabhi, flag[q], pos[q]);
+        scan_exclusive(h, pos[q], nlast, h->scan_tmp.p);
+      } else CK(cudaMemsetAsync(pos[q], 0, sizeof(int), h->st));
+      if (capS[q] >= 0) {
+        s.sendlist.ensure(capS[q] + 1);
+        LAUNCH(h, k_pack_border_compact, nblk(std::max(nlast, 1), B), B, nlast, flag[q], pos[q], capS[q], s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep,
+               h->sendbuf.p + soff[q]);
       }
-      h->sendbuf.ensure((size_t)s.nsend * NB_BORDER + 1);
-      if (s.nsend) LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, h->sendbuf.p);
-      swap_counts(h, s);
+      CK(cudaMemcpyAsync(h->h_flags + 28 + q, pos[q] + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    }
+    // fast path: header + cap records in one grouped call for the swaps that have history on both ends
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      nsd[q] = (s.do_send && capS[q] >= 0) ? (size_t)capS[q] * NB_BORDER + 1 : 0;
+      nrd[q] = (s.do_recv && capR[q] >= 0 && !swap_self(h, s)) ? (size_t)capR[q] * NB_BORDER + 1 : 0;
+    }
+    dim_transfer(h, k0, k1, nsd, nrd, soff, roff, rbuf, false);
+    for (int q = 0; q < ns; q++)
+      if (h->swaps[k0 + q].do_recv && capR[q] >= 0) CK(cudaMemcpyAsync(h->h_red + 14 + q, rbuf[q], sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));                       // the one synchronisation of this dimension
+    bool redo[2] = {false, false};
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      s.nsend = s.do_send ? h->h_flags[28 + q] : 0;
+      if (s.do_send && (capS[q] < 0 || s.nsend > capS[q])) redo[q] = true;
+      if (s.do_recv && capR[q] >= 0) { s.nrecv = (int)h->h_red[14 + q]; if (s.nrecv > capR[q]) redo[q] = true; }
+      else if (s.do_recv) redo[q] = true;
+      if (swap_self(h, s)) s.nrecv = s.nsend;
+    }
+    // exact path for the swaps that need it.  Pairwise consistent: the sender of a swap and its receiver hold the same cap (same
+    // history) and see the same count (header), so "send exact" on one end <=> "receive exact" on the other; every rank walks
+    // q = 0, 1 in the same order and posts a swap's operations in one group.
+    for (int q = 0; q < ns; q++) {
+      if (!redo[q]) continue;
+      Swap &s = h->swaps[k0 + q];
+      const bool self = swap_self(h, s);
+      const bool send_exact = s.do_send && (capS[q] < 0 || s.nsend > capS[q]);
+      if (send_exact) {
+        s.sendlist.ensure(s.nsend + 1);
+        h->xs[q].ensure((size_t)s.nsend * NB_BORDER + 2);
+        if (s.nsend) {
+          LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, flag[q], pos[q], s.sendlist.p);
+          LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, h->xs[q].p + 1);
+        }
+      }
+      if (self) { s.nrecv = s.nsend; if (send_exact) rbuf[q] = h->xs[q].p; continue; }
+      const bool count_send = s.do_send && capS[q] < 0, count_recv = s.do_recv && capR[q] < 0;
+      if (count_send || count_recv) {      // no history: the 1-int MPI_Sendrecv of borders() (:819)
+        h->h_red[q] = (double)s.nsend;                        // staging slots per swap: the async copy of q = 0 may still be pending at q = 1
+        CK(cudaMemcpyAsync(h->d_red + q, h->h_red + q, sizeof(double), cudaMemcpyHostToDevice, h->st));
+        NCK(g_nccl.GroupStart());
+        if (count_send) NCK(g_nccl.Send(h->d_red + q, 1, ncclDouble, s.sendproc, h->nccl, h->st));
+        if (count_recv) NCK(g_nccl.Recv(h->d_red + 2 + q, 1, ncclDouble, s.recvproc, h->nccl, h->st));
+        NCK(g_nccl.GroupEnd());
+        if (count_recv) {
+          CK(cudaMemcpyAsync(h->h_red + 2 + q, h->d_red + 2 + q, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+          CK(cudaStreamSynchronize(h->st));
+          s.nrecv = (int)h->h_red[2 + q];
+        }
+      }
+      const bool recv_exact = s.do_recv && (capR[q] < 0 || s.nrecv > capR[q]);
+      if (recv_exact) { h->xr[q].ensure((size_t)s.nrecv * NB_BORDER + 2); rbuf[q] = h->xr[q].p; }
+      NCK(g_nccl.GroupStart());
+      if (send_exact && s.nsend) NCK(g_nccl.Send(h->xs[q].p + 1, (size_t)s.nsend * NB_BORDER, ncclDouble, s.sendproc, h->nccl, h->st));
+      if (recv_exact && s.nrecv) NCK(g_nccl.Recv(h->xr[q].p + 1, (size_t)s.nrecv * NB_BORDER, ncclDouble, s.recvproc, h->nccl, h->st));
+      NCK(g_nccl.GroupEnd());
+    }
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
       if (!s.do_recv) s.nrecv = 0;
       s.firstrecv = h->nlocal + h->nghost;
       h->ensure_cap((size_t)s.firstrecv + s.nrecv, true);
-      double *buf = swap_transfer(h, s, (size_t)s.nsend * NB_BORDER, (size_t)s.nrecv * NB_BORDER);
-      if (s.nrecv) LAUNCH(h, k_unpack_border, nblk(s.nrecv, B), B, g, s.nrecv, s.firstrecv, h->comm_arrays(), buf);
+      if (s.nrecv) LAUNCH(h, k_unpack_border, nblk(s.nrecv, B), B, g, s.nrecv, s.firstrecv, h->comm_arrays(), rbuf[q] + 1);
       h->nghost += s.nrecv;
+      s.last_nsend = s.do_send ? s.nsend : -1; s.last_nrecv = s.do_recv ? s.nrecv : -1;
     }
   }
 }
-// generic staged swap loop: forward direction
+// generic staged swap loop, one grouped transfer per dimension: forward direction
 template <class Pack, class Unpack> static void comm_forward_generic(b200_sph *h, int width, Pack pack, Unpack unpack)
 {
-  for (int k = 0; k < h->nswap; k++) {
-    Swap &s = h->swaps[k];
-    h->sendbuf.ensure((size_t)s.nsend * width + 1);
-    if (s.nsend) pack(s);
-    double *buf = swap_transfer(h, s, (size_t)s.nsend * width, (size_t)s.nrecv * width);
-    if (s.nrecv) unpack(s, buf);
+  for (int k0 = 0; k0 < h->nswap; k0 = dim_end(h, k0)) {
+    const int k1 = dim_end(h, k0), ns = k1 - k0;
+    size_t soff[2], roff[2], nsd[2], nrd[2]; double *rbuf[2];
+    size_t so = 0, ro = 0;
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      nsd[q] = (size_t)s.nsend * width; nrd[q] = swap_self(h, s) ? 0 : (size_t)s.nrecv * width;
+      soff[q] = so; roff[q] = ro; so += nsd[q]; ro += nrd[q];
+    }
+    h->sendbuf.ensure(so + 1); h->recvbuf.ensure(ro + 1);
+    for (int q = 0; q < ns; q++) if (h->swaps[k0 + q].nsend) pack(h->swaps[k0 + q], h->sendbuf.p + soff[q]);
+    dim_transfer(h, k0, k1, nsd, nrd, soff, roff, rbuf, false);
+    for (int q = 0; q < ns; q++) if (h->swaps[k0 + q].nrecv) unpack(h->swaps[k0 + q], rbuf[q]);
   }
 }
-// reverse direction: ghosts' values go back to the atoms they were copied from (comm_brick.cpp:513-560)
+// reverse direction: ghosts' values go back to the atoms they were copied from (comm_brick.cpp:513-560); dimensions and, inside a
+// dimension, the unpacks run in the reference's reverse swap order (an atom in both send lists receives its two additions in that order)
 template <class Pack, class Unpack> static void comm_reverse_generic(b200_sph *h, int width, Pack pack, Unpack unpack)
 {
-  for (int k = h->nswap - 1; k >= 0; k--) {
-    Swap &s = h->swaps[k];
-    h->sendbuf.ensure((size_t)s.nrecv * width + 1);
-    if (s.nrecv) pack(s);
-    double *buf;
-    if (s.sendproc == h->rank && s.recvproc == h->rank) buf = h->sendbuf.p;
-    else {
-      h->recvbuf.ensure((size_t)s.nsend * width + 1);
-      NCK(g_nccl.GroupStart());
-      if (s.nrecv) NCK(g_nccl.Send(h->sendbuf.p, (size_t)s.nrecv * width, ncclDouble, s.recvproc, h->nccl, h->st));
-      if (s.nsend) NCK(g_nccl.Recv(h->recvbuf.p, (size_t)s.nsend * width, ncclDouble, s.sendproc, h->nccl, h->st));
-      NCK(g_nccl.GroupEnd());
-      buf = h->recvbuf.p;
+  std::vector<int> starts;
+  for (int k0 = 0; k0 < h->nswap; k0 = dim_end(h, k0)) starts.push_back(k0);
+  for (int d = (int)starts.size() - 1; d >= 0; d--) {
+    const int k0 = starts[d], k1 = dim_end(h, k0), ns = k1 - k0;
+    size_t soff[2], roff[2], nsd[2], nrd[2]; double *rbuf[2];
+    size_t so = 0, ro = 0;
+    for (int q = 0; q < ns; q++) {
+      Swap &s = h->swaps[k0 + q];
+      nsd[q] = (size_t)s.nrecv * width; nrd[q] = swap_self(h, s) ? 0 : (size_t)s.nsend * width;
+      soff[q] = so; roff[q] = ro; so += nsd[q]; ro += nrd[q];
     }
-    if (s.nsend) unpack(s, buf);
+    h->sendbuf.ensure(so + 1); h->recvbuf.ensure(ro + 1);
+    for (int q = ns - 1; q >= 0; q--) if (h->swaps[k0 + q].nrecv) pack(h->swaps[k0 + q], h->sendbuf.p + soff[q]);
+    dim_transfer(h, k0, k1, nsd, nrd, soff, roff, rbuf, true);
+    for (int q = ns - 1; q >= 0; q--) if (h->swaps[k0 + q].nsend) unpack(h->swaps[k0 + q], rbuf[q]);
   }
 }
 static void comm_reverse_scalar_add(b200_sph *h, double *arr)      // comm->reverse_comm_fix (dmass)
 {
   const int B = 256;
   comm_reverse_generic(h, 1,
-    [&](Swap &s) { LAUNCH(h, k_pack_scalar, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, arr, h->sendbuf.p); },
+    [&](Swap &s, double *dst) { LAUNCH(h, k_pack_scalar, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, arr, dst); },
     [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_scalar_add, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, arr, buf); });
 }
 // CommBrick::exchange, comm_brick.cpp:573-684: returns the number of slots now in use (dead ones included)
@@ -568,8 +655,8 @@ static bool tile_rows(b200_sph *h)
       if (set) { B.tiles = h->gtiles.p; B.ntiles = h->ngtiles; }
       int nt = set ? h->ngtiles : h->ntiles;
       const bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
-#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
-                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm, B, nt); } while (0)
+#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm + 4 * TILE_BUILD_MASK_BYTES, B, nt); \
+                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm + 8 * TILE_BUILD_MASK_BYTES, B, nt); } while (0)
       if (mp) { if (B.uni) BUILD_LAUNCH(true, true); else BUILD_LAUNCH(false, true); }
       else { if (B.uni) BUILD_LAUNCH(true, false); else BUILD_LAUNCH(false, false); }
 #undef BUILD_LAUNCH
@@ -964,6 +1051,7 @@ static void run_pass_tile_mp(b200_sph *h, const Pass &p)
   A.rec = h->trec.p;
   h->tend();
   h->tbegin(T_FORCE);
+  A.accum = h->f_clean ? 0 : 1; h->f_clean = false;
   switch (p.kinds) {
   case K_TAITMP: launch_tile_force_mp<K_TAITMP>(h, A, gu); break;
   case K_SURF: launch_tile_force_mp<K_SURF>(h, A, gu); break;
@@ -1013,7 +1101,7 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
     if (h->nghost || h->world > 1) {      // comm->forward_comm_pair (:203): the ghosts' new rho (decided from global state: peers may wait for this rank)
       auto rho_halo = [&]() {
         comm_forward_generic(h, 1,
-          [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
+          [&](Swap &s, double *dst) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, dst); },
           [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
       };
       if (overlap_ok(h)) halo_async(h, rho_halo); else rho_halo();
@@ -1035,6 +1123,7 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
   if (heat) { uni = tile_uni(h, *hheat, A.uni[nk]) && uni; A.tab[nk++] = heat; }
   if (fluid && heat && (A.uni[0].mass != A.uni[1].mass)) uni = false;
   h->tbegin(T_FORCE);
+  A.accum = h->f_clean ? 0 : 1; h->f_clean = false;
   tile_pass(h, A,
     [&](TileArgs &a, int reserve) {
       switch (p.kinds) {
@@ -1070,7 +1159,7 @@ static void run_pass(b200_sph *h, const Pass &p)
       if (active) LAUNCH(h, k_rhosum<false>, grid, PAIR_THREADS, A);
       if (h->nghost || h->world > 1)       // comm->forward_comm_pair (:203)
         comm_forward_generic(h, 1,
-          [&](Swap &s) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, h->sendbuf.p); },
+          [&](Swap &s, double *dst) { LAUNCH(h, k_pack_rho, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->C().vr.p, dst); },
           [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_rho, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->C().vr.p, buf); });
       h->tend();
     } else if (p.type == 1) {
@@ -1101,6 +1190,7 @@ static void run_pass(b200_sph *h, const Pass &p)
   h->tend();
   A.nrec = nrec;
   h->tbegin(T_FORCE);
+  h->f_clean = false;
   switch (p.kinds) {
   case K_TAIT: launch_force<K_TAIT>(h, A); break;
   case K_MORRIS: launch_force<K_MORRIS>(h, A); break;
@@ -1131,6 +1221,7 @@ static void force_clear(b200_sph *h)
   if (!na) return;
   CK(cudaMemsetAsync(h->C().fd.p, 0, (size_t)na * sizeof(double4), h->st));
   CK(cudaMemsetAsync(h->C().de.p, 0, (size_t)na * sizeof(double), h->st));
+  h->f_clean = true;
 }
 // Pair::virial_fdotr_compute (pair.cpp:1403-1451) of the pair forces just computed, before the reverse halo
 static void pair_compute_all(b200_sph *h)
@@ -1151,10 +1242,11 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
 {
   const int B = 256;
   halo_wait(h);
+  h->f_clean = false;
   h->tbegin(T_FINAL);
   if (rev && (h->nghost || h->world > 1) && (!h->tile_on || h->multiphase))      // the single-phase tile path puts nothing on ghosts (b200_tile.cuh)
     comm_reverse_generic(h, NB_REVERSE,
-      [&](Swap &s) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), h->sendbuf.p); },
+      [&](Swap &s, double *dst) { LAUNCH(h, k_pack_reverse, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), dst); },
       [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
   if ((post || fin) && h->nlocal)
     LAUNCH(h, k_post_final, nblk(h->nlocal, B), B, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, post, fin,
@@ -1177,8 +1269,8 @@ static void forward_comm(b200_sph *h)
   if (!h->nghost && h->world == 1) return;
   const int B = 256;
   h->tbegin(T_COMM);
-  comm_forward_generic(h, NB_FORWARD,
-    [&](Swap &s) { LAUNCH(h, k_pack_forward, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), s.dim, s.shift, h->sendbuf.p); },
+  comm_forward_generic(h, fwd_width(h->multiphase, h->ghost_velocity),
+    [&](Swap &s, double *dst) { LAUNCH(h, k_pack_forward, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), s.dim, s.shift, dst, h->multiphase, h->ghost_velocity); },
     [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_forward, nblk(s.nrecv, B), B, s.nrecv, s.firstrecv, h->comm_arrays(), buf, h->multiphase, h->ghost_velocity,
                                        h->far_margin > 0.0 ? h->xhold.p : (const double *)nullptr, h->d_dmaxsq, h->gcell.p,
                                        zones_on(h) ? h->celld.p : (unsigned *)nullptr, h->nlocal); });
@@ -1444,7 +1536,7 @@ int b200_destroy(b200_sph *h)
   h->S[0].release(); h->S[1].release(); h->pc_flag.release(); h->pc_thr.release(); h->pc_dmass.release(); h->pc_dev.release(); h->pc_new.release(); for (PcFix &f : h->pcs) cudaFree(f.d_state); for (PcFix &f : h->pcs_old) cudaFree(f.d_state);
   h->rec.release(); h->far.release(); h->numfar.release(); h->d_prunesq.release(); h->d_farsq.release(); h->d_midsq.release(); cudaFree(h->d_dmaxsq); h->gimage.release();
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
-  h->sendbuf.release(); h->recvbuf.release(); for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
+  h->sendbuf.release(); h->recvbuf.release(); for (int q = 0; q < 2; q++) { h->xs[q].release(); h->xr[q].release(); } for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
   if (h->nccl) g_nccl.CommDestroy(h->nccl);
   cudaFree(h->d_red); cudaFreeHost(h->h_red); if (h->d_dt) cudaFree(h->d_dt);
   h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
@@ -1696,7 +1788,6 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
   h->ensure_cap(n, false);
   h->setup_done = false;
   h->maxtag = n; h->next_orig = n;
-  if (a->tag) for (int i = 0; i < n; i++) h->maxtag = std::max(h->maxtag, a->tag[i]);
   if (!n) return 0;
   size_t nd, ni;
   HostMirror m = stage_layout(h, n, a, &nd, &ni);
@@ -1708,11 +1799,12 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
   if (a->tag) CK(cudaMemcpyAsync(m.tag, a->tag, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
   h->d_mass.ensure(MAXT1);
   CK(cudaMemcpyAsync(h->d_mass.p, h->mass, sizeof h->mass, cudaMemcpyHostToDevice, h->st));
-  CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->d_flags + 2, 0, 2 * sizeof(int), h->st));       // [2] bad type, [3] largest tag (no host pass over the tags)
   LAUNCH(h, k_pack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase, h->d_mass.p, h->ntypes, h->d_flags + 2);
-  CK(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   if (h->h_flags[2]) throw std::string("b200_set_atoms: atom type out of range");
+  h->maxtag = std::max(h->maxtag, h->h_flags[3]);
   API_END
 }
 int b200_get_natoms(b200_sph *h, int *nlocal, int *nghost) { if (nlocal) *nlocal = h->nlocal; if (nghost) *nghost = h->nghost; return 0; }

@@ -40,6 +40,8 @@
 #define TILE_SLOT_MASK 0x1fffu
 #define TILE_MAXSLOTS 8190
 #define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
+#define TILE_NBLK 12             // k_tile_build: blocks of 32 candidates per super-chunk (2 mask words per block and lane in shared memory)
+#define TILE_BUILD_MASK_BYTES (2 * TILE_NBLK * 32 * 4)     // per warp
 // multiphase entries carry two more flags (their records are 64-128 B, so a tile never holds more than 2047 slots):
 //   [15:13] type of j | [12] the row particle is the reference's "i" of the pair (half-list owner, frozen at build time)
 //   | [11] j is a ghost | [10:0] slot
@@ -268,7 +270,7 @@ __device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int 
 // NT: 256 threads for big tiles (C2: 8 chunks of 32 rows per tile), 128 when the tiles are small (more CTAs per SM to overlap the
 // per-tile barriers); the (cell, chunk) work items of a tile are handed to the warps through a shared counter.
 template <bool UNI, bool MP, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __grid_constant__ TileBuildArgs A)
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
   constexpr int TILE_BUILD_NT = NT;
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
   float *fx = (float *)tile_smem, *fy = fx + cap4, *fz = fy + cap4;
   int *so = (int *)(fz + cap4);                                // MP: LAMMPS local index of the owned candidates
   unsigned char *ty = (unsigned char *)(MP ? (void *)(so + cap4) : (void *)so);
+  unsigned *const msk = (unsigned *)(ty + cap4) + (threadIdx.x >> 5) * (2 * TILE_NBLK * 32) + (threadIdx.x & 31);     // this lane's column of its warp's mask store
   __shared__ TileDesc D;
   __shared__ int s_tile, s_item;
   __shared__ unsigned s_emax;
@@ -384,71 +387,83 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
             } else if (oi < so[slot]) ent |= TMP_OWNER;
             return true;
           };
-          for (int bj = s0 & ~3; bj < s1; bj += 32) {
-            // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
-            // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
-            // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
-            unsigned in = 0, mb = 0, fr = 0, md = 0; int nq = 0;
+          // A super-chunk = up to TILE_NBLK blocks of 32 candidates (a whole candidate range of the usual deck).  Phase A leaves the
+          // near / mid / far masks of every block (this lane's row; two words) in the warp's mask store; phase B then drains one zone at a time in a flattened loop --
+          // every iteration emits one entry for every lane that still has one, whichever block it sits in.  Draining block by
+          // block (round 1) made the warp wait for its fullest lane 1 600 / 32 times per row: lanes hold 5.5 +- 2.3 entries per
+          // block, but 42 +- 6 per super-chunk (profiles/r02_build_*: thread efficiency 21.5 -> see there).
+          for (int bj0 = s0 & ~3; bj0 < s1; bj0 += 32 * TILE_NBLK) {
+            const int nb = imin(TILE_NBLK, (s1 - bj0 + 31) >> 5);
+            for (int b = 0; b < nb; b++) {
+              const int bj = bj0 + 32 * b;
+              // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
+              // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
+              // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
+              unsigned in = 0, mb = 0, fr = 0, md = 0; int nq = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
-              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+              for (int k = 0; k < 8; k++) {
+                const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
+                const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-              for (int c = 0; c < 4; c++) {
-                const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
-                const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
-                mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
-                if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
+                for (int c = 0; c < 4; c++) {
+                  const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
+                  const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                  in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
+                  mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
+                  if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
+                }
+                nq = k + 1;
+                if (bj + 4 * k + 4 >= s1) break;
               }
-              nq = k + 1;
-              if (bj + 4 * k + 4 >= s1) break;
-            }
-            // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
-            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
-            // only the slots of [s0, s1), and never the row particle itself
-            unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
-            if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
-            if (myslot >= bj && myslot < bj + 32) vm &= ~(1u << (myslot - bj));
-            if (!valid) vm = 0;
-            in &= vm; mb &= vm;
-            unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
-            if (!UNI) in = 0;
-            while (border) {
-              const int idx = __ffs((int)border) - 1; border &= border - 1;
-              const int slot = bj + idx;
-              int cls = -1;
-              if (!UNI) {
-                const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
-                const float rsq = dx * dx + dy * dy + dz * dz;
-                const float *th = s_thr[ti * MAXT1 + ty[slot]];
-                if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
-                else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
+              // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
+              in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
+              // only the slots of [s0, s1), and never the row particle itself
+              unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
+              if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
+              if (myslot >= bj && myslot < bj + 32) vm &= ~(1u << (myslot - bj));
+              if (!valid) vm = 0;
+              in &= vm; mb &= vm;
+              unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
+              if (!UNI) in = 0;
+              while (border) {
+                const int idx = __ffs((int)border) - 1; border &= border - 1;
+                const int slot = bj + idx;
+                int cls = -1;
+                if (!UNI) {
+                  const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
+                  const float rsq = dx * dx + dy * dy + dz * dz;
+                  const float *th = s_thr[ti * MAXT1 + ty[slot]];
+                  if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
+                  else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
+                }
+                if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
+                if (cls) in |= 1u << idx;
+                if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
+                if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
               }
-              if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
-              if (cls) in |= 1u << idx;
-              if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
-              if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
+              // one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin
+              // two words per block: near = lo & ~hi, mid = hi & ~lo, far = lo & hi
+              msk[(0 * TILE_NBLK + b) * 32] = in & (fr | ~md);
+              msk[(1 * TILE_NBLK + b) * 32] = in & (fr | md);
             }
-            // phase B: entries straight from the masks (one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin)
-            unsigned nearm = in & ~fr & ~md, midm = in & ~fr & md, farm = in & fr;
-            while (nearm) {
-              const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
-              const int slot = bj + idx;
-              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
-              if (flags(slot, ent)) wn.push(ent, q, nrow16, stride);
-            }
-            while (midm) {
-              const int idx = __ffs((int)midm) - 1; midm &= midm - 1;
-              const int slot = bj + idx;
-              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
-              if (flags(slot, ent)) wm.push(ent, frow, A.ngrp);
-            }
-            while (farm) {
-              const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
-              const int slot = bj + idx;
-              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
-              if (flags(slot, ent)) wf.push(ent, frow, A.ngrp);
+            // phase B: entries straight from the masks, one zone after the other
+#pragma unroll
+            for (int z = 0; z < 3; z++) {
+              const unsigned *lo = msk, *hi = msk + TILE_NBLK * 32;
+              auto word = [&](int b) { const unsigned l = lo[b * 32], u = hi[b * 32]; return z == 0 ? (l & ~u) : (z == 1 ? (u & ~l) : (l & u)); };
+              int b = 0; unsigned m = word(0);
+              for (;;) {
+                while (m == 0 && b + 1 < nb) { b++; m = word(b); }
+                if (m == 0) break;
+                const int idx = __ffs((int)m) - 1; m &= m - 1;
+                const int slot = bj0 + 32 * b + idx;
+                unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+                if (flags(slot, ent)) {
+                  if (z == 0) wn.push(ent, q, nrow16, stride);
+                  else if (z == 1) wm.push(ent, frow, A.ngrp);
+                  else wf.push(ent, frow, A.ngrp);
+                }
+              }
             }
           }
         };
@@ -620,6 +635,7 @@ struct TileArgs {
   const double4 *vm; double4 *cg_out; const int *gorder; int dim;
   double *virow;                             // VIR kernels: per-row virial sums [row][6]
   const unsigned char *tzone;                // single-phase stage kernels: per-tile zone flags (bit 0 far, bit 1 mid), or NULL -> scan_far
+  int accum;                                 // force kernels: 0 = first force pass since force_clear (f, drho, de are zero: plain stores), 1 = add to what is there
 };
 
 // shared-memory map of the stage kernels: [NPARTS][cap] double2 | PairTab[NK] | TileDesc[2] | mbarrier | tile id[2]
@@ -672,14 +688,17 @@ template <int PM, int NK, int NT> struct TileLoop {
     __syncthreads();                                     // also: tables loaded, mbarrier initialised
     if (S.tile[0] < ntiles && threadIdx.x < 32) issue(S.D[0]);
   }
-  // the descriptor of the current tile once its records have landed, or nullptr when the tiles are used up
-  __device__ __forceinline__ const TileDesc *acquire()
+  // the descriptor of the current tile (visible since the last barrier), or nullptr when the tiles are used up.  Its records may
+  // still be in flight: the caller issues the global loads of its rows (counts, first entries) and only then calls wait(), so
+  // that their latency overlaps the bulk copies instead of following them (profiles/r02_force_*: long-scoreboard stalls)
+  __device__ __forceinline__ const TileDesc *peek()
   {
     if (S.tile[cur] >= ntiles) return nullptr;
     if ((threadIdx.x >> 5) == 1) fetch(cur ^ 1, threadIdx.x & 31);
-    mbar_wait(S.bar, phase); phase ^= 1;
     return S.D + cur;
   }
+  __device__ __forceinline__ void wait() { mbar_wait(S.bar, phase); phase ^= 1; }
+  __device__ __forceinline__ const TileDesc *acquire() { const TileDesc *d = peek(); if (d) wait(); return d; }
   __device__ __forceinline__ void release()
   {
     __syncthreads();                                     // everyone is done with this tile's records; the next descriptor is visible
@@ -749,7 +768,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
   const int ntiles = A.ntiles, g_far = A.scan_far[0], g_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
-  while (const TileDesc *Dp = L.acquire()) {
+  while (const TileDesc *Dp = L.peek()) {
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
@@ -757,20 +776,28 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
-      double2 a = make_double2(0, 0), b = a; int ti = 0;
-      if (valid) { a = P0[myslot]; b = P1[myslot]; ti = tw_type(__double_as_longlong(A.xt[row].w)); }
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      // global loads of the row first (type, counts, first group), the wait for the tile's records after them
+      int ti = 0, nn0 = 0, nf0 = 0; uint4 E0 = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
+        if (scan_far | scan_mid) nf0 = A.numfar[row];
+        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+      }
+      if (rb == 0) L.wait();
+      double2 a = make_double2(0, 0), b = a;
+      if (valid) { a = P0[myslot]; b = P1[myslot]; }
       if (valid && T.iskip[ti]) valid = false;                    // atoms of skipped types keep their integrated rho
       const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
-      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double acc = 0.0;
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
-        const int nf = (pass && valid) ? A.numfar[row] : 0;
-        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const int nf = valid ? nf0 : 0;
+        const int ng = pass == 0 ? (valid ? (nn0 + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
         const ptrdiff_t dir = pass == 1 ? -32 : 32;
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
-        uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
+        uint4 En = E0;
+        if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = En;
           if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
@@ -840,7 +867,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   const int ntiles = A.ntiles, g_far = A.scan_far[0], g_mid = A.scan_far[2];
   TileLoop<(1 << NPARTS) - 1, NK, NT> L(A, S, ntiles);
   L.start();
-  while (const TileDesc *Dp = L.acquire()) {
+  while (const TileDesc *Dp = L.peek()) {
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
@@ -848,17 +875,24 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
       const bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
-      double2 a = make_double2(0, 0), b = make_double2(0, 1), c = a, d = a; double ei = 0.0; int ti = 0;
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      // global loads of the row first (type, counts, first group), the wait for the tile's records after them
+      int ti = 0, nn0 = 0, nf0 = 0; uint4 E0 = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
+        if (scan_far | scan_mid) nf0 = A.numfar[row];
+        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+      }
+      if (rb == 0) L.wait();
+      double2 a = make_double2(0, 0), b = make_double2(0, 1), c = a, d = a; double ei = 0.0;
       if (valid) {
         a = P0[myslot]; b = P1[myslot];
         if (HAS_FLUID) { c = P2[myslot]; d = P3[myslot]; }
         if (HAS_HEAT) ei = PEp[myslot].x;
-        ti = tw_type(__double_as_longlong(A.xt[row].w));
       }
       const double rhoi = b.y, mi = S.T[0].mass[ti];
       const double ci = (KINDS & K_IDEAL) ? sqrt(fmax(d.y * rhoi, 0.0)) : 0.0;
       const unsigned maskf = (unsigned)(UF.mapmask >> (ti * 8)) & 0xffu, maskh = (unsigned)(UH.mapmask >> (ti * 8)) & 0xffu;
-      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, adrho = 0, ade = 0;
       double u_drho = 0, u_de = 0, u_deh = 0;                                 // uniform body: raw sums, scaled after the loop
       double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;                   // VIR: xx yy zz xy xz yz
@@ -867,12 +901,12 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       };
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
-        const int nf = (pass && valid) ? A.numfar[row] : 0;
-        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const int nf = valid ? nf0 : 0;
+        const int ng = pass == 0 ? (valid ? (nn0 + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
         const ptrdiff_t dir = pass == 1 ? -32 : 32;
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
-        uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
+        uint4 En = E0;
+        if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += SPLIT) {
           const uint4 E = En;
           if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
@@ -982,10 +1016,11 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         }
       }
       if (valid && sub == 0) {
-        double4 f = A.fd[row];
+        double4 f = make_double4(0, 0, 0, 0); double de0 = 0.0;
+        if (A.accum) { f = A.fd[row]; de0 = A.de[row]; }          // first force pass since force_clear: both are zero, no read-modify-write
         f.x += fx; f.y += fy; f.z += fz; f.w += adrho;
         A.fd[row] = f;
-        A.de[row] += ade;
+        A.de[row] = de0 + ade;
         if (VIR) {
           double *w = A.virow + (size_t)row * 6;
           w[0] += 0.5 * w0; w[1] += 0.5 * w1; w[2] += 0.5 * w2; w[3] += 0.5 * w3; w[4] += 0.5 * w4; w[5] += 0.5 * w5;
@@ -1074,7 +1109,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
   const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   TileLoop<0x3, 1, NT> L(A, S, ntiles);
   L.start();
-  while (const TileDesc *Dp = L.acquire()) {
+  while (const TileDesc *Dp = L.peek()) {
     const TileDesc &D = *Dp;
     const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
     const int sub = lane / lpw, rl = lane % lpw;
@@ -1082,20 +1117,28 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
       const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
-      double2 a = make_double2(0, 0), b = a; int ti = 0;
-      if (valid) { a = P0[myslot]; b = P1[myslot]; ti = tw_type(__double_as_longlong(A.xt[row].w)); }
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      // global loads of the row first (type, counts, first group), the wait for the tile's records after them
+      int ti = 0, nn0 = 0, nf0 = 0; uint4 E0 = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
+        if (scan_far | scan_mid) nf0 = A.numfar[row];
+        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+      }
+      if (rb == 0) L.wait();
+      double2 a = make_double2(0, 0), b = a;
+      if (valid) { a = P0[myslot]; b = P1[myslot]; }
       if (valid && T.iskip[ti]) valid = false;
       const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
-      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double acc = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
-        const int nf = (pass && valid) ? A.numfar[row] : 0;
-        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const int nf = valid ? nf0 : 0;
+        const int ng = pass == 0 ? (valid ? (nn0 + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
         const ptrdiff_t dir = pass == 1 ? -32 : 32;
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
-        uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
+        uint4 En = E0;
+        if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
           if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);
@@ -1177,7 +1220,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
   const size_t ps = A.pstride;
   TileLoop<MP::mask, NK, NT> L(A, S, ntiles);
   L.start();
-  while (const TileDesc *Dp = L.acquire()) {
+  while (const TileDesc *Dp = L.peek()) {
     const TileDesc &D = *Dp;
     const bool ghostrow = D.ghost != 0;
     const int lpw = D.nrows <= TILE_ROWS / 2 ? 8 : 16, split = 32 / lpw, rpp = (NT / 32) * lpw;
@@ -1194,20 +1237,27 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
       if (HAS_SURF) { g5 = A.rec[5 * ps + rr]; g6 = A.rec[6 * ps + rr]; }
       const int dev = ghostrow ? A.nlocal + A.gorder[rr - A.nlocal] : rr;     // device index
       const int ti = valid ? tw_type(__double_as_longlong(A.xt[dev].w)) : 0;
+      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
+      int nn0 = 0, nf0 = 0; uint4 E0 = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        nn0 = A.numneigh[row];
+        if (scan_far | scan_mid) nf0 = A.numfar[row];
+        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+      }
+      if (rb == 0) L.wait();                  // everything above came from global memory: its latency overlaps the tile's bulk copies
       const double rhoi = b.y;
       unsigned rmask[3] = {0, 0, 0};
 #pragma unroll
       for (int t = 0; t < NK; t++) rmask[t] = (unsigned)(A.uni[t].mapmask >> (ti * 8)) & 0xffu;
-      const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
       double fx = 0, fy = 0, fz = 0, ade = 0;
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
-        const int nf = (pass && valid) ? A.numfar[row] : 0;
-        const int ng = pass == 0 ? (valid ? (A.numneigh[row] + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
+        const int nf = valid ? nf0 : 0;
+        const int ng = pass == 0 ? (valid ? (nn0 + 7) >> 3 : 0) : (((pass == 1 ? nf >> 16 : nf & 0xffff) + 7) >> 3);
         const ptrdiff_t dir = pass == 1 ? -32 : 32;
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
-        uint4 En = make_uint4(0, 0, 0, 0);
-        if (sub < ng) En = ldg_nc_u4(lp + sub * dir);
+        uint4 En = E0;
+        if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
         for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
           if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);
@@ -1302,10 +1352,11 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
         if (WRITES_DE) ade += __shfl_xor_sync(FULLMASK, ade, o);
       }
       if (valid && sub == 0) {
-        double4 f = A.fd[dev];
+        double4 f = make_double4(0, 0, 0, 0); double de0 = 0.0;
+        if (A.accum) { f = A.fd[dev]; if (WRITES_DE) de0 = A.de[dev]; }      // first force pass since force_clear: both are zero, no read-modify-write
         f.x += fx; f.y += fy; f.z += fz;
         A.fd[dev] = f;
-        if (WRITES_DE) A.de[dev] += ade;
+        if (WRITES_DE) A.de[dev] = de0 + ade;
       }
     }
     L.release();

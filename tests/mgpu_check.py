@@ -1,11 +1,9 @@
-"""Multi-GPU correctness run (launched by torchrun, one rank per GPU):
-each parity case is decomposed into bricks, run through the C-ABI with NCCL halo exchange /
-migration, gathered by tag on rank 0 and compared with the reference fixture (tests/golden) of
-the SAME deck, i.e. with what the reference's CPU path produced on one rank.
+"""Multi-GPU correctness run (launched by torchrun, one rank per GPU); the comparison recipe is tests/mgpu_lib.py.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py [case ...]
+  ... tests/mgpu_check.py --grid 2x2x2 dam3d droplet3d          (force a processor grid where the box allows it)
+  ... tests/mgpu_check.py --empty-rank                           (one brick without atoms: the dry half of a dam break)
 """
-import importlib
 import os
 import sys
 
@@ -15,96 +13,79 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import cases     # noqa: E402
-import harness   # noqa: E402
-from util import relerr  # noqa: E402
+import mgpu_lib  # noqa: E402
 
-pkg = importlib.import_module("lammps-sph-multiphase_b200")
+DEFAULT = ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin",
+           "droplet3d_heat", "bubble3d", "shock3d_shrink"]
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
-    names = sys.argv[1:] or ["dam3d", "dam2d", "heat3d", "heat2d_rhosum", "droplet3d_static", "droplet2d_static", "droplet3d", "droplet2d_pcheat_skin", "droplet3d_heat", "bubble3d", "shock3d_shrink"]
-    api = pkg.load()
+    args = sys.argv[1:]
+    grid = None
+    if "--grid" in args:
+        k = args.index("--grid"); grid = tuple(int(v) for v in args[k + 1].split("x")); del args[k:k + 2]
     failed = 0
+    if "--empty-rank" in args:
+        args.remove("--empty-rank")
+        failed += empty_rank_case(rank, world, local)
+        names = args
+    else:
+        names = args or DEFAULT
     for name in names:
-        case = cases.CASES[name]
-        g = harness.load_golden(name)
-        deck = case.deck()
-        brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, deck.dimension)
-        nid = pkg.parallel.nccl_id(api, dist)
-        sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=nid)
-        # the reference sequence: run 0 from the initial state, then run N (tests/golden/make_golden.py)
-        st = harness.state_from(g, "init_", case.multiphase)
-        mine = brick.owns(st["x"])
-        sim.set_atoms(**{k: v[mine] for k, v in st.items()})
-        sim.setup()
-        sim.setup()
-        sim.run(case.nsteps)
-        out = sim.get_atoms()
-        nl, ng = sim.natoms()
-        c = sim.counters()
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (out, nl, ng, c["builds"]))
+        r = mgpu_lib.check_case(name, dist, rank, world, local, grid)
         if rank == 0:
-            tags = np.concatenate([o[0]["tag"] for o in gathered])
-            order = np.argsort(tags)
-            ref_order = np.argsort(g["sN_tag"])
-            # The multiphase styles read one-step-stale ghost rho / colorgradient, so a moving multiphase
-            # deck depends on WHERE the ghosts are, i.e. on the decomposition -- in the reference too.  Exact checks:
-            # single-phase decks and static multiphase decks against the 1-rank fixtures; moving multiphase decks against the CPU oracle
-            # emulating the same ranks (below);
-            # fix phase_change draws one RNG stream per rank (fix_phase_change.cpp:116), so only counts are sane-checked.
-            moving_mp = case.multiphase and "static" not in name
-            pc = "phase_change" in str(case.cmds)
-            tol = 3e-2 if moving_mp else 10 * case.tol_traj
-            if pc:
-                ok = abs(len(tags) - len(g["sN_tag"])) < 40 and len(np.unique(tags)) == len(tags)
-                print("%-24s grid %s atoms/rank %s (1 rank: %d)  builds %s  %s (per-rank RNG streams)" % (
-                    name, brick.grid, [o[1] for o in gathered], len(g["sN_tag"]), [o[3] for o in gathered], "OK" if ok else "FAIL"), flush=True)
-                failed += 0 if ok else 1
-                sim.close(); dist.barrier()
-                continue
-            ok = len(tags) == len(g["sN_tag"]) and np.array_equal(tags[order], g["sN_tag"][ref_order])
-            errs = {}
-            if ok:
-                fields = ["x", "v", "f", "rho", "e", "de", "drho"] + (["colorgradient", "rmass"] if case.multiphase else [])
-                for k in fields:
-                    a = np.concatenate([o[0][k] for o in gathered])[order]
-                    errs[k] = relerr(a, g["sN_" + k][ref_order])
-                ok = all(v <= tol for v in errs.values())
-            wline = None
-            if moving_mp and len(tags) == len(g["sN_tag"]):
-                # what the reference's algorithm gives on THIS brick grid: the CPU oracle emulating the same P ranks (tests/pworld.py,
-                # pinned against the 1-rank fixtures by tests/test_world_cpu.py).  This is the check that counts for these decks.
-                from pworld import OracleWorld
-                w = OracleWorld(case.deck(), world, brick.grid)
-                w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
-                w.setup(); w.setup(); w.run(case.nsteps)
-                want = w.get_atoms(); w.close()
-                wfields = ["x", "v", "f", "rho", "e", "de", "drho", "colorgradient", "rmass"]
-                werrs = {k: relerr(np.concatenate([o[0][k] for o in gathered])[order], want[k]) for k in wfields}
-                wok = np.array_equal(tags[order], want["tag"]) and all(v <= 100 * case.tol_traj for v in werrs.values())
-                wline = "%-24s grid %s vs the oracle emulating the same %d ranks: %s  %s" % (name, brick.grid, world, "OK" if wok else "FAIL", {k: "%.1e" % v for k, v in werrs.items()})
-                failed += 0 if wok else 1
-            verdict = "OK" if ok else ("INFO (1 rank vs %d ranks: decomposition-dependent by design, not counted)" % world if moving_mp else "FAIL")
-            print("%-24s grid %s atoms/rank %s ghosts %s builds %s  %s  %s" % (
-                name, brick.grid, [o[1] for o in gathered], [o[2] for o in gathered], [o[3] for o in gathered],
-                verdict, {k: "%.1e" % v for k, v in errs.items()}), flush=True)
-            if wline:
-                print(wline, flush=True)
-            failed += 0 if (ok or moving_mp) else 1
-        if rank != 0 and "phase_change" in str(case.cmds):
-            sim.close(); dist.barrier()
-            continue
-        sim.close()
-        dist.barrier()
+            print(mgpu_lib.format_result(r), flush=True)
+            failed += 0 if r["ok"] else 1
     flag = [failed]
     dist.broadcast_object_list(flag, src=0)
     dist.destroy_process_group()
     sys.exit(1 if flag[0] else 0)
+
+
+def empty_rank_case(rank, world, local):
+    """dam3d with the box stretched in x so that the last brick owns no atom at all: it still holds send lists / ghosts of its
+    neighbour and must keep taking part in every halo and collective (hang in ncclSend/ncclRecv).  Expected values:
+    the CPU oracle emulating the same ranks on the same stretched box."""
+    import cases
+    import harness
+    from pworld import OracleWorld
+    from util import relerr
+    pkg = mgpu_lib.pkg
+    case = cases.CASES["dam3d"]
+    g = harness.load_golden("dam3d")
+    (x0, y0, z0), (x1, y1, z1) = case.box
+    import copy
+    c2 = copy.copy(case)
+    c2.box = ((x0, y0, z0), (x0 + (x1 - x0) * 2.2 * world / 2, y1, z1))      # atoms fill less than the first half of the box
+    deck = c2.deck()
+    grid = (world, 1, 1)
+    brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, 3, grid)
+    st = harness.state_from(g, "init_", False)
+    mine = brick.owns(st["x"])
+    counts = [None] * world
+    dist.all_gather_object(counts, int(mine.sum()))
+    sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=pkg.parallel.nccl_id(pkg.load(), dist))
+    sim.set_atoms(**{k: np.ascontiguousarray(v[mine]) for k, v in st.items()})
+    sim.setup(); sim.run(case.nsteps)
+    out = sim.get_atoms(); sim.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    bad = 0
+    if rank == 0:
+        w = OracleWorld(c2.deck(), world, grid)
+        w.set_atoms(**st); w.setup(); w.run(case.nsteps)
+        want = w.get_atoms(); w.close()
+        tags = np.concatenate([o["tag"] for o in gathered]); order = np.argsort(tags)
+        errs = {k: relerr(np.concatenate([o[k] for o in gathered])[order], want[k]) for k in ("x", "v", "f", "rho", "e", "de", "drho")}
+        ok = min(counts) == 0 and np.array_equal(tags[order], want["tag"]) and max(errs.values()) <= 1e-8
+        print("%-24s grid %s atoms/rank %s (one brick empty) vs the oracle emulating the same ranks: %s  %s" % (
+            "dam3d_empty_rank", grid, counts, "OK" if ok else "FAIL", {k: "%.1e" % v for k, v in errs.items()}), flush=True)
+        bad = 0 if ok else 1
+    dist.barrier()
+    return bad
 
 
 if __name__ == "__main__":

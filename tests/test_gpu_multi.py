@@ -35,3 +35,16 @@ def test_two_rank_halo_overlap_matches_fixtures():
     print("\n".join(lines))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert len(lines) >= 4 and not any("FAIL" in l for l in lines)
+
+
+def test_two_rank_run_with_an_empty_brick():
+    """one rank owns no atoms: it must keep taking part in the halos and collectives instead of hanging its neighbour"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29535", os.path.join(ROOT, "tests", "mgpu_check.py"), "--empty-rank"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if " grid " in l]
+    print("\n".join(lines))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert len(lines) == 1 and "OK" in lines[0]

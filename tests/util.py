@@ -31,3 +31,17 @@ def relerr(a, b):
     s = np.abs(b).max()
     d = np.abs(a - b).max()
     return d / s if s > 0 else d
+
+
+def relerr_elem(a, b, floor=1e-4):
+    """element-wise figure: max_i |a_i - b_i| / max(|b_i|, floor * max|b|).  Components that cancel to (almost) nothing -- the
+    force on a particle at rest inside the bulk -- are measured against the floor; everything above it against its own size."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    if a.shape != b.shape:
+        return np.inf
+    if a.size == 0:
+        return 0.0
+    s = np.abs(b).max()
+    if not s > 0:
+        return float(np.abs(a - b).max())
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor * s)).max())
