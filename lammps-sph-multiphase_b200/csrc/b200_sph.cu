@@ -213,6 +213,7 @@ static inline int nblk(long long n, int b) { return (int)std::max<long long>(1, 
 static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch)
 {
   // data[0..n) counts -> exclusive offsets, data[n] = total; recursive on the per-block totals
+  if (n <= 0) { CK(cudaMemsetAsync(data, 0, sizeof(int), h->st)); return; }      // an empty rank (no owned atoms, no slots): total 0
   int per = SCAN_T * SCAN_E, nb = (n + per - 1) / per;
   LAUNCH(h, k_scan_block, nb, SCAN_T, data, n, scratch);
   if (nb == 1) {
@@ -654,9 +655,10 @@ static bool tile_rows(b200_sph *h)
     for (int set = 0; set < (mp ? 2 : 1); set++) {
       if (set) { B.tiles = h->gtiles.p; B.ntiles = h->ngtiles; }
       int nt = set ? h->ngtiles : h->ntiles;
-      const bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
-#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm + 4 * TILE_BUILD_MASK_BYTES, B, nt); \
-                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm + 8 * TILE_BUILD_MASK_BYTES, B, nt); } while (0)
+      bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
+      if (const char *e = getenv("B200_BUILD_NT")) small = atoi(e) == 128;
+#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
+                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm, B, nt); } while (0)
       if (mp) { if (B.uni) BUILD_LAUNCH(true, true); else BUILD_LAUNCH(false, true); }
       else { if (B.uni) BUILD_LAUNCH(true, false); else BUILD_LAUNCH(false, false); }
 #undef BUILD_LAUNCH
@@ -730,7 +732,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     LAUNCH(h, k_sort_segments, nblk((long long)g.ncells * 32, B), B, g.ncells, h->csg.p, h->gperm.p, h->gorder.p, h->gkey.p);
   }
   h->ensure_cap(nl + ng, true);
-  if ((h->check || h->far_margin > 0.0) && nl) { h->xhold.ensure((size_t)3 * (nl + ng)); LAUNCH(h, k_store_xhold, nblk(nl + ng, B), B, nl + ng, h->C().xt.p, h->xhold.p); }
+  if ((h->check || h->far_margin > 0.0) && nl + ng) { h->xhold.ensure((size_t)3 * (nl + ng)); LAUNCH(h, k_store_xhold, nblk(nl + ng, B), B, nl + ng, h->C().xt.p, h->xhold.p); }      // ghosts of a rank without owned atoms included (k_unpack_forward reads them)
   h->tend();
   // 3. rows
   h->tbegin(T_NEIGH_BUILD);

@@ -40,8 +40,6 @@
 #define TILE_SLOT_MASK 0x1fffu
 #define TILE_MAXSLOTS 8190
 #define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
-#define TILE_NBLK 12             // k_tile_build: blocks of 32 candidates per super-chunk (2 mask words per block and lane in shared memory)
-#define TILE_BUILD_MASK_BYTES (2 * TILE_NBLK * 32 * 4)     // per warp
 // multiphase entries carry two more flags (their records are 64-128 B, so a tile never holds more than 2047 slots):
 //   [15:13] type of j | [12] the row particle is the reference's "i" of the pair (half-list owner, frozen at build time)
 //   | [11] j is a ghost | [10:0] slot
@@ -270,7 +268,7 @@ __device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int 
 // NT: 256 threads for big tiles (C2: 8 chunks of 32 rows per tile), 128 when the tiles are small (more CTAs per SM to overlap the
 // per-tile barriers); the (cell, chunk) work items of a tile are handed to the warps through a shared counter.
 template <bool UNI, bool MP, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_tile_build(const __grid_constant__ TileBuildArgs A)
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
   constexpr int TILE_BUILD_NT = NT;
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -278,7 +276,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_tile_build(const __gr
   float *fx = (float *)tile_smem, *fy = fx + cap4, *fz = fy + cap4;
   int *so = (int *)(fz + cap4);                                // MP: LAMMPS local index of the owned candidates
   unsigned char *ty = (unsigned char *)(MP ? (void *)(so + cap4) : (void *)so);
-  unsigned *const msk = (unsigned *)(ty + cap4) + (threadIdx.x >> 5) * (2 * TILE_NBLK * 32) + (threadIdx.x & 31);     // this lane's column of its warp's mask store
   __shared__ TileDesc D;
   __shared__ int s_tile, s_item;
   __shared__ unsigned s_emax;
@@ -387,83 +384,71 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_tile_build(const __gr
             } else if (oi < so[slot]) ent |= TMP_OWNER;
             return true;
           };
-          // A super-chunk = up to TILE_NBLK blocks of 32 candidates (a whole candidate range of the usual deck).  Phase A leaves the
-          // near / mid / far masks of every block (this lane's row; two words) in the warp's mask store; phase B then drains one zone at a time in a flattened loop --
-          // every iteration emits one entry for every lane that still has one, whichever block it sits in.  Draining block by
-          // block (round 1) made the warp wait for its fullest lane 1 600 / 32 times per row: lanes hold 5.5 +- 2.3 entries per
-          // block, but 42 +- 6 per super-chunk (profiles/r02_build_*: thread efficiency 21.5 -> see there).
-          for (int bj0 = s0 & ~3; bj0 < s1; bj0 += 32 * TILE_NBLK) {
-            const int nb = imin(TILE_NBLK, (s1 - bj0 + 31) >> 5);
-            for (int b = 0; b < nb; b++) {
-              const int bj = bj0 + 32 * b;
-              // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
-              // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
-              // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
-              unsigned in = 0, mb = 0, fr = 0, md = 0; int nq = 0;
+          for (int bj = s0 & ~3; bj < s1; bj += 32) {
+            // phase A: 32 candidates, three compares each.  in: surely inside the cutoff; mb: inside or in its error band;
+            // fr: surely in the far zone (one-sided: an entry just beyond the far threshold may stay in the near row, where it is only tested more often)
+            // the sign bit of (rsq - threshold) is the compare; a funnel shift appends it to the mask (2 instructions per compare)
+            unsigned in = 0, mb = 0, fr = 0, md = 0; int nq = 0;
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
-                const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+            for (int k = 0; k < 8; k++) {
+              const float4 X = *(const float4 *)(fx + bj + 4 * k), Y = *(const float4 *)(fy + bj + 4 * k), Z = *(const float4 *)(fz + bj + 4 * k);
+              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                  const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
-                  const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                  in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
-                  mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
-                  if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
-                }
-                nq = k + 1;
-                if (bj + 4 * k + 4 >= s1) break;
+              for (int c = 0; c < 4; c++) {
+                const float dx = xi - xs[c], dy = yi - ys[c], dz = zi - zs[c];
+                const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
+                mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
+                if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
               }
-              // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
-              in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
-              // only the slots of [s0, s1), and never the row particle itself
-              unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
-              if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
-              if (myslot >= bj && myslot < bj + 32) vm &= ~(1u << (myslot - bj));
-              if (!valid) vm = 0;
-              in &= vm; mb &= vm;
-              unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
-              if (!UNI) in = 0;
-              while (border) {
-                const int idx = __ffs((int)border) - 1; border &= border - 1;
-                const int slot = bj + idx;
-                int cls = -1;
-                if (!UNI) {
-                  const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
-                  const float rsq = dx * dx + dy * dy + dz * dz;
-                  const float *th = s_thr[ti * MAXT1 + ty[slot]];
-                  if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
-                  else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
-                }
-                if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
-                if (cls) in |= 1u << idx;
-                if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
-                if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
-              }
-              // one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin
-              // two words per block: near = lo & ~hi, mid = hi & ~lo, far = lo & hi
-              msk[(0 * TILE_NBLK + b) * 32] = in & (fr | ~md);
-              msk[(1 * TILE_NBLK + b) * 32] = in & (fr | md);
+              nq = k + 1;
+              if (bj + 4 * k + 4 >= s1) break;
             }
-            // phase B: entries straight from the masks, one zone after the other
-#pragma unroll
-            for (int z = 0; z < 3; z++) {
-              const unsigned *lo = msk, *hi = msk + TILE_NBLK * 32;
-              auto word = [&](int b) { const unsigned l = lo[b * 32], u = hi[b * 32]; return z == 0 ? (l & ~u) : (z == 1 ? (u & ~l) : (l & u)); };
-              int b = 0; unsigned m = word(0);
-              for (;;) {
-                while (m == 0 && b + 1 < nb) { b++; m = word(b); }
-                if (m == 0) break;
-                const int idx = __ffs((int)m) - 1; m &= m - 1;
-                const int slot = bj0 + 32 * b + idx;
-                unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
-                if (flags(slot, ent)) {
-                  if (z == 0) wn.push(ent, q, nrow16, stride);
-                  else if (z == 1) wm.push(ent, frow, A.ngrp);
-                  else wf.push(ent, frow, A.ngrp);
-                }
+            // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
+            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
+            // only the slots of [s0, s1), and never the row particle itself
+            unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
+            if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
+            if (myslot >= bj && myslot < bj + 32) vm &= ~(1u << (myslot - bj));
+            if (!valid) vm = 0;
+            in &= vm; mb &= vm;
+            unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
+            if (!UNI) in = 0;
+            while (border) {
+              const int idx = __ffs((int)border) - 1; border &= border - 1;
+              const int slot = bj + idx;
+              int cls = -1;
+              if (!UNI) {
+                const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
+                const float rsq = dx * dx + dy * dy + dz * dz;
+                const float *th = s_thr[ti * MAXT1 + ty[slot]];
+                if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
+                else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
               }
+              if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
+              if (cls) in |= 1u << idx;
+              if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
+              if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
+            }
+            // phase B: entries straight from the masks (one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin)
+            unsigned nearm = in & ~fr & ~md, midm = in & ~fr & md, farm = in & fr;
+            while (nearm) {
+              const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
+              const int slot = bj + idx;
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wn.push(ent, q, nrow16, stride);
+            }
+            while (midm) {
+              const int idx = __ffs((int)midm) - 1; midm &= midm - 1;
+              const int slot = bj + idx;
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wm.push(ent, frow, A.ngrp);
+            }
+            while (farm) {
+              const int idx = __ffs((int)farm) - 1; farm &= farm - 1;
+              const int slot = bj + idx;
+              unsigned ent = ((unsigned)ty[slot] << TILE_SLOT_BITS) | (unsigned)slot;
+              if (flags(slot, ent)) wf.push(ent, frow, A.ngrp);
             }
           }
         };
@@ -759,7 +744,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
   constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;        // LPW rows per warp, SPLIT lanes per row
   extern __shared__ __align__(128) unsigned char tile_smem[];
   TileSmem<2, 1> S(tile_smem, A.cap);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane / LPW, rl = lane % LPW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   load_tab(S.T, A.tab[0]);
   if (tid == 0) mbar_init(S.bar, 1);
   const PairTab &T = S.T[0];
@@ -772,8 +757,12 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
-    for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
-      const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
+    // lanes per row by the size of the tile: a tile of <= 128 (<= 64) rows -- the end of an x-run, a free surface -- would leave
+    // half (three quarters) of the CTA's warps idle at the tile barrier with a fixed split
+    const int lpw = (SPLIT == 1 || D.nrows > TILE_ROWS / 2) ? LPW : (D.nrows > TILE_ROWS / 4 ? LPW / 2 : LPW / 4), split = 32 / lpw;
+    const int sub = lane / lpw, rl = lane % lpw, rpp = (NT / 32) * lpw;
+    for (int rb = 0; rb < D.nrows; rb += rpp) {
+      const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
       bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
@@ -782,7 +771,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
       if (valid) {
         ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
         if (scan_far | scan_mid) nf0 = A.numfar[row];
-        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+        if (sub < A.ngrp) E0 = ldg_nc_u4(A.near + rbase + sub * 32);
       }
       if (rb == 0) L.wait();
       double2 a = make_double2(0, 0), b = a;
@@ -798,9 +787,9 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = E0;
         if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
-        for (int gi = sub; gi < ng; gi += SPLIT) {
+        for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
-          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
+          if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -824,8 +813,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
           }
         }
       }
-#pragma unroll
-      for (int o = LPW; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+      for (int o = lpw; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
       if (UNI) acc *= U.mass * U.c0;
       if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
     }
@@ -855,7 +843,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
   constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;
   extern __shared__ __align__(128) unsigned char tile_smem[];
   TileSmem<NPARTS, NK> S(tile_smem, A.cap);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane / LPW, rl = lane % LPW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int t = 0; t < NK; t++) load_tab(S.T + t, A.tab[t]);
   if (tid == 0) mbar_init(S.bar, 1);
   const double2 *P0 = S.part, *P1 = P0 + A.cap, *P2 = P1 + A.cap, *P3 = P2 + A.cap, *PEp = S.part + (size_t)PE * A.cap;
@@ -871,8 +859,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
-    for (int rb = 0; rb < D.nrows; rb += TILE_ROWS) {
-      const int rt = rb + warp * LPW + rl, row = D.row0 + rt;
+    const int lpw = (SPLIT == 1 || D.nrows > TILE_ROWS / 2) ? LPW : (D.nrows > TILE_ROWS / 4 ? LPW / 2 : LPW / 4), split = 32 / lpw;      // see k_tile_rhosum
+    const int sub = lane / lpw, rl = lane % lpw, rpp = (NT / 32) * lpw;
+    for (int rb = 0; rb < D.nrows; rb += rpp) {
+      const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
       const bool valid = rt < D.nrows;
       const int myslot = D.seg_slot[2 * D.center] + (D.row0 - D.seg_src[2 * D.center]) + rt;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
@@ -881,7 +871,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
       if (valid) {
         ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
         if (scan_far | scan_mid) nf0 = A.numfar[row];
-        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+        if (sub < A.ngrp) E0 = ldg_nc_u4(A.near + rbase + sub * 32);
       }
       if (rb == 0) L.wait();
       double2 a = make_double2(0, 0), b = make_double2(0, 1), c = a, d = a; double ei = 0.0;
@@ -907,9 +897,9 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         const uint4 *lp = pass == 0 ? A.near + rbase : (pass == 1 ? A.far + rbase + (size_t)(A.ngrp - 1) * 32 : A.far + rbase);
         uint4 En = E0;
         if (pass && sub < ng) En = ldg_nc_u4(lp + sub * dir);
-        for (int gi = sub; gi < ng; gi += SPLIT) {
+        for (int gi = sub; gi < ng; gi += split) {
           const uint4 E = En;
-          if (gi + SPLIT < ng) En = ldg_nc_u4(lp + (gi + SPLIT) * dir);     // next group in flight while this one is evaluated
+          if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int e = 0; e < 8; e++) {
@@ -1006,8 +996,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         }
       }
       if (UNI) { adrho = u_k3 * u_drho; ade = -0.5 * u_de + u_heat * u_deh; }
-#pragma unroll
-      for (int o = LPW; o < 32; o <<= 1) {
+      for (int o = lpw; o < 32; o <<= 1) {
         fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
         adrho += __shfl_xor_sync(FULLMASK, adrho, o); ade += __shfl_xor_sync(FULLMASK, ade, o);
         if (VIR) {
@@ -1123,7 +1112,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
       if (valid) {
         ti = tw_type(__double_as_longlong(A.xt[row].w)); nn0 = A.numneigh[row];
         if (scan_far | scan_mid) nf0 = A.numfar[row];
-        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+        if (sub < A.ngrp) E0 = ldg_nc_u4(A.near + rbase + sub * 32);
       }
       if (rb == 0) L.wait();
       double2 a = make_double2(0, 0), b = a;
@@ -1242,7 +1231,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
       if (valid) {
         nn0 = A.numneigh[row];
         if (scan_far | scan_mid) nf0 = A.numfar[row];
-        E0 = ldg_nc_u4(A.near + rbase + sub * 32);
+        if (sub < A.ngrp) E0 = ldg_nc_u4(A.near + rbase + sub * 32);
       }
       if (rb == 0) L.wait();                  // everything above came from global memory: its latency overlaps the tile's bulk copies
       const double rhoi = b.y;

@@ -98,7 +98,7 @@ def test_host_end_of_step_fixes_fire(tmp_path):
     device-resident segment on every `nevery`, refreshes the host arrays and calls modify->end_of_step() (verlet.cpp:300)"""
     case = cases.CASES["dam2d"]
     nsteps = 30
-    extra = "\n".join(["variable s equal step", "variable k equal ke", "variable xc equal xcm(all,x)",
+    extra = "\n".join(["variable s equal step", "variable k equal vcm(all,x)", "variable xc equal xcm(all,x)",
                        'fix pr all print 7 "PRINTED ${s} ${k} ${xc}"'])
     text = deck_text(case, nsteps).replace("run %d" % nsteps, extra + "\nrun %d" % nsteps)
     a, a_out, b, b_out = _both(tmp_path, text)
