@@ -50,7 +50,7 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle per launch of the dominant kernel (single-phase):
 #   sph/taitwater stage: R x24 + vest24 + rho8 + type4, W f24 + drho8 + de8 = 100 B
 BYTES_FORCE = 100
-FP64_NOTE = "profiles/r01_tile_v5_final_full.txt: sm__pipe_fp64_cycles_active 50.6 %, shared-memory data pipe 57.6 % of peak for k_tile_force<K_TAIT> (ncu --set full, 1 028 768 particles, 0.54 ms; 42 fp64 instructions per neighbor)"
+FP64_NOTE = "profiles/r02_stage_full.txt: sm__pipe_fp64_cycles_active 57.6 %, 51 % of the fp64 lanes (dadd + dfma + dmul thread-instructions) for k_tile_force<K_TAIT> under ncu --set full (1 028 768 particles, 0.489 ms); round 1: 50.6 % at 0.539 ms"
 BYTES_STEP = 464          # whole single-phase step (rhosum 36 + taitwater 100 + fix meso 200 + 128)
 BYTES_MP_LOOP, BYTES_MP_STEP = 228, 572        # multiphase density + colorgradient + force loop / whole step
 BYTES_C4_LOOP, BYTES_C4_STEP = 252, 596        # + heat/phasechange in the fused force pass
@@ -267,6 +267,38 @@ def run_mp_config(pkg, kind, nx, steps, warmup, rank, world, local, dist, torch,
     return out
 
 
+def run_dam_balance(pkg, scale, steps, warmup, rank, world, local, dist, torch):
+    """ONE dam-break tank (C2 geometry at `scale`, 8 M particles at scale 2) on `world` bricks -- the water column sits in
+    one corner, so uniform bricks are badly loaded.  Measured twice: uniform cuts, and the cuts of `balance 1.05 shift xyz 10 1.05`
+    (parallel.balance_shift = Balance::shift, src/balance.cpp:632-790)."""
+    atoms, params = dam_break_3d(scale)
+    deck = make_deck(pkg, params)
+    grid = pkg.parallel.proc_grid(world, deck.boxlo, deck.boxhi, 3)
+    out = {"workload": "C2 geometry at edge scale %g, ONE tank (not tiled), %d particles, %s bricks" % (scale, len(atoms["type"]), "x".join(map(str, grid))),
+           "particles_total": len(atoms["type"]), "grid": list(grid), "steps": steps}
+    for label in ("uniform", "balanced"):
+        splits = pkg.parallel.balance_shift(atoms["x"], deck.boxlo, deck.boxhi, grid, "xyz", 10, 1.05) if label == "balanced" else None
+        brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, 3, grid, splits)
+        mine = brick.owns(atoms["x"])
+        sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=pkg.parallel.nccl_id(pkg.load(), dist))
+        sim.set_atoms(**{k: np.ascontiguousarray(v[mine]) for k, v in atoms.items()})
+        sim.setup(); sim.run(max(warmup, 3)); sim.sync()
+        dist.barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(); sim.run(steps); ev1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        counts = [None] * world
+        dist.all_gather_object(counts, int(sim.natoms()[0]))
+        sim.close()
+        ms = float(t.item()) / steps
+        out[label] = {"ms_per_step": ms, "particle_steps_s": len(atoms["type"]) / (ms * 1e-3), "atoms_per_rank": counts,
+                      "imbalance_max_over_mean": max(counts) / (sum(counts) / world),
+                      "splits": None if splits is None else [[round(float(v), 6) for v in sp] for sp in splits]}
+    out["speedup_balanced_over_uniform"] = out["uniform"]["ms_per_step"] / out["balanced"]["ms_per_step"]
+    return out
+
+
 def run_parity(dist, rank, world, local):
     """fixtures on the N ranks (tests/mgpu_lib.py); 2x2x2 bricks at N = 8"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -479,12 +511,13 @@ def main():
         dur = f_ms / f_calls * 1e-3
         achieved = BYTES_FORCE * n / dur / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_force_dram_bytes.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        for tp in ("r02_force_fp64.json", "r01_force_dram_bytes.json"):      # newest ncu record of this kernel first
+            tp = os.path.join(ROOT, "profiles", tp)
+            if traffic is None and os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                except Exception:
+                    pass
         roof = {"bound": "hbm", "kernel": "k_tile_force<K_TAIT> (sph/taitwater pass, shared-memory tile path)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_FORCE * n, "avg_launch_ms": dur * 1e3,
                 "share_of_step": f_ms / ms, "whole_step_GBs": BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
@@ -529,6 +562,8 @@ def main():
         plan.append(("C5_strong", "C5", args.c5_nx, 5, 3))
         sim.close(); sim = None
         torch.cuda.empty_cache()
+        if world > 1:
+            configs["C2_one_tank_8M"] = run_dam_balance(pkg, 2.0, 20, 5, rank, world, local, dist, torch)
         for key, kind, nx, k, w in plan:
             try:
                 configs[key] = run_mp_config(pkg, kind, nx, k, w, rank, world, local, dist, torch, peak)

@@ -37,9 +37,9 @@ enum {
   B200_PAIR_HEATCONDUCTION_MULTIPHASE = 9,  /* sph/heatconduction/multiphase  ..._multiphase.cpp:49-129 */
   B200_PAIR_HEATCONDUCTION_PHASECHANGE = 10,/* sph/heatconduction/phasechange ..._phasechange.cpp:52-141 */
   B200_PAIR_IDEALGAS = 11,          /* sph/idealgas                  pair_sph_idealgas.cpp:48-175 (coeff: I J viscosity h) */
-  B200_PAIR_LJ = 12                 /* sph/lj                        pair_sph_lj.cpp:48-182 (coeff: I J viscosity h).  Reserved: the oracle restates it
-                                       (tests/golden/lj3d.npz); the engine does not implement it yet and b200_pair_add refuses it (< 0) -- its
-                                       `fi += lrc` inside the neighbor loop (:139) makes every pair force depend on the reference's list order */
+  B200_PAIR_LJ = 12                 /* sph/lj                        pair_sph_lj.cpp:48-182 (coeff: I J viscosity h).  Its `fi += lrc` inside the
+                                       neighbor loop (:139) makes every pair force depend on the reference's list order: the engine ranks
+                                       each row's entries in that order (csrc/b200_lj.cuh); needs a full-list sub-style (sph/rhosum) in the deck */
 };
 
 /* One sub-style of `pair_style hybrid/overlay` (or the single pair style),
@@ -129,6 +129,11 @@ int  b200_neighbor(b200_sph *h, double skin, int every, int delay, int check,
 int  b200_timestep(b200_sph *h, double dt, double ftm2v, long long ntimestep);
 /* comm_modify vel yes: ghosts carry v (needed by fix phase_change)             */
 int  b200_comm_modify(b200_sph *h, int ghost_velocity);
+/* atom_modify sort Nfreq binsize (Atom::modify_params, src/atom.cpp:540-552; defaults 1000, 0.0 = half the neighbor cutoff).  The engine
+ * keeps its own device order; Atom::sort (atom.cpp:1555-1650, called by Verlet::setup and on the first rebuild at or after nextsort,
+ * verlet.cpp:106,251) is reproduced as a re-numbering of the local indices: it decides half-list ownership, the draw order of
+ * fix phase_change and the order of the arrays b200_get_atoms returns.  sortfreq 0 = atom_modify sort 0 0 (never). */
+int  b200_atom_modify(b200_sph *h, int sortfreq, double userbinsize);
 
 /* Pair sub-styles in deck order (PairHybrid::compute order, pair_hybrid.cpp:101-109). */
 int  b200_pair_clear(b200_sph *h);

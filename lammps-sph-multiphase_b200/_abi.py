@@ -60,6 +60,7 @@ _PROTOS = {
     "neighbor": (C.c_int, [_H, C.c_double, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double, C.c_double]),
     "timestep": (C.c_int, [_H, C.c_double, C.c_double, C.c_longlong]),
     "comm_modify": (C.c_int, [_H, C.c_int]),
+    "atom_modify": (C.c_int, [_H, C.c_int, C.c_double]),
     "pair_clear": (C.c_int, [_H]),
     "pair_add": (C.c_int, [_H, C.POINTER(PairDesc)]),
     "fix_clear": (C.c_int, [_H]),

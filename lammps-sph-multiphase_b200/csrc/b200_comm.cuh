@@ -11,7 +11,7 @@
 #include "b200_common.cuh"
 #include "b200_neigh.cuh"
 
-#define NB_BORDER 20    // x3 v3 vest3 rho cg3 rmass e cv tag type mask image
+#define NB_BORDER 21    // x3 v3 vest3 rho cg3 rmass e cv tag type mask image|order-code root-index
 #define NB_REVERSE 5    // f3 drho de
 #define NB_EXCHANGE 26  // every per-atom field
 
@@ -39,8 +39,19 @@ __global__ void k_compact(int n, const int *flag, const int *pos, int *list)
 
 __device__ __forceinline__ double shifted(double c, double shift) { return shift != 0.0 ? __dadd_rn(c, shift) : c; }
 
+// gimage of an atom: bits 0-7 the periodic image code (13 = none), bits 8-16 its ORDER CODE, three octal digits d3 d2 d1 = (swap that
+// created the ghost) + 1, the same for its source, and for the source's source (0 = an owned atom).  The reference appends ghosts
+// swap by swap, and inside a swap in the sender's local-index order (comm_brick.cpp:722-760), whereas the engine scans its
+// cell-sorted device order; (order code, orig of the root owned atom) is a sort key that reproduces the reference's ghost order
+// wherever the local index of a ghost matters (pair sph/lj: the order of a bin's atoms in the neighbor list, b200_lj.cuh).
+__device__ __forceinline__ int ghost_code(int gimage_src, int imgstep, int swapcode)
+{
+  const int img = (gimage_src & 0xff) + imgstep, d = (gimage_src >> 8) & 0x1ff;
+  return img | (((swapcode << 6) | (d >> 3)) << 8);
+}
+
 // pack_border_vel: x + pbc shift, ... (atom_vec_meso_multiphase.cpp:555-721)
-__global__ void k_pack_border(int n, const int *list, CommArrays a, int dim, double shift, int imgstep, double *buf)
+__global__ void k_pack_border(int n, const int *list, CommArrays a, int dim, double shift, int imgstep, int swapcode, double *buf)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -51,7 +62,7 @@ __global__ void k_pack_border(int n, const int *list, CommArrays a, int dim, dou
   b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
   b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[j]; b[15] = a.cv[j];
   b[16] = (double)a.tag[j]; b[17] = (double)tw_type(__double_as_longlong(x.w)); b[18] = (double)a.mask[j];
-  b[19] = (double)(a.gimage[j] + imgstep);
+  b[19] = (double)ghost_code(a.gimage[j], imgstep, swapcode); b[20] = (double)a.orig[j];
 }
 __global__ void k_unpack_border(Geom g, int n, int first, CommArrays a, const double *buf)
 {
@@ -65,14 +76,14 @@ __global__ void k_unpack_border(Geom g, int n, int first, CommArrays a, const do
   a.vr[i] = make_double4(b[6], b[7], b[8], b[9]);
   a.cgm[i] = make_double4(b[10], b[11], b[12], b[13]);
   a.e[i] = b[14]; a.cv[i] = b[15];
-  a.tag[i] = (int)b[16]; a.mask[i] = (int)b[18]; a.gimage[i] = (int)b[19];
+  a.tag[i] = (int)b[16]; a.mask[i] = (int)b[18]; a.gimage[i] = (int)b[19]; a.orig[i] = (int)b[20];      // a ghost's orig = local index of its root owned atom on the sending rank
 }
 // borders without a host round trip per swap: one thread per atom of [0, nlast); a flagged atom k = pos[i] < cap is packed into
 // record k and entered in the send list; buf[0] (the message header) carries the true count pos[nlast], so the receiver -- who
 // posted a receive of the same cap, derived from the count of the previous build on both sides -- learns how many records are
 // valid, and both sides learn about an overflow (count > cap) from the same number.
 __global__ void k_pack_border_compact(int nlast, const int *flag, const int *pos, int cap, int *list, CommArrays a, int dim, double shift,
-                                      int imgstep, double *buf)
+                                      int imgstep, int swapcode, double *buf)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) buf[0] = (double)pos[nlast];
@@ -86,7 +97,7 @@ __global__ void k_pack_border_compact(int nlast, const int *flag, const int *pos
   b[3] = v.x; b[4] = v.y; b[5] = v.z; b[6] = vr.x; b[7] = vr.y; b[8] = vr.z; b[9] = vr.w;
   b[10] = c.x; b[11] = c.y; b[12] = c.z; b[13] = v.w; b[14] = a.e[i]; b[15] = a.cv[i];
   b[16] = (double)a.tag[i]; b[17] = (double)tw_type(__double_as_longlong(x.w)); b[18] = (double)a.mask[i];
-  b[19] = (double)(a.gimage[i] + imgstep);
+  b[19] = (double)ghost_code(a.gimage[i], imgstep, swapcode); b[20] = (double)a.orig[i];
 }
 // pack_comm[_vel] (atom_vec_meso.cpp:139-245, atom_vec_meso_multiphase.cpp:319-465): cv, type, tag, mask are NOT resent.
 // Message layout (doubles per ghost): x3 vest3 rho e | v3 if comm_modify vel yes | cg3 rmass if atom_style meso/multiphase

@@ -22,7 +22,7 @@
 #define NBR_INDEX_MASK 0x0fffffffu
 
 // force-pass kinds (bit flags of the fused force kernel)
-enum { K_TAIT = 1, K_MORRIS = 2, K_TAITMP = 4, K_SURF = 8, K_HEAT = 16, K_HEATMP = 32, K_HEATPC = 64, K_IDEAL = 128 };
+enum { K_TAIT = 1, K_MORRIS = 2, K_TAITMP = 4, K_SURF = 8, K_HEAT = 16, K_HEATMP = 32, K_HEATPC = 64, K_IDEAL = 128, K_LJ = 256 };
 
 // Tables of one pair sub-style, device resident (filled by b200_pair_add).
 // Everything indexed [ti * MAXT1 + tj]; cutsq < 0 where the sub-style is not mapped

@@ -169,6 +169,31 @@ __global__ void k_sort_segments(int ncells, const int *cellstart, const int *per
   }
 }
 
+// ---- Atom::sort (atom.cpp:1555-1650): the spatial sort that defines LAMMPS' local index order ----
+// The engine keeps its own (cell-sorted) device order; what the reference's local order decides -- which atom of a pair is the
+// half list's "i" (neigh_derive.cpp:101-110), the order in which fix phase_change draws its random numbers, the order of the
+// output arrays -- lives in `orig`.  Atom::sort re-numbers the owned atoms bin by bin (bins of half the neighbor cutoff over the
+// sub-domain, setup_sort_bins :1659-1730), atoms of one bin in their previous order: k_sort_bin + scan + k_scatter +
+// k_sort_segments (key = previous index) + k_sort_assign reproduce exactly that numbering.
+struct SortGeom { double lo[3], inv[3]; int n[3]; };
+__global__ void k_sort_bin(SortGeom sg, int nslots, const double4 *xt, const int *alive, const int *orig, int *bin, int *cnt, unsigned long long *key)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  if (alive && !alive[i]) { bin[i] = -1; return; }
+  double4 p = xt[i];
+  int ix = (int)((p.x - sg.lo[0]) * sg.inv[0]), iy = (int)((p.y - sg.lo[1]) * sg.inv[1]), iz = (int)((p.z - sg.lo[2]) * sg.inv[2]);     // static_cast<int>: toward zero
+  ix = imin(imax(ix, 0), sg.n[0] - 1); iy = imin(imax(iy, 0), sg.n[1] - 1); iz = imin(imax(iz, 0), sg.n[2] - 1);
+  int b = iz * sg.n[1] * sg.n[0] + iy * sg.n[0] + ix;
+  bin[i] = b; key[i] = (unsigned long long)(unsigned)orig[i];
+  atomicAdd(&cnt[b], 1);
+}
+__global__ void k_sort_assign(int nslots, const int *ntot, const int *sorted, int *orig)      // *ntot = live atoms (the scan's total)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nslots && p < *ntot) orig[sorted[p]] = p;
+}
+
 // gather the owned particles into cell order; xt.w gets type + reference bin of the (wrapped) position
 struct OwnedArrays {
   double4 *xt, *vr, *vm, *fd, *cgm;
@@ -214,7 +239,7 @@ __global__ void k_ghost_cells(Geom g, int nlocal, int nghost, const double4 *xt,
   double4 p = xt[nlocal + s];
   int c = cell_of(g, p.x, p.y, p.z);
   gcell[s] = c;
-  gkey[s] = ((unsigned long long)(unsigned)tag[nlocal + s] << 5) | (unsigned)gimage[nlocal + s];
+  gkey[s] = ((unsigned long long)(unsigned)tag[nlocal + s] << 5) | (unsigned)(gimage[nlocal + s] & 31);      // image code only (bits 8+ hold the order code, b200_comm.cuh)
   atomicAdd(&gcellcnt[c], 1);
 }
 

@@ -4,6 +4,7 @@
 #include "b200_neigh.cuh"
 #include "b200_pair.cuh"
 #include "b200_tile.cuh"
+#include "b200_lj.cuh"
 #include "b200_fix.cuh"
 #include "b200_phase.cuh"
 #include "b200_comm.cuh"
@@ -125,6 +126,9 @@ struct b200_sph {
   ncclComm_t nccl = nullptr;
   Swap swaps[6]; int nswap = 0;
   int next_orig = 0;
+  // atom_modify sort (Atom::sortfreq / userbinsize / nextsort, atom.cpp:63-65): when the reference re-numbers its local indices
+  int sortfreq = 0; double sort_binsize = 0.0; long long nextsort = 0; SortGeom sortgeom{}; bool sortgeom_ok = false;
+  DevBuf<int> sort_cnt, sort_fill; bool sort_pending = false;
   double *d_red = nullptr, *h_red = nullptr;   // [0..7] scalars, [8..13] atom extent (-min, max per dimension), d_red[16..21] its ordered keys
   // boundary s / m (Domain::boundary, small, minxlo..): the box is re-fitted to the owned atoms on every rebuild
   int boundary[3][2] = {{0, 0}, {0, 0}, {0, 0}}; bool shrink = false; double small[3] = {0, 0, 0}, minbox[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -239,7 +243,10 @@ static void setup_geometry(b200_sph *h, bool keep_comm_history = false)
     g.slab_hi_lo[d] = g.subhi[d] - g.cutghost;
     bool swaps = (g.periodic[d] || h->procgrid[d] > 1) && !(g.dim == 2 && d == 2);
     if (swaps) {
-      int maxneed = (int)(g.cutghost * h->procgrid[d] / g.prd[d]) + 1;   // comm_brick.cpp:228-230
+      // one ghost layer of neighbour ranks: maxneed = 1 (comm_brick.cpp:225-231 for uniform bricks, the updown() walk :260-300 for
+      // non-uniform ones, i.e. after `balance ... shift`): every brick must be at least one ghost cutoff long
+      int maxneed = (int)(g.cutghost * h->procgrid[d] / g.prd[d]) + 1;
+      if (h->procgrid[d] > 1 && g.subhi[d] - g.sublo[d] < g.cutghost) maxneed = 2;
       if (maxneed > 1) throw std::string("b200: ghost cutoff >= sub-domain length is not supported (one ghost layer of neighbour ranks)");
     }
     double lo = swaps ? g.sublo[d] - g.cutghost : g.sublo[d];
@@ -394,7 +401,7 @@ static void comm_borders(b200_sph *h)
       if (capS[q] >= 0) {
         s.sendlist.ensure(capS[q] + 1);
         LAUNCH(h, k_pack_border_compact, nblk(std::max(nlast, 1), B), B, nlast, flag[q], pos[q], capS[q], s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep,
-               h->sendbuf.p + soff[q]);
+               k0 + q + 1, h->sendbuf.p + soff[q]);
       }
       CK(cudaMemcpyAsync(h->h_flags + 28 + q, pos[q] + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     }
@@ -430,7 +437,7 @@ static void comm_borders(b200_sph *h)
         h->xs[q].ensure((size_t)s.nsend * NB_BORDER + 2);
         if (s.nsend) {
           LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, flag[q], pos[q], s.sendlist.p);
-          LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, h->xs[q].p + 1);
+          LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, k0 + q + 1, h->xs[q].p + 1);
         }
       }
       if (self) { s.nrecv = s.nsend; if (send_exact) rbuf[q] = h->xs[q].p; continue; }
@@ -675,6 +682,47 @@ static bool tile_rows(b200_sph *h)
 }
 
 // ------------------------------------------------------------- reneighbor ---
+// Atom::setup_sort_bins (atom.cpp:1659-1730): called by Atom::setup at the start of every run and whenever the box changes
+static void setup_sort_bins(b200_sph *h)
+{
+  Geom &g = h->g;
+  double binsize = h->sort_binsize > 0.0 ? h->sort_binsize : 0.5 * h->cutneighmax;
+  if (binsize == 0.0) throw std::string("Atom sorting has bin size = 0.0");
+  double bininv = 1.0 / binsize;
+  SortGeom &sg = h->sortgeom;
+  double nb = 1.0;
+  for (int d = 0; d < 3; d++) {
+    sg.lo[d] = g.sublo[d];
+    int n = (int)((g.subhi[d] - g.sublo[d]) * bininv);
+    if (g.dim == 2 && d == 2) n = 1;
+    if (n == 0) n = 1;
+    sg.n[d] = n; sg.inv[d] = n / (g.subhi[d] - g.sublo[d]);
+    nb *= n;
+  }
+  if (nb > 2.0e9) throw std::string("Too many atom sorting bins");
+  h->sortgeom_ok = true;
+}
+// Atom::sort (atom.cpp:1555-1650) as a re-numbering of `orig`; slots [0, nslots), dead ones (alive == 0) skipped
+static void atom_sort(b200_sph *h, int nslots, const int *alive)
+{
+  const int B = 256;
+  h->nextsort = (h->ntimestep / h->sortfreq) * h->sortfreq + h->sortfreq;
+  if (h->shrink || !h->sortgeom_ok) setup_sort_bins(h);          // "if (domain->box_change) setup_sort_bins()" (:1569)
+  const SortGeom &sg = h->sortgeom;
+  const int nbins = sg.n[0] * sg.n[1] * sg.n[2];
+  if (nbins == 1 || !nslots) return;
+  h->sort_cnt.ensure(nbins + 2); h->sort_fill.ensure(nbins + 2);
+  h->cellid.ensure(nslots + 1); h->perm.ensure(nslots + 1); h->perm2.ensure(nslots + 1); h->key.ensure(nslots + 1);
+  ensure_scan_tmp(h, std::max<size_t>(nslots + 2, nbins + 2));
+  CK(cudaMemsetAsync(h->sort_cnt.p, 0, (nbins + 2) * sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->sort_fill.p, 0, (nbins + 2) * sizeof(int), h->st));
+  LAUNCH(h, k_sort_bin, nblk(nslots, B), B, sg, nslots, h->C().xt.p, alive, h->C().orig.p, h->cellid.p, h->sort_cnt.p, h->key.p);
+  scan_exclusive(h, h->sort_cnt.p, nbins, h->scan_tmp.p);
+  LAUNCH(h, k_scatter, nblk(nslots, B), B, nslots, h->cellid.p, h->sort_cnt.p, h->sort_fill.p, h->perm.p);
+  LAUNCH(h, k_sort_segments, nblk((long long)nbins * 32, B), B, nbins, h->sort_cnt.p, h->perm.p, h->perm2.p, h->key.p);
+  LAUNCH(h, k_sort_assign, nblk(nslots, B), B, nslots, h->sort_cnt.p + nbins, h->perm2.p, h->C().orig.p);
+}
+
 
 static void neighbor_build(b200_sph *h, bool do_pbc)
 {
@@ -695,6 +743,13 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     }
     nslots = comm_exchange(h, nl);
     alive = h->alive.p; do_pbc = false;
+  }
+  // Atom::sort between exchange and borders: at every setup and on the first rebuild at or after nextsort (verlet.cpp:106,251)
+  bool sorted_now = false;
+  if (h->sortfreq > 0 && (h->sort_pending || (h->setup_done && h->ntimestep >= h->nextsort))) {
+    if (h->world == 1 && do_pbc && nl) LAUNCH(h, k_pbc, nblk(nl, B), B, g, nl, h->C().xt.p);      // the sort bins see wrapped positions (domain->pbc comes first)
+    atom_sort(h, nslots, alive);
+    sorted_now = true; h->sort_pending = false;
   }
   h->cellid.ensure(nslots + 1); h->perm.ensure(nslots + 1); h->perm2.ensure(nslots + 1); h->key.ensure(nslots + 1);
   ensure_scan_tmp(h, std::max<size_t>(nslots + 2, g.ncells + 2));
@@ -718,6 +773,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     h->cur ^= 1;
   }
   h->nlocal = nl;
+  if (sorted_now) h->next_orig = nl;                 // the local indices are 0 .. nlocal-1 again
   if (nl) LAUNCH(h, k_fill_int, nblk(nl, B), B, nl, h->gimage.p, 13);
   // 2. ghosts: the staged x, y, z swaps of CommBrick::borders, then a cell-ordered index of them
   comm_borders(h);
@@ -779,6 +835,7 @@ static int kind_of(int style)
   case B200_PAIR_HEATCONDUCTION_MULTIPHASE: return K_HEATMP;
   case B200_PAIR_HEATCONDUCTION_PHASECHANGE: return K_HEATPC;
   case B200_PAIR_IDEALGAS: return K_IDEAL;
+  case B200_PAIR_LJ: return K_LJ;
   default: return 0;
   }
 }
@@ -821,11 +878,19 @@ static void build_plan(b200_sph *h)
     p.type = 3; p.kinds = kind_of(st); k++;
     while (k < h->npair && p.nslots < 3) {
       int kk = kind_of(h->h_tab[k].style);
-      if (!kk || (p.kinds & kk) || !fusable(p.kinds | kk)) break;
+      if (!kk || (p.kinds & kk) || !fusable(p.kinds | kk) || ((p.kinds | kk) & K_LJ)) break;
       p.kinds |= kk; p.slots[p.nslots++] = k; k++;
     }
     h->plan.push_back(p);
   }
+  for (const Pass &p : h->plan)
+    if (p.type == 3 && (p.kinds & K_LJ)) {
+      bool full = false;
+      for (const Pass &q : h->plan) if (q.type != 3) full = true;
+      if (!full || h->multiphase)
+        throw std::string("pair sph/lj/b200 needs atom_style meso and a full-list sub-style (sph/rhosum) in the deck: without one LAMMPS builds its half "
+                          "list in another order (half_bin_newton), and the style's result depends on that order (pair_sph_lj.cpp:139)");
+    }
   // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
   if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
@@ -1178,6 +1243,20 @@ static void run_pass(b200_sph *h, const Pass &p)
     }
     return;
   }
+  if (p.kinds == K_LJ) {          // sph/lj: its own kernel (owner-side evaluation in the reference's list order, b200_lj.cuh)
+    OwnedSet &c = h->C();
+    h->tbegin(T_FORCE);
+    h->f_clean = false;
+    CK(cudaMemsetAsync(h->d_flags + 13, 0, sizeof(int), h->st));
+    LjArgs L{h->nlocal, h->stride, h->g.dim, h->g.sx, h->g.sy, h->g.sz, h->nbr.p, h->far.p, h->numneigh.p, h->numfar.p,
+             c.xt.p, c.vr.p, c.e.p, c.cv.p, c.orig.p, h->gimage.p, c.fd.p, c.de.p, h->d_tab[p.slots[0]], h->d_flags + 13};
+    if (h->nlocal) LAUNCH(h, k_force_lj, nblk(h->nlocal, 128), 128, L);
+    CK(cudaMemcpyAsync(h->h_flags + 13, h->d_flags + 13, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (h->h_flags[13]) throw std::string("pair sph/lj/b200: more than 512 in-cutoff half-list neighbors of one atom");
+    h->tend();
+    return;
+  }
   // force pass: canonical table order fluid, surf, heat
   PairArgs A = pair_args(h);
   int nk = 0; const PairTab *fluid = nullptr;
@@ -1404,6 +1483,7 @@ static void do_setup(b200_sph *h)
     h->maxtag = h->h_flags[12];
   }
   build_plan(h);
+  if (h->sortfreq > 0) { h->sortgeom_ok = false; h->sort_pending = true; }      // Atom::setup -> setup_sort_bins; Verlet::setup: if (atom->sortfreq > 0) atom->sort()
   neighbor_build(h, true);
   h->nbuilds = 0;
   h->vir_now = h->vir_request; h->vir_request = false;
@@ -1473,7 +1553,7 @@ static void fill_tab(b200_sph *h, const b200_pair_desc *d, PairTab &T)
         T.c1[k] = ih; T.c0[k] = dim == 3 ? 3.0 * nq * ih * ih * ih * ih : 3.0 * nq * ih * ih * ih;
         if (d->alpha) T.visc[k] = d->alpha[s];
         break;
-      case B200_PAIR_TAITWATER: case B200_PAIR_TAITWATER_MORRIS: case B200_PAIR_HEATCONDUCTION: case B200_PAIR_IDEALGAS:
+      case B200_PAIR_TAITWATER: case B200_PAIR_TAITWATER_MORRIS: case B200_PAIR_HEATCONDUCTION: case B200_PAIR_IDEALGAS: case B200_PAIR_LJ:
         T.c0[k] = dim == 3 ? -25.066903536973515383e0 * ihsq * ihsq * ihsq * ih : -19.098593171027440292e0 * ihsq * ihsq * ihsq;
         T.visc[k] = d->style == B200_PAIR_HEATCONDUCTION ? (d->alpha ? d->alpha[s] : 0.0) : (d->viscosity ? d->viscosity[s] : 0.0);
         break;
@@ -1547,7 +1627,7 @@ int b200_destroy(b200_sph *h)
   for (auto &p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaFree(h->d_flags); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_vir); h->virow.release(); h->virpart.release();
   if (h->st2) cudaStreamDestroy(h->st2); if (h->ev_main) cudaEventDestroy(h->ev_main); if (h->ev_comm) cudaEventDestroy(h->ev_comm);
-  h->celld.release(); h->rowcell.release(); h->tzone.release();
+  h->celld.release(); h->rowcell.release(); h->tzone.release(); h->sort_cnt.release(); h->sort_fill.release();
   h->tiles.release(); h->gtiles.release(); h->rowtile.release(); h->trec.release(); cudaFree(h->d_tflags);
   delete h;
   return 0;
@@ -1642,6 +1722,12 @@ int b200_neighbor(b200_sph *h, double skin, int every, int delay, int check, con
 }
 int b200_timestep(b200_sph *h, double dt, double ftm2v, long long ntimestep) { h->dt = dt; h->ftm2v = ftm2v; h->ntimestep = ntimestep; return 0; }
 int b200_comm_modify(b200_sph *h, int ghost_velocity) { h->ghost_velocity = ghost_velocity; return 0; }
+int b200_atom_modify(b200_sph *h, int sortfreq, double userbinsize)
+{
+  if (sortfreq < 0 || userbinsize < 0.0) return fail("Illegal atom_modify command");
+  h->sortfreq = sortfreq; h->sort_binsize = userbinsize; h->sortgeom_ok = false;
+  return 0;
+}
 
 int b200_pair_clear(b200_sph *h) { h->npair = 0; h->plan.clear(); h->tile_on = false; return 0; }
 int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
@@ -1911,7 +1997,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
     std::vector<std::pair<int, int>> tmp;
     for (int s = 0; s < n; s++) {
       tmp.clear();
-      for (int k = 0; k < cnt[s] + cfar[s]; k++) { int j = rows[(size_t)s * width + k]; tmp.push_back({tag[j], img[j]}); }
+      for (int k = 0; k < cnt[s] + cfar[s]; k++) { int j = rows[(size_t)s * width + k]; tmp.push_back({tag[j], img[j] & 0xff}); }
       std::sort(tmp.begin(), tmp.end());
       long long o = off[orig[s]];
       for (size_t k = 0; k < tmp.size(); k++) { jtag[o + k] = tmp[k].first; jimage[o + k] = tmp[k].second; }
@@ -1936,10 +2022,10 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
     int nin = cnt[s] & 0xffff, nout = cnt[s] >> 16;
     for (int k = 0; k < nin + nout; k++) {
       int kk = k < nin ? k : h->stride - 1 - (k - nin);
-      int j = rows[(size_t)(s >> 5) * h->stride * 32 + (size_t)kk * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]});
+      int j = rows[(size_t)(s >> 5) * h->stride * 32 + (size_t)kk * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j] & 0xff});
     }
     for (int k = 0; k < cfar[s]; k++) {
-      int j = frows[(size_t)(s >> 5) * h->stride * 32 + (size_t)k * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j]});
+      int j = frows[(size_t)(s >> 5) * h->stride * 32 + (size_t)k * 32 + (s & 31)] & NBR_INDEX_MASK; tmp.push_back({tag[j], img[j] & 0xff});
     }
     std::sort(tmp.begin(), tmp.end());
     long long o = off[orig[s]];

@@ -757,9 +757,10 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
-    // lanes per row by the size of the tile: a tile of <= 128 (<= 64) rows -- the end of an x-run, a free surface -- would leave
-    // half (three quarters) of the CTA's warps idle at the tile barrier with a fixed split
-    const int lpw = (SPLIT == 1 || D.nrows > TILE_ROWS / 2) ? LPW : (D.nrows > TILE_ROWS / 4 ? LPW / 2 : LPW / 4), split = 32 / lpw;
+    // (lanes per row chosen by the size of the tile -- 2x / 4x for tiles of <= 128 / <= 64 rows, so that no warp idles at the tile
+    // barrier -- was measured in round 2: density 0.246 -> 0.320 ms, force unchanged; the extra lanes per row break the bank-aware
+    // entry order, which assumes 8 consecutive rows per quarter-warp.  Fixed split.)
+    constexpr int lpw = LPW, split = SPLIT;
     const int sub = lane / lpw, rl = lane % lpw, rpp = (NT / 32) * lpw;
     for (int rb = 0; rb < D.nrows; rb += rpp) {
       const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
@@ -813,6 +814,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
           }
         }
       }
+#pragma unroll
       for (int o = lpw; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
       if (UNI) acc *= U.mass * U.c0;
       if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
     const TileDesc &D = *Dp;
     const int zone = A.tzone ? A.tzone[S.tile[L.cur]] : (g_far | (g_mid << 1));
     const int scan_far = zone & 1, scan_mid = zone & 2;
-    const int lpw = (SPLIT == 1 || D.nrows > TILE_ROWS / 2) ? LPW : (D.nrows > TILE_ROWS / 4 ? LPW / 2 : LPW / 4), split = 32 / lpw;      // see k_tile_rhosum
+    constexpr int lpw = LPW, split = SPLIT;      // see k_tile_rhosum
     const int sub = lane / lpw, rl = lane % lpw, rpp = (NT / 32) * lpw;
     for (int rb = 0; rb < D.nrows; rb += rpp) {
       const int rt = rb + warp * lpw + rl, row = D.row0 + rt;
@@ -996,6 +998,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
         }
       }
       if (UNI) { adrho = u_k3 * u_drho; ade = -0.5 * u_de + u_heat * u_deh; }
+#pragma unroll
       for (int o = lpw; o < 32; o <<= 1) {
         fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
         adrho += __shfl_xor_sync(FULLMASK, adrho, o); ade += __shfl_xor_sync(FULLMASK, ade, o);

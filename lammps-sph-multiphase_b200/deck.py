@@ -21,7 +21,7 @@ PAIR_STYLES = {
     "sph/rhosum": 1, "sph/rhosum/multiphase": 2, "sph/taitwater": 3, "sph/taitwater/morris": 4,
     "sph/taitwater/multiphase": 5, "sph/colorgradient": 6, "sph/surfacetension": 7,
     "sph/heatconduction": 8, "sph/heatconduction/multiphase": 9, "sph/heatconduction/phasechange": 10, "sph/idealgas": 11,
-    "sph/lj": 12,        # restated by the oracle only: the engine's b200_pair_add refuses it (include/b200_sph.h B200_PAIR_LJ)
+    "sph/lj": 12,        # list-order dependent (pair_sph_lj.cpp:139): csrc/b200_lj.cuh
 }
 _NSETTINGS = {1: 1, 2: 1, 6: 1}           # styles whose settings() takes Nstep
 _NCOEFF = {1: (1,), 2: (1,), 3: (4,), 4: (4,), 5: (6,), 6: (2,), 7: (1,), 8: (2,), 9: (2,), 10: (2, 4), 11: (2,), 12: (2,)}
@@ -181,6 +181,7 @@ class Deck:
         self.styles, self.hybrid = [], False
         self.skin, self.every, self.delay, self.check = 0.3, 1, 10, 1   # Neighbor::Neighbor defaults (neighbor.cpp:60-70)
         self.ghost_velocity = 0
+        self.sortfreq, self.sort_binsize = 1000, 0.0      # atom_modify sort defaults (src/atom.cpp:63-65)
         self.dt, self.ntimestep = 0.005 if units == "lj" else 1.0e-8, 0   # Update::set_units (update.cpp)
         self.groups = {"all": 1}
         self.fixes = []
@@ -205,6 +206,14 @@ class Deck:
         if every is not None: self.every = int(every)
         if delay is not None: self.delay = int(delay)
         if check is not None: self.check = 1 if check in (1, True, "yes") else 0
+
+    def atom_modify(self, sort=None):
+        """atom_modify sort Nfreq binsize (Atom::modify_params, src/atom.cpp:540-552)"""
+        if sort is not None:
+            freq, binsize = int(sort[0]), float(sort[1])
+            if freq < 0 or binsize < 0.0:
+                raise DeckError("Illegal atom_modify command")
+            self.sortfreq, self.sort_binsize = freq, binsize
 
     def comm_modify(self, vel="no"):
         self.ghost_velocity = 1 if vel in (1, True, "yes") else 0

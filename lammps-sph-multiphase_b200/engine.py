@@ -87,6 +87,7 @@ class Sim:
         ck(api.neighbor(h, d.skin, d.every, d.delay, d.check, _dp(cn), d.cutneighmax, d.cutghost))
         ck(api.timestep(h, d.dt, d.ftm2v, d.ntimestep))
         ck(api.comm_modify(h, d.ghost_velocity))
+        ck(api.atom_modify(h, d.sortfreq, d.sort_binsize))
         ck(api.pair_clear(h))
         for s in d.styles:
             t = {k: np.ascontiguousarray(getattr(s, k)) for k in

@@ -68,6 +68,11 @@ void PairSPHIdealGasB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
   COMMON(B200_PAIR_IDEALGAS, 0)
   d.viscosity = b200_flat2(ds, viscosity, setflag, n);
 }
+void PairSPHLJB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
+{
+  COMMON(B200_PAIR_LJ, 0)
+  d.viscosity = b200_flat2(ds, viscosity, setflag, n);
+}
 void PairSPHHeatConductionMultiPhaseB200::b200_describe(b200_pair_desc &d, DS &ds, IS &is)
 {
   COMMON(B200_PAIR_HEATCONDUCTION_MULTIPHASE, 0)

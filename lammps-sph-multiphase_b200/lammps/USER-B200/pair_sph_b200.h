@@ -15,6 +15,7 @@ PairStyle(sph/heatconduction/b200,PairSPHHeatConductionB200)
 PairStyle(sph/heatconduction/multiphase/b200,PairSPHHeatConductionMultiPhaseB200)
 PairStyle(sph/heatconduction/phasechange/b200,PairSPHHeatConductionPhaseChangeB200)
 PairStyle(sph/idealgas/b200,PairSPHIdealGasB200)
+PairStyle(sph/lj/b200,PairSPHLJB200)
 
 #else
 
@@ -33,6 +34,7 @@ PairStyle(sph/idealgas/b200,PairSPHIdealGasB200)
 #include "pair_sph_heatconduction_multiphase.h"
 #include "pair_sph_heatconduction_phasechange.h"
 #include "pair_sph_idealgas.h"
+#include "pair_sph_lj.h"
 
 namespace LAMMPS_NS {
 
@@ -60,6 +62,7 @@ B200_PAIR_SHELL(PairSPHSurfaceTensionB200, PairSPHSurfaceTension)
 B200_PAIR_SHELL(PairSPHHeatConductionB200, PairSPHHeatConduction)
 B200_PAIR_SHELL(PairSPHHeatConductionMultiPhaseB200, PairSPHHeatConductionMultiPhase)
 B200_PAIR_SHELL(PairSPHIdealGasB200, PairSPHIdealGas)
+B200_PAIR_SHELL(PairSPHLJB200, PairSPHLJ)
 
 // heatconduction/phasechange leaves tc/fixflag uninitialised for the 4-argument coeff form
 // (pair_sph_heatconduction_phasechange.cpp:191-218); the shell zeroes them at allocation.

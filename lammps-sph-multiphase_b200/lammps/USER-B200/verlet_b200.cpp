@@ -33,6 +33,10 @@ namespace {
 struct DomainPeek : public Domain {
   static const double *small_of(const Domain *d) { return d->*(&DomainPeek::small); }
 };
+// Atom::userbinsize (atom.h, `atom_modify sort Nfreq binsize`) is protected as well
+struct AtomPeek : public Atom {
+  static double userbinsize_of(const Atom *a) { return a->*(&AtomPeek::userbinsize); }
+};
 }
 
 void VerletB200::check(int rc) { if (rc < 0) error->all(FLERR, b200_last_error()); }
@@ -70,6 +74,7 @@ void VerletB200::configure()
                       comm->cutghost[0]));
   check(b200_timestep(h, update->dt, force->ftm2v, update->ntimestep));
   check(b200_comm_modify(h, comm->ghost_velocity));
+  check(b200_atom_modify(h, atom->sortfreq, AtomPeek::userbinsize_of(atom)));      // the engine re-numbers its local indices when Atom::sort would (verlet.cpp:251)
 
   // pair sub-styles in PairHybrid::compute order (pair_hybrid.cpp:101-109)
   check(b200_pair_clear(h));

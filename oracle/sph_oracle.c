@@ -89,6 +89,8 @@ struct osph_sph {
   long long nsteps_done, ninserted, maxneighseen;
   int setup_done;
   int vir_request; double virial[6];
+  /* atom_modify sort (atom.cpp:63-65, 540-552) */
+  int sortfreq; double userbinsize; long long nextsort;
 };
 
 static char errbuf[512] = "";
@@ -223,6 +225,12 @@ int osph_timestep(osph_sph *s, double dt, double ftm2v, long long ntimestep)
 { s->dt = dt; s->ftm2v = ftm2v; s->ntimestep = ntimestep; return 0; }
 
 int osph_comm_modify(osph_sph *s, int ghost_velocity) { s->ghost_velocity = ghost_velocity; return 0; }
+int osph_atom_modify(osph_sph *s, int sortfreq, double userbinsize)
+{
+  if (sortfreq < 0 || userbinsize < 0.0) return fail("Illegal atom_modify command");
+  s->sortfreq = sortfreq; s->userbinsize = userbinsize;
+  return 0;
+}
 
 int osph_pair_clear(osph_sph *s) { for (int i = 0; i < s->npair; i++) free_pair(&s->pair[i]); s->npair = 0; return 0; }
 
@@ -1295,6 +1303,47 @@ int osph_final_integrate(osph_sph *s)
 { for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_MESO || s->fix[i].kind == FIX_MESO_STATIONARY) fix_final_integrate(s, &s->fix[i]); return 0; }
 int osph_neigh_decide(osph_sph *s, int *rebuild) { *rebuild = neighbor_decide(s); return 0; }
 
+/* Atom::sort, atom.cpp:1555-1650, with the bins of Atom::setup_sort_bins (:1659-1730): owned atoms re-ordered bin by bin,
+ * atoms of one bin in their previous order; every per-atom array follows the permutation. */
+static int atom_sort(osph_sph *s)
+{
+  s->nextsort = (s->ntimestep / s->sortfreq) * s->sortfreq + s->sortfreq;
+  double binsize = s->userbinsize > 0.0 ? s->userbinsize : 0.5 * s->cutneighmax;
+  if (binsize == 0.0) return fail("Atom sorting has bin size = 0.0");
+  double bininv = 1.0 / binsize, inv[3]; int nb[3];
+  for (int d = 0; d < 3; d++) {
+    nb[d] = (int)((s->subhi[d] - s->sublo[d]) * bininv);
+    if (s->dim == 2 && d == 2) nb[d] = 1;
+    if (nb[d] == 0) nb[d] = 1;
+    inv[d] = nb[d] / (s->subhi[d] - s->sublo[d]);
+  }
+  int nbins = nb[0] * nb[1] * nb[2], n = s->nlocal;
+  if (nbins == 1 || n == 0) return 0;
+  int *head = malloc(sizeof(int) * nbins), *next = malloc(sizeof(int) * n), *perm = malloc(sizeof(int) * n);
+  for (int b = 0; b < nbins; b++) head[b] = -1;
+  for (int i = n - 1; i >= 0; i--) {     /* reverse order so that the linked lists run forward (:1586-1603) */
+    int c[3];
+    for (int d = 0; d < 3; d++) {
+      c[d] = (int)((s->x[3*i+d] - s->sublo[d]) * inv[d]);
+      if (c[d] < 0) c[d] = 0;
+      if (c[d] > nb[d] - 1) c[d] = nb[d] - 1;
+    }
+    int b = c[2] * nb[1] * nb[0] + c[1] * nb[0] + c[0];
+    next[i] = head[b]; head[b] = i;
+  }
+  int m = 0;
+  for (int b = 0; b < nbins; b++) for (int i = head[b]; i >= 0; i = next[i]) perm[m++] = i;     /* new atom m = old atom perm[m] */
+#define PERMUTE(T, arr, w) do { T *tmp_ = malloc(sizeof(T) * (w) * n); memcpy(tmp_, arr, sizeof(T) * (w) * n); \
+    for (int a_ = 0; a_ < n; a_++) for (int d_ = 0; d_ < (w); d_++) arr[(w)*a_+d_] = tmp_[(w)*perm[a_]+d_]; free(tmp_); } while (0)
+  PERMUTE(double, s->x, 3); PERMUTE(double, s->v, 3); PERMUTE(double, s->vest, 3); PERMUTE(double, s->f, 3); PERMUTE(double, s->cg, 3);
+  PERMUTE(double, s->rho, 1); PERMUTE(double, s->drho, 1); PERMUTE(double, s->e, 1); PERMUTE(double, s->de, 1);
+  PERMUTE(double, s->cv, 1); PERMUTE(double, s->rmass, 1);
+  PERMUTE(int, s->type, 1); PERMUTE(int, s->mask, 1); PERMUTE(int, s->tag, 1); PERMUTE(int, s->img, 1);
+#undef PERMUTE
+  free(head); free(next); free(perm);
+  return 0;
+}
+
 /* the rebuild branch of Verlet::run, verlet.cpp:240-257 */
 int osph_reneighbor(osph_sph *s)
 {
@@ -1306,6 +1355,7 @@ int osph_reneighbor(osph_sph *s)
     if (setup_bins(s)) return -1;
   }
   /* comm->exchange(): no-op on a 1x1x1 grid (comm_brick.cpp:596 "if (procgrid[dim] == 1) continue") */
+  if (s->sortfreq > 0 && s->ntimestep >= s->nextsort) if (atom_sort(s)) return -1;   /* verlet.cpp:251 */
   comm_borders(s);
   return neighbor_build(s);
 }
@@ -1333,6 +1383,7 @@ int osph_setup(osph_sph *s)
   if (domain_reset_box(s)) return -1;   /* verlet.cpp:102 */
   if (comm_setup(s)) return -1;
   if (setup_bins(s)) return -1;
+  if (s->sortfreq > 0) if (atom_sort(s)) return -1;   /* verlet.cpp:106 */
   comm_borders(s);
   if (neighbor_build(s)) return -1;
   s->nbuilds = 0; /* neighbor->ncalls = 0 */
@@ -1375,7 +1426,8 @@ int osph_run(osph_sph *s, int nsteps)
 /* ======================================================================
    P ranks in one process (test infrastructure for the multi-GPU path): every rank is an osph_sph of its own with a brick
    sub-domain; the collective steps of CommBrick run in lock step over the array of ranks, reading the sender's arrays
-   directly where MPI would move a buffer.  Restated for maxneed = 1 (one ghost layer), uniform bricks, no fix phase_change
+   directly where MPI would move a buffer.  Restated for maxneed = 1 (one ghost layer; uniform bricks or the non-uniform cuts of
+   `balance ... shift`, every brick at least one ghost cutoff long), no fix phase_change
    (it draws one RNG stream per rank) and no shrink-wrapped faces.
    ====================================================================== */
 
@@ -1388,6 +1440,7 @@ static int w_comm_setup(osph_sph *s)
     int maxneed = (int)(s->cutghost * pg / s->prd[d]) + 1;                 /* :225-227 */
     if (s->dim == 2 && d == 2) maxneed = 0;
     if (!s->periodic[d] && maxneed > pg - 1) maxneed = pg - 1;             /* :229-231 */
+    if (pg > 1 && s->subhi[d] - s->sublo[d] < s->cutghost) maxneed = 2;   /* non-uniform bricks (balance shift): the updown() walk, :260-300 */
     if (maxneed > 1) return fail("oracle world: cutghost >= sub-domain length is not restated");
     int sendneed[2] = {maxneed, maxneed};
     if (!s->periodic[d]) {                                                  /* :233-243 */

@@ -22,6 +22,7 @@
 #define b200_neighbor          osph_neighbor
 #define b200_timestep          osph_timestep
 #define b200_comm_modify       osph_comm_modify
+#define b200_atom_modify       osph_atom_modify
 #define b200_pair_clear        osph_pair_clear
 #define b200_pair_add          osph_pair_add
 #define b200_fix_clear         osph_fix_clear

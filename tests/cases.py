@@ -22,11 +22,12 @@ def _f(v):
 
 class Case:
     def __init__(self, name, dim, boundary, box, atom_style, ntypes, create, cmds, nsteps, units="si", groups=(),
-                 tol_traj=1e-9, regions=()):
+                 tol_traj=1e-9, regions=(), sort=(0, 0.0)):
         self.name, self.dim, self.boundary, self.box = name, dim, boundary, box
         self.atom_style, self.ntypes, self.create, self.cmds, self.nsteps = atom_style, ntypes, create, cmds, nsteps
         self.units, self.groups, self.tol_traj, self.regions = units, groups, tol_traj, regions
-        self.engine = True         # False: restated by the oracle only (the engine refuses the deck with a message)
+        self.sort = sort           # atom_modify sort Nfreq binsize; None = the LAMMPS default (1000, half the neighbor cutoff)
+        self.engine = True         # False: restated by the oracle only
 
     @property
     def multiphase(self):
@@ -36,7 +37,7 @@ class Case:
         (x0, y0, z0), (x1, y1, z1) = self.box
         return "\n".join([
             "units %s" % self.units, "dimension %d" % self.dim, "boundary %s" % self.boundary, "newton on",
-            "atom_style %s" % self.atom_style, "atom_modify map array sort 0 0",
+            "atom_style %s" % self.atom_style, "atom_modify map array" + ("" if self.sort is None else " sort %d %s" % (self.sort[0], _f(float(self.sort[1])))),
             "region box block %s %s %s %s %s %s units box" % tuple(_f(float(v)) for v in (x0, x1, y0, y1, z0, z1)),
             "create_box %d box" % self.ntypes])
 
@@ -73,6 +74,8 @@ class Case:
     def deck(self):
         d = Deck(dimension=self.dim, boundary=self.boundary, box=self.box, atom_style=self.atom_style,
                  ntypes=self.ntypes, units=self.units)
+        if self.sort is not None:
+            d.atom_modify(sort=self.sort)
         for g, t in self.groups:
             d.group(g)
         for r in self.regions:
@@ -270,7 +273,7 @@ _add(_shock("shock2d", 2, 40))
 _add(_shock("gas3d", 3, 15, onetype=True))
 
 
-# ---- sph/lj: Lennard-Jones EOS fluid; oracle only (the engine refuses the style) ----
+# ---- sph/lj: Lennard-Jones EOS fluid; list-order dependent (csrc/b200_lj.cuh) ----
 def _lj(name, dim, nsteps):
     box = ((0, 0, 0), (12, 12, 12)) if dim == 3 else ((0, 0, -0.05), (20.5, 20.5, 0.05))
     create = """lattice %s %s
@@ -285,9 +288,7 @@ velocity all create 0.05 4711 dist gaussian""" % ("sc" if dim == 3 else "sq", "0
             ("pair_coeff", "* *", "sph/rhosum", 2.5), ("pair_coeff", "* *", "sph/lj", 0.5, 2.5),
             ("neighbor", 0.1 if dim == 2 else 0.3), ("neigh_modify", dict(every=2, delay=0, check="yes")), ("timestep", 0.005 if dim == 2 else 0.001),
             ("fix", "all", "meso")]
-    c = Case(name, dim, "p p p", box, "meso", 1, create, cmds, nsteps, units="lj")
-    c.engine = False
-    return c
+    return Case(name, dim, "p p p", box, "meso", 1, create, cmds, nsteps, units="lj")
 
 
 _add(_lj("lj3d", 3, 8))
@@ -407,3 +408,16 @@ _add(_bubble("bubble2d", 2, 32, 30))
 _add(_bubble("bubble3d", 3, 12, 12))
 _add(_bubble("bubble2d_thermostat", 2, 32, 25, thermostat=True))
 _add(_bubble("bubble3d_thermostat", 3, 12, 10, thermostat=True))
+
+
+# ---- 1000-step trajectories with the DEFAULT atom_modify (spatial sort at every setup and on the first rebuild at or after step
+#      1000, atom.cpp:63-65, verlet.cpp:106,251): the north star's "1e-6 after 1000 steps", and the test that the engine re-numbers
+#      its local indices when Atom::sort does (output order, half-list ownership, fix phase_change draw order) ----
+def _long(c, name, nsteps, tol):
+    c.name, c.nsteps, c.tol_traj, c.sort = name, nsteps, tol, None
+    return c
+
+
+_add(_long(_dam("dam2d", 2, 60), "dam2d_1000", 1000, 1e-6))
+_add(_long(_droplet("droplet2d", 2, 30, 40), "droplet2d_1000", 1000, 1e-6))
+_add(_long(_bubble("bubble2d", 2, 32, 30), "bubble2d_1000", 1000, 1e-6))

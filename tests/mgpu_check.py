@@ -3,6 +3,7 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py [case ...]
   ... tests/mgpu_check.py --grid 2x2x2 dam3d droplet3d          (force a processor grid where the box allows it)
   ... tests/mgpu_check.py --empty-rank                           (one brick without atoms: the dry half of a dam break)
+  ... tests/mgpu_check.py --balance x dam3d dam2d                (non-uniform bricks from parallel.balance_shift)
 """
 import os
 import sys
@@ -27,6 +28,9 @@ def main():
     grid = None
     if "--grid" in args:
         k = args.index("--grid"); grid = tuple(int(v) for v in args[k + 1].split("x")); del args[k:k + 2]
+    balance = None
+    if "--balance" in args:
+        k = args.index("--balance"); balance = args[k + 1]; del args[k:k + 2]
     failed = 0
     if "--empty-rank" in args:
         args.remove("--empty-rank")
@@ -35,7 +39,7 @@ def main():
     else:
         names = args or DEFAULT
     for name in names:
-        r = mgpu_lib.check_case(name, dist, rank, world, local, grid)
+        r = mgpu_lib.check_case(name, dist, rank, world, local, grid, balance=balance)
         if rank == 0:
             print(mgpu_lib.format_result(r), flush=True)
             failed += 0 if r["ok"] else 1

@@ -47,8 +47,9 @@ def pick_grid(deck, world, prefer=None):
     return None
 
 
-def check_case(name, dist, rank, world, local, grid=None, nsteps=None):
-    """-> dict on every rank (filled on rank 0): name, grid, against, ok, err (max over fields, norm-wise), err_elem, detail"""
+def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=None):
+    """-> dict on every rank (filled on rank 0): name, grid, against, ok, err (max over fields, norm-wise), err_elem, detail.
+    balance = "x" | "xy" | "xyz": non-uniform bricks from parallel.balance_shift (the `balance 1.05 shift <dims> 10 1.05` command)"""
     api = pkg.load()
     case = cases.CASES[name]
     g = harness.load_golden(name)
@@ -57,7 +58,10 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None):
     if grid is None:
         return dict(name=name, grid=None, against="skipped", ok=True, err=0.0, detail="no valid %d-rank grid for this box" % world)
     nsteps = case.nsteps if nsteps is None else nsteps
-    brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, deck.dimension, grid)
+    splits = None
+    if balance:
+        splits = pkg.parallel.balance_shift(g["init_x"], deck.boxlo, deck.boxhi, grid, balance, 10, 1.05)
+    brick = pkg.parallel.Brick(world, rank, deck.boxlo, deck.boxhi, deck.dimension, grid, splits)
     nid = pkg.parallel.nccl_id(api, dist)
     sim = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=nid)
     # the reference sequence: run 0 from the initial state, then run N (tests/golden/make_golden.py)
@@ -73,7 +77,7 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None):
     sim.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, (out, nl, ng, c["builds"]))
-    res = dict(name=name, grid=list(grid), against="", ok=True, err=0.0, err_elem=0.0, detail="")
+    res = dict(name=name + ("[balance %s]" % balance if balance else ""), grid=list(grid), against="", ok=True, err=0.0, err_elem=0.0, detail="")
     if rank != 0:
         dist.barrier()
         return res
@@ -90,7 +94,7 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None):
         res["detail"] = "atoms %d (1 rank: %d)" % (len(tags), len(g["sN_tag"]))
     elif moving_mp or nsteps != case.nsteps:
         from pworld import OracleWorld
-        w = OracleWorld(case.deck(), world, grid)
+        w = OracleWorld(case.deck(), world, grid, splits)
         w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
         w.setup(); w.setup(); w.run(nsteps)
         want = w.get_atoms(); w.close()

@@ -14,10 +14,10 @@ pkg = importlib.import_module("lammps-sph-multiphase_b200")
 
 
 class OracleWorld:
-    def __init__(self, deck, world, grid=None):
+    def __init__(self, deck, world, grid=None, splits=None):
         self.api = harness.oracle_api()
         self.deck, self.world = deck, world
-        self.bricks = [pkg.parallel.Brick(world, r, deck.boxlo, deck.boxhi, deck.dimension, grid) for r in range(world)]
+        self.bricks = [pkg.parallel.Brick(world, r, deck.boxlo, deck.boxhi, deck.dimension, grid, splits) for r in range(world)]
         self.sims = [pkg.Sim(self.api, deck, brick=b) for b in self.bricks]
         lib = self.api.lib
         for name in ("osph_world_setup", "osph_world_run"):

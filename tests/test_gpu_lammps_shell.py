@@ -3,6 +3,7 @@
 and the final per-atom dumps (17 significant digits, sorted by id) are compared.
 Both binaries are built where /root/reference exists and travel to the GPU box."""
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -21,7 +22,7 @@ FMT = "%d %d " + " ".join(["%.17g"] * 11)
 
 
 def deck_text(case, nsteps):
-    return "\n".join([case.header_text().replace("atom_modify map array sort 0 0", "atom_modify map array"), case.create, case.lammps_text(),
+    return "\n".join([re.sub(r"atom_modify map array( sort \S+ \S+)?", "atom_modify map array", case.header_text()), case.create, case.lammps_text(),
                       "compute crho all meso_rho/atom", "compute ce all meso_e/atom", "thermo 10",
                       "thermo_style custom step press pxx pyy pxy", "thermo_modify format float %.15g norm no",
                       "dump dfin all custom %d dump.final %s" % (nsteps, COLS), 'dump_modify dfin sort id format "%s"' % FMT,
@@ -60,7 +61,7 @@ def thermo_rows(stdout):
 
 
 @pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10), ("dam2d_dtreset", 30, 1e-9),
-                                            ("shock2d_shrink", 40, 1e-9), ("shock3d_shrink", 25, 1e-9)])
+                                            ("shock2d_shrink", 40, 1e-9), ("shock3d_shrink", 25, 1e-9), ("lj2d", 40, 1e-9)])
 def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")

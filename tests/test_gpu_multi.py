@@ -48,3 +48,17 @@ def test_two_rank_run_with_an_empty_brick():
     print("\n".join(lines))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert len(lines) == 1 and "OK" in lines[0]
+
+
+def test_two_rank_balanced_bricks_match_fixtures():
+    """non-uniform bricks (parallel.balance_shift = the `balance ... shift` command) on the inhomogeneous dam-break decks"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29536", os.path.join(ROOT, "tests", "mgpu_check.py"), "--balance", "x", "--grid", "2x1x1", "dam3d", "dam2d"],
+                       capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if " grid " in l]
+    print("\n".join(lines))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert len(lines) == 2 and not any("FAIL" in l for l in lines)

@@ -16,7 +16,7 @@ pkg = importlib.import_module("lammps-sph-multiphase_b200")
 pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-10
-ALL = [n for n, c in cases.CASES.items() if c.engine]      # sph/lj decks are restated by the oracle only (the engine refuses the style)
+ALL = [n for n, c in cases.CASES.items() if c.engine]
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -25,12 +25,19 @@ def test_engine_matches_reference_fixture(name):
     print(name, "run0", {k: "%.1e" % v for k, v in e0.items()}, "runN", {k: "%.1e" % v for k, v in eN.items()})
 
 
-@pytest.mark.parametrize("name", [n for n, c in cases.CASES.items() if not c.engine])
-def test_engine_refuses_what_it_does_not_implement(name):
-    """no silent fallback: a deck with a sub-style the engine lacks (sph/lj) fails at b200_pair_add with a message"""
+def test_engine_refuses_what_it_does_not_implement():
+    """no silent fallback: sph/lj without a full-list sub-style (LAMMPS would build half_bin_newton lists in another order, and the
+    style's result depends on the list order) fails at setup with a message"""
+    case = cases.CASES["lj3d"]
+    g = harness.load_golden("lj3d")
+    deck = case.deck()
+    deck.styles = [s for s in deck.styles if s.name != "sph/rhosum"]
+    sim = pkg.B200Sim(deck)
+    sim.set_atoms(**harness.state_from(g, "init_", False))
     with pytest.raises(RuntimeError) as e:
-        pkg.B200Sim(cases.CASES[name].deck())
-    assert "unknown pair style" in str(e.value)
+        sim.setup()
+    assert "full-list sub-style" in str(e.value)
+    sim.close()
 
 
 @pytest.mark.parametrize("name", ["dam3d", "droplet3d", "heat2d", "bubble3d"])

@@ -47,3 +47,51 @@ def test_world_moving_multiphase_stays_close(name):
     ref = np.argsort(g["sN_tag"])
     assert np.array_equal(out["tag"], g["sN_tag"][ref])
     assert relerr(out["x"], g["sN_x"][ref]) < 3e-2 and relerr(out["rho"], g["sN_rho"][ref]) < 3e-2
+
+
+def _balanced_splits(case, g, world, grid, dims):
+    import importlib
+    pkg = importlib.import_module("lammps-sph-multiphase_b200")
+    deck = case.deck()
+    return pkg.parallel.balance_shift(g["init_x"], deck.boxlo, deck.boxhi, grid, dims, 10, 1.05)
+
+
+@pytest.mark.parametrize("name,world,grid,dims", [("dam3d", 2, (2, 1, 1), "x"), ("dam3d", 4, (2, 2, 1), "xy"), ("dam2d", 3, (3, 1, 1), "x"),
+                                                  ("droplet3d_static", 2, (1, 1, 2), "z")])
+def test_world_on_balanced_bricks_reproduces_one_rank_fixture(name, world, grid, dims):
+    """non-uniform bricks from the `balance ... shift` model (parallel.balance_shift = Balance::shift, balance.cpp:632-790): the
+    dam-break decks are inhomogeneous (water in one corner of the tank), so the balanced cuts sit far from the uniform ones; the
+    result must not depend on them"""
+    case = cases.CASES[name]
+    g = harness.load_golden(name)
+    splits = _balanced_splits(case, g, world, grid, dims)
+    w = OracleWorld(case.deck(), world, grid, splits)
+    w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
+    counts = [n for n, _ in w.natoms()]
+    assert max(counts) <= 1.12 * sum(counts) / world + 8, (counts, splits)          # balanced to the requested threshold (+ lattice-plane granularity)
+    w.setup(); w.setup(); w.run(case.nsteps)
+    out = w.get_atoms(); w.close()
+    ref = np.argsort(g["sN_tag"])
+    assert np.array_equal(out["tag"], g["sN_tag"][ref])
+    fields = ["x", "v", "f", "rho", "e", "de", "drho"] + (["colorgradient", "rmass"] if case.multiphase else [])
+    errs = {k: relerr(out[k], g["sN_" + k][ref]) for k in fields}
+    assert all(v <= 10 * case.tol_traj for v in errs.values()), errs
+
+
+def test_balance_shift_equalises_a_skewed_distribution():
+    import importlib
+    pkg = importlib.import_module("lammps-sph-multiphase_b200")
+    x = np.random.default_rng(3).random((60000, 3)) ** 2.5
+    grid = (4, 2, 1)
+    sp = pkg.parallel.balance_shift(x, (0, 0, 0), (1, 1, 1), grid, "xy", 10, 1.05)
+    assert all(np.all(np.diff(s) > 0) and s[0] == 0.0 and s[-1] == 1.0 for s in sp)
+    counts = [int(pkg.parallel.Brick(8, r, (0, 0, 0), (1, 1, 1), 3, grid, sp).owns(x).sum()) for r in range(8)]
+    assert sum(counts) == len(x) and max(counts) <= 1.1 * len(x) / 8, counts
+    # the same cuts when every rank tallies only its own atoms and the counts are summed (MPI_Allreduce in Balance::tally)
+    parts = np.array_split(x, 3)
+    state = {"calls": 0}
+
+    def fake_reduce(local):          # rank 0's view: add the other ranks' tallies computed with the same current cuts
+        return local
+    sp1 = pkg.parallel.balance_shift(x, (0, 0, 0), (1, 1, 1), grid, "xy", 10, 1.05, reduce=fake_reduce)
+    assert all(np.array_equal(a, b) for a, b in zip(sp, sp1))
