@@ -481,21 +481,30 @@ def main():
         h2d = sum(v.nbytes for v in pinned.values())
         nid2 = pkg.parallel.nccl_id(pkg.load(), dist) if world > 1 else None
         sim2 = pkg.B200Sim(deck, device=local, brick=brick, nccl_id=nid2)
-        sim2.set_atoms(**pinned); sim2.setup(); sim2.run(2); sim2.get_atoms(out_names); sim2.sync()   # warm allocations
+        # result buffers are the caller's pinned arrays too (the LAMMPS shell hands the engine its own atom arrays);
+        # sized with head room for atoms that migrate in (N > 1)
+        cap = int(n * 1.25) + 1024
+        outbuf = {k: torch.empty((cap, 3) if k in ("x", "v", "vest", "f") else (cap,), dtype=torch.float64).pin_memory().numpy() for k in out_names}
+        sim2.set_atoms(**pinned); sim2.setup(); sim2.run(2); sim2.get_atoms(out_names, out=outbuf); sim2.sync()   # warm allocations
         barrier()
         t0 = time.perf_counter()
         sim2.set_atoms(**pinned)
         sim2.setup()
         sim2.run(args.steps)
-        res = sim2.get_atoms(out_names)
+        res = sim2.get_atoms(out_names, out=outbuf)
         sim2.sync()
         t_e2e = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([t_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); t_e2e = float(t.item())
         d2h = sum(v.nbytes for v in res.values())
+        # where the end-to-end time goes: the same sequence once more with a stream synchronisation after every call (untimed above)
+        parts = {}
+        for nm, fn in (("set_atoms", lambda: sim2.set_atoms(**pinned)), ("setup", sim2.setup), ("run", lambda: sim2.run(args.steps)),
+                       ("get_atoms", lambda: sim2.get_atoms(out_names, out=outbuf))):
+            t1 = time.perf_counter(); fn(); sim2.sync(); parts[nm] = round(time.perf_counter() - t1, 5)
         e2e = {"value": ntot * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "mode": "pinned host arrays -> b200_set_atoms + b200_setup + b200_run(K) + b200_get_atoms (one host round trip per K-step run, setup included)",
-               "seconds": t_e2e}
+               "mode": "pinned host arrays -> b200_set_atoms + b200_setup + b200_run(K) + b200_get_atoms -> pinned host arrays (one host round trip per K-step run, setup included)",
+               "seconds": t_e2e, "breakdown_s": parts}
         sim2.close()
 
     # ---- roofline of the dominant kernel (fused force pass, k_force<K_TAIT>) ----

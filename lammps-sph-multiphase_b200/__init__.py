@@ -15,7 +15,8 @@ from .engine import Sim
 from . import parallel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200sph.so")
+# B200_LIB: another build of the same sources (A/B measurements of compile-time variants, tools/gpu_*.sh); not a fallback
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "csrc", "libb200sph.so")
 _api = None
 
 

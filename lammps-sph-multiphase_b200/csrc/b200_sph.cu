@@ -149,7 +149,7 @@ struct b200_sph {
   double *d_dt = nullptr;
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
-  int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
+  int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2, tile_fsplit = 2;
   DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
   int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
   // halo overlap (single-phase tile path): tiles [0, nint) neither read ghosts nor feed a send list and run while the halo flies
@@ -908,7 +908,7 @@ static void build_plan(b200_sph *h)
       bool fluid = (p.kinds & (K_TAIT | K_MORRIS | K_IDEAL)) != 0, heat = (p.kinds & K_HEAT) != 0;
       np = std::max(np, fluid ? (heat ? 5 : 4) : 3); nk = std::max(nk, (fluid ? 1 : 0) + (heat ? 1 : 0));
     } else if (h->multiphase && !(p.kinds & ~MPK)) {
-      int mask = 0x03 | ((p.kinds & K_TAITMP) ? 0x1c : 0) | ((p.kinds & K_SURF) ? 0x70 : 0) | ((p.kinds & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
+      int mask = 0x03 | ((p.kinds & K_TAITMP) ? 0x1c : 0) | ((p.kinds & K_SURF) ? (h->g.dim == 3 ? 0x160 : 0x60) : 0) | ((p.kinds & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
       np = std::max(np, __builtin_popcount(mask));
       nk = std::max(nk, ((p.kinds & K_TAITMP) ? 1 : 0) + ((p.kinds & K_SURF) ? 1 : 0) + ((p.kinds & (K_HEATMP | K_HEATPC)) ? 1 : 0));
     } else { ok = false; break; }
@@ -919,6 +919,7 @@ static void build_plan(b200_sph *h)
   if (const char *e = getenv("B200_TILE_SLOTCAP")) h->tile_slotcap = std::max(2, std::min(h->tile_slotcap, atoi(e)) & ~1);   // tests: force small tiles / the row-path fall-back
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
   if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
+  if (const char *e = getenv("B200_FORCE_SPLIT")) h->tile_fsplit = atoi(e);
 }
 
 static PairArgs pair_args(b200_sph *h)
@@ -1029,6 +1030,8 @@ template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &
   if (h->vir_now && F) {            // thermo step: the instantiation that also sums the rows' virial
     if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
     else launch_tiles(h, k_tile_force<KINDS, 2, false, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
+  } else if (h->tile_fsplit == 4 && uni) {
+    launch_tiles(h, k_tile_force<KINDS, 4, true, false>, "k_tile_force", TILE_ROWS * 4, smem, A, A.ntiles, reserve);
   } else if (h->tile_split == 1) {
     if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
     else launch_tiles(h, k_tile_force<KINDS, 1, false, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
@@ -1040,9 +1043,9 @@ template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &
 static int tile_records_mp(b200_sph *h, int mode, const PairTab *fluid)
 {
   int na = h->nall(), pstride = (na + 7) & ~7;
-  h->trec.ensure((size_t)pstride * (mode ? 8 : 2));
+  h->trec.ensure((size_t)pstride * (mode ? TILE_MP_NPART : 2));
   OwnedSet &c = h->C();
-  TileRecMpArgs R{h->nlocal, na, pstride, mode, h->gorder.p, c.xt.p, c.vr.p, c.cgm.p, c.e.p, c.cv.p, fluid, h->trec.p};
+  TileRecMpArgs R{h->nlocal, na, pstride, mode, h->g.dim, h->gorder.p, c.xt.p, c.vr.p, c.cgm.p, c.e.p, c.cv.p, fluid, h->trec.p};
   LAUNCH(h, k_tile_records_mp, nblk(na, 256), 256, R);
   return pstride;
 }
@@ -1063,9 +1066,8 @@ static bool tile_uni_geo(const b200_sph *h, const PairTab &T, TileUni &U)
 }
 template <int KINDS> static void launch_tile_force_mp(b200_sph *h, TileArgs &A, bool gu)
 {
-  using MP = MpParts<KINDS>;
-  size_t smem = TileSmem<MP::n, MP::nk>::bytes(h->tile_cap);
   const bool d3 = h->g.dim == 3 || !(KINDS & K_SURF);
+  size_t smem = d3 ? TileSmem<MpParts<KINDS, true>::n, MpParts<KINDS, true>::nk>::bytes(h->tile_cap) : TileSmem<MpParts<KINDS, false>::n, MpParts<KINDS, false>::nk>::bytes(h->tile_cap);
   for (int set = 0; set < 2; set++) {          // owned rows, then the ghost rows
     int nt = set ? h->ngtiles : h->ntiles;
     if (set) { A.tiles = h->gtiles.p; A.ntiles = h->ngtiles; }

@@ -39,6 +39,7 @@
 #define TILE_SLOT_BITS 13
 #define TILE_SLOT_MASK 0x1fffu
 #define TILE_MAXSLOTS 8190
+#define TILE_MP_NPART 9           // record parts of the multiphase force pass (P0..P8, see k_tile_records_mp)
 #define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
 // multiphase entries carry two more flags (their records are 64-128 B, so a tile never holds more than 2047 slots):
 //   [15:13] type of j | [12] the row particle is the reference's "i" of the pair (half-list owner, frozen at build time)
@@ -159,30 +160,50 @@ struct TileBuildArgs {
 
 // 8 entries of a row are one uint4 (16 bits each: [15:13] type of j, [12:0] slot; 0 = empty); group g of row r sits at
 // [((r >> 5) * ngrp + g) * 32 + (r & 31)], so a warp of consecutive rows reads one group of each of its rows as 512 contiguous bytes.
+// The 8 entries of a group travel through a 128-bit shift register (4 funnel shifts per entry): entry k of a group ends up at
+// element k after 8 pushes; finish() shifts a partial group the rest of the way with zeros.
 struct RowWriter {
-  uint4 acc; int n;
-  __device__ __forceinline__ RowWriter() : acc(make_uint4(0, 0, 0, 0)), n(0) {}
+  unsigned x, y, z, w; int n;
+  __device__ __forceinline__ RowWriter() : x(0), y(0), z(0), w(0), n(0) {}
+  __device__ __forceinline__ void shift(unsigned ent)
+  {
+    x = __funnelshift_r(x, y, 16); y = __funnelshift_r(y, z, 16); z = __funnelshift_r(z, w, 16); w = __funnelshift_r(w, ent, 16);
+  }
   __device__ __forceinline__ void push(unsigned ent, uint4 *base, int ngrp)
   {
-    const unsigned v = ent << ((n & 1) * 16); const int w = (n & 7) >> 1;
-    acc.x |= w == 0 ? v : 0u; acc.y |= w == 1 ? v : 0u; acc.z |= w == 2 ? v : 0u; acc.w |= w == 3 ? v : 0u;
-    if ((n & 7) == 7) { if ((n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; acc = make_uint4(0, 0, 0, 0); }
+    shift(ent);
+    if ((n & 7) == 7 && (n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = make_uint4(x, y, z, w);
     n++;
   }
-  __device__ __forceinline__ void finish(uint4 *base, int ngrp) { if ((n & 7) && (n >> 3) < ngrp) base[(size_t)(n >> 3) * 32] = acc; }
+  __device__ __forceinline__ void finish(uint4 *base, int ngrp)
+  {
+    if (!(n & 7) || (n >> 3) >= ngrp) return;
+    for (int k = n & 7; k < 8; k++) shift(0u);
+    base[(size_t)(n >> 3) * 32] = make_uint4(x, y, z, w);
+  }
 };
 // the same from the back of the row: entry k at element 7 - (k & 7) of group ngrp - 1 - (k >> 3)  (the mid zone shares the far array)
 struct RowWriterBack {
-  uint4 acc; int n;
-  __device__ __forceinline__ RowWriterBack() : acc(make_uint4(0, 0, 0, 0)), n(0) {}
+  unsigned x, y, z, w; int n;
+  __device__ __forceinline__ RowWriterBack() : x(0), y(0), z(0), w(0), n(0) {}
+  __device__ __forceinline__ void shift(unsigned ent)
+  {
+    w = __funnelshift_l(z, w, 16); z = __funnelshift_l(y, z, 16); y = __funnelshift_l(x, y, 16); x = (x << 16) | ent;
+  }
   __device__ __forceinline__ void push(unsigned ent, uint4 *base, int ngrp)
   {
-    const int e = 7 - (n & 7); const unsigned v = ent << ((e & 1) * 16); const int w = e >> 1;
-    acc.x |= w == 0 ? v : 0u; acc.y |= w == 1 ? v : 0u; acc.z |= w == 2 ? v : 0u; acc.w |= w == 3 ? v : 0u;
-    if ((n & 7) == 7) { const int g = ngrp - 1 - (n >> 3); if (g >= 0) base[(size_t)g * 32] = acc; acc = make_uint4(0, 0, 0, 0); }
+    shift(ent);
+    const int g = ngrp - 1 - (n >> 3);
+    if ((n & 7) == 7 && g >= 0) base[(size_t)g * 32] = make_uint4(x, y, z, w);
     n++;
   }
-  __device__ __forceinline__ void finish(uint4 *base, int ngrp) { const int g = ngrp - 1 - (n >> 3); if ((n & 7) && g >= 0) base[(size_t)g * 32] = acc; }
+  __device__ __forceinline__ void finish(uint4 *base, int ngrp)
+  {
+    const int g = ngrp - 1 - (n >> 3);
+    if (!(n & 7) || g < 0) return;
+    for (int k = n & 7; k < 8; k++) shift(0u);
+    base[(size_t)g * 32] = make_uint4(x, y, z, w);
+  }
 };
 
 // Near rows are written in a bank-aware order.  The stage kernels read a neighbor's record parts with 128-bit LDS, served per
@@ -240,14 +261,13 @@ __device__ __forceinline__ int tile_slot_src(const TileDesc &D, int slot, int nl
 }
 
 // the exact pair test of Neighbor::full_bin (neigh_full.cpp:241-340) as k_build restates it: 0 = not a neighbor, 1 = near row, 2 = far row
-__device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int j)
+template <bool UNI> __device__ __forceinline__ int tile_exact_class(const TileBuildArgs &A, const double4 pi, const double4 pj)
 {
   const Geom &g = A.g;
-  const double4 pi = A.xt[i], pj = A.xt[j];
   const unsigned long long wi = (unsigned long long)__double_as_longlong(pi.w), wj = (unsigned long long)__double_as_longlong(pj.w);
   const double rsq = rsq_nofma(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
   const int tij = tw_type(wi) * MAXT1 + tw_type(wj);
-  if (!(rsq <= A.cutneighsq[tij])) return 0;
+  if (!(rsq <= (UNI ? A.cutsq_u : A.cutneighsq[tij]))) return 0;       // UNI: the one threshold of every type pair travels as a kernel parameter
   const double cutmaxsq = g.cutneighmaxsq;
   if (rsq >= cutmaxsq * (1.0 - 1.0e-9)) {          // the reference's own bin stencil (neigh_stencil.cpp:434-448), see k_build
     int dbx = abs(tw_bx(wj) - tw_bx(wi)), dby = abs(tw_by(wj) - tw_by(wi)), dbz = abs(tw_bz(wj) - tw_bz(wi));
@@ -255,7 +275,7 @@ __device__ __noinline__ int tile_exact_class(const TileBuildArgs &A, int i, int 
     double ex = dbx ? (dbx - 1) * g.binsize[0] : 0.0, ey = dby ? (dby - 1) * g.binsize[1] : 0.0, ez = dbz ? (dbz - 1) * g.binsize[2] : 0.0;
     if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) return 0;
   }
-  return rsq >= A.farsq[tij] ? 2 : 1;
+  return rsq >= (UNI ? A.farsq_u : A.farsq[tij]) ? 2 : 1;
 }
 
 // One CTA per tile.  Candidate positions are staged as fp32 offsets from the tile's corner; every (row, candidate) pair is decided in
@@ -414,18 +434,39 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
             in &= vm; mb &= vm;
             unsigned border = UNI ? (mb ^ in) : mb;                  // per-type thresholds: classify every coarse hit
             if (!UNI) in = 0;
-            while (border) {
+            if (UNI && border) {
+              // band pairs take the fp64 test on the particles' own coordinates (global memory).  On a lattice whole shells of
+              // neighbors sit exactly on the cutoff and land here (profiles/r02_mpbuild_lines.txt: 28 % of the samples of the C3
+              // build, all of them waiting for these loads), so the next pair's coordinates are fetched while this one is decided.
+              if (!(MP || gt)) pI = A.xt[dev];
+              int idx = __ffs((int)border) - 1; border &= border - 1;
+              double4 pj = A.xt[dev_of(bj + idx)];
+              for (;;) {
+                const int cur = idx; const double4 pc = pj;
+                const bool more = border != 0;
+                if (more) { idx = __ffs((int)border) - 1; border &= border - 1; pj = A.xt[dev_of(bj + idx)]; }
+                const int cls = tile_exact_class<true>(A, pI, pc);
+                if (cls) in |= 1u << cur;
+                if (cls == 2) fr |= 1u << cur; else fr &= ~(1u << cur);
+                if (cls == 3) md |= 1u << cur; else md &= ~(1u << cur);
+                if (!more) break;
+              }
+            }
+            while (!UNI && border) {
               const int idx = __ffs((int)border) - 1; border &= border - 1;
               const int slot = bj + idx;
               int cls = -1;
-              if (!UNI) {
+              {
                 const float dx = xi - fx[slot], dy = yi - fy[slot], dz = zi - fz[slot];
                 const float rsq = dx * dx + dy * dy + dz * dz;
                 const float *th = s_thr[ti * MAXT1 + ty[slot]];
                 if (rsq >= th[3]) cls = 0;                         // surely outside the neighbor cutoff
                 else if (rsq < th[2]) cls = rsq >= th[1] ? 2 : (rsq >= th[5] ? 3 : 1);    // surely inside: far / mid zone only if surely beyond that threshold
               }
-              if (cls < 0) cls = tile_exact_class(A, dev, dev_of(slot));
+              if (cls < 0) {
+                if (!(MP || gt)) pI = A.xt[dev];
+                cls = tile_exact_class<false>(A, pI, A.xt[dev_of(slot)]);
+              }
               if (cls) in |= 1u << idx;
               if (cls == 2) fr |= 1u << idx; else fr &= ~(1u << idx);
               if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
@@ -654,7 +695,7 @@ template <int PM, int NK, int NT> struct TileLoop {
       if (n > 0) {
         int q = 0;
 #pragma unroll
-        for (int p = 0; p < 8; p++)
+        for (int p = 0; p < TILE_MP_NPART; p++)
           if (PM & (1 << p)) { bulk_g2s(S.part + (size_t)q * A.cap + s0, A.rec + (size_t)p * A.pstride + D.seg_src[s], (unsigned)n * 16u, S.bar); q++; }
       }
     }
@@ -664,8 +705,9 @@ template <int PM, int NK, int NT> struct TileLoop {
     int t = 0;
     if (lane == 0) { t = atomicAdd(A.counter, 1); S.tile[slot] = t; }
     t = __shfl_sync(FULLMASK, t, 0);
-    if (t < ntiles)
+    if (t < ntiles) {
       for (int k = lane; k < (int)(sizeof(TileDesc) / 4); k += 32) ((int *)(S.D + slot))[k] = ((const int *)(A.tiles + t))[k];
+    }
   }
   __device__ __forceinline__ void start()
   {
@@ -912,23 +954,39 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
             const double rhoj = qb.y;
             if (UNI) {
               const double rsq = rsq_fma(dx, dy, dz);
-              const double r = fast_sqrt13(rsq);                              // NaN for coincident particles: masked by dpos()
+              // r = sqrt(rsq) to ~1e-13 (fast_sqrt13).  The MUFU seed is clamped to a finite value and halved on the integer
+              // pipe, so coincident particles give r = 0 (not 0 * inf) and flow through the formulas as in the reference,
+              // which has no division by r either
+              double y;
+              asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
+              const int yhi = min(__double2hiint(y), 0x7fe00000);
+              y = __hiloint2double(yhi, 0);                                   // (the seed's low word is zero)
+              const double g = rsq * y;
+              const double r = fma(g, fma(-__hiloint2double(yhi - 0x00100000, 0), g, 0.5), g);
               if (HAS_FLUID) {
-                const bool hit = (rsq < UF.cutsq) & ((maskf >> tj) & 1u) & dpos(rsq);
+                // inside the cutoff <=> h - r >= 0, read off the sign bit (integer pipe; cut = h for these styles and the
+                // weight (h - r)^2 vanishes there, so a pair within rounding of the cutoff adds ~1e-26 h^2 either way)
+                const double hr = UF.h - r;
+                const int hit = (~__double2hiint(hr) >> 31) & (int)(maskf >> tj) & 1;
                 const double2 qc = P2[slot], qd = P3[slot];
-                double wfd = UF.h - r; wfd = wfd * wfd;                       // Lucy (dW/dr)/r = c0 (h - r)^2  (:135-151), c0 folded into the constants
+                double wfd = hr * hr;                                         // Lucy (dW/dr)/r = c0 (h - r)^2  (:135-151), c0 folded into the constants
                 wfd = hit ? wfd : 0.0;
                 const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
                 const double dvdr = dx * dvx + dy * dvy + dz * dvz;
                 if (KINDS & (K_TAIT | K_IDEAL)) {
                   // sph/idealgas: the sound speeds are per particle, c = sqrt(0.4 e / m) = sqrt((p/rho^2) rho)
                   const double vch = (KINDS & K_IDEAL) ? u_vci * (ci + fast_sqrt(fmax(qd.y * rhoj, 0.0))) : u_vch;
-                  double fvisc = fast_div15(vch * dvdr, (rsq + u_eta) * (rhoi + rhoj));   // Monaghan artificial viscosity (:163-169)
-                  fvisc = dvdr < 0.0 ? fvisc : 0.0;
-                  const double fpair = u_k1 * (d.y + qd.y + fvisc) * wfd;     // -m m c0 (...) (h - r)^2
-                  fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                  // Monaghan artificial viscosity (:163-169), only for approaching pairs (sign bit of dvdr, integer pipe)
+                  double nv = vch * dvdr;
+                  nv = __double2hiint(dvdr) < 0 ? nv : 0.0;
+                  const double den = (rsq + u_eta) * (rhoi + rhoj);
+                  double yr;
+                  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(den));
+                  yr = fma(yr, fma(-den, yr, 1.0), yr);                       // one Newton step on the MUFU seed: ~1e-13, as the sqrt above
+                  const double fpair = fma(nv, yr, d.y + qd.y) * wfd;         // x -m m c0 after the loop
+                  fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
                   if (VIR) vir(dx, dy, dz, dx * fpair, dy * fpair, dz * fpair);
-                  u_de += fpair * dvdr;                                       // x -0.5 at the end
+                  u_de = fma(fpair, dvdr, u_de);                              // x -0.5 (-m m c0) at the end
                 } else {                                                      // Morris viscosity (morris :165-176)
                   const double fvisc = fast_div(u_k2 * wfd, rhoi * rhoj);     // 2 mu m m c0 (h - r)^2 / (rho_i rho_j)
                   const double fpair = u_k1 * (d.y + qd.y) * wfd;
@@ -936,11 +994,12 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
                   if (VIR) vir(dx, dy, dz, dx * fpair + dvx * fvisc, dy * fpair + dvy * fvisc, dz * fpair + dvz * fvisc);
                   u_de += fpair * dvdr + fvisc * (dvx * dvx + dvy * dvy + dvz * dvz);
                 }
-                u_drho += dvdr * wfd;                                         // x m c0 at the end
+                u_drho = fma(dvdr, wfd, u_drho);                              // x m c0 at the end
               }
               if (HAS_HEAT) {
-                const bool hit = (rsq < UH.cutsq) & ((maskh >> tj) & 1u) & dpos(rsq);
-                double wfd = UH.h - r; wfd = wfd * wfd;
+                double wfd = UH.h - r;
+                const int hit = (~__double2hiint(wfd) >> 31) & (int)(maskh >> tj) & 1;
+                wfd = wfd * wfd;
                 wfd = hit ? wfd : 0.0;
                 const double ej = PEp[slot].x;
                 // 2 mi mj/(mi+mj) (rho_i+rho_j)/(rho_i rho_j) D (e_i - e_j) W'/r  (:122-125), one division
@@ -997,7 +1056,13 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
           }
         }
       }
-      if (UNI) { adrho = u_k3 * u_drho; ade = -0.5 * u_de + u_heat * u_deh; }
+      if (UNI) {
+        if (KINDS & (K_TAIT | K_IDEAL)) {                                       // the pair sums above are without the factor -m m c0
+          fx *= u_k1; fy *= u_k1; fz *= u_k1; u_de *= u_k1;
+          if (VIR) { w0 *= u_k1; w1 *= u_k1; w2 *= u_k1; w3 *= u_k1; w4 *= u_k1; w5 *= u_k1; }
+        }
+        adrho = u_k3 * u_drho; ade = -0.5 * u_de + u_heat * u_deh;
+      }
 #pragma unroll
       for (int o = lpw; o < 32; o <<= 1) {
         fx += __shfl_xor_sync(FULLMASK, fx, o); fy += __shfl_xor_sync(FULLMASK, fy, o); fz += __shfl_xor_sync(FULLMASK, fz, o);
@@ -1025,10 +1090,15 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
 
 // ======================================================================= multiphase styles on tiles ====
 // Record parts (tile order, ghosts keep their possibly one-step-stale rho / colorgradient):
-//   P0 x,y   P1 z,rho   P2 vest.x,vest.y   P3 vest.z, pressure   P4 V^2 = (m/rho)^2, T = e/cv   P5 cg.x,cg.y   P6 cg.z, 1/|cg| or 0   P7 m,0
+//   P0 x,y   P1 z,rho   P2 vest.x,vest.y   P3 vest.z, pressure   P4 V^2 = (m/rho)^2, T = e/cv   P7 m,0
+//   P5 Axx,Ayy   P6 Axy,Azz   P8 Axz,Ayz (3-D)      A = V^2 Pi, the particle's surface stress
 // colorgradient pass: P0 x,y   P1 z, V^2
+// PairSPHSurfaceTension::compute (pair_sph_surfacetension.cpp:140-169) spells out, pair by pair, the product of the unit vector e_ij
+// with Pi = (|c|^2 / d  I - c (x) c) / |c|  (c = colorgradient, d = dimension, Pi = 0 where |c| <= EPSILON) of either particle and adds
+// (Pi_i e V_i^2 + Pi_j e V_j^2) dW/dr.  Pi depends on one particle only, so it is formed once per particle here and the pair loop is
+// left with (A_i + A_j) e: 19 fp64 instructions per pair instead of 72 (profiles/r02_mpforce_*: the pass is bound by the fp64 pipe).
 struct TileRecMpArgs {
-  int nlocal, nall, pstride, mode;       // mode 0: colorgradient records, 1: force records
+  int nlocal, nall, pstride, mode, dim;  // mode 0: colorgradient records, 1: force records
   const int *gorder; const double4 *xt, *vr, *cgm; const double *e, *cv; const PairTab *fluid;
   double2 *rec;
 };
@@ -1045,38 +1115,55 @@ __global__ void k_tile_records_mp(TileRecMpArgs A)
   int t = tw_type(__double_as_longlong(x.w));
   // pair_sph_taitwater_multiphase.cpp:289-292
   double P = A.fluid ? A.fluid->B[t] * (pow(rho / A.fluid->rho0[t], A.fluid->gamma[t]) - A.fluid->rb[t]) : 0.0;
-  double a = sqrt(c.x * c.x + c.y * c.y + c.z * c.z);
   A.rec[ps + i] = make_double2(x.z, rho);
   A.rec[2 * ps + i] = make_double2(v.x, v.y);
   A.rec[3 * ps + i] = make_double2(v.z, P);
   A.rec[4 * ps + i] = make_double2(V * V, A.e[src] / A.cv[src]);
-  A.rec[5 * ps + i] = make_double2(c.x, c.y);
-  A.rec[6 * ps + i] = make_double2(c.z, a > EPSILON_CG ? 1.0 / a : 0.0);
   A.rec[7 * ps + i] = make_double2(c.w, 0.0);
+  const double cxx = c.x * c.x, cyy = c.y * c.y, czz = c.z * c.z;
+  if (A.dim == 3) {                      // (:153-169)
+    const double o3 = 0.3333333333333333, t3 = 0.6666666666666666;
+    const double a = sqrt(cxx + cyy + czz), s = (a > EPSILON_CG ? 1.0 / a : 0.0) * (V * V);
+    A.rec[5 * ps + i] = make_double2((o3 * czz + o3 * cyy - t3 * cxx) * s, (o3 * czz - t3 * cyy + o3 * cxx) * s);
+    A.rec[6 * ps + i] = make_double2(-(c.x * c.y) * s, (-t3 * czz + o3 * cyy + o3 * cxx) * s);
+    A.rec[8 * ps + i] = make_double2(-(c.x * c.z) * s, -(c.y * c.z) * s);
+  } else {                               // (:140-151): the 2-D norm and trace
+    const double a = sqrt(cxx + cyy), s = (a > EPSILON_CG ? 1.0 / a : 0.0) * (V * V), h2 = (cyy + cxx) / 2;
+    A.rec[5 * ps + i] = make_double2((h2 - cxx) * s, (h2 - cyy) * s);
+    A.rec[6 * ps + i] = make_double2(-(c.x * c.y) * s, 0.0);
+  }
 }
 
 // branch-free quintic spline (sph_kernel_quintic.cpp:17-73, argument q = 3 r / h, without the norm): the clamped form
 // max(3-q,0)^5 - 6 max(2-q,0)^5 + 15 max(1-q,0)^5 is the same piecewise polynomial as quintic_w / quintic_dw
+// max(x, 0) on the integer pipe (the fp64 pipe is what binds these kernels): the sign bit masks both words
+__device__ __forceinline__ double dclamp0(double x)
+{
+  const int hi = __double2hiint(x), m = ~(hi >> 31);
+  return __hiloint2double(hi & m, __double2loint(x) & m);
+}
 __device__ __forceinline__ double quintic_w_bf(double q)
 {
-  const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);
+  const double a = dclamp0(3.0 - q), b = dclamp0(2.0 - q), c = dclamp0(1.0 - q);
   const double a2 = a * a, b2 = b * b, c2 = c * c;
   return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a * (a2 * a2)));
 }
-__device__ __forceinline__ double quintic_dw_bf(double q)
+// dW/dq / (-5) = max(3-q,0)^4 - 6 max(2-q,0)^4 + 15 max(1-q,0)^4: the callers fold the factor -5 into their constants
+__device__ __forceinline__ double quintic_dw5_bf(double q)
 {
-  const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);
+  const double a = dclamp0(3.0 - q), b = dclamp0(2.0 - q), c = dclamp0(1.0 - q);
   const double a2 = a * a, b2 = b * b, c2 = c * c;
-  return fma(-75.0 * c2, c2, fma(30.0 * b2, b2, -5.0 * (a2 * a2)));
+  return fma(15.0 * c2, c2, fma(-6.0 * b2, b2, a2 * a2));
 }
+__device__ __forceinline__ double quintic_dw_bf(double q) { return -5.0 * quintic_dw5_bf(q); }
 // r = sqrt(a) and 1/r, branch-free (see fast_sqrt); NaN / inf for a = 0, which the callers mask with dpos()
 __device__ __forceinline__ void fast_sqrt_rinv(double a, double &r, double &rinv)
-{ // one coupled Newton step from the 2^-22 seed: both results to ~1e-13 (see fast_sqrt13)
+{ // one coupled Newton step from the 2^-22 seed: both results to ~1e-13 (see fast_sqrt13); the seed is halved on the integer pipe
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double g = a * y, hh = 0.5 * y;
+  const double g = a * y, hh = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
   const double e = fma(-hh, g, 0.5);
-  r = fma(g, e, g); rinv = 2.0 * fma(hh, e, hh);
+  r = fma(g, e, g); rinv = fma(y, e, y);
 }
 
 // rows per pass and lanes per row of a 512-thread stage CTA: 256 rows x 2 lanes, or 128 rows x 4 lanes for small tiles
@@ -1184,9 +1271,11 @@ __global__ void __launch_bounds__(TILE_MP_NT, 2) k_tile_full_mp(const __grid_con
 // other side owns.  See b200_pair.cuh for the two orientation quirks that use the ownership bit.
 // The body is branch-free (predicated contributions) so that ptxas interleaves the neighbors of a group.
 // GU: every sub-style has one cutoff / one set of kernel constants for all its mapped type pairs AND all sub-styles share
-// the smoothing length (the usual deck) -> one kernel-derivative evaluation per pair on register constants.
-template <int KINDS> struct MpParts {
-  static constexpr int mask = 0x03 | ((KINDS & K_TAITMP) ? 0x1c : 0) | ((KINDS & K_SURF) ? 0x70 : 0) | ((KINDS & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
+// the smoothing length (the usual deck) -> one kernel-derivative evaluation per pair on register constants.  The cutoff of
+// these styles is the support of the spline (cut = h, fill_tab), whose clamped form is exactly 0 beyond it, so the GU body
+// needs no cutoff compare: an entry outside contributes 0.0 by itself.
+template <int KINDS, bool DIM3> struct MpParts {
+  static constexpr int mask = 0x03 | ((KINDS & K_TAITMP) ? 0x1c : 0) | ((KINDS & K_SURF) ? (DIM3 ? 0x160 : 0x60) : 0) | ((KINDS & (K_HEATMP | K_HEATPC)) ? 0x90 : 0);
   static constexpr int n = __builtin_popcount(mask);
   static constexpr int nk = ((KINDS & K_TAITMP) ? 1 : 0) + ((KINDS & K_SURF) ? 1 : 0) + ((KINDS & (K_HEATMP | K_HEATPC)) ? 1 : 0);
   __host__ __device__ static constexpr int idx(int p) { return __builtin_popcount(mask & ((1 << p) - 1)); }
@@ -1194,7 +1283,7 @@ template <int KINDS> struct MpParts {
 template <int KINDS, bool DIM3, bool GU>
 __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_constant__ TileArgs A)
 {
-  using MP = MpParts<KINDS>;
+  using MP = MpParts<KINDS, DIM3>;
   constexpr bool HAS_FLUID = (KINDS & K_TAITMP) != 0, HAS_SURF = (KINDS & K_SURF) != 0, HAS_HEAT = (KINDS & (K_HEATMP | K_HEATPC)) != 0;
   constexpr int NK = MP::nk, NP = MP::n;
   constexpr int I_FLUID = 0, I_SURF = HAS_FLUID ? 1 : 0, I_HEAT = I_SURF + (HAS_SURF ? 1 : 0);
@@ -1207,9 +1296,14 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
   if (tid == 0) mbar_init(S.bar, 1);
   const PairTab *T = S.T;
   auto part = [&](int p) { return S.part + (size_t)MP::idx(p) * A.cap; };
-  const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7);
+  const double2 *P0 = part(0), *P1 = part(1), *P2 = part(2), *P3 = part(3), *P4 = part(4), *P5 = part(5), *P6 = part(6), *P7 = part(7), *P8 = part(8);
   const int ntiles = A.ntiles, scan_far = A.scan_far[0], scan_mid = A.scan_far[2];
   const size_t ps = A.pstride;
+  // GU: q = 3 r / h and the factor -5 of the spline derivative folded into register constants
+  const double gu_q = 3.0 * A.uni[0].c1;
+  double gu_c0[3] = {0, 0, 0};
+#pragma unroll
+  for (int t = 0; t < NK; t++) gu_c0[t] = -5.0 * A.uni[t].c0;
   TileLoop<MP::mask, NK, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.peek()) {
@@ -1223,10 +1317,10 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
       const int rr = valid ? row : D.row0;
       // the row particle's own record (global, coalesced): ghost rows are not among the staged candidates
       const double2 a = A.rec[rr], b = A.rec[ps + rr];
-      double2 c = make_double2(0, 0), d = c, v4 = c, g5 = c, g6 = c;
+      double2 c = make_double2(0, 0), d = c, v4 = c, a5 = c, a6 = c, a8 = c;
       if (HAS_FLUID) { c = A.rec[2 * ps + rr]; d = A.rec[3 * ps + rr]; }
-      v4 = A.rec[4 * ps + rr];
-      if (HAS_SURF) { g5 = A.rec[5 * ps + rr]; g6 = A.rec[6 * ps + rr]; }
+      if (HAS_FLUID || HAS_HEAT) v4 = A.rec[4 * ps + rr];
+      if (HAS_SURF) { a5 = A.rec[5 * ps + rr]; a6 = A.rec[6 * ps + rr]; if (DIM3) a8 = A.rec[8 * ps + rr]; }
       const int dev = ghostrow ? A.nlocal + A.gorder[rr - A.nlocal] : rr;     // device index
       const int ti = valid ? tw_type(__double_as_longlong(A.xt[dev].w)) : 0;
       const size_t rbase = (size_t)(row >> 5) * A.ngrp * 32 + (row & 31);
@@ -1261,19 +1355,21 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
             const bool live = ghostrow | ((ent & (TMP_GHOST | TMP_OWNER)) != TMP_GHOST);
             const bool row_owns = !ghostrow & ((ent & TMP_OWNER) != 0);
             const int slot = ent & TMP_SLOT_MASK, tj = ent >> TILE_SLOT_BITS, ij = ti * MAXT1 + tj;
-            const double2 qa = P0[slot], qb = P1[slot], q4 = P4[slot];
+            const double2 qa = P0[slot], qb = P1[slot];
+            double2 q4 = make_double2(0, 0);
+            if (HAS_FLUID || HAS_HEAT) q4 = P4[slot];
             const double dx = a.x - qa.x, dy = a.y - qa.y, dz = b.x - qb.x;
             const double rsq = rsq_fma(dx, dy, dz);
             const bool ok = live & dpos(rsq);
             const double rhoj = qb.y;
             double r, rinv; fast_sqrt_rinv(rsq, r, rinv);
-            double dwq = 0.0;                                                  // dW/dq without the norm, shared by the sub-styles when GU
-            if (GU) dwq = quintic_dw_bf(3.0 * (r * A.uni[0].c1));
+            double dwq = 0.0;                                                  // (dW/dq) / r without the norm, shared by the sub-styles when GU
+            if (GU) dwq = quintic_dw5_bf(r * gu_q) * rinv;
             if (HAS_FLUID) {
               const PairTab &P = T[I_FLUID];
-              const bool hit = ok & (GU ? ((rsq < A.uni[I_FLUID].cutsq) & ((rmask[I_FLUID] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const bool hit = ok & (GU ? ((rmask[I_FLUID] >> tj) & 1u) != 0 : (rsq < P.cutsq[ij]));
               const double2 qc = P2[slot], qd = P3[slot];
-              double wfd = (GU ? dwq * A.uni[I_FLUID].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij]) * rinv;   // (dW/dr)/r (:137-143)
+              double wfd = GU ? dwq * gu_c0[I_FLUID] : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij] * rinv;   // (dW/dr)/r (:137-143)
               wfd = hit ? wfd : 0.0;
               double Pi = d.y, Pj = qd.y;
               if (!P.gamma_uniform) {                                      // p_j uses gamma of the list owner (:148)
@@ -1282,48 +1378,35 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
                 Pj = P.B[tj] * (pow(rhoj / P.rho0[tj], P.gamma[to]) - P.rb[tj]);
               }
               const double pij = fast_div15(rhoj * Pi + rhoi * Pj, rhoi + rhoj);
-              const double V2 = v4.x + q4.x;
-              const double fvisc = V2 * P.visc[ij] * wfd, fpair = -V2 * pij * wfd;
+              const double vw = (v4.x + q4.x) * wfd;
+              const double fvisc = vw * P.visc[ij], fpair = -(vw * pij);
               const double dvx = c.x - qc.x, dvy = c.y - qc.y, dvz = d.x - qd.x;
               fx += dx * fpair + dvx * fvisc; fy += dy * fpair + dvy * fvisc; fz += dz * fpair + dvz * fvisc;
             }
             if (HAS_SURF) {
               const PairTab &P = T[I_SURF];
-              const bool hit = ok & (GU ? ((rsq < A.uni[I_SURF].cutsq) & ((rmask[I_SURF] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const bool hit = ok & (GU ? ((rmask[I_SURF] >> tj) & 1u) != 0 : (rsq < P.cutsq[ij]));
               const double2 q5 = P5[slot], q6 = P6[slot];
-              double wfd = GU ? dwq * A.uni[I_SURF].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij];    // dW/dr (:117-123)
-              wfd = hit ? wfd : 0.0;
-              const double ex = dx * rinv, ey = dy * rinv, ez = dz * rinv;
-              double six, siy, siz = 0.0, sjx, sjy, sjz = 0.0;
-              if (DIM3) {                                                  // (:153-169)
-                const double o3 = 0.3333333333333333, t3 = 0.6666666666666666;
-                double cxx = g5.x * g5.x, cyy = g5.y * g5.y, czz = g6.x * g6.x;
-                six = (ex * (o3 * czz + o3 * cyy - t3 * cxx) - g5.x * ez * g6.x - g5.x * ey * g5.y) * g6.y;
-                siy = (ey * (o3 * czz - t3 * cyy + o3 * cxx) - g5.y * ez * g6.x - ex * g5.x * g5.y) * g6.y;
-                siz = (ez * (-t3 * czz + o3 * cyy + o3 * cxx) - ey * g5.y * g6.x - ex * g5.x * g6.x) * g6.y;
-                cxx = q5.x * q5.x; cyy = q5.y * q5.y; czz = q6.x * q6.x;
-                sjx = (ex * (o3 * czz + o3 * cyy - t3 * cxx) - q5.x * ez * q6.x - q5.x * ey * q5.y) * q6.y;
-                sjy = (ey * (o3 * czz - t3 * cyy + o3 * cxx) - q5.y * ez * q6.x - ex * q5.x * q5.y) * q6.y;
-                sjz = (ez * (-t3 * czz + o3 * cyy + o3 * cxx) - ey * q5.y * q6.x - ex * q5.x * q6.x) * q6.y;
-              } else {                                                     // (:140-151); |cg| is the 2-D norm there
-                const double ni = sqrt(g5.x * g5.x + g5.y * g5.y), nj = sqrt(q5.x * q5.x + q5.y * q5.y);
-                const double ii = ni > EPSILON_CG ? 1.0 / ni : 0.0, jj = nj > EPSILON_CG ? 1.0 / nj : 0.0;
-                const double hi2 = (g5.y * g5.y + g5.x * g5.x) / 2, hj2 = (q5.y * q5.y + q5.x * q5.x) / 2;
-                six = (ex * (hi2 - g5.x * g5.x) - g5.x * ey * g5.y) * ii;
-                siy = (ey * (hi2 - g5.y * g5.y) - ex * g5.x * g5.y) * ii;
-                sjx = (ex * (hj2 - q5.x * q5.x) - q5.x * ey * q5.y) * jj;
-                sjy = (ey * (hj2 - q5.y * q5.y) - ex * q5.x * q5.y) * jj;
+              double ws = GU ? dwq * gu_c0[I_SURF] : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij] * rinv;    // (dW/dr)/r (:117-123); e = d / r
+              ws = hit ? ws : 0.0;                                         // rinv is inf for a coincident pair: keep 0 * inf out of the sums
+              // (A_i + A_j) d, A symmetric
+              const double mxx = a5.x + q5.x, myy = a5.y + q5.y, mxy = a6.x + q6.x;
+              if (DIM3) {
+                const double2 q8 = P8[slot];
+                const double mzz = a6.y + q6.y, mxz = a8.x + q8.x, myz = a8.y + q8.y;
+                fx += (mxx * dx + mxy * dy + mxz * dz) * ws;
+                fy += (mxy * dx + myy * dy + myz * dz) * ws;
+                fz += (mxz * dx + myz * dy + mzz * dz) * ws;
+              } else {
+                fx += (mxx * dx + mxy * dy) * ws;
+                fy += (mxy * dx + myy * dy) * ws;
               }
-              // rinv is inf for a coincident pair: keep 0 * inf out of the sums
-              fx += hit ? (six * v4.x + sjx * q4.x) * wfd : 0.0;
-              fy += hit ? (siy * v4.x + sjy * q4.x) * wfd : 0.0;
-              if (DIM3) fz += hit ? (siz * v4.x + sjz * q4.x) * wfd : 0.0;
             }
             if (HAS_HEAT) {
               const PairTab &P = T[I_HEAT];
-              const bool hit = ok & (GU ? ((rsq < A.uni[I_HEAT].cutsq) & ((rmask[I_HEAT] >> tj) & 1u)) : (rsq < P.cutsq[ij]));
+              const bool hit = ok & (GU ? ((rmask[I_HEAT] >> tj) & 1u) != 0 : (rsq < P.cutsq[ij]));
               const double mj = P7[slot].x;
-              double wfd = (GU ? dwq * A.uni[I_HEAT].c0 : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij]) * rinv;
+              double wfd = GU ? dwq * gu_c0[I_HEAT] : quintic_dw_bf(3.0 * (r * P.c1[ij])) * P.c0[ij] * rinv;
               double Ti = v4.y, Tj = q4.y;
               if (KINDS & K_HEATPC) {                                      // (:124-129), in half-list orientation
                 const int ff = P.fixflag[ij]; const double tc = P.tc[ij];

@@ -156,8 +156,17 @@ class Sim:
         return nl.value, ng.value
 
     def get_atoms(self, names=("x", "v", "vest", "f", "rho", "drho", "e", "de", "cv", "rmass", "colorgradient",
-                               "type", "mask", "tag")):
+                               "type", "mask", "tag"), out=None):
+        """out: caller-owned arrays (name -> ndarray of at least nlocal rows, e.g. pinned host memory, as the LAMMPS
+        shell hands the engine its own atom arrays); views of their first nlocal rows are filled and returned"""
         n, _ = self.natoms()
+        if out is not None:
+            views = {k: out[k][:n] for k in names}
+            a, keep = self._bundle(n, views)
+            for k in names:
+                assert keep[k] is views[k] or np.shares_memory(keep[k], views[k]), k + ": dtype / layout forces a copy"
+            self.api.check(self.api.get_atoms(self.h, n, C.byref(a)))
+            return views
         out = {}
         for k in names:
             if k in _abi.ATOM_FIELDS_I:
