@@ -149,6 +149,21 @@ int  b200_fix_phase_change(b200_sph *h, const b200_phase_change_desc *d); /* fix
  * region_kind 0 none | 1 block (xlo xhi ylo yhi zlo zhi) | 2 sphere (xc yc zc radius); match_inside = 1 for `region`,
  * 0 for `noregion` (apply outside).  Region tests as RegBlock/RegSphere::inside (region_block.cpp:114-119, region_sphere.cpp:96-105). */
 int  b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int region_kind, const double region[6], int match_inside);
+/* fix setmeso with a variable value (`v_name`, fix_setmeso.cpp:100-140,238-262): `formula` is the text of the equal- or atom-style
+ * variable (src/variable.cpp), compiled for the device: numbers, PI, the atom vectors id mass type x y z vx vy vz fx fy fz, the thermo
+ * keywords step and dt, the operators + - * / % ^ == != < <= > >= && || ! with the reference's precedence and left-to-right
+ * association (variable.cpp:99-107,1641), sqrt exp ln log abs sin cos tan asin acos atan atan2 ceil floor round.  Anything else is
+ * refused with a message. */
+int  b200_fix_setmeso_var(b200_sph *h, int groupbit, int which, const char *formula, int region_kind, const double region[6], int match_inside);
+/* fix addforce fx fy fz (src/fix_addforce.cpp:40-150,243-330): per component either the constant value[d] (formula[d] == NULL) or the
+ * formula of the equal- / atom-style variable the deck names with v_name (the shipped body-force decks: examples/USER/sph/poiseuille/
+ * poiseuille.lmp:57-58, flow_around_cylinder/flow.lmp:84-85, bubble_on_wall/bubble.lmp:187-188).  All three components are evaluated
+ * on the forces as they stand before this fix, then added.  No `every`, `region`, `energy` keywords. */
+int  b200_fix_addforce(b200_sph *h, int groupbit, const double value[3], const char *const formula[3]);
+/* host-side check of a formula (what `variable` + `fix ... v_name` would hand the two calls above): compiles it and, when atom != NULL,
+ * evaluates the compiled program on the host for one atom {x y z vx vy vz fx fy fz mass}.  -1 + b200_last_error() if the formula uses
+ * anything the device evaluator does not have.  Needs no device. */
+int  b200_formula_check(const char *formula, const double atom[12], int type, int id, double step, double dt, double *value);
 int  b200_fix_enforce2d(b200_sph *h, int groupbit);                          /* fix_enforce2d.cpp:77-89 */
 /* fix setmesode value [region ID] (fix_setmesode.cpp:38-78,171-199): de = value for the group's atoms (inside the region); constant value,
  * region as for b200_fix_setmeso */

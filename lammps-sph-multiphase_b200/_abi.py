@@ -72,6 +72,9 @@ _PROTOS = {
     "fix_enforce2d": (C.c_int, [_H, C.c_int]),
     "fix_setforce": (C.c_int, [_H, C.c_int, c_int_p, c_double_p]),
     "fix_setmesode": (C.c_int, [_H, C.c_int, C.c_double, C.c_int, c_double_p]),
+    "fix_setmeso_var": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p, C.c_int, c_double_p, C.c_int]),
+    "fix_addforce": (C.c_int, [_H, C.c_int, c_double_p, C.POINTER(C.c_char_p)]),
+    "formula_check": (C.c_int, [C.c_char_p, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double, c_double_p]),
     "fix_dt_reset": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "get_timestep": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "request_virial": (C.c_int, [_H]),

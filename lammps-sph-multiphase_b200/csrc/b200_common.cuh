@@ -46,7 +46,8 @@ struct PairTab {
 
 struct FixList {
   int n;
-  int kind[MAXFIX];     // 1 meso, 2 meso/stationary, 3 gravity, 4 setmeso, 5 enforce2d, 6 setforce (ipar = which components, par = values), 7 setmesode (ipar[1] region kind, par = value, region)
+  int kind[MAXFIX];     // 1 meso, 2 meso/stationary, 3 gravity, 4 setmeso, 5 enforce2d, 6 setforce (ipar = which components, par = values), 7 setmesode (ipar[1] region kind, par = value, region), 8 addforce (acc = constant components)
+  int prog[MAXFIX][3];  // addforce x, y, z / setmeso value: 1 + index of the compiled variable formula (b200_expr.cuh), 0 = constant
   int bit[MAXFIX];
   double acc[MAXFIX][3];
   int ipar[MAXFIX][3];  // setmeso: which, region kind, match_inside

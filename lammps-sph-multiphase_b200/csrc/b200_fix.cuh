@@ -1,6 +1,7 @@
 // b200_fix.cuh -- per-atom stages: fix meso / meso/stationary / gravity, reverse
 // accumulation of ghost contributions, and the rebuild trigger.
 #pragma once
+#include "b200_expr.cuh"
 #include "b200_common.cuh"
 
 struct StepArrays {
@@ -8,6 +9,7 @@ struct StepArrays {
   double *e, *de;
   const int *mask;
   const double *cv;
+  const int *tag;
 };
 
 // FixMeso::setup_pre_force (fix_meso.cpp:68-85): vest = v for atoms of the fix group
@@ -83,11 +85,21 @@ __global__ void k_far_flag(const unsigned long long *dmaxsq, double marginsq, do
 // (comm->reverse_comm runs before this kernel: b200_comm.cuh) modify->post_force (FixGravity::post_force, fix_gravity.cpp:262-295), then modify->final_integrate
 // (fix_meso.cpp:144-180, fix_meso_stationary.cpp:96-112).  The three stages can be run fused (one
 // pass over the owned atoms) or one by one for the stage-level ABI.
-__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_post, int do_final, const double *dtp, double dtf_per_dt)
+// progs / step / dt: the compiled variable formulas of fix addforce / setmeso (b200_expr.cuh) and the thermo keywords they may name
+__global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, int do_post, int do_final, const double *dtp, double dtf_per_dt,
+                             const ExprProg *progs, double step, double dt)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
-  if (dtp) dtf = dtf_per_dt * *dtp;
+  if (dtp) { dtf = dtf_per_dt * *dtp; dt = *dtp; }
+  // what a formula can name about atom i (Variable::eval_tree: x, v, f as they stand when the fix runs; mass = rmass or mass[type])
+  auto expr_in = [&](const double4 &fnow, const double4 &vnow) {
+    const double4 x = a.xt[i];
+    ExprIn in;
+    in.x = x.x; in.y = x.y; in.z = x.z; in.vx = vnow.x; in.vy = vnow.y; in.vz = vnow.z; in.fx = fnow.x; in.fy = fnow.y; in.fz = fnow.z;
+    in.mass = vnow.w; in.type = tw_type(__double_as_longlong(x.w)); in.id = a.tag[i]; in.step = step; in.dt = dt; in.time = 0.0;
+    return in;
+  };
   double4 f = a.fd[i];
   double de = a.de[i];
   bool fdirty = false;
@@ -110,14 +122,26 @@ __global__ void k_post_final(int nlocal, FixList fl, StepArrays a, double dtf, i
           else { double dx = x.x - r[0], dy = x.y - r[1], dz = x.z - r[2]; in = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) <= r[3]; }
           if (in != (fl.ipar[k][2] != 0)) continue;
         }
-        if (fl.ipar[k][0] == 0) { double4 vr = a.vr[i]; vr.w = fl.par[k][0]; a.vr[i] = vr; }
-        else a.e[i] = fl.ipar[k][0] == 2 ? a.cv[i] * fl.par[k][0] : fl.par[k][0];
+        double val = fl.par[k][0];
+        if (fl.prog[k][0]) { const ExprIn in = expr_in(f, v); val = expr_eval(progs[fl.prog[k][0] - 1], in); }      // varflag ATOM / EQUAL (fix_setmeso.cpp:238-262)
+        if (fl.ipar[k][0] == 0) { double4 vr = a.vr[i]; vr.w = val; a.vr[i] = vr; }
+        else a.e[i] = fl.ipar[k][0] == 2 ? a.cv[i] * val : val;
       } else if (fl.kind[k] == 5) {                           // FixEnforce2D::post_force (fix_enforce2d.cpp:77-89)
         v.z = 0.0; f.z = 0.0; fdirty = true; vdirty = true;
       } else if (fl.kind[k] == 6) {                           // FixSetForce::post_force, constant values (fix_setforce.cpp:241-251)
         if (fl.ipar[k][0]) f.x = fl.par[k][0];
         if (fl.ipar[k][1]) f.y = fl.par[k][1];
         if (fl.ipar[k][2]) f.z = fl.par[k][2];
+        fdirty = true;
+      } else if (fl.kind[k] == 8) {                           // FixAddForce::post_force (fix_addforce.cpp:269-320): all three components are evaluated before any is added
+        double ax = fl.acc[k][0], ay = fl.acc[k][1], az = fl.acc[k][2];
+        if (fl.prog[k][0] | fl.prog[k][1] | fl.prog[k][2]) {
+          const ExprIn in = expr_in(f, v);
+          if (fl.prog[k][0]) ax = expr_eval(progs[fl.prog[k][0] - 1], in);
+          if (fl.prog[k][1]) ay = expr_eval(progs[fl.prog[k][1] - 1], in);
+          if (fl.prog[k][2]) az = expr_eval(progs[fl.prog[k][2] - 1], in);
+        }
+        f.x += ax; f.y += ay; f.z += az;
         fdirty = true;
       }
     }

@@ -149,7 +149,7 @@ struct b200_sph {
   double *d_dt = nullptr;
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
-  int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2, tile_fsplit = 2;
+  int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
   DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
   int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
   // halo overlap (single-phase tile path): tiles [0, nint) neither read ghosts nor feed a send list and run while the halo flies
@@ -172,7 +172,8 @@ struct b200_sph {
     rec.ensure(n * 4, false, st); gimage.ensure(n, true, st);
     numneigh.ensure(n, false, st); numfar.ensure(n, false, st);
   }
-  StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p, c.cv.p}; }
+  StepArrays step_arrays() { OwnedSet &c = C(); return StepArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.e.p, c.de.p, c.mask.p, c.cv.p, c.tag.p}; }
+  std::vector<ExprProg> progs; DevBuf<ExprProg> d_progs;       // compiled variable formulas of the registered fixes
   CommArrays comm_arrays() { OwnedSet &c = C(); return CommArrays{c.xt.p, c.vr.p, c.vm.p, c.fd.p, c.cgm.p, c.e.p, c.de.p, c.cv.p, c.tag.p, c.mask.p, c.orig.p, gimage.p}; }
 
   // ---- timing helpers ----
@@ -606,7 +607,7 @@ static bool tile_rows(b200_sph *h)
   CK(cudaMemsetAsync(h->d_tflags, 0, 16 * sizeof(int), h->st));
   bool classes = false;
   if (nl) {
-    h->tiles.ensure((size_t)g.ncells + 1);
+    h->tiles.ensure((mp ? 2 : 1) * ((size_t)g.ncells + 1));      // multiphase: the ghost-row tiles are appended (below)
     TilePlanArgs P{g, nl, TILE_ROWS, h->tile_slotcap, 0, mp ? 1 : 0, -1, {0, 0, 0}, h->cso.p, h->csg.p, h->tiles.p, h->d_tflags};
     classes = !mp && h->nswap > 0 && !h->no_overlap;
     for (int k = 0; k < h->nswap; k++)       // the interior criterion of k_tile_plan needs cells at least one ghost cutoff wide
@@ -638,6 +639,9 @@ static bool tile_rows(b200_sph *h)
   if (!nl) return true;
   h->ntiles = hf[0]; h->ngtiles = hf[8]; h->nint = classes ? hf[5] : 0;
   h->tile_cap = std::max(2, (std::max(hf[1], hf[9]) + 1) & ~1);
+  // one tile queue: owned-row tiles [0, ntiles), then the ghost-row tiles -- the build and the force pass walk both in ONE persistent
+  // launch (the short ghost tiles fill the tail of the owned ones; profiles/r02_launches_c3: 0.26 + 0.13 ms as launches of their own)
+  if (h->ngtiles) CK(cudaMemcpyAsync(h->tiles.p + h->ntiles, h->gtiles.p, (size_t)h->ngtiles * sizeof(TileDesc), cudaMemcpyDeviceToDevice, h->st));
   const int nrows = mp ? na : nl;
   if (mp) h->rowtile.ensure(nl + 1);
   for (int attempt = 0; attempt < 8; attempt++) {
@@ -659,9 +663,9 @@ static bool tile_rows(b200_sph *h)
     for (int i = 1; i <= h->ntypes; i++) for (int j = 1; j <= h->ntypes; j++)
       if (h->h_cutneighsq[i * MAXT1 + j] != B.cutsq_u || h->h_farsq[i * MAXT1 + j] != B.farsq_u || h->h_midsq[i * MAXT1 + j] != B.midsq_u) B.uni = 0;
     size_t bsm = (size_t)(mp ? 17 : 13) * (((h->tile_cap + 3) & ~3) + 4);
-    for (int set = 0; set < (mp ? 2 : 1); set++) {
-      if (set) { B.tiles = h->gtiles.p; B.ntiles = h->ngtiles; }
-      int nt = set ? h->ngtiles : h->ntiles;
+    {
+      const int nt = h->ntiles + h->ngtiles;
+      B.ntiles = nt;
       bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
       if (const char *e = getenv("B200_BUILD_NT")) small = atoi(e) == 128;
 #define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
@@ -919,7 +923,6 @@ static void build_plan(b200_sph *h)
   if (const char *e = getenv("B200_TILE_SLOTCAP")) h->tile_slotcap = std::max(2, std::min(h->tile_slotcap, atoi(e)) & ~1);   // tests: force small tiles / the row-path fall-back
   if (const char *e = getenv("B200_TILE_SPLIT")) h->tile_split = atoi(e);
   if (h->tile_split != 1 && h->tile_split != 2 && h->tile_split != 4) h->tile_split = 2;    // 4: density pass only
-  if (const char *e = getenv("B200_FORCE_SPLIT")) h->tile_fsplit = atoi(e);
 }
 
 static PairArgs pair_args(b200_sph *h)
@@ -1030,8 +1033,6 @@ template <int KINDS> static void launch_tile_force(b200_sph *h, const TileArgs &
   if (h->vir_now && F) {            // thermo step: the instantiation that also sums the rows' virial
     if (uni) launch_tiles(h, k_tile_force<KINDS, 2, true, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
     else launch_tiles(h, k_tile_force<KINDS, 2, false, true>, "k_tile_force", TILE_ROWS * 2, smem, A, A.ntiles, reserve);
-  } else if (h->tile_fsplit == 4 && uni) {
-    launch_tiles(h, k_tile_force<KINDS, 4, true, false>, "k_tile_force", TILE_ROWS * 4, smem, A, A.ntiles, reserve);
   } else if (h->tile_split == 1) {
     if (uni) launch_tiles(h, k_tile_force<KINDS, 1, true, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
     else launch_tiles(h, k_tile_force<KINDS, 1, false, false>, "k_tile_force", TILE_ROWS, smem, A, A.ntiles, reserve);
@@ -1068,9 +1069,9 @@ template <int KINDS> static void launch_tile_force_mp(b200_sph *h, TileArgs &A, 
 {
   const bool d3 = h->g.dim == 3 || !(KINDS & K_SURF);
   size_t smem = d3 ? TileSmem<MpParts<KINDS, true>::n, MpParts<KINDS, true>::nk>::bytes(h->tile_cap) : TileSmem<MpParts<KINDS, false>::n, MpParts<KINDS, false>::nk>::bytes(h->tile_cap);
-  for (int set = 0; set < 2; set++) {          // owned rows, then the ghost rows
-    int nt = set ? h->ngtiles : h->ntiles;
-    if (set) { A.tiles = h->gtiles.p; A.ntiles = h->ngtiles; }
+  {                                            // owned rows, then the ghost rows, in one tile queue (tile_rows)
+    const int nt = h->ntiles + h->ngtiles;
+    A.ntiles = nt;
     if (d3) {
       if (gu) launch_tiles(h, k_tile_force_mp<KINDS, true, true>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
       else launch_tiles(h, k_tile_force_mp<KINDS, true, false>, "k_tile_force_mp", TILE_MP_NT, smem, A, nt);
@@ -1333,7 +1334,7 @@ static void post_final(b200_sph *h, int rev, int post, int fin)
       [&](Swap &s, double *buf) { LAUNCH(h, k_unpack_reverse, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), buf); });
   if ((post || fin) && h->nlocal)
     LAUNCH(h, k_post_final, nblk(h->nlocal, B), B, h->nlocal, h->fl, h->step_arrays(), 0.5 * h->dt * h->ftm2v, post, fin,
-           h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v);
+           h->dtreset ? h->d_dt : (const double *)nullptr, 0.5 * h->ftm2v, h->d_progs.p, (double)h->ntimestep, h->dt);
   h->tend();
 }
 static void initial_integrate(b200_sph *h)
@@ -1752,6 +1753,7 @@ int b200_pair_add(b200_sph *h, const b200_pair_desc *d)
 int b200_fix_clear(b200_sph *h)
 {
   memset(&h->fl, 0, sizeof h->fl);
+  h->progs.clear();
   // FixPhaseChange keeps next_reneighbor and its RanPark stream across `run` commands (fix_phase_change.cpp:116,345): when the
   // caller re-registers the same fix (VerletB200::configure runs per `run`), b200_fix_phase_change adopts that state again
   for (PcFix &f : h->pcs_old) cudaFree(f.d_state);
@@ -1779,6 +1781,46 @@ int b200_fix_setmeso(b200_sph *h, int groupbit, int which, double value, int reg
   h->fl.par[k][0] = value;
   for (int q = 0; q < 6; q++) h->fl.par[k][1 + q] = (region_kind && region) ? region[q] : 0.0;
   return 0;
+}
+// a variable formula of the fix being registered -> its program slot (1-based; 0 = none)
+static int add_formula(b200_sph *h, const char *text, int *slot)
+{
+  ExprProg P;
+  std::string err = expr_compile(text, P);
+  if (!err.empty()) return fail(err + " (formula: " + text + ")");
+  h->progs.push_back(P);
+  h->d_progs.ensure(h->progs.size());
+  CK(cudaMemcpy(h->d_progs.p, h->progs.data(), h->progs.size() * sizeof(ExprProg), cudaMemcpyHostToDevice));
+  *slot = (int)h->progs.size();
+  return 0;
+}
+int b200_formula_check(const char *formula, const double atom[12], int type, int id, double step, double dt, double *value)
+{
+  ExprProg P;
+  std::string err = expr_compile(formula, P);
+  if (!err.empty()) return fail(err + " (formula: " + formula + ")");
+  if (value && atom) {
+    ExprIn in{atom[0], atom[1], atom[2], atom[3], atom[4], atom[5], atom[6], atom[7], atom[8], atom[9], step, dt, 0.0, type, id};
+    *value = expr_eval(P, in);
+  }
+  return 0;
+}
+int b200_fix_setmeso_var(b200_sph *h, int groupbit, int which, const char *formula, int region_kind, const double region[6], int match_inside)
+{
+  API_BEGIN
+  if (!formula) return fail("b200_fix_setmeso_var: no formula");
+  if (b200_fix_setmeso(h, groupbit, which, 0.0, region_kind, region, match_inside)) return -1;
+  if (add_formula(h, formula, &h->fl.prog[h->fl.n - 1][0])) { h->fl.n--; return -1; }
+  API_END
+}
+int b200_fix_addforce(b200_sph *h, int groupbit, const double value[3], const char *const formula[3])
+{
+  API_BEGIN
+  if (add_fix(h, 8, groupbit, value ? value[0] : 0.0, value ? value[1] : 0.0, value ? value[2] : 0.0)) return -1;
+  const int k = h->fl.n - 1;
+  for (int d = 0; d < 3; d++)
+    if (formula && formula[d] && add_formula(h, formula[d], &h->fl.prog[k][d])) { h->fl.n--; return -1; }
+  API_END
 }
 int b200_fix_enforce2d(b200_sph *h, int groupbit) { return add_fix(h, 5, groupbit, 0, 0, 0); }
 int b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax)

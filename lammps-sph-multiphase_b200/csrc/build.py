@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = ["b200_sph.cu"]
-HDR = ["b200_common.cuh", "b200_neigh.cuh", "b200_pair.cuh", "b200_tile.cuh", "b200_fix.cuh", "b200_phase.cuh", "b200_comm.cuh", "../../include/b200_sph.h"]
+HDR = ["b200_common.cuh", "b200_neigh.cuh", "b200_pair.cuh", "b200_tile.cuh", "b200_fix.cuh", "b200_phase.cuh", "b200_comm.cuh", "b200_lj.cuh", "b200_expr.cuh", "../../include/b200_sph.h"]
 OUT = os.path.join(HERE, "libb200sph.so")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-shared", "-cudart", "static", "-ldl"]

@@ -185,6 +185,7 @@ class Deck:
         self.dt, self.ntimestep = 0.005 if units == "lj" else 1.0e-8, 0   # Update::set_units (update.cpp)
         self.groups = {"all": 1}
         self.fixes = []
+        self.variables = {}
         self.regions = {}
         self._initd = False
 
@@ -273,6 +274,23 @@ class Deck:
         else:
             self.styles[0].coeff(I, J, args)
 
+    # ---- variables ---------------------------------------------------------
+    def variable(self, name, style, formula):
+        """variable name equal|atom formula (variable.cpp:136-330): kept as text; `v_other` references are spliced in
+        (in parentheses) when a fix takes the variable, ${} is the caller's business as it is the input parser's in the reference"""
+        if style not in ("equal", "atom"):
+            raise DeckError("b200 SPH package: variable styles equal and atom")
+        self.variables[name] = str(formula)
+
+    def _formula(self, vname, depth=0):
+        import re
+        name = str(vname)[2:]
+        if name not in self.variables:
+            raise DeckError("Variable name for fix does not exist")
+        if depth > 8:
+            raise DeckError("Variable has circular dependency")
+        return re.sub(r"\bv_(\w+)", lambda m: "(" + self._formula(m.group(0), depth + 1) + ")", self.variables[name])
+
     # ---- fixes -------------------------------------------------------------
     def fix(self, ID, group, style, *args):
         """fix ID group style args: meso (fix_meso.cpp:38-49), meso/stationary, gravity
@@ -334,8 +352,7 @@ class Deck:
             which = {"meso_rho": 0, "meso_e": 1, "meso_t": 2}.get(args[0])
             if which is None:
                 raise DeckError("Illegal fix setmeso command, meso_rho or meso_e must be given")
-            if str(args[1]).startswith("v_"):
-                raise DeckError("b200 SPH package: fix setmeso supports constant values")
+            formula = self._formula(args[1]) if str(args[1]).startswith("v_") else None
             kind, reg, inside = 0, [0.0] * 6, 1
             if len(args) > 2:
                 if args[2] not in ("region", "noregion") or len(args) < 4:
@@ -344,7 +361,16 @@ class Deck:
                     raise DeckError("Region ID for fix setmesode does not exist")
                 kind, reg = self.regions[args[3]]
                 inside = 1 if args[2] == "region" else 0
-            self.fixes.append((style, bit, (which, float(args[1]), kind, list(reg), inside)))
+            if formula is not None:    # varflag EQUAL / ATOM (fix_setmeso.cpp:100-140): the variable's formula goes to the device
+                self.fixes.append(("setmeso/var", bit, (which, formula, kind, list(reg), inside)))
+            else:
+                self.fixes.append((style, bit, (which, float(args[1]), kind, list(reg), inside)))
+        elif style == "addforce":      # fix_addforce.cpp:40-110: fx fy fz, each a constant or v_name; no every / region / energy
+            if len(args) != 3:
+                raise DeckError("b200 SPH package: fix addforce supports `fx fy fz` without keywords")
+            vals = [0.0 if str(a).startswith("v_") else float(a) for a in args]
+            forms = [self._formula(a) if str(a).startswith("v_") else None for a in args]
+            self.fixes.append((style, bit, (vals, forms)))
         elif style == "phase_change":
             a = list(args)
             if len(a) < 11:

@@ -121,6 +121,14 @@ class Sim:
                 which, value, kind, reg, inside = arg
                 r = np.array(reg, np.float64)
                 ck(api.fix_setmeso(h, bit, which, value, kind, _dp(r), inside))
+            elif style == "setmeso/var":
+                which, formula, kind, reg, inside = arg
+                r = np.array(reg, np.float64)
+                ck(api.fix_setmeso_var(h, bit, which, formula.encode(), kind, _dp(r), inside))
+            elif style == "addforce":
+                vals = np.array(arg[0], np.float64)
+                forms = (C.c_char_p * 3)(*[f.encode() if f is not None else None for f in arg[1]])
+                ck(api.fix_addforce(h, bit, _dp(vals), forms))
             elif style == "phase_change":
                 pc = PhaseChangeDesc(groupbit=bit, **arg)
                 ck(api.fix_phase_change(h, C.byref(pc)))

@@ -6,9 +6,50 @@
 #include "region.h"
 #include "error.h"
 #include "update.h"
+#include "input.h"
+#include "variable.h"
+#include <string>
 
 using namespace LAMMPS_NS;
 using namespace FixConst;
+
+// Variable keeps the formula text of its variables private (variable.h:55 `char ***data`) and retrieve() returns NULL for atom-style
+// ones (variable.cpp:647).  An explicit template instantiation may name a private member, which gives the shell a read-only view
+// without touching the reference's sources.
+namespace {
+template <typename Tag, typename Tag::type M> struct PrivateMember { friend typename Tag::type b200_get(Tag) { return M; } };
+struct VariableData { typedef char ***Variable::*type; friend type b200_get(VariableData); };
+template struct PrivateMember<VariableData, &Variable::data>;
+
+std::string formula_of(LAMMPS *lmp, const char *name, int depth)
+{
+  Variable *var = lmp->input->variable;
+  int ivar = var->find((char *) name);
+  if (ivar < 0) lmp->error->all(FLERR, "Variable name for fix /b200 does not exist");
+  if (!var->equalstyle(ivar) && !var->atomstyle(ivar)) lmp->error->all(FLERR, "Variable for fix /b200 is invalid style");
+  if (depth > 8) lmp->error->all(FLERR, "Variable has circular dependency");
+  char ***data = var->*b200_get(VariableData());
+  std::string text = data[ivar][0], out;
+  for (size_t i = 0; i < text.size();) {
+    const bool start = i == 0 || !(isalnum((unsigned char) text[i - 1]) || text[i - 1] == '_');
+    if (start && text.compare(i, 2, "v_") == 0) {
+      size_t j = i + 2;
+      while (j < text.size() && (isalnum((unsigned char) text[j]) || text[j] == '_')) j++;
+      out += "(" + formula_of(lmp, text.substr(i + 2, j - i - 2).c_str(), depth + 1) + ")";
+      i = j;
+    } else out += text[i++];
+  }
+  return out;
+}
+}
+
+char *LAMMPS_NS::b200_variable_formula(LAMMPS *lmp, const char *vname)
+{
+  std::string f = formula_of(lmp, vname, 0);
+  char *s = new char[f.size() + 1];
+  strcpy(s, f.c_str());
+  return s;
+}
 
 void LAMMPS_NS::b200_fix_guard(LAMMPS *lmp, const char *name)
 {
@@ -63,15 +104,16 @@ FixPhaseChangeB200::FixPhaseChangeB200(LAMMPS *lmp, int narg, char **arg) : Fix(
 int FixPhaseChangeB200::setmask() { return PRE_EXCHANGE; }
 int FixPhaseChangeB200::b200_register(b200_sph *h) { return b200_fix_phase_change(h, &d); }
 
-FixSetMesoB200::FixSetMesoB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), idregion(NULL)
+FixSetMesoB200::FixSetMesoB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), idregion(NULL), vname(NULL)
 {
   if (narg < 5) error->all(FLERR, "Illegal fix setmeso command");
   if (strcmp(arg[3], "meso_rho") == 0) which = 0;
   else if (strcmp(arg[3], "meso_e") == 0) which = 1;
   else if (strcmp(arg[3], "meso_t") == 0) which = 2;
   else error->all(FLERR, "Illegal fix setmeso command, meso_rho or meso_e must be given");
-  if (strstr(arg[4], "v_") == arg[4]) error->all(FLERR, "fix setmeso/b200 supports constant values only");
-  value = atof(arg[4]);
+  value = 0.0;
+  if (strstr(arg[4], "v_") == arg[4]) { vname = new char[strlen(arg[4]) - 1]; strcpy(vname, arg[4] + 2); }      // xstr, fix_setmeso.cpp:52-56
+  else value = atof(arg[4]);
   regionflag = 1;
   int iarg = 5;
   while (iarg < narg) {
@@ -108,7 +150,34 @@ int FixSetMesoB200::b200_register(b200_sph *h)
       r[3] = 0.5 * (reg->extent_xhi - reg->extent_xlo);
     } else error->all(FLERR, "fix setmeso/b200 supports block and sphere regions");
   }
+  if (vname) {      // the variable branch of the reference tests `!match` whatever region / noregion said (fix_setmeso.cpp:247-249)
+    char *f = b200_variable_formula(lmp, vname);
+    int rc = b200_fix_setmeso_var(h, groupbit, which, f, kind, r, 1);
+    delete [] f;
+    return rc;
+  }
   return b200_fix_setmeso(h, groupbit, which, value, kind, r, regionflag);
+}
+
+FixAddForceB200::FixAddForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
+{
+  for (int d = 0; d < 3; d++) { vname[d] = NULL; value[d] = 0.0; }
+  if (narg < 6) error->all(FLERR, "Illegal fix addforce command");
+  if (narg > 6) error->all(FLERR, "fix addforce/b200 supports `fx fy fz` without the every / region / energy keywords");
+  for (int d = 0; d < 3; d++) {
+    const char *a = arg[3 + d];
+    if (strstr(a, "v_") == a) { vname[d] = new char[strlen(a) - 1]; strcpy(vname[d], a + 2); }
+    else value[d] = atof(a);
+  }
+}
+int FixAddForceB200::setmask() { return POST_FORCE; }
+int FixAddForceB200::b200_register(b200_sph *h)
+{
+  char *f[3] = {NULL, NULL, NULL};
+  for (int d = 0; d < 3; d++) if (vname[d]) f[d] = b200_variable_formula(lmp, vname[d]);
+  int rc = b200_fix_addforce(h, groupbit, value, f);
+  for (int d = 0; d < 3; d++) delete [] f[d];
+  return rc;
 }
 
 FixSetForceB200::FixSetForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)

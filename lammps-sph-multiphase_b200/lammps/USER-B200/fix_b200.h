@@ -13,6 +13,7 @@ FixStyle(enforce2d/b200,FixEnforce2DB200)
 FixStyle(setforce/b200,FixSetForceB200)
 FixStyle(setmesode/b200,FixSetMesodEB200)
 FixStyle(dt/reset/b200,FixDtResetB200)
+FixStyle(addforce/b200,FixAddForceB200)
 
 #else
 
@@ -67,19 +68,36 @@ class FixPhaseChangeB200 : public Fix, public B200FixShell {
   b200_phase_change_desc d;
 };
 
+// text of an equal- or atom-style variable with its v_name references spliced in (parenthesised), for the device evaluator of the
+// engine (csrc/b200_expr.cuh); errors out for other variable styles
+char *b200_variable_formula(class LAMMPS *, const char *vname);
+
 // FixSetMeso keeps its parameters private (fix_setmeso.h:42-53): same argument list re-parsed,
-//   fix ID grp setmeso meso_rho|meso_e|meso_t value [region|noregion ID]      (fix_setmeso.cpp:38-89), constant values only
+//   fix ID grp setmeso meso_rho|meso_e|meso_t value|v_name [region|noregion ID]      (fix_setmeso.cpp:38-89)
 class FixSetMesoB200 : public Fix, public B200FixShell {
  public:
   FixSetMesoB200(class LAMMPS *, int, char **);
-  ~FixSetMesoB200() { delete [] idregion; }
+  ~FixSetMesoB200() { delete [] idregion; delete [] vname; }
   int setmask();
   void post_force(int) { b200_fix_guard(lmp, "setmeso"); }
   int b200_register(b200_sph *h);
  private:
   int which, regionflag;
   double value;
-  char *idregion;
+  char *idregion, *vname;
+};
+
+// FixAddForce (fix_addforce.cpp:40-150, members private): fix ID grp addforce fx fy fz, each a constant or v_name (equal- or atom-style
+// variable, evaluated per atom and step on the device); the keywords every / region / energy are refused
+class FixAddForceB200 : public Fix, public B200FixShell {
+ public:
+  FixAddForceB200(class LAMMPS *, int, char **);
+  ~FixAddForceB200() { for (int d = 0; d < 3; d++) delete [] vname[d]; }
+  int setmask();
+  void post_force(int) { b200_fix_guard(lmp, "addforce"); }
+  int b200_register(b200_sph *h);
+ private:
+  double value[3]; char *vname[3];
 };
 
 class FixEnforce2DB200 : public FixEnforce2D, public B200FixShell {

@@ -25,6 +25,7 @@
  * /root/reference/).  Compile with -ffp-contract=off (no FMA), like the
  * reference's generic x86-64 build.
  */
+#include <ctype.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,7 +39,7 @@
 #define EPSILON 1.0e-12 /* pair_sph_surfacetension.cpp */
 #define CG_SMALL 1.0e-20 /* fix_phase_change.cpp:42 */
 
-enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE, FIX_SETMESODE, FIX_DT_RESET };
+enum { FIX_MESO = 1, FIX_MESO_STATIONARY, FIX_GRAVITY, FIX_PHASE_CHANGE, FIX_SETMESO, FIX_ENFORCE2D, FIX_SETFORCE, FIX_SETMESODE, FIX_DT_RESET, FIX_ADDFORCE };
 
 typedef struct {
   int style, nstep;
@@ -51,6 +52,7 @@ typedef struct {
   double acc[3];
   int which, region_kind, match_inside; double value, region[6];
   int fset[3]; double fvalue[3];   /* fix setforce */
+  char *formula[3];                /* fix addforce x y z / fix setmeso value: text of the v_ variable, or NULL */
   int nevery, minbound, maxbound; double tmin, tmax, xmax;   /* fix dt/reset */
   osph_phase_change_desc pc;
   long long next_reneighbor;
@@ -234,6 +236,7 @@ int osph_atom_modify(osph_sph *s, int sortfreq, double userbinsize)
 
 int osph_pair_clear(osph_sph *s) { for (int i = 0; i < s->npair; i++) free_pair(&s->pair[i]); s->npair = 0; return 0; }
 
+static char *dups(const char *p) { char *q = malloc(strlen(p) + 1); strcpy(q, p); return q; }
 static double *dupd(const double *p, int n) { if (!p) return NULL; double *q = malloc(sizeof(double) * n); memcpy(q, p, sizeof(double) * n); return q; }
 static int *dupi(const int *p, int n) { if (!p) return NULL; int *q = malloc(sizeof(int) * n); memcpy(q, p, sizeof(int) * n); return q; }
 
@@ -268,6 +271,19 @@ int osph_fix_setmeso(osph_sph *s, int groupbit, int which, double value, int reg
   ofix *f = newfix(s, FIX_SETMESO, groupbit); if (!f) return fail("too many fixes");
   f->which = which; f->value = value; f->region_kind = region_kind; f->match_inside = match_inside;
   for (int q = 0; q < 6; q++) f->region[q] = (region_kind && region) ? region[q] : 0.0;
+  return 0;
+}
+int osph_fix_setmeso_var(osph_sph *s, int groupbit, int which, const char *formula, int region_kind, const double region[6], int match_inside)
+{
+  if (!formula) return fail("osph_fix_setmeso_var: no formula");
+  if (osph_fix_setmeso(s, groupbit, which, 0.0, region_kind, region, match_inside)) return -1;
+  s->fix[s->nfix - 1].formula[0] = dups(formula);
+  return 0;
+}
+int osph_fix_addforce(osph_sph *s, int groupbit, const double value[3], const char *const formula[3])
+{
+  ofix *f = newfix(s, FIX_ADDFORCE, groupbit); if (!f) return fail("too many fixes");
+  for (int d = 0; d < 3; d++) { f->acc[d] = value ? value[d] : 0.0; f->formula[d] = (formula && formula[d]) ? dups(formula[d]) : NULL; }
   return 0;
 }
 int osph_fix_enforce2d(osph_sph *s, int groupbit) { return newfix(s, FIX_ENFORCE2D, groupbit) ? 0 : fail("too many fixes"); }
@@ -1061,6 +1077,126 @@ static void fix_gravity(osph_sph *s, ofix *fx)
     }
 }
 
+/* ---- variable formulas: Variable::evaluate restated (variable.cpp:1480-1735), evaluated directly for one atom with an argument
+ * stack and an operator stack: an operator of precedence p first pops and applies every stacked operator of precedence >= p
+ * (:1641), so all binary operators, `^` included, associate to the left; precedences :99-107.  Atom vectors as in
+ * Variable::is_atom_vector / atom_vector (:3480-3560): id mass type x y z vx vy vz fx fy fz; thermo keywords step, dt. ---- */
+enum { V_DONE, V_ADD, V_SUB, V_MUL, V_DIV, V_CARAT, V_MOD, V_UNARY, V_NOT, V_EQ, V_NE, V_LT, V_LE, V_GT, V_GE, V_AND, V_OR };
+static const int v_prec[] = {0, 5, 5, 6, 6, 7, 6, 8, 8, 3, 3, 4, 4, 4, 4, 2, 1};
+typedef struct { osph_sph *s; int i; const char *p; int bad; } vctx;
+static double v_formula(vctx *c, const char *stops);
+static double v_atomword(vctx *c, const char *w)
+{
+  osph_sph *s = c->s; int i = c->i;
+  if (!strcmp(w, "id")) return s->tag[i];
+  if (!strcmp(w, "mass")) return s->multiphase ? s->rmass[i] : s->mass[s->type[i]];
+  if (!strcmp(w, "type")) return s->type[i];
+  if (!strcmp(w, "x")) return s->x[3*i]; if (!strcmp(w, "y")) return s->x[3*i+1]; if (!strcmp(w, "z")) return s->x[3*i+2];
+  if (!strcmp(w, "vx")) return s->v[3*i]; if (!strcmp(w, "vy")) return s->v[3*i+1]; if (!strcmp(w, "vz")) return s->v[3*i+2];
+  if (!strcmp(w, "fx")) return s->f[3*i]; if (!strcmp(w, "fy")) return s->f[3*i+1]; if (!strcmp(w, "fz")) return s->f[3*i+2];
+  if (!strcmp(w, "step")) return (double)s->ntimestep;
+  if (!strcmp(w, "dt")) return s->dt;
+  if (!strcmp(w, "PI")) return 3.14159265358979323846;
+  c->bad = 1; return 0.0;
+}
+static double v_apply(int op, double v1, double v2)
+{
+  switch (op) {
+  case V_ADD: return v1 + v2; case V_SUB: return v1 - v2; case V_MUL: return v1 * v2; case V_DIV: return v1 / v2;
+  case V_MOD: return fmod(v1, v2); case V_CARAT: return pow(v1, v2); case V_UNARY: return -v2; case V_NOT: return v2 == 0.0 ? 1.0 : 0.0;
+  case V_EQ: return v1 == v2 ? 1.0 : 0.0; case V_NE: return v1 != v2 ? 1.0 : 0.0; case V_LT: return v1 < v2 ? 1.0 : 0.0;
+  case V_LE: return v1 <= v2 ? 1.0 : 0.0; case V_GT: return v1 > v2 ? 1.0 : 0.0; case V_GE: return v1 >= v2 ? 1.0 : 0.0;
+  case V_AND: return (v1 != 0.0 && v2 != 0.0) ? 1.0 : 0.0; default: return (v1 != 0.0 || v2 != 0.0) ? 1.0 : 0.0;
+  }
+}
+static double v_formula(vctx *c, const char *stops)
+{
+  double arg[64]; int op[64], narg = 0, nop = 0, expect_arg = 1;
+  for (;;) {
+    while (*c->p == ' ' || *c->p == '\t') c->p++;
+    char ch = *c->p;
+    if (expect_arg && ch == '(') { c->p++; arg[narg++] = v_formula(c, ")"); if (*c->p != ')') c->bad = 1; else c->p++; expect_arg = 0; continue; }
+    if (expect_arg && (isdigit((unsigned char)ch) || ch == '.')) {
+      const char *q = c->p;
+      while (isdigit((unsigned char)*q) || *q == '.' || *q == 'e' || *q == 'E' || ((*q == '-' || *q == '+') && q > c->p && (q[-1] == 'e' || q[-1] == 'E'))) q++;
+      char buf[64]; int n = (int)(q - c->p); if (n > 63) n = 63; memcpy(buf, c->p, n); buf[n] = 0;
+      arg[narg++] = atof(buf); c->p = q; expect_arg = 0; continue;
+    }
+    if (expect_arg && (isalpha((unsigned char)ch) || ch == '_')) {
+      char w[32]; int n = 0;
+      while ((isalnum((unsigned char)*c->p) || *c->p == '_') && n < 31) w[n++] = *c->p++;
+      w[n] = 0;
+      if (*c->p == '(') {                        /* math functions, variable.cpp:2560-2900 */
+        c->p++;
+        double a = v_formula(c, ",)"), b = 0.0;
+        if (*c->p == ',') { c->p++; b = v_formula(c, ")"); }
+        if (*c->p != ')') c->bad = 1; else c->p++;
+        double r = 0.0;
+        if (!strcmp(w, "sqrt")) r = sqrt(a); else if (!strcmp(w, "exp")) r = exp(a); else if (!strcmp(w, "ln")) r = log(a);
+        else if (!strcmp(w, "log")) r = log10(a); else if (!strcmp(w, "abs")) r = fabs(a); else if (!strcmp(w, "sin")) r = sin(a);
+        else if (!strcmp(w, "cos")) r = cos(a); else if (!strcmp(w, "tan")) r = tan(a); else if (!strcmp(w, "asin")) r = asin(a);
+        else if (!strcmp(w, "acos")) r = acos(a); else if (!strcmp(w, "atan")) r = atan(a); else if (!strcmp(w, "atan2")) r = atan2(a, b);
+        else if (!strcmp(w, "ceil")) r = ceil(a); else if (!strcmp(w, "floor")) r = floor(a);
+        else if (!strcmp(w, "round")) r = (a < 0.0) ? ceil(a - 0.5) : floor(a + 0.5); else c->bad = 1;
+        arg[narg++] = r;
+      } else arg[narg++] = v_atomword(c, w);
+      expect_arg = 0; continue;
+    }
+    int o = -1, len = 1;
+    if (ch == 0 || strchr(stops, ch)) o = V_DONE;
+    else if (ch == '-' && expect_arg) o = V_UNARY; else if (ch == '!' && c->p[1] != '=' && expect_arg) o = V_NOT;
+    else if (expect_arg) { c->bad = 1; return 0.0; }
+    else if (ch == '+') o = V_ADD; else if (ch == '-') o = V_SUB; else if (ch == '*') o = V_MUL; else if (ch == '/') o = V_DIV;
+    else if (ch == '^') o = V_CARAT; else if (ch == '%') o = V_MOD;
+    else if (ch == '=' && c->p[1] == '=') { o = V_EQ; len = 2; } else if (ch == '!' && c->p[1] == '=') { o = V_NE; len = 2; }
+    else if (ch == '<' && c->p[1] == '=') { o = V_LE; len = 2; } else if (ch == '<') o = V_LT;
+    else if (ch == '>' && c->p[1] == '=') { o = V_GE; len = 2; } else if (ch == '>') o = V_GT;
+    else if (ch == '&' && c->p[1] == '&') { o = V_AND; len = 2; } else if (ch == '|' && c->p[1] == '|') { o = V_OR; len = 2; }
+    if (o < 0 || narg >= 60 || nop >= 60) { c->bad = 1; return 0.0; }
+    if (o != V_UNARY && o != V_NOT)
+      while (nop && v_prec[op[nop - 1]] >= v_prec[o]) {
+        int prev = op[--nop]; double v2 = arg[--narg], v1 = 0.0;
+        if (prev != V_UNARY && prev != V_NOT) v1 = arg[--narg];
+        arg[narg++] = v_apply(prev, v1, v2);
+      }
+    if (o == V_DONE) return narg == 1 ? arg[0] : (c->bad = 1, 0.0);
+    op[nop++] = o; c->p += len; expect_arg = 1;
+  }
+}
+static double var_eval(osph_sph *s, const char *text, int i)
+{
+  vctx c = {s, i, text, 0};
+  double v = v_formula(&c, "");
+  if (c.bad || *c.p) { fprintf(stderr, "sph_oracle: cannot evaluate variable formula '%s'\n", text); abort(); }
+  return v;
+}
+int osph_formula_check(const char *formula, const double atom[12], int type, int id, double step, double dt, double *value)
+{
+  osph_sph *s = calloc(1, sizeof *s);
+  double x[3], v[3], f[3], rm[1]; int ty[1] = {type}, tg[1] = {id};
+  if (atom) { memcpy(x, atom, sizeof x); memcpy(v, atom + 3, sizeof v); memcpy(f, atom + 6, sizeof f); rm[0] = atom[9]; }
+  else { memset(x, 0, sizeof x); memset(v, 0, sizeof v); memset(f, 0, sizeof f); rm[0] = 1.0; }
+  s->multiphase = 1; s->x = x; s->v = v; s->f = f; s->rmass = rm; s->type = ty; s->tag = tg; s->ntimestep = (long long)step; s->dt = dt;
+  vctx c = {s, 0, formula, 0};
+  double r = v_formula(&c, "");
+  int bad = c.bad || *c.p;
+  free(s);
+  if (bad) return fail("Invalid syntax in variable formula");
+  if (value) *value = r;
+  return 0;
+}
+/* FixAddForce::post_force, fix_addforce.cpp:243-330: the variable components are evaluated for the whole group first
+ * (Variable::compute_atom), then added */
+static void fix_addforce(osph_sph *s, ofix *fx)
+{
+  double *add = malloc(sizeof(double) * 3 * (s->nlocal + 1));
+  for (int i = 0; i < s->nlocal; i++)
+    for (int d = 0; d < 3; d++)
+      add[3*i+d] = !(s->mask[i] & fx->groupbit) ? 0.0 : (fx->formula[d] ? var_eval(s, fx->formula[d], i) : fx->acc[d]);
+  for (int i = 0; i < 3 * s->nlocal; i++) s->f[i] += add[i];
+  free(add);
+}
+
 /* FixSetMeso::post_force, constant value (fix_setmeso.cpp:180-236); Region::match with side in
  * (region.cpp:127-131, region_block.cpp:114-119, region_sphere.cpp:96-105) */
 static void fix_setmeso(osph_sph *s, ofix *fx)
@@ -1074,9 +1210,10 @@ static void fix_setmeso(osph_sph *s, ofix *fx)
       if (fx->match_inside && !in) continue;
       if (!fx->match_inside && in) continue;
     }
-    if (fx->which == 0) s->rho[i] = fx->value;
-    else if (fx->which == 1) s->e[i] = fx->value;
-    else s->e[i] = s->cv[i] * fx->value;      /* sph_t2energy */
+    const double value = fx->formula[0] ? var_eval(s, fx->formula[0], i) : fx->value;     /* varflag ATOM / EQUAL, :238-262 */
+    if (fx->which == 0) s->rho[i] = value;
+    else if (fx->which == 1) s->e[i] = value;
+    else s->e[i] = s->cv[i] * value;      /* sph_t2energy */
   }
 }
 /* FixEnforce2D::post_force, fix_enforce2d.cpp:77-89 */
@@ -1294,6 +1431,7 @@ int osph_post_force(osph_sph *s)
     else if (s->fix[i].kind == FIX_ENFORCE2D) fix_enforce2d(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_SETFORCE) fix_setforce(s, &s->fix[i]);
     else if (s->fix[i].kind == FIX_SETMESODE) fix_setmesode(s, &s->fix[i]);
+    else if (s->fix[i].kind == FIX_ADDFORCE) fix_addforce(s, &s->fix[i]);
   }
   return 0;
 }

@@ -32,6 +32,9 @@
 #define b200_fix_phase_change  osph_fix_phase_change
 #define b200_fix_setmeso       osph_fix_setmeso
 #define b200_fix_enforce2d     osph_fix_enforce2d
+#define b200_fix_setmeso_var   osph_fix_setmeso_var
+#define b200_fix_addforce      osph_fix_addforce
+#define b200_formula_check     osph_formula_check
 #define b200_fix_setforce      osph_fix_setforce
 #define b200_fix_setmesode     osph_fix_setmesode
 #define b200_fix_dt_reset      osph_fix_dt_reset

@@ -64,6 +64,8 @@ class Case:
                 out.append("comm_modify vel %s" % a[0])
             elif k == "timestep":
                 out.append("timestep %s" % _f(a[0]))
+            elif k == "variable":
+                out.append("variable %s %s %s" % (a[0], a[1], a[2]))
             elif k == "fix":
                 nfix += 1
                 out.append("fix f%d %s %s %s" % (nfix, a[0], a[1], " ".join(_f(v) for v in a[2:])))
@@ -97,6 +99,8 @@ class Case:
                 d.comm_modify(a[0])
             elif k == "timestep":
                 d.timestep(a[0])
+            elif k == "variable":
+                d.variable(*a)
             elif k == "fix":
                 nfix += 1
                 d.fix("f%d" % nfix, a[0], a[1], *a[2:])
@@ -171,6 +175,13 @@ _add(Case("heat2d_setmesode", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso"
           [("mass", "1", 1.0e-5), ("pair_style", "sph/heatconduction"), ("pair_coeff", "1 1", 1.0e-4, 2.0e-2),
            ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso/stationary"), ("fix", "all", "setmesode", 0.5, "region", "rheat")],
           40, regions=(("rheat", "block", 0.3, 0.7, "EDGE", "EDGE", "EDGE", "EDGE"),)))
+# fix setmeso with an atom-style variable (fix_setmeso.cpp:238-262; bubble_on_wall/bubble.lmp:143-144 sets a temperature profile this way):
+# the left third of the C1 bar is held on a profile in x, every step
+_add(Case("heat2d_setmeso_var", 2, "f p p", ((0, 0, 0), (1.0, 0.1, 0.001)), "meso", 1, _heat2d_create,
+          [("mass", "1", 1.0e-5), ("pair_style", "sph/heatconduction"), ("pair_coeff", "1 1", 1.0e-4, 2.0e-2),
+           ("timestep", 0.025), ("neighbor", 0.002), ("fix", "all", "meso/stationary"),
+           ("variable", "eprof", "atom", "1.0+sqrt(x)*(x<=0.3)+abs(-0.5)*(x>0.3)"), ("fix", "all", "setmeso", "meso_e", "v_eprof", "region", "rleft")],
+          40, regions=(("rleft", "block", "EDGE", 0.33, "EDGE", "EDGE", "EDGE", "EDGE"),)))
 _add(Case("heat3d", 3, "f p p", ((0, 0, 0), (0.4, 0.08, 0.08)), "meso", 1,
           """lattice sc 0.01
 create_atoms 1 box
@@ -219,6 +230,13 @@ _add(_dam("dam2d", 2, 60))
 # examples/USER/sph/water_collapse/water_collapse.lmp:32: the shipped 2-D dam break runs with a variable timestep
 _c = _dam("dam2d_dtreset", 2, 60)
 _c.cmds = _c.cmds + [("fix", "all", "dt/reset", 1, "NULL", 0.1 * 0.03 / 30.0, 2.0e-8, "units", "box")]      # xmax small enough to bite from step 0
+_add(_c)
+# fix addforce with atom-style variables, the body-force idiom of the shipped channel decks (poiseuille.lmp:57-58 `mass*${gx}*((y<..)-(y>..))`,
+# flow_around_cylinder/flow.lmp:84-85, bubble_on_wall/bubble.lmp:187-188 `mass*${gy}`): gravity as mass * g, plus a shear force that flips sign at y = 0.2
+_c = _dam("dam2d_addforce", 2, 40)
+_c.cmds = [c for c in _c.cmds if not (c[0] == "fix" and c[2] == "gravity")]
+_c.cmds = [("variable", "bodyfy", "atom", "mass*-9.81"), ("variable", "gx", "equal", "0.5*2.0^2/4"),
+           ("variable", "bodyfx", "atom", "mass*v_gx*((y<0.2)-(y>0.2))"), ("fix", "water", "addforce", "v_bodyfx", "v_bodyfy", 0.0)] + _c.cmds
 _add(_c)
 _add(_dam("dam3d", 3, 25))
 _add(_dam("dam2d_morris", 2, 40, morris=True))

@@ -52,3 +52,27 @@ def test_fix_setforce_setmesode_dt_reset_arguments():
     kinds = [f[0] for f in d.fixes]
     assert kinds == ["setforce", "setmesode", "dt/reset"]
     assert d.fixes[0][2] == ([0, 1, 1], [0.0, 0.0, 0.0])
+
+
+def test_variable_formulas_engine_compiler_vs_oracle():
+    """the engine's formula compiler + postfix evaluator (csrc/b200_expr.cuh, host side) against the oracle's direct evaluator
+    (Variable::evaluate restated) and against values worked out by hand; precedence and left association as variable.cpp:99-107,1641"""
+    import ctypes as C
+    import harness
+    eng, ora = pkg.load(), harness.oracle_api()
+    rng = np.random.default_rng(5)
+    formulas = ["mass*-9.81", "mass*0.5*((y<0.2)-(y>0.2))", "2^3^2", "-2^2", "1-2-3", "2*3%4", "1.5e-3*x+y/z", "!(x>y)||(vx<=vy&&fz!=0)",
+                "sqrt(abs(fx))+exp(-x)*ln(mass)+log(100)", "atan2(y,x)+sin(PI/2)+round(-2.5)+ceil(x)+floor(y)", "(type==2)*id+step*dt",
+                "((3.0-1)*y/1.0-((3.0-1)*0.1-1.0)/1.0)*(y-0.1<1.0)+3.0*(y-0.1>1.0)", "1.0+sqrt(x)*(x<=0.3)+abs(-0.5)*(x>0.3)", "2--3" if False else "2-(-3)"]
+    known = {"2^3^2": 64.0, "-2^2": 4.0, "1-2-3": -4.0, "2*3%4": 2.0, "2-(-3)": 5.0}
+    for f in formulas:
+        for _ in range(5):
+            atom = np.ascontiguousarray(rng.uniform(0.05, 2.0, 12)); ty, tag, step, dt = int(rng.integers(1, 4)), int(rng.integers(1, 1000)), 17.0, 2.5e-4
+            a, b = C.c_double(), C.c_double()
+            assert eng.formula_check(f.encode(), atom.ctypes.data_as(C.POINTER(C.c_double)), ty, tag, step, dt, C.byref(a)) == 0, (f, eng.last_error())
+            assert ora.formula_check(f.encode(), atom.ctypes.data_as(C.POINTER(C.c_double)), ty, tag, step, dt, C.byref(b)) == 0, f
+            assert a.value == b.value or abs(a.value - b.value) <= 1e-15 * abs(b.value), (f, a.value, b.value)
+            if f in known:
+                assert a.value == known[f], (f, a.value)
+    for bad in ("mass*", "foo(x)", "c_pe*2", "x+", "random(0,1,5)", "(x"):
+        assert eng.formula_check(bad.encode(), None, 1, 1, 0.0, 0.0, None) < 0, bad

@@ -61,7 +61,8 @@ def thermo_rows(stdout):
 
 
 @pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10), ("dam2d_dtreset", 30, 1e-9),
-                                            ("shock2d_shrink", 40, 1e-9), ("shock3d_shrink", 25, 1e-9), ("lj2d", 40, 1e-9)])
+                                            ("shock2d_shrink", 40, 1e-9), ("shock3d_shrink", 25, 1e-9), ("lj2d", 40, 1e-9),
+                                            ("dam2d_addforce", 30, 1e-9), ("heat2d_setmeso_var", 30, 1e-10)])
 def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
