@@ -573,20 +573,23 @@ static int comm_exchange(b200_sph *h, int nslots)
 
 // ------------------------------------------------------------- tile path ----
 // persistent launch of a tile kernel: as many CTAs as fit on the device (or tiles), dynamic shared memory opted in once per kernel
+// opt a tile kernel into the 227 KB of dynamic shared memory (once per kernel); returns what it may use
+static size_t tile_optin(const void *fp)
+{
+  static std::vector<std::pair<const void *, size_t>> opted;     // kernel -> dynamic shared memory it may use
+  for (auto &o : opted) if (o.first == fp) return o.second;
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, fp));
+  size_t maxdyn = TILE_SMEM_MAX - fa.sharedSizeBytes;
+  CK(cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxdyn));
+  opted.push_back({fp, maxdyn});
+  return maxdyn;
+}
 template <class K, class A> static void launch_tiles(b200_sph *h, K kern, const char *name, int nthreads, size_t smem, const A &args, int ntiles = -1, int reserve_sms = 0)
 {
   if (ntiles < 0) ntiles = h->ntiles;
   if (!ntiles) return;
-  static std::vector<std::pair<const void *, size_t>> opted;     // kernel -> dynamic shared memory it may use
   const void *fp = (const void *)kern;
-  size_t maxdyn = 0;
-  for (auto &o : opted) if (o.first == fp) maxdyn = o.second;
-  if (!maxdyn) {
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, fp));
-    maxdyn = TILE_SMEM_MAX - fa.sharedSizeBytes;
-    CK(cudaFuncSetAttribute(fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxdyn));
-    opted.push_back({fp, maxdyn});
-  }
+  const size_t maxdyn = tile_optin(fp);
   if (smem > maxdyn) throw std::string(name) + ": tile does not fit in shared memory";
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp, nthreads, smem));
@@ -679,7 +682,10 @@ static bool tile_rows(b200_sph *h)
     CK(cudaStreamSynchronize(h->st));
     int mx = h->h_flags[0];
     if (mx <= h->stride) { h->maxneigh = std::max<long long>(h->maxneigh, h->h_flags[11]); break; }
-    h->stride = ((int)(mx * 1.2) + 8 + 31) / 32 * 32;
+    // head room of 40 %: a longer row costs address space, not traffic (rows are read up to their counts), while every overflow later in
+    // the run costs a second build plus a cudaFree / cudaMalloc of both row arrays (seen as 10-170 ms outliers of one build, gpurun r02p / r02q)
+    if (getenv("B200_VERBOSE")) fprintf(stderr, "b200: step %lld, longest row %d > stride %d: rebuilding with longer rows\n", (long long)h->ntimestep, mx, h->stride);
+    h->stride = ((int)(mx * 1.4) + 8 + 31) / 32 * 32;
     if (attempt == 7) throw std::string("b200: neighbor row overflow");
   }
   return true;
@@ -1151,8 +1157,17 @@ static void run_pass_tile(b200_sph *h, const Pass &p)
       TileArgs A = tile_args(h, 0);
       A.tab[0] = h->d_tab[p.slots[0]];
       bool uni = tile_uni(h, T, A.uni[0]) && !h->tile_nouni;
-      size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
-      const int dsplit = getenv("B200_TILE_SPLIT") ? h->tile_split : 4;      // measured: 4 lanes per row (32 warps per SM) is fastest for the density pass
+      size_t smem = uni ? TileSmem<2, 0>::bytes(h->tile_cap) : TileSmem<2, 1>::bytes(h->tile_cap);
+      // lanes per row: 2 when two 512-thread CTAs then share an SM (one evaluates while the other sits at its tile barrier / bulk copies:
+      // C2 density 0.256 -> 0.211 ms, gpurun r02p), else 4 lanes in one 1024-thread CTA (round 1: beats 2 lanes in one CTA per SM)
+      int dsplit = 4;
+      if (uni) {
+        int occ = 0;
+        if (smem <= tile_optin((const void *)k_tile_rhosum<2, true>)) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_rhosum<2, true>, TILE_ROWS * 2, smem));
+        if (occ >= 2) dsplit = 2;
+      }
+      if (getenv("B200_TILE_SPLIT")) dsplit = h->tile_split;
+      if (const char *e = getenv("B200_DENSITY_SPLIT")) dsplit = atoi(e);
       tile_pass(h, A,
         [&](TileArgs &a, int reserve) {
           if (dsplit == 1) {
@@ -1941,19 +1956,27 @@ int b200_set_atoms(b200_sph *h, int n, const b200_atoms *a)
 }
 int b200_get_natoms(b200_sph *h, int *nlocal, int *nghost) { if (nlocal) *nlocal = h->nlocal; if (nghost) *nghost = h->nghost; return 0; }
 
-// output index of every owned device slot: the LAMMPS local index (one rank), or the rank of that index
-// when migration has made the local-index sequence sparse (several ranks)
-static std::vector<int> out_positions(b200_sph *h)
+// output index of every owned device slot: the LAMMPS local index (one rank), or the rank of that index among the owned atoms
+// when migration has made the local-index sequence sparse (several ranks).  On the device: mark the indices in use, scan, look up.
+__global__ void k_mark_orig(int n, const int *orig, int *flag) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) flag[orig[i]] = 1; }
+__global__ void k_rank_orig(int n, const int *orig, const int *scan, int *pos) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) pos[i] = scan[orig[i]]; }
+static const int *out_positions(b200_sph *h)
 {
-  int n = h->nlocal;
-  std::vector<int> orig(n), pos(n);
+  const int n = h->nlocal, m = std::max(h->next_orig, n) + 1;
+  h->flag.ensure((size_t)m + 2); h->perm.ensure(n + 1); ensure_scan_tmp(h, m + 2);
+  CK(cudaMemsetAsync(h->flag.p, 0, (size_t)(m + 1) * sizeof(int), h->st));
+  LAUNCH(h, k_mark_orig, nblk(n, 256), 256, n, h->C().orig.p, h->flag.p);
+  scan_exclusive(h, h->flag.p, m, h->scan_tmp.p);
+  LAUNCH(h, k_rank_orig, nblk(n, 256), 256, n, h->C().orig.p, h->flag.p, h->perm.p);
+  return h->perm.p;
+}
+
+static std::vector<int> out_positions_host(b200_sph *h)      // b200_get_neighbor_list (tests)
+{
+  std::vector<int> pos(h->nlocal);
+  const int *src = h->world > 1 ? out_positions(h) : h->C().orig.p;
   CK(cudaStreamSynchronize(h->st));
-  if (n) CK(cudaMemcpy(orig.data(), h->C().orig.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-  if (h->world == 1) return orig;
-  std::vector<int> idx(n);
-  for (int s = 0; s < n; s++) idx[s] = s;
-  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return orig[a] < orig[b]; });
-  for (int r = 0; r < n; r++) pos[idx[r]] = r;
+  if (h->nlocal) CK(cudaMemcpy(pos.data(), src, (size_t)h->nlocal * sizeof(int), cudaMemcpyDeviceToHost));
   return pos;
 }
 
@@ -1967,13 +1990,7 @@ int b200_get_atoms(b200_sph *h, int nmax, b200_atoms *a)
   size_t nd, ni;
   HostMirror m = stage_layout(h, n, a, &nd, &ni);
   const int *outpos = nullptr;
-  if (h->world > 1) {
-    std::vector<int> pos = out_positions(h);
-    h->perm.ensure(n);
-    CK(cudaMemcpyAsync(h->perm.p, pos.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    outpos = h->perm.p;
-  }
+  if (h->world > 1) outpos = out_positions(h);
   LAUNCH(h, k_unpack_atoms, nblk(n, 256), 256, n, m, pack_arrays(h), h->multiphase, outpos);
 #define DOWN(dev, host, w) if (a->host) CK(cudaMemcpyAsync(a->host, m.dev, (size_t)(w) * n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   FOR_FIELDS(DOWN)
@@ -2017,7 +2034,7 @@ int b200_get_neighbor_list(b200_sph *h, int nlocal, int *numneigh, long long nen
   if (!n) return 0;
   CK(cudaStreamSynchronize(h->st));
   std::vector<int> cnt(n), tag(na), img(na);
-  std::vector<int> orig = out_positions(h);
+  std::vector<int> orig = out_positions_host(h);
   CK(cudaMemcpy(cnt.data(), h->numneigh.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<int> cfar(n);
   CK(cudaMemcpy(cfar.data(), h->numfar.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));

@@ -785,15 +785,18 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
 {
   constexpr int NT = TILE_ROWS * SPLIT, LPW = 32 / SPLIT;        // LPW rows per warp, SPLIT lanes per row
   extern __shared__ __align__(128) unsigned char tile_smem[];
-  TileSmem<2, 1> S(tile_smem, A.cap);
+  // UNI: no per-type table in shared memory (its constants are kernel parameters), which is what lets two CTAs share an SM on
+  // the C2 tiles (2 x (3508 slots x 32 B + 0.6 KB) = 226 KB): one evaluates while the other waits at its tile barrier / bulk copies
+  constexpr int NK = UNI ? 0 : 1;
+  TileSmem<2, NK> S(tile_smem, A.cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  load_tab(S.T, A.tab[0]);
+  if (!UNI) load_tab(S.T, A.tab[0]);
   if (tid == 0) mbar_init(S.bar, 1);
-  const PairTab &T = S.T[0];
+  const PairTab &T = S.T[0];                                      // (not read when UNI)
   const TileUni &U = A.uni[0];
   const double2 *P0 = S.part, *P1 = S.part + A.cap;
   const int ntiles = A.ntiles, g_far = A.scan_far[0], g_mid = A.scan_far[2];
-  TileLoop<0x3, 1, NT> L(A, S, ntiles);
+  TileLoop<0x3, NK, NT> L(A, S, ntiles);
   L.start();
   while (const TileDesc *Dp = L.peek()) {
     const TileDesc &D = *Dp;
@@ -819,8 +822,8 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
       if (rb == 0) L.wait();
       double2 a = make_double2(0, 0), b = a;
       if (valid) { a = P0[myslot]; b = P1[myslot]; }
-      if (valid && T.iskip[ti]) valid = false;                    // atoms of skipped types keep their integrated rho
       const unsigned rowmask = (unsigned)(U.mapmask >> (ti * 8)) & 0xffu;
+      if (valid && (UNI ? rowmask == 0 : T.iskip[ti] != 0)) valid = false;     // atoms of skipped types keep their integrated rho; iskip = no mapped partner type
       double acc = 0.0;
       for (int pass = 0; pass < 3; pass++) {           // near row | mid entries (from the back of the far row) | far row
         if (pass && !(pass == 1 ? scan_mid : scan_far)) continue;
@@ -859,7 +862,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, SPLIT <= 2 ? 2 : 1) k_tile_
 #pragma unroll
       for (int o = lpw; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
       if (UNI) acc *= U.mass * U.c0;
-      if (valid && sub == 0) A.vr_out[row].w = T.mass[ti] * T.self0[ti] + acc;
+      if (valid && sub == 0) A.vr_out[row].w = (UNI ? U.mass * U.self : T.mass[ti] * T.self0[ti]) + acc;
     }
     L.release();
   }

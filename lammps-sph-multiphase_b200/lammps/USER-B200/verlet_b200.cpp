@@ -1,5 +1,5 @@
 /* ----------------------------------------------------------------------
-   run_style verlet/b200 -- see verlet_b200.h.  Single MPI rank per engine instance.
+   run_style verlet/b200 -- see verlet_b200.h.  One engine instance (one GPU) per MPI rank.
 ------------------------------------------------------------------------- */
 #include "string.h"
 #include "math.h"
@@ -44,7 +44,16 @@ void VerletB200::check(int rc) { if (rc < 0) error->all(FLERR, b200_last_error()
 void VerletB200::init()
 {
   Verlet::init();
-  if (comm->nprocs != 1) error->all(FLERR, "run_style verlet/b200: one MPI rank per engine instance (multi-GPU bricks: see DESIGN.md)");
+  // several MPI ranks = one engine instance (one GPU) per rank, LAMMPS' own brick decomposition handed to b200_comm_init (configure).
+  // The engine's halo is CommBrick with one ghost layer per swap: a multi-layer setup (comm_brick.cpp:150-170, maxneed > 1) and
+  // the tiled layout (comm_style tiled, comm_tiled.cpp) are refused here rather than approximated.
+  if (comm->nprocs > 1) {
+    if (comm->style != 0) error->all(FLERR, "run_style verlet/b200 supports comm_style brick");
+    if (comm->layout > 1) error->all(FLERR, "run_style verlet/b200 supports brick layouts (uniform, or non-uniform from balance shift)");      // enum{LAYOUT_UNIFORM,LAYOUT_NONUNIFORM,LAYOUT_TILED}, comm.cpp:44
+    for (int d = 0; d < domain->dimension; d++)
+      if (comm->cutghost[d] > domain->subhi[d] - domain->sublo[d])
+        error->all(FLERR, "run_style verlet/b200: the ghost cutoff exceeds the sub-domain (more than one ghost layer per swap)");
+  }
   if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton on");
   if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 supports orthogonal boxes");
   if (!atom->rho_flag || !atom->e_flag) error->all(FLERR, "run_style verlet/b200 requires atom_style meso or meso/multiphase");
@@ -53,7 +62,22 @@ void VerletB200::init()
 /* push everything LAMMPS parsed across the C-ABI (tables only, verbatim from the host objects) */
 void VerletB200::configure()
 {
-  if (!h) check(b200_create(&h, 0));
+  if (!h) {
+    // one rank per GPU: ranks of a node take the devices round robin (the launcher's binding, as -pk gpu does in lib/gpu)
+    int ndev = 1;
+    if (const char *e = getenv("B200_DEVICES_PER_NODE")) ndev = atoi(e) > 0 ? atoi(e) : 1;
+    check(b200_create(&h, comm->nprocs > 1 ? comm->me % ndev : 0));
+    if (comm->nprocs > 1) {
+      // NCCL rendezvous over MPI: rank 0 draws the unique id, everybody receives it (ncclGetUniqueId / ncclCommInitRank)
+      char id[128];
+      memset(id, 0, sizeof id);
+      if (comm->me == 0) check(b200_comm_unique_id(id));
+      MPI_Bcast(id, 128, MPI_CHAR, 0, world);
+      int procneigh[6];
+      for (int d = 0; d < 3; d++) { procneigh[2 * d] = comm->procneigh[d][0]; procneigh[2 * d + 1] = comm->procneigh[d][1]; }
+      check(b200_comm_init(h, comm->nprocs, comm->me, comm->procgrid, comm->myloc, procneigh, id));
+    }
+  }
   int n = atom->ntypes;
   int multiphase = atom->rmass_flag ? 1 : 0;
   check(b200_domain(h, domain->dimension, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi));
@@ -134,9 +158,15 @@ void VerletB200::download()
 {
   int nl, ng;
   check(b200_get_natoms(h, &nl, &ng));
-  if (nl != atom->nlocal) {                    // fix phase_change/b200 created atoms
+  if (nl != atom->nlocal) {                    // fix phase_change/b200 created atoms, or atoms migrated between the ranks' engines
     while (nl > atom->nmax) atom->avec->grow(0);
-    atom->nlocal = nl; atom->natoms = nl; atom->nghost = 0;
+    // what the engine does not carry starts from create_atom's defaults for atoms this rank has not held before (atom_vec_meso.cpp:760-790);
+    // image flags of wrapped atoms are not tracked by the engine (limits)
+    for (int i = atom->nlocal; i < nl; i++)
+      atom->image[i] = ((imageint) IMGMAX << IMG2BITS) | ((imageint) IMGMAX << IMGBITS) | IMGMAX;
+    atom->nlocal = nl; atom->nghost = 0;
+    bigint nblocal = nl;
+    MPI_Allreduce(&nblocal, &atom->natoms, 1, MPI_LMP_BIGINT, MPI_SUM, world);
   }
   b200_atoms a; memset(&a, 0, sizeof a);
   a.x = &atom->x[0][0]; a.v = &atom->v[0][0]; a.vest = &atom->vest[0][0]; a.f = &atom->f[0][0];
