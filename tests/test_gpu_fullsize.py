@@ -79,6 +79,35 @@ def test_c3_one_million_against_oracle():
     print("C3 1 M: %d neighbor entries, errors %s" % (dig[1], {k: "%.1e" % v for k, v in errs.items()}))
 
 
+def test_c4_one_million_phase_change_against_oracle():
+    """C4's styles (heat conduction with phase change + fix phase_change) at 1 M particles, three phase-change calls, against the oracle,
+    which restates fix phase_change including create_atom writing over the first live ghost slots while later candidates still read them
+    (fix_phase_change.cpp:456-457); the engine stages the new atoms instead (waiver 1).  ~900 insertions happen here.  The test
+    measures what the waiver costs: every insertion of the oracle must be made by the engine too, in the same order (same RNG walk), and
+    vice versa.  A new atom sits at x_i + dr e(colorgradient_i) with e built from normalised cross products of the colorgradient
+    (fix_phase_change.cpp:473-513), which amplifies the 1e-13 relative differences of the colorgradient sums where two of its components
+    nearly vanish (the poles of the bubble): new positions agree to ~3e-11 of the box, and the fields of their neighbors to 1e-8, not 1e-10."""
+    nx, nsteps = 100, 3
+    atoms = _mp_atoms(nx, "c4")
+    out = []
+    for mk in (pkg.B200Sim, harness.oracle_sim):
+        sim = mk(cases._bubble("c4", 3, nx, nsteps).deck())
+        sim.set_atoms(**atoms)
+        sim.setup(); sim.run(nsteps)
+        out.append((sim.get_atoms(), sim.counters()))
+        sim.close()
+    (a, ca), (b, cb) = out
+    n0 = len(atoms["type"])
+    assert ca["inserted"] == cb["inserted"] > 100 and ca["builds"] == cb["builds"] == nsteps, (ca, cb)
+    assert np.array_equal(a["tag"], b["tag"]) and np.array_equal(a["type"], b["type"])
+    dpos = np.abs(a["x"][n0:] - b["x"][n0:]).max()           # same insertions in the same order
+    errs = {k: relerr(a[k], b[k]) for k in ("x", "v", "f", "rho", "e", "de", "drho", "colorgradient", "rmass")}
+    print("C4 1 M, %d steps: %d insertions, identical order, positions of the new atoms within %.1e; errors %s" % (
+        nsteps, ca["inserted"], dpos, {k: "%.1e" % v for k, v in errs.items()}))
+    assert dpos <= 1e-9
+    assert all(v <= 1e-8 for v in errs.values()), errs
+
+
 def brute_rows(x, tag, lo, hi, cutsq, sample):
     """the reference's pair test (neigh_full.cpp:241-340: rsq = dx*dx + dy*dy + dz*dz <= cutneighsq, fp64, no FMA) for the sampled
     atoms against every particle and every periodic image (a ghost sits at x + shift, comm_brick.cpp:368); image code = 13 + sx + 3 sy + 9 sz"""
