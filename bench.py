@@ -50,7 +50,7 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle per launch of the dominant kernel (single-phase):
 #   sph/taitwater stage: R x24 + vest24 + rho8 + type4, W f24 + drho8 + de8 = 100 B
 BYTES_FORCE = 100
-FP64_NOTE = "profiles/r02_stage_full.txt: sm__pipe_fp64_cycles_active 57.6 %, 51 % of the fp64 lanes (dadd + dfma + dmul thread-instructions) for k_tile_force<K_TAIT> under ncu --set full (1 028 768 particles, 0.489 ms); round 1: 50.6 % at 0.539 ms"
+FP64_NOTE = "profiles/r02_force_v2_full.txt: k_tile_force<K_TAIT> under ncu --set full (1 028 768 particles, 0.512 ms, launch with the mid rows of part of the tiles): sm__pipe_fp64_cycles_active 50.0 %, shared-memory data pipe 71.6 %, 46 % of the fp64 lanes (dadd + dfma + dmul thread-instructions); 31 fp64 instructions per list entry (round 1: 42, 50.6 % at 0.539 ms)"
 BYTES_STEP = 464          # whole single-phase step (rhosum 36 + taitwater 100 + fix meso 200 + 128)
 BYTES_MP_LOOP, BYTES_MP_STEP = 228, 572        # multiphase density + colorgradient + force loop / whole step
 BYTES_C4_LOOP, BYTES_C4_STEP = 252, 596        # + heat/phasechange in the fused force pass
@@ -61,8 +61,8 @@ PARITY_CASES = ("dam3d", "heat3d", "droplet3d_static", "droplet3d", "droplet3d_h
 # ----------------------------------------------------------------------------- workload ----
 def dam_break_3d(scale=1.0, tiles=1):
     """C2 geometry; scale shrinks every edge (scale=0.5 -> ~1/8 of the particles).
-    tiles > 1 (weak scaling): the tank is `tiles` units long in x and holds one water column per unit,
-    so an (N,1,1) brick decomposition gives every GPU the same C2-sized load."""
+    tiles > 1 (weak scaling): `tiles` complete tanks (walls included) side by side in x, one water column each,
+    so an (N,1,1) brick decomposition gives every GPU exactly the C2 load of the 1-GPU run (1 028 768 particles at scale 1)."""
     dx = 0.01
     nwx, nwy, nwz = (max(4, int(round(v * scale))) for v in (100, 100, 80))      # water block (sites)
     nix, niy, niz = (max(6, int(round(v * scale))) for v in (160, 106, 106))     # tank inner size
@@ -71,7 +71,7 @@ def dam_break_3d(scale=1.0, tiles=1):
     NX, NY, NZ = unit * tiles, niy + 2 * nl, niz + nl                             # open top
     ix, iy, iz = np.meshgrid(np.arange(NX), np.arange(NY), np.arange(NZ), indexing="ij")
     ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
-    wall = (ix < nl) | (ix >= NX - nl) | (iy < nl) | (iy >= NY - nl) | (iz < nl)
+    wall = ((ix % unit) < nl) | ((ix % unit) >= unit - nl) | (iy < nl) | (iy >= NY - nl) | (iz < nl)      # every unit is a complete tank: the same particle count per GPU at every N
     water = (~wall) & ((ix % unit) >= nl) & ((ix % unit) < nl + nwx) & (iy < nl + nwy) & (iz < nl + nwz)
     keep = wall | water
     x = np.stack([(ix[keep] + 0.5) * dx, (iy[keep] + 0.5) * dx, (iz[keep] + 0.5) * dx], axis=1)
@@ -296,6 +296,7 @@ def run_dam_balance(pkg, scale, steps, warmup, rank, world, local, dist, torch):
                       "imbalance_max_over_mean": max(counts) / (sum(counts) / world),
                       "splits": None if splits is None else [[round(float(v), 6) for v in sp] for sp in splits]}
     out["speedup_balanced_over_uniform"] = out["uniform"]["ms_per_step"] / out["balanced"]["ms_per_step"]
+    out["ms_per_step"] = out["balanced"]["ms_per_step"]; out["particle_steps_s"] = out["balanced"]["particle_steps_s"]      # the record's own figures: the balanced run
     return out
 
 
@@ -531,8 +532,8 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_FORCE * n, "avg_launch_ms": dur * 1e3,
                 "share_of_step": f_ms / ms, "whole_step_GBs": BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
                 "fp64_pipe": FP64_NOTE,
-                "note": "bound by the fp64 pipe, not by HBM, at ~113 fp64 pair evaluations per particle (SURVEY 8d): the HBM fraction cannot approach 1; "
-                        "the ncu fp64-pipe utilisation of the same kernel is in profiles/ (see fp64_pipe)"}
+                "note": "bound by the fp64 pipe and the shared-memory data pipe together, not by HBM, at ~110 list entries per particle (SURVEY 8d): the HBM fraction cannot approach 1; "
+                        "fp64_frac = fp64 thread-instructions per launch (ncu) / live launch time / fp64 lane peak"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
