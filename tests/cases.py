@@ -360,6 +360,30 @@ displace_atoms all random %s %s %s 4711 units box""" % (lat, _f(dx), rsq, _f(rho
     return Case(name, dim, "p p p", box, "meso/multiphase", 2, create, cmds, nsteps)
 
 
+# examples/USER/sph/poiseuille/poiseuille.lmp with its vars.lmp values (nx 5 -> 10, ny 30): reverse Poiseuille flow in a periodic 2-D box, one type,
+# meso/multiphase, rhosum/multiphase + taitwater/multiphase, the body force as an atom-style variable that flips sign at Ly / 2, fix enforce2d
+def _poiseuille(name, nsteps):
+    nx, ny, Ly = 10, 30, 2e-3
+    dx = Ly / ny; Lx = dx * nx; h = 3.0 * dx
+    rho, c, eta, gx = 1e3, 1.25e-4, 1e-3, 1e-4
+    m = dx ** 2 * rho
+    dt = min(0.25 * h / c, 0.125 * h * h * rho / eta) * 0.25
+    create = """lattice sq %s origin 0.5 0.5 0.0
+create_atoms 1 region box
+set group all meso_rho %s
+set group all mass %s
+displace_atoms all random %s %s 0.0 9731 units box""" % (_f(dx), _f(rho), _f(m), _f(0.02 * dx), _f(0.02 * dx))
+    # (the shipped deck starts from the perfect lattice, where whole neighbor shells sit exactly on the cutoff and stay there -- rows move
+    #  rigidly in x -- so that list membership hangs on the last bit of every coordinate; the 2 % jitter keeps the fixture well-posed)
+    cmds = [("fix", "all", "meso"), ("neighbor", 0.0), ("neigh_modify", dict(delay=0, every=1)), ("comm_modify", "yes"),
+            ("pair_style", "hybrid/overlay", "sph/rhosum/multiphase 1", "sph/taitwater/multiphase"),
+            ("pair_coeff", "* *", "sph/taitwater/multiphase", rho, c, eta, 1.0, h, 0.0), ("pair_coeff", "* *", "sph/rhosum/multiphase", h),
+            ("timestep", dt), ("variable", "bodyfx", "atom", "mass*%s*((y<%s/2.0)-(y>%s/2.0))" % (_f(gx), _f(Ly), _f(Ly))),
+            ("fix", "all", "addforce", "v_bodyfx", 0.0, 0.0), ("fix", "all", "enforce2d")]
+    return Case(name, 2, "p p p", ((0, 0, 0), (Lx, Ly, dx)), "meso/multiphase", 1, create, cmds, nsteps)
+
+
+_add(_poiseuille("poiseuille2d", 60))
 _add(_droplet("droplet2d", 2, 30, 40))
 _add(_droplet("droplet3d", 3, 12, 20))
 _add(_droplet("droplet3d_heat", 3, 12, 15, heat="sph/heatconduction/multiphase"))

@@ -62,7 +62,7 @@ def thermo_rows(stdout):
 
 @pytest.mark.parametrize("name,nsteps,tol", [("dam2d", 40, 1e-9), ("heat2d", 60, 1e-10), ("droplet3d", 10, 1e-9), ("bubble2d", 20, 1e-8), ("shock2d", 30, 1e-9), ("heat2d_setmesode", 30, 1e-10), ("dam2d_dtreset", 30, 1e-9),
                                             ("shock2d_shrink", 40, 1e-9), ("shock3d_shrink", 25, 1e-9), ("lj2d", 40, 1e-9),
-                                            ("dam2d_addforce", 30, 1e-9), ("heat2d_setmeso_var", 30, 1e-10)])
+                                            ("dam2d_addforce", 30, 1e-9), ("heat2d_setmeso_var", 30, 1e-10), ("poiseuille2d", 50, 1e-9)])
 def test_same_deck_reference_vs_b200(name, nsteps, tol, tmp_path):
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("lmp_serial / lmp_b200 not built (they are built only where /root/reference exists)")
@@ -111,6 +111,25 @@ def test_host_end_of_step_fixes_fire(tmp_path):
         assert ra[0] == rb[0]
         assert relerr(np.array([float(v) for v in rb[1:]]), np.array([float(v) for v in ra[1:]])) <= 1e-5     # fix print writes %g-style 6 digits... compare at that precision
     assert relerr(b[:, 2:5], a[:, 2:5]) <= 1e-9
+
+
+def test_poiseuille_profile_by_fix_ave_spatial(tmp_path):
+    """the second half of examples/USER/sph/poiseuille/poiseuille.lmp: the velocity profile is collected by fix ave/spatial (a host
+    END_OF_STEP fix fed by a compute and an atom-style variable) while fix addforce/b200 drives the flow on the device"""
+    case = cases.CASES["poiseuille2d"]
+    nsteps = 40
+    extra = "\n".join(["compute vxav all reduce ave vx", "variable vx_cm atom vx-c_vxav",
+                       "fix av_vx all ave/spatial 5 4 20 y center 0.05 v_vx_cm file vx.av ave one units reduced"])
+    text = deck_text(case, nsteps).replace("run %d" % nsteps, extra + "\nrun %d" % nsteps)
+    a, a_out, b, b_out = _both(tmp_path, text)
+    prof = []
+    for d in ("ref", "b200"):
+        rows = [[float(v) for v in l.split()] for l in open(str(tmp_path / d / "vx.av")) if not l.startswith("#")]
+        prof.append(np.array([r for r in rows if len(r) == 4]))          # chunk rows: index coord ncount value
+    assert prof[0].shape == prof[1].shape and len(prof[0]) >= 20, (prof[0].shape, prof[1].shape)
+    assert np.array_equal(prof[0][:, :3], prof[1][:, :3])
+    assert relerr(prof[1][:, 3], prof[0][:, 3]) <= 1e-5                   # the file holds 6 significant digits
+    assert relerr(b[:, 5:8], a[:, 5:8]) <= 1e-9
 
 
 def test_unsupported_stepping_fix_is_refused(tmp_path):
