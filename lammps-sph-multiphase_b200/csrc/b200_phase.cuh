@@ -87,6 +87,10 @@ __device__ __forceinline__ double ranpark(int *seed)
   return (1.0 / 2147483647) * *seed;
 }
 
+// RanPark is the Park-Miller generator seed' = 16807 seed mod (2^31 - 1) (Schrage's split in ranpark() gives the same integers), so
+// k steps at once are one modular multiplication by 16807^k: the walk below evaluates the draws of 32 candidates in parallel.
+__device__ __forceinline__ int ranpark_skip(unsigned apow, int seed) { return (int)(((unsigned long long)apow * (unsigned)seed) % 2147483647ull); }
+
 // one thread per owned atom (device order): writes, indexed by LAMMPS local index,
 //   flag = 0 not a candidate | 1 candidate | 3 candidate that passes every non-random condition
 //   thr  = probability threshold of the draw, dev = device index
@@ -136,19 +140,31 @@ __global__ void __launch_bounds__(32) k_pc_walk(PcParams P, PcArrays a, const un
   const b200_phase_change_desc &d = P.d;
   const int lane = threadIdx.x;
   int seed = state[0], nins = 0;
+  // lane r holds 16807^(r+1) mod (2^31 - 1): the multiplier that advances the stream by r + 1 draws
+  unsigned apow = 16807u;
+  for (int k = 0; k < lane; k++) apow = (unsigned)(((unsigned long long)apow * 16807u) % 2147483647ull);
   for (int base = 0; base < ncand; base += 32) {
     int oc_l = base + lane < ncand ? clist[base + lane] : 0;
     unsigned char fl = base + lane < ncand ? flag[oc_l] : 0;
     double thr_l = base + lane < ncand ? thr[oc_l] : 0.0;
     unsigned cand = __ballot_sync(FULLMASK, fl != 0);
     while (cand) {
-      int b = __ffs(cand) - 1; cand &= cand - 1;
+      // The draw happens for every candidate, before the other tests (:210,212), one draw each as long as nobody passes.  All remaining
+      // candidates of this batch take theirs at once: candidate number r (0-based among the remaining ones) sees the stream r + 1 steps on.
+      // Only a candidate that passes consumes more (its position draws); the batch is then resumed behind it with the stream where that left it.
+      const int r = __popc(cand & ((1u << lane) - 1u));
+      const unsigned mult = __shfl_sync(FULLMASK, apow, r);
+      const double u_l = (1.0 / 2147483647) * ranpark_skip(mult, seed);
+      const unsigned pass = __ballot_sync(FULLMASK, ((cand >> lane) & 1u) && fl == 3 && u_l < thr_l);
+      if (!pass) {                                   // nobody: the stream moves on by the number of candidates
+        seed = ranpark_skip(__shfl_sync(FULLMASK, apow, __popc(cand) - 1), seed);
+        break;
+      }
+      const int b = __ffs(pass) - 1;                 // the first one that passes, in LAMMPS local order
+      const unsigned upto = cand & ((2u << b) - 1u);
+      seed = ranpark_skip(__shfl_sync(FULLMASK, apow, __popc(upto) - 1), seed);
+      cand &= ~upto;
       int oc = __shfl_sync(FULLMASK, oc_l, b);
-      double thr_c = __shfl_sync(FULLMASK, thr_l, b);
-      unsigned char f = __shfl_sync(FULLMASK, fl, b);
-      // the draw happens for every candidate, before the other tests (:210,212)
-      double u = ranpark(&seed);                     // all lanes advance the same stream redundantly
-      if (!(f == 3 && u < thr_c)) continue;
       int i = dev[oc];
       double4 xi = a.xt[i], ci = a.cgm[i];
       double coord[3]; bool ok = false;
