@@ -31,10 +31,22 @@ __global__ void k_slab_flag(int n, const double4 *xt, int dim, double lo, double
   int f = (c >= lo && c <= hi) ? 1 : 0;
   flag[i] = f; pos[i] = f;
 }
-__global__ void k_compact(int n, const int *flag, const int *pos, int *list)
+// both swaps of a dimension in one pass over the atoms (they scan the same atoms, comm_brick.cpp:722-725): flag / pos hold swap 0 in
+// [0, n) and swap 1 in [n, 2n), so ONE scan over 2n elements gives pos0 = P, count0 = P[n], pos1[i] = P[n + i] - P[n], count1 = P[2n] - P[n]
+__global__ void k_slab_flag2(int n, const double4 *xt, int dim, double lo0, double hi0, int on0, double lo1, double hi1, int on1, int *flag, int *pos)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) list[pos[i]] = i;
+  if (i >= n) return;
+  double4 p = xt[i];
+  double c = dim == 0 ? p.x : (dim == 1 ? p.y : p.z);
+  int f0 = (on0 && c >= lo0 && c <= hi0) ? 1 : 0, f1 = (on1 && c >= lo1 && c <= hi1) ? 1 : 0;
+  flag[i] = f0; pos[i] = f0; flag[n + i] = f1; pos[n + i] = f1;
+}
+// bias: where the offsets of this swap start inside a shared scan (NULL = 0)
+__global__ void k_compact(int n, const int *flag, const int *pos, int *list, const int *bias)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) list[pos[i] - (bias ? *bias : 0)] = i;
 }
 
 __device__ __forceinline__ double shifted(double c, double shift) { return shift != 0.0 ? __dadd_rn(c, shift) : c; }
@@ -82,13 +94,14 @@ __global__ void k_unpack_border(Geom g, int n, int first, CommArrays a, const do
 // record k and entered in the send list; buf[0] (the message header) carries the true count pos[nlast], so the receiver -- who
 // posted a receive of the same cap, derived from the count of the previous build on both sides -- learns how many records are
 // valid, and both sides learn about an overflow (count > cap) from the same number.
-__global__ void k_pack_border_compact(int nlast, const int *flag, const int *pos, int cap, int *list, CommArrays a, int dim, double shift,
+__global__ void k_pack_border_compact(int nlast, const int *flag, const int *pos, const int *bias, int cap, int *list, CommArrays a, int dim, double shift,
                                       int imgstep, int swapcode, double *buf)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) buf[0] = (double)pos[nlast];
+  const int b0 = bias ? *bias : 0;
+  if (i == 0) buf[0] = (double)(pos[nlast] - b0);
   if (i >= nlast || !flag[i]) return;
-  int k = pos[i];
+  int k = pos[i] - b0;
   if (k >= cap) return;
   list[k] = i;
   double4 x = a.xt[i], vr = a.vr[i], v = a.vm[i], c = a.cgm[i];

@@ -67,6 +67,31 @@ __global__ void k_scan_block(int *data, int n, int *sums)
 #pragma unroll
   for (int k = 0; k < SCAN_E; k++) { if (base + k < n) data[base + k] = excl; excl += v[k]; }
 }
+// the per-block totals of k_scan_block -> exclusive offsets in place, grand total to *total: ONE CTA walks them (<= 62 500 totals for
+// 64 M elements), which replaces the recursion of round 1 (two more scan levels + three device copies per scan: the ghost construction
+// of a 1 M-particle box was 85 launches, profiles/r02_launches_c3.csv)
+__global__ void __launch_bounds__(1024) k_scan_sums(int *sums, int nb, int *total)
+{
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, per = (nb + 1023) / 1024, lo = min(tid * per, nb), hi = min(lo + per, nb);
+  int t = 0;
+  for (int k = lo; k < hi; k++) t += sums[k];
+  int incl = t;                                                   // inclusive scan of the threads' partial sums
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULLMASK, incl, o); if ((tid & 31) >= o) incl += v; }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = wsum[tid], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULLMASK, wi, o); if (tid >= o) wi += v; }
+    wsum[tid] = wi - w;                                           // exclusive offset of warp tid
+    if (tid == 31) *total = wi;
+  }
+  __syncthreads();
+  int run = wsum[tid >> 5] + incl - t;
+  for (int k = lo; k < hi; k++) { int v = sums[k]; sums[k] = run; run += v; }
+}
 __global__ void k_scan_add(int *data, int n, const int *sums)
 {
   int i = blockIdx.x * SCAN_T * SCAN_E + threadIdx.x;

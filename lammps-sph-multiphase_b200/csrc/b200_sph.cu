@@ -221,13 +221,8 @@ static void scan_exclusive(b200_sph *h, int *data, int n, int *scratch)
   if (n <= 0) { CK(cudaMemsetAsync(data, 0, sizeof(int), h->st)); return; }      // an empty rank (no owned atoms, no slots): total 0
   int per = SCAN_T * SCAN_E, nb = (n + per - 1) / per;
   LAUNCH(h, k_scan_block, nb, SCAN_T, data, n, scratch);
-  if (nb == 1) {
-    CK(cudaMemcpyAsync(data + n, scratch, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
-  } else {
-    scan_exclusive(h, scratch, nb, scratch + nb + 2);
-    LAUNCH(h, k_scan_add, nb, SCAN_T, data, n, scratch);
-    CK(cudaMemcpyAsync(data + n, scratch + nb, sizeof(int), cudaMemcpyDeviceToDevice, h->st));
-  }
+  LAUNCH(h, k_scan_sums, 1, 1024, scratch, nb, data + n);
+  if (nb > 1) LAUNCH(h, k_scan_add, nb, SCAN_T, data, n, scratch);
 }
 
 static bool zones_on(const b200_sph *h) { return h->zone_local && h->far_margin > 0.0 && h->rows_tiled && !h->multiphase && h->ntiles > 0; }
@@ -377,11 +372,12 @@ static void comm_borders(b200_sph *h)
     const int k1 = dim_end(h, k0), dim = h->swaps[k0].dim, ns = k1 - k0;
     const int nlast = h->nlocal + h->nghost;                 // both swaps of a dimension scan the atoms present before it (:722-725)
     int *flag[2], *pos[2]; int capS[2], capR[2]; size_t soff[2], roff[2], nsd[2], nrd[2]; double *rbuf[2];
-    h->flag.ensure((size_t)2 * (nlast + 2)); h->pos.ensure((size_t)2 * (nlast + 2)); ensure_scan_tmp(h, nlast + 2);
+    if (ns != 2) throw std::string("b200: a dimension with other than two swaps (more than one ghost layer)");
+    h->flag.ensure((size_t)2 * nlast + 4); h->pos.ensure((size_t)2 * nlast + 4); ensure_scan_tmp(h, 2 * (size_t)nlast + 4);
     size_t so = 0, ro = 0;
     for (int q = 0; q < ns; q++) {
       Swap &s = h->swaps[k0 + q];
-      flag[q] = h->flag.p + (size_t)q * (nlast + 2); pos[q] = h->pos.p + (size_t)q * (nlast + 2);
+      flag[q] = h->flag.p + (size_t)q * nlast; pos[q] = h->pos.p + (size_t)q * nlast;      // one scan serves both swaps (k_slab_flag2)
       // cap from the last count of this swap: the sender's last nsend IS the receiver's last nrecv, so both sides size alike
       capS[q] = (s.do_send && s.last_nsend >= 0) ? s.last_nsend + s.last_nsend / 4 + 64 : -1;
       capR[q] = (s.do_recv && s.last_nrecv >= 0) ? s.last_nrecv + s.last_nrecv / 4 + 64 : -1;
@@ -391,21 +387,26 @@ static void comm_borders(b200_sph *h)
       s.nsend = s.nrecv = 0;
     }
     h->sendbuf.ensure(so + 1); h->recvbuf.ensure(ro + 1);
-    // senders: flag + scan (+ compacting pack where a cap exists)
+    // senders: flag both swaps in one pass, one scan (+ compacting pack where a cap exists)
+    const int *bias[2] = {nullptr, h->pos.p + nlast};             // swap 1's offsets start at count0 = P[nlast]
+    if (nlast) {
+      Swap &s0 = h->swaps[k0], &s1 = h->swaps[k0 + 1];
+      LAUNCH(h, k_slab_flag2, nblk(nlast, B), B, nlast, h->C().xt.p, dim, s0.slablo, s0.slabhi, s0.do_send ? 1 : 0, s1.slablo, s1.slabhi, s1.do_send ? 1 : 0,
+             h->flag.p, h->pos.p);
+      scan_exclusive(h, h->pos.p, 2 * nlast, h->scan_tmp.p);
+    } else CK(cudaMemsetAsync(h->pos.p, 0, 2 * sizeof(int), h->st));
     for (int q = 0; q < ns; q++) {
       Swap &s = h->swaps[k0 + q];
       if (!s.do_send) continue;
-      if (nlast) {
-        LAUNCH(h, k_slab_flag, nblk(nlast, B), B, nlast, h->C().xt.p, dim, s.slablo, s.slabhi, flag[q], pos[q]);
-        scan_exclusive(h, pos[q], nlast, h->scan_tmp.p);
-      } else CK(cudaMemsetAsync(pos[q], 0, sizeof(int), h->st));
       if (capS[q] >= 0) {
         s.sendlist.ensure(capS[q] + 1);
-        LAUNCH(h, k_pack_border_compact, nblk(std::max(nlast, 1), B), B, nlast, flag[q], pos[q], capS[q], s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep,
+        LAUNCH(h, k_pack_border_compact, nblk(std::max(nlast, 1), B), B, nlast, flag[q], pos[q], bias[q], capS[q], s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep,
                k0 + q + 1, h->sendbuf.p + soff[q]);
       }
-      CK(cudaMemcpyAsync(h->h_flags + 28 + q, pos[q] + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     }
+    // P[nlast] = count0, P[2 nlast] = count0 + count1 (a swap that does not send flagged nothing)
+    CK(cudaMemcpyAsync(h->h_flags + 28, h->pos.p + nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->h_flags + 29, h->pos.p + 2 * (size_t)nlast, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     // fast path: header + cap records in one grouped call for the swaps that have history on both ends
     for (int q = 0; q < ns; q++) {
       Swap &s = h->swaps[k0 + q];
@@ -419,7 +420,7 @@ static void comm_borders(b200_sph *h)
     bool redo[2] = {false, false};
     for (int q = 0; q < ns; q++) {
       Swap &s = h->swaps[k0 + q];
-      s.nsend = s.do_send ? h->h_flags[28 + q] : 0;
+      s.nsend = s.do_send ? (q == 0 ? h->h_flags[28] : h->h_flags[29] - h->h_flags[28]) : 0;
       if (s.do_send && (capS[q] < 0 || s.nsend > capS[q])) redo[q] = true;
       if (s.do_recv && capR[q] >= 0) { s.nrecv = (int)h->h_red[14 + q]; if (s.nrecv > capR[q]) redo[q] = true; }
       else if (s.do_recv) redo[q] = true;
@@ -437,7 +438,7 @@ static void comm_borders(b200_sph *h)
         s.sendlist.ensure(s.nsend + 1);
         h->xs[q].ensure((size_t)s.nsend * NB_BORDER + 2);
         if (s.nsend) {
-          LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, flag[q], pos[q], s.sendlist.p);
+          LAUNCH(h, k_compact, nblk(nlast, B), B, nlast, flag[q], pos[q], s.sendlist.p, bias[q]);
           LAUNCH(h, k_pack_border, nblk(s.nsend, B), B, s.nsend, s.sendlist.p, h->comm_arrays(), dim, s.shift, s.imgstep, k0 + q + 1, h->xs[q].p + 1);
         }
       }
@@ -536,7 +537,7 @@ static int comm_exchange(b200_sph *h, int nslots)
     h->perm.ensure(nsend + 1);
     h->sendbuf.ensure((size_t)nsend * NB_EXCHANGE + 1);
     if (nsend) {
-      LAUNCH(h, k_compact, nblk(nslots, B), B, nslots, h->flag.p, h->pos.p, h->perm.p);
+      LAUNCH(h, k_compact, nblk(nslots, B), B, nslots, h->flag.p, h->pos.p, h->perm.p, (const int *)nullptr);
       LAUNCH(h, k_pack_exchange, nblk(nsend, B), B, nsend, h->perm.p, h->comm_arrays(), h->alive.p, h->sendbuf.p);
     }
     // the whole buffer goes to both neighbours; each keeps what falls inside its bounds (:640-664)
