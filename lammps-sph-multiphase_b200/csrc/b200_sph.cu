@@ -672,10 +672,11 @@ static bool tile_rows(b200_sph *h)
       B.ntiles = nt;
       bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
       if (const char *e = getenv("B200_BUILD_NT")) small = atoi(e) == 128;
-#define BUILD_LAUNCH(U, M) do { if (small) launch_tiles(h, k_tile_build<U, M, 128>, "k_tile_build", 128, bsm, B, nt); \
-                                else launch_tiles(h, k_tile_build<U, M, 256>, "k_tile_build", 256, bsm, B, nt); } while (0)
-      if (mp) { if (B.uni) BUILD_LAUNCH(true, true); else BUILD_LAUNCH(false, true); }
-      else { if (B.uni) BUILD_LAUNCH(true, false); else BUILD_LAUNCH(false, false); }
+      const bool zones = h->far_margin > 0.0 || !B.uni;      // skin 0: no far / mid rows to split off
+#define BUILD_LAUNCH(U, M, Z) do { if (small) launch_tiles(h, k_tile_build<U, M, 128, Z>, "k_tile_build", 128, bsm, B, nt); \
+                                   else launch_tiles(h, k_tile_build<U, M, 256, Z>, "k_tile_build", 256, bsm, B, nt); } while (0)
+      if (mp) { if (!B.uni) BUILD_LAUNCH(false, true, true); else if (zones) BUILD_LAUNCH(true, true, true); else BUILD_LAUNCH(true, true, false); }
+      else { if (!B.uni) BUILD_LAUNCH(false, false, true); else if (zones) BUILD_LAUNCH(true, false, true); else BUILD_LAUNCH(true, false, false); }
 #undef BUILD_LAUNCH
     }
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));

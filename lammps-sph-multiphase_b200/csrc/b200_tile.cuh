@@ -287,7 +287,9 @@ template <bool UNI> __device__ __forceinline__ int tile_exact_class(const TileBu
 // atoms whose half list holds (i,g) -- what the reference adds to ghost atoms and reverse-communicates.
 // NT: 256 threads for big tiles (C2: 8 chunks of 32 rows per tile), 128 when the tiles are small (more CTAs per SM to overlap the
 // per-tile barriers); the (cell, chunk) work items of a tile are handed to the warps through a shared counter.
-template <bool UNI, bool MP, int NT>
+// ZONES = false (decks with skin 0, e.g. the shipped multiphase decks: rebuilt every step, every entry is a near entry): the far / mid
+// compares of phase A and their entry loops are compiled out -- 2 of the 4 compares per candidate.
+template <bool UNI, bool MP, int NT, bool ZONES>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __grid_constant__ TileBuildArgs A)
 {
   constexpr int TILE_BUILD_NT = NT;
@@ -419,13 +421,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
                 const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 in = __funnelshift_l(__float_as_uint(rsq - cut_lo), in, 1);
                 mb = __funnelshift_l(__float_as_uint(rsq - cut_hi), mb, 1);
-                if (UNI) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
+                if (UNI && ZONES) { fr = __funnelshift_l(__float_as_uint(rsq - far_hi), fr, 1); md = __funnelshift_l(__float_as_uint(rsq - mid_hi), md, 1); }   // 1 = NOT surely far / mid
               }
               nq = k + 1;
               if (bj + 4 * k + 4 >= s1) break;
             }
             // candidate bj + i sits at bit 4 nq - 1 - i: back to natural order
-            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq)); fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq));
+            in = __brev(in << (32 - 4 * nq)); mb = __brev(mb << (32 - 4 * nq));
+            if (UNI && ZONES) { fr = ~__brev(fr << (32 - 4 * nq)); md = ~__brev(md << (32 - 4 * nq)); }
+            else if (UNI) fr = md = 0;
             // only the slots of [s0, s1), and never the row particle itself
             unsigned vm = (s1 - bj >= 32) ? 0xffffffffu : ((1u << (s1 - bj)) - 1u);
             if (bj < s0) vm &= ~((1u << (s0 - bj)) - 1u);
@@ -447,8 +451,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
                 if (more) { idx = __ffs((int)border) - 1; border &= border - 1; pj = A.xt[dev_of(bj + idx)]; }
                 const int cls = tile_exact_class<true>(A, pI, pc);
                 if (cls) in |= 1u << cur;
-                if (cls == 2) fr |= 1u << cur; else fr &= ~(1u << cur);
-                if (cls == 3) md |= 1u << cur; else md &= ~(1u << cur);
+                if (ZONES) {
+                  if (cls == 2) fr |= 1u << cur; else fr &= ~(1u << cur);
+                  if (cls == 3) md |= 1u << cur; else md &= ~(1u << cur);
+                }
                 if (!more) break;
               }
             }
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 0) k_tile_build(const __gr
               if (cls == 3) md |= 1u << idx; else md &= ~(1u << idx);
             }
             // phase B: entries straight from the masks (one-sided zone thresholds: md = surely beyond cut + mid margin, fr = surely beyond cut + far margin)
-            unsigned nearm = in & ~fr & ~md, midm = in & ~fr & md, farm = in & fr;
+            unsigned nearm = ZONES ? in & ~fr & ~md : in, midm = ZONES ? in & ~fr & md : 0u, farm = ZONES ? in & fr : 0u;
             while (nearm) {
               const int idx = __ffs((int)nearm) - 1; nearm &= nearm - 1;
               const int slot = bj + idx;
