@@ -50,7 +50,7 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle per launch of the dominant kernel (single-phase):
 #   sph/taitwater stage: R x24 + vest24 + rho8 + type4, W f24 + drho8 + de8 = 100 B
 BYTES_FORCE = 100
-FP64_NOTE = "profiles/r02_force_v2_full.txt: k_tile_force<K_TAIT> under ncu --set full (1 028 768 particles, 0.512 ms, launch with the mid rows of part of the tiles): sm__pipe_fp64_cycles_active 50.0 %, shared-memory data pipe 71.6 %, 46 % of the fp64 lanes (dadd + dfma + dmul thread-instructions); 31 fp64 instructions per list entry (round 1: 42, 50.6 % at 0.539 ms)"
+FP64_NOTE = "profiles/r02_final_full.txt: k_tile_force<K_TAIT> under ncu --set full (1 028 768 particles, 0.459 ms): sm__pipe_fp64_cycles_active 50.4 %, shared-memory data pipe 69.5 %, 47 % of the fp64 lanes (dadd + dfma + dmul thread-instructions); 31 fp64 instructions per list entry (round 1: 42, 50.6 % at 0.539 ms)"
 BYTES_STEP = 464          # whole single-phase step (rhosum 36 + taitwater 100 + fix meso 200 + 128)
 BYTES_MP_LOOP, BYTES_MP_STEP = 228, 572        # multiphase density + colorgradient + force loop / whole step
 BYTES_C4_LOOP, BYTES_C4_STEP = 252, 596        # + heat/phasechange in the fused force pass
