@@ -1384,7 +1384,7 @@ static void far_flags(b200_sph *h)
   if (h->far_margin > 0.0 && h->nlocal)
     LAUNCH(h, k_far_flag, 1, 1, h->d_dmaxsq, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->d_scan_far);
   if (zones_on(h))
-    LAUNCH(h, k_tile_zone, nblk(h->ntiles, 128), 128, h->tiles.p, h->ntiles, h->celld.p, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->tzone.p);
+    LAUNCH(h, k_tile_zone, nblk((long long)h->ntiles * 32, 128), 128, h->tiles.p, h->ntiles, h->celld.p, h->far_margin * h->far_margin, h->mid_margin * h->mid_margin, h->tzone.p);
 }
 // Neighbor::decide, neighbor.cpp:1332-1347 (+ check_distance :1360-1410)
 static int neigh_decide(b200_sph *h)

@@ -39,6 +39,13 @@
 #define TILE_SLOT_BITS 13
 #define TILE_SLOT_MASK 0x1fffu
 #define TILE_MAXSLOTS 8190
+#ifndef TILE_FORCE_UNROLL
+#define TILE_FORCE_UNROLL 8      // neighbors of a group evaluated side by side in the single-phase force body (A/B: tools/gpu_r02aa.sh)
+#endif
+#ifndef TILE_MPFORCE_UNROLL
+#define TILE_MPFORCE_UNROLL 8      // measured on the C3 styles: 8 -> 1.253 ms, 4 -> 1.278, 2 -> 1.332 (single-phase: 8 -> 0.483, 4 -> 0.493)
+#endif
+constexpr int kForceUnroll = TILE_FORCE_UNROLL, kMpForceUnroll = TILE_MPFORCE_UNROLL;
 #define TILE_MP_NPART 9           // record parts of the multiphase force pass (P0..P8, see k_tile_records_mp)
 #define TILE_SMEM_MAX 232448     // 227 KB opt-in dynamic shared memory per CTA on sm_100
 // multiphase entries carry two more flags (their records are 64-128 B, so a tile never holds more than 2047 slots):
@@ -572,15 +579,17 @@ __global__ void k_row_cells(int n, const int *perm2, const int *cellid, int *row
 // rows AND candidates, i.e. over the atoms of the cells of its candidate ranges (celld).  A handful of fast atoms (a jet, a free
 // surface) then no longer switches the far rows on for the whole domain.
 __global__ void k_tile_zone(const TileDesc *tiles, int ntiles, const unsigned *celld, double marginsq, double midmarginsq, unsigned char *tzone)
-{
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+{ // one warp per tile: the lanes share out the cells of its candidate ranges (a thread per tile walked ~50 dependent loads: 19 us per launch)
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= ntiles) return;
   const TileDesc &D = tiles[t];
   unsigned m = 0;
   for (int r = 0; r < D.nrange; r++)
-    for (int k = 0; k < D.rncell[r]; k++) m = max(m, celld[D.rcell[r] + k]);
+    for (int k = lane; k < D.rncell[r]; k += 32) m = max(m, celld[D.rcell[r] + k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULLMASK, m, o));
   const double d = 4.0 * (double)__uint_as_float(m);
-  tzone[t] = (unsigned char)((d >= 0.99 * marginsq ? 1 : 0) | (d >= 0.99 * midmarginsq ? 2 : 0));
+  if (lane == 0) tzone[t] = (unsigned char)((d >= 0.99 * marginsq ? 1 : 0) | (d >= 0.99 * midmarginsq ? 2 : 0));
 }
 
 // --------------------------------------------------------------- records ----
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
           const uint4 E = En;
           if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);     // next group in flight while this one is evaluated
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
-#pragma unroll
+#pragma unroll kForceUnroll
           for (int e = 0; e < 8; e++) {
             const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
             const int slot = ent & TILE_SLOT_MASK, tj = ent >> TILE_SLOT_BITS;
@@ -1357,7 +1366,7 @@ __global__ void __launch_bounds__(TILE_MP_NT, 1) k_tile_force_mp(const __grid_co
           const uint4 E = En;
           if (gi + split < ng) En = ldg_nc_u4(lp + (gi + split) * dir);
           const unsigned w[4] = {E.x, E.y, E.z, E.w};
-#pragma unroll 4
+#pragma unroll kMpForceUnroll
           for (int e = 0; e < 8; e++) {
             const unsigned ent = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
             // an owned row skips the ghost pairs the other side owns; empty entries have type 0 (mapped nowhere, cutsq = -1)
