@@ -53,6 +53,7 @@ typedef struct {
   int which, region_kind, match_inside; double value, region[6];
   int fset[3]; double fvalue[3];   /* fix setforce */
   char *formula[3];                /* fix addforce x y z / fix setmeso value: text of the v_ variable, or NULL */
+  int pc_nins, pc_nlocal0;         /* fix phase_change between its local part and its finish: insertions of this call, nlocal before them */
   int nevery, minbound, maxbound; double tmin, tmax, xmax;   /* fix dt/reset */
   osph_phase_change_desc pc;
   long long next_reneighbor;
@@ -1333,7 +1334,8 @@ static int pc_insert_one_atom(osph_sph *s, ofix *fx, const double *coord)
   return 1;
 }
 
-static int fix_phase_change_pre_exchange(osph_sph *s, ofix *fx)
+/* FixPhaseChange::pre_exchange up to the reverse communication of dmass (:167-323), on one rank: 0 = not due this step, 1 = done */
+static int pc_local(osph_sph *s, ofix *fx)
 {
   const osph_phase_change_desc *pc = &fx->pc;
   if (fx->next_reneighbor != s->ntimestep) return 0;
@@ -1388,23 +1390,36 @@ static int fix_phase_change_pre_exchange(osph_sph *s, ofix *fx)
     double energy_aux = 0.5 * (s->e[i] - pc->Hwv);
     s->e[i] = energy_aux; s->e[m] = energy_aux;
   }
-  comm_reverse_dmass(s); /* :324 (uses the old ghost slots, some now overwritten by new atoms -- as in the reference) */
-  for (int i = 0; i < nlocal; i++) {
+  fx->pc_nins = nins; fx->pc_nlocal0 = nlocal;
+  return 1;
+}
+/* after comm->reverse_comm_fix(this) (:324): the mass debit and energy renormalisation of the atoms owned before the call (:324-332),
+ * then tag_extend / nghost = 0 when ANY rank inserted (:338-350).  itag = first tag for this rank's untagged atoms (Atom::tag_extend, atom.cpp:598-630) */
+static void pc_finish(osph_sph *s, ofix *fx, int ninsall, int itag)
+{
+  double *dmass = s->drho;
+  for (int i = 0; i < fx->pc_nlocal0; i++) {
     double mold = s->rmass[i];
     s->rmass[i] -= dmass[i];
     s->e[i] = s->e[i] * mold / s->rmass[i];
     dmass[i] = 0;
   }
-  fx->next_reneighbor += pc->nfreq;
-  if (nins > 0) {
-    /* atom->tag_extend (atom.cpp): new tags = maxtag+1.. in local order; nghost = 0 */
-    int maxtag = 0;
-    for (int i = 0; i < s->nlocal; i++) if (s->tag[i] > maxtag) maxtag = s->tag[i];
-    for (int i = 0; i < s->nlocal; i++) if (s->tag[i] == 0) s->tag[i] = ++maxtag;
+  fx->next_reneighbor += fx->pc.nfreq;
+  if (ninsall > 0) {
+    for (int i = 0; i < s->nlocal; i++) if (s->tag[i] == 0) s->tag[i] = itag++;
     s->nghost = 0;
     for (int k = 0; k < s->nswap; k++) s->sendnum[k] = 0;
-    s->ninserted += nins;
+    s->ninserted += fx->pc_nins;
   }
+}
+static int fix_phase_change_pre_exchange(osph_sph *s, ofix *fx)
+{
+  int did = pc_local(s, fx);
+  if (did <= 0) return did;
+  comm_reverse_dmass(s); /* :324 (uses the old ghost slots, some now overwritten by new atoms -- as in the reference) */
+  int maxtag = 0;
+  for (int i = 0; i < s->nlocal; i++) if (s->tag[i] > maxtag) maxtag = s->tag[i];
+  pc_finish(s, fx, fx->pc_nins, maxtag + 1);
   return 0;
 }
 
@@ -1565,8 +1580,8 @@ int osph_run(osph_sph *s, int nsteps)
    P ranks in one process (test infrastructure for the multi-GPU path): every rank is an osph_sph of its own with a brick
    sub-domain; the collective steps of CommBrick run in lock step over the array of ranks, reading the sender's arrays
    directly where MPI would move a buffer.  Restated for maxneed = 1 (one ghost layer; uniform bricks or the non-uniform cuts of
-   `balance ... shift`, every brick at least one ghost cutoff long), no fix phase_change
-   (it draws one RNG stream per rank) and no shrink-wrapped faces.
+   `balance ... shift`, every brick at least one ghost cutoff long) and no shrink-wrapped faces; fix phase_change runs with one RanPark
+   stream per rank (w_phase_change).
    ====================================================================== */
 
 /* CommBrick::setup, comm_brick.cpp:150-386, for this rank's place in the grid */
@@ -1757,7 +1772,6 @@ static int w_check(osph_sph **R, int n)
     if (!R[r]->inworld || R[r]->me != r) return fail("world: rank r must have been given osph_comm_init(world, r, ...)");
     if (!R[r]->cutneighsq) return fail("world setup: b200_neighbor not called");
     if (R[r]->shrink) return fail("world: shrink-wrapped boundaries are not restated for P > 1");
-    for (int i = 0; i < R[r]->nfix; i++) if (R[r]->fix[i].kind == FIX_PHASE_CHANGE) return fail("world: fix phase_change is not restated for P > 1");
   }
   return 0;
 }
@@ -1770,8 +1784,35 @@ static int w_pair_compute_all(osph_sph **R, int n)
   }
   return 0;
 }
+/* FixPhaseChange::pre_exchange on every rank (modify->pre_exchange, verlet.cpp:241): every rank walks ITS copy of the RanPark stream (all
+ * constructed from the same seed, fix_phase_change.cpp:107) over its own atoms, comm->reverse_comm_fix adds the ghosts' dmass to their
+ * owners across the ranks (comm_brick.cpp:930-965 with FixPhaseChange::pack/unpack_reverse_comm :518-537), Atom::tag_extend numbers the
+ * new atoms rank after rank */
+static int w_phase_change(osph_sph **R, int n)
+{
+  for (int f = 0; f < R[0]->nfix; f++) {
+    if (R[0]->fix[f].kind != FIX_PHASE_CHANGE) continue;
+    int due = 0;
+    for (int r = 0; r < n; r++) { int d = pc_local(R[r], &R[r]->fix[f]); if (d < 0) return -1; due |= d; }
+    if (!due) continue;
+    for (int iswap = R[0]->nswap - 1; iswap >= 0; iswap--)
+      for (int r = 0; r < n; r++) {
+        osph_sph *s = R[r]; osph_sph *src = R[s->recvproc[iswap]];
+        for (int k = 0; k < src->sendnum[iswap]; k++) src->drho[src->sendlist[iswap][k]] += s->drho[s->firstrecv[iswap] + k];
+      }
+    int ninsall = 0, maxtag = 0;
+    for (int r = 0; r < n; r++) {
+      ninsall += R[r]->fix[f].pc_nins;
+      for (int i = 0; i < R[r]->nlocal; i++) if (R[r]->tag[i] > maxtag) maxtag = R[r]->tag[i];
+    }
+    int itag = maxtag + 1;
+    for (int r = 0; r < n; r++) { pc_finish(R[r], &R[r]->fix[f], ninsall, itag); itag += R[r]->fix[f].pc_nins; }
+  }
+  return 0;
+}
 static int w_rebuild(osph_sph **R, int n)
 {
+  if (w_phase_change(R, n)) return -1;
   for (int r = 0; r < n; r++) domain_pbc(R[r]);
   w_exchange(R, n);
   w_borders(R, n);

@@ -6,7 +6,8 @@ bricks, run through the C-ABI with NCCL halo exchange / migration, gathered by t
   * with the CPU oracle emulating the same P ranks (tests/pworld.py) when it does: moving multiphase decks read one-step-stale
     ghost rho / colorgradient, in the reference too.  The P-rank emulation has no reference MPI run behind it (no
     MPI in this image); it is pinned on decomposition-independent decks only (tests/test_world_cpu.py);
-  * fix phase_change decks draw one RNG stream per rank (fix_phase_change.cpp:116): particle bookkeeping only.
+  * fix phase_change decks draw one RNG stream per rank (fix_phase_change.cpp:107): they too are compared with the P-rank oracle, which
+    walks one stream per emulated rank and numbers the new atoms as Atom::tag_extend does (sph_oracle.c w_phase_change).
 
 Used by tests/mgpu_check.py (pytest -m gpu on >= 2 GPUs) and by bench.py's parity block at N > 1 (checker role only, after the
 timed region)."""
@@ -88,11 +89,7 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=N
     res["builds"] = [o[3] for o in gathered]
     moving_mp = case.multiphase and "static" not in name
     pc = "phase_change" in str(case.cmds)
-    if pc:
-        res["against"] = "bookkeeping (per-rank RNG streams)"
-        res["ok"] = bool(abs(len(tags) - len(g["sN_tag"])) < 40 and len(np.unique(tags)) == len(tags))
-        res["detail"] = "atoms %d (1 rank: %d)" % (len(tags), len(g["sN_tag"]))
-    elif moving_mp or nsteps != case.nsteps:
+    if moving_mp or pc or nsteps != case.nsteps:      # fix phase_change decks: every rank walks its own RanPark stream, in the P-rank oracle too
         from pworld import OracleWorld
         w = OracleWorld(case.deck(), world, grid, splits)
         w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
@@ -101,8 +98,10 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=N
         fields = ["x", "v", "f", "rho", "e", "de", "drho"] + (["colorgradient", "rmass"] if case.multiphase else [])
         res["against"] = "oracle emulating the same %d ranks" % world
         if len(tags) != len(want["tag"]) or not np.array_equal(tags[order], want["tag"]):
-            res["ok"] = False; res["detail"] = "particle sets differ"
+            res["ok"] = False; res["detail"] = "particle sets differ: %d atoms vs %d in the P-rank oracle" % (len(tags), len(want["tag"]))
         else:
+            if pc:
+                res["detail_pc"] = "%d atoms, %d inserted" % (len(tags), len(tags) - len(g["init_tag"]))
             errs = {k: relerr(np.concatenate([o[0][k] for o in gathered])[order], want[k]) for k in fields}
             elem = {k: relerr_elem(np.concatenate([o[0][k] for o in gathered])[order], want[k]) for k in fields}
             res["err"] = float(max(errs.values())); res["err_elem"] = float(max(elem.values()))
