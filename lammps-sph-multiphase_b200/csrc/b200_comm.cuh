@@ -202,6 +202,42 @@ __global__ void k_exchange_flag(int n, const double4 *xt, const int *alive, int 
   int f = (alive[i] && (c < lo || c >= hi)) ? 1 : 0;
   flag[i] = f; pos[i] = f;
 }
+// ---- CommBrick::exchange's own order (comm_brick.cpp:628-650) ---------------------------------------------------------------
+// The reference walks its local indices upwards; an atom that left is packed and the LAST atom is copied into its place
+// (avec->copy(nlocal-1,i,1); nlocal--), the same index being examined again.  That decides (a) the order of the atoms in the
+// message, hence the local indices they get on the receiving rank, and (b) which of the staying atoms change their index.  The
+// local index is the engine's `orig` key (half-list orientation of the two quirks, the RNG walk of fix phase_change, output order),
+// so the walk is replayed on the keys: ranks of the keys (dense local indices), the leavers' ranks in ascending order, then one
+// thread follows the hole-filling chain -- its length is the number of leavers, not of atoms.
+__global__ void k_orig_mark(int n, const int *alive, const int *orig, int *mark) { int s = blockIdx.x * blockDim.x + threadIdx.x; if (s < n && alive[s]) mark[orig[s]] = 1; }
+// rank of every live atom's key = its LAMMPS local index; inv[index] = slot; leaver flags re-ordered by index
+__global__ void k_orig_rank(int n, const int *alive, int *orig, const int *scan, int *inv, const int *leave, int *leave_by_index)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || !alive[s]) return;
+  const int r = scan[orig[s]];
+  orig[s] = r; inv[r] = s; leave_by_index[r] = leave[s];
+}
+__global__ void k_index_compact(int n, const int *flag, const int *pos, int *list) { int r = blockIdx.x * blockDim.x + threadIdx.x; if (r < n && flag[r]) list[pos[r]] = r; }
+// a[0..m): local indices of the leavers, ascending; N: live atoms.  packlist[0..m): slots in the reference's pack order
+__global__ void k_holefill(const int *a, int m, int N, const int *inv, const int *leave, int *orig, int *packlist)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  int tail = N - 1, np = 0;
+  for (int k = 0; k < m && a[k] <= tail; k++) {
+    const int i = a[k];
+    int cur = inv[i];
+    for (;;) {
+      packlist[np++] = cur;                       // the atom now at index i left: packed
+      if (i == tail) { tail--; break; }           // it was the last one: nothing to copy in
+      const int t = inv[tail]; tail--;            // avec->copy(nlocal-1, i, 1); nlocal--
+      if (leave[t]) { cur = t; continue; }        // the atom copied in leaves as well: index i is examined again
+      orig[t] = i;
+      break;
+    }
+  }
+}
+
 __global__ void k_pack_exchange(int n, const int *list, CommArrays a, int *alive, double *buf)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -150,6 +150,7 @@ struct b200_sph {
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
+  DevBuf<int> x_mark, x_inv, x_lflag, x_lpos, x_list;      // comm_exchange: replay of the reference's hole-filling order
   DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
   int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
   // halo overlap (single-phase tile path): tiles [0, nint) neither read ghosts nor feed a send list and run while the halo flies
@@ -537,7 +538,22 @@ static int comm_exchange(b200_sph *h, int nslots)
     h->perm.ensure(nsend + 1);
     h->sendbuf.ensure((size_t)nsend * NB_EXCHANGE + 1);
     if (nsend) {
-      LAUNCH(h, k_compact, nblk(nslots, B), B, nslots, h->flag.p, h->pos.p, h->perm.p, (const int *)nullptr);
+      // the reference's hole-filling walk on the local-index keys (b200_comm.cuh): dense indices, leavers by index, the chain, the pack order
+      const int M = std::max(h->next_orig, nslots) + 1;
+      h->x_mark.ensure((size_t)M + 2); h->x_inv.ensure((size_t)nslots + 2); h->x_lflag.ensure((size_t)nslots + 2); h->x_lpos.ensure((size_t)nslots + 2);
+      h->x_list.ensure((size_t)nsend + 2); ensure_scan_tmp(h, (size_t)M + 2);
+      CK(cudaMemsetAsync(h->x_mark.p, 0, (size_t)(M + 1) * sizeof(int), h->st));
+      LAUNCH(h, k_orig_mark, nblk(nslots, B), B, nslots, h->alive.p, h->C().orig.p, h->x_mark.p);
+      scan_exclusive(h, h->x_mark.p, M, h->scan_tmp.p);
+      CK(cudaMemcpyAsync(h->h_flags + 5, h->x_mark.p + M, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+      LAUNCH(h, k_orig_rank, nblk(nslots, B), B, nslots, h->alive.p, h->C().orig.p, h->x_mark.p, h->x_inv.p, h->flag.p, h->x_lflag.p);
+      CK(cudaStreamSynchronize(h->st));
+      const int nlive = h->h_flags[5];
+      CK(cudaMemcpyAsync(h->x_lpos.p, h->x_lflag.p, (size_t)nlive * sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+      scan_exclusive(h, h->x_lpos.p, nlive, h->scan_tmp.p);
+      LAUNCH(h, k_index_compact, nblk(nlive, B), B, nlive, h->x_lflag.p, h->x_lpos.p, h->x_list.p);
+      LAUNCH(h, k_holefill, 1, 32, h->x_list.p, nsend, nlive, h->x_inv.p, h->flag.p, h->C().orig.p, h->perm.p);
+      h->next_orig = nlive - nsend;               // the staying atoms hold the indices 0 .. nlive - nsend - 1 again
       LAUNCH(h, k_pack_exchange, nblk(nsend, B), B, nsend, h->perm.p, h->comm_arrays(), h->alive.p, h->sendbuf.p);
     }
     // the whole buffer goes to both neighbours; each keeps what falls inside its bounds (:640-664)

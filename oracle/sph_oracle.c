@@ -1815,6 +1815,8 @@ static int w_rebuild(osph_sph **R, int n)
   if (w_phase_change(R, n)) return -1;
   for (int r = 0; r < n; r++) domain_pbc(R[r]);
   w_exchange(R, n);
+  for (int r = 0; r < n; r++)      /* verlet.cpp:251: every rank sorts its own atoms in the bins of its sub-domain (atom.cpp:1555-1730) */
+    if (R[r]->sortfreq > 0 && R[r]->ntimestep >= R[r]->nextsort) if (atom_sort(R[r])) return -1;
   w_borders(R, n);
   for (int r = 0; r < n; r++) if (neighbor_build(R[r])) return -1;
   return 0;
@@ -1826,6 +1828,7 @@ int osph_world_setup(osph_sph **R, int n)
   if (w_check(R, n)) return -1;
   for (int r = 0; r < n; r++) { domain_pbc(R[r]); if (w_comm_setup(R[r])) return -1; if (setup_bins(R[r])) return -1; }
   w_exchange(R, n);
+  for (int r = 0; r < n; r++) if (R[r]->sortfreq > 0) if (atom_sort(R[r])) return -1;      /* verlet.cpp:106 */
   w_borders(R, n);
   for (int r = 0; r < n; r++) {
     osph_sph *s = R[r];

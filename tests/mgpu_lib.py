@@ -48,7 +48,7 @@ def pick_grid(deck, world, prefer=None):
     return None
 
 
-def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=None):
+def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=None, vs_world=False):
     """-> dict on every rank (filled on rank 0): name, grid, against, ok, err (max over fields, norm-wise), err_elem, detail.
     balance = "x" | "xy" | "xyz": non-uniform bricks from parallel.balance_shift (the `balance 1.05 shift <dims> 10 1.05` command)"""
     api = pkg.load()
@@ -89,11 +89,14 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=N
     res["builds"] = [o[3] for o in gathered]
     moving_mp = case.multiphase and "static" not in name
     pc = "phase_change" in str(case.cmds)
-    if moving_mp or pc or nsteps != case.nsteps:      # fix phase_change decks: every rank walks its own RanPark stream, in the P-rank oracle too
+    if moving_mp or pc or vs_world or nsteps != case.nsteps:      # fix phase_change decks: every rank walks its own RanPark stream, in the P-rank oracle too
         from pworld import OracleWorld
         w = OracleWorld(case.deck(), world, grid, splits)
         w.set_atoms(**harness.state_from(g, "init_", case.multiphase))
         w.setup(); w.setup(); w.run(nsteps)
+        # the ranks' LOCAL ORDER (LAMMPS local indices after migration: exchange()'s hole filling, arrivals appended, comm_brick.cpp:628-664)
+        per_rank = [sim.get_atoms(("tag",))["tag"] for sim in w.sims]
+        res["local_order_same"] = bool(all(np.array_equal(per_rank[r], gathered[r][0]["tag"]) for r in range(world)))
         want = w.get_atoms(); w.close()
         fields = ["x", "v", "f", "rho", "e", "de", "drho"] + (["colorgradient", "rmass"] if case.multiphase else [])
         res["against"] = "oracle emulating the same %d ranks" % world
@@ -124,6 +127,7 @@ def check_case(name, dist, rank, world, local, grid=None, nsteps=None, balance=N
 
 
 def format_result(r):
-    return "%-24s grid %s vs %s: %s  err %.1e (element-wise %.1e)  atoms/rank %s ghosts %s builds %s  %s" % (
+    order = "" if "local_order_same" not in r else ("  local order of every rank as in the oracle" if r["local_order_same"] else "  LOCAL ORDER DIFFERS")
+    return "%-24s grid %s vs %s: %s  err %.1e (element-wise %.1e)  atoms/rank %s ghosts %s builds %s%s  %s" % (
         r["name"], r["grid"], r["against"], "OK" if r["ok"] else "FAIL", r.get("err", 0.0), r.get("err_elem", 0.0),
-        r.get("atoms_per_rank"), r.get("ghosts_per_rank"), r.get("builds"), r.get("detail"))
+        r.get("atoms_per_rank"), r.get("ghosts_per_rank"), r.get("builds"), order, r.get("detail"))

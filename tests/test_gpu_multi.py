@@ -62,3 +62,19 @@ def test_two_rank_balanced_bricks_match_fixtures():
     print("\n".join(lines))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert len(lines) == 2 and not any("FAIL" in l for l in lines)
+
+
+def test_two_rank_local_order_is_the_reference_order():
+    """after migration, Atom::sort and fix phase_change insertions every rank holds its atoms in LAMMPS' own local order: exchange() packs
+    the leavers while filling each hole with the rank's last atom (comm_brick.cpp:628-650), arrivals are appended, sort() re-numbers
+    (atom.cpp:1555), tag_extend numbers new atoms rank after rank -- checked against the P-rank oracle, order and fields"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29537", os.path.join(ROOT, "tests", "mgpu_check.py"), "--vs-world", "dam3d", "dam2d_1000", "droplet2d", "bubble2d_1000", "shock3d"],
+                       capture_output=True, text=True, timeout=900)
+    lines = [l for l in p.stdout.splitlines() if " grid " in l]
+    print("\n".join(lines))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert len(lines) == 5 and not any("FAIL" in l or "LOCAL ORDER DIFFERS" in l for l in lines)
