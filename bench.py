@@ -567,7 +567,7 @@ def main():
         plan = []
         if world == 1:
             plan.append(("C3", "C3", args.c3_nx, 20, 5))
-        if world in (2, 4):
+        if world in (1, 2, 4):
             plan.append(("C4", "C4", args.c4_nx, 10, 3))
         plan.append(("C5_strong", "C5", args.c5_nx, 5, 3))
         sim.close(); sim = None
