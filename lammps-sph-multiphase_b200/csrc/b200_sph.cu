@@ -150,7 +150,7 @@ struct b200_sph {
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
-  DevBuf<int> x_mark, x_inv, x_lflag, x_lpos, x_list;      // comm_exchange: replay of the reference's hole-filling order
+  DevBuf<int> x_mark, x_inv, x_lflag, x_lpos, x_list, x_work;      // comm_exchange: replay of the reference's hole-filling order
   DevBuf<TileDesc> tiles, gtiles; DevBuf<double2> trec; DevBuf<int> rowtile;
   int ngtiles = 0;                              // tiles of ghost rows (multiphase styles)
   // halo overlap (single-phase tile path): tiles [0, nint) neither read ghosts nor feed a send list and run while the halo flies
@@ -545,15 +545,14 @@ static int comm_exchange(b200_sph *h, int nslots)
       CK(cudaMemsetAsync(h->x_mark.p, 0, (size_t)(M + 1) * sizeof(int), h->st));
       LAUNCH(h, k_orig_mark, nblk(nslots, B), B, nslots, h->alive.p, h->C().orig.p, h->x_mark.p);
       scan_exclusive(h, h->x_mark.p, M, h->scan_tmp.p);
-      CK(cudaMemcpyAsync(h->h_flags + 5, h->x_mark.p + M, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaMemsetAsync(h->x_lflag.p, 0, (size_t)(nslots + 1) * sizeof(int), h->st));      // indices >= the number of live atoms hold no leaver
       LAUNCH(h, k_orig_rank, nblk(nslots, B), B, nslots, h->alive.p, h->C().orig.p, h->x_mark.p, h->x_inv.p, h->flag.p, h->x_lflag.p);
-      CK(cudaStreamSynchronize(h->st));
-      const int nlive = h->h_flags[5];
-      CK(cudaMemcpyAsync(h->x_lpos.p, h->x_lflag.p, (size_t)nlive * sizeof(int), cudaMemcpyDeviceToDevice, h->st));
-      scan_exclusive(h, h->x_lpos.p, nlive, h->scan_tmp.p);
-      LAUNCH(h, k_index_compact, nblk(nlive, B), B, nlive, h->x_lflag.p, h->x_lpos.p, h->x_list.p);
-      LAUNCH(h, k_holefill, 1, 32, h->x_list.p, nsend, nlive, h->x_inv.p, h->flag.p, h->C().orig.p, h->perm.p);
-      h->next_orig = nlive - nsend;               // the staying atoms hold the indices 0 .. nlive - nsend - 1 again
+      CK(cudaMemcpyAsync(h->x_lpos.p, h->x_lflag.p, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, h->st));
+      scan_exclusive(h, h->x_lpos.p, nslots, h->scan_tmp.p);
+      LAUNCH(h, k_index_compact, nblk(nslots, B), B, nslots, h->x_lflag.p, h->x_lpos.p, h->x_list.p);
+      h->x_work.ensure((size_t)3 * nsend + 4);
+      LAUNCH(h, k_holefill, 1, 256, h->x_list.p, nsend, h->x_mark.p + M, h->x_inv.p, h->flag.p, h->C().orig.p, h->perm.p, h->x_work.p);      // x_mark[M] = live atoms (no host round trip)
+      h->next_orig = nslots - nsend;              // above every staying atom's index (they hold 0 .. live - nsend - 1 again); arrivals continue from here
       LAUNCH(h, k_pack_exchange, nblk(nsend, B), B, nsend, h->perm.p, h->comm_arrays(), h->alive.p, h->sendbuf.p);
     }
     // the whole buffer goes to both neighbours; each keeps what falls inside its bounds (:640-664)
