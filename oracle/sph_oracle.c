@@ -14,7 +14,9 @@
  * be run against the real reference here (the image has no MPI): it is pinned
  * through the decks whose result does not depend on the decomposition, which must
  * reproduce the 1-rank reference fixtures on 2-4 ranks (tests/test_world_cpu.py);
- * for decomposition-dependent decks at P > 1 it is a restatement only.
+ * for decomposition-dependent decks at P > 1 (moving multiphase decks, fix phase_change
+ * with one RanPark stream per rank, Atom::sort per rank) it is a restatement only,
+ * held to its invariants (tags, mass) on the CPU.
  *
  * It is a deliberately plain, sequential, single-rank restatement that follows
  * the reference's own data structures (AoS per-atom arrays with ghosts behind
