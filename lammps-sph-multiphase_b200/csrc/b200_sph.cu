@@ -1118,11 +1118,11 @@ static void run_pass_tile_mp(b200_sph *h, const Pass &p)
     const bool gu = tile_uni_geo(h, T, A.uni[0]) && !h->tile_nouni;
     size_t smem = TileSmem<2, 1>::bytes(h->tile_cap);
     if (p.type == 1) {
-      if (gu) launch_tiles(h, k_tile_full_mp<0, true>, "k_tile_rhosum_mp", TILE_MP_NT, smem, A);
-      else launch_tiles(h, k_tile_full_mp<0, false>, "k_tile_rhosum_mp", TILE_MP_NT, smem, A);
+      if (gu) launch_tiles(h, k_tile_full_mp<0, true>, "k_tile_rhosum_mp", TILE_MPFULL_NT, smem, A);
+      else launch_tiles(h, k_tile_full_mp<0, false>, "k_tile_rhosum_mp", TILE_MPFULL_NT, smem, A);
     } else {
-      if (gu) launch_tiles(h, k_tile_full_mp<1, true>, "k_tile_colorgradient", TILE_MP_NT, smem, A);
-      else launch_tiles(h, k_tile_full_mp<1, false>, "k_tile_colorgradient", TILE_MP_NT, smem, A);
+      if (gu) launch_tiles(h, k_tile_full_mp<1, true>, "k_tile_colorgradient", TILE_MPFULL_NT, smem, A);
+      else launch_tiles(h, k_tile_full_mp<1, false>, "k_tile_colorgradient", TILE_MPFULL_NT, smem, A);
     }
     h->tend();
     return;
