@@ -27,7 +27,8 @@ def _run(name, world, grid=None):
 @pytest.mark.parametrize("name,world,grid", [("dam3d", 2, None), ("dam3d", 4, None), ("dam3d", 3, (3, 1, 1)), ("dam2d", 2, None), ("dam2d", 4, (2, 2, 1)),
                                              ("heat3d", 2, None), ("heat2d_rhosum", 2, None), ("heat2d_rhosum", 4, (2, 2, 1)), ("gas3d", 2, None), ("gas3d", 4, None),
                                              ("droplet3d_static", 2, None), ("droplet2d_static", 2, None), ("droplet2d_static", 4, (2, 2, 1)),
-                                             ("dam2d_1000", 2, None)])      # default atom_modify: every rank sorts its atoms at step 1000 (verlet.cpp:251)
+                                             ("dam2d_1000", 2, None),       # default atom_modify: every rank sorts its atoms at step 1000 (verlet.cpp:251)
+                                             ("dam3d", 8, (2, 2, 2)), ("heat3d", 8, (2, 2, 2)), ("droplet3d_static", 8, (2, 2, 2))])      # the grid of bench.py's parity block at N = 8
 def test_world_reproduces_one_rank_fixture(name, world, grid):
     # not in the list: the two-type shock decks.  PairSPHIdealGas leaves viscosity[j][i] unset, so a cross-type pair
     # depends on which atom the half list puts first, i.e. on the local index order -- and CommBrick::exchange fills the hole of a
