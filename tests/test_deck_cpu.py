@@ -76,3 +76,25 @@ def test_variable_formulas_engine_compiler_vs_oracle():
                 assert a.value == known[f], (f, a.value)
     for bad in ("mass*", "foo(x)", "c_pe*2", "x+", "random(0,1,5)", "(x"):
         assert eng.formula_check(bad.encode(), None, 1, 1, 0.0, 0.0, None) < 0, bad
+
+
+def test_addforce_and_variable_parsing():
+    """fix addforce fx fy fz with v_name arguments (fix_addforce.cpp:40-110) and variable references (variable.cpp): what the mirror accepts and refuses"""
+    d = _deck()
+    d.variable("gx", "equal", "0.5*2.0")
+    d.variable("bodyfx", "atom", "mass*v_gx*((y<0.2)-(y>0.2))")
+    d.fix("f1", "all", "addforce", "v_bodyfx", 0.0, "v_gx")
+    style, bit, (vals, forms) = d.fixes[-1]
+    assert style == "addforce" and vals == [0.0, 0.0, 0.0]
+    assert forms == ["mass*(0.5*2.0)*((y<0.2)-(y>0.2))", None, "0.5*2.0"]
+    with pytest.raises(DeckError):
+        d.fix("f2", "all", "addforce", "v_nope", 0.0, 0.0)                     # unknown variable
+    with pytest.raises(DeckError):
+        d.fix("f3", "all", "addforce", 1.0, 0.0, 0.0, "every", 2)             # keywords are not taken
+    d.variable("a", "equal", "v_b+1"); d.variable("b", "equal", "v_a+1")
+    with pytest.raises(DeckError):
+        d.fix("f4", "all", "addforce", "v_a", 0.0, 0.0)                        # circular
+    with pytest.raises(DeckError):
+        d.variable("s", "string", "abc")                                       # only equal / atom styles
+    d.fix("f5", "all", "setmeso", "meso_e", "v_gx")
+    assert d.fixes[-1][0] == "setmeso/var" and d.fixes[-1][2][1] == "0.5*2.0"
