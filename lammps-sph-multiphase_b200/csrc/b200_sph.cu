@@ -685,7 +685,8 @@ static bool tile_rows(b200_sph *h)
     {
       const int nt = h->ntiles + h->ngtiles;
       B.ntiles = nt;
-      bool small = bsm <= 56 * 1024;      // small tiles: 128-thread CTAs, more of them per SM
+      bool small = bsm <= 40 * 1024;      // small tiles (the 27-row cells of the multiphase decks, 35 KB: 1.94 ms with 128 threads, 2.92 with 256): 128-thread CTAs, more of them
+                                          // per SM; the C2 tiles (46 KB) build 5 % faster with 256 threads (2.11 vs 2.23 ms, gpurun r02 last A/B)
       if (const char *e = getenv("B200_BUILD_NT")) small = atoi(e) == 128;
       const bool zones = h->far_margin > 0.0 || !B.uni;      // skin 0: no far / mid rows to split off
 #define BUILD_LAUNCH(U, M, Z) do { if (small) launch_tiles(h, k_tile_build<U, M, 128, Z>, "k_tile_build", 128, bsm, B, nt); \
