@@ -65,3 +65,47 @@ def test_two_ranks_gloo():
     assert [o[0] for o in out] == [b"id-from-rank0"] * 2
     assert sum(o[1] for o in out) == 2000 and out[0][1] == 1000
     assert out[0][2] == (2, 1, 1)
+
+
+def test_hole_filling_chain_equals_the_sequential_exchange_loop():
+    """the algorithm of k_holefill (csrc/b200_comm.cuh) restated in Python against CommBrick::exchange's loop (comm_brick.cpp:628-650):
+    same pack order, same final local indices, for random leaver sets (incl. leavers at the end, runs of leavers, everybody leaving)"""
+    import numpy as np
+    rng = np.random.default_rng(11)
+
+    def reference(n, leave):
+        atoms = list(range(n)); packed = []; nlocal = n; i = 0
+        while i < nlocal:
+            if leave[atoms[i]]:
+                packed.append(atoms[i]); atoms[i] = atoms[nlocal - 1]; nlocal -= 1      # avec->copy(nlocal-1,i,1); nlocal--
+            else:
+                i += 1
+        return packed, atoms[:nlocal]
+
+    def chain(n, leave):
+        a = [i for i in range(n) if leave[i]]                    # leaver indices ascending (x_list)
+        m = len(a); index_of = list(range(n)); tail = n - 1; packed = []
+        k = 0
+        while k < m and a[k] <= tail:
+            i = a[k]; cur = i
+            while True:
+                packed.append(cur)
+                if i == tail:
+                    tail -= 1; break
+                t = tail; tail -= 1
+                if leave[t]:
+                    cur = t; continue
+                index_of[t] = i
+                break
+            k += 1
+        stay = [None] * (n - m)
+        for atom in range(n):
+            if not leave[atom]:
+                stay[index_of[atom]] = atom
+        return packed, stay
+
+    for trial in range(400):
+        n = int(rng.integers(1, 40))
+        p = rng.choice([0.0, 0.1, 0.5, 0.9, 1.0])
+        leave = [bool(v) for v in (rng.random(n) < p)]
+        assert reference(n, leave) == chain(n, leave), (n, leave)
