@@ -173,6 +173,13 @@ int  b200_fix_setmesode(b200_sph *h, int groupbit, double value, int region_kind
  * the device; b200_get_timestep returns the current value (update->dt). */
 int  b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, double tmin, int maxbound, double tmax, double xmax);
 int  b200_get_timestep(b200_sph *h, double *dt);
+/* Elapsed simulation time under a varying timestep.  Update::update_time (update.cpp:480-484) adds (ntimestep - atimestep) * dt to atime
+ * and moves atimestep whenever FixDtReset::end_of_step changes dt, and the fix remembers that step as `laststep` (fix_dt_reset.cpp:175-181;
+ * thermo keyword `time` = atime + (ntimestep - atimestep) * dt, thermo.cpp:1500; f_ID of the fix = laststep, fix_dt_reset.cpp:190-193).
+ * With fix dt/reset registered the engine keeps the three on the device next to dt: b200_set_time hands over the caller's values before
+ * b200_setup, b200_get_time returns them after b200_setup / b200_run.  Without the fix they come back unchanged. */
+int  b200_set_time(b200_sph *h, double atime, long long atimestep, long long laststep);
+int  b200_get_time(b200_sph *h, double *atime, long long *atimestep, long long *laststep);
 /* Pair virial (Pair::virial_fdotr_compute, pair.cpp:1403-1451: sum of x (x) f over owned + ghost atoms of the pair forces, before the
  * reverse halo; xx yy zz xy xz yz, this rank's share).  b200_request_virial arms it for the next force evaluation that ends a call:
  * the one of b200_setup, or the LAST step of the next b200_run (Verlet's ev_set on thermo steps, integrate.cpp:120-150). */

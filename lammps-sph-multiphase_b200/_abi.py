@@ -77,6 +77,8 @@ _PROTOS = {
     "formula_check": (C.c_int, [C.c_char_p, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double, c_double_p]),
     "fix_dt_reset": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "get_timestep": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "set_time": (C.c_int, [_H, C.c_double, C.c_longlong, C.c_longlong]),
+    "get_time": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "request_virial": (C.c_int, [_H]),
     "get_virial": (C.c_int, [_H, c_double_p]),
     "set_atoms": (C.c_int, [_H, C.c_int, C.POINTER(Atoms)]),

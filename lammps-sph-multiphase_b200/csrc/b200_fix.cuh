@@ -205,11 +205,19 @@ __global__ void k_dt_min(int nlocal, int groupbit, const int *mask, const double
   const unsigned long long b = (unsigned long long)__double_as_longlong(dt);
   if (b < *(volatile unsigned long long *)dtmin_bits) atomicMin(dtmin_bits, b);
 }
-__global__ void k_dt_apply(const unsigned long long *dtmin_bits, int minbound, double tmin, int maxbound, double tmax, double *dtp)
+// dtp[0] = dt, dtp[2] = Update::atime, ((long long *)dtp)[3] = Update::atimestep, ((long long *)dtp)[4] = FixDtReset::laststep
+// (fix_dt_reset.cpp:175-181: nothing moves when the timestep did not change; else update_time() with the OLD dt, update.cpp:480-484)
+__global__ void k_dt_apply(const unsigned long long *dtmin_bits, int minbound, double tmin, int maxbound, double tmax, double *dtp, long long step)
 {
   double dt = __longlong_as_double((long long)*dtmin_bits);
   if (minbound) dt = fmax(dt, tmin);
   if (maxbound) dt = fmin(dt, tmax);
+  const double old = dtp[0];
+  if (dt == old) return;
+  long long *lp = (long long *)dtp;
+  dtp[2] = __dadd_rn(dtp[2], __dmul_rn((double)(step - lp[3]), old));
+  lp[3] = step;
+  lp[4] = step;
   dtp[0] = dt;
 }
 

@@ -146,7 +146,8 @@ struct b200_sph {
   bool vir_request = false, vir_now = false; DevBuf<double> virow, virpart; double *h_vir = nullptr;
   // fix dt/reset: device-resident timestep  d_dt[0] = dt, ((unsigned long long *)d_dt)[1] = running minimum (bits)
   bool dtreset = false; int dtr_bit = 0, dtr_every = 1, dtr_minbound = 0, dtr_maxbound = 0; double dtr_tmin = 0, dtr_tmax = 0, dtr_xmax = 0;
-  double *d_dt = nullptr;
+  double *d_dt = nullptr, *h_dtv = nullptr;      // h_dtv: pinned mirror of d_dt[0..4]
+  double atime = 0.0; long long atimestep = 0, laststep = 0;      // Update::atime / atimestep, FixDtReset::laststep (b200_set_time / b200_get_time)
   // tile path (b200_tile.cuh): single-phase decks
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
@@ -1492,14 +1493,15 @@ static void dt_reset(b200_sph *h)
   if (h->nlocal) LAUNCH(h, k_dt_min, nblk(h->nlocal, 256), 256, h->nlocal, h->dtr_bit, h->C().mask.p, h->C().vm.p, h->C().fd.p, h->dtr_xmax, h->ftm2v,
                         (unsigned long long *)h->d_dt + 1);
   if (h->world > 1) NCK(g_nccl.AllReduce((unsigned long long *)h->d_dt + 1, (unsigned long long *)h->d_dt + 1, 1, ncclUint64, ncclMin, h->nccl, h->st));   // MPI_Allreduce MIN (:171)
-  LAUNCH(h, k_dt_apply, 1, 1, (const unsigned long long *)h->d_dt + 1, h->dtr_minbound, h->dtr_tmin, h->dtr_maxbound, h->dtr_tmax, h->d_dt);
+  LAUNCH(h, k_dt_apply, 1, 1, (const unsigned long long *)h->d_dt + 1, h->dtr_minbound, h->dtr_tmin, h->dtr_maxbound, h->dtr_tmax, h->d_dt, h->ntimestep);
 }
 static void dt_download(b200_sph *h)
 {
   if (!h->dtreset) return;
-  CK(cudaMemcpyAsync(h->h_red + 4, h->d_dt, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_dtv, h->d_dt, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  h->dt = h->h_red[4];
+  h->dt = h->h_dtv[0]; h->atime = h->h_dtv[2];
+  memcpy(&h->atimestep, h->h_dtv + 3, sizeof(long long)); memcpy(&h->laststep, h->h_dtv + 4, sizeof(long long));
 }
 static void reneighbor(b200_sph *h)
 {
@@ -1529,7 +1531,10 @@ static void do_setup(b200_sph *h)
   pair_compute_all(h);
   post_final(h, 1, 1, 0);
   if (h->dtreset) {            // FixDtReset::setup -> end_of_step
-    CK(cudaMemcpyAsync(h->d_dt, &h->dt, sizeof(double), cudaMemcpyHostToDevice, h->st));
+    h->h_dtv[0] = h->dt; h->h_dtv[1] = 0.0; h->h_dtv[2] = h->atime;
+    memcpy(h->h_dtv + 3, &h->atimestep, sizeof(long long)); memcpy(h->h_dtv + 4, &h->laststep, sizeof(long long));
+    CK(cudaMemcpyAsync(h->d_dt, h->h_dtv, 5 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));                   // h_dtv is read back into by dt_download right after
     dt_reset(h); dt_download(h);
   }
   h->setup_done = true;
@@ -1656,7 +1661,7 @@ int b200_destroy(b200_sph *h)
   h->cellid.release(); h->perm.release(); h->perm2.release(); h->gcell.release(); h->gperm.release(); h->gorder.release(); h->flag.release(); h->pos.release(); h->alive.release();
   h->sendbuf.release(); h->recvbuf.release(); for (int q = 0; q < 2; q++) { h->xs[q].release(); h->xr[q].release(); } for (int k = 0; k < 6; k++) h->swaps[k].sendlist.release();
   if (h->nccl) g_nccl.CommDestroy(h->nccl);
-  cudaFree(h->d_red); cudaFreeHost(h->h_red); if (h->d_dt) cudaFree(h->d_dt);
+  cudaFree(h->d_red); cudaFreeHost(h->h_red); if (h->d_dt) cudaFree(h->d_dt); if (h->h_dtv) cudaFreeHost(h->h_dtv);
   h->key.release(); h->gkey.release(); h->cso.release(); h->csg.release();
   h->cellfill.release(); h->scan_tmp.release(); h->xhold.release(); h->stage_d.release(); h->stage_i.release(); h->d_mass.release(); h->nbr.release(); h->numneigh.release(); h->d_cutneighsq.release();
   for (int k = 0; k < MAXPAIR; k++) if (h->d_tab[k]) cudaFree(h->d_tab[k]);
@@ -1862,12 +1867,15 @@ int b200_fix_dt_reset(b200_sph *h, int groupbit, int nevery, int minbound, doubl
   if (nevery <= 0 || xmax <= 0.0 || (minbound && tmin < 0.0) || (maxbound && tmax < 0.0) || (minbound && maxbound && tmin >= tmax))
     throw std::string("Illegal fix dt/reset command");
   CK(cudaSetDevice(h->device));
-  if (!h->d_dt) CK(cudaMalloc(&h->d_dt, 4 * sizeof(double)));
+  if (!h->d_dt) { CK(cudaMalloc(&h->d_dt, 8 * sizeof(double))); CK(cudaMallocHost(&h->h_dtv, 8 * sizeof(double))); }
   h->dtreset = true; h->dtr_bit = groupbit; h->dtr_every = nevery; h->dtr_minbound = minbound; h->dtr_tmin = tmin;
   h->dtr_maxbound = maxbound; h->dtr_tmax = tmax; h->dtr_xmax = xmax;
   API_END
 }
 int b200_get_timestep(b200_sph *h, double *dt) { *dt = h->dt; return 0; }
+int b200_set_time(b200_sph *h, double atime, long long atimestep, long long laststep) { h->atime = atime; h->atimestep = atimestep; h->laststep = laststep; return 0; }
+int b200_get_time(b200_sph *h, double *atime, long long *atimestep, long long *laststep)
+{ if (atime) *atime = h->atime; if (atimestep) *atimestep = h->atimestep; if (laststep) *laststep = h->laststep; return 0; }
 int b200_request_virial(b200_sph *h) { h->vir_request = true; return 0; }
 int b200_get_virial(b200_sph *h, double v[6])
 {

@@ -55,6 +55,17 @@ class Sim:
         self.api.check(self.api.get_timestep(self.h, C.byref(dt)))
         return dt.value
 
+    def set_time(self, atime, atimestep, laststep):
+        """Update::atime / atimestep and FixDtReset::laststep as the caller holds them (before setup)"""
+        self.api.check(self.api.set_time(self.h, float(atime), int(atimestep), int(laststep)))
+
+    def time(self):
+        """(atime, atimestep, laststep): elapsed-time bookkeeping under fix dt/reset (update.cpp:480-484, fix_dt_reset.cpp:175-181);
+        thermo's `time` is atime + (ntimestep - atimestep) * dt"""
+        a, s, l = C.c_double(), C.c_longlong(), C.c_longlong()
+        self.api.check(self.api.get_time(self.h, C.byref(a), C.byref(s), C.byref(l)))
+        return a.value, s.value, l.value
+
     def close(self):
         if self.h:
             self.api.destroy(self.h)

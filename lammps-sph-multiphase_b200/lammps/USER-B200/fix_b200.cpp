@@ -67,6 +67,26 @@ int FixGravityB200::b200_register(b200_sph *h)
   return b200_fix_gravity(h, groupbit, xacc, yacc, zacc);
 }
 
+// FixGravity::post_force sums the potential energy of the group while it adds the force (fix_gravity.cpp:262-283:
+// egrav -= massone * (xacc x + yacc y + zacc z), owned atoms in index order) and compute_scalar all-reduces it (:342-351).
+// The engine adds the force; the sum is formed here from the host arrays, which VerletB200 refreshes on every step that
+// evaluates thermo output or an END_OF_STEP fix -- the positions are those post_force saw on that step.
+double FixGravityB200::compute_scalar()
+{
+  double **x = atom->x;
+  double *rmass = atom->rmass, *mass = atom->mass;
+  int *mask = atom->mask, *type = atom->type;
+  int nlocal = atom->nlocal;
+  egrav = 0.0;
+  for (int i = 0; i < nlocal; i++)
+    if (mask[i] & groupbit) {
+      double massone = rmass ? rmass[i] : mass[type[i]];
+      egrav -= massone * (xacc*x[i][0] + yacc*x[i][1] + zacc*x[i][2]);
+    }
+  MPI_Allreduce(&egrav, &egrav_all, 1, MPI_DOUBLE, MPI_SUM, world);
+  return egrav_all;
+}
+
 FixPhaseChangeB200::FixPhaseChangeB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
 {
   if (narg < 14) error->all(FLERR, "Illegal fix phase_change command");
@@ -228,6 +248,8 @@ FixDtResetB200::FixDtResetB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, nar
 {
   if (narg < 7) error->all(FLERR, "Illegal fix dt/reset command");
   time_depend = 1;
+  scalar_flag = 1; global_freq = 1; extscalar = 0; extvector = 0;      // fix_dt_reset.cpp:46-50
+  laststep = update->ntimestep;                                        // :88-89
   nevery_ = atoi(arg[3]);
   minbound = maxbound = 1; tmin = tmax = 0.0;
   if (strcmp(arg[4], "NULL") == 0) minbound = 0; else tmin = atof(arg[4]);

@@ -52,6 +52,7 @@ class FixGravityB200 : public FixGravity, public B200FixShell {
   FixGravityB200(class LAMMPS *lmp, int narg, char **arg) : FixGravity(lmp, narg, arg) {}
   void setup(int) {}
   void post_force(int) { b200_fix_guard(lmp, "gravity"); }
+  double compute_scalar();                             // f_ID in thermo / variables (water_collapse.lmp: v_etot = c_esph+c_ke+f_gfix)
   int b200_register(b200_sph *h);
 };
 
@@ -132,13 +133,16 @@ class FixSetMesodEB200 : public Fix, public B200FixShell {
 };
 
 // FixDtReset (fix_dt_reset.cpp:40-98, members private): fix ID grp dt/reset N Tmin Tmax Xmax units box.  The timestep lives on the
-// device during a run; VerletB200 copies it back into update->dt after every b200_run segment.
+// device during a run; VerletB200 copies it back into update->dt after every b200_run segment, together with update->atime / atimestep
+// (thermo keyword `time`) and `laststep` (f_ID).
 class FixDtResetB200 : public Fix, public B200FixShell {
  public:
   FixDtResetB200(class LAMMPS *, int, char **);
   int setmask();
   void end_of_step() { b200_fix_guard(lmp, "dt/reset"); }
+  double compute_scalar() { return (double) laststep; }      // fix_dt_reset.cpp:190-193
   int b200_register(b200_sph *h) { return b200_fix_dt_reset(h, groupbit, nevery_, minbound, tmin, maxbound, tmax, xmax); }
+  bigint laststep;                                     // last step the engine changed the timestep on (VerletB200 copies it back with update->atime)
  private:
   int nevery_, minbound, maxbound; double tmin, tmax, xmax;
 };

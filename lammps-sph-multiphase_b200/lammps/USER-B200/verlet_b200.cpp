@@ -24,7 +24,7 @@
 
 using namespace LAMMPS_NS;
 
-VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), h(NULL) {}
+VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) : Verlet(lmp, narg, arg), h(NULL), dtfix(NULL) {}
 
 VerletB200::~VerletB200() { if (h) b200_destroy(h); }
 
@@ -36,6 +36,15 @@ struct DomainPeek : public Domain {
 // Atom::userbinsize (atom.h, `atom_modify sort Nfreq binsize`) is protected as well
 struct AtomPeek : public Atom {
   static double userbinsize_of(const Atom *a) { return a->*(&AtomPeek::userbinsize); }
+};
+// PairHybrid::nmap / map (pair_hybrid.h:59-60, protected): which sub-styles a type pair is assigned to
+struct HybridPeek : public PairHybrid {
+  static bool maps(const PairHybrid *p, int i, int j, int m)
+  {
+    int **nmap = p->*(&HybridPeek::nmap); int ***map = p->*(&HybridPeek::map);
+    for (int k = 0; k < nmap[i][j]; k++) if (map[i][j][k] == m) return true;
+    return false;
+  }
 };
 }
 
@@ -97,6 +106,9 @@ void VerletB200::configure()
   check(b200_neighbor(h, neighbor->skin, neighbor->every, neighbor->delay, neighbor->dist_check, cn.data(), neighbor->cutneighmax,
                       comm->cutghost[0]));
   check(b200_timestep(h, update->dt, force->ftm2v, update->ntimestep));
+  dtfix = NULL;
+  for (int i = 0; i < modify->nfix; i++) if (FixDtResetB200 *f = dynamic_cast<FixDtResetB200 *>(modify->fix[i])) dtfix = f;
+  check(b200_set_time(h, update->atime, update->atimestep, dtfix ? dtfix->laststep : update->ntimestep));
   check(b200_comm_modify(h, comm->ghost_velocity));
   check(b200_atom_modify(h, atom->sortfreq, AtomPeek::userbinsize_of(atom)));      // the engine re-numbers its local indices when Atom::sort would (verlet.cpp:251)
 
@@ -111,6 +123,16 @@ void VerletB200::configure()
     b200_pair_desc d; std::vector<std::vector<double> > ds; std::vector<std::vector<int> > is;
     ds.reserve(16); is.reserve(4);
     shell->b200_describe(d, ds, is);
+    // under pair hybrid the type pairs a sub-style computes are the hybrid's assignment, not the sub-style's own setflag
+    // (`pair_coeff * * A ...` followed by `pair_coeff 2 3 none` or `pair_coeff 1 2 B ...` leaves A's setflag set; the reference
+    // keeps such pairs out of A's list through ijskip, pair_hybrid.cpp:560-600 -- cavity_flow.lmp:37-38)
+    std::vector<int> mapped;
+    if (hyb) {
+      mapped.assign((n + 1) * (n + 1), 0);
+      for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= n; j++) mapped[i * (n + 1) + j] = HybridPeek::maps(hyb, i, j, m) ? 1 : 0;
+      d.mapped = mapped.data();
+    }
     check(b200_pair_add(h, &d));
   }
 
@@ -189,6 +211,20 @@ void VerletB200::download()
   }
 }
 
+/* update->dt and, under fix dt/reset/b200, the elapsed-time bookkeeping of Update::update_time (update.cpp:480-484; thermo keyword
+   `time`, thermo.cpp:1500) and FixDtReset::laststep -- the engine advanced them on the device exactly as end_of_step does on the host */
+void VerletB200::pull_time()
+{
+  double dtnow;
+  check(b200_get_timestep(h, &dtnow));
+  update->dt = dtnow;
+  if (dtfix) {
+    double atime; long long atimestep, laststep;
+    check(b200_get_time(h, &atime, &atimestep, &laststep));
+    update->atime = atime; update->atimestep = atimestep; dtfix->laststep = laststep;
+  }
+}
+
 /* Verlet::setup, verlet.cpp:88-142 */
 void VerletB200::setup()
 {
@@ -207,7 +243,7 @@ void VerletB200::setup()
   ev_set(update->ntimestep);
   if (vflag) check(b200_request_virial(h));       // thermo output of step 0 needs the pair virial (Pair::virial_fdotr_compute)
   check(b200_setup(h));
-  { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // FixDtReset::setup may already have changed it
+  pull_time();                                    // FixDtReset::setup may already have changed the timestep
   download();
   if (vflag && force->pair) check(b200_get_virial(h, force->pair->virial));
   modify->setup(vflag);
@@ -239,7 +275,7 @@ void VerletB200::run(int n)
     check(b200_run(h, k));
     check(b200_sync(h));
     update->ntimestep += k;
-    { double dtnow; check(b200_get_timestep(h, &dtnow)); update->dt = dtnow; }      // fix dt/reset/b200 changes it on the device
+    pull_time();                                    // fix dt/reset/b200 changes the timestep on the device
     timer->stamp(TIME_PAIR);
     bool host_due = false;
     for (size_t q = 0; q < host_every.size(); q++) if (update->ntimestep % host_every[q] == 0) host_due = true;

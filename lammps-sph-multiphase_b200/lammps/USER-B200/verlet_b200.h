@@ -29,7 +29,9 @@ class VerletB200 : public Verlet {
  private:
   b200_sph *h;
   std::vector<int> host_every;   // nevery of the host-side END_OF_STEP fixes (fix print, fix ave/...): segment boundaries of run()
+  class FixDtResetB200 *dtfix;   // the deck's fix dt/reset/b200, if any: update->atime / atimestep and its laststep follow the engine
   void check(int rc);
+  void pull_time();
   void configure();
   void upload();
   void download();

@@ -81,7 +81,8 @@ struct osph_sph {
   int *binhead, *bins; int maxbin;
   int nstencil, *stencil;
   long long *firstneigh; int *numneigh; int *neigh; long long maxneigh; int maxlist;
-  unsigned char *halfkeep; /* per full-list entry: kept by half_from_full_newton AT BUILD TIME */
+  unsigned char *halfkeep; /* per full-list entry: kept by the reference's half list AT BUILD TIME (half_keeps) */
+  int half_bin;            /* no full-list sub-style in the deck: the half list is half_bin_newton's, not half_from_full_newton's */
   /* comm: up to 6 swaps for P=1 (comm_brick.cpp:330-386) */
   int nswap, swapdim[6], swappbc[6], sendnum[6], firstrecv[6], *sendlist[6], maxsend[6];
   double slablo[6], slabhi[6];
@@ -91,6 +92,7 @@ struct osph_sph {
   int npair; opair pair[MAXPAIR];
   int nfix; ofix fix[MAXFIX];
   double dt, ftm2v; long long ntimestep;
+  double atime; long long atimestep, laststep;   /* Update::atime / atimestep, FixDtReset::laststep (osph_set_time / osph_get_time) */
   long long nsteps_done, ninserted, maxneighseen;
   int setup_done;
   int vir_request; double virial[6];
@@ -300,6 +302,9 @@ int osph_fix_dt_reset(osph_sph *s, int groupbit, int nevery, int minbound, doubl
   return 0;
 }
 int osph_get_timestep(osph_sph *s, double *dt) { *dt = s->dt; return 0; }
+int osph_set_time(osph_sph *s, double atime, long long atimestep, long long laststep) { s->atime = atime; s->atimestep = atimestep; s->laststep = laststep; return 0; }
+int osph_get_time(osph_sph *s, double *atime, long long *atimestep, long long *laststep)
+{ if (atime) *atime = s->atime; if (atimestep) *atimestep = s->atimestep; if (laststep) *laststep = s->laststep; return 0; }
 int osph_fix_setmesode(osph_sph *s, int groupbit, double value, int region_kind, const double region[6])
 {
   ofix *f = newfix(s, FIX_SETMESODE, groupbit);
@@ -570,7 +575,7 @@ static int setup_bins(osph_sph *s)
 }
 
 /* Neighbor::coord2bin, neighbor.cpp:1961-1990 */
-static int coord2bin(osph_sph *s, const double *x)
+static void coord2bin3(osph_sph *s, const double *x, int *pix, int *piy, int *piz)
 {
   int ix, iy, iz;
   if (x[0] >= s->boxhi[0]) ix = (int)((x[0] - s->boxhi[0]) * s->bininvx) + s->nbinx;
@@ -582,6 +587,12 @@ static int coord2bin(osph_sph *s, const double *x)
   if (x[2] >= s->boxhi[2]) iz = (int)((x[2] - s->boxhi[2]) * s->bininvz) + s->nbinz;
   else if (x[2] >= s->boxlo[2]) { iz = (int)((x[2] - s->boxlo[2]) * s->bininvz); if (iz > s->nbinz - 1) iz = s->nbinz - 1; }
   else iz = (int)((x[2] - s->boxlo[2]) * s->bininvz) - 1;
+  *pix = ix; *piy = iy; *piz = iz;
+}
+static int coord2bin(osph_sph *s, const double *x)
+{
+  int ix, iy, iz;
+  coord2bin3(s, x, &ix, &iy, &iz);
   return (iz - s->mbinzlo) * s->mbiny * s->mbinx + (iy - s->mbinylo) * s->mbinx + (ix - s->mbinxlo);
 }
 
@@ -592,6 +603,9 @@ static int neighbor_build(osph_sph *s)
 {
   int nlocal = s->nlocal, nall = nlocal + s->nghost, nt = s->ntypes + 1;
   s->ago = 0; s->nbuilds++;
+  s->half_bin = 1;
+  for (int k = 0; k < s->npair; k++)
+    if (s->pair[k].style == B200_PAIR_RHOSUM || s->pair[k].style == B200_PAIR_RHOSUM_MULTIPHASE || s->pair[k].style == B200_PAIR_COLORGRADIENT) s->half_bin = 0;
   if (s->check) { /* dist_check: store xhold (:1428-1441) */
     if (nlocal > s->maxhold) { s->maxhold = s->nmax; s->xhold = xrealloc(s->xhold, sizeof(double) * 3 * s->maxhold); }
     memcpy(s->xhold, s->x, sizeof(double) * 3 * nlocal);
@@ -650,9 +664,22 @@ static int neighbor_decide(osph_sph *s)
   return 0;
 }
 
-/* half_from_full_newton ownership test, neigh_derive.cpp:117-135 */
+/* Which atom of a pair holds it in the reference's half list.
+ * A deck with a full-list sub-style (sph/rhosum, sph/rhosum/multiphase, sph/colorgradient: pair_sph_rhosum.cpp:60-61) derives the half
+ * list from the full one: half_from_full_newton, neigh_derive.cpp:117-135.
+ * A deck without one builds it directly: half_bin_newton, neigh_half_bin.cpp:339-400 -- inside i's own bin the atoms behind i in the
+ * bin's linked list (owned atoms in index order, then ghosts, which must lie "above and to the right"), and EVERY atom of the bins of the
+ * upper half stencil (stencil_half_bin_{2d,3d}_newton, neigh_stencil.cpp:125-158: k > 0 || j > 0 || (j == 0 && i > 0)).
+ * The pair sets are the same; who holds a pair matters where a style is not symmetric in (i, j): stale ghost fields (vest of a ghost at
+ * setup is the border-time copy, examples/USER/sph/cavity_flow), the phase-change clamp, gamma of the list owner. */
 static int half_keeps(osph_sph *s, int i, int j)
 {
+  if (s->half_bin) {
+    int ix, iy, iz, jx, jy, jz;
+    coord2bin3(s, &s->x[3*i], &ix, &iy, &iz); coord2bin3(s, &s->x[3*j], &jx, &jy, &jz);
+    int dx = jx - ix, dy = jy - iy, dz = jz - iz;
+    if (dx || dy || dz) return dz > 0 || (dz == 0 && (dy > 0 || (dy == 0 && dx > 0)));
+  }
   if (j < s->nlocal) return !(i > j);
   if (s->x[3*j+2] < s->x[3*i+2]) return 0;
   if (s->x[3*j+2] == s->x[3*i+2]) {
@@ -1245,6 +1272,10 @@ static void fix_dt_reset(osph_sph *s, ofix *fx)
   double dt = dtmin;
   if (fx->minbound && dt < fx->tmin) dt = fx->tmin;
   if (fx->maxbound && dt > fx->tmax) dt = fx->tmax;
+  if (dt == s->dt) return;                                   /* fix_dt_reset.cpp:175 */
+  s->laststep = s->ntimestep;
+  s->atime += (s->ntimestep - s->atimestep) * s->dt;         /* Update::update_time, update.cpp:480-484 */
+  s->atimestep = s->ntimestep;
   s->dt = dt;
 }
 /* FixSetMesodE::post_force, constant value, fix_setmesode.cpp:171-199 */

@@ -39,6 +39,8 @@
 #define b200_fix_setmesode     osph_fix_setmesode
 #define b200_fix_dt_reset      osph_fix_dt_reset
 #define b200_get_timestep      osph_get_timestep
+#define b200_set_time          osph_set_time
+#define b200_get_time          osph_get_time
 #define b200_request_virial    osph_request_virial
 #define b200_get_virial        osph_get_virial
 #define b200_set_atoms         osph_set_atoms

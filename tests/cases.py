@@ -463,3 +463,42 @@ def _long(c, name, nsteps, tol):
 _add(_long(_dam("dam2d", 2, 60), "dam2d_1000", 1000, 1e-6))
 _add(_long(_droplet("droplet2d", 2, 30, 40), "droplet2d_1000", 1000, 1e-6))
 _add(_long(_bubble("bubble2d", 2, 32, 30), "bubble2d_1000", 1000, 1e-6))
+
+
+# ---- lid-driven cavity (examples/USER/sph/cavity_flow/cavity_flow.lmp): sph/taitwater/morris ALONE in a periodic box, a strip of driver
+#      particles that starts with a velocity and feels no force (fix setforce 0 0 0).  Two things no other deck has:
+#      (1) no full-list sub-style, so the reference builds its half list with half_bin_newton (neigh_half_bin.cpp:285-420), whose pair
+#          ownership is not half_from_full_newton's;
+#      (2) non-zero velocities at setup: the ghosts carry the border-time copy of vest (zero) through the setup force evaluation, the owned
+#          atoms the value FixMeso::setup_pre_force gave them (fix_meso.cpp:68-85), so every pair across a periodic face is evaluated with one
+#          fresh and one stale velocity -- from the side of the atom that holds the pair.
+#      `cavity2d_rhosum` is the same box behind hybrid/overlay sph/rhosum (full list -> half_from_full_newton): (2) without (1). ----
+def _cavity(name, nsteps, rhosum=False):
+    dx = 0.025e-3; h = 6.5e-5; L = 44 * dx
+    box = ((0.0, 0.0, -1.0e-6), (L, L, 1.0e-6))
+    m = 1000.0 * dx * dx
+    create = """lattice sq %s
+create_atoms 1 box
+region strip block EDGE EDGE %s EDGE EDGE EDGE units box
+set region strip type 2
+set group all meso_rho 1000.0
+mass 1 %s
+mass 2 %s
+group driver type 2
+variable vx0 atom 0.0005*sin(6.283185307179586*y/%s)
+variable vy0 atom 0.0003*cos(6.283185307179586*x/%s)
+velocity all set v_vx0 v_vy0 0.0 units box
+velocity driver set 0.001 0.0 0.0 units box""" % (_f(dx), _f(0.8 * L), _f(m), _f(m), _f(L), _f(L))
+    if rhosum:
+        ps = [("pair_style", "hybrid/overlay", "sph/rhosum 1", "sph/taitwater/morris"),
+              ("pair_coeff", "* *", "sph/taitwater/morris", 1000.0, 0.1, 1.0e-3, h), ("pair_coeff", "* *", "sph/rhosum", h)]
+    else:
+        ps = [("pair_style", "sph/taitwater/morris"), ("pair_coeff", "* *", 1000.0, 0.1, 1.0e-3, h)]
+    cmds = [("mass", "1", m), ("mass", "2", m)] + ps + [("neighbor", 3.0e-6), ("timestep", 5.0e-5),
+            ("fix", "all", "meso"), ("fix", "driver", "setforce", 0.0, 0.0, 0.0)]
+    return Case(name, 2, "p p p", box, "meso", 2, create, cmds, nsteps, groups=(("driver", 2),))
+
+
+_add(_cavity("cavity2d", 60))
+_add(_cavity("cavity2d_rhosum", 60, rhosum=True))
+CASES["cavity2d"].engine = CASES["cavity2d_rhosum"].engine = False

@@ -61,3 +61,28 @@ def test_engine_matches_oracle_live(name):
             assert harness.relerr(a[k], b[k]) < 1e-9, (name, chunk, k, harness.relerr(a[k], b[k]))
     for s in sims:
         s.close()
+
+
+def test_elapsed_time_under_fix_dt_reset_matches_oracle():
+    """Update::atime / atimestep and FixDtReset::laststep (thermo `time`, f_ID of the fix) advance on the device exactly as
+    FixDtReset::end_of_step + Update::update_time advance them (fix_dt_reset.cpp:175-181, update.cpp:480-484); the oracle's
+    restatement is itself checked against lmp_serial's thermo output of the shipped water_collapse deck (tests/test_shell_shipped_cpu.py)"""
+    case = cases.CASES["dam2d_dtreset"]
+    g = harness.load_golden("dam2d_dtreset")
+    sims = [mk(case.deck()) for mk in (pkg.B200Sim, harness.oracle_sim)]
+    for s in sims:
+        s.set_atoms(**harness.state_from(g, "init_", case.multiphase))
+        s.set_time(0.125, 0, 0)
+        s.setup()
+    seen = set()
+    for chunk in range(4):
+        for s in sims:
+            s.run(7)
+        (ta, sa, la), (tb, sb, lb) = sims[0].time(), sims[1].time()
+        assert (sa, la) == (sb, lb), (chunk, sa, la, sb, lb)
+        assert abs(ta - tb) <= 1e-14 * abs(tb), (chunk, ta, tb)
+        assert abs(sims[0].timestep() - sims[1].timestep()) <= 1e-13 * sims[1].timestep()
+        seen.add(la)
+    assert len(seen) > 1 and tb > 0.125          # the timestep did change along the way
+    for s in sims:
+        s.close()
