@@ -26,6 +26,22 @@ __global__ void k_setup_pre_force(int nlocal, FixList fl, StepArrays a)
     }
 }
 
+// Is FixMeso::setup_pre_force about to change vest for any owned atom?  Then the ghosts this setup's borders made carry a vest their
+// owners no longer have through the setup force evaluation (Verlet::setup, verlet.cpp:106-127: borders, then setup_pre_force, then
+// the pair styles; the next forward_comm comes with step 1) -- non-zero initial velocities, or a run that continues an earlier one.
+__global__ void k_vest_stale(int nlocal, FixList fl, StepArrays a, int *flag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  int m = a.mask[i];
+  for (int k = 0; k < fl.n; k++)
+    if (fl.kind[k] == 1 && (m & fl.bit[k])) {
+      double4 v = a.vm[i], vr = a.vr[i];
+      if (v.x != vr.x || v.y != vr.y || v.z != vr.z) *flag = 1;
+      return;
+    }
+}
+
 // modify->initial_integrate: FixMeso::initial_integrate (fix_meso.cpp:91-140) and
 // largest squared displacement since the build of the atoms (owned or ghost) a cell held at the build, as fp32 bits rounded up
 // (non-negative floats order like their bit patterns): the tile path decides per tile whether its mid / far rows are due

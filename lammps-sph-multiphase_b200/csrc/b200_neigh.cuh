@@ -288,6 +288,7 @@ struct BuildArgs {
   const double *farsq;           // [MAXTT] (cut + margin)^2: entries beyond go to the far rows (see FAR_MARGIN_FRAC)
   unsigned *far; int *numfar;
   unsigned *nbr;
+  int hbn;                       // the deck has no full-list sub-style: pair ownership of half_bin_newton (see half_bin_upper)
   int *numneigh;
   int *maxcount;
 };
@@ -301,6 +302,15 @@ __device__ __forceinline__ bool ghost_above(double xi, double yi, double zi, dou
     if (yj == yi && xj < xi) return false;
   }
   return true;
+}
+
+// Neighbor::half_bin_newton (neigh_half_bin.cpp:339-400), the half list of a deck WITHOUT a full-list sub-style: atom i holds the pairs
+// with every atom of the bins of the upper half stencil (stencil_half_bin_{2d,3d}_newton, neigh_stencil.cpp:125-158:
+// k > 0 || j > 0 || (j == 0 && i > 0)); inside i's own bin the rule is the one of half_from_full_newton (owned atoms behind i in the
+// bin's linked list = larger local index, ghosts "above and to the right").  d* = reference bin of j minus reference bin of i.
+__device__ __forceinline__ bool half_bin_upper(int dbx, int dby, int dbz)
+{
+  return dbz > 0 || (dbz == 0 && (dby > 0 || (dby == 0 && dbx > 0)));
 }
 
 // One warp per engine cell.  Each lane owns one row particle; the candidates of the
@@ -384,11 +394,14 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build(BuildArgs A)
             if (!(rsq_nofma(ex, ey, ez) < cutmaxsq)) continue;
           }
           unsigned ent = (unsigned)j | ((unsigned)tj << NBR_TYPE_SHIFT);
+          const int hbx = tw_bx(wj) - bxi, hby = tw_by(wj) - byi, hbz = tw_bz(wj) - bzi;      // reference bin of j relative to i's
+          const bool other_bin = A.hbn && (hbx | hby | hbz);
           if (!pass) {
-            bool own = (j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj);
+            bool own = other_bin ? half_bin_upper(hbx, hby, hbz) : ((j < A.nlocal) ? (oi < sm.o[idx]) : ghost_above(xi, yi, zi, xj, yj, zj));
             if (own) ent |= NBR_OWNER_BIT;
           } else {
-            if (!ghost_above(xj, yj, zj, xi, yi, zi)) continue;   // (owned j, ghost i): kept by j's half list?
+            // (owned j, ghost i): kept by j's half list?
+            if (!(other_bin ? half_bin_upper(-hbx, -hby, -hbz) : ghost_above(xj, yj, zj, xi, yi, zi))) continue;
             ent |= NBR_OWNER_BIT;
           }
           // inner zone (inside the pair cutoff now): filled from the front; outer zone (skin shell, or

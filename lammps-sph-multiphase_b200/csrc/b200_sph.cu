@@ -149,6 +149,7 @@ struct b200_sph {
   double *d_dt = nullptr, *h_dtv = nullptr;      // h_dtv: pinned mirror of d_dt[0..4]
   double atime = 0.0; long long atimestep = 0, laststep = 0;      // Update::atime / atimestep, FixDtReset::laststep (b200_set_time / b200_get_time)
   // tile path (b200_tile.cuh): single-phase decks
+  bool half_bin = false;      // no full-list sub-style in the deck: the reference's half list is half_bin_newton's (k_build, BuildArgs::hbn)
   bool tile_on = false, tile_ok = true, rows_tiled = false, tile_nouni = getenv("B200_TILE_NOUNI") != nullptr;
   int tile_nparts = 2, tile_nk = 1, tile_slotcap = 0, tile_cap = 0, ntiles = 0, nsm = 0, tile_split = 2;
   DevBuf<int> x_mark, x_inv, x_lflag, x_lpos, x_list, x_work;      // comm_exchange: replay of the reference's hole-filling order
@@ -829,7 +830,7 @@ static void neighbor_build(b200_sph *h, bool do_pbc)
     BuildArgs A;
     A.g = g; A.nlocal = nl; A.nghost = h->nghost; A.stride = h->stride; A.ntypes1 = h->ntypes + 1;
     A.xt = h->C().xt.p; A.orig = h->C().orig.p; A.cso = h->cso.p; A.csg = h->csg.p; A.gorder = h->gorder.p; A.cutneighsq = h->d_cutneighsq.p; A.prunesq = h->d_prunesq.p; A.farsq = h->d_farsq.p; A.far = h->far.p; A.numfar = h->numfar.p;
-    A.nbr = h->nbr.p; A.numneigh = h->numneigh.p; A.maxcount = h->d_flags;
+    A.nbr = h->nbr.p; A.numneigh = h->numneigh.p; A.maxcount = h->d_flags; A.hbn = h->half_bin ? 1 : 0;
     LAUNCH(h, k_build, nblk(g.ncells, BUILD_WARPS), BUILD_WARPS * 32, A);
     CK(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -920,9 +921,14 @@ static void build_plan(b200_sph *h)
         throw std::string("pair sph/lj/b200 needs atom_style meso and a full-list sub-style (sph/rhosum) in the deck: without one LAMMPS builds its half "
                           "list in another order (half_bin_newton), and the style's result depends on that order (pair_sph_lj.cpp:139)");
     }
+  // Without a full-list sub-style (sph/rhosum, sph/rhosum/multiphase, sph/colorgradient) the reference derives nothing from a full list:
+  // its half list is half_bin_newton's (neigh_half_bin.cpp:285-420), with another pair ownership than half_from_full_newton's
+  h->half_bin = true;
+  for (const Pass &p : h->plan) if (p.type != 3) h->half_bin = false;
   // tile path (b200_tile.cuh): single-phase decks, and multiphase decks without fix phase_change
   bool ok = h->tile_ok && !getenv("B200_NO_TILE") && !h->plan.empty();
   if (h->multiphase && getenv("B200_NO_TILE_MP")) ok = false;
+  if (h->multiphase && h->half_bin) ok = false;      // the multiphase tile entries carry half_from_full_newton's ownership; k_build knows both rules
   int np = 2, nk = 1;
   const int SP = K_TAIT | K_MORRIS | K_HEAT | K_IDEAL, MPK = K_TAITMP | K_SURF | K_HEATMP | K_HEATPC;
   for (const Pass &p : h->plan) {
@@ -1521,6 +1527,18 @@ static void do_setup(b200_sph *h)
     h->maxtag = h->h_flags[12];
   }
   build_plan(h);
+  // The single-phase tile path evaluates a pair with a ghost on both owners' sides, which equals the reference's one evaluation as long
+  // as the ghost's fields are fresh copies of its owner's.  Through the setup force evaluation they are not when setup_pre_force changes
+  // vest (k_vest_stale): the pair must then be evaluated where the reference's half list holds it, ghost rows and reverse halo included,
+  // which is what the row path does.  Such a run stays on the row path (shipped deck: examples/USER/sph/cavity_flow, fixture cavity2d).
+  if (h->tile_on && !h->multiphase && (h->world > 1 || h->g.periodic[0] || h->g.periodic[1] || h->g.periodic[2])) {
+    CK(cudaMemsetAsync(h->d_flags + 14, 0, sizeof(int), h->st));
+    if (h->nlocal) LAUNCH(h, k_vest_stale, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->d_flags + 14);
+    if (h->world > 1) NCK(g_nccl.AllReduce(h->d_flags + 14, h->d_flags + 14, 1, ncclInt, ncclMax, h->nccl, h->st));
+    CK(cudaMemcpyAsync(h->h_flags + 14, h->d_flags + 14, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (h->h_flags[14]) h->tile_on = false;
+  }
   if (h->sortfreq > 0) { h->sortgeom_ok = false; h->sort_pending = true; }      // Atom::setup -> setup_sort_bins; Verlet::setup: if (atom->sortfreq > 0) atom->sort()
   neighbor_build(h, true);
   h->nbuilds = 0;

@@ -501,4 +501,3 @@ velocity driver set 0.001 0.0 0.0 units box""" % (_f(dx), _f(0.8 * L), _f(m), _f
 
 _add(_cavity("cavity2d", 60))
 _add(_cavity("cavity2d_rhosum", 60, rhosum=True))
-CASES["cavity2d"].engine = CASES["cavity2d_rhosum"].engine = False
