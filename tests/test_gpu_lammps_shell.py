@@ -155,3 +155,36 @@ def test_phase_change_state_survives_a_second_run(tmp_path):
     assert np.array_equal(a[:, :2], b[:, :2])
     for lo, hi in ((2, 5), (5, 8), (8, 11), (11, 12), (12, 13)):
         assert relerr(b[:, lo:hi], a[:, lo:hi]) <= 1e-8
+
+
+def test_water_collapse_thermo_keywords(tmp_path):
+    """examples/USER/sph/water_collapse/water_collapse.lmp:42 prints `ke c_esph v_etot f_gfix press time f_dtfix`: the potential energy of
+    fix gravity (FixGravity::compute_scalar), the elapsed time under the variable timestep (Update::atime, thermo.cpp:1500) and the last
+    step fix dt/reset changed it on (FixDtReset::compute_scalar) -- with the force, the timestep and the time bookkeeping on the device"""
+    case = cases.CASES["dam2d_dtreset"]
+    text = "\n".join([case.header_text(), case.create, case.lammps_text(),
+                      "compute ce all meso_e/atom", "compute esph all reduce sum c_ce", "compute cke all ke", "variable etot equal c_esph+c_cke+f_f1",
+                      "thermo 7", "thermo_style custom step ke c_esph v_etot f_f1 press time f_f4", "thermo_modify format float %.15g norm no",
+                      "dump dfin all custom 35 dump.final %s" % COLS.replace("c_crho c_ce", "vx vy"), 'dump_modify dfin sort id format "%s"' % FMT,
+                      "run 35", "run 14", ""])
+    a, a_out, b, b_out = _both(tmp_path, text)
+
+    def rows(out):
+        r, on = [], False
+        for l in out.splitlines():
+            t = l.split()
+            if t[:2] == ["Step", "KinEng"]:
+                on = True; continue
+            if on:
+                try:
+                    r.append([float(v) for v in t]); assert len(t) == 8
+                except (ValueError, AssertionError):
+                    on = False
+        return np.array(r)
+    ra, rb = rows(a_out), rows(b_out)
+    assert ra.shape == rb.shape and len(ra) >= 9, (ra.shape, rb.shape)
+    assert np.array_equal(ra[:, 0], rb[:, 0]) and np.array_equal(ra[:, 7], rb[:, 7]), (ra[:, 7], rb[:, 7])      # steps, f_dtfix
+    assert len(set(ra[:, 7])) > 2                                                                              # the timestep did change
+    for c, nm in ((1, "ke"), (2, "esph"), (3, "etot"), (4, "f_gfix"), (5, "press"), (6, "time")):
+        s = np.abs(ra[:, c]).max()
+        assert np.abs(ra[:, c] - rb[:, c]).max() <= 1e-8 * max(s, 1e-300), (nm, ra[:, c], rb[:, c])
