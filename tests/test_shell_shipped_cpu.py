@@ -44,6 +44,25 @@ CASES = [
 ]
 
 
+# multiphase_two_atoms/*.lmp include an in.atoms (and in.vars) that `maxima -b <deck>.mac` prints from the lists at the top of each .mac
+# (x, type; gamma, soundspeed, eta, rbackground, rho0): written here from those same lists.  The decks print per-atom results through fix print.
+def _atoms(xs, types):
+    return "printf '%s' > in.atoms" % "".join("create_atoms %d single %s units box\n" % (t, " ".join("%g" % v for v in x)) for x, t in zip(xs, types))
+
+
+T3 = [[5, 5, 5], [5.5, 5, 5], [5, 5, 4.8]]
+CASES += [
+    Shipped("two_atoms_colorgradient", "multiphase_two_atoms", "colorgradient.lmp", cap=1, pre=[_atoms(T3, [1, 2, 2])], files=["outpt.dat"]),
+    Shipped("two_atoms_rhosum", "multiphase_two_atoms", "sph_rhosum_multiphase.lmp", cap=1, pre=[_atoms(T3, [1, 2, 2])], files=["outpt.dat"]),
+    Shipped("two_atoms_taitwater", "multiphase_two_atoms", "sph_taitwater_multiphase.lmp", cap=1, files=["outpt.dat"],
+            pre=[_atoms(T3, [1, 2, 2]), "printf 'variable gamma equal 1\nvariable soundspeed equal 1\nvariable eta equal 0\nvariable rbackground equal 0.5\nvariable rho0 equal 1\n' > in.vars"]),
+    Shipped("two_atoms_surfacetension", "multiphase_two_atoms", "surfacetension.lmp", cap=1, files=["output.dat"],
+            pre=[_atoms([[4.6, 5.3, 5], [5.5, 5, 5.2], [5.0, 5.0, 5.0]], [1, 2, 2])]),
+    Shipped("two_atoms_heat_phase_change", "multiphase_two_atoms", "heatconduction_phase_change.lmp", cap=1, pre=[_atoms([[5, 5, 5], [5.6, 5, 5]], [1, 2])]),
+    Shipped("two_atoms_phase_change", "multiphase_two_atoms", "phase_change.lmp", cap=1, pre=[_atoms([[5, 5, 5], [5.6, 5, 5]], [1, 2])]),
+]
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_shipped_deck_through_the_shells(case, tmp_path):
     shim = shipped.build_shim()
