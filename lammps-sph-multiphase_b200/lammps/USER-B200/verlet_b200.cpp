@@ -63,6 +63,10 @@ void VerletB200::init()
       if (comm->cutghost[d] > domain->subhi[d] - domain->sublo[d])
         error->all(FLERR, "run_style verlet/b200: the ghost cutoff exceeds the sub-domain (more than one ghost layer per swap)");
   }
+  // per-atom energy / virial tallies (Pair::ev_tally into eatom / vatom, pair.cpp:867-1000) are not formed by the engine, only the
+  // global pair virial is: a compute that reads them (stress/atom, pe/atom, ...; Integrate::ev_setup collected them) is refused
+  if (nelist_atom || nvlist_atom)
+    error->all(FLERR, "run_style verlet/b200: per-atom energy / virial tallies (compute pe/atom, stress/atom, ...) are not computed by the engine");
   if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton on");
   if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 supports orthogonal boxes");
   if (!atom->rho_flag || !atom->e_flag) error->all(FLERR, "run_style verlet/b200 requires atom_style meso or meso/multiphase");
@@ -87,6 +91,11 @@ void VerletB200::configure()
       check(b200_comm_init(h, comm->nprocs, comm->me, comm->procgrid, comm->myloc, procneigh, id));
     }
   }
+  // the engine restates the binned builds (full_bin / half_bin_newton) over all atoms and type pairs (checked here, after
+  // Neighbor::init has digested the neigh_modify settings: LAMMPS::init runs it after Integrate::init)
+  if (neighbor->style != 1) error->all(FLERR, "run_style verlet/b200 supports neighbor style bin");       // enum{NSQ,BIN,MULTI}, neighbor.cpp:50
+  if (neighbor->exclude_setting()) error->all(FLERR, "run_style verlet/b200: neigh_modify exclude is not supported (use pair_coeff I J none)");
+  if (neighbor->includegroup) error->all(FLERR, "run_style verlet/b200: neigh_modify include is not supported");
   int n = atom->ntypes;
   int multiphase = atom->rmass_flag ? 1 : 0;
   check(b200_domain(h, domain->dimension, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi));

@@ -1,0 +1,69 @@
+"""CPU: what the USER-B200 shells refuse, and deck idioms beyond the shipped examples, through `lmp_b200 -sf b200` with the oracle
+behind the C-ABI (tests/shipped.py) against `lmp_serial`.  The base text is the shipped water_collapse deck (read from the reference at
+test time) with one edit per case."""
+import os
+import re
+
+import pytest
+
+import shipped
+from shipped import Shipped
+
+pytestmark = pytest.mark.skipif(not shipped.available(), reason="needs /root/reference, oracle/_ref/lmp_serial and lmp_b200")
+
+REFUSED = [
+    # (edit: regex -> replacement on water_collapse.lmp, message the shell must print)
+    ("per_atom_virial", (r"^thermo_style.*$", "compute st all stress/atom NULL\ncompute sts all reduce sum c_st[1]\nthermo_style custom step c_sts"),
+     "per-atom energy / virial tallies"),
+    ("host_stepping_fix", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nfix wl water wall/reflect ylo EDGE"), "has no /b200 variant"),
+    ("end_of_step_fix_that_writes", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nfix mom water momentum 1 linear 1 1 0"), "has no /b200 variant"),
+    ("neigh_exclude", (r"^neigh_modify.*$", "neigh_modify every 5 delay 0 check no exclude type 1 2"), "neigh_modify exclude is not supported"),
+    ("neighbor_nsq", (r"^neighbor\s.*$", "neighbor ${skin} nsq"), "supports neighbor style bin"),
+    ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
+    ("variable_gravity", (r"^fix\s+gfix.*$", "variable gmag equal 9.81*(1.0+0.0*step)\nfix gfix water gravity v_gmag vector 0 -1 0"), "constant gravity only"),
+]
+
+
+@pytest.mark.parametrize("name,edit,message", REFUSED, ids=[r[0] for r in REFUSED])
+def test_refused_with_a_message(name, edit, message, tmp_path):
+    """no silent fallback and no crash: the run stops with the shell's own message before any step is taken"""
+    case = Shipped(name, "water_collapse", "water_collapse.lmp", cap=10, subs=[edit], dump=False)
+    p = shipped.run_one(case, shipped.B200, str(tmp_path / "b200"), shipped.build_shim())
+    assert p.returncode == 1, (p.returncode, p.stdout[-1500:], p.stderr[-500:])
+    assert "ERROR" in p.stdout and message in p.stdout, p.stdout[-1500:]
+    assert "Loop time" not in p.stdout
+
+
+VARIANTS = [
+    # run N upto / start-stop keywords, runs that continue an earlier one (their setups see vest != v)
+    ("run_keywords", [(r"^run\s+\S+.*$", "run 12\nrun 30 upto\nrun 10 start 0 stop 200")], 1e-9),
+    # restart files written during a run and read back into a fresh deck would need a second deck: here the periodic write itself (an output step)
+    ("restart_every", [(r"^run\s+\S+.*$", "restart 8 zz.restart\nrun 24")], 1e-9),
+    # thermo every step (every step is an output step: one-step segments), dump every 3
+    ("every_step_output", [(r"^thermo\s+10", "thermo 1"), (r"^run\s+\S+.*$", "run 9")], 1e-9),
+    # fix ave/time over a compute reduce, fix ave/atom of a per-atom compute (END_OF_STEP, read-only, evaluated on their own steps)
+    ("fix_ave", [(r"^run\s+\S+.*$", "fix avt all ave/time 2 3 6 c_esph file zz.avt\nfix ava all ave/atom 1 4 4 c_rho_peratom\nrun 12")], 1e-9),
+]
+
+
+@pytest.mark.parametrize("name,edits,tol", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_deck_idioms_match_the_reference(name, edits, tol, tmp_path):
+    case = Shipped(name, "water_collapse", "water_collapse.lmp", cap=10 ** 9, subs=edits, files=["zz.avt"] if name == "fix_ave" else [])
+    case.cap = 4           # only the interval of the appended full-precision dump (text() caps literal run lengths at 10**9 = not at all)
+    text = case.text
+    case.text = lambda: re.sub(r"^(\s*)run (\d+)", lambda m: "%srun %s" % (m.group(1), m.group(2)), text(), flags=re.M)
+    out = {}
+    for who, exe, pre in (("ref", shipped.REF, None), ("b200", shipped.B200, shipped.build_shim())):
+        wd = str(tmp_path / who)
+        p = shipped.run_one(case, exe, wd, pre)
+        assert p.returncode == 0 and "ERROR" not in p.stdout, who + ":\n" + p.stdout[-3000:] + p.stderr[-2000:]
+        out[who] = (wd, p.stdout)
+    assert "B200 engine: sph_oracle" in out["b200"][1]
+    ta, tb = shipped.thermo_block(out["ref"][1]), shipped.thermo_block(out["b200"][1])
+    assert len(ta) > 4
+    shipped.compare_rows(ta, tb, tol, name + " thermo")
+    for f in list(case.files) + ["zz.dump"]:
+        a = shipped.numeric_rows(os.path.join(out["ref"][0], f))
+        b = shipped.numeric_rows(os.path.join(out["b200"][0], f))
+        assert len(a) > 0, f
+        shipped.compare_rows(a, b, tol, name + " " + f)
