@@ -1530,14 +1530,17 @@ static void do_setup(b200_sph *h)
   // The single-phase tile path evaluates a pair with a ghost on both owners' sides, which equals the reference's one evaluation as long
   // as the ghost's fields are fresh copies of its owner's.  Through the setup force evaluation they are not when setup_pre_force changes
   // vest (k_vest_stale): the pair must then be evaluated where the reference's half list holds it, ghost rows and reverse halo included,
-  // which is what the row path does.  Such a run stays on the row path (shipped deck: examples/USER/sph/cavity_flow, fixture cavity2d).
+  // which is what the row path does.  The setup evaluation of such a run is taken on the row path; the rows of the tile path are built
+  // right after it (same atoms, same ghosts, now with their owners' vest -- which the reference's ghosts receive with the forward halo
+  // of step 1 before anything reads them).  Shipped deck: examples/USER/sph/cavity_flow; fixtures cavity2d, cavity2d_rhosum.
+  bool row_setup = false;
   if (h->tile_on && !h->multiphase && (h->world > 1 || h->g.periodic[0] || h->g.periodic[1] || h->g.periodic[2])) {
     CK(cudaMemsetAsync(h->d_flags + 14, 0, sizeof(int), h->st));
     if (h->nlocal) LAUNCH(h, k_vest_stale, nblk(h->nlocal, 256), 256, h->nlocal, h->fl, h->step_arrays(), h->d_flags + 14);
     if (h->world > 1) NCK(g_nccl.AllReduce(h->d_flags + 14, h->d_flags + 14, 1, ncclInt, ncclMax, h->nccl, h->st));
     CK(cudaMemcpyAsync(h->h_flags + 14, h->d_flags + 14, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    if (h->h_flags[14]) h->tile_on = false;
+    if (h->h_flags[14]) { h->tile_on = false; row_setup = true; }
   }
   if (h->sortfreq > 0) { h->sortgeom_ok = false; h->sort_pending = true; }      // Atom::setup -> setup_sort_bins; Verlet::setup: if (atom->sortfreq > 0) atom->sort()
   neighbor_build(h, true);
@@ -1548,6 +1551,11 @@ static void do_setup(b200_sph *h)
   // ghosts carry vest of the border comm (before setup_pre_force), exactly as in Verlet::setup
   pair_compute_all(h);
   post_final(h, 1, 1, 0);
+  if (row_setup && !getenv("B200_STALE_SETUP_STAYS_ON_ROWS")) {      // (the switch keeps the whole run on the row path: A/B in tests/test_gpu_tile.py)
+    h->tile_on = true;
+    neighbor_build(h, true);       // falls back to rows by itself (collectively) if a tile does not fit
+    h->nbuilds = 0;
+  }
   if (h->dtreset) {            // FixDtReset::setup -> end_of_step
     h->h_dtv[0] = h->dt; h->h_dtv[1] = 0.0; h->h_dtv[2] = h->atime;
     memcpy(h->h_dtv + 3, &h->atimestep, sizeof(long long)); memcpy(h->h_dtv + 4, &h->laststep, sizeof(long long));

@@ -130,3 +130,20 @@ def test_per_tile_zone_flags_equal_the_global_flag(name, nsteps):
         b = _run(name, nsteps, {"B200_ZONE_GLOBAL": "1"})[0]
     for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de"):
         assert np.array_equal(a[k], b[k]), (name, k, harness.relerr(a[k], b[k]))
+
+
+@pytest.mark.parametrize("name", ["cavity2d_rhosum", "cavity2d"])
+def test_stale_setup_returns_to_the_tile_path(name):
+    """non-zero initial velocities in a periodic single-phase box: the ghosts carry a stale vest through the setup force evaluation, which
+    is taken on the row path (reference pair orientation, reverse halo); the run itself is back on the tile kernels and equals a run
+    that stays on the row path"""
+    a, na, ca = _run(name, 30, {})
+    b, nb, cb = _run(name, 30, {"B200_STALE_SETUP_STAYS_ON_ROWS": "1"})
+    c, nc, cc = _run(name, 30, {"B200_NO_TILE": "1"})
+    assert ca["builds"] == cb["builds"] == cc["builds"]
+    assert ca["launches"] != cb["launches"]          # tile kernels against row kernels over the 30 steps
+    for p, q, r in zip(na, nb, nc):
+        assert np.array_equal(p, q) and np.array_equal(p, r), "neighbor lists differ"
+    for k in ("x", "v", "vest", "f", "rho", "drho", "e", "de"):
+        assert harness.relerr(a[k], b[k]) < 2e-11, (name, k, harness.relerr(a[k], b[k]))
+        assert harness.relerr(b[k], c[k]) == 0.0, (name, k)
