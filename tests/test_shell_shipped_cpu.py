@@ -31,6 +31,12 @@ CASES = [
     Shipped("droplet_grid", "droplet_grid", "droplet.lmp", var=["-var", "icase", "2", "-var", "nx", "42"] + D, cap=40, pre=["mkdir -p data"],
             files=["data/rg.dat", "data/cm.dat"]),
     Shipped("square_to_sphere", "square_to_sphere", "droplet.lmp", var=["-var", "ndim", "3", "-var", "nx", "14"] + D, cap=30, files=["data/rg.dat"]),
+    # the decks' other documented cases: icase 1 (no wall), the 2-D square (cylinder.lmp instead of cube.lmp), the 2-D bubble
+    Shipped("contact_angle_case1", "contact_angle", "droplet.lmp", var=["-var", "icase", "1", "-var", "nx", "41"] + D, cap=30, pre=["mkdir -p data"], files=["data/com.dat"]),
+    Shipped("droplet_grid_case1", "droplet_grid", "droplet.lmp", var=["-var", "icase", "1", "-var", "nx", "42"] + D, cap=30, pre=["mkdir -p data"],
+            files=["data/rg.dat", "data/cm.dat"]),
+    Shipped("square_to_sphere_2d", "square_to_sphere", "droplet.lmp", var=["-var", "ndim", "2", "-var", "nx", "40"] + D, cap=40, files=["data/rg.dat"]),
+    Shipped("bubble_random_2d", "bubble_random", "bubble.lmp", var=["-var", "nx", "40", "-var", "ndim", "2"] + D, cap=40),
     # sph/taitwater/morris alone (half_bin_newton lists), `pair_coeff 2 3 none`, a driver strip that starts with a velocity in a periodic box
     Shipped("cavity_flow", "cavity_flow", "cavity_flow.lmp", cap=400),
     # read_data, fix gravity + its potential energy f_gfix, fix dt/reset + f_dtfix and the thermo keyword `time`, enforce2d, press
