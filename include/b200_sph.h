@@ -50,7 +50,12 @@ enum {
  *   cut, cutsq   = PairSPH*::cut / Pair::cutsq of the sub-style
  * per-type:  rho0, B, soundspeed (taitwater*), gamma, rbackground (multiphase)
  * per-pair:  viscosity (taitwater*), alpha (colorgradient alpha / heat D),
- *            tc + fixflag (heatconduction/phasechange :124-129)               */
+ *            tc + fixflag (heatconduction/phasechange :124-129)
+ * Which atom of a pair holds it in the reference's half list follows from the set of sub-styles: with a full-list style among them
+ * (sph/rhosum, sph/rhosum/multiphase, sph/colorgradient: pair_sph_rhosum.cpp:60-61) the half lists are derived from the full one
+ * (half_from_full_newton, neigh_derive.cpp:83-145), without one they are built by half_bin_newton (neigh_half_bin.cpp:285-420).  The
+ * engine applies the matching rule wherever a result depends on the holder (stale ghost fields at setup, gamma of the list owner,
+ * the phase-change clamp, the viscosity table of sph/idealgas).                */
 typedef struct {
   int style;                 /* B200_PAIR_* */
   int nstep;                 /* rhosum*, colorgradient: settings() arg; else 0 */
