@@ -247,9 +247,11 @@ class Deck:
         """pair_style <style> args | pair_style hybrid/overlay <sub1 args> <sub2 args> ...
         (PairHybrid::settings, pair_hybrid.cpp:190-258)"""
         self.styles, self._initd = [], False
+        n1 = self.ntypes + 1
+        self.hset = np.zeros((n1, n1), np.int32)                 # PairHybrid::setflag
+        self.hmap = [[[] for _ in range(n1)] for _ in range(n1)]   # PairHybrid::nmap / map (pair_hybrid.h:59-60)
+        self.overlay = name == "hybrid/overlay"
         if name in ("hybrid/overlay", "hybrid"):
-            if name == "hybrid":
-                raise DeckError("b200 SPH package supports hybrid/overlay")
             self.hybrid = True
             for s in sub:
                 w = s.split()
@@ -268,9 +270,28 @@ class Deck:
         if self.hybrid:
             sub, args = args[0], args[1:]
             m = [k for k, s in enumerate(self.styles) if s.name == sub]
-            if not m:
+            none = not m and sub == "none"
+            if not m and not none:
                 raise DeckError("Pair coeff for hybrid has invalid style")
-            self.styles[m[0]].coeff(I, J, args)
+            if not none:
+                self.styles[m[0]].coeff(I, J, args)
+            # which type pairs map to which sub-style: `none` wipes the map, plain hybrid replaces it (pair_hybrid.cpp:378-398),
+            # hybrid/overlay adds the sub-style if it is new for the pair (pair_hybrid_overlay.cpp:88-104)
+            ilo, ihi = bounds(I, self.ntypes); jlo, jhi = bounds(J, self.ntypes)
+            count = 0
+            for i in range(ilo, ihi + 1):
+                for j in range(max(jlo, i), jhi + 1):
+                    if none:
+                        self.hset[i, j] = 1; self.hmap[i][j] = []; count += 1
+                    elif self.styles[m[0]].setflag[i, j]:
+                        if self.overlay:
+                            if m[0] not in self.hmap[i][j]:
+                                self.hmap[i][j].append(m[0])
+                        else:
+                            self.hmap[i][j] = [m[0]]
+                        self.hset[i, j] = 1; count += 1
+            if count == 0:
+                raise DeckError("Incorrect args for pair coefficients")
         else:
             self.styles[0].coeff(I, J, args)
 
@@ -414,20 +435,30 @@ class Deck:
         for s in self.styles:
             s.mapped[:] = 0
         if self.hybrid:
-            for s in self.styles:
-                if not s.setflag.any():
+            used = {k for i in range(1, n1) for j in range(i, n1) for k in self.hmap[i][j]}
+            for k, s in enumerate(self.styles):      # pair_hybrid.cpp:425-433: every sub-style must be mapped somewhere
+                if k not in used:
                     raise DeckError("Pair hybrid sub-style is not used")
-        for i in range(1, n1):
-            if not any(s.setflag[i, i] for s in self.styles):
-                raise DeckError("All pair coeffs are not set")
+            for i in range(1, n1):
+                if not self.hset[i, i]:
+                    raise DeckError("All pair coeffs are not set")
+        else:
+            for i in range(1, n1):
+                if not self.styles[0].setflag[i, i]:
+                    raise DeckError("All pair coeffs are not set")
         self.cutsq = np.zeros((n1, n1))
         for i in range(1, n1):
             for j in range(i, n1):
-                mapped = [s for s in self.styles if s.setflag[i, j]]
-                if not mapped:
-                    # mixing needs I,I and J,J on one identical single sub-style, which then
-                    # fails in PairSPH*::init_one (no mixing rule) -> same message either way
-                    raise DeckError("All pair coeffs are not set")
+                if self.hybrid:
+                    if not self.hset[i, j]:
+                        # mixing needs I,I and J,J on one identical single sub-style, which then
+                        # fails in PairSPH*::init_one (no mixing rule) -> same message either way
+                        raise DeckError("All pair coeffs are not set")
+                    mapped = [self.styles[k] for k in self.hmap[i][j]]      # empty after `pair_coeff I J none`: cutoff 0 (pair_hybrid.cpp:519-542)
+                else:
+                    mapped = [s for s in self.styles if s.setflag[i, j]]
+                    if not mapped:
+                        raise DeckError("All pair coeffs are not set")
                 cutmax = 0.0
                 for s in mapped:
                     cut = s.init_one(i, j)

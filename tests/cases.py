@@ -501,3 +501,36 @@ velocity driver set 0.001 0.0 0.0 units box""" % (_f(dx), _f(0.8 * L), _f(m), _f
 
 _add(_cavity("cavity2d", 60))
 _add(_cavity("cavity2d_rhosum", 60, rhosum=True))
+
+
+# cavity_flow.lmp as shipped, in miniature: three types (fluid, stationary walls, driver strip), `pair_style hybrid` with ONE sub-style and
+# `pair_coeff 2 3 none` (walls and driver do not interact: their cutneighsq is 0, the sub-style's own setflag stays set -- the hybrid's map
+# decides, pair_hybrid.cpp:378-398, 519-542), everything periodic so walls and driver meet their own images
+def _cavity_none(name, nsteps):
+    dx = 0.025e-3; h = 6.5e-5; L = 44 * dx
+    box = ((0.0, 0.0, -1.0e-6), (L, L, 1.0e-6))
+    m = 1000.0 * dx * dx
+    create = """lattice sq %s
+create_atoms 1 box
+region rlow block EDGE EDGE EDGE %s EDGE EDGE units box
+region rleft block EDGE %s EDGE EDGE EDGE EDGE units box
+region rright block %s EDGE EDGE EDGE EDGE EDGE units box
+region strip block EDGE EDGE %s EDGE EDGE EDGE units box
+set region rlow type 2
+set region rleft type 2
+set region rright type 2
+set region strip type 3
+set group all meso_rho 1000.0
+mass 1 %s
+mass 2 %s
+mass 3 %s
+group driver type 3
+velocity driver set 0.001 0.0 0.0 units box""" % (_f(dx), _f(3.2 * dx), _f(3.2 * dx), _f(L - 3.2 * dx), _f(L - 3.2 * dx), _f(m), _f(0.5 * m), _f(0.5 * m))
+    cmds = [("mass", "1", m), ("mass", "2", 0.5 * m), ("mass", "3", 0.5 * m),
+            ("pair_style", "hybrid", "sph/taitwater/morris"), ("pair_coeff", "* *", "sph/taitwater/morris", 1000.0, 0.1, 1.0e-3, h),
+            ("pair_coeff", "2 3", "none"), ("neighbor", 3.0e-6), ("timestep", 5.0e-5),
+            ("fix", "fluid", "meso"), ("fix", "driver", "meso"), ("fix", "walls", "meso/stationary"), ("fix", "driver", "setforce", 0.0, 0.0, 0.0)]
+    return Case(name, 2, "p p p", box, "meso", 3, create, cmds, nsteps, groups=(("driver", 3), ("fluid", 1), ("walls", 2)))      # `driver` first: its group bit is taken when the create text defines it
+
+
+_add(_cavity_none("cavity2d_none", 60))
