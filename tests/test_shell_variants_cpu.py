@@ -41,6 +41,11 @@ VARIANTS = [
     ("restart_every", [(r"^run\s+\S+.*$", "restart 8 zz.restart\nrun 24")], 1e-9),
     # thermo every step (every step is an output step: one-step segments), dump every 3
     ("every_step_output", [(r"^thermo\s+10", "thermo 1"), (r"^run\s+\S+.*$", "run 9")], 1e-9),
+    # the host changes the system between runs: atoms deleted and displaced, fields set, a fix removed and another added, timestep and
+    # neighbor settings changed -- every setup uploads the host arrays and re-registers the deck
+    ("edits_between_runs", [(r"^run\s+\S+.*$", "run 8\nregion cut block 0.5 0.9 0.3 0.6 EDGE EDGE units box\ndelete_atoms region cut\n"
+                                                "displace_atoms water move 0.0 0.002 0.0 units box\nset group water meso_e 0.5\nunfix dtfix\ntimestep 2.0e-5\n"
+                                                "neigh_modify every 3 delay 0 check yes\nfix frz bc setforce 0.0 NULL 0.0\nthermo_style custom step ke c_esph press\nrun 10")], 1e-9),
     # fix ave/time over a compute reduce, fix ave/atom of a per-atom compute (END_OF_STEP, read-only, evaluated on their own steps)
     ("fix_ave", [(r"^run\s+\S+.*$", "fix avt all ave/time 2 3 6 c_esph file zz.avt\nfix ava all ave/atom 1 4 4 c_rho_peratom\nrun 12")], 1e-9),
 ]
