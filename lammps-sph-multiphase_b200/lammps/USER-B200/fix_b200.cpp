@@ -60,11 +60,48 @@ void LAMMPS_NS::b200_fix_guard(LAMMPS *lmp, const char *name)
   }
 }
 
+// Constant gravity is the engine's own fix (b200_fix_gravity).  With equal-style variables (fix_gravity.cpp:244-258: magnitude and, for
+// `vector`, the direction components are re-evaluated every step) the force is handed over as the formula FixGravity::post_force
+// evaluates, f += massone * (magnitude * xgrav) with xgrav = xdir / sqrt(xdir xdir + ydir ydir [+ zdir zdir]) (set_acceleration,
+// :304-337), in the same association, to the engine's per-atom formula evaluator (b200_fix_addforce; csrc/b200_expr.cuh: step, dt,
+// time, arithmetic and math functions -- anything else is refused there).  Variable chute / spherical angles are refused.
 int FixGravityB200::b200_register(b200_sph *h)
 {
-  if (varflag != 0) error->all(FLERR, "fix gravity/b200 supports constant gravity only");
-  set_acceleration();
-  return b200_fix_gravity(h, groupbit, xacc, yacc, zacc);
+  if (varflag == 0) {      // enum{CONSTANT,EQUAL}, fix_gravity.cpp:34
+    set_acceleration();
+    return b200_fix_gravity(h, groupbit, xacc, yacc, zacc);
+  }
+  if (vstyle || pstyle || tstyle) error->all(FLERR, "fix gravity/b200 supports variables for the magnitude and the components of `vector`");
+  char num[64];
+  std::string M, D[3];
+  if (mstyle) { char *s = b200_variable_formula(lmp, mstr); M = std::string("(") + s + ")"; delete [] s; }
+  else { sprintf(num, "(%.17g)", magnitude); M = num; }
+  const int dim = domain->dimension;
+  if (style == 2) {        // enum{CHUTE,SPHERICAL,VECTOR}: constant direction computed once, as set_acceleration does
+    char *vs[3] = {xstr, ystr, zstr}; int st[3] = {xstyle, ystyle, zstyle}; double dv[3] = {xdir, ydir, zdir};
+    if (!xstyle && !ystyle && !zstyle) {
+      double m0 = magnitude; magnitude = 1.0; set_acceleration(); magnitude = m0;      // xacc = 1.0 * xgrav
+      double g[3] = {xacc, yacc, zacc};
+      for (int d = 0; d < 3; d++) { sprintf(num, "(%.17g)", g[d]); D[d] = num; }
+    } else {
+      std::string c[3];
+      for (int d = 0; d < 3; d++) {
+        if (st[d]) { char *s = b200_variable_formula(lmp, vs[d]); c[d] = std::string("(") + s + ")"; delete [] s; }
+        else { sprintf(num, "(%.17g)", dv[d]); c[d] = num; }
+      }
+      std::string len = "sqrt(" + c[0] + "*" + c[0] + "+" + c[1] + "*" + c[1] + (dim == 3 ? "+" + c[2] + "*" + c[2] : std::string("")) + ")";
+      for (int d = 0; d < 3; d++) D[d] = (d == 2 && dim == 2) ? std::string("(0.0)") : "(" + c[d] + "/" + len + ")";
+    }
+  } else {                 // chute / spherical with constant angles
+    double m0 = magnitude; magnitude = 1.0; set_acceleration(); magnitude = m0;
+    double g[3] = {xacc, yacc, zacc};
+    for (int d = 0; d < 3; d++) { sprintf(num, "(%.17g)", g[d]); D[d] = num; }
+  }
+  std::string F[3];
+  const char *f[3];
+  const double zero[3] = {0.0, 0.0, 0.0};
+  for (int d = 0; d < 3; d++) { F[d] = "mass*(" + M + "*" + D[d] + ")"; f[d] = F[d].c_str(); }
+  return b200_fix_addforce(h, groupbit, zero, f);
 }
 
 // FixGravity::post_force sums the potential energy of the group while it adds the force (fix_gravity.cpp:262-283:
@@ -77,6 +114,13 @@ double FixGravityB200::compute_scalar()
   double *rmass = atom->rmass, *mass = atom->mass;
   int *mask = atom->mask, *type = atom->type;
   int nlocal = atom->nlocal;
+  if (varflag != 0) {      // the acceleration of this step (fix_gravity.cpp:248-258)
+    if (mstyle) magnitude = input->variable->compute_equal(mvar);
+    if (xstyle) xdir = input->variable->compute_equal(xvar);
+    if (ystyle) ydir = input->variable->compute_equal(yvar);
+    if (zstyle) zdir = input->variable->compute_equal(zvar);
+    set_acceleration();
+  }
   egrav = 0.0;
   for (int i = 0; i < nlocal; i++)
     if (mask[i] & groupbit) {

@@ -63,7 +63,10 @@ def test_variable_formulas_engine_compiler_vs_oracle():
     rng = np.random.default_rng(5)
     formulas = ["mass*-9.81", "mass*0.5*((y<0.2)-(y>0.2))", "2^3^2", "-2^2", "1-2-3", "2*3%4", "1.5e-3*x+y/z", "!(x>y)||(vx<=vy&&fz!=0)",
                 "sqrt(abs(fx))+exp(-x)*ln(mass)+log(100)", "atan2(y,x)+sin(PI/2)+round(-2.5)+ceil(x)+floor(y)", "(type==2)*id+step*dt",
-                "((3.0-1)*y/1.0-((3.0-1)*0.1-1.0)/1.0)*(y-0.1<1.0)+3.0*(y-0.1>1.0)", "1.0+sqrt(x)*(x<=0.3)+abs(-0.5)*(x>0.3)", "2--3" if False else "2-(-3)"]
+                "((3.0-1)*y/1.0-((3.0-1)*0.1-1.0)/1.0)*(y-0.1<1.0)+3.0*(y-0.1>1.0)", "1.0+sqrt(x)*(x<=0.3)+abs(-0.5)*(x>0.3)", "2--3" if False else "2-(-3)",
+                # what FixGravityB200 composes for `fix gravity v_gmag vector v_gx 1 0` (fix_b200.cpp): massone * (magnitude * xdir / length)
+                "mass*((-9.81*(step>3)*(1.0+0.01*step))*((0.02*step*dt/1.0e-4)/sqrt((0.02*step*dt/1.0e-4)*(0.02*step*dt/1.0e-4)+(1)*(1))))",
+                "mass*((-9.81*(step>3)*(1.0+0.01*step))*((1)/sqrt((0.02*step*dt/1.0e-4)*(0.02*step*dt/1.0e-4)+(1)*(1))))", "mass*((-9.81)*(0.0))"]
     known = {"2^3^2": 64.0, "-2^2": 4.0, "1-2-3": -4.0, "2*3%4": 2.0, "2-(-3)": 5.0}
     for f in formulas:
         for _ in range(5):

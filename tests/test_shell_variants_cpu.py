@@ -20,7 +20,7 @@ REFUSED = [
     ("neigh_exclude", (r"^neigh_modify.*$", "neigh_modify every 5 delay 0 check no exclude type 1 2"), "neigh_modify exclude is not supported"),
     ("neighbor_nsq", (r"^neighbor\s.*$", "neighbor ${skin} nsq"), "supports neighbor style bin"),
     ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
-    ("variable_gravity", (r"^fix\s+gfix.*$", "variable gmag equal 9.81*(1.0+0.0*step)\nfix gfix water gravity v_gmag vector 0 -1 0"), "constant gravity only"),
+    ("variable_gravity_angle", (r"^fix\s+gfix.*$", "variable ang equal 10.0+0.01*step\nfix gfix water gravity 9.81 chute v_ang"), "supports variables for the magnitude"),
 ]
 
 
@@ -46,6 +46,10 @@ VARIANTS = [
     ("edits_between_runs", [(r"^run\s+\S+.*$", "run 8\nregion cut block 0.5 0.9 0.3 0.6 EDGE EDGE units box\ndelete_atoms region cut\n"
                                                 "displace_atoms water move 0.0 0.002 0.0 units box\nset group water meso_e 0.5\nunfix dtfix\ntimestep 2.0e-5\n"
                                                 "neigh_modify every 3 delay 0 check yes\nfix frz bc setforce 0.0 NULL 0.0\nthermo_style custom step ke c_esph press\nrun 10")], 1e-9),
+    # fix gravity with equal-style variables (magnitude switched on over the first steps, a direction that tilts with time): the formula
+    # FixGravity::post_force evaluates goes to the engine's per-atom evaluator; f_gfix on the thermo line follows the same variables
+    ("variable_gravity", [(r"^fix\s+gfix.*$", "variable gmag equal -9.81*(step>3)*(1.0+0.01*step)\nvariable gx equal 0.02*step*dt/1.0e-4\n"
+                                              "fix gfix water gravity v_gmag vector v_gx 1 0"), (r"^run\s+\S+.*$", "run 20")], 1e-9),
     # fix ave/time over a compute reduce, fix ave/atom of a per-atom compute (END_OF_STEP, read-only, evaluated on their own steps)
     ("fix_ave", [(r"^run\s+\S+.*$", "fix avt all ave/time 2 3 6 c_esph file zz.avt\nfix ava all ave/atom 1 4 4 c_rho_peratom\nrun 12")], 1e-9),
 ]
