@@ -50,6 +50,8 @@ VARIANTS = [
     # FixGravity::post_force evaluates goes to the engine's per-atom evaluator; f_gfix on the thermo line follows the same variables
     ("variable_gravity", [(r"^fix\s+gfix.*$", "variable gmag equal -9.81*(step>3)*(1.0+0.01*step)\nvariable gx equal 0.02*step*dt/1.0e-4\n"
                                               "fix gfix water gravity v_gmag vector v_gx 1 0"), (r"^run\s+\S+.*$", "run 20")], 1e-9),
+    # run N every M "command" with the default pre yes: the command writes per-atom data on the host, every chunk sets up again (uploads)
+    ("run_every_writes", [(r"^run\s+\S+.*$", 'run 12 every 4 "velocity water scale 0.5" "set group water meso_e 0.1"')], 1e-9),
     # fix ave/time over a compute reduce, fix ave/atom of a per-atom compute (END_OF_STEP, read-only, evaluated on their own steps)
     ("fix_ave", [(r"^run\s+\S+.*$", "fix avt all ave/time 2 3 6 c_esph file zz.avt\nfix ava all ave/atom 1 4 4 c_rho_peratom\nrun 12")], 1e-9),
 ]
