@@ -8,6 +8,7 @@
 #include "fix_b200.h"
 #include "pair_hybrid.h"
 #include "neighbor.h"
+#include "neigh_request.h"
 #include "domain.h"
 #include "comm.h"
 #include "atom.h"
@@ -96,6 +97,13 @@ void VerletB200::configure()
   if (neighbor->style != 1) error->all(FLERR, "run_style verlet/b200 supports neighbor style bin");       // enum{NSQ,BIN,MULTI}, neighbor.cpp:50
   if (neighbor->exclude_setting()) error->all(FLERR, "run_style verlet/b200: neigh_modify exclude is not supported (use pair_coeff I J none)");
   if (neighbor->includegroup) error->all(FLERR, "run_style verlet/b200: neigh_modify include is not supported");
+  // the host holds no ghosts and builds no neighbor lists under verlet/b200 (the /b200 pair styles request none): a compute, fix or
+  // command that asked Neighbor for one (compute rdf, coord/atom, ...; Neighbor::init moved the requests to old_requests) would read garbage
+  for (int i = 0; i < neighbor->old_nrequest; i++) {
+    NeighRequest *rq = neighbor->old_requests[i];
+    if (rq->compute || rq->fix || rq->command)
+      error->all(FLERR, "run_style verlet/b200: a compute / fix / command that needs a host neighbor list is not supported");
+  }
   int n = atom->ntypes;
   int multiphase = atom->rmass_flag ? 1 : 0;
   check(b200_domain(h, domain->dimension, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi));

@@ -19,6 +19,8 @@ REFUSED = [
     ("end_of_step_fix_that_writes", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nfix mom water momentum 1 linear 1 1 0"), "has no /b200 variant"),
     ("neigh_exclude", (r"^neigh_modify.*$", "neigh_modify every 5 delay 0 check no exclude type 1 2"), "neigh_modify exclude is not supported"),
     ("neighbor_nsq", (r"^neighbor\s.*$", "neighbor ${skin} nsq"), "supports neighbor style bin"),
+    ("compute_with_neighbor_list", (r"^thermo_style.*$", "compute rd all rdf 20\nfix rdav all ave/time 5 1 5 c_rd file zz.rdf mode vector\nthermo_style custom step ke"),
+     "needs a host neighbor list"),
     ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
     ("variable_gravity_angle", (r"^fix\s+gfix.*$", "variable ang equal 10.0+0.01*step\nfix gfix water gravity 9.81 chute v_ang"), "supports variables for the magnitude"),
 ]
