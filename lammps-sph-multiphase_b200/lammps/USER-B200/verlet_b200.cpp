@@ -38,6 +38,11 @@ struct DomainPeek : public Domain {
 struct AtomPeek : public Atom {
   static double userbinsize_of(const Atom *a) { return a->*(&AtomPeek::userbinsize); }
 };
+// Comm::mode / bordergroup (comm.h:102-103, protected): comm_modify mode multi | group ID
+struct CommPeek : public Comm {
+  static int mode_of(const Comm *c) { return c->*(&CommPeek::mode); }
+  static int bordergroup_of(const Comm *c) { return c->*(&CommPeek::bordergroup); }
+};
 // PairHybrid::nmap / map (pair_hybrid.h:59-60, protected): which sub-styles a type pair is assigned to
 struct HybridPeek : public PairHybrid {
   static bool maps(const PairHybrid *p, int i, int j, int m)
@@ -68,6 +73,8 @@ void VerletB200::init()
   // global pair virial is: a compute that reads them (stress/atom, pe/atom, ...; Integrate::ev_setup collected them) is refused
   if (nelist_atom || nvlist_atom)
     error->all(FLERR, "run_style verlet/b200: per-atom energy / virial tallies (compute pe/atom, stress/atom, ...) are not computed by the engine");
+  if (CommPeek::mode_of(comm) || CommPeek::bordergroup_of(comm))
+    error->all(FLERR, "run_style verlet/b200 supports comm_modify mode single without a border group (one ghost cutoff for all atoms)");
   if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton on");
   if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 supports orthogonal boxes");
   if (!atom->rho_flag || !atom->e_flag) error->all(FLERR, "run_style verlet/b200 requires atom_style meso or meso/multiphase");

@@ -21,6 +21,7 @@ REFUSED = [
     ("neighbor_nsq", (r"^neighbor\s.*$", "neighbor ${skin} nsq"), "supports neighbor style bin"),
     ("compute_with_neighbor_list", (r"^thermo_style.*$", "compute rd all rdf 20\nfix rdav all ave/time 5 1 5 c_rd file zz.rdf mode vector\nthermo_style custom step ke"),
      "needs a host neighbor list"),
+    ("comm_mode_multi", (r"^neigh_modify.*$", "neigh_modify every 5 delay 0 check no\ncomm_modify mode multi"), "comm_modify mode single"),
     ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
     ("variable_gravity_angle", (r"^fix\s+gfix.*$", "variable ang equal 10.0+0.01*step\nfix gfix water gravity 9.81 chute v_ang"), "supports variables for the magnitude"),
 ]
