@@ -224,6 +224,26 @@ void VerletB200::download()
   check(b200_get_atoms(h, nl, &a));
   for (int i = 0; i < nl; i++) atom->tag[i] = tag[i];
   atom->nghost = 0;
+  // An atom beyond a fixed (f) face: the reference drops it at its next reneighboring (CommBrick::exchange keeps what lies inside the
+  // sub-box, comm_brick.cpp:596-650) and thermo then stops with "Lost atoms" (thermo.cpp lost_check); the engine keeps such an atom in
+  // its boundary cell.  The two would part ways silently, so the run stops here with a message instead.
+  {
+    bigint nout = 0;
+    for (int d = 0; d < domain->dimension; d++) {
+      const bool flo = domain->boundary[d][0] == 1, fhi = domain->boundary[d][1] == 1;      // 0 p, 1 f, 2 s, 3 m (domain.h)
+      if (!flo && !fhi) continue;
+      for (int i = 0; i < nl; i++)
+        if ((flo && atom->x[i][d] < domain->boxlo[d]) || (fhi && atom->x[i][d] >= domain->boxhi[d])) nout++;
+    }
+    bigint nall;
+    MPI_Allreduce(&nout, &nall, 1, MPI_LMP_BIGINT, MPI_SUM, world);
+    if (nall) {
+      char msg[256];
+      sprintf(msg, "run_style verlet/b200: " BIGINT_FORMAT " atom coordinate(s) beyond a fixed box face at step " BIGINT_FORMAT
+              " (the reference would lose these atoms at its next reneighboring: Lost atoms)", nall, update->ntimestep);
+      error->all(FLERR, msg);
+    }
+  }
   if (atom->map_style) { atom->map_init(); atom->map_set(); }
   long long c[8];
   b200_get_counters(h, c);
