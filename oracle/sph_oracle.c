@@ -91,6 +91,7 @@ struct osph_sph {
   /* styles */
   int npair; opair pair[MAXPAIR];
   int nfix; ofix fix[MAXFIX];
+  int nold; ofix oldpc[MAXFIX];   /* fix phase_change entries of the registration osph_fix_clear dropped: an identical one keeps its state */
   double dt, ftm2v; long long ntimestep;
   double atime; long long atimestep, laststep;   /* Update::atime / atimestep, FixDtReset::laststep (osph_set_time / osph_get_time) */
   long long nsteps_done, ninserted, maxneighseen;
@@ -264,7 +265,15 @@ int osph_pair_add(osph_sph *s, const osph_pair_desc *d)
   return s->npair++;
 }
 
-int osph_fix_clear(osph_sph *s) { s->nfix = 0; return 0; }
+/* FixPhaseChange keeps next_reneighbor and its RanPark position across `run` commands (fix_phase_change.cpp:116,345); the caller
+ * re-registers the deck at every setup, so an identical fix phase_change takes its state over from the previous registration */
+int osph_fix_clear(osph_sph *s)
+{
+  s->nold = 0;
+  for (int i = 0; i < s->nfix; i++) if (s->fix[i].kind == FIX_PHASE_CHANGE) s->oldpc[s->nold++] = s->fix[i];
+  s->nfix = 0;
+  return 0;
+}
 static ofix *newfix(osph_sph *s, int kind, int groupbit)
 { if (s->nfix == MAXFIX) return NULL; ofix *f = &s->fix[s->nfix++]; memset(f, 0, sizeof *f); f->kind = kind; f->groupbit = groupbit; return f; }
 int osph_fix_meso(osph_sph *s, int groupbit) { return newfix(s, FIX_MESO, groupbit) ? 0 : fail("too many fixes"); }
@@ -325,6 +334,17 @@ int osph_fix_phase_change(osph_sph *s, const osph_phase_change_desc *d)
   if (d->seed <= 0) return fail("Illegal value for seed"); /* fix_phase_change.cpp:70 */
   ofix *f = newfix(s, FIX_PHASE_CHANGE, d->groupbit); if (!f) return fail("too many fixes");
   f->pc = *d; f->next_reneighbor = d->first_step; f->seed = d->seed;
+  for (int k = 0; k < s->nold; k++) {
+    const osph_phase_change_desc *o = &s->oldpc[k].pc;
+    if (s->oldpc[k].groupbit == d->groupbit && o->groupbit == d->groupbit && o->Tc == d->Tc && o->Tt == d->Tt && o->Hwv == d->Hwv && o->dr == d->dr && o->to_mass == d->to_mass &&
+        o->cutoff == d->cutoff && o->from_type == d->from_type && o->to_type == d->to_type && o->nfreq == d->nfreq && o->seed == d->seed &&
+        o->energy_chance_flag == d->energy_chance_flag && o->change_chance == d->change_chance && o->phase_change_rate == d->phase_change_rate &&
+        o->maxattempt == d->maxattempt && o->first_step == d->first_step) {
+      f->next_reneighbor = s->oldpc[k].next_reneighbor; f->seed = s->oldpc[k].seed;
+      s->oldpc[k] = s->oldpc[--s->nold];
+      break;
+    }
+  }
   return 0;
 }
 

@@ -82,3 +82,24 @@ def test_deck_idioms_match_the_reference(name, edits, tol, tmp_path):
         b = shipped.numeric_rows(os.path.join(out["b200"][0], f))
         assert len(a) > 0, f
         shipped.compare_rows(a, b, tol, name + " " + f)
+
+
+def test_phase_change_keeps_its_state_across_runs(tmp_path):
+    """bubble_on_wall.lmp with its long `run ... pre no every` replaced by three plain runs: every `run` sets up again and re-registers
+    the deck, fix phase_change must go on with its next step and its RanPark stream (fix_phase_change.cpp:116,345) -- atom counts,
+    the deck's own rg.dat (fix print 1) and the final dump against lmp_serial"""
+    case = Shipped("bubble_on_wall_three_runs", "bubble_on_wall", "bubble.lmp", var=["-var", "dname", "data"], cap=10 ** 9, files=["data/rg.dat"],
+                   subs=[(r"^run\s+10000000 pre no\s+post no every 1000 &\n.*&\n.*$", "run 15\nrun 15\nrun 15")])
+    case.cap = 15
+    out = {}
+    for who, exe, pre in (("ref", shipped.REF, None), ("b200", shipped.B200, shipped.build_shim())):
+        wd = str(tmp_path / who)
+        p = shipped.run_one(case, exe, wd, pre)
+        assert p.returncode == 0 and "ERROR" not in p.stdout, who + ":\n" + p.stdout[-3000:] + p.stderr[-2000:]
+        out[who] = (wd, p.stdout)
+    ta, tb = shipped.thermo_block(out["ref"][1]), shipped.thermo_block(out["b200"][1])
+    natoms = [r[1] for r in ta if r[0] == "atoms"]
+    assert len(natoms) == 4 and natoms[-1] > natoms[0], natoms          # run 0 + three runs; atoms were inserted
+    shipped.compare_rows(ta, tb, 1e-9, "thermo")
+    for f in ("data/rg.dat", "zz.dump"):
+        shipped.compare_rows(shipped.numeric_rows(os.path.join(out["ref"][0], f)), shipped.numeric_rows(os.path.join(out["b200"][0], f)), 1e-9, f)
