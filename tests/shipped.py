@@ -113,7 +113,7 @@ class Shipped:
         return t
 
 
-def run_one(case, exe, workdir, preload=None, suffix=False):
+def run_one(case, exe, workdir, preload=None, suffix=False, timeout=900):
     shutil.copytree(os.path.join(examples_dir(), case.directory), workdir)
     for cmd in case.pre:
         subprocess.check_call(cmd, shell=True, cwd=workdir)
@@ -123,7 +123,7 @@ def run_one(case, exe, workdir, preload=None, suffix=False):
     if preload:
         env["LD_PRELOAD"] = preload
     args = [exe] + (["-sf", "b200"] if (preload or suffix) else []) + ["-in", "zz_deck.lmp", "-log", "zz.log", "-echo", "none"] + case.var
-    p = subprocess.run(args, cwd=workdir, capture_output=True, text=True, timeout=900, env=env)
+    p = subprocess.run(args, cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env)
     return p
 
 

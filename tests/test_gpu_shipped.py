@@ -29,7 +29,7 @@ def test_shipped_deck_on_the_engine(case, tmp_path):
     out = {}
     for who, exe, sfx in (("ref", shipped.REF, False), ("b200", shipped.B200, True)):
         wd = str(tmp_path / who)
-        p = shipped.run_one(case, exe, wd, None, sfx)
+        p = shipped.run_one(case, exe, wd, None, sfx, timeout=150)      # the slowest deck takes ~6 s on the host, ~2 s on the engine
         assert p.returncode == 0 and "ERROR" not in p.stdout, who + ":\n" + p.stdout[-3000:] + p.stderr[-2000:]
         out[who] = (wd, p.stdout)
     assert "B200 engine: b200sph" in out["b200"][1]
