@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, FORCE_MIN_BLOCKS(KINDS)) k_force
     if (NREC >= 4) q3 = ld256(rj + 3);
     const double rhoj = q0.w;
     const double mj = MP ? q3.z : T[0].mass[tj];
-    const double rinv = rsqrt(rsq), r = rsq * rinv;
+    // coincident particles (two atoms created at one position, e.g. where the wall and driver regions of cavity_flow.lmp overlap): r = 0 as
+    // the reference's sqrt gives, not 0 * inf; the single-phase formulas never divide by r (the multiphase ones do, in the reference as well)
+    const double rinv = rsqrt(rsq), r = rsq > 0.0 ? rsq * rinv : 0.0;
 
     if (KINDS & (K_TAIT | K_MORRIS | K_IDEAL)) {
       const PairTab &P = T[I_FLUID];

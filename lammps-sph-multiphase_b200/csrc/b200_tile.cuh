@@ -1031,7 +1031,7 @@ __global__ void __launch_bounds__(TILE_ROWS * SPLIT, 1) k_tile_force(const __gri
               for (int t = 0; t < NK; t++) any |= rsq < S.T[t].cutsq[ij];
               if (!any) continue;
               const double mj = S.T[0].mass[tj];
-              const double rinv = rsqrt(rsq), r = rsq * rinv;
+              const double rinv = rsqrt(rsq), r = rsq > 0.0 ? rsq * rinv : 0.0;      // coincident particles: r = 0 as the reference's sqrt gives (not 0 * inf)
               if (HAS_FLUID) {
                 const PairTab &P = S.T[0];
                 if (rsq < P.cutsq[ij]) {

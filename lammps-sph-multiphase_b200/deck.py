@@ -455,6 +455,14 @@ class Deck:
                         # fails in PairSPH*::init_one (no mixing rule) -> same message either way
                         raise DeckError("All pair coeffs are not set")
                     mapped = [self.styles[k] for k in self.hmap[i][j]]      # empty after `pair_coeff I J none`: cutoff 0 (pair_hybrid.cpp:519-542)
+                    # ... but NOT skipped in the list of a sub-style that owns both I,I and J,J alone (PairHybrid::init_style's "mixing will
+                    # assign this pair" clause, pair_hybrid.cpp:459-462): atoms of such types at the same position (rsq = 0 <= 0) interact
+                    if not mapped and len(self.hmap[i][i]) == 1 and self.hmap[i][i] == self.hmap[j][j]:
+                        s = self.styles[self.hmap[i][i][0]]
+                        if s.setflag[i, j]:
+                            cut = s.init_one(i, j)
+                            s.cutsq[i, j] = s.cutsq[j, i] = cut * cut
+                        s.mapped[i, j] = s.mapped[j, i] = 1
                 else:
                     mapped = [s for s in self.styles if s.setflag[i, j]]
                     if not mapped:

@@ -45,11 +45,17 @@ struct CommPeek : public Comm {
 };
 // PairHybrid::nmap / map (pair_hybrid.h:59-60, protected): which sub-styles a type pair is assigned to
 struct HybridPeek : public PairHybrid {
+  // !ijskip of sub-style m's neighbor request, exactly as PairHybrid::init_style forms it (pair_hybrid.cpp:452-466): the pair is assigned
+  // to m, OR it is assigned to nothing while I,I and J,J both belong to m alone.  The second clause is the reference's "mixing will assign
+  // this pair" case, and it also catches `pair_coeff I J none` between two types of the same sub-style: such a pair is NOT skipped -- it is
+  // kept out of the list only by its zero neighbor cutoff (PairHybrid::init_one returns 0), so two atoms of these types at the SAME
+  // position (rsq = 0 <= 0) do interact, with the sub-style's own coefficients (cavity_flow.lmp creates such twins where walls and driver overlap)
   static bool maps(const PairHybrid *p, int i, int j, int m)
   {
     int **nmap = p->*(&HybridPeek::nmap); int ***map = p->*(&HybridPeek::map);
+    if (i > j) { int s = i; i = j; j = s; }
     for (int k = 0; k < nmap[i][j]; k++) if (map[i][j][k] == m) return true;
-    return false;
+    return nmap[i][j] == 0 && nmap[i][i] == 1 && map[i][i][0] == m && nmap[j][j] == 1 && map[j][j][0] == m;
   }
 };
 }
@@ -147,9 +153,8 @@ void VerletB200::configure()
     b200_pair_desc d; std::vector<std::vector<double> > ds; std::vector<std::vector<int> > is;
     ds.reserve(16); is.reserve(4);
     shell->b200_describe(d, ds, is);
-    // under pair hybrid the type pairs a sub-style computes are the hybrid's assignment, not the sub-style's own setflag
-    // (`pair_coeff * * A ...` followed by `pair_coeff 2 3 none` or `pair_coeff 1 2 B ...` leaves A's setflag set; the reference
-    // keeps such pairs out of A's list through ijskip, pair_hybrid.cpp:560-600 -- cavity_flow.lmp:37-38)
+    // under pair hybrid the type pairs a sub-style computes are those its neighbor request does not skip (HybridPeek::maps), not the
+    // sub-style's own setflag: `pair_coeff * * A ...` followed by `pair_coeff 1 2 B ...` leaves A's setflag set for (1,2)
     std::vector<int> mapped;
     if (hyb) {
       mapped.assign((n + 1) * (n + 1), 0);

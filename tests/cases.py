@@ -534,3 +534,11 @@ velocity driver set 0.001 0.0 0.0 units box""" % (_f(dx), _f(3.2 * dx), _f(3.2 *
 
 
 _add(_cavity_none("cavity2d_none", 60))
+# (The shipped deck also has TWINS: walls and driver are created separately, so where their regions overlap a wall atom and a driver atom
+# sit on one lattice site.  `pair_coeff 2 3 none` gives the pair a zero neighbor cutoff but does not skip it in the sub-style's list
+# (PairHybrid::init_style's mixing clause, pair_hybrid.cpp:459-462), so the twins (rsq = 0 <= 0) do interact -- with the sub-style's
+# cutsq[2][3], which nothing ever initialises for an unassigned pair (PairHybrid::init_one only fills assigned ones; the array comes from
+# malloc), and with cut[3][2] / viscosity[3][2] unset if the list holds the pair the other way round.  A fixture built that way gave NaN
+# in the reference for one atom order and an interaction that lasts "until rsq exceeds the garbage" for the other, so there is none:
+# the shipped deck itself is compared through the shells, where the shell reads the very arrays the reference would
+# (tests/test_shell_shipped_cpu.py, tests/test_gpu_zz_shipped.py).)

@@ -139,19 +139,38 @@ def numeric_rows(path):
     return rows
 
 
-def compare_rows(a, b, tol, what):
-    """same line structure, same words, numbers to `tol` relative to the largest magnitude of their column block"""
+DUMP_VECTORS = [(2, 3, 4), (5, 6, 7), (8, 9, 10)]       # x, v, f of the appended dump: the components of a vector share one scale
+
+
+def compare_rows(a, b, tol, what, vectors=()):
+    """same line structure and the same words; numbers column by column: |a - b| <= tol * (largest |a| of that column over all lines of
+    the same shape), so ids, types, steps and counts must agree exactly and every field is measured against its own scale.
+    `vectors`: tuples of token positions whose columns are the components of one vector field (scaled by its largest component, as
+    tests/harness.py measures per-atom vectors -- a component that is zero by symmetry holds only rounding noise)"""
     assert len(a) == len(b), "%s: %d lines against %d" % (what, len(a), len(b))
-    worst = 0.0
+    groups = {}
     for i, (ra, rb) in enumerate(zip(a, b)):
         assert len(ra) == len(rb), "%s line %d: %r / %r" % (what, i + 1, ra, rb)
-        na = np.array([v for v in ra if isinstance(v, float)])
-        nb = np.array([v for v in rb if isinstance(v, float)])
-        assert [v for v in ra if not isinstance(v, float)] == [v for v in rb if not isinstance(v, float)], "%s line %d: %r / %r" % (what, i + 1, ra, rb)
-        if len(na):
-            scale = max(np.abs(na).max(), 1e-300)
-            worst = max(worst, float(np.abs(na - nb).max() / scale))
-    assert worst <= tol, "%s: %.3g > %.3g" % (what, worst, tol)
+        wa = tuple(v if not isinstance(v, float) else None for v in ra)
+        wb = tuple(v if not isinstance(v, float) else None for v in rb)
+        assert wa == wb, "%s line %d: %r / %r" % (what, i + 1, ra, rb)
+        groups.setdefault(wa, []).append(i)
+    worst = 0.0
+    for shape, rows in groups.items():
+        cols = [c for c, w in enumerate(shape) if w is None]
+        if not cols:
+            continue
+        A = np.array([[a[i][c] for c in cols] for i in rows]); B = np.array([[b[i][c] for c in cols] for i in rows])
+        scale = np.maximum(np.abs(A).max(axis=0), 1e-300)
+        for vec in vectors:
+            idx = [cols.index(c) for c in vec if c in cols]
+            if len(idx) == len(vec):
+                scale[idx] = scale[idx].max()
+        err = np.abs(A - B) / scale
+        k = np.unravel_index(err.argmax(), err.shape)
+        assert err[k] <= tol, "%s line %d column %d: %r against %r (%.3g > %.3g of the column's scale %.3g)" % (
+            what, rows[k[0]] + 1, cols[k[1]] + 1, A[k], B[k], err[k], tol, scale[k[1]])
+        worst = max(worst, float(err.max()))
     return worst
 
 

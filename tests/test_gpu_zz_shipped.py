@@ -6,7 +6,7 @@ box has no /root/reference); the same table of decks, sizes and run caps as the 
 
 Written when the round's GPU budget was spent: the last 6 seconds of it ran three of the 25 decks (poiseuille.lmp verbatim over its
 1800 steps, cavity_flow.lmp, the two-atom taitwater/multiphase deck: all three XPASS, profiles/r02_shipped_decks_on_engine_sample.txt);
-those three are plain tests; the first execution of the other 22 is the driver's own at round end, so they are marked
+two of those are plain tests; the first execution of the others is the driver's own at round end, so they are marked
 xfail(strict=False) -- a deck the engine handles shows as XPASS, one it does not as XFAIL with the assertion text, and neither hides the
 rest of the suite behind `-x`.
 Every deck here passes on CPU with the oracle behind the same shells, and the engine is pinned against the oracle on the same styles by
@@ -24,7 +24,9 @@ pytestmark = [pytest.mark.gpu,
 TOL = 1e-7          # engine vs reference over <= 900 steps (fields ~1e-12 per step; rows are compared relative to their largest number)
 
 
-SEEN_ON_B200 = ("poiseuille", "cavity_flow", "two_atoms_taitwater")      # profiles/r02_shipped_decks_on_engine_sample.txt: plain tests
+# profiles/r02_shipped_decks_on_engine_sample.txt: plain tests.  (cavity_flow.lmp was green in that run too, but the treatment of its
+# coincident wall / driver atoms changed afterwards -- they now interact as in the reference, r = 0 -- so it waits for its next GPU run.)
+SEEN_ON_B200 = ("poiseuille", "two_atoms_taitwater")
 FIRST_RUN = pytest.mark.xfail(strict=False, reason="not yet run on a GPU (the round's budget ran out after three decks); green over the oracle on CPU")
 
 
@@ -42,4 +44,4 @@ def test_shipped_deck_on_the_engine(case, tmp_path):
         a = shipped.numeric_rows(os.path.join(out["ref"][0], f))
         b = shipped.numeric_rows(os.path.join(out["b200"][0], f))
         assert len(a) > 0, f
-        shipped.compare_rows(a, b, TOL, case.name + " " + f)
+        shipped.compare_rows(a, b, TOL, case.name + " " + f, shipped.DUMP_VECTORS if f == "zz.dump" else ())
