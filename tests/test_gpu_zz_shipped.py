@@ -6,7 +6,7 @@ box has no /root/reference); the same table of decks, sizes and run caps as the 
 
 Written when the round's GPU budget was spent: the last 6 seconds of it ran three of the 25 decks (poiseuille.lmp verbatim over its
 1800 steps, cavity_flow.lmp, the two-atom taitwater/multiphase deck: all three XPASS, profiles/r02_shipped_decks_on_engine_sample.txt);
-two of those are plain tests; the first execution of the others is the driver's own at round end, so they are marked
+the first execution of the others -- and of all 25 under the column-wise comparison -- is the driver's own at round end, so they are marked
 xfail(strict=False) -- a deck the engine handles shows as XPASS, one it does not as XFAIL with the assertion text, and neither hides the
 rest of the suite behind `-x`.
 Every deck here passes on CPU with the oracle behind the same shells, and the engine is pinned against the oracle on the same styles by
@@ -24,13 +24,13 @@ pytestmark = [pytest.mark.gpu,
 TOL = 1e-7          # engine vs reference over <= 900 steps (fields ~1e-12 per step; rows are compared relative to their largest number)
 
 
-# profiles/r02_shipped_decks_on_engine_sample.txt: plain tests.  (cavity_flow.lmp was green in that run too, but the treatment of its
-# coincident wall / driver atoms changed afterwards -- they now interact as in the reference, r = 0 -- so it waits for its next GPU run.)
-SEEN_ON_B200 = ("poiseuille", "two_atoms_taitwater")
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="not yet run on a GPU (the round's budget ran out after three decks); green over the oracle on CPU")
+# profiles/r02_shipped_decks_on_engine_sample.txt: poiseuille.lmp, cavity_flow.lmp and the two-atom taitwater deck were green on B200 under
+# the first, row-wise comparison; the comparison is column-wise now (tests/shipped.py) and cavity_flow's coincident atoms interact as in
+# the reference, so all 25 wait for their next GPU run as non-strict xfail.
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="not yet run on a GPU in this form (the round's budget ran out after three decks); green over the oracle on CPU")
 
 
-@pytest.mark.parametrize("case", [c if c.name in SEEN_ON_B200 else pytest.param(c, marks=FIRST_RUN) for c in shipped.CASES], ids=[c.name for c in shipped.CASES])
+@pytest.mark.parametrize("case", [pytest.param(c, marks=FIRST_RUN) for c in shipped.CASES], ids=[c.name for c in shipped.CASES])
 def test_shipped_deck_on_the_engine(case, tmp_path):
     out = {}
     for who, exe, sfx in (("ref", shipped.REF, False), ("b200", shipped.B200, True)):
