@@ -103,3 +103,24 @@ def test_phase_change_keeps_its_state_across_runs(tmp_path):
     shipped.compare_rows(ta, tb, 1e-9, "thermo")
     for f in ("data/rg.dat", "zz.dump"):
         shipped.compare_rows(shipped.numeric_rows(os.path.join(out["ref"][0], f)), shipped.numeric_rows(os.path.join(out["b200"][0], f)), 1e-9, f, shipped.DUMP_VECTORS if f == "zz.dump" else ())
+
+
+@pytest.mark.parametrize("form", ["ENERGY 0.02", "${prob} attempt 3"], ids=["energy_rate", "attempt"])
+def test_phase_change_argument_forms(form, tmp_path):
+    """fix phase_change's other argument forms (fix_phase_change.cpp:57-79,358-390: `ENERGY rate` instead of a probability, `attempt N`)
+    through the shell's own parser, on the shipped bubble_on_wall deck"""
+    case = Shipped("bubble_on_wall_" + form.split()[0], "bubble_on_wall", "bubble.lmp", var=["-var", "dname", "data"], cap=10 ** 9, files=["data/rg.dat"],
+                   subs=[(r"12345 \$\{prob\} region rflow", "12345 " + form + " region rflow"),
+                         (r"^run\s+10000000 pre no\s+post no every 1000 &\n.*&\n.*$", "run 40")])
+    case.cap = 40
+    out = {}
+    for who, exe, pre in (("ref", shipped.REF, None), ("b200", shipped.B200, shipped.build_shim())):
+        wd = str(tmp_path / who)
+        p = shipped.run_one(case, exe, wd, pre)
+        assert p.returncode == 0 and "ERROR" not in p.stdout, who + ":\n" + p.stdout[-3000:] + p.stderr[-2000:]
+        out[who] = (wd, p.stdout)
+    ta, tb = shipped.thermo_block(out["ref"][1]), shipped.thermo_block(out["b200"][1])
+    shipped.compare_rows(ta, tb, 1e-9, "thermo")
+    for f in ("data/rg.dat", "zz.dump"):
+        shipped.compare_rows(shipped.numeric_rows(os.path.join(out["ref"][0], f)), shipped.numeric_rows(os.path.join(out["b200"][0], f)), 1e-9, f,
+                             shipped.DUMP_VECTORS if f == "zz.dump" else ())
