@@ -124,3 +124,28 @@ def test_phase_change_argument_forms(form, tmp_path):
     for f in ("data/rg.dat", "zz.dump"):
         shipped.compare_rows(shipped.numeric_rows(os.path.join(out["ref"][0], f)), shipped.numeric_rows(os.path.join(out["b200"][0], f)), 1e-9, f,
                              shipped.DUMP_VECTORS if f == "zz.dump" else ())
+
+
+HEAT_VARIANTS = [
+    # regions are in lattice units in this deck (no `units box`): block / sphere, region / noregion, constant and variable values
+    ("setmesode_region", "region hot block 20 30 EDGE EDGE EDGE EDGE\nfix sde all setmesode 0.002 region hot"),
+    ("setmeso_sphere_noregion", "region ball sphere 70 5 0 8\nfix sm all setmeso meso_e 1.5 noregion ball"),
+    ("setmeso_equal_variable", "variable ramp equal 1.0+0.001*step\nfix sm all setmeso meso_e v_ramp region left"),
+    ("setmeso_atom_variable_temperature", "variable prof atom 1.0+0.01*x\nfix sm all setmeso meso_t v_prof region right"),
+]
+
+
+@pytest.mark.parametrize("name,lines", HEAT_VARIANTS, ids=[v[0] for v in HEAT_VARIANTS])
+def test_setmeso_forms_on_the_heat_deck(name, lines, tmp_path):
+    """fix setmeso / setmesode argument forms (fix_setmeso.cpp:38-89,180-271, fix_setmesode.cpp:38-78) added to the shipped 2-D heat deck"""
+    case = Shipped(name, "heatconduction", "sph_heat_conduction_2d.lmp", cap=40, subs=[(r"^fix\s+integrate_fix.*$", "fix integrate_fix all meso/stationary\n" + lines)])
+    out = {}
+    for who, exe, pre in (("ref", shipped.REF, None), ("b200", shipped.B200, shipped.build_shim())):
+        wd = str(tmp_path / who)
+        p = shipped.run_one(case, exe, wd, pre)
+        assert p.returncode == 0 and "ERROR" not in p.stdout, who + ":\n" + p.stdout[-3000:] + p.stderr[-2000:]
+        out[who] = (wd, p.stdout)
+    shipped.compare_rows(shipped.thermo_block(out["ref"][1]), shipped.thermo_block(out["b200"][1]), 1e-10, "thermo")
+    a, b = (shipped.numeric_rows(os.path.join(out[w][0], "zz.dump")) for w in ("ref", "b200"))
+    shipped.compare_rows(a, b, 1e-10, "zz.dump", shipped.DUMP_VECTORS)
+    assert len({r[12] for r in a if len(r) == 13}) > 5          # the energies did change
