@@ -23,6 +23,10 @@ REFUSED = [
      "needs a host neighbor list"),
     ("comm_mode_multi", (r"^neigh_modify.*$", "neigh_modify every 5 delay 0 check no\ncomm_modify mode multi"), "comm_modify mode single"),
     ("atom_leaves_a_fixed_face", (r"^run\s+\S+.*$", "group one id 9000\nset group one y 7.9995\nvelocity one set 0.0 100.0 0.0 units box\nthermo 1\nrun 8"), "beyond a fixed box face"),
+    ("region_style", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nregion cyl cylinder z 1.0 1.0 0.5 EDGE EDGE units box\nfix sm water setmeso meso_e 0.1 region cyl"),
+     "supports block and sphere regions"),
+    ("addforce_keywords", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nfix af water addforce 0.0 1.0 0.0 every 2"), "without the every / region / energy keywords"),
+    ("setforce_variable", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nvariable fz equal 0.0\nfix sf bc setforce 0.0 0.0 v_fz"), "constant values"),
     ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
     ("variable_gravity_angle", (r"^fix\s+gfix.*$", "variable ang equal 10.0+0.01*step\nfix gfix water gravity 9.81 chute v_ang"), "supports variables for the magnitude"),
 ]
