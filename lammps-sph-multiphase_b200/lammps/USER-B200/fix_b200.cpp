@@ -4,6 +4,7 @@
 #include "atom.h"
 #include "domain.h"
 #include "region.h"
+#include "region_sphere.h"
 #include "error.h"
 #include "update.h"
 #include "input.h"
@@ -20,6 +21,21 @@ namespace {
 template <typename Tag, typename Tag::type M> struct PrivateMember { friend typename Tag::type b200_get(Tag) { return M; } };
 struct VariableData { typedef char ***Variable::*type; friend type b200_get(VariableData); };
 template struct PrivateMember<VariableData, &Variable::data>;
+// RegSphere keeps centre and radius private (region_sphere.h:37-39).  The bounding box would give them back only up to rounding
+// ((xc + r) - (xc - r) is not 2 r in floating point), and RegSphere::inside tests `r <= radius` exactly: an atom ON the sphere must not flip
+struct SphereXc { typedef double RegSphere::*type; friend type b200_get(SphereXc); };
+struct SphereYc { typedef double RegSphere::*type; friend type b200_get(SphereYc); };
+struct SphereZc { typedef double RegSphere::*type; friend type b200_get(SphereZc); };
+struct SphereR { typedef double RegSphere::*type; friend type b200_get(SphereR); };
+template struct PrivateMember<SphereXc, &RegSphere::xc>;
+template struct PrivateMember<SphereYc, &RegSphere::yc>;
+template struct PrivateMember<SphereZc, &RegSphere::zc>;
+template struct PrivateMember<SphereR, &RegSphere::radius>;
+void sphere_geometry(Region *reg, double *c, double *rad)
+{
+  RegSphere *s = dynamic_cast<RegSphere *>(reg);
+  c[0] = s->*b200_get(SphereXc()); c[1] = s->*b200_get(SphereYc()); c[2] = s->*b200_get(SphereZc()); *rad = s->*b200_get(SphereR());
+}
 
 std::string formula_of(LAMMPS *lmp, const char *name, int depth)
 {
@@ -204,14 +220,13 @@ int FixSetMesoB200::b200_register(b200_sph *h)
     if (ir == -1) error->all(FLERR, "Region ID for fix setmesode does not exist");
     Region *reg = domain->regions[ir];
     if (reg->dynamic_check() || !reg->interior) error->all(FLERR, "fix setmeso/b200 supports static regions with side in");
-    // RegBlock / RegSphere keep their geometry private; their bounding box (region.h extent_*) carries it
+    // RegBlock keeps its bounds private; its bounding box (region.h extent_*) is exactly them.  RegSphere: see sphere_geometry
     if (strcmp(reg->style, "block") == 0) {
       kind = 1;
       r[0] = reg->extent_xlo; r[1] = reg->extent_xhi; r[2] = reg->extent_ylo; r[3] = reg->extent_yhi; r[4] = reg->extent_zlo; r[5] = reg->extent_zhi;
     } else if (strcmp(reg->style, "sphere") == 0) {
       kind = 2;
-      r[0] = 0.5 * (reg->extent_xlo + reg->extent_xhi); r[1] = 0.5 * (reg->extent_ylo + reg->extent_yhi); r[2] = 0.5 * (reg->extent_zlo + reg->extent_zhi);
-      r[3] = 0.5 * (reg->extent_xhi - reg->extent_xlo);
+      sphere_geometry(reg, r, r + 3);
     } else error->all(FLERR, "fix setmeso/b200 supports block and sphere regions");
   }
   if (vname) {      // the variable branch of the reference tests `!match` whatever region / noregion said (fix_setmeso.cpp:247-249)
@@ -227,21 +242,60 @@ FixAddForceB200::FixAddForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, n
 {
   for (int d = 0; d < 3; d++) { vname[d] = NULL; value[d] = 0.0; }
   if (narg < 6) error->all(FLERR, "Illegal fix addforce command");
-  if (narg > 6) error->all(FLERR, "fix addforce/b200 supports `fx fy fz` without the every / region / energy keywords");
   for (int d = 0; d < 3; d++) {
     const char *a = arg[3 + d];
     if (strstr(a, "v_") == a) { vname[d] = new char[strlen(a) - 1]; strcpy(vname[d], a + 2); }
     else value[d] = atof(a);
   }
+  every = 1; idregion = NULL;
+  for (int iarg = 6; iarg < narg; iarg += 2) {      // fix_addforce.cpp:88-118
+    if (iarg + 2 > narg) error->all(FLERR, "Illegal fix addforce command");
+    if (strcmp(arg[iarg], "every") == 0) {
+      every = atoi(arg[iarg + 1]);
+      if (every <= 0) error->all(FLERR, "Illegal fix addforce command");
+    } else if (strcmp(arg[iarg], "region") == 0) {
+      if (domain->find_region(arg[iarg + 1]) == -1) error->all(FLERR, "Region ID for fix addforce does not exist");
+      delete [] idregion;
+      idregion = new char[strlen(arg[iarg + 1]) + 1];
+      strcpy(idregion, arg[iarg + 1]);
+    } else if (strcmp(arg[iarg], "energy") == 0) error->all(FLERR, "fix addforce/b200 does not take the energy keyword");
+    else error->all(FLERR, "Illegal fix addforce command");
+  }
 }
 int FixAddForceB200::setmask() { return POST_FORCE; }
+// `every N` (the force is added on steps that are multiples of N, fix_addforce.cpp:246) and `region ID` (atoms the region matches, :262, :290)
+// become factors of the formula the engine evaluates per atom and step: value * ((step % N) == 0) * (inside), each factor 1.0 or 0.0 as
+// the reference's variable arithmetic gives them, so an atom the reference skips receives + value * 0.  Region tests as RegBlock::inside /
+// RegSphere::inside write them (region_block.cpp, region_sphere.cpp); static block / sphere regions with side in, as for fix setmeso/b200.
 int FixAddForceB200::b200_register(b200_sph *h)
 {
-  char *f[3] = {NULL, NULL, NULL};
-  for (int d = 0; d < 3; d++) if (vname[d]) f[d] = b200_variable_formula(lmp, vname[d]);
-  int rc = b200_fix_addforce(h, groupbit, value, f);
-  for (int d = 0; d < 3; d++) delete [] f[d];
-  return rc;
+  std::string gate;
+  char num[512];
+  if (every > 1) { sprintf(num, "*((step%%%d)==0)", every); gate += num; }
+  if (idregion) {
+    int ir = domain->find_region(idregion);
+    if (ir == -1) error->all(FLERR, "Region ID for fix addforce does not exist");
+    Region *reg = domain->regions[ir];
+    if (reg->dynamic_check() || !reg->interior) error->all(FLERR, "fix addforce/b200 supports static regions with side in");
+    if (strcmp(reg->style, "block") == 0) {
+      sprintf(num, "*((x>=(%.17g))&&(x<=(%.17g))&&(y>=(%.17g))&&(y<=(%.17g))&&(z>=(%.17g))&&(z<=(%.17g)))", reg->extent_xlo, reg->extent_xhi,
+              reg->extent_ylo, reg->extent_yhi, reg->extent_zlo, reg->extent_zhi);
+    } else if (strcmp(reg->style, "sphere") == 0) {
+      double c3[3], rad;
+      sphere_geometry(reg, c3, &rad);
+      const double xc = c3[0], yc = c3[1], zc = c3[2];
+      sprintf(num, "*(sqrt((x-(%.17g))*(x-(%.17g))+(y-(%.17g))*(y-(%.17g))+(z-(%.17g))*(z-(%.17g)))<=(%.17g))", xc, xc, yc, yc, zc, zc, rad);
+    } else error->all(FLERR, "fix addforce/b200 supports block and sphere regions");
+    gate += num;
+  }
+  std::string F[3];
+  const char *f[3] = {NULL, NULL, NULL};
+  double v[3] = {value[0], value[1], value[2]};
+  for (int d = 0; d < 3; d++) {
+    if (vname[d]) { char *s = b200_variable_formula(lmp, vname[d]); F[d] = gate.empty() ? std::string(s) : "(" + std::string(s) + ")" + gate; delete [] s; f[d] = F[d].c_str(); }
+    else if (!gate.empty() && value[d] != 0.0) { sprintf(num, "(%.17g)", value[d]); F[d] = num + gate; f[d] = F[d].c_str(); v[d] = 0.0; }
+  }
+  return b200_fix_addforce(h, groupbit, v, f);
 }
 
 FixSetForceB200::FixSetForceB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
@@ -282,7 +336,7 @@ int FixSetMesodEB200::b200_register(b200_sph *h)
     Region *reg = domain->regions[ir];
     if (reg->dynamic_check() || !reg->interior) error->all(FLERR, "fix setmesode/b200 supports static regions with side in");
     if (strcmp(reg->style, "block") == 0) { kind = 1; r[0] = reg->extent_xlo; r[1] = reg->extent_xhi; r[2] = reg->extent_ylo; r[3] = reg->extent_yhi; r[4] = reg->extent_zlo; r[5] = reg->extent_zhi; }
-    else if (strcmp(reg->style, "sphere") == 0) { kind = 2; r[0] = 0.5 * (reg->extent_xlo + reg->extent_xhi); r[1] = 0.5 * (reg->extent_ylo + reg->extent_yhi); r[2] = 0.5 * (reg->extent_zlo + reg->extent_zhi); r[3] = 0.5 * (reg->extent_xhi - reg->extent_xlo); }
+    else if (strcmp(reg->style, "sphere") == 0) { kind = 2; sphere_geometry(reg, r, r + 3); }
     else error->all(FLERR, "fix setmesode/b200 supports block and sphere regions");
   }
   return b200_fix_setmesode(h, groupbit, value, kind, r);

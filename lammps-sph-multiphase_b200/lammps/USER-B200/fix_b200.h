@@ -89,16 +89,18 @@ class FixSetMesoB200 : public Fix, public B200FixShell {
 };
 
 // FixAddForce (fix_addforce.cpp:40-150, members private): fix ID grp addforce fx fy fz, each a constant or v_name (equal- or atom-style
-// variable, evaluated per atom and step on the device); the keywords every / region / energy are refused
+// variable, evaluated per atom and step on the device), `every N` and `region ID` (static block / sphere) as factors of that formula;
+// the energy keyword is refused
 class FixAddForceB200 : public Fix, public B200FixShell {
  public:
   FixAddForceB200(class LAMMPS *, int, char **);
-  ~FixAddForceB200() { for (int d = 0; d < 3; d++) delete [] vname[d]; }
+  ~FixAddForceB200() { for (int d = 0; d < 3; d++) delete [] vname[d]; delete [] idregion; }
   int setmask();
   void post_force(int) { b200_fix_guard(lmp, "addforce"); }
   int b200_register(b200_sph *h);
  private:
   double value[3]; char *vname[3];
+  int every; char *idregion;
 };
 
 class FixEnforce2DB200 : public FixEnforce2D, public B200FixShell {

@@ -25,7 +25,7 @@ REFUSED = [
     ("atom_leaves_a_fixed_face", (r"^run\s+\S+.*$", "group one id 9000\nset group one y 7.9995\nvelocity one set 0.0 100.0 0.0 units box\nthermo 1\nrun 8"), "beyond a fixed box face"),
     ("region_style", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nregion cyl cylinder z 1.0 1.0 0.5 EDGE EDGE units box\nfix sm water setmeso meso_e 0.1 region cyl"),
      "supports block and sphere regions"),
-    ("addforce_keywords", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nfix af water addforce 0.0 1.0 0.0 every 2"), "without the every / region / energy keywords"),
+    ("addforce_energy_keyword", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nvariable en atom 0.0\nfix af water addforce 0.0 1.0 0.0 energy v_en"), "does not take the energy keyword"),
     ("setforce_variable", (r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nvariable fz equal 0.0\nfix sf bc setforce 0.0 0.0 v_fz"), "constant values"),
     ("newton_off", (r"^newton\s+on", "newton off"), "requires newton on"),
     ("variable_gravity_angle", (r"^fix\s+gfix.*$", "variable ang equal 10.0+0.01*step\nfix gfix water gravity 9.81 chute v_ang"), "supports variables for the magnitude"),
@@ -60,6 +60,11 @@ VARIANTS = [
                                               "fix gfix water gravity v_gmag vector v_gx 1 0"), (r"^run\s+\S+.*$", "run 20")], 1e-9),
     # run N every M "command" with the default pre yes: the command writes per-atom data on the host, every chunk sets up again (uploads)
     ("run_every_writes", [(r"^run\s+\S+.*$", 'run 12 every 4 "velocity water scale 0.5" "set group water meso_e 0.1"')], 1e-9),
+    # fix addforce with `every N` and `region ID` (block, sphere), constant and atom-style variable components
+    ("addforce_every_region", [(r"^fix\s+2d_fix.*$", "fix 2d_fix all enforce2d\nregion rb block 0.5 1.5 0.2 1.0 EDGE EDGE units box\nregion rs sphere 1.0 0.5 0.0 0.4 units box\n"
+                                                      "variable push atom mass*2.0*(y>0.3)\nfix a1 water addforce v_push 0.5e-3 0.0 every 3 region rb\n"
+                                                      "fix a2 water addforce 0.0 -1.0e-3 0.0 region rs\nfix a3 water addforce 1.0e-4 0.0 0.0 every 2"),
+                               (r"^run\s+\S+.*$", "run 14")], 1e-9),
     # fix ave/time over a compute reduce, fix ave/atom of a per-atom compute (END_OF_STEP, read-only, evaluated on their own steps)
     ("fix_ave", [(r"^run\s+\S+.*$", "fix avt all ave/time 2 3 6 c_esph file zz.avt\nfix ava all ave/atom 1 4 4 c_rho_peratom\nrun 12")], 1e-9),
 ]
