@@ -66,7 +66,10 @@ def test_variable_formulas_engine_compiler_vs_oracle():
                 "((3.0-1)*y/1.0-((3.0-1)*0.1-1.0)/1.0)*(y-0.1<1.0)+3.0*(y-0.1>1.0)", "1.0+sqrt(x)*(x<=0.3)+abs(-0.5)*(x>0.3)", "2--3" if False else "2-(-3)",
                 # what FixGravityB200 composes for `fix gravity v_gmag vector v_gx 1 0` (fix_b200.cpp): massone * (magnitude * xdir / length)
                 "mass*((-9.81*(step>3)*(1.0+0.01*step))*((0.02*step*dt/1.0e-4)/sqrt((0.02*step*dt/1.0e-4)*(0.02*step*dt/1.0e-4)+(1)*(1))))",
-                "mass*((-9.81*(step>3)*(1.0+0.01*step))*((1)/sqrt((0.02*step*dt/1.0e-4)*(0.02*step*dt/1.0e-4)+(1)*(1))))", "mass*((-9.81)*(0.0))"]
+                "mass*((-9.81*(step>3)*(1.0+0.01*step))*((1)/sqrt((0.02*step*dt/1.0e-4)*(0.02*step*dt/1.0e-4)+(1)*(1))))", "mass*((-9.81)*(0.0))",
+                # what FixAddForceB200 composes for `every N` / `region ID` (block with EDGE bounds, sphere)
+                "(2.5)*((step%2)==0)*((x>=(-1e+20))&&(x<=(1.5))&&(y>=(0.10000000000000001))&&(y<=(1e+20))&&(z>=(-1e+20))&&(z<=(1e+20)))",
+                "(mass*-9.81)*((step%17)==0)*(sqrt((x-(0.5))*(x-(0.5))+(y-(0.5))*(y-(0.5))+(z-(0))*(z-(0)))<=(0.75))"]
     known = {"2^3^2": 64.0, "-2^2": 4.0, "1-2-3": -4.0, "2*3%4": 2.0, "2-(-3)": 5.0}
     for f in formulas:
         for _ in range(5):
