@@ -11,10 +11,13 @@ computed with); the CUDA engine behind the same ABI is pinned against the oracle
 The product never loads this shim: `libb200sph.so` is resolved through lmp_b200's rpath unless this
 test preloads the stand-in.
 
-The decks are read from /root/reference/examples/USER/sph at test time (this container only; the
-tests skip where the reference is absent).  Two edits are applied to the text, both listed per deck
-below: `run` lengths are capped so the CPU suite stays short, and a full-precision per-atom dump is
-added in front of the first `run` so the final states can be compared digit by digit.
+The decks are read from /root/reference/examples/USER/sph at test time (the CPU tests skip where the
+reference is absent; tests/test_gpu_zz_shipped.py, which runs the same table on the CUDA engine, takes
+them from the archive `make -C oracle ref` packs beside the reference binaries).  Two edits are applied
+to the text, both listed per deck below: `run` lengths are capped so the suites stay short, and a
+full-precision per-atom dump is added in front of the first `run` so the final states can be compared
+digit by digit.  Outputs are compared column by column (compare_rows): words, ids, types, steps and counts
+exactly, every numeric column against its own largest magnitude, vector components against the vector's.
 """
 import os
 import re
