@@ -163,7 +163,10 @@ int  b200_fix_setmeso_var(b200_sph *h, int groupbit, int which, const char *form
 /* fix addforce fx fy fz (src/fix_addforce.cpp:40-150,243-330): per component either the constant value[d] (formula[d] == NULL) or the
  * formula of the equal- / atom-style variable the deck names with v_name (the shipped body-force decks: examples/USER/sph/poiseuille/
  * poiseuille.lmp:57-58, flow_around_cylinder/flow.lmp:84-85, bubble_on_wall/bubble.lmp:187-188).  All three components are evaluated
- * on the forces as they stand before this fix, then added.  No `every`, `region`, `energy` keywords. */
+ * on the forces as they stand before this fix, then added.  The keywords `every N` and `region ID` have no argument of their own: the
+ * caller writes them as factors of the formula, `(value)*((step%N)==0)*(<the region's inside test on x y z>)` (FixAddForceB200 in
+ * lammps/USER-B200/fix_b200.cpp; fix gravity with equal-style variables arrives the same way, `mass*((magnitude)*(direction))`).
+ * `energy` has no counterpart. */
 int  b200_fix_addforce(b200_sph *h, int groupbit, const double value[3], const char *const formula[3]);
 /* host-side check of a formula (what `variable` + `fix ... v_name` would hand the two calls above): compiles it and, when atom != NULL,
  * evaluates the compiled program on the host for one atom {x y z vx vy vz fx fy fz mass}.  -1 + b200_last_error() if the formula uses

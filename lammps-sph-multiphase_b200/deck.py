@@ -386,7 +386,7 @@ class Deck:
                 self.fixes.append(("setmeso/var", bit, (which, formula, kind, list(reg), inside)))
             else:
                 self.fixes.append((style, bit, (which, float(args[1]), kind, list(reg), inside)))
-        elif style == "addforce":      # fix_addforce.cpp:40-110: fx fy fz, each a constant or v_name; no every / region / energy
+        elif style == "addforce":      # fix_addforce.cpp:40-110: fx fy fz, each a constant or v_name (this mirror takes no keywords; the C++ shell composes every / region into the formula)
             if len(args) != 3:
                 raise DeckError("b200 SPH package: fix addforce supports `fx fy fz` without keywords")
             vals = [0.0 if str(a).startswith("v_") else float(a) for a in args]
